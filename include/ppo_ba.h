@@ -1,0 +1,259 @@
+/*
+ * ppo_ba.h — C-ABI of the B200-native local bundle-adjustment engine for the mixed
+ * point / plane / cuboid factor graph of benchun123/point-plane-object-SLAM.
+ *
+ * The reference has no FFI layer: its boundary is the C++ static-method API
+ *   Optimizer::LocalBundleAdjustment      (include/Optimizer.h:45,  src/Optimizer.cc:461-786)
+ *   Optimizer::LocalBACameraPlaneCuboids  (include/Optimizer.h:62,  src/Optimizer.cc:1994-2967)
+ * which build a g2o graph, call SparseOptimizer::optimize() twice and write the map back.
+ * This header is what a replacement Optimizer.cc binds instead of g2o (INTEGRATION.md shows
+ * the stub).  Each entry point cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; the caller owns every input
+ * array (copied at ppo_ba_set_graph); outputs are copied into caller buffers; all functions
+ * return PPO_OK (0) or a negative error code; a handle is single-caller (one CUDA stream).
+ * All solver arithmetic is IEEE double ("f64"), as in g2o; observations/intrinsics arrive as
+ * float32 because that is what KeyFrame stores (KeyFrame.h:184,191-192,209).
+ */
+#ifndef PPO_BA_H
+#define PPO_BA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPO_OK 0
+#define PPO_E_INVALID (-1)  /* bad argument / inconsistent graph                              */
+#define PPO_E_CUDA (-2)     /* CUDA runtime error (ppo_ba_last_error gives the string)        */
+#define PPO_E_NCCL (-3)     /* collective error in the multi-GPU variants                     */
+#define PPO_E_NOGPU (-4)    /* no CUDA device: the engine has no CPU fallback by design       */
+#define PPO_E_EMPTY (-5)    /* no active vertex (g2o: "0 vertices to optimize",
+                               core/sparse_optimizer.cpp:356-359)                             */
+
+/* Edge families, in the order Optimizer.cc adds them. */
+enum ppo_edge_kind {
+  PPO_EDGE_POINT = 0,        /* EdgeSE3ProjectXYZ / EdgeStereoSE3ProjectXYZ  (Optimizer.cc:2357-2424) */
+  PPO_EDGE_PLANE = 1,        /* EdgePlane / EdgeVerticalPlane / EdgeParallelPlane (:2222-2309)        */
+  PPO_EDGE_CUBOID_CAM = 2,   /* EdgeSE3CuboidProj / EdgeSE3CuboidCornerProj  (:2433-2551)             */
+  PPO_EDGE_POINT_CUBOID = 3, /* EdgePointCuboidOnlyObject                    (:2556-2655)             */
+  PPO_EDGE_CUBOID_PLANE = 4, /* EdgeCuboidPlane (constant residual, G2O_Plane3D.h:470-473)            */
+  PPO_EDGE_KINDS = 5
+};
+
+/* ple_kind values */
+#define PPO_PLANE_OBS 0 /* EdgePlane         3-D, Plane3D::ominus     */
+#define PPO_PLANE_VER 1 /* EdgeVerticalPlane 2-D, Plane3D::ominus_ver */
+#define PPO_PLANE_PAR 2 /* EdgeParallelPlane 2-D, Plane3D::ominus_par */
+/* cbe_kind values */
+#define PPO_CUBOID_BBOX 0   /* EdgeSE3CuboidProj       4-D  */
+#define PPO_CUBOID_CORNER 1 /* EdgeSE3CuboidCornerProj 16-D */
+/* cu_flags bits (VertexCuboid, g2o_cuboid.h:281-285) */
+#define PPO_CU_FIXROLLPITCH 1u
+#define PPO_CU_FIXHEIGHT 2u
+/* per-edge flag bits (ppo_ba_set_levels / ppo_ba_get_edge_flags) */
+#define PPO_EF_LEVEL1 1u /* edge->setLevel(1): inactive in optimize() of level 0      */
+#define PPO_EF_ROBUST 2u /* a RobustKernelHuber is attached                            */
+
+/* Solver flavour: which g2o stack the call mirrors. Both run the same dense Cholesky of the
+ * Schur-reduced pose system on the GPU; the value is recorded in the stats for reporting. */
+#define PPO_SOLVER_DENSE_X 0 /* BlockSolverX + LinearSolverDense   (Optimizer.cc:2108-2113) */
+#define PPO_SOLVER_6_3 1     /* BlockSolver_6_3 + LinearSolverEigen (Optimizer.cc:516-522)   */
+
+/* BA-wide configuration: the globals of include/Parameters.h:45-76 and the literals inside
+ * Optimizer.cc, snapshotted per call by the host shim.  ppo_ba_default_params() fills the
+ * reference defaults (Parameters.cc:58-74; Optimizer.cc:2194-2204,2326-2327). */
+typedef struct ppo_ba_params {
+  /* Huber deltas exactly as the reference forms them: (double)(float)sqrt(threshold) */
+  double huber_mono;         /* sqrt(5.991)              Optimizer.cc:2326 */
+  double huber_stereo;       /* sqrt(7.815)              :2327 */
+  double huber_plane;        /* sqrt(plane_chi=500)      :2202-2203 */
+  double huber_vp_plane;     /* sqrt(200)                :2204-2205 */
+  double huber_bbox;         /* sqrt(thHuberBbox2d=80)   :2470 */
+  double huber_corner;       /* sqrt(thHuberConer2d=10)  :2536 */
+  double huber_cuboid_plane; /* sqrt(cuboid_plane_chi=500) :2671 */
+  /* outlier thresholds of the re-levelling pass (Optimizer.cc:2736-2833), used by
+   * ppo_ba_outlier_pass / ppo_ba_local_ba */
+  double chi2_mono;        /* 5.991 */
+  double chi2_stereo;      /* 7.815 */
+  double chi2_plane;       /* plane_chi      */
+  double chi2_vp_plane;    /* 200            */
+  double norm_bbox;        /* thHuberBbox2d: compared with ||error|| (:2774) */
+  double norm_corner;      /* thHuberConer2d (:2783) */
+  /* Levenberg-Marquardt constants (optimization_algorithm_levenberg.cpp:42-55) */
+  double lm_tau;           /* 1e-5 */
+  double lm_good_upper;    /* 2/3  */
+  double lm_good_lower;    /* 1/3  */
+  int32_t lm_max_trials;   /* 10   */
+  int32_t solver;          /* PPO_SOLVER_* */
+  int32_t iters_round1;    /* 5  (Optimizer.cc:2728) */
+  int32_t iters_round2;    /* 10 (Optimizer.cc:2837) */
+  /* point-cuboid edge constants (Optimizer.cc:2647, g2o_cuboid.cc:147) */
+  double ptcu_max_outside_margin_ratio; /* 1.0 */
+  double ptcu_prior_weight;             /* 0.2 */
+} ppo_ba_params;
+
+/* Flat SoA factor graph. Index spaces are typed (KF slot, point, plane, cuboid) instead of
+ * g2o's single colliding id space. KF slots must be sorted by KeyFrame::mnId
+ * (g2o orders the Hessian by vertex id, core/sparse_optimizer.cpp:166-190,482-487); cuboids
+ * follow the KFs in the pose block; planes and points are the marginalised landmark block. */
+typedef struct ppo_ba_graph {
+  /* -- vertices -------------------------------------------------------------------------- */
+  int32_t n_kf;            /* local + fixed KeyFrames                                          */
+  const double *kf_pose;   /* n_kf x 7  Tcw as [qx qy qz qw tx ty tz] (SE3Quat, se3quat.h:46-47) */
+  const uint8_t *kf_fixed; /* n_kf      1 = setFixed(true)  (Optimizer.cc:2126-2128,2141)       */
+  const float *kf_intr;    /* n_kf x 5  fx fy cx cy mbf  (KeyFrame.h:184)                       */
+  int32_t n_pt;
+  const double *pt_xyz;    /* n_pt x 3  (VertexSBAPointXYZ)                                     */
+  const uint8_t *pt_fixed; /* n_pt or NULL: fixPoint (Optimizer.cc:2343-2346)                   */
+  int32_t n_pl;
+  const double *pl_coef;   /* n_pl x 4  Plane3D coeffs (normalised on entry like fromVector)    */
+  int32_t n_cu;
+  const double *cu_state;  /* n_cu x 10 [tx ty tz qx qy qz qw sx sy sz] (cuboid::toVector)      */
+  const uint8_t *cu_flags; /* n_cu      PPO_CU_* bits                                           */
+  /* -- point edges, CSR by point (rows = points) ----------------------------------------- */
+  const int32_t *pt_rowptr; /* n_pt + 1 */
+  int32_t n_pe;
+  const int32_t *pe_kf;      /* n_pe   KF slot                                                  */
+  const float *pe_obs;       /* n_pe x 3  u v u_right; u_right < 0 => monocular edge            */
+  const float *pe_invsigma2; /* n_pe   mvInvLevelSigma2[octave]                                 */
+  /* -- plane edges ------------------------------------------------------------------------ */
+  int32_t n_ple;
+  const int32_t *ple_plane;
+  const int32_t *ple_kf;
+  const uint8_t *ple_kind;   /* PPO_PLANE_*                                                     */
+  const double *ple_meas;    /* n_ple x 4  Converter::toPlane3D(kf->mvPlaneCoefficients[idx])   */
+  const double *ple_info;    /* n_ple x 3  diagonal of the information matrix (3rd unused for 2-D) */
+  /* -- camera-cuboid edges ---------------------------------------------------------------- */
+  int32_t n_cbe;
+  const int32_t *cbe_kf;
+  const int32_t *cbe_cuboid;
+  const uint8_t *cbe_kind;   /* PPO_CUBOID_*                                                    */
+  const double *cbe_meas;    /* n_cbe x 16 (bbox uses the first 4: cx cy w h)                   */
+  const double *cbe_info;    /* n_cbe   (weight*meas_quality)^2, scalar times identity          */
+  /* -- point-cuboid unary edges ----------------------------------------------------------- */
+  int32_t n_pce;
+  const int32_t *pce_cuboid;
+  const int32_t *pce_rowptr; /* n_pce + 1 into pce_pts                                          */
+  const double *pce_pts;     /* x 3  constant world points captured at graph build              */
+  /* -- cuboid-plane edges (constant residual) --------------------------------------------- */
+  int32_t n_cpe;
+  const int32_t *cpe_cuboid;
+  const int32_t *cpe_plane;
+  const double *cpe_meas;    /* n_cpe x 3 */
+  const double *cpe_info;    /* n_cpe x 3 diagonal */
+} ppo_ba_graph;
+
+/* Mutable state returned by ppo_ba_get_state (same layouts as the graph's vertex arrays). */
+typedef struct ppo_ba_state {
+  double *kf_pose;  /* n_kf x 7  */
+  double *pt_xyz;   /* n_pt x 3  */
+  double *pl_coef;  /* n_pl x 4  */
+  double *cu_state; /* n_cu x 10 */
+} ppo_ba_state;
+
+#define PPO_TRACE_MAX 64
+/* One record per outer LM iteration (OptimizationAlgorithmLevenberg::solve). */
+typedef struct ppo_ba_iter {
+  double chi2_before; /* currentChi at entry                        */
+  double chi2_after;  /* currentChi after the accepted trial (or unchanged) */
+  double lambda;      /* _currentLambda after the iteration          */
+  double rho;         /* last rho                                    */
+  int32_t trials;     /* qmax                                        */
+  int32_t accepted;   /* 1 if the last trial was accepted            */
+} ppo_ba_iter;
+
+typedef struct ppo_ba_stats {
+  int32_t iterations;       /* outer iterations executed (return of optimize())             */
+  int32_t terminated;       /* 1: LM returned Terminate; 2: stop flag seen                  */
+  int32_t n_pose_dim;       /* scalar size of the reduced system                             */
+  int32_t n_landmarks;      /* active marginalised landmarks                                 */
+  int32_t n_active_edges;
+  int32_t total_trials;
+  double chi2_initial, chi2_final;
+  double ms_total;          /* device time of the call, CUDA events                          */
+  double ms_linearize, ms_schur, ms_solve, ms_update; /* filled when profiling is enabled     */
+  ppo_ba_iter trace[PPO_TRACE_MAX];
+} ppo_ba_stats;
+
+/* Result of the fused whole-call schedule. */
+typedef struct ppo_ba_result {
+  ppo_ba_stats round1, round2;
+  int32_t n_outlier_point_edges; /* edges levelled out between the rounds                    */
+  int32_t n_outlier_plane_edges;
+  int32_t n_outlier_cuboid_edges;
+  int32_t skipped;               /* 1: stop flag was set on entry -> nothing done (:2723-2725) */
+} ppo_ba_result;
+
+typedef struct ppo_ba_handle ppo_ba_handle;
+
+/* Reference defaults. */
+void ppo_ba_default_params(ppo_ba_params *p);
+
+/* Replaces the construction of SparseOptimizer + BlockSolver + LinearSolver + Levenberg
+ * (Optimizer.cc:2108-2116 / :516-522). device = CUDA ordinal. */
+int ppo_ba_create(const ppo_ba_params *params, int device, ppo_ba_handle **out);
+void ppo_ba_destroy(ppo_ba_handle *h);
+const char *ppo_ba_last_error(const ppo_ba_handle *h);
+
+/* Replaces every optimizer.addVertex / addEdge of Optimizer.cc:2120-2714 (and :526-650).
+ * Copies the graph to the device; all edges start at level 0 with their Huber kernel on
+ * (point, plane, cuboid-cam, cuboid-plane) or off (point-cuboid), as the reference builds them. */
+int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *g);
+
+/* One SparseOptimizer::initializeOptimization(0) + optimize(iters)
+ * (core/sparse_optimizer.cpp:199-267,354-420): rebuilds the index mapping from the current
+ * edge levels, re-initialises lambda, runs <= iters LM iterations.  stop_flag (may be NULL)
+ * is polled where g2o polls forceStopFlag (sparse_optimizer.cpp:376, levenberg.cpp:149). */
+int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *stop_flag,
+                    ppo_ba_stats *stats);
+
+/* e->chi2() of every edge of a kind as g2o holds it after the last computeActiveErrors
+ * (stale for level-1 edges and after a rejected last trial), and
+ * e->isDepthPositive() from the current estimates (point edges; plane edges: distance()>0).
+ * err_norm (may be NULL) receives ||e->error()|| (used for cuboid edges, Optimizer.cc:2774). */
+int ppo_ba_edge_chi2(ppo_ba_handle *h, int kind, double *chi2, unsigned char *depth_positive,
+                     double *err_norm);
+
+/* e->setLevel(level) / e->setRobustKernel(0) for all edges of a kind.  flags[i] = PPO_EF_* bits. */
+int ppo_ba_set_edge_flags(ppo_ba_handle *h, int kind, const unsigned char *flags);
+int ppo_ba_get_edge_flags(ppo_ba_handle *h, int kind, unsigned char *flags);
+int ppo_ba_edge_count(const ppo_ba_handle *h, int kind);
+
+/* The outlier pass of Optimizer.cc:2736-2833 executed on the device (no per-edge D2H). */
+int ppo_ba_outlier_pass(ppo_ba_handle *h, int32_t n_out[3]);
+
+/* Whole call: [stop?] optimize(iters_round1) -> [stop?] outlier pass -> optimize(iters_round2)
+ * = stages C-E of Optimizer.cc:2727-2837 (or :668-715 for the points-only graph). */
+int ppo_ba_local_ba(ppo_ba_handle *h, const volatile unsigned char *stop_flag, ppo_ba_result *res);
+
+/* Reads the vertex estimates back (stage G inputs, Optimizer.cc:2913-2966). NULL members skipped. */
+int ppo_ba_get_state(ppo_ba_handle *h, ppo_ba_state *out);
+
+/* Restores the estimates given at ppo_ba_set_graph and the initial edge flags (benchmark reuse). */
+int ppo_ba_reset(ppo_ba_handle *h);
+
+/* -- instrumentation -------------------------------------------------------------------- */
+/* Device timing of individual phases of the last linearisation (CUDA events on the handle's
+ * stream).  enable != 0 adds per-phase events to ppo_ba_optimize. */
+int ppo_ba_set_profiling(ppo_ba_handle *h, int enable);
+/* Number of kernel launches issued by this handle since creation. */
+long long ppo_ba_launch_count(const ppo_ba_handle *h);
+/* Runs ONLY the point-edge Jacobian/assembly kernel `reps` times on the current state and
+ * returns its mean device time in ms (CUDA events on the handle's stream) and the algorithmic
+ * bytes one launch moves.  Used by bench.py for the roofline object. */
+int ppo_ba_time_assembly(ppo_ba_handle *h, int reps, double *ms_mean, double *algo_bytes);
+
+/* -- multi-GPU: one window, landmarks sharded over ranks ------------------------ */
+/* Each rank builds a handle with the SAME poses/cuboids/plane/cuboid edges and ITS OWN
+ * contiguous slice of points.  The reduced system [Hschur | bschur | chi2 | scale] is summed
+ * over ranks with ncclAllReduce (f64) on the handle's stream; every rank then factorises the
+ * identical system.  nccl_comm is an ncclComm_t passed as void*; rank 0 alone accumulates the
+ * non-point edges. */
+int ppo_ba_set_shard(ppo_ba_handle *h, void *nccl_comm, int rank, int world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPO_BA_H */

@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def ppo():
+    from ppo_pkg import ppo as _p
+    return _p
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle_lib
+    oracle_lib.lib()
+    return oracle_lib

@@ -1,0 +1,402 @@
+"""Known-answer tests pinning the CPU oracle (oracle/) — the reference ships no tests or golden
+vectors for this path, so the restatement is pinned by (1) closed-form
+answers written from the cited reference lines, (2) an independent numpy transliteration
+(tests/np_ref.py), (3) analytic-vs-numeric Jacobian agreement, (4) a dense numpy re-derivation of
+the whole normal-equation / Schur / LM-step algebra on a tiny mixed graph."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import np_ref as R
+
+
+def _d(n):
+    return (C.c_double * n)()
+
+
+def _arr(x, ct=C.c_double):
+    x = np.asarray(x, dtype=np.float64 if ct is C.c_double else np.float32).ravel()
+    return (ct * len(x))(*x)
+
+
+@pytest.fixture(scope="module")
+def L(oracle_mod):
+    return oracle_mod.lib()
+
+
+def se3_exp(L, u):
+    o = _d(7)
+    L.ppo_oracle_se3_exp(_arr(u), o)
+    return np.array(o)
+
+
+def test_exp_identity_and_small_angle_branch(L):
+    # se3quat.h:274-308
+    assert np.allclose(se3_exp(L, [0] * 6), [0, 0, 0, 1, 0, 0, 0], atol=0)
+    for th in (0.999e-5, 1.001e-5, 0.3, 2.5):
+        u = np.r_[th * np.array([0.6, -0.48, 0.64]), 0.1, -0.2, 0.3]
+        p = se3_exp(L, u)
+        Rn, tn = R.se3_exp(u)
+        assert np.allclose(R.quat_to_R(p[:4]), Rn, atol=2e-10)  # I+W+W^2 is orthonormal to O(theta^2)=1e-10
+        assert np.allclose(p[4:], tn, atol=1e-12)
+        assert p[3] >= 0 and abs(np.linalg.norm(p[:4]) - 1) < 1e-15
+
+
+def test_se3_from_float_rotation_branches(L):
+    # Converter.cc:37-47 + Eigen Quaterniond(Matrix3d): trace>0 and the three largest-diagonal branches
+    rng = np.random.default_rng(1)
+    for axis, ang in [([1, 0, 0], 0.3), ([1, 0, 0], 3.0), ([0, 1, 0], 3.0), ([0, 0, 1], 3.1), ([0.5, 0.5, 0.7071], 2.9)]:
+        a = np.array(axis) / np.linalg.norm(axis)
+        Rm = R.axis_angle_R(a, ang).astype(np.float32).astype(np.float64)
+        t = rng.normal(size=3)
+        o = _d(7)
+        L.ppo_oracle_se3_from_Rt(_arr(Rm), _arr(t), o)
+        p = np.array(o)
+        assert p[3] >= 0
+        assert np.allclose(R.quat_to_R(p[:4]), Rm, atol=3e-7)  # float32-rounded input
+        assert np.allclose(p[4:], t)
+
+
+def test_se3_oplus_and_map(L):
+    rng = np.random.default_rng(2)
+    for _ in range(5):
+        pose = se3_exp(L, rng.normal(size=6))
+        u = rng.normal(size=6) * 0.1
+        o = _d(7)
+        L.ppo_oracle_se3_oplus(_arr(pose), _arr(u), o)
+        Rd, td = R.se3_exp(u)
+        R0, t0 = R.pose_to_Rt(pose)
+        assert np.allclose(R.quat_to_R(np.array(o)[:4]), Rd @ R0, atol=1e-13)
+        assert np.allclose(np.array(o)[4:], Rd @ t0 + td, atol=1e-13)
+        x = rng.normal(size=3)
+        m = _d(3)
+        L.ppo_oracle_se3_map(_arr(pose), _arr(x), m)
+        assert np.allclose(np.array(m), R0 @ x + t0, atol=1e-14)
+
+
+def test_plane_normalize_sign_rule(L):
+    # G2O_Plane3D.h:120-125: unit normal, coeffs(3) >= 0
+    o = _d(4)
+    L.ppo_oracle_plane_normalize(_arr([0, 0, 2, -4]), o)
+    assert np.allclose(np.array(o), [0, 0, -1, 2])
+    L.ppo_oracle_plane_normalize(_arr([3, 0, 4, 10]), o)
+    assert np.allclose(np.array(o), [0.6, 0, 0.8, 2])
+
+
+def test_plane_ominus_oplus(L):
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        a = np.r_[rng.normal(size=3), rng.uniform(0.5, 4)]
+        o3 = _d(3)
+        L.ppo_oracle_plane_ominus(0, _arr(a), _arr(a), o3)
+        assert np.allclose(np.array(o3), 0, atol=1e-15)  # ominus(self) = 0
+        v = rng.normal(size=3) * 0.05
+        o4 = _d(4)
+        L.ppo_oracle_plane_oplus(_arr(a), _arr(v), o4)
+        assert np.allclose(np.array(o4), R.plane_oplus(a, v), atol=1e-14)
+        L.ppo_oracle_plane_ominus(0, _arr(a), o4, o3)  # a.ominus(a (+) v) = (az, el, -dd)
+        assert np.allclose(np.array(o3), [v[0], v[1], -v[2]], atol=1e-12)
+        b = np.r_[rng.normal(size=3), rng.uniform(0.5, 4)]
+        for kind, f in ((0, R.plane_ominus), (1, R.plane_ominus_ver), (2, R.plane_ominus_par)):
+            L.ppo_oracle_plane_ominus(kind, _arr(a), _arr(b), o3)
+            ref = f(a, b)
+            assert np.allclose(np.array(o3)[:len(ref)], ref, atol=1e-13)
+
+
+def test_plane_ver_par_zero_cases(L):
+    o3 = _d(3)
+    L.ppo_oracle_plane_ominus(1, _arr([1, 0, 0, 1]), _arr([0, 1, 0, 2]), o3)  # perpendicular
+    assert np.allclose(np.array(o3)[:2], 0, atol=1e-15)
+    L.ppo_oracle_plane_ominus(2, _arr([0, 0, 1, 1]), _arr([0, 0, 1, 3]), o3)  # parallel
+    assert np.allclose(np.array(o3)[:2], 0, atol=1e-15)
+    L.ppo_oracle_plane_ominus(2, _arr([0.6, 0, 0.8, 1]), _arr([-0.6, 0, -0.8, 3]), o3)  # anti-parallel
+    assert np.allclose(np.array(o3)[:2], 0, atol=1e-15)
+
+
+def test_plane_transform(L):
+    rng = np.random.default_rng(4)
+    for _ in range(10):
+        pose = se3_exp(L, rng.normal(size=6))
+        c = np.r_[rng.normal(size=3), rng.uniform(0.5, 4)]
+        o = _d(4)
+        L.ppo_oracle_plane_transform(_arr(pose), _arr(c), o)
+        assert np.allclose(np.array(o), R.plane_transform(pose, c), atol=1e-14)
+        # a world point on the plane stays on the transformed plane
+        cn = R.plane_normalize(c)
+        X = -cn[3] * cn[:3] + np.cross(cn[:3], rng.normal(size=3))
+        Rm, t = R.pose_to_Rt(pose)
+        assert abs(np.array(o)[:3] @ (Rm @ X + t) + np.array(o)[3]) < 1e-12
+
+
+def test_cuboid_corners_order_and_bbox(L):
+    # g2o_cuboid.h:198-207: corner sign table; unit cube at identity
+    c = [0, 0, 0, 0, 0, 0, 1, 1, 1, 1]
+    o = _d(24)
+    L.ppo_oracle_cuboid_corners(_arr(c), o)
+    assert np.array_equal(np.array(o).reshape(3, 8), R.SGN)
+    # camera looking down +z from z=-5: K = [500 0 320; 0 500 240]
+    pose = [0, 0, 0, 1, 0, 0, 5]
+    intr = _arr([500, 500, 320, 240, 40], C.c_float)
+    corners, bbox = _d(16), _d(4)
+    L.ppo_oracle_cuboid_project(_arr(c), _arr(pose), intr, corners, bbox)
+    # nearest face at depth 4: half-extent 500/4 = 125 px
+    assert np.allclose(np.array(bbox), [320, 240, 250, 250])
+    assert np.allclose(np.array(corners).reshape(8, 2).T, R.cuboid_project(np.array(c, float), np.array(pose, float), [500, 500, 320, 240]))
+
+
+def test_cuboid_oplus_yaw_only_fixheight(L):
+    rng = np.random.default_rng(5)
+    for th in (0.0, 1e-9, 0.2, -1.3):
+        yaw0 = rng.uniform(-3, 3)
+        c = np.r_[rng.normal(size=3), 0, 0, np.sin(yaw0 / 2), np.cos(yaw0 / 2), rng.uniform(0.2, 0.8, 3)]
+        if c[6] < 0:
+            c[3:7] *= -1
+        u = np.r_[0.3, -0.2, th, rng.normal(size=3) * 0.1, rng.normal(size=3) * 0.01]  # roll/pitch entries ignored
+        o = _d(10)
+        L.ppo_oracle_cuboid_oplus(_arr(c), 3, _arr(u), o)
+        o = np.array(o)
+        Rn, tn, sn = R.cuboid_oplus_yaw(c, u)
+        assert np.allclose(R.quat_to_R(o[3:7]), Rn, atol=1e-13)
+        assert np.allclose(o[:3], tn, atol=1e-13) and o[1] == c[1]  # height (translation y) kept exactly
+        assert np.allclose(o[7:], sn)
+
+
+def test_point_cuboid_error_known_values(L):
+    # g2o_cuboid.h:237-255, g2o_cuboid.cc:132-160: scale (1, 2, 0.5)
+    c = [0, 0, 0, 0, 0, 0, 1, 1, 2, 0.5]
+    pts = np.array([[0.5, 0.5, 0.1],    # inside -> 0
+                    [1.5, 0.0, 0.0],    # x outside by 0.5 (< 2*s)
+                    [0.0, 5.0, 0.0],    # y beyond 2*s -> capped at s = 2
+                    [0.0, 0.0, -0.75]])  # z outside by 0.25
+    o = _d(3)
+    L.ppo_oracle_cuboid_point_error(_arr(c), _arr(pts), 4, C.c_double(1.0), C.c_double(0.2), o)
+    expect = np.array([0.5 / 4 / 1 + 0.2 * 1, 2.0 / 4 / 2 + 0.2 * 2, 0.25 / 4 / 0.5 + 0.2 * 0.5])
+    assert np.allclose(np.array(o), expect, atol=1e-15)
+    assert np.allclose(np.array(o), R.point_cuboid_error(np.array(c, float), pts))
+
+
+def test_huber_at_threshold(L):
+    # robust_kernel_impl.cpp:76-90
+    d = float(np.float32(np.sqrt(5.991)))
+    rho = _d(3)
+    L.ppo_oracle_huber.argtypes = [C.c_double, C.c_double, C.c_void_p]
+    L.ppo_oracle_huber(d * d, d, rho)
+    assert rho[0] == d * d and rho[1] == 1.0
+    L.ppo_oracle_huber(d * d * (1 + 1e-12), d, rho)
+    assert rho[1] < 1.0 and abs(rho[0] - d * d) < 1e-9
+    L.ppo_oracle_huber(100.0, 2.0, rho)
+    assert np.allclose(list(rho), [2 * 10 * 2 - 4, 0.2, -0.5 * 0.2 / 100])
+
+
+def test_point_edge_residual_float_quirk_and_jacobians(L):
+    rng = np.random.default_rng(6)
+    intr = np.array([517.306408, 516.469215, 318.643040, 255.313989, 40.0], np.float32)
+    delta = 1e-6
+    for stereo in (False, True):
+        for _ in range(5):
+            pose = se3_exp(L, rng.normal(size=6) * 0.3)
+            X = rng.normal(size=3) + [0, 0, 4]
+            Rm, t = R.pose_to_Rt(pose)
+            pm = _d(3)
+            L.ppo_oracle_se3_map(_arr(pose), _arr(X), pm)
+            p = np.array(pm)  # the oracle's own camera-frame point (quaternion rotation), so the float quirk is bit-testable
+            obs = np.array([300.5, 200.25, 290.0 if stereo else -1.0], np.float32)
+            err, Jpt, Jkf = _d(3), _d(9), _d(18)
+            D = L.ppo_oracle_point_edge(_arr(pose), _arr(X), _arr(intr, C.c_float), _arr(obs, C.c_float), err, Jpt, Jkf)
+            assert D == (3 if stereo else 2)
+            e = np.array(err)[:D]
+            if stereo:  # types_six_dof_expmap.cpp:182-189: invz and bf*invz in float
+                invz = np.float32(1.0 / p[2])
+                r0 = p[0] * float(invz) * float(intr[0]) + float(intr[2])
+                r1 = p[1] * float(invz) * float(intr[1]) + float(intr[3])
+                r2 = r0 - float(np.float32(intr[4]) * invz)
+                assert np.array_equal(e, [float(obs[0]) - r0, float(obs[1]) - r1, float(obs[2]) - r2])
+                assert np.allclose(e, R.project(p, intr, obs), atol=5e-4)  # float 1/z costs ~1e-5 px
+            else:
+                assert np.allclose(e, R.project(p, intr, obs), atol=1e-11)
+            # analytic Jacobians vs central differences of the exact (double) projection
+            Jn_pt = np.zeros((D, 3))
+            Jn_kf = np.zeros((D, 6))
+            for d in range(3):
+                dx = np.zeros(3); dx[d] = delta
+                Jn_pt[:, d] = (R.project(Rm @ (X + dx) + t, intr, obs) - R.project(Rm @ (X - dx) + t, intr, obs)) / (2 * delta)
+            for d in range(6):
+                du = np.zeros(6); du[d] = delta
+                Rp, tp = R.se3_exp(du); Rq, tq = R.se3_exp(-du)
+                Jn_kf[:, d] = (R.project(Rp @ p + tp, intr, obs) - R.project(Rq @ p + tq, intr, obs)) / (2 * delta)
+            assert np.allclose(np.array(Jpt)[:3 * D].reshape(D, 3), Jn_pt, rtol=1e-6, atol=1e-4)
+            assert np.allclose(np.array(Jkf)[:6 * D].reshape(D, 6), Jn_kf, rtol=1e-6, atol=1e-4)
+
+
+def test_dense_ldlt(L):
+    rng = np.random.default_rng(7)
+    n = 57
+    M = rng.normal(size=(n, n))
+    Aspd = M @ M.T + n * np.eye(n)
+    rhs = rng.normal(size=n)
+    sol = _d(n)
+    assert L.ppo_oracle_dense_solve(n, _arr(np.triu(Aspd)), _arr(rhs), sol) == 1
+    assert np.allclose(np.array(sol), np.linalg.solve(Aspd, rhs), rtol=1e-10)
+    Aind = Aspd - 3 * n * np.eye(n)  # not positive definite -> isPositive() false (linear_solver_dense.h:108-112)
+    assert L.ppo_oracle_dense_solve(n, _arr(np.triu(Aind)), _arr(rhs), sol) == 0
+
+
+# ----- whole-system algebra re-derived densely in numpy -------------------------------------------
+def _np_system(g, P, A):
+    """Builds the full (un-reduced) Gauss-Newton system of a tiny graph with np_ref residuals and
+    central differences (step 1e-6), ordering [free KFs | cuboids | planes | points]."""
+    a = g.a
+    n_kf, n_pt, n_pl, n_cu = g.c.n_kf, g.c.n_pt, g.c.n_pl, g.c.n_cu
+    free_kf = [i for i in range(n_kf) if not a["kf_fixed"][i]]
+    off = {}
+    o = 0
+    for i in free_kf:
+        off[("kf", i)] = o; o += 6
+    for i in range(n_cu):
+        off[("cu", i)] = o; o += 9
+    n_p = o
+    for i in range(n_pl):
+        off[("pl", i)] = o; o += 3
+    for i in range(n_pt):
+        off[("pt", i)] = o; o += 3
+    N = o
+    H = np.zeros((N, N)); b = np.zeros(N)
+    chi_tot = 0.0
+
+    def kf_oplus(p, u):
+        Rd, td = R.se3_exp(u); R0, t0 = R.pose_to_Rt(p)
+        return Rd @ R0, Rd @ t0 + td
+
+    def add(res_fn, verts, W, delta_h):
+        # verts: list of (key, dim, oplus_fn(u) -> replacement value), res_fn(values dict) -> residual
+        nonlocal chi_tot
+        r0 = res_fn({})
+        chi = float(r0 @ (W * r0))
+        w = 1.0
+        rho0 = chi
+        if delta_h is not None:
+            rho0, w = R.huber(chi, delta_h)
+        chi_tot += rho0
+        Js = []
+        for key, dim, _ in verts:
+            J = np.zeros((len(r0), dim))
+            for d in range(dim):
+                u = np.zeros(dim); u[d] = 1e-6
+                J[:, d] = (res_fn({key: u}) - res_fn({key: -u})) / 2e-6
+            Js.append(J)
+        for (k1, d1, _), J1 in zip(verts, Js):
+            if k1 not in off:
+                continue
+            o1 = off[k1]
+            b[o1:o1 + d1] += -w * J1.T @ (W * r0)
+            for (k2, d2, _), J2 in zip(verts, Js):
+                if k2 not in off:
+                    continue
+                o2 = off[k2]
+                H[o1:o1 + d1, o2:o2 + d2] += w * J1.T @ (W[:, None] * J2)
+
+    rp = a["pt_rowptr"]
+    for p in range(n_pt):
+        for e in range(rp[p], rp[p + 1]):
+            k = int(a["pe_kf"][e]); obs = a["pe_obs"][e]; intr = a["kf_intr"][k]
+            D = 2 if obs[2] < 0 else 3
+
+            def res(pert, k=k, p=p, obs=obs, intr=intr):
+                Rk, tk = kf_oplus(a["kf_pose"][k], pert.get(("kf", k), np.zeros(6)))
+                X = a["pt_xyz"][p] + pert.get(("pt", p), np.zeros(3))
+                return R.project(Rk @ X + tk, intr, obs)
+            W = np.full(D, float(a["pe_invsigma2"][e]))
+            add(res, [(("kf", k), 6, None), (("pt", p), 3, None)], W, P.huber_mono if D == 2 else P.huber_stereo)
+    for e in range(g.c.n_ple):
+        k = int(a["ple_kf"][e]); pl = int(a["ple_plane"][e]); kind = int(a["ple_kind"][e]); meas = a["ple_meas"][e]
+        D = 3 if kind == 0 else 2
+
+        def res(pert, k=k, pl=pl, kind=kind, meas=meas):
+            Rk, tk = kf_oplus(a["kf_pose"][k], pert.get(("kf", k), np.zeros(6)))
+            c = R.plane_oplus(a["pl_coef"][pl], pert[("pl", pl)]) if ("pl", pl) in pert else R.plane_normalize(a["pl_coef"][pl])
+            n2 = Rk @ c[:3]; d2 = c[3] - tk @ n2
+            loc = R.plane_normalize(np.r_[n2, d2] if d2 >= 0 else -np.r_[n2, d2])
+            return (R.plane_ominus, R.plane_ominus_ver, R.plane_ominus_par)[kind](loc, meas)
+        add(res, [(("pl", pl), 3, None), (("kf", k), 6, None)], a["ple_info"][e][:D], P.huber_plane if kind == 0 else P.huber_vp_plane)
+    for e in range(g.c.n_cbe):
+        k = int(a["cbe_kf"][e]); cu = int(a["cbe_cuboid"][e]); kind = int(a["cbe_kind"][e])
+        D = 4 if kind == 0 else 16
+        meas = a["cbe_meas"][e][:D]; intr = a["kf_intr"][k]
+
+        def res(pert, k=k, cu=cu, kind=kind, meas=meas, intr=intr):
+            Rk, tk = kf_oplus(a["kf_pose"][k], pert.get(("kf", k), np.zeros(6)))
+            Rc, tc, sc = R.cuboid_oplus_yaw(a["cu_state"][cu], pert.get(("cu", cu), np.zeros(9)))
+            pc = Rk @ (Rc @ (sc[:, None] * R.SGN) + tc[:, None]) + tk[:, None]
+            uv = np.stack([float(intr[0]) * pc[0] / pc[2] + float(intr[2]), float(intr[1]) * pc[1] / pc[2] + float(intr[3])])
+            if kind == 0:
+                mn, mx = uv.min(axis=1), uv.max(axis=1)
+                return np.r_[(mn + mx) / 2, mx - mn] - meas
+            return uv.T.ravel() - meas
+        add(res, [(("kf", k), 6, None), (("cu", cu), 9, None)], np.full(D, a["cbe_info"][e]), P.huber_bbox if kind == 0 else P.huber_corner)
+    for e in range(g.c.n_pce):
+        cu = int(a["pce_cuboid"][e]); pts = a["pce_pts"][a["pce_rowptr"][e]:a["pce_rowptr"][e + 1]]
+
+        def res(pert, cu=cu, pts=pts):
+            Rc, tc, sc = R.cuboid_oplus_yaw(a["cu_state"][cu], pert.get(("cu", cu), np.zeros(9)))
+            lp = np.abs((pts - tc) @ Rc)
+            er = np.where(lp < sc, 0.0, np.where(lp < 2 * sc, lp - sc, sc))
+            return er.mean(axis=0) / sc + 0.2 * sc
+        add(res, [(("cu", cu), 9, None)], np.ones(3), None)
+    for e in range(g.c.n_cpe):
+        r0 = a["cpe_meas"][e]
+        chi = float(r0 @ (a["cpe_info"][e] * r0))
+        chi_tot += R.huber(chi, P.huber_cuboid_plane)[0]
+    return H, b, n_p, N, chi_tot
+
+
+def test_system_schur_and_lm_step_against_dense_numpy(ppo, oracle_mod):
+    A = ppo.abi
+    cfg = ppo.synth.config(1, n_kf=5, n_fixed=2, n_pt=40, n_pl=3, n_cu=2, corners_2d=1)
+    g = ppo.synth.make_graph(cfg)
+    assert g.c.n_ple > 0 and g.c.n_cbe > 0 and g.c.n_pce > 0 and g.c.n_cpe > 0
+    o = oracle_mod.Oracle()
+    o.set_graph(g)
+    lin = o.debug_linearize()
+    H, b, n_p, N, chi = _np_system(g, o.params, A)
+    assert lin["n_p"] == n_p and lin["n_p"] + 3 * lin["n_l"] == N
+    assert np.isclose(lin["chi2"], chi, rtol=1e-7)  # stereo float quirk only
+    scale = np.abs(H).max()
+    # pose block (upper part as g2o stores it)
+    assert np.allclose(np.triu(lin["Hpp"]), np.triu(H[:n_p, :n_p]), rtol=2e-5, atol=2e-6 * scale)
+    Hll = np.stack([H[n_p + 3 * l:n_p + 3 * l + 3, n_p + 3 * l:n_p + 3 * l + 3].ravel() for l in range(lin["n_l"])])
+    assert np.allclose(lin["Hll"], Hll, rtol=2e-5, atol=2e-6 * scale)
+    assert np.allclose(lin["b"], b, rtol=2e-5, atol=2e-6 * np.abs(b).max())
+    # damped step: the Schur route must equal the dense solve of the full system
+    lam = 1e-5 * np.abs(np.diag(H)).max()
+    sol = o.debug_solve(lam, lin["n_p"], lin["n_l"])
+    assert sol["ok"] == 1
+    x_ref = np.linalg.solve(H + lam * np.eye(N), b)
+    assert np.allclose(sol["x"], x_ref, rtol=1e-4, atol=1e-6 * np.abs(x_ref).max())
+    # Schur complement itself
+    Hpl = H[:n_p, n_p:]
+    Hll_full = H[n_p:, n_p:] + lam * np.eye(N - n_p)
+    S_ref = H[:n_p, :n_p] + lam * np.eye(n_p) - Hpl @ np.linalg.solve(Hll_full, Hpl.T)
+    assert np.allclose(np.triu(sol["Hschur"]), np.triu(S_ref), rtol=1e-4, atol=1e-6 * np.abs(S_ref).max())
+
+
+def test_lm_schedule_converges_and_matches_reference_rules(ppo, oracle_mod):
+    g, truth = ppo.synth.make_graph(ppo.synth.config(0), with_truth=True)
+    o = oracle_mod.Oracle()
+    o.set_graph(g)
+    res = o.local_ba()
+    assert res.round1.iterations == 5 and res.round1.n_pose_dim == 54  # 9 free KFs x 6
+    tr = res.round1.trace_list()
+    assert all(t["accepted"] for t in tr) and tr[-1]["chi2_after"] < 0.2 * tr[0]["chi2_before"]
+    # lambda follows levenberg.cpp:134-141 on accepted steps: x max(1/3, min(1-(2rho-1)^3, 2/3))
+    for a_, b_ in zip(tr[:-1], tr[1:]):
+        f = max(1 / 3, min(1 - (2 * b_["rho"] - 1) ** 3, 2 / 3))
+        assert np.isclose(b_["lam"], a_["lam"] * f, rtol=1e-12)
+    s = o.get_state()
+    assert np.abs(s.kf_pose - truth.kf_pose).max() < 5e-3
+    assert 0.02 < res.n_outlier_point_edges / g.c.n_pe < 0.12  # 3 % gross + chi2 tail
+    # stop flag set on entry: nothing happens (Optimizer.cc:2723-2725)
+    o.reset()
+    stop = np.ones(1, np.uint8)
+    res2 = o.local_ba(stop)
+    assert res2.skipped == 1 and np.allclose(o.get_state().kf_pose, g["kf_pose"], rtol=0, atol=1e-15)
