@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""bench.py — LM iterations/sec (and KF-windows/sec) of the local bundle adjustment on synthetic windows.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl ours|reference]
+
+A "step" is one complete local BA call (optimize(5) -> outlier pass -> optimize(10), the reference
+schedule of Optimizer.cc:2727-2837) on one synthetic window per GPU.  N=1 workload: BASELINE.json
+configs[2] (200 KF / 80k points / 200 planes / 50 cuboids), the window the north_star target
+(>= 50 LM it/s on 1 GPU) is quoted on.  N>1: every rank solves its own window of the same size
+(independent key-frame windows, no data-path collective) -> weak scaling.
+`value`  : device-resident — graph already in HBM, timed with CUDA events on the engine's stream.
+`e2e`    : through the C-ABI with host buffers: ppo_ba_set_graph (H2D) + ppo_ba_local_ba + ppo_ba_get_state (D2H).
+`--impl reference`: the CPU oracle (single thread, the reference's own configuration: g2o OpenMP off).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LM iterations/sec"
+UNIT = "LM it/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(ci):
+    return {0: "config0: 10 KF / 2k points, points-only LocalBundleAdjustment",
+            1: "config1: 50 KF / 20k points / 50 planes / 10 cuboids",
+            2: "config2: 200 KF / 80k points / 200 planes / 50 cuboids",
+            3: "config3 window: 50 KF / 20k points / 50 planes / 10 cuboids",
+            4: "config4: 1000 KF / 400k points / 1k planes / 200 cuboids"}[ci]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def oracle_lm_rate(ppo, g, full_call):
+    """Times the CPU oracle (tests-only code, used here as the reported CPU baseline)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    o = oracle_lib.Oracle()
+    o.set_graph(g)
+    t0 = time.perf_counter()
+    if full_call:
+        r = o.local_ba()
+        iters = r.round1.iterations + r.round2.iterations
+    else:
+        iters = o.optimize(o.params.iters_round1).iterations
+    dt = time.perf_counter() - t0
+    return iters / dt, iters, dt
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU path. It cannot be compiled here (Eigen3 missing),
+    so the oracle port is timed, single-threaded like the reference (G2O_OPENMP off). Rank 0 only."""
+    if rank != 0:
+        return
+    from ppo_pkg import ppo
+    g = ppo.synth.make_graph(ppo.synth.config(args.config))
+    for _ in range(min(args.warmup, 1)):
+        oracle_lm_rate(ppo, g, False)
+    tot_it, tot_t = 0, 0.0
+    for _ in range(max(1, args.steps)):
+        _, it, dt = oracle_lm_rate(ppo, g, False)
+        tot_it += it
+        tot_t += dt
+    v = tot_it / tot_t
+    sample = f"round 1 only (optimize({5}) = {tot_it // max(1, args.steps)} LM iterations) of the same window per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_name(args.config), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import numpy as np
+    import torch
+    from ppo_pkg import ppo
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ci = args.config
+    g = ppo.synth.make_graph(ppo.synth.config(ci, window=rank))  # one independent window per rank
+    params = ppo.default_params()
+    if ci == 0:
+        params.solver = ppo.abi.SOLVER_6_3  # points-only LocalBundleAdjustment stack (Optimizer.cc:516-522)
+    eng = ppo.LocalBA(params, device=local_rank)
+    eng.set_graph(g)
+
+    def step_resident():
+        eng.reset()
+        eng.flush_l2()  # L2 flushed between timed steps (working set of config 2 is ~110 MB < 126 MB L2)
+        r = eng.local_ba()
+        return r.round1.iterations + r.round2.iterations, r
+
+    def step_e2e():
+        eng.set_graph(g)  # host buffers -> HBM inside the timed region
+        r = eng.local_ba()
+        eng.get_state()   # HBM -> host
+        return r.round1.iterations + r.round2.iterations
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = eng.launch_count()
+    eng.mark(0)
+    iters = 0
+    last = None
+    for _ in range(args.steps):
+        n, last = step_resident()
+        iters += n
+    eng.mark(1)
+    ms = eng.elapsed_ms()
+    barrier()
+    launches = eng.launch_count() - l0
+    sampler.stop_flag = True
+    # end-to-end through the C-ABI with host buffers
+    for _ in range(1):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    n_e2e = max(1, min(args.steps, 5))
+    for _ in range(n_e2e):
+        e2e_iters += step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    # roofline of the Jacobian / assembly kernel (cold L2 each launch, CUDA events on the engine's stream)
+    eng.reset()
+    asm_ms, asm_bytes = eng.time_assembly(20)
+    prof = None
+    if rank == 0:
+        eng.reset()
+        eng.set_profiling(True)
+        pr = eng.local_ba()
+        eng.set_profiling(False)
+        prof = {k: getattr(pr.round1, k) + getattr(pr.round2, k) for k in ("ms_linearize", "ms_schur", "ms_solve", "ms_update", "ms_total")}
+
+    vals = torch.tensor([ms, float(iters), e2e_s, float(e2e_iters)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(mx[0]), float(mx[2])
+        iters, e2e_iters = float(sm[1]), float(sm[3])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = asm_bytes / (asm_ms * 1e-3) / 1e9
+        value = iters / (ms * 1e-3)
+        state_bytes = 8 * (7 * g.c.n_kf + 3 * g.c.n_pt + 4 * g.c.n_pl + 10 * g.c.n_cu)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(ci), "windows_per_gpu": 1, "schedule": "optimize(5)+outlier pass+optimize(10)",
+                       "l2": "flushed between timed steps (256 MiB memset)", "lm_iterations_per_step": iters / max(1, args.steps) / world,
+                       "n_pose_dim": last.round1.n_pose_dim, "n_point_edges": g.c.n_pe},
+            "kf_windows_per_sec": world * args.steps / (ms * 1e-3),
+            "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": g.nbytes(), "d2h_bytes_per_step": state_bytes,
+                    "ms_per_step": 1e3 * e2e_s / n_e2e},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "k_point_linearize (point-edge Jacobian/assembly)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "ms": asm_ms, "algo_bytes": asm_bytes,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            "phases_ms_per_call": prof,
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            g0 = g if world == 1 else ppo.synth.make_graph(ppo.synth.config(ci))
+            v, it, dt = oracle_lm_rate(ppo, g0, True)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": f"one full local BA call ({it} LM iterations, {dt:.1f} s) of the same window on 1 host thread "
+                                             f"(the reference runs g2o single-threaded); host has {os.cpu_count()} cores"}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

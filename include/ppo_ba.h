@@ -245,6 +245,23 @@ long long ppo_ba_launch_count(const ppo_ba_handle *h);
  * bytes one launch moves.  Used by bench.py for the roofline object. */
 int ppo_ba_time_assembly(ppo_ba_handle *h, int reps, double *ms_mean, double *algo_bytes);
 
+/* Device-side stopwatch on the handle's stream: mark(0) ... mark(1), elapsed = ms between the two
+ * CUDA events (includes every gap in which the stream idles waiting for the host LM controller). */
+int ppo_ba_mark(ppo_ba_handle *h, int which);
+int ppo_ba_elapsed_ms(ppo_ba_handle *h, double *ms);
+/* Writes a scratch buffer larger than L2 (256 MiB) on the handle's stream: L2 flush between timed steps. */
+int ppo_ba_flush_l2(ppo_ba_handle *h);
+
+/* -- parity / debugging exports (the oracle offers the same two calls) ---------------------- */
+/* One linearisation at the current estimates: Hpp n_p x n_p row-major (upper blocks filled),
+ * b = [pose gradient | landmark gradients of the ACTIVE landmarks, planes first], Hll n_l x 9.
+ * dims = {n_p, n_l}; call with NULL outputs to size the buffers. */
+int ppo_ba_debug_linearize(ppo_ba_handle *h, int32_t dims[2], double *Hpp, double *b, double *Hll,
+                           double *chi2);
+/* After debug_linearize: damped Schur system and its solution for a given lambda. */
+int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, double *bschur,
+                       double *x, int32_t *ok);
+
 /* -- multi-GPU: one window, landmarks sharded over ranks ------------------------ */
 /* Each rank builds a handle with the SAME poses/cuboids/plane/cuboid edges and ITS OWN
  * contiguous slice of points.  The reduced system [Hschur | bschur | chi2 | scale] is summed

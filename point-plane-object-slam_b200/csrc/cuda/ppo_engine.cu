@@ -1,0 +1,1056 @@
+// Host side of the B200 local-BA engine and its C-ABI (include/ppo_ba.h).
+// One handle = one key-frame window resident in HBM + one CUDA stream.  The LM control loop
+// (OptimizationAlgorithmLevenberg::solve, core/optimization_algorithm_levenberg.cpp:61-164) runs on
+// the host and reads back three scalars per damped trial; everything else stays on the device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../../include/ppo_ba.h"
+#include "ppo_dense.h"
+#include "ppo_kernels.cuh"
+
+using namespace ppo;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char buf_[512];                                                                              \
+      snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      h->err = buf_;                                                                               \
+      return PPO_E_CUDA;                                                                           \
+    }                                                                                              \
+  } while (0)
+
+// ---- minimal NCCL binding (dlopen: the torch wheel already maps libnccl.so.2 into the process) -----
+typedef struct ncclComm *ncclComm_t;
+typedef enum { ncclSum_ = 0, ncclMax_ = 2 } ncclRedOp_t_;
+typedef enum { ncclFloat64_ = 8 } ncclDataType_t_;
+struct NcclApi {
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  void load() {
+    if (ok) return;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return;
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    ok = AllReduce != nullptr;
+  }
+};
+static NcclApi g_nccl;
+
+struct ppo_ba_handle {
+  ppo_ba_params P;
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t evm[2] = {nullptr, nullptr};
+  void *d_flush = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  long long launches = 0;
+  bool profiling = false;
+  bool have_graph = false;
+  std::vector<void *> allocs;
+  DevGraph g;
+  DevState sa, sb;  // current / trial (swapped on accept)
+  DevState s0;      // estimates as given at set_graph (for reset)
+  // host copies needed after set_graph
+  int max_np = 0, ld = 0;
+  int n_chunks = 0;
+  int *d_kf_chunk_ptr = nullptr;
+  double *d_chunk_part = nullptr;
+  int *d_lm_small = nullptr, *d_lm_big = nullptr;
+  int n_lm_small = 0, n_lm_big = 0;
+  // cuboid-plane edges (constant residual): host side
+  std::vector<int> cpe_cuboid, cpe_plane;
+  std::vector<double> cpe_chi2, cpe_norm;
+  std::vector<uint8_t> cpe_flags;
+  int *d_cpe_cuboid = nullptr, *d_cpe_plane = nullptr;
+  uint8_t *d_cpe_flags = nullptr;
+  // partial-sum buffers
+  double *d_chi_pt = nullptr, *d_chi_pl = nullptr, *d_chi_cb = nullptr, *d_chi_pc = nullptr, *d_scale_part = nullptr;
+  int nb_lin = 0, nb_res = 0, nb_pl = 0, nb_cb = 0, nb_pc = 0, nb_bs = 0;
+  Scalars *d_scal = nullptr, *h_scal = nullptr;
+  int *d_not_spd = nullptr, *d_nout = nullptr;
+  int *h_dims = nullptr;
+  // current mapping
+  int n_p = 0, n_kf_free = 0, n_l = 0, n_active_edges = 0;
+  // LM state
+  double lambda = -1, ni = 2;
+  int nBad = 0;
+  // sharding (multi-GPU, single window)
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  double *d_red = nullptr;  // 4 doubles for scalar allreduce
+
+  template <typename T>
+  int dalloc(T **p, size_t n) {
+    ppo_ba_handle *h = this;
+    *p = nullptr;
+    if (n == 0) n = 1;
+    void *q = nullptr;
+    CK(cudaMalloc(&q, n * sizeof(T)));
+    allocs.push_back(q);
+    *p = (T *)q;
+    return PPO_OK;
+  }
+  template <typename T>
+  int upload(T **p, const std::vector<T> &v) {
+    ppo_ba_handle *h = this;
+    int rc = dalloc(p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return PPO_OK;
+  }
+  void free_graph() {
+    for (void *p : allocs) cudaFree(p);
+    allocs.clear();
+    have_graph = false;
+  }
+  bool owner() const { return rank == 0; }  // accumulates the non-point ("shared") edges in sharded mode
+};
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+extern "C" {
+
+void ppo_ba_default_params(ppo_ba_params *p) {
+  std::memset(p, 0, sizeof *p);
+  auto hd = [](double th) { return (double)(float)std::sqrt(th); };  // "const float th = sqrt(..)" in Optimizer.cc
+  p->huber_mono = hd(5.991);
+  p->huber_stereo = hd(7.815);
+  p->huber_plane = hd(500.0);
+  p->huber_vp_plane = hd(200.0);
+  p->huber_bbox = hd(80.0);
+  p->huber_corner = hd(10.0);
+  p->huber_cuboid_plane = hd(500.0);
+  p->chi2_mono = 5.991;
+  p->chi2_stereo = 7.815;
+  p->chi2_plane = 500.0;
+  p->chi2_vp_plane = 200.0;
+  p->norm_bbox = 80.0;
+  p->norm_corner = 10.0;
+  p->lm_tau = 1e-5;
+  p->lm_good_upper = 2. / 3.;
+  p->lm_good_lower = 1. / 3.;
+  p->lm_max_trials = 10;
+  p->solver = PPO_SOLVER_DENSE_X;
+  p->iters_round1 = 5;
+  p->iters_round2 = 10;
+  p->ptcu_max_outside_margin_ratio = 1.0;
+  p->ptcu_prior_weight = 0.2;
+}
+
+int ppo_ba_create(const ppo_ba_params *params, int device, ppo_ba_handle **out) {
+  if (!params || !out) return PPO_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return PPO_E_NOGPU;
+  ppo_ba_handle *h = new ppo_ba_handle();
+  h->P = *params;
+  h->device = device;
+  std::memset(&h->g, 0, sizeof h->g);
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return PPO_E_CUDA;
+  }
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  for (auto &e : h->evp) cudaEventCreate(&e);
+  for (auto &e : h->evm) cudaEventCreate(&e);
+  cudaMallocHost((void **)&h->h_scal, sizeof(Scalars));
+  cudaMallocHost((void **)&h->h_dims, 8 * sizeof(int));
+  *out = h;
+  return PPO_OK;
+}
+
+void ppo_ba_destroy(ppo_ba_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->st);
+  h->free_graph();
+  cudaFreeHost(h->h_scal);
+  cudaFreeHost(h->h_dims);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  for (auto &e : h->evp) cudaEventDestroy(e);
+  for (auto &e : h->evm) cudaEventDestroy(e);
+  if (h->d_flush) cudaFree(h->d_flush);
+  cudaStreamDestroy(h->st);
+  delete h;
+}
+
+const char *ppo_ba_last_error(const ppo_ba_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int ppo_ba_edge_count(const ppo_ba_handle *h, int kind) {
+  switch (kind) {
+    case PPO_EDGE_POINT: return h->g.n_pe;
+    case PPO_EDGE_PLANE: return h->g.n_ple;
+    case PPO_EDGE_CUBOID_CAM: return h->g.n_cbe;
+    case PPO_EDGE_POINT_CUBOID: return h->g.n_pce;
+    case PPO_EDGE_CUBOID_PLANE: return h->g.n_cpe;
+  }
+  return -1;
+}
+
+static int alloc_state(ppo_ba_handle *h, DevState *s) {
+  int rc;
+  if ((rc = h->dalloc(&s->kf_pose, 7 * (size_t)h->g.n_kf))) return rc;
+  if ((rc = h->dalloc(&s->kf_Rt, 12 * (size_t)h->g.n_kf))) return rc;
+  if ((rc = h->dalloc(&s->pt, 3 * (size_t)h->g.n_pt))) return rc;
+  if ((rc = h->dalloc(&s->pl, 4 * (size_t)h->g.n_pl))) return rc;
+  if ((rc = h->dalloc(&s->cu, 10 * (size_t)h->g.n_cu))) return rc;
+  return PPO_OK;
+}
+static int copy_state(ppo_ba_handle *h, const DevState &dst, const DevState &src) {
+  const DevGraph &g = h->g;
+  CK(cudaMemcpyAsync(dst.kf_pose, src.kf_pose, 7 * sizeof(double) * g.n_kf, cudaMemcpyDeviceToDevice, h->st));
+  CK(cudaMemcpyAsync(dst.kf_Rt, src.kf_Rt, 12 * sizeof(double) * g.n_kf, cudaMemcpyDeviceToDevice, h->st));
+  CK(cudaMemcpyAsync(dst.pt, src.pt, 3 * sizeof(double) * g.n_pt, cudaMemcpyDeviceToDevice, h->st));
+  CK(cudaMemcpyAsync(dst.pl, src.pl, 4 * sizeof(double) * g.n_pl, cudaMemcpyDeviceToDevice, h->st));
+  CK(cudaMemcpyAsync(dst.cu, src.cu, 10 * sizeof(double) * g.n_cu, cudaMemcpyDeviceToDevice, h->st));
+  return PPO_OK;
+}
+
+static void recompute_cpe(ppo_ba_handle *h, const double *meas, const double *info) {
+  // EdgeCuboidPlane::computeError: _error = _measurement (G2O_Plane3D.h:470-473)
+  for (size_t e = 0; e < h->cpe_chi2.size(); e++) {
+    double c = 0, n = 0;
+    for (int i = 0; i < 3; i++) c += meas[3 * e + i] * (info[3 * e + i] * meas[3 * e + i]), n += meas[3 * e + i] * meas[3 * e + i];
+    h->cpe_chi2[e] = c;
+    h->cpe_norm[e] = std::sqrt(n);
+  }
+}
+static double cpe_chi_const(const ppo_ba_handle *h) {
+  if (!h->owner()) return 0.0;
+  double s = 0;
+  for (size_t e = 0; e < h->cpe_chi2.size(); e++) {
+    if (h->cpe_flags[e] & PPO_EF_LEVEL1) continue;
+    double c = h->cpe_chi2[e];
+    if (h->cpe_flags[e] & PPO_EF_ROBUST) {
+      const double d = h->P.huber_cuboid_plane, dsqr = d * d;
+      if (c > dsqr) c = 2 * std::sqrt(c) * d - dsqr;
+    }
+    s += c;
+  }
+  return s;
+}
+
+int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
+  if (!h || !gi) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->st));
+  h->free_graph();
+  DevGraph &g = h->g;
+  std::memset(&g, 0, sizeof g);
+  if (gi->n_kf <= 0 || gi->n_pt < 0 || gi->n_pl < 0 || gi->n_cu < 0) { h->err = "bad vertex counts"; return PPO_E_INVALID; }
+  g.n_kf = gi->n_kf; g.n_pt = gi->n_pt; g.n_pl = gi->n_pl; g.n_cu = gi->n_cu;
+  g.n_pe = gi->n_pe; g.n_ple = gi->n_ple; g.n_cbe = gi->n_cbe; g.n_pce = gi->n_pce; g.n_cpe = gi->n_cpe;
+  if (g.n_pt > 0 && (!gi->pt_rowptr || gi->pt_rowptr[0] != 0 || gi->pt_rowptr[g.n_pt] != g.n_pe)) { h->err = "pt_rowptr inconsistent with n_pe"; return PPO_E_INVALID; }
+  if (g.n_pt == 0 && g.n_pe != 0) { h->err = "point edges without points"; return PPO_E_INVALID; }
+  for (int e = 0; e < g.n_pe; e++) if (gi->pe_kf[e] < 0 || gi->pe_kf[e] >= g.n_kf) { h->err = "pe_kf out of range"; return PPO_E_INVALID; }
+  for (int p = 0; p < g.n_pt; p++) if (gi->pt_rowptr[p + 1] < gi->pt_rowptr[p]) { h->err = "pt_rowptr not monotone"; return PPO_E_INVALID; }
+  for (int e = 0; e < g.n_ple; e++)
+    if (gi->ple_kf[e] < 0 || gi->ple_kf[e] >= g.n_kf || gi->ple_plane[e] < 0 || gi->ple_plane[e] >= g.n_pl || gi->ple_kind[e] > 2) { h->err = "plane edge out of range"; return PPO_E_INVALID; }
+  for (int e = 0; e < g.n_cbe; e++)
+    if (gi->cbe_kf[e] < 0 || gi->cbe_kf[e] >= g.n_kf || gi->cbe_cuboid[e] < 0 || gi->cbe_cuboid[e] >= g.n_cu || gi->cbe_kind[e] > 1) { h->err = "cuboid edge out of range"; return PPO_E_INVALID; }
+  for (int e = 0; e < g.n_pce; e++)
+    if (gi->pce_cuboid[e] < 0 || gi->pce_cuboid[e] >= g.n_cu || gi->pce_rowptr[e + 1] < gi->pce_rowptr[e]) { h->err = "point-cuboid edge out of range"; return PPO_E_INVALID; }
+  for (int e = 0; e < g.n_cpe; e++)
+    if (gi->cpe_cuboid[e] < 0 || gi->cpe_cuboid[e] >= g.n_cu || gi->cpe_plane[e] < 0 || gi->cpe_plane[e] >= g.n_pl) { h->err = "cuboid-plane edge out of range"; return PPO_E_INVALID; }
+
+  int rc;
+#define UP(dst, vec) if ((rc = h->upload(&(dst), (vec)))) return rc
+  // ---- vertices: constants ------------------------------------------------------------------------
+  std::vector<uint8_t> kf_fixed(gi->kf_fixed, gi->kf_fixed + g.n_kf), pt_fixed(g.n_pt, 0), cu_flags(g.n_cu, 0);
+  if (gi->pt_fixed) pt_fixed.assign(gi->pt_fixed, gi->pt_fixed + g.n_pt);
+  if (g.n_cu) cu_flags.assign(gi->cu_flags, gi->cu_flags + g.n_cu);
+  std::vector<float> kf_intr(gi->kf_intr, gi->kf_intr + 5 * (size_t)g.n_kf);
+  { uint8_t *p; UP(p, kf_fixed); g.kf_fixed = p; UP(p, pt_fixed); g.pt_fixed = p; UP(p, cu_flags); g.cu_flags = p; }
+  { float *p; UP(p, kf_intr); g.kf_intr = p; }
+  // ---- estimates, normalised as the g2o vertex setters do -------------------------------------------
+  std::vector<double> kf_pose(7 * (size_t)g.n_kf), pl(4 * (size_t)g.n_pl), cu(10 * (size_t)g.n_cu);
+  auto norm_q = [](double *q) {  // SE3Quat::normalizeRotation
+    double s = q[3] < 0 ? -1.0 : 1.0;
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (q[3] < 0) for (int i = 0; i < 4; i++) q[i] = -q[i];
+    (void)s;
+    for (int i = 0; i < 4; i++) q[i] /= n;
+  };
+  for (int i = 0; i < g.n_kf; i++) {
+    for (int k = 0; k < 7; k++) kf_pose[7 * (size_t)i + k] = gi->kf_pose[7 * (size_t)i + k];
+    norm_q(&kf_pose[7 * (size_t)i]);
+  }
+  for (int i = 0; i < g.n_pl; i++) {  // Plane3D::fromVector -> normalize
+    double *c = &pl[4 * (size_t)i];
+    for (int k = 0; k < 4; k++) c[k] = gi->pl_coef[4 * (size_t)i + k];
+    double inv = 1. / std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    for (int k = 0; k < 4; k++) c[k] = c[k] * inv;
+    if (c[3] < 0.0) for (int k = 0; k < 4; k++) c[k] = -c[k];
+  }
+  for (int i = 0; i < g.n_cu; i++) {
+    for (int k = 0; k < 10; k++) cu[10 * (size_t)i + k] = gi->cu_state[10 * (size_t)i + k];
+    norm_q(&cu[10 * (size_t)i + 3]);
+  }
+  std::vector<double> pt(gi->pt_xyz, gi->pt_xyz + 3 * (size_t)g.n_pt);
+  if ((rc = alloc_state(h, &h->sa)) || (rc = alloc_state(h, &h->sb)) || (rc = alloc_state(h, &h->s0))) return rc;
+  if (g.n_kf) CK(cudaMemcpyAsync(h->s0.kf_pose, kf_pose.data(), kf_pose.size() * 8, cudaMemcpyHostToDevice, h->st));
+  if (g.n_pt) CK(cudaMemcpyAsync(h->s0.pt, pt.data(), pt.size() * 8, cudaMemcpyHostToDevice, h->st));
+  if (g.n_pl) CK(cudaMemcpyAsync(h->s0.pl, pl.data(), pl.size() * 8, cudaMemcpyHostToDevice, h->st));
+  if (g.n_cu) CK(cudaMemcpyAsync(h->s0.cu, cu.data(), cu.size() * 8, cudaMemcpyHostToDevice, h->st));
+  k_pose_cache<<<cdiv(g.n_kf, 128), 128, 0, h->st>>>(g.n_kf, h->s0.kf_pose, h->s0.kf_Rt);
+  h->launches++;
+  if ((rc = copy_state(h, h->sa, h->s0))) return rc;
+  if ((rc = copy_state(h, h->sb, h->s0))) return rc;
+
+  // ---- point edges --------------------------------------------------------------------------------
+  std::vector<PointEdgeRec> rec(g.n_pe);
+  std::vector<int> pe_pt(g.n_pe);
+  std::vector<int> rowptr(g.n_pt + 1, 0);
+  for (int p = 0; p < g.n_pt; p++) {
+    rowptr[p + 1] = gi->pt_rowptr[p + 1];
+    for (int e = gi->pt_rowptr[p]; e < gi->pt_rowptr[p + 1]; e++) {
+      pe_pt[e] = p;
+      rec[e].kf = gi->pe_kf[e];
+      rec[e].u = gi->pe_obs[3 * (size_t)e];
+      rec[e].v = gi->pe_obs[3 * (size_t)e + 1];
+      rec[e].ur = gi->pe_obs[3 * (size_t)e + 2];
+    }
+  }
+  std::vector<float> is2(gi->pe_invsigma2, gi->pe_invsigma2 + g.n_pe);
+  { int *p; UP(p, rowptr); g.pt_rowptr = p; UP(p, pe_pt); g.pe_pt = p; }
+  { PointEdgeRec *p; UP(p, rec); g.pe_rec = p; }
+  { float *p; UP(p, is2); g.pe_is2 = p; }
+  // work units: consecutive points, <= 32 edges per warp (a point with > 32 edges is its own unit)
+  std::vector<int> unit_pt0;
+  unit_pt0.push_back(0);
+  {
+    int cnt = 0;
+    for (int p = 0; p < g.n_pt; p++) {
+      const int k = rowptr[p + 1] - rowptr[p];
+      if (cnt > 0 && cnt + k > 32) {
+        unit_pt0.push_back(p);
+        cnt = 0;
+      }
+      cnt += k;
+    }
+    if (g.n_pt > 0) unit_pt0.push_back(g.n_pt);
+  }
+  g.n_units = (int)unit_pt0.size() - 1;
+  { int *p; UP(p, unit_pt0); g.unit_pt0 = p; }
+  // edges grouped by key-frame, chunks of <= POSE_THREADS
+  std::vector<int> kf_cnt(g.n_kf + 1, 0), kfe(g.n_pe);
+  for (int e = 0; e < g.n_pe; e++) kf_cnt[rec[e].kf + 1]++;
+  for (int i = 0; i < g.n_kf; i++) kf_cnt[i + 1] += kf_cnt[i];
+  {
+    std::vector<int> pos(kf_cnt.begin(), kf_cnt.end() - 1);
+    for (int e = 0; e < g.n_pe; e++) kfe[pos[rec[e].kf]++] = e;
+  }
+  std::vector<int> chunk_kf, chunk_b, chunk_e, kf_chunk_ptr(g.n_kf + 1, 0);
+  for (int i = 0; i < g.n_kf; i++) {
+    kf_chunk_ptr[i] = (int)chunk_kf.size();
+    if (!kf_fixed[i])
+      for (int b = kf_cnt[i]; b < kf_cnt[i + 1]; b += POSE_THREADS) {
+        chunk_kf.push_back(i);
+        chunk_b.push_back(b);
+        chunk_e.push_back(std::min(b + POSE_THREADS, kf_cnt[i + 1]));
+      }
+  }
+  kf_chunk_ptr[g.n_kf] = (int)chunk_kf.size();
+  g.n_chunks = h->n_chunks = (int)chunk_kf.size();
+  { int *p; UP(p, chunk_kf); g.chunk_kf = p; UP(p, chunk_b); g.chunk_begin = p; UP(p, chunk_e); g.chunk_end = p; UP(p, kfe); g.kfe_edge = p; }
+  UP(h->d_kf_chunk_ptr, kf_chunk_ptr);
+  if ((rc = h->dalloc(&h->d_chunk_part, 27 * (size_t)g.n_chunks))) return rc;
+
+  // ---- plane edges: slots = unique (plane, key-frame) pairs, sorted by (plane, kf) ---------------------
+  std::vector<std::pair<int, int>> pairs(g.n_ple);
+  for (int e = 0; e < g.n_ple; e++) pairs[e] = {gi->ple_plane[e], gi->ple_kf[e]};
+  std::vector<std::pair<int, int>> uniq = pairs;
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  g.n_slots = (int)uniq.size();
+  g.n_ent = g.n_slots + g.n_pe;
+  g.n_lm = g.n_pl + g.n_pt;
+  std::vector<int> ple_slot(g.n_ple), slot_kf(g.n_slots), lm_rowptr(g.n_lm + 1, 0);
+  for (int e = 0; e < g.n_ple; e++) ple_slot[e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), pairs[e]) - uniq.begin());
+  for (int s = 0; s < g.n_slots; s++) {
+    slot_kf[s] = uniq[s].second;
+    lm_rowptr[uniq[s].first + 1]++;
+  }
+  for (int p = 0; p < g.n_pl; p++) lm_rowptr[p + 1] += lm_rowptr[p];
+  for (int p = 0; p < g.n_pt; p++) lm_rowptr[g.n_pl + p + 1] = g.n_slots + rowptr[p + 1];
+  std::vector<int> lm_small, lm_big;
+  for (int L = 0; L < g.n_lm; L++) (lm_rowptr[L + 1] - lm_rowptr[L] > 24 ? lm_big : lm_small).push_back(L);
+  h->n_lm_small = (int)lm_small.size();
+  h->n_lm_big = (int)lm_big.size();
+  UP(h->d_lm_small, lm_small);
+  UP(h->d_lm_big, lm_big);
+  {
+    int *p;
+    std::vector<int> v(gi->ple_plane, gi->ple_plane + g.n_ple); UP(p, v); g.ple_plane = p;
+    v.assign(gi->ple_kf, gi->ple_kf + g.n_ple); UP(p, v); g.ple_kf = p;
+    UP(p, ple_slot); g.ple_slot = p;
+    UP(p, slot_kf); g.slot_kf = p;
+    UP(p, lm_rowptr); g.lm_rowptr = p;
+    uint8_t *q;
+    std::vector<uint8_t> k(gi->ple_kind, gi->ple_kind + g.n_ple); UP(q, k); g.ple_kind = q;
+    // measurements normalised like setMeasurement(Plane3D(v)) -> fromVector
+    std::vector<double> meas(4 * (size_t)g.n_ple);
+    for (int e = 0; e < g.n_ple; e++) {
+      double *c = &meas[4 * (size_t)e];
+      for (int i = 0; i < 4; i++) c[i] = gi->ple_meas[4 * (size_t)e + i];
+      double inv = 1. / std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+      for (int i = 0; i < 4; i++) c[i] = c[i] * inv;
+      if (c[3] < 0.0) for (int i = 0; i < 4; i++) c[i] = -c[i];
+    }
+    double *d;
+    UP(d, meas); g.ple_meas = d;
+    std::vector<double> info(gi->ple_info, gi->ple_info + 3 * (size_t)g.n_ple); UP(d, info); g.ple_info = d;
+  }
+  // ---- camera-cuboid / point-cuboid / cuboid-plane edges ---------------------------------------------
+  {
+    int *p; uint8_t *q; double *d;
+    std::vector<int> v(gi->cbe_kf, gi->cbe_kf + g.n_cbe); UP(p, v); g.cbe_kf = p;
+    v.assign(gi->cbe_cuboid, gi->cbe_cuboid + g.n_cbe); UP(p, v); g.cbe_cuboid = p;
+    std::vector<uint8_t> k(gi->cbe_kind, gi->cbe_kind + g.n_cbe); UP(q, k); g.cbe_kind = q;
+    std::vector<double> m(gi->cbe_meas, gi->cbe_meas + 16 * (size_t)g.n_cbe); UP(d, m); g.cbe_meas = d;
+    m.assign(gi->cbe_info, gi->cbe_info + g.n_cbe); UP(d, m); g.cbe_info = d;
+    v.assign(gi->pce_cuboid, gi->pce_cuboid + g.n_pce); UP(p, v); g.pce_cuboid = p;
+    if (g.n_pce) v.assign(gi->pce_rowptr, gi->pce_rowptr + g.n_pce + 1); else v.assign(1, 0);
+    const int npts = v.back();
+    UP(p, v); g.pce_rowptr = p;
+    if (npts) m.assign(gi->pce_pts, gi->pce_pts + 3 * (size_t)npts); else m.clear();
+    UP(d, m); g.pce_pts = d;
+  }
+  h->cpe_cuboid.assign(gi->cpe_cuboid, gi->cpe_cuboid + g.n_cpe);
+  h->cpe_plane.assign(gi->cpe_plane, gi->cpe_plane + g.n_cpe);
+  h->cpe_chi2.assign(g.n_cpe, 0.0);
+  h->cpe_norm.assign(g.n_cpe, 0.0);
+  h->cpe_flags.assign(g.n_cpe, PPO_EF_ROBUST);
+  if (g.n_cpe) recompute_cpe(h, gi->cpe_meas, gi->cpe_info);
+  UP(h->d_cpe_cuboid, h->cpe_cuboid);
+  UP(h->d_cpe_plane, h->cpe_plane);
+  UP(h->d_cpe_flags, h->cpe_flags);
+
+  // ---- flags, per-edge outputs, scratch -----------------------------------------------------------------
+#define DA(ptr, n) if ((rc = h->dalloc(&(ptr), (n)))) return rc
+  DA(g.pe_flags, (size_t)g.n_pe); DA(g.ple_flags, (size_t)g.n_ple); DA(g.cbe_flags, (size_t)g.n_cbe); DA(g.pce_flags, (size_t)g.n_pce);
+  DA(g.pe_chi2, (size_t)g.n_pe); DA(g.ple_chi2, (size_t)g.n_ple); DA(g.cbe_chi2, (size_t)g.n_cbe); DA(g.cbe_norm, (size_t)g.n_cbe); DA(g.pce_chi2, (size_t)g.n_pce);
+  DA(g.ple_J, 27 * (size_t)g.n_ple); DA(g.cbe_J, 240 * (size_t)g.n_cbe); DA(g.pce_J, 27 * (size_t)g.n_pce);
+  DA(g.kf_act, (size_t)g.n_kf); DA(g.cu_act, (size_t)g.n_cu); DA(g.pl_act, (size_t)g.n_pl); DA(g.pt_act, (size_t)g.n_pt);
+  DA(g.kf_idx, (size_t)g.n_kf); DA(g.cu_off, (size_t)g.n_cu); DA(g.ent_pidx, (size_t)g.n_ent); DA(g.dims, 8);
+  int n_free = 0;
+  for (int i = 0; i < g.n_kf; i++) n_free += !kf_fixed[i];
+  h->max_np = 6 * n_free + 9 * g.n_cu;
+  h->ld = h->max_np + 1;
+  DA(g.Hpp_kf, 36 * (size_t)g.n_kf); DA(g.Hpp_cu, 81 * (size_t)g.n_cu); DA(g.Hpc, 54 * (size_t)g.n_cbe); DA(g.bp, (size_t)h->max_np);
+  DA(g.Hll, 6 * (size_t)g.n_lm); DA(g.bl, 3 * (size_t)g.n_lm); DA(g.Hpl, 18 * (size_t)g.n_ent); DA(g.Dinv, 6 * (size_t)g.n_lm);
+  DA(g.xl, 3 * (size_t)g.n_lm); DA(g.S, (size_t)(h->max_np + 1) * h->ld); DA(g.xp, (size_t)h->max_np);
+  h->nb_lin = cdiv(g.n_units, LIN_WARPS); h->nb_res = cdiv(g.n_pe, RES_THREADS);
+  h->nb_pl = cdiv(g.n_ple, SMALL_THREADS); h->nb_cb = cdiv(g.n_cbe, SMALL_THREADS); h->nb_pc = cdiv(g.n_pce, SMALL_THREADS);
+  h->nb_bs = cdiv(g.n_lm, BS_WARPS);
+  DA(h->d_chi_pt, (size_t)std::max(h->nb_lin, h->nb_res)); DA(h->d_chi_pl, (size_t)h->nb_pl); DA(h->d_chi_cb, (size_t)h->nb_cb); DA(h->d_chi_pc, (size_t)h->nb_pc);
+  DA(h->d_scale_part, (size_t)h->nb_bs);
+  DA(h->d_scal, 1); DA(h->d_not_spd, 1); DA(h->d_nout, 4); DA(h->d_red, 4);
+  CK(cudaMemsetAsync(g.pe_chi2, 0, 8 * (size_t)g.n_pe, h->st));
+  CK(cudaMemsetAsync(g.ple_chi2, 0, 8 * (size_t)g.n_ple, h->st));
+  CK(cudaMemsetAsync(g.cbe_chi2, 0, 8 * (size_t)g.n_cbe, h->st));
+  CK(cudaMemsetAsync(g.cbe_norm, 0, 8 * (size_t)g.n_cbe, h->st));
+  CK(cudaMemsetAsync(g.pce_chi2, 0, 8 * (size_t)g.n_pce, h->st));
+  CK(cudaMemsetAsync(g.Hpl, 0, 8 * 18 * (size_t)g.n_ent, h->st));
+  CK(cudaMemsetAsync(g.xl, 0, 8 * 3 * (size_t)g.n_lm, h->st));
+  CK(cudaMemsetAsync(g.pe_flags, PPO_EF_ROBUST, (size_t)g.n_pe, h->st));
+  CK(cudaMemsetAsync(g.ple_flags, PPO_EF_ROBUST, (size_t)g.n_ple, h->st));
+  CK(cudaMemsetAsync(g.cbe_flags, PPO_EF_ROBUST, (size_t)g.n_cbe, h->st));
+  CK(cudaMemsetAsync(g.pce_flags, 0, (size_t)g.n_pce, h->st));
+  g.huber_mono = h->P.huber_mono; g.huber_stereo = h->P.huber_stereo; g.huber_plane = h->P.huber_plane; g.huber_vp = h->P.huber_vp_plane;
+  g.huber_bbox = h->P.huber_bbox; g.huber_corner = h->P.huber_corner;
+  g.ptcu_ratio = h->P.ptcu_max_outside_margin_ratio; g.ptcu_prior = h->P.ptcu_prior_weight;
+  CK(cudaStreamSynchronize(h->st));  // host vectors go out of scope
+  CK(cudaGetLastError());
+  h->have_graph = true;
+  h->lambda = -1;
+  return PPO_OK;
+#undef UP
+#undef DA
+}
+
+int ppo_ba_reset(ppo_ba_handle *h) {
+  if (!h || !h->have_graph) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevGraph &g = h->g;
+  int rc;
+  if ((rc = copy_state(h, h->sa, h->s0))) return rc;
+  CK(cudaMemsetAsync(g.pe_flags, PPO_EF_ROBUST, (size_t)g.n_pe, h->st));
+  CK(cudaMemsetAsync(g.ple_flags, PPO_EF_ROBUST, (size_t)g.n_ple, h->st));
+  CK(cudaMemsetAsync(g.cbe_flags, PPO_EF_ROBUST, (size_t)g.n_cbe, h->st));
+  CK(cudaMemsetAsync(g.pce_flags, 0, (size_t)g.n_pce, h->st));
+  std::fill(h->cpe_flags.begin(), h->cpe_flags.end(), (uint8_t)PPO_EF_ROBUST);
+  if (g.n_cpe) CK(cudaMemcpyAsync(h->d_cpe_flags, h->cpe_flags.data(), g.n_cpe, cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return PPO_OK;
+}
+
+// ---- SparseOptimizer::initializeOptimization(0) ------------------------------------------------------
+static int init_mapping(ppo_ba_handle *h) {
+  DevGraph &g = h->g;
+  cudaStream_t st = h->st;
+  CK(cudaMemsetAsync(g.kf_act, 0, 4 * (size_t)g.n_kf, st));
+  CK(cudaMemsetAsync(g.cu_act, 0, 4 * (size_t)g.n_cu, st));
+  CK(cudaMemsetAsync(g.pl_act, 0, 4 * (size_t)g.n_pl, st));
+  CK(cudaMemsetAsync(g.pt_act, 0, 4 * (size_t)g.n_pt, st));
+  const int nmax = std::max(std::max(g.n_pe, g.n_ple), std::max(std::max(g.n_cbe, g.n_pce), std::max(g.n_slots, g.n_pt)));
+  if (nmax > 0) {
+    k_mark_active<<<cdiv(nmax, 256), 256, 0, st>>>(g);
+    h->launches++;
+  }
+  if (g.n_cpe) {
+    k_mark_active_cpe<<<cdiv(g.n_cpe, 256), 256, 0, st>>>(g, h->d_cpe_cuboid, h->d_cpe_plane, h->d_cpe_flags);
+    h->launches++;
+  }
+  k_build_index<<<1, 32, 0, st>>>(g);
+  h->launches++;
+  if (nmax > 0) {
+    k_entry_pidx<<<cdiv(nmax, 256), 256, 0, st>>>(g);
+    h->launches++;
+  }
+  if (g.n_ple) {
+    k_slot_pidx<<<cdiv(g.n_ple, 256), 256, 0, st>>>(g);
+    h->launches++;
+  }
+  CK(cudaMemcpyAsync(h->h_dims, g.dims, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h->n_kf_free = h->h_dims[0];
+  h->n_p = h->h_dims[1];
+  h->n_l = h->h_dims[2] + h->h_dims[3];
+  h->n_active_edges = h->h_dims[4];
+  for (size_t e = 0; e < h->cpe_flags.size(); e++) h->n_active_edges += !(h->cpe_flags[e] & PPO_EF_LEVEL1);
+  return PPO_OK;
+}
+
+static int allreduce(ppo_ba_handle *h, double *buf, size_t n, int op) {
+  if (h->world <= 1) return PPO_OK;
+  int r = g_nccl.AllReduce(buf, buf, n, ncclFloat64_, op, h->comm, h->st);
+  if (r != 0) {
+    h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    return PPO_E_NCCL;
+  }
+  return PPO_OK;
+}
+
+// ---- computeActiveErrors + buildSystem at the current estimates -------------------------------------------
+static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kernel = false) {
+  DevGraph &g = h->g;
+  cudaStream_t st = h->st;
+  const DevState &s = h->sa;
+  if (!only_points_kernel) {
+    CK(cudaMemsetAsync(g.Hpp_kf, 0, 8 * 36 * (size_t)g.n_kf, st));
+    CK(cudaMemsetAsync(g.Hpp_cu, 0, 8 * 81 * (size_t)g.n_cu, st));
+    CK(cudaMemsetAsync(g.bp, 0, 8 * (size_t)h->max_np, st));
+    CK(cudaMemsetAsync(g.Hll, 0, 8 * 6 * (size_t)g.n_lm, st));
+    CK(cudaMemsetAsync(g.bl, 0, 8 * 3 * (size_t)g.n_lm, st));
+    CK(cudaMemsetAsync(g.Hpl, 0, 8 * 18 * (size_t)g.n_slots, st));
+  }
+  if (h->profiling) cudaEventRecord(h->evp[0], st);
+  if (g.n_units) {
+    k_point_linearize<<<h->nb_lin, LIN_WARPS * 32, 0, st>>>(g, s, h->d_chi_pt);
+    h->launches++;
+  }
+  if (only_points_kernel) return PPO_OK;
+  if (g.n_chunks) {
+    k_pose_accumulate<<<g.n_chunks, POSE_THREADS, 0, st>>>(g, s, h->d_chunk_part);
+    k_pose_reduce<<<cdiv(g.n_kf * 27, 128), 128, 0, st>>>(g, h->d_kf_chunk_ptr, h->d_chunk_part);
+    h->launches += 2;
+  }
+  const bool own = h->owner();
+  if (g.n_ple) {
+    k_plane_jac<<<cdiv(g.n_ple * 9, 128), 128, 0, st>>>(g, s);
+    if (own) k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pl);
+    else k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pl);
+    h->launches += 2;
+  }
+  if (g.n_cbe) {
+    k_cuboid_jac<<<cdiv(g.n_cbe * 15, 128), 128, 0, st>>>(g, s);
+    k_cuboid_edges<true><<<h->nb_cb, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_cb);
+    h->launches += 2;
+  }
+  if (g.n_pce) {
+    k_ptcu_jac<<<cdiv(g.n_pce * 9, 128), 128, 0, st>>>(g, s);
+    k_ptcu_edges<true><<<h->nb_pc, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pc);
+    h->launches += 2;
+  }
+  if (h->profiling) cudaEventRecord(h->evp[1], st);
+  k_scalars<<<1, 256, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, g.n_ple ? h->nb_pl : 0, h->d_chi_cb,
+                              g.n_cbe ? h->nb_cb : 0, h->d_chi_pc, g.n_pce ? h->nb_pc : 0, cpe_chi_const(h), nullptr, 0, 0.0, 0, nullptr);
+  h->launches++;
+  if (want_max_diag) {
+    k_max_diag<<<1, 256, 0, st>>>(g, h->d_scal);
+    h->launches++;
+  }
+  CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  return PPO_OK;
+}
+
+// ---- residuals at the trial estimates ---------------------------------------------------------------------
+static void residual_kernels(ppo_ba_handle *h, const DevState &s) {
+  DevGraph &g = h->g;
+  cudaStream_t st = h->st;
+  if (g.n_pe) { k_point_residual<<<h->nb_res, RES_THREADS, 0, st>>>(g, s, h->d_chi_pt); h->launches++; }
+  if (g.n_ple) { k_plane_edges<false><<<h->nb_pl, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pl); h->launches++; }
+  if (g.n_cbe) { k_cuboid_edges<false><<<h->nb_cb, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_cb); h->launches++; }
+  if (g.n_pce) { k_ptcu_edges<false><<<h->nb_pc, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pc); h->launches++; }
+}
+
+// ---- setLambda + Schur complement (+ optional factorisation / back-substitution) ----------------------------
+static int schur_system(ppo_ba_handle *h, double lambda) {
+  DevGraph &g = h->g;
+  cudaStream_t st = h->st;
+  const int n_p = h->n_p, ld = h->ld;
+  CK(cudaMemsetAsync(g.S, 0, 8 * (size_t)(n_p + 1) * ld, st));
+  CK(cudaMemsetAsync(h->d_not_spd, 0, sizeof(int), st));
+  if (h->n_lm_small) { k_schur<false><<<cdiv(h->n_lm_small, SCHUR_WARPS), SCHUR_WARPS * 32, 0, st>>>(g, h->d_lm_small, h->n_lm_small, lambda, n_p, ld); h->launches++; }
+  if (h->n_lm_big) { k_schur<true><<<h->n_lm_big, SCHUR_WARPS * 32, 0, st>>>(g, h->d_lm_big, h->n_lm_big, lambda, n_p, ld); h->launches++; }
+  const int n_comp = g.n_kf * 36 + g.n_cu * 81 + g.n_cbe * 54 + n_p;
+  if (n_comp) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, lambda, n_p, ld); h->launches++; }
+  return PPO_OK;
+}
+static int solve_and_backsub(ppo_ba_handle *h, double lambda) {
+  DevGraph &g = h->g;
+  dense_cholesky_solve(g.S, h->n_p, h->ld, g.xp, h->d_not_spd, h->st, &h->launches);
+  if (g.n_lm) { k_backsub<<<h->nb_bs, BS_WARPS * 32, 0, h->st>>>(g, lambda, h->d_scale_part); h->launches++; }
+  return PPO_OK;
+}
+
+// ---- SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve ------------------------------------------
+int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *stop, ppo_ba_stats *stats) {
+  if (!h || !h->have_graph) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  DevGraph &g = h->g;
+  cudaStream_t st = h->st;
+  CK(cudaEventRecord(h->ev0, st));
+  int rc = init_mapping(h);
+  if (rc) return rc;
+  if (h->n_p + h->n_l == 0) return PPO_E_EMPTY;
+  auto terminate = [&]() { return stop && *stop; };
+  const ppo_ba_params &P = h->P;
+  int done = 0, term = 0;
+  bool ok = true;
+  float ms;
+  for (int it = 0; it < iters && !terminate() && ok; it++) {
+    if ((rc = linearize(h, it == 0))) return rc;
+    double currentChi = h->h_scal->chi2, tempChi = currentChi;
+    const double iniChi = currentChi;
+    if (stats && it == 0) stats->chi2_initial = currentChi;
+    if (it == 0) {
+      h->lambda = P.lm_tau * h->h_scal->max_diag;  // computeLambdaInit
+      h->ni = 2;
+      h->nBad = 0;
+    }
+    if (h->profiling && stats) {
+      cudaEventElapsedTime(&ms, h->evp[0], h->evp[1]);
+      stats->ms_linearize += ms;
+    }
+    double rho = 0;
+    int qmax = 0;
+    bool accepted = false;
+    do {
+      if (h->profiling) cudaEventRecord(h->evp[2], st);
+      if ((rc = schur_system(h, h->lambda))) return rc;
+      if (h->profiling) cudaEventRecord(h->evp[3], st);
+      if ((rc = solve_and_backsub(h, h->lambda))) return rc;
+      if (h->profiling) cudaEventRecord(h->evp[4], st);
+      const int nv = g.n_kf + g.n_cu + g.n_pl + g.n_pt;
+      k_update<<<cdiv(nv, 128), 128, 0, st>>>(g, h->sa, h->sb);
+      h->launches++;
+      residual_kernels(h, h->sb);
+      k_scalars<<<1, 256, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_pe ? h->nb_res : 0, h->d_chi_pl, g.n_ple ? h->nb_pl : 0, h->d_chi_cb,
+                                  g.n_cbe ? h->nb_cb : 0, h->d_chi_pc, g.n_pce ? h->nb_pc : 0, cpe_chi_const(h), h->d_scale_part,
+                                  g.n_lm ? h->nb_bs : 0, h->lambda, h->n_p, h->d_not_spd);
+      h->launches++;
+      if (h->profiling) cudaEventRecord(h->evp[5], st);
+      CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaGetLastError());
+      if (h->profiling && stats) {
+        cudaEventElapsedTime(&ms, h->evp[2], h->evp[3]); stats->ms_schur += ms;
+        cudaEventElapsedTime(&ms, h->evp[3], h->evp[4]); stats->ms_solve += ms;
+        cudaEventElapsedTime(&ms, h->evp[4], h->evp[5]); stats->ms_update += ms;
+      }
+      const bool ok2 = !h->h_scal->not_spd;
+      tempChi = h->h_scal->chi2;
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = (currentChi - tempChi);
+      double scale = h->h_scal->scale;
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, P.lm_good_upper);
+        const double scaleFactor = std::max(P.lm_good_lower, alpha);
+        h->lambda *= scaleFactor;
+        h->ni = 2;
+        currentChi = tempChi;
+        std::swap(h->sa, h->sb);  // discardTop: the trial becomes the estimate
+        accepted = true;
+      } else {
+        h->lambda *= h->ni;
+        h->ni *= 2;
+        accepted = false;  // pop: sa is untouched
+      }
+      qmax++;
+    } while (rho < 0 && qmax < P.lm_max_trials && !terminate());
+    done++;
+    if (stats) {
+      stats->total_trials += qmax;
+      if (it < PPO_TRACE_MAX) {
+        ppo_ba_iter &r = stats->trace[it];
+        r.chi2_before = iniChi;
+        r.chi2_after = currentChi;
+        r.lambda = h->lambda;
+        r.rho = rho;
+        r.trials = qmax;
+        r.accepted = accepted;
+      }
+      stats->chi2_final = currentChi;
+    }
+    if (qmax == P.lm_max_trials || rho == 0) {
+      ok = false;
+      term = 1;
+    } else {
+      if ((iniChi - currentChi) * 1e3 < iniChi) h->nBad++;
+      else h->nBad = 0;
+      if (h->nBad >= 3) {
+        ok = false;
+        term = 1;
+      }
+    }
+  }
+  CK(cudaEventRecord(h->ev1, st));
+  CK(cudaEventSynchronize(h->ev1));
+  if (stats) {
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    stats->ms_total = ms;
+    stats->iterations = done;
+    stats->terminated = term ? term : (terminate() ? 2 : 0);
+    stats->n_pose_dim = h->n_p;
+    stats->n_landmarks = h->n_l;
+    stats->n_active_edges = h->n_active_edges;
+  }
+  return PPO_OK;
+}
+
+int ppo_ba_edge_chi2(ppo_ba_handle *h, int kind, double *chi2, unsigned char *depth_positive, double *err_norm) {
+  if (!h || !h->have_graph) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevGraph &g = h->g;
+  const int n = ppo_ba_edge_count(h, kind);
+  if (n < 0) return PPO_E_INVALID;
+  if (n == 0) return PPO_OK;
+  CK(cudaStreamSynchronize(h->st));
+  const double *src = nullptr;
+  switch (kind) {
+    case PPO_EDGE_POINT: src = g.pe_chi2; break;
+    case PPO_EDGE_PLANE: src = g.ple_chi2; break;
+    case PPO_EDGE_CUBOID_CAM: src = g.cbe_chi2; break;
+    case PPO_EDGE_POINT_CUBOID: src = g.pce_chi2; break;
+    default: break;
+  }
+  if (kind == PPO_EDGE_CUBOID_PLANE) {
+    if (chi2) std::copy(h->cpe_chi2.begin(), h->cpe_chi2.end(), chi2);
+    if (err_norm) std::copy(h->cpe_norm.begin(), h->cpe_norm.end(), err_norm);
+    if (depth_positive) std::memset(depth_positive, 1, n);
+    return PPO_OK;
+  }
+  if (chi2) CK(cudaMemcpy(chi2, src, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+  if (err_norm) {
+    if (kind == PPO_EDGE_CUBOID_CAM) CK(cudaMemcpy(err_norm, g.cbe_norm, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    else std::fill(err_norm, err_norm + n, std::numeric_limits<double>::quiet_NaN());  // only defined for cuboid edges
+  }
+  if (depth_positive) {
+    if (kind == PPO_EDGE_POINT || kind == PPO_EDGE_PLANE) {
+      unsigned char *d = nullptr;
+      CK(cudaMalloc((void **)&d, n));
+      k_depth_flags<<<cdiv(n, 256), 256, 0, h->st>>>(g, h->sa, kind, d);
+      h->launches++;
+      cudaError_t e = cudaMemcpyAsync(depth_positive, d, n, cudaMemcpyDeviceToHost, h->st);
+      cudaStreamSynchronize(h->st);
+      cudaFree(d);
+      CK(e);
+    } else {
+      std::memset(depth_positive, 1, n);
+    }
+  }
+  return PPO_OK;
+}
+
+static uint8_t *flags_ptr(ppo_ba_handle *h, int kind) {
+  switch (kind) {
+    case PPO_EDGE_POINT: return h->g.pe_flags;
+    case PPO_EDGE_PLANE: return h->g.ple_flags;
+    case PPO_EDGE_CUBOID_CAM: return h->g.cbe_flags;
+    case PPO_EDGE_POINT_CUBOID: return h->g.pce_flags;
+    case PPO_EDGE_CUBOID_PLANE: return h->d_cpe_flags;
+  }
+  return nullptr;
+}
+int ppo_ba_set_edge_flags(ppo_ba_handle *h, int kind, const unsigned char *flags) {
+  if (!h || !h->have_graph || !flags) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int n = ppo_ba_edge_count(h, kind);
+  if (n < 0) return PPO_E_INVALID;
+  if (kind == PPO_EDGE_CUBOID_PLANE) h->cpe_flags.assign(flags, flags + n);
+  if (n) CK(cudaMemcpy(flags_ptr(h, kind), flags, n, cudaMemcpyHostToDevice));
+  return PPO_OK;
+}
+int ppo_ba_get_edge_flags(ppo_ba_handle *h, int kind, unsigned char *flags) {
+  if (!h || !h->have_graph || !flags) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int n = ppo_ba_edge_count(h, kind);
+  if (n < 0) return PPO_E_INVALID;
+  CK(cudaStreamSynchronize(h->st));
+  if (n) CK(cudaMemcpy(flags, flags_ptr(h, kind), n, cudaMemcpyDeviceToHost));
+  return PPO_OK;
+}
+
+int ppo_ba_outlier_pass(ppo_ba_handle *h, int32_t n_out[3]) {
+  if (!h || !h->have_graph) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevGraph &g = h->g;
+  const ppo_ba_params &P = h->P;
+  CK(cudaMemsetAsync(h->d_nout, 0, 4 * sizeof(int), h->st));
+  const int nmax = std::max(g.n_pe, std::max(g.n_ple, g.n_cbe));
+  if (nmax) {
+    k_outlier_pass<<<cdiv(nmax, 256), 256, 0, h->st>>>(g, h->sa, P.chi2_mono, P.chi2_stereo, P.chi2_plane, P.chi2_vp_plane, P.norm_bbox,
+                                                     P.norm_corner, h->d_nout);
+    h->launches++;
+  }
+  int out[4];
+  CK(cudaMemcpyAsync(out, h->d_nout, sizeof out, cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  if (n_out) n_out[0] = out[0], n_out[1] = out[1], n_out[2] = out[2];
+  return PPO_OK;
+}
+
+int ppo_ba_local_ba(ppo_ba_handle *h, const volatile unsigned char *stop, ppo_ba_result *res) {
+  if (!h || !res) return PPO_E_INVALID;
+  std::memset(res, 0, sizeof *res);
+  if (stop && *stop) {  // Optimizer.cc:2723-2725
+    res->skipped = 1;
+    return PPO_OK;
+  }
+  int rc = ppo_ba_optimize(h, h->P.iters_round1, stop, &res->round1);
+  if (rc != PPO_OK) return rc;
+  if (!(stop && *stop)) {
+    int32_t n_out[3];
+    if ((rc = ppo_ba_outlier_pass(h, n_out))) return rc;
+    res->n_outlier_point_edges = n_out[0];
+    res->n_outlier_plane_edges = n_out[1];
+    res->n_outlier_cuboid_edges = n_out[2];
+    rc = ppo_ba_optimize(h, h->P.iters_round2, stop, &res->round2);
+    if (rc == PPO_E_EMPTY) rc = PPO_OK;
+  }
+  return rc;
+}
+
+int ppo_ba_get_state(ppo_ba_handle *h, ppo_ba_state *out) {
+  if (!h || !h->have_graph || !out) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevGraph &g = h->g;
+  CK(cudaStreamSynchronize(h->st));
+  if (out->kf_pose && g.n_kf) CK(cudaMemcpy(out->kf_pose, h->sa.kf_pose, 56 * (size_t)g.n_kf, cudaMemcpyDeviceToHost));
+  if (out->pt_xyz && g.n_pt) CK(cudaMemcpy(out->pt_xyz, h->sa.pt, 24 * (size_t)g.n_pt, cudaMemcpyDeviceToHost));
+  if (out->pl_coef && g.n_pl) CK(cudaMemcpy(out->pl_coef, h->sa.pl, 32 * (size_t)g.n_pl, cudaMemcpyDeviceToHost));
+  if (out->cu_state && g.n_cu) CK(cudaMemcpy(out->cu_state, h->sa.cu, 80 * (size_t)g.n_cu, cudaMemcpyDeviceToHost));
+  return PPO_OK;
+}
+
+int ppo_ba_set_profiling(ppo_ba_handle *h, int enable) {
+  if (!h) return PPO_E_INVALID;
+  h->profiling = enable != 0;
+  return PPO_OK;
+}
+long long ppo_ba_launch_count(const ppo_ba_handle *h) { return h ? h->launches : 0; }
+
+static const size_t FLUSH_BYTES = 256ull << 20;
+int ppo_ba_flush_l2(ppo_ba_handle *h) {
+  if (!h) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (!h->d_flush) CK(cudaMalloc(&h->d_flush, FLUSH_BYTES));
+  CK(cudaMemsetAsync(h->d_flush, 0, FLUSH_BYTES, h->st));
+  return PPO_OK;
+}
+int ppo_ba_mark(ppo_ba_handle *h, int which) {
+  if (!h || which < 0 || which > 1) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->evm[which], h->st));
+  return PPO_OK;
+}
+int ppo_ba_elapsed_ms(ppo_ba_handle *h, double *ms) {
+  if (!h || !ms) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->evm[1]));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, h->evm[0], h->evm[1]));
+  *ms = f;
+  return PPO_OK;
+}
+
+int ppo_ba_time_assembly(ppo_ba_handle *h, int reps, double *ms_mean, double *algo_bytes) {
+  if (!h || !h->have_graph || reps <= 0) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevGraph &g = h->g;
+  int rc = init_mapping(h);
+  if (rc) return rc;
+  // warm-up
+  for (int i = 0; i < 3; i++) {
+    CK(cudaMemsetAsync(g.Hll, 0, 8 * 6 * (size_t)g.n_lm, h->st));
+    CK(cudaMemsetAsync(g.bl, 0, 8 * 3 * (size_t)g.n_lm, h->st));
+    if ((rc = linearize(h, false, true))) return rc;
+  }
+  double total = 0;
+  for (int i = 0; i < reps; i++) {
+    CK(cudaMemsetAsync(g.Hll, 0, 8 * 6 * (size_t)g.n_lm, h->st));
+    CK(cudaMemsetAsync(g.bl, 0, 8 * 3 * (size_t)g.n_lm, h->st));
+    if ((rc = ppo_ba_flush_l2(h))) return rc;  // cold L2 for every timed launch
+    CK(cudaEventRecord(h->ev0, h->st));
+    k_point_linearize<<<h->nb_lin, LIN_WARPS * 32, 0, h->st>>>(g, h->sa, h->d_chi_pt);
+    h->launches++;
+    CK(cudaEventRecord(h->ev1, h->st));
+    CK(cudaEventSynchronize(h->ev1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    total += ms;
+  }
+  if (ms_mean) *ms_mean = total / reps;
+  // algorithmic bytes of one launch: per edge 16 B record + 4 B inv_sigma2 + 4 B point index
+  // + 1 B flags read, 144 B Hpl + 8 B chi2 written; per point 4 B rowptr + 24 B xyz read, 72 B Hll/bl written;
+  // per key-frame 96 B pose cache + 20 B intrinsics read.
+  if (algo_bytes) *algo_bytes = (double)g.n_pe * (16 + 4 + 4 + 1 + 144 + 8) + (double)g.n_pt * (4 + 24 + 72) + (double)g.n_kf * (96 + 20);
+  return PPO_OK;
+}
+
+// ---- parity / debugging exports (mirrored by the oracle's ppo_oracle_debug_*) ----------------------------------
+int ppo_ba_debug_linearize(ppo_ba_handle *h, int32_t dims[2], double *Hpp, double *b, double *Hll, double *chi2) {
+  if (!h || !h->have_graph) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevGraph &g = h->g;
+  int rc = init_mapping(h);
+  if (rc) return rc;
+  if ((rc = linearize(h, true))) return rc;
+  const int n_p = h->n_p;
+  dims[0] = n_p;
+  dims[1] = h->n_l;
+  if (chi2) *chi2 = h->h_scal->chi2;
+  if (!Hpp && !b && !Hll) return PPO_OK;
+  std::vector<int> kf_idx(g.n_kf), cu_off(g.n_cu), pl_act(g.n_pl), pt_act(g.n_pt), cbe_kf(g.n_cbe), cbe_cu(g.n_cbe);
+  std::vector<uint8_t> pt_fixed(g.n_pt), cbe_flags(g.n_cbe);
+  std::vector<double> hkf(36 * (size_t)g.n_kf), hcu(81 * (size_t)g.n_cu), hpc(54 * (size_t)g.n_cbe), bp(h->max_np), hll(6 * (size_t)g.n_lm), bl(3 * (size_t)g.n_lm);
+#define DL(dst, src, n) if ((n) > 0) CK(cudaMemcpy((dst).data(), (src), sizeof((dst)[0]) * (size_t)(n), cudaMemcpyDeviceToHost))
+  DL(kf_idx, g.kf_idx, g.n_kf); DL(cu_off, g.cu_off, g.n_cu); DL(pl_act, g.pl_act, g.n_pl); DL(pt_act, g.pt_act, g.n_pt);
+  DL(cbe_kf, g.cbe_kf, g.n_cbe); DL(cbe_cu, g.cbe_cuboid, g.n_cbe); DL(pt_fixed, g.pt_fixed, g.n_pt); DL(cbe_flags, g.cbe_flags, g.n_cbe);
+  DL(hkf, g.Hpp_kf, 36 * (size_t)g.n_kf); DL(hcu, g.Hpp_cu, 81 * (size_t)g.n_cu); DL(hpc, g.Hpc, 54 * (size_t)g.n_cbe); DL(bp, g.bp, h->max_np);
+  DL(hll, g.Hll, 6 * (size_t)g.n_lm); DL(bl, g.bl, 3 * (size_t)g.n_lm);
+  if (Hpp) {
+    std::fill(Hpp, Hpp + (size_t)n_p * n_p, 0.0);
+    for (int k = 0; k < g.n_kf; k++)
+      if (kf_idx[k] >= 0)
+        for (int a = 0; a < 6; a++)
+          for (int c = 0; c < 6; c++) Hpp[(size_t)(6 * kf_idx[k] + a) * n_p + 6 * kf_idx[k] + c] = hkf[36 * (size_t)kf_idx[k] + 6 * a + c];
+    for (int k = 0; k < g.n_cu; k++)
+      if (cu_off[k] >= 0)
+        for (int a = 0; a < 9; a++)
+          for (int c = 0; c < 9; c++) Hpp[(size_t)(cu_off[k] + a) * n_p + cu_off[k] + c] = hcu[81 * (size_t)k + 9 * a + c];
+    for (int e = 0; e < g.n_cbe; e++) {
+      if (cbe_flags[e] & PPO_EF_LEVEL1) continue;
+      const int idx = kf_idx[cbe_kf[e]], off = cu_off[cbe_cu[e]];
+      if (idx < 0 || off < 0) continue;
+      for (int a = 0; a < 6; a++)
+        for (int c = 0; c < 9; c++) Hpp[(size_t)(6 * idx + a) * n_p + off + c] += hpc[54 * (size_t)e + 9 * a + c];
+    }
+  }
+  int l = 0;
+  for (int L = 0; L < g.n_lm; L++) {
+    const bool act = L < g.n_pl ? pl_act[L] != 0 : (pt_act[L - g.n_pl] != 0 && !pt_fixed[L - g.n_pl]);
+    if (!act) continue;
+    if (Hll) {
+      const double *s = &hll[6 * (size_t)L];
+      double *d = &Hll[9 * (size_t)l];
+      d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[1]; d[4] = s[3]; d[5] = s[4]; d[6] = s[2]; d[7] = s[4]; d[8] = s[5];
+    }
+    if (b) for (int i = 0; i < 3; i++) b[n_p + 3 * (size_t)l + i] = bl[3 * (size_t)L + i];
+    l++;
+  }
+  if (b) for (int i = 0; i < n_p; i++) b[i] = bp[i];
+  return PPO_OK;
+}
+
+int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, double *bschur, double *x, int32_t *ok) {
+  if (!h || !h->have_graph) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevGraph &g = h->g;
+  const int n_p = h->n_p, ld = h->ld;
+  int rc;
+  if ((rc = schur_system(h, lambda))) return rc;
+  CK(cudaStreamSynchronize(h->st));
+  if (Hschur_upper || bschur) {
+    std::vector<double> S((size_t)(n_p + 1) * ld);
+    if (n_p) CK(cudaMemcpy(S.data(), g.S, 8 * (size_t)n_p * ld, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n_p; i++) {
+      if (Hschur_upper)
+        for (int j = 0; j < n_p; j++) Hschur_upper[(size_t)i * n_p + j] = j >= i ? S[(size_t)i * ld + j] : 0.0;
+      if (bschur) bschur[i] = S[(size_t)i * ld + n_p];
+    }
+  }
+  if ((rc = solve_and_backsub(h, lambda))) return rc;
+  int ns = 0;
+  CK(cudaMemcpyAsync(&ns, h->d_not_spd, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaGetLastError());
+  if (ok) *ok = !ns;
+  if (x) {
+    std::vector<double> xl(3 * (size_t)g.n_lm);
+    std::vector<int> pl_act(g.n_pl), pt_act(g.n_pt);
+    std::vector<uint8_t> pt_fixed(g.n_pt);
+    if (n_p) CK(cudaMemcpy(x, g.xp, 8 * (size_t)n_p, cudaMemcpyDeviceToHost));
+    DL(xl, g.xl, 3 * (size_t)g.n_lm); DL(pl_act, g.pl_act, g.n_pl); DL(pt_act, g.pt_act, g.n_pt); DL(pt_fixed, g.pt_fixed, g.n_pt);
+    int l = 0;
+    for (int L = 0; L < g.n_lm; L++) {
+      const bool act = L < g.n_pl ? pl_act[L] != 0 : (pt_act[L - g.n_pl] != 0 && !pt_fixed[L - g.n_pl]);
+      if (!act) continue;
+      for (int i = 0; i < 3; i++) x[n_p + 3 * (size_t)l + i] = xl[3 * (size_t)L + i];
+      l++;
+    }
+  }
+#undef DL
+  return PPO_OK;
+}
+
+int ppo_ba_set_shard(ppo_ba_handle *h, void *nccl_comm, int rank, int world) {
+  if (!h || world < 1 || rank < 0 || rank >= world) return PPO_E_INVALID;
+  if (world > 1) {
+    g_nccl.load();
+    if (!g_nccl.ok || !nccl_comm) {
+      h->err = "NCCL not available (libnccl.so.2 could not be opened) or null communicator";
+      return PPO_E_NCCL;
+    }
+  }
+  h->comm = (ncclComm_t)nccl_comm;
+  h->rank = rank;
+  h->world = world;
+  return PPO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,997 @@
+// CUDA kernels of the local-BA engine (sm_100a).  All arithmetic is IEEE double like g2o.
+// Kernel inventory and the roofline that bounds each: DESIGN.md section 5.
+#pragma once
+#include "ppo_device.cuh"
+#include "ppo_geom.cuh"
+
+namespace ppo {
+
+#define PPO_EF_LEVEL1_ 1u
+#define PPO_EF_ROBUST_ 2u
+constexpr unsigned FULL = 0xffffffffu;
+constexpr double NUM_DELTA = 1e-9;                      // base_binary_edge.hpp:232
+constexpr double NUM_SCALAR = 1.0 / (2 * NUM_DELTA);    // :233
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+// deterministic block sum (fixed tree), result valid in thread 0
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double *sm /* THREADS/32 */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double r = 0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < THREADS / 32; i++) r += sm[i];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// index mapping: SparseOptimizer::initializeOptimization + buildIndexMapping
+// (core/sparse_optimizer.cpp:166-267)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_mark_active(DevGraph g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.n_pe) {
+    const int kf = g.pe_rec[i].kf, pt = g.pe_pt[i];
+    if (!(g.pe_flags[i] & PPO_EF_LEVEL1_) && !(g.kf_fixed[kf] && g.pt_fixed[pt])) {
+      g.kf_act[kf] = 1;
+      g.pt_act[pt] = 1;
+    }
+  }
+  if (i < g.n_ple && !(g.ple_flags[i] & PPO_EF_LEVEL1_)) {
+    g.kf_act[g.ple_kf[i]] = 1;
+    g.pl_act[g.ple_plane[i]] = 1;
+  }
+  if (i < g.n_cbe && !(g.cbe_flags[i] & PPO_EF_LEVEL1_)) {
+    g.kf_act[g.cbe_kf[i]] = 1;
+    g.cu_act[g.cbe_cuboid[i]] = 1;
+  }
+  if (i < g.n_pce && !(g.pce_flags[i] & PPO_EF_LEVEL1_)) g.cu_act[g.pce_cuboid[i]] = 1;
+}
+// cuboid-plane edges (constant residual) only make their vertices active; host passes them packed
+__global__ void k_mark_active_cpe(DevGraph g, const int *cpe_cuboid, const int *cpe_plane, const uint8_t *cpe_flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.n_cpe && !(cpe_flags[i] & PPO_EF_LEVEL1_)) {
+    g.cu_act[cpe_cuboid[i]] = 1;
+    g.pl_act[cpe_plane[i]] = 1;
+  }
+}
+__global__ void k_build_index(DevGraph g) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int nb = 0;
+    for (int i = 0; i < g.n_kf; i++) g.kf_idx[i] = (g.kf_act[i] && !g.kf_fixed[i]) ? nb++ : -1;
+    int off = 6 * nb;
+    for (int i = 0; i < g.n_cu; i++) {
+      g.cu_off[i] = g.cu_act[i] ? off : -1;
+      if (g.cu_act[i]) off += 9;
+    }
+    g.dims[0] = nb;
+    g.dims[1] = off;
+    int nl = 0;
+    for (int i = 0; i < g.n_pl; i++) nl += g.pl_act[i] != 0;
+    g.dims[2] = nl;  // active planes; active points are counted by k_entry_pidx
+    g.dims[3] = 0;
+    g.dims[4] = 0;
+  }
+}
+__global__ void k_entry_pidx(DevGraph g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.n_slots) g.ent_pidx[i] = -2;
+  if (i < g.n_pe) {
+    const int kf = g.pe_rec[i].kf, pt = g.pe_pt[i];
+    const bool act = !(g.pe_flags[i] & PPO_EF_LEVEL1_) && !(g.kf_fixed[kf] && g.pt_fixed[pt]);
+    g.ent_pidx[g.n_slots + i] = act ? g.kf_idx[kf] : -2;
+    if (act) atomicAdd(&g.dims[4], 1);
+  }
+  if (i < g.n_pt && g.pt_act[i] && !g.pt_fixed[i]) atomicAdd(&g.dims[3], 1);
+  if (i < g.n_ple && !(g.ple_flags[i] & PPO_EF_LEVEL1_)) atomicAdd(&g.dims[4], 1);
+  if (i < g.n_cbe && !(g.cbe_flags[i] & PPO_EF_LEVEL1_)) atomicAdd(&g.dims[4], 1);
+  if (i < g.n_pce && !(g.pce_flags[i] & PPO_EF_LEVEL1_)) atomicAdd(&g.dims[4], 1);
+}
+__global__ void k_slot_pidx(DevGraph g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.n_ple && !(g.ple_flags[i] & PPO_EF_LEVEL1_)) g.ent_pidx[g.ple_slot[i]] = g.kf_idx[g.ple_kf[i]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// point edges: residual + analytic Jacobians (types_six_dof_expmap.cpp:135-266)
+// ---------------------------------------------------------------------------------------------
+struct PointEdgeLin {
+  double err[3];
+  double Jpt[9];   // D x 3
+  double Jkf[18];  // D x 6
+  int D;
+};
+PPO_D void point_edge_linearize(const double Rt[12], const double X[3], const float intr[5], const PointEdgeRec &rec,
+                                PointEdgeLin &L) {
+  double p[3];
+  cam_point(Rt, X, p);
+  L.D = point_edge_error(p, intr, rec.u, rec.v, rec.ur, L.err);
+  const double fx = intr[0], fy = intr[1], bf = intr[4];
+  const double x = p[0], y = p[1], z = p[2], z_2 = z * z;
+  // d(residual)/d(camera-frame point), rows 0..2
+  const double a0[3] = {-fx / z, 0.0, fx * x / z_2};
+  const double a1[3] = {0.0, -fy / z, fy * y / z_2};
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    L.Jpt[j] = a0[0] * Rt[j] + a0[2] * Rt[6 + j];
+    L.Jpt[3 + j] = a1[1] * Rt[3 + j] + a1[2] * Rt[6 + j];
+    L.Jpt[6 + j] = L.Jpt[j] - bf * Rt[6 + j] / z_2;
+  }
+  L.Jkf[0] = x * y / z_2 * fx;
+  L.Jkf[1] = -(1 + (x * x / z_2)) * fx;
+  L.Jkf[2] = y / z * fx;
+  L.Jkf[3] = -1. / z * fx;
+  L.Jkf[4] = 0;
+  L.Jkf[5] = x / z_2 * fx;
+  L.Jkf[6] = (1 + y * y / z_2) * fy;
+  L.Jkf[7] = -x * y / z_2 * fy;
+  L.Jkf[8] = -x / z * fy;
+  L.Jkf[9] = 0;
+  L.Jkf[10] = -1. / z * fy;
+  L.Jkf[11] = y / z_2 * fy;
+  L.Jkf[12] = L.Jkf[0] - bf * y / z_2;
+  L.Jkf[13] = L.Jkf[1] + bf * x / z_2;
+  L.Jkf[14] = L.Jkf[2];
+  L.Jkf[15] = L.Jkf[3];
+  L.Jkf[16] = 0;
+  L.Jkf[17] = L.Jkf[5] - bf / z_2;
+  if (L.D == 2) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) L.Jpt[6 + j] = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) L.Jkf[12 + j] = 0;
+  }
+}
+
+constexpr int LIN_WARPS = 4;
+constexpr int STAGE_LD = 19;  // 18 doubles per 6x3 block + 1 pad: conflict-free half-warp stores
+
+// The Jacobian / assembly pass over the point edges (computeActiveErrors + linearizeOplus +
+// constructQuadraticForm of core/block_solver.hpp:502-560 for EdgeSE3ProjectXYZ /
+// EdgeStereoSE3ProjectXYZ, landmark side): one warp owns a run of consecutive points with <= 32
+// edges, one lane per edge; Hll / bl come from a segmented warp-shuffle scan, the 6x3 Hpl blocks
+// are staged in shared memory and stored as one contiguous coalesced run.
+__global__ void __launch_bounds__(LIN_WARPS * 32) k_point_linearize(DevGraph g, DevState s, double *chi_part) {
+  __shared__ double stage[LIN_WARPS][32 * STAGE_LD];
+  __shared__ double wsum[LIN_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * LIN_WARPS + warp;
+  double rho_sum = 0;
+  if (unit < g.n_units) {
+    const int p0 = g.unit_pt0[unit], p1 = g.unit_pt0[unit + 1];
+    const int e0 = g.pt_rowptr[p0], e1 = g.pt_rowptr[p1];
+    for (int base = e0; base < e1; base += 32) {
+      const int e = base + lane;
+      const bool valid = e < e1;
+      double acc[9];  // Hll xx xy xz yy yz zz, bl x y z
+#pragma unroll
+      for (int i = 0; i < 9; i++) acc[i] = 0;
+      double hpl[18];
+#pragma unroll
+      for (int i = 0; i < 18; i++) hpl[i] = 0;
+      int key = -1;
+      bool lm_free = false;
+      if (valid) {
+        const PointEdgeRec rec = g.pe_rec[e];
+        const int pt = g.pe_pt[e];
+        key = pt;
+        const unsigned fl = g.pe_flags[e];
+        const bool ptfix = g.pt_fixed[pt];
+        lm_free = !ptfix;
+        const bool active = !(fl & PPO_EF_LEVEL1_) && !(g.kf_fixed[rec.kf] && ptfix);
+        if (active) {
+          double Rt[12], X[3];
+          float intr[5];
+#pragma unroll
+          for (int i = 0; i < 12; i++) Rt[i] = __ldg(&s.kf_Rt[12 * rec.kf + i]);
+#pragma unroll
+          for (int i = 0; i < 3; i++) X[i] = s.pt[3 * pt + i];
+#pragma unroll
+          for (int i = 0; i < 5; i++) intr[i] = __ldg(&g.kf_intr[5 * rec.kf + i]);
+          PointEdgeLin L;
+          point_edge_linearize(Rt, X, intr, rec, L);
+          const double is2 = (double)g.pe_is2[e];
+          const double chi2 = L.err[0] * (is2 * L.err[0]) + L.err[1] * (is2 * L.err[1]) + L.err[2] * (is2 * L.err[2]);
+          g.pe_chi2[e] = chi2;
+          double rho0 = chi2, w = 1.0;
+          if (fl & PPO_EF_ROBUST_) w = huber_w(chi2, L.D == 2 ? g.huber_mono : g.huber_stereo, &rho0);
+          rho_sum += rho0;
+          const double ws = w * is2;
+          if (!ptfix) {
+            // Hll += Jpt^T (w Omega) Jpt ; bl += -Jpt^T (w Omega) r
+            double wj[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) wj[i] = ws * L.Jpt[i];
+            acc[0] = wj[0] * L.Jpt[0] + wj[3] * L.Jpt[3] + wj[6] * L.Jpt[6];
+            acc[1] = wj[0] * L.Jpt[1] + wj[3] * L.Jpt[4] + wj[6] * L.Jpt[7];
+            acc[2] = wj[0] * L.Jpt[2] + wj[3] * L.Jpt[5] + wj[6] * L.Jpt[8];
+            acc[3] = wj[1] * L.Jpt[1] + wj[4] * L.Jpt[4] + wj[7] * L.Jpt[7];
+            acc[4] = wj[1] * L.Jpt[2] + wj[4] * L.Jpt[5] + wj[7] * L.Jpt[8];
+            acc[5] = wj[2] * L.Jpt[2] + wj[5] * L.Jpt[5] + wj[8] * L.Jpt[8];
+#pragma unroll
+            for (int a = 0; a < 3; a++) acc[6 + a] = -(wj[a] * L.err[0] + wj[3 + a] * L.err[1] + wj[6 + a] * L.err[2]);
+            if (g.ent_pidx[g.n_slots + e] >= 0) {
+#pragma unroll
+              for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) hpl[a * 3 + c] = L.Jkf[a] * wj[c] + L.Jkf[6 + a] * wj[3 + c] + L.Jkf[12 + a] * wj[6 + c];
+            }
+          }
+        }
+      }
+      // segmented inclusive scan over the lanes of one point
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int ku = __shfl_up_sync(FULL, key, d);
+        const bool take = lane >= d && ku == key;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+          const double t = __shfl_up_sync(FULL, acc[i], d);
+          if (take) acc[i] += t;
+        }
+      }
+      const int kn = __shfl_down_sync(FULL, key, 1);
+      const bool seg_end = valid && (lane == 31 || kn != key);
+      if (seg_end && lm_free) {
+        const int L = g.n_pl + key;
+#pragma unroll
+        for (int i = 0; i < 6; i++) atomicAdd(&g.Hll[6 * (size_t)L + i], acc[i]);  // one add per value unless the point has > 32 edges
+#pragma unroll
+        for (int i = 0; i < 3; i++) atomicAdd(&g.bl[3 * (size_t)L + i], acc[6 + i]);
+      }
+      // Hpl blocks of this run: stage and store contiguously
+#pragma unroll
+      for (int i = 0; i < 18; i++) stage[warp][lane * STAGE_LD + i] = hpl[i];
+      __syncwarp();
+      const int n = (min(e1, base + 32) - base) * 18;
+      double *dst = g.Hpl + 18 * (size_t)(g.n_slots + base);
+      for (int i = lane; i < n; i += 32) dst[i] = stage[warp][(i / 18) * STAGE_LD + (i % 18)];
+      __syncwarp();
+    }
+  }
+  rho_sum = warp_sum(rho_sum);
+  if (lane == 0) wsum[warp] = rho_sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < LIN_WARPS; i++) t += wsum[i];
+    chi_part[blockIdx.x] = t;
+  }
+}
+
+// residual-only pass (computeActiveErrors + activeRobustChi2, core/sparse_optimizer.cpp:61-114)
+constexpr int RES_THREADS = 256;
+__global__ void __launch_bounds__(RES_THREADS) k_point_residual(DevGraph g, DevState s, double *chi_part) {
+  __shared__ double sm[RES_THREADS / 32];
+  const int e = blockIdx.x * RES_THREADS + threadIdx.x;
+  double rho0 = 0;
+  if (e < g.n_pe) {
+    const PointEdgeRec rec = g.pe_rec[e];
+    const int pt = g.pe_pt[e];
+    const unsigned fl = g.pe_flags[e];
+    if (!(fl & PPO_EF_LEVEL1_) && !(g.kf_fixed[rec.kf] && g.pt_fixed[pt])) {
+      double Rt[12], X[3], p[3], err[3];
+      float intr[5];
+#pragma unroll
+      for (int i = 0; i < 12; i++) Rt[i] = __ldg(&s.kf_Rt[12 * rec.kf + i]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) X[i] = s.pt[3 * pt + i];
+#pragma unroll
+      for (int i = 0; i < 5; i++) intr[i] = __ldg(&g.kf_intr[5 * rec.kf + i]);
+      cam_point(Rt, X, p);
+      const int D = point_edge_error(p, intr, rec.u, rec.v, rec.ur, err);
+      const double is2 = (double)g.pe_is2[e];
+      const double chi2 = err[0] * (is2 * err[0]) + err[1] * (is2 * err[1]) + err[2] * (is2 * err[2]);
+      g.pe_chi2[e] = chi2;
+      rho0 = chi2;
+      if (fl & PPO_EF_ROBUST_) huber_w(chi2, D == 2 ? g.huber_mono : g.huber_stereo, &rho0);
+    }
+  }
+  const double t = block_sum<RES_THREADS>(rho0, sm);
+  if (threadIdx.x == 0) chi_part[blockIdx.x] = t;
+}
+
+// pose side of the point edges: Hpp_jj += Jkf^T (w Omega) Jkf, bp_j += -Jkf^T (w Omega) r.
+// Edges are grouped by key-frame and cut into chunks; every chunk writes a 27-value partial
+// (21 upper entries + 6 gradient) that k_pose_reduce sums in a fixed order (deterministic, no atomics).
+constexpr int POSE_THREADS = 256;
+__global__ void __launch_bounds__(POSE_THREADS) k_pose_accumulate(DevGraph g, DevState s, double *chunk_part) {
+  __shared__ double sm[POSE_THREADS / 32][27];
+  const int c = blockIdx.x;
+  const int kf = g.chunk_kf[c];
+  const int idx = g.kf_idx[kf];
+  double v[27];
+#pragma unroll
+  for (int i = 0; i < 27; i++) v[i] = 0;
+  const int k = g.chunk_begin[c] + threadIdx.x;
+  if (idx >= 0 && k < g.chunk_end[c]) {
+    const int e = g.kfe_edge[k];
+    const unsigned fl = g.pe_flags[e];
+    if (!(fl & PPO_EF_LEVEL1_)) {
+      const PointEdgeRec rec = g.pe_rec[e];
+      const int pt = g.pe_pt[e];
+      double Rt[12], X[3];
+      float intr[5];
+#pragma unroll
+      for (int i = 0; i < 12; i++) Rt[i] = __ldg(&s.kf_Rt[12 * kf + i]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) X[i] = s.pt[3 * pt + i];
+#pragma unroll
+      for (int i = 0; i < 5; i++) intr[i] = __ldg(&g.kf_intr[5 * kf + i]);
+      PointEdgeLin L;
+      point_edge_linearize(Rt, X, intr, rec, L);
+      const double is2 = (double)g.pe_is2[e];
+      const double chi2 = L.err[0] * (is2 * L.err[0]) + L.err[1] * (is2 * L.err[1]) + L.err[2] * (is2 * L.err[2]);
+      double rho0, w = 1.0;
+      if (fl & PPO_EF_ROBUST_) w = huber_w(chi2, L.D == 2 ? g.huber_mono : g.huber_stereo, &rho0);
+      const double ws = w * is2;
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = a; b < 6; b++) v[q++] = ws * (L.Jkf[a] * L.Jkf[b] + L.Jkf[6 + a] * L.Jkf[6 + b] + L.Jkf[12 + a] * L.Jkf[12 + b]);
+#pragma unroll
+      for (int a = 0; a < 6; a++) v[21 + a] = -ws * (L.Jkf[a] * L.err[0] + L.Jkf[6 + a] * L.err[1] + L.Jkf[12 + a] * L.err[2]);
+    }
+  }
+  const int lane = threadIdx.x & 31, w_ = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 27; i++) {
+    const double t = warp_sum(v[i]);
+    if (lane == 0) sm[w_][i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double t = 0;
+    for (int i = 0; i < POSE_THREADS / 32; i++) t += sm[i][threadIdx.x];
+    chunk_part[27 * (size_t)c + threadIdx.x] = t;
+  }
+}
+__global__ void k_pose_reduce(DevGraph g, const int *kf_chunk_ptr, const double *chunk_part) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kf = t / 27, i = t % 27;
+  if (kf >= g.n_kf) return;
+  const int idx = g.kf_idx[kf];
+  if (idx < 0) return;
+  double sum = 0;
+  for (int c = kf_chunk_ptr[kf]; c < kf_chunk_ptr[kf + 1]; c++) sum += chunk_part[27 * (size_t)c + i];
+  if (i < 21) {
+    int a = 0, rem = i;  // unpack upper-triangular index
+    while (rem >= 6 - a) {
+      rem -= 6 - a;
+      a++;
+    }
+    const int b = a + rem;
+    atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * a + b], sum);
+    if (a != b) atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * b + a], sum);
+  } else {
+    atomicAdd(&g.bp[6 * idx + (i - 21)], sum);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plane edges (numeric Jacobians, base_binary_edge.hpp:216-320): vertex 0 = plane (3), vertex 1 = KF (6)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_plane_jac(DevGraph g, DevState s) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t / 9, col = t % 9;
+  if (e >= g.n_ple) return;
+  if (g.ple_flags[e] & PPO_EF_LEVEL1_) return;
+  const int kf = g.ple_kf[e], pl = g.ple_plane[e], kind = g.ple_kind[e];
+  double meas[4], pc[4], ep[3], em[3];
+#pragma unroll
+  for (int i = 0; i < 4; i++) meas[i] = g.ple_meas[4 * e + i], pc[i] = s.pl[4 * pl + i];
+  double *J = g.ple_J + 27 * (size_t)e + 3 * col;
+  if (col < 3) {
+    double Rt[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) Rt[i] = s.kf_Rt[12 * kf + i];
+    double add[3] = {0, 0, 0}, pp[4];
+    add[col] = NUM_DELTA;
+    plane_oplus(pc, add, pp);
+    plane_edge_error(kind, pp, Rt, meas, ep);
+    add[col] = -NUM_DELTA;
+    plane_oplus(pc, add, pp);
+    plane_edge_error(kind, pp, Rt, meas, em);
+  } else {
+    if (g.kf_fixed[kf]) {
+      J[0] = J[1] = J[2] = 0;
+      return;
+    }
+    double pose[7], po[7], Rt[12], add[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 7; i++) pose[i] = s.kf_pose[7 * kf + i];
+    add[col - 3] = NUM_DELTA;
+    se3_oplus(pose, add, po);
+    pose_to_Rt(po, Rt);
+    plane_edge_error(kind, pc, Rt, meas, ep);
+    add[col - 3] = -NUM_DELTA;
+    se3_oplus(pose, add, po);
+    pose_to_Rt(po, Rt);
+    plane_edge_error(kind, pc, Rt, meas, em);
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) J[r] = NUM_SCALAR * (ep[r] - em[r]);
+}
+// residual (+ optional quadratic form) of the plane edges
+constexpr int SMALL_THREADS = 128;
+template <bool ASSEMBLE>
+__global__ void __launch_bounds__(SMALL_THREADS) k_plane_edges(DevGraph g, DevState s, double *chi_part) {
+  __shared__ double sm[SMALL_THREADS / 32];
+  const int e = blockIdx.x * SMALL_THREADS + threadIdx.x;
+  double rho0 = 0;
+  if (e < g.n_ple && !(g.ple_flags[e] & PPO_EF_LEVEL1_)) {
+    const int kf = g.ple_kf[e], pl = g.ple_plane[e], kind = g.ple_kind[e];
+    double meas[4], pc[4], Rt[12], err[3];
+#pragma unroll
+    for (int i = 0; i < 4; i++) meas[i] = g.ple_meas[4 * e + i], pc[i] = s.pl[4 * pl + i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) Rt[i] = s.kf_Rt[12 * kf + i];
+    const int D = plane_edge_error(kind, pc, Rt, meas, err);
+    double info[3] = {g.ple_info[3 * e], g.ple_info[3 * e + 1], D == 3 ? g.ple_info[3 * e + 2] : 0.0};
+    const double chi2 = err[0] * (info[0] * err[0]) + err[1] * (info[1] * err[1]) + err[2] * (info[2] * err[2]);
+    g.ple_chi2[e] = chi2;
+    rho0 = chi2;
+    double w = 1.0;
+    if (g.ple_flags[e] & PPO_EF_ROBUST_) w = huber_w(chi2, kind == 0 ? g.huber_plane : g.huber_vp, &rho0);
+    if (ASSEMBLE) {
+      double J[27];  // [col][row]
+#pragma unroll
+      for (int i = 0; i < 27; i++) J[i] = g.ple_J[27 * (size_t)e + i];
+      if (D == 2) {
+#pragma unroll
+        for (int c = 0; c < 9; c++) J[3 * c + 2] = 0;
+      }
+      double wi[3] = {w * info[0], w * info[1], w * info[2]};
+      // landmark (plane) block
+      const int q6[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        const int a = q6[i][0], b = q6[i][1];
+        atomicAdd(&g.Hll[6 * (size_t)pl + i], J[3 * a] * wi[0] * J[3 * b] + J[3 * a + 1] * wi[1] * J[3 * b + 1] + J[3 * a + 2] * wi[2] * J[3 * b + 2]);
+      }
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+        atomicAdd(&g.bl[3 * (size_t)pl + a], -(J[3 * a] * wi[0] * err[0] + J[3 * a + 1] * wi[1] * err[1] + J[3 * a + 2] * wi[2] * err[2]));
+      const int idx = g.kf_idx[kf];
+      if (idx >= 0) {
+        const double *Jk = J + 9;  // KF columns
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+#pragma unroll
+          for (int b = 0; b < 6; b++)
+            atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * a + b],
+                      Jk[3 * a] * wi[0] * Jk[3 * b] + Jk[3 * a + 1] * wi[1] * Jk[3 * b + 1] + Jk[3 * a + 2] * wi[2] * Jk[3 * b + 2]);
+          atomicAdd(&g.bp[6 * idx + a], -(Jk[3 * a] * wi[0] * err[0] + Jk[3 * a + 1] * wi[1] * err[1] + Jk[3 * a + 2] * wi[2] * err[2]));
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+            atomicAdd(&g.Hpl[18 * (size_t)g.ple_slot[e] + 3 * a + c],
+                      Jk[3 * a] * wi[0] * J[3 * c] + Jk[3 * a + 1] * wi[1] * J[3 * c + 1] + Jk[3 * a + 2] * wi[2] * J[3 * c + 2]);
+        }
+      }
+    }
+  }
+  const double t = block_sum<SMALL_THREADS>(rho0, sm);
+  if (threadIdx.x == 0) chi_part[blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera-cuboid edges (numeric): vertex 0 = KF (6), vertex 1 = cuboid (9)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_cuboid_jac(DevGraph g, DevState s) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t / 15, col = t % 15;
+  if (e >= g.n_cbe) return;
+  if (g.cbe_flags[e] & PPO_EF_LEVEL1_) return;
+  const int kf = g.cbe_kf[e], cu = g.cbe_cuboid[e], kind = g.cbe_kind[e];
+  const double *meas = g.cbe_meas + 16 * (size_t)e;
+  float intr[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) intr[i] = g.kf_intr[5 * kf + i];
+  double c[10], ep[16], em[16];
+#pragma unroll
+  for (int i = 0; i < 10; i++) c[i] = s.cu[10 * cu + i];
+  double *J = g.cbe_J + 240 * (size_t)e + 16 * col;
+  const int D = kind == 0 ? 4 : 16;
+  if (col < 6) {
+    if (g.kf_fixed[kf]) {
+      for (int r = 0; r < 16; r++) J[r] = 0;
+      return;
+    }
+    double pose[7], po[7], Rt[12], add[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 7; i++) pose[i] = s.kf_pose[7 * kf + i];
+    add[col] = NUM_DELTA;
+    se3_oplus(pose, add, po);
+    pose_to_Rt(po, Rt);
+    cuboid_cam_error(kind, Rt, c, intr, meas, ep);
+    add[col] = -NUM_DELTA;
+    se3_oplus(pose, add, po);
+    pose_to_Rt(po, Rt);
+    cuboid_cam_error(kind, Rt, c, intr, meas, em);
+  } else {
+    double Rt[12], add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, co[10];
+#pragma unroll
+    for (int i = 0; i < 12; i++) Rt[i] = s.kf_Rt[12 * kf + i];
+    const unsigned cf = g.cu_flags[cu];
+    add[col - 6] = NUM_DELTA;
+    cuboid_oplus(c, cf, add, co);
+    cuboid_cam_error(kind, Rt, co, intr, meas, ep);
+    add[col - 6] = -NUM_DELTA;
+    cuboid_oplus(c, cf, add, co);
+    cuboid_cam_error(kind, Rt, co, intr, meas, em);
+  }
+  for (int r = 0; r < 16; r++) J[r] = r < D ? NUM_SCALAR * (ep[r] - em[r]) : 0.0;
+}
+template <bool ASSEMBLE>
+__global__ void __launch_bounds__(SMALL_THREADS) k_cuboid_edges(DevGraph g, DevState s, double *chi_part) {
+  __shared__ double sm[SMALL_THREADS / 32];
+  const int e = blockIdx.x * SMALL_THREADS + threadIdx.x;
+  double rho0 = 0;
+  if (e < g.n_cbe && !(g.cbe_flags[e] & PPO_EF_LEVEL1_)) {
+    const int kf = g.cbe_kf[e], cu = g.cbe_cuboid[e], kind = g.cbe_kind[e];
+    float intr[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) intr[i] = g.kf_intr[5 * kf + i];
+    double c[10], Rt[12], err[16];
+#pragma unroll
+    for (int i = 0; i < 10; i++) c[i] = s.cu[10 * cu + i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) Rt[i] = s.kf_Rt[12 * kf + i];
+    const int D = cuboid_cam_error(kind, Rt, c, intr, g.cbe_meas + 16 * (size_t)e, err);
+    const double info = g.cbe_info[e];
+    double chi2 = 0, nrm = 0;
+    for (int r = 0; r < D; r++) chi2 += err[r] * (info * err[r]), nrm += err[r] * err[r];
+    g.cbe_chi2[e] = chi2;
+    g.cbe_norm[e] = sqrt(nrm);
+    rho0 = chi2;
+    double w = 1.0;
+    if (g.cbe_flags[e] & PPO_EF_ROBUST_) w = huber_w(chi2, kind == 0 ? g.huber_bbox : g.huber_corner, &rho0);
+    if (ASSEMBLE) {
+      const double wi = w * info;
+      const double *J = g.cbe_J + 240 * (size_t)e;  // [col][row16]
+      const int idx = g.kf_idx[kf], off = g.cu_off[cu];
+      const int a0 = idx >= 0 ? 0 : 6;
+      for (int a = a0; a < 15; a++) {
+        double ga = 0;
+        for (int r = 0; r < D; r++) ga += J[16 * a + r] * err[r];
+        ga *= -wi;
+        if (a < 6) atomicAdd(&g.bp[6 * idx + a], ga);
+        else atomicAdd(&g.bp[off + a - 6], ga);
+        for (int b = (a < 6 ? a0 : 6); b < 15; b++) {
+          if (a >= 6 && b < 6) continue;
+          double h = 0;
+          for (int r = 0; r < D; r++) h += J[16 * a + r] * J[16 * b + r];
+          h *= wi;
+          if (a < 6 && b < 6) atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * a + b], h);
+          else if (a < 6) g.Hpc[54 * (size_t)e + 9 * a + (b - 6)] = h;
+          else atomicAdd(&g.Hpp_cu[81 * (size_t)cu + 9 * (a - 6) + (b - 6)], h);
+        }
+      }
+    }
+  }
+  const double t = block_sum<SMALL_THREADS>(rho0, sm);
+  if (threadIdx.x == 0) chi_part[blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// point-cuboid unary edges (numeric, base_unary_edge.hpp:81-123)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_ptcu_jac(DevGraph g, DevState s) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t / 9, col = t % 9;
+  if (e >= g.n_pce) return;
+  if (g.pce_flags[e] & PPO_EF_LEVEL1_) return;
+  const int cu = g.pce_cuboid[e];
+  double c[10], co[10], ep[3], em[3], add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 10; i++) c[i] = s.cu[10 * cu + i];
+  const double *pts = g.pce_pts + 3 * (size_t)g.pce_rowptr[e];
+  const int n = g.pce_rowptr[e + 1] - g.pce_rowptr[e];
+  const unsigned cf = g.cu_flags[cu];
+  add[col] = NUM_DELTA;
+  cuboid_oplus(c, cf, add, co);
+  point_cuboid_error(co, pts, n, g.ptcu_ratio, g.ptcu_prior, ep);
+  add[col] = -NUM_DELTA;
+  cuboid_oplus(c, cf, add, co);
+  point_cuboid_error(co, pts, n, g.ptcu_ratio, g.ptcu_prior, em);
+  double *J = g.pce_J + 27 * (size_t)e + 3 * col;
+#pragma unroll
+  for (int r = 0; r < 3; r++) J[r] = NUM_SCALAR * (ep[r] - em[r]);
+}
+template <bool ASSEMBLE>
+__global__ void __launch_bounds__(SMALL_THREADS) k_ptcu_edges(DevGraph g, DevState s, double *chi_part) {
+  __shared__ double sm[SMALL_THREADS / 32];
+  const int e = blockIdx.x * SMALL_THREADS + threadIdx.x;
+  double rho0 = 0;
+  if (e < g.n_pce && !(g.pce_flags[e] & PPO_EF_LEVEL1_)) {
+    const int cu = g.pce_cuboid[e];
+    double c[10], err[3];
+#pragma unroll
+    for (int i = 0; i < 10; i++) c[i] = s.cu[10 * cu + i];
+    point_cuboid_error(c, g.pce_pts + 3 * (size_t)g.pce_rowptr[e], g.pce_rowptr[e + 1] - g.pce_rowptr[e], g.ptcu_ratio, g.ptcu_prior, err);
+    const double chi2 = err[0] * err[0] + err[1] * err[1] + err[2] * err[2];  // information = I (Optimizer.cc:2644-2646)
+    g.pce_chi2[e] = chi2;
+    rho0 = chi2;
+    double w = 1.0;
+    if (g.pce_flags[e] & PPO_EF_ROBUST_) w = huber_w(chi2, 1.0, &rho0);
+    if (ASSEMBLE) {
+      const double *J = g.pce_J + 27 * (size_t)e;
+      const int off = g.cu_off[cu];
+      for (int a = 0; a < 9; a++) {
+        atomicAdd(&g.bp[off + a], -w * (J[3 * a] * err[0] + J[3 * a + 1] * err[1] + J[3 * a + 2] * err[2]));
+        for (int b = 0; b < 9; b++)
+          atomicAdd(&g.Hpp_cu[81 * (size_t)cu + 9 * a + b], w * (J[3 * a] * J[3 * b] + J[3 * a + 1] * J[3 * b + 1] + J[3 * a + 2] * J[3 * b + 2]));
+      }
+    }
+  }
+  const double t = block_sum<SMALL_THREADS>(rho0, sm);
+  if (threadIdx.x == 0) chi_part[blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Schur complement (BlockSolver::solve, core/block_solver.hpp:376-431) with lambda on the diagonal of
+// Hll as setLambda adds it (:582-587).  S is zero on entry; k_compose adds Hpp afterwards.
+// Work unit = (landmark, first-block stride): small landmarks take one warp, big ones a whole CTA.
+// ---------------------------------------------------------------------------------------------
+PPO_D void inv_sym3(const double h[6], double lam, double d[6]) {
+  const double a = h[0] + lam, b = h[1], c = h[2], e = h[3] + lam, f = h[4], i = h[5] + lam;
+  const double c00 = e * i - f * f, c01 = f * c - b * i, c02 = b * f - e * c;
+  const double det = a * c00 + b * c01 + c * c02;
+  const double id = 1.0 / det;
+  d[0] = c00 * id;
+  d[1] = (c * f - b * i) * id;
+  d[2] = (b * f - c * e) * id;
+  d[3] = (a * i - c * c) * id;
+  d[4] = (c * b - a * f) * id;
+  d[5] = (a * e - b * b) * id;
+}
+PPO_D bool landmark_active(const DevGraph &g, int L) {
+  return L < g.n_pl ? g.pl_act[L] != 0 : (g.pt_act[L - g.n_pl] != 0 && !g.pt_fixed[L - g.n_pl]);
+}
+constexpr int SCHUR_WARPS = 8;
+// lm_list: landmarks handled by this launch; WHOLE_CTA: one landmark per CTA instead of per warp
+template <bool WHOLE_CTA>
+__global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const int *lm_list, int n_list, double lambda, int n_p, int ld) {
+  __shared__ double bd[SCHUR_WARPS][18];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int li = WHOLE_CTA ? blockIdx.x : blockIdx.x * SCHUR_WARPS + warp;
+  if (li >= n_list) return;
+  const int L = lm_list ? lm_list[li] : li;
+  if (!landmark_active(g, L)) return;
+  double h[6], D[6], bl[3], db[3];
+#pragma unroll
+  for (int i = 0; i < 6; i++) h[i] = g.Hll[6 * (size_t)L + i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) bl[i] = g.bl[3 * (size_t)L + i];
+  inv_sym3(h, lambda, D);
+  db[0] = D[0] * bl[0] + D[1] * bl[1] + D[2] * bl[2];
+  db[1] = D[1] * bl[0] + D[3] * bl[1] + D[4] * bl[2];
+  db[2] = D[2] * bl[0] + D[4] * bl[1] + D[5] * bl[2];
+  if (lane == 0 && (!WHOLE_CTA || warp == 0)) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) g.Dinv[6 * (size_t)L + i] = D[i];
+  }
+  const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
+  const int step = WHOLE_CTA ? SCHUR_WARPS : 1;
+  for (int i1 = b0 + (WHOLE_CTA ? warp : 0); i1 < b1; i1 += step) {
+    const int p1 = g.ent_pidx[i1];
+    if (p1 < 0) continue;  // warp-uniform
+    const double *W1 = g.Hpl + 18 * (size_t)i1;
+    // BD = W1 * Dinv (6 x 3), one lane per entry
+    __syncwarp();
+    if (lane < 18) {
+      const int r = lane / 3, c = lane % 3;
+      const double dc0 = c == 0 ? D[0] : (c == 1 ? D[1] : D[2]);
+      const double dc1 = c == 0 ? D[1] : (c == 1 ? D[3] : D[4]);
+      const double dc2 = c == 0 ? D[2] : (c == 1 ? D[4] : D[5]);
+      bd[warp][lane] = W1[3 * r] * dc0 + W1[3 * r + 1] * dc1 + W1[3 * r + 2] * dc2;
+    }
+    __syncwarp();
+    if (lane < 6)  // reduced gradient: bschur_i -= W1 * Dinv * bl   (coefficients, :403-405)
+      atomicAdd(&g.S[(size_t)(6 * p1 + lane) * ld + n_p], -(W1[3 * lane] * db[0] + W1[3 * lane + 1] * db[1] + W1[3 * lane + 2] * db[2]));
+    const int n_items = (b1 - i1) * 36;
+    for (int it = lane; it < n_items; it += 32) {
+      const int i2 = i1 + it / 36, en = it % 36;
+      const int p2 = g.ent_pidx[i2];
+      if (p2 < 0) continue;
+      const int r = en / 6, c = en % 6;
+      const double *W2 = g.Hpl + 18 * (size_t)i2 + 3 * c;
+      const double v = bd[warp][3 * r] * W2[0] + bd[warp][3 * r + 1] * W2[1] + bd[warp][3 * r + 2] * W2[2];
+      // keep the upper block triangle (row-major): (p1,p2) if p1 <= p2 else the transposed entry
+      size_t row, colx;
+      if (p1 <= p2) row = 6 * (size_t)p1 + r, colx = 6 * (size_t)p2 + c;
+      else row = 6 * (size_t)p2 + c, colx = 6 * (size_t)p1 + r;
+      if (p1 == p2 && i1 != i2) {
+        // two different entries on the same key-frame: W1 D W2^T + W2 D W1^T lands on one diagonal block
+        atomicAdd(&g.S[(6 * (size_t)p1 + r) * ld + 6 * p1 + c], -v);
+        atomicAdd(&g.S[(6 * (size_t)p1 + c) * ld + 6 * p1 + r], -v);
+      } else {
+        atomicAdd(&g.S[row * ld + colx], -v);
+      }
+    }
+  }
+}
+// S += Hpp (+ lambda on the diagonal), rhs column += bp.  One thread per scalar of each block.
+__global__ void k_compose(DevGraph g, double lambda, int n_p, int ld) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nkf = g.n_kf * 36, ncu = g.n_cu * 81, nhpc = g.n_cbe * 54;
+  if (t < nkf) {
+    const int kf = t / 36, a = (t % 36) / 6, b = t % 6;
+    const int idx = g.kf_idx[kf];
+    if (idx >= 0 && a <= b) {
+      double v = g.Hpp_kf[36 * (size_t)idx + 6 * a + b];
+      if (a == b) v += lambda;
+      atomicAdd(&g.S[(size_t)(6 * idx + a) * ld + 6 * idx + b], v);
+    }
+  } else if (t < nkf + ncu) {
+    const int u = t - nkf, cu = u / 81, a = (u % 81) / 9, b = u % 9;
+    const int off = g.cu_off[cu];
+    if (off >= 0 && a <= b) {
+      double v = g.Hpp_cu[81 * (size_t)cu + 9 * a + b];
+      if (a == b) v += lambda;
+      atomicAdd(&g.S[(size_t)(off + a) * ld + off + b], v);
+    }
+  } else if (t < nkf + ncu + nhpc) {
+    const int u = t - nkf - ncu, e = u / 54, a = (u % 54) / 9, b = u % 9;
+    if (!(g.cbe_flags[e] & PPO_EF_LEVEL1_)) {
+      const int idx = g.kf_idx[g.cbe_kf[e]], off = g.cu_off[g.cbe_cuboid[e]];
+      if (idx >= 0 && off >= 0) atomicAdd(&g.S[(size_t)(6 * idx + a) * ld + off + b], g.Hpc[54 * (size_t)e + 9 * a + b]);
+    }
+  } else if (t < nkf + ncu + nhpc + n_p) {
+    const int j = t - nkf - ncu - nhpc;
+    atomicAdd(&g.S[(size_t)j * ld + n_p], g.bp[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// back-substitution  xl = Dinv (bl - Hpl^T xp)   (core/block_solver.hpp:459-481) + landmark part of
+// computeScale (levenberg.cpp:182-189).  One warp per landmark, lanes stride the contiguous blocks.
+// ---------------------------------------------------------------------------------------------
+constexpr int BS_WARPS = 8;
+__global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double lambda, double *scale_part) {
+  __shared__ double wsum[BS_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = blockIdx.x * BS_WARPS + warp;
+  double sc = 0;
+  if (L < g.n_lm) {
+    if (landmark_active(g, L)) {
+      const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
+      double c[3] = {0, 0, 0};
+      const int n = (b1 - b0) * 18;
+      const double *W = g.Hpl + 18 * (size_t)b0;
+      for (int i = lane; i < n; i += 32) {
+        const int ent = b0 + i / 18, a = (i % 18) / 3, col = i % 3;
+        const int p = g.ent_pidx[ent];
+        if (p >= 0) {
+          const double t = W[i] * g.xp[6 * p + a];
+          if (col == 0) c[0] += t;
+          else if (col == 1) c[1] += t;
+          else c[2] += t;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) c[k] = warp_sum(c[k]);
+      if (lane == 0) {
+        double D[6], bl[3], cl[3], x[3];
+#pragma unroll
+        for (int i = 0; i < 6; i++) D[i] = g.Dinv[6 * (size_t)L + i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) bl[i] = g.bl[3 * (size_t)L + i], cl[i] = bl[i] - c[i];
+        x[0] = D[0] * cl[0] + D[1] * cl[1] + D[2] * cl[2];
+        x[1] = D[1] * cl[0] + D[3] * cl[1] + D[4] * cl[2];
+        x[2] = D[2] * cl[0] + D[4] * cl[1] + D[5] * cl[2];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          g.xl[3 * (size_t)L + i] = x[i];
+          sc += x[i] * (lambda * x[i] + bl[i]);
+        }
+      }
+    } else if (lane < 3) {
+      g.xl[3 * (size_t)L + lane] = 0.0;
+    }
+  }
+  if (lane == 0) wsum[warp] = sc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < BS_WARPS; i++) t += wsum[i];
+    scale_part[blockIdx.x] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SparseOptimizer::update (core/sparse_optimizer.cpp:422-435): trial = cur (+) x
+// ---------------------------------------------------------------------------------------------
+__global__ void k_update(DevGraph g, DevState cur, DevState tr) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < g.n_kf) {
+    double p[7], o[7], Rt[12];
+#pragma unroll
+    for (int i = 0; i < 7; i++) p[i] = cur.kf_pose[7 * t + i];
+    const int idx = g.kf_idx[t];
+    if (idx >= 0) {
+      double u[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) u[i] = g.xp[6 * idx + i];
+      se3_oplus(p, u, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 7; i++) o[i] = p[i];
+    }
+    pose_to_Rt(o, Rt);
+#pragma unroll
+    for (int i = 0; i < 7; i++) tr.kf_pose[7 * t + i] = o[i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) tr.kf_Rt[12 * t + i] = Rt[i];
+    return;
+  }
+  t -= g.n_kf;
+  if (t < g.n_cu) {
+    double c[10], o[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) c[i] = cur.cu[10 * t + i];
+    const int off = g.cu_off[t];
+    if (off >= 0) {
+      double u[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) u[i] = g.xp[off + i];
+      cuboid_oplus(c, g.cu_flags[t], u, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 10; i++) o[i] = c[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 10; i++) tr.cu[10 * t + i] = o[i];
+    return;
+  }
+  t -= g.n_cu;
+  if (t < g.n_pl) {
+    double c[4], o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) c[i] = cur.pl[4 * t + i];
+    if (g.pl_act[t]) {
+      const double v[3] = {g.xl[3 * (size_t)t], g.xl[3 * (size_t)t + 1], g.xl[3 * (size_t)t + 2]};
+      plane_oplus(c, v, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) o[i] = c[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) tr.pl[4 * t + i] = o[i];
+    return;
+  }
+  t -= g.n_pl;
+  if (t < g.n_pt) {
+    const bool act = g.pt_act[t] && !g.pt_fixed[t];
+    const size_t L = (size_t)g.n_pl + t;
+#pragma unroll
+    for (int i = 0; i < 3; i++) tr.pt[3 * (size_t)t + i] = cur.pt[3 * (size_t)t + i] + (act ? g.xl[3 * L + i] : 0.0);
+  }
+}
+// kf_Rt cache from kf_pose (after set_graph / reset)
+__global__ void k_pose_cache(int n_kf, const double *pose, double *Rt) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_kf) return;
+  double p[7], r[12];
+#pragma unroll
+  for (int i = 0; i < 7; i++) p[i] = pose[7 * t + i];
+  pose_to_Rt(p, r);
+#pragma unroll
+  for (int i = 0; i < 12; i++) Rt[12 * t + i] = r[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalars
+// ---------------------------------------------------------------------------------------------
+struct Scalars {
+  double chi2;      // active robust chi2
+  double scale;     // computeScale
+  double max_diag;  // for computeLambdaInit
+  int not_spd;
+  int pad;
+};
+// sums partial arrays in a fixed order; single block
+__global__ void k_scalars(DevGraph g, Scalars *out, const double *chi_a, int na, const double *chi_b, int nb, const double *chi_c, int nc,
+                          const double *chi_d, int nd, double chi_const, const double *scale_part, int ns, double lambda, int n_p,
+                          const int *not_spd) {
+  __shared__ double sm[8];
+  double c = 0, s = 0;
+  for (int i = threadIdx.x; i < na; i += 256) c += chi_a[i];
+  for (int i = threadIdx.x; i < nb; i += 256) c += chi_b[i];
+  for (int i = threadIdx.x; i < nc; i += 256) c += chi_c[i];
+  for (int i = threadIdx.x; i < nd; i += 256) c += chi_d[i];
+  for (int i = threadIdx.x; i < ns; i += 256) s += scale_part[i];
+  for (int i = threadIdx.x; i < n_p; i += 256) s += g.xp[i] * (lambda * g.xp[i] + g.bp[i]);
+  c = block_sum<256>(c, sm);
+  s = block_sum<256>(s, sm);
+  if (threadIdx.x == 0) {
+    out->chi2 = c + chi_const;
+    out->scale = s;
+    out->not_spd = not_spd ? *not_spd : 0;
+  }
+}
+// max |diagonal| over the active blocks (computeLambdaInit, levenberg.cpp:166-180); single block
+__global__ void k_max_diag(DevGraph g, Scalars *out) {
+  __shared__ double sm[256];
+  double m = 0;
+  const int nb = g.dims[0];
+  for (int i = threadIdx.x; i < nb * 6; i += 256) m = fmax(m, fabs(g.Hpp_kf[36 * (size_t)(i / 6) + 7 * (i % 6)]));
+  for (int i = threadIdx.x; i < g.n_cu * 9; i += 256)
+    if (g.cu_off[i / 9] >= 0) m = fmax(m, fabs(g.Hpp_cu[81 * (size_t)(i / 9) + 10 * (i % 9)]));
+  for (int i = threadIdx.x; i < g.n_lm * 3; i += 256) {
+    const int L = i / 3, j = i % 3;
+    m = fmax(m, fabs(g.Hll[6 * (size_t)L + (j == 0 ? 0 : (j == 1 ? 3 : 5))]));
+  }
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out->max_diag = sm[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// outlier pass (Optimizer.cc:2736-2833) and depth test
+// ---------------------------------------------------------------------------------------------
+__global__ void k_outlier_pass(DevGraph g, DevState s, double chi2_mono, double chi2_stereo, double chi2_plane, double chi2_vp,
+                               double norm_bbox, double norm_corner, int *n_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.n_pe) {
+    const PointEdgeRec rec = g.pe_rec[i];
+    const int pt = g.pe_pt[i];
+    const double z = s.kf_Rt[12 * rec.kf + 6] * s.pt[3 * pt] + s.kf_Rt[12 * rec.kf + 7] * s.pt[3 * pt + 1] +
+                     s.kf_Rt[12 * rec.kf + 8] * s.pt[3 * pt + 2] + s.kf_Rt[12 * rec.kf + 11];
+    unsigned fl = g.pe_flags[i];
+    if (g.pe_chi2[i] > (rec.ur < 0.f ? chi2_mono : chi2_stereo) || !(z > 0.0)) {
+      if (!(fl & PPO_EF_LEVEL1_)) atomicAdd(&n_out[0], 1);
+      fl |= PPO_EF_LEVEL1_;
+    }
+    fl &= ~PPO_EF_ROBUST_;
+    g.pe_flags[i] = (uint8_t)fl;
+  }
+  if (i < g.n_cbe) {
+    unsigned fl = g.cbe_flags[i];
+    if (g.cbe_norm[i] > (g.cbe_kind[i] == 0 ? norm_bbox : norm_corner)) {
+      if (!(fl & PPO_EF_LEVEL1_)) atomicAdd(&n_out[2], 1);
+      fl |= PPO_EF_LEVEL1_;
+    }
+    g.cbe_flags[i] = (uint8_t)fl;
+  }
+  if (i < g.n_ple) {
+    unsigned fl = g.ple_flags[i];
+    if (g.ple_chi2[i] > (g.ple_kind[i] == 0 ? chi2_plane : chi2_vp)) {
+      if (!(fl & PPO_EF_LEVEL1_)) atomicAdd(&n_out[1], 1);
+      fl |= PPO_EF_LEVEL1_;
+    }
+    fl &= ~PPO_EF_ROBUST_;
+    g.ple_flags[i] = (uint8_t)fl;
+  }
+}
+__global__ void k_depth_flags(DevGraph g, DevState s, int kind, unsigned char *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (kind == 0 && i < g.n_pe) {
+    const int kf = g.pe_rec[i].kf, pt = g.pe_pt[i];
+    double p[3], X[3] = {s.pt[3 * pt], s.pt[3 * pt + 1], s.pt[3 * pt + 2]};
+    double q[4] = {s.kf_pose[7 * kf], s.kf_pose[7 * kf + 1], s.kf_pose[7 * kf + 2], s.kf_pose[7 * kf + 3]};
+    quat_rot(q, X, p);
+    out[i] = (p[2] + s.kf_pose[7 * kf + 6]) > 0.0;
+  }
+  if (kind == 1 && i < g.n_ple) {  // EdgePlane::isDepthPositive, G2O_Plane3D.h:199-209
+    double l[4], pc[4], Rt[12];
+    for (int k = 0; k < 4; k++) pc[k] = s.pl[4 * g.ple_plane[i] + k];
+    for (int k = 0; k < 12; k++) Rt[k] = s.kf_Rt[12 * g.ple_kf[i] + k];
+    plane_transform(Rt, pc, l);
+    out[i] = (-l[3]) > 0;
+  }
+}
+
+}  // namespace ppo

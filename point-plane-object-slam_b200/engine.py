@@ -56,6 +56,9 @@ def load_library():
         lib.ppo_ba_launch_count.argtypes = [C.c_void_p]
         lib.ppo_ba_launch_count.restype = C.c_longlong
         lib.ppo_ba_time_assembly.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.ppo_ba_mark.argtypes = [C.c_void_p, C.c_int]
+        lib.ppo_ba_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        lib.ppo_ba_flush_l2.argtypes = [C.c_void_p]
         lib.ppo_ba_set_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.ppo_ba_debug_linearize.argtypes = [C.c_void_p, C.POINTER(C.c_int32 * 2), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ppo_ba_debug_solve.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
@@ -194,6 +197,17 @@ class LocalBA(Handle):
         ms, by = C.c_double(), C.c_double()
         self._check(self.lib.ppo_ba_time_assembly(self.h, reps, C.byref(ms), C.byref(by)), "time_assembly")
         return ms.value, by.value
+
+    def mark(self, which):
+        self._check(self.lib.ppo_ba_mark(self.h, which), "mark")
+
+    def elapsed_ms(self):
+        ms = C.c_double()
+        self._check(self.lib.ppo_ba_elapsed_ms(self.h, C.byref(ms)), "elapsed_ms")
+        return ms.value
+
+    def flush_l2(self):
+        self._check(self.lib.ppo_ba_flush_l2(self.h), "flush_l2")
 
     # reference-named entry points ---------------------------------------------------------------
     def LocalBACameraPlaneCuboids(self, graph, stop_flag=None):
