@@ -7,6 +7,11 @@
 // 0..n-1 and the reduced gradient in column n; read column-major it is the LOWER triangle with the
 // gradient as an extra row n.  Factoring the lower triangle while carrying row n through the panel
 // solves and trailing updates turns row n into y = L^-1 b (forward substitution for free).
+//
+// Per 64-column panel:  k_potrf_inv   (1 CTA)   L_kk = chol(A_kk) and W_kk = L_kk^-1
+//                       k_panel_gemm  (rows/64) A_ik <- A_ik W_kk^T           (TRSM as a GEMM)
+//                       k_syrk_update (tiles)   A_ij -= A_ik A_jk^T           (FP64 tensor cores, DMMA)
+// then per 64-block, last to first:  k_backsolve_step   x_B = W_BB^T y_B ; y_A -= L_BA^T x_B
 #include <cuda_runtime.h>
 
 #include "ppo_dense.h"
@@ -17,68 +22,156 @@ constexpr int NB = 64;  // panel width
 
 #define A_(i, j) S[(size_t)(j) * ld + (i)]
 
-// --- diagonal block: unblocked Cholesky of an nb x nb block in shared memory -----------------------
-__global__ void __launch_bounds__(256) k_potrf_diag(double *S, int ld, int k, int nb, int *not_spd) {
-  __shared__ double a[NB][NB + 1];
+// --- diagonal block: Cholesky + explicit inverse of the 64 x 64 factor --------------------------------
+// Gaussian elimination of [A | I] without scaling: A ends as L_u D (unit-lower factor times pivots), the
+// identity part as X = L_u^-1; then L = L_u D^1/2 and W = L^-1 = D^-1/2 X.
+// 128 threads: thread (i, h) keeps 32 entries of row i (columns c = h + 2 q) in REGISTERS.  Register V[c]
+// holds A(i,c) until column c is eliminated; at step j = c the finished L(i,j) is written out and the register
+// is recycled for X(i,j).  Per column only one 64-vector travels through (double-buffered) shared memory:
+// vec[r] = A(r,j) for r > j and vec[c] = X(j,c) for c < j.  One barrier and one reciprocal per column.
+constexpr int PF_THREADS = 128;
+__global__ void __launch_bounds__(PF_THREADS) k_potrf_inv(double *S, int ld, int k, int nb, double *Winv, int *not_spd) {
+  __shared__ double vec[2][NB];
+  __shared__ double rinv[NB];         // 1 / d_j
+  __shared__ double Lu[NB][NB + 1];   // finished columns A(i,j) = L_u(i,j) d_j, scaled and written out after the loop
   const int tid = threadIdx.x;
-  for (int t = tid; t < nb * nb; t += 256) {
-    const int i = t % nb, j = t / nb;
-    a[i][j] = (i >= j) ? A_(k + i, k + j) : 0.0;
+  const int i = tid & 63, h = tid >> 6;
+  double V[32];
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    const int c = h + 2 * q;
+    V[q] = (i < nb && c < nb && i >= c) ? A_(k + i, k + c) : (i == c ? 1.0 : 0.0);
+  }
+  if (h == 0) {
+    vec[0][i] = V[0];
+    if (i == 0) {
+      double d = V[0];
+      if (!(d > 0.0)) {
+        *not_spd = 1;
+        d = 1.0;
+      }
+      rinv[0] = __drcp_rn(d);
+    }
+  }
+  for (int j = 0; j < NB; j++) {
+    __syncthreads();
+    if ((i | 31) < j) continue;  // all rows of this warp are final (warp-uniform)
+    const int cur = j & 1, nxt = cur ^ 1;
+    if (i >= j) {
+      const double rj = rinv[j];
+      const double aij = vec[cur][i];
+      const double f = aij * rj;  // L_u(i,j)
+      const bool below = i > j;
+      const double xj = below ? -f : 1.0;  // X(i,j) ; X(j,j) = 1
+      const bool rownext = i == j + 1;
+      // all operand loads first (the stores below alias the same shared array and would serialise them)
+      double T[32];
+#pragma unroll
+      for (int q = 0; q < 32; q++) T[q] = vec[cur][h + 2 * q];
+      // lean, fully predicated update (c is warp-uniform for a given q)
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const int c = h + 2 * q;
+        const double upd = V[q] - f * T[q];
+        V[q] = (c == j) ? xj : ((below && c <= i) ? upd : V[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const int c = h + 2 * q;
+        if (below && c == j + 1) vec[nxt][i] = V[q];   // A(i, j+1): operand column of the next step
+        if (rownext && c <= j) vec[nxt][c] = V[q];     // X(j+1, c): row j+1 is final after this step
+      }
+      if (h == (j & 1)) Lu[i][j] = aij;  // finished column j (kept unscaled: no sqrt / divide inside the loop)
+      if (rownext && h == ((j + 1) & 1)) {  // next pivot (this thread stored vec[nxt][j+1] itself)
+        double d = vec[nxt][j + 1];
+        if (!(d > 0.0)) {
+          *not_spd = 1;
+          d = 1.0;
+        }
+        rinv[j + 1] = __drcp_rn(d);
+      }
+    }
   }
   __syncthreads();
-  for (int j = 0; j < nb; j++) {
-    double d = a[j][j];
-    __syncthreads();
-    if (!(d > 0.0)) {
-      if (tid == 0) *not_spd = 1;
-      d = 1.0;
+  const double rsi = sqrt(rinv[i]);
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    const int c = h + 2 * q;
+    Winv[(size_t)c * NB + i] = c <= i ? V[q] * rsi : 0.0;  // W(i,c) = X(i,c) / sqrt(d_i)
+    if (i < nb && c < nb && i >= c) {                     // L(i,c) = A(i,c) / sqrt(d_c) ; L(c,c) = sqrt(d_c)
+      const double rsc = sqrt(rinv[c]);
+      A_(k + i, k + c) = i > c ? Lu[i][c] * rsc : 1.0 / rsc;
     }
-    const double s = sqrt(d);
-    if (tid == 0) a[j][j] = s;
-    for (int i = j + 1 + tid; i < nb; i += 256) a[i][j] /= s;
-    __syncthreads();
-    // trailing rank-1 update of the lower triangle
-    const int m = nb - j - 1;
-    for (int t = tid; t < m * m; t += 256) {
-      const int i = j + 1 + t % m, c = j + 1 + t / m;
-      if (i >= c) a[i][c] -= a[i][j] * a[c][j];
-    }
-    __syncthreads();
-  }
-  for (int t = tid; t < nb * nb; t += 256) {
-    const int i = t % nb, j = t / nb;
-    if (i >= j) A_(k + i, k + j) = a[i][j];
   }
 }
 
-// --- panel: X = A(rows, k:k+nb) * L^-T, one row per thread -------------------------------------------
-constexpr int TRSM_ROWS = 32;
-__global__ void __launch_bounds__(TRSM_ROWS) k_trsm_panel(double *S, int ld, int k, int nb, int n_rows_total) {
-  __shared__ double L[NB][NB];  // reads are warp-wide broadcasts: no padding needed (keeps static smem at 48 KB)
-  __shared__ double xs[NB][TRSM_ROWS];
-  const int tid = threadIdx.x;
-  for (int t = tid; t < nb * nb; t += TRSM_ROWS) {
-    const int i = t % nb, j = t / nb;
-    L[i][j] = (i >= j) ? A_(k + i, k + j) : 0.0;
-  }
-  __syncthreads();
-  const int i = k + nb + blockIdx.x * TRSM_ROWS + tid;
-  if (i >= n_rows_total) return;
-  for (int j = 0; j < nb; j++) {
-    double v = A_(i, k + j);
-    for (int m = 0; m < j; m++) v -= xs[m][tid] * L[j][m];
-    v /= L[j][j];
-    xs[j][tid] = v;
-    A_(i, k + j) = v;
-  }
+// --- 64 x 64 output tile of  C = sum_m A(i,m) B(j,m)  on the FP64 tensor cores ---------------------------
+// mma.sync.aligned.m8n8k4.row.col.f64: A fragment a[row = lane/4][k = lane%4], B fragment b[k = lane%4][col = lane/4],
+// C fragment c0,c1 = C[row = lane/4][col = 2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-
-// --- trailing update: C(i,j) -= sum_m P(i,m) P(j,m) over 64x64 tiles of the lower triangle -----------
 constexpr int TS = 64;
-__global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, int nb, int n, int n_tiles_side) {
-  constexpr int KC = 32;  // panel columns staged per pass (2 x 16 KB of shared memory)
-  __shared__ __align__(16) double Pi[KC][TS];
-  __shared__ __align__(16) double Pj[KC][TS];
+constexpr int KC = 32;       // K staged per pass
+constexpr int SLD = TS + 4;  // padded leading dimension of the staged tiles (bank-conflict-free fragment loads)
+// 8 warps; warp w owns rows 8w..8w+7 of the tile and all 64 columns (8 DMMA column blocks).
+// sA[m][r] = A(i0 + r, m), sB[m][r] = B(j0 + r, m)
+__device__ __forceinline__ void tile_mma(const double (*sA)[SLD], const double (*sB)[SLD], int mc, double acc[8][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = warp * 8 + (lane >> 2), kk = lane & 3;
+  for (int m0 = 0; m0 < mc; m0 += 4) {
+    const double a = sA[m0 + kk][row];
+#pragma unroll
+    for (int nbk = 0; nbk < 8; nbk++) {
+      const double b = sB[m0 + kk][nbk * 8 + (lane >> 2)];
+      dmma(acc[nbk][0], acc[nbk][1], a, b);
+    }
+  }
+}
+
+// --- panel: X = A(rows, k:k+nb) * W^T  (W = inverse of the diagonal factor) --------------------------------
+__global__ void __launch_bounds__(256) k_panel_gemm(double *S, int ld, int k, int nb, int n_rows_total, const double *Winv) {
+  __shared__ double sA[KC][SLD];
+  __shared__ double sB[KC][SLD];
+  const int i0 = k + nb + blockIdx.x * TS;
+  const int tid = threadIdx.x;
+  double acc[8][2];
+#pragma unroll
+  for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
+  for (int m0 = 0; m0 < nb; m0 += KC) {
+    const int mc = min(KC, nb - m0);
+    __syncthreads();
+    {
+      const int r = tid % TS, mb = tid / TS;  // 8 independent loads per operand in flight
+      double ra[KC / 4], rb[KC / 4];
+#pragma unroll
+      for (int q = 0; q < KC / 4; q++) {
+        const int m = mb + 4 * q;
+        ra[q] = (m < mc && i0 + r < n_rows_total) ? A_(i0 + r, k + m0 + m) : 0.0;
+        rb[q] = (m < mc) ? Winv[(size_t)(m0 + m) * NB + r] : 0.0;  // W(j = r, m)
+      }
+#pragma unroll
+      for (int q = 0; q < KC / 4; q++) sA[mb + 4 * q][r] = ra[q], sB[mb + 4 * q][r] = rb[q];
+    }
+    __syncthreads();
+    tile_mma(sA, sB, (mc + 3) & ~3, acc);
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+  const int i = i0 + warp * 8 + (lane >> 2);
+  if (i < n_rows_total) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int j = q * 8 + 2 * (lane & 3);
+      if (j < nb) A_(i, k + j) = acc[q][0];
+      if (j + 1 < nb) A_(i, k + j + 1) = acc[q][1];
+    }
+  }
+}
+
+// --- trailing update: C(i,j) -= sum_m P(i,m) P(j,m) over 64x64 tiles of the lower triangle ----------------
+__global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, int nb, int n) {
+  __shared__ double sA[KC][SLD];
+  __shared__ double sB[KC][SLD];
   // map linear block id -> (bi, bj), bj <= bi
   int bid = blockIdx.x, bi = 0;
   while (bid >= bi + 1) {
@@ -89,102 +182,124 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
   const int k2 = k + nb;
   const int i0 = k2 + bi * TS, j0 = k2 + bj * TS;
   const int tid = threadIdx.x;
-  const int tr = tid % 16, tc = tid / 16;
-  double acc[4][4];
+  double acc[8][2];
 #pragma unroll
-  for (int a = 0; a < 4; a++)
-#pragma unroll
-    for (int b = 0; b < 4; b++) acc[a][b] = 0;
+  for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
   for (int m0 = 0; m0 < nb; m0 += KC) {
     const int mc = min(KC, nb - m0);
     __syncthreads();
-    for (int t = tid; t < mc * TS; t += 256) {
-      const int r = t % TS, m = t / TS;
-      Pi[m][r] = (i0 + r <= n) ? A_(i0 + r, k + m0 + m) : 0.0;
-      Pj[m][r] = (j0 + r <= n) ? A_(j0 + r, k + m0 + m) : 0.0;
-    }
-    __syncthreads();
-    for (int m = 0; m < mc; m++) {
-      const double2 r01 = *reinterpret_cast<const double2 *>(&Pi[m][tr * 4]);
-      const double2 r23 = *reinterpret_cast<const double2 *>(&Pi[m][tr * 4 + 2]);
-      const double2 c01 = *reinterpret_cast<const double2 *>(&Pj[m][tc * 4]);
-      const double2 c23 = *reinterpret_cast<const double2 *>(&Pj[m][tc * 4 + 2]);
-      const double rv[4] = {r01.x, r01.y, r23.x, r23.y}, cv[4] = {c01.x, c01.y, c23.x, c23.y};
+    {
+      const int r = tid % TS, mb = tid / TS;
+      double ra[KC / 4], rb[KC / 4];
 #pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] += rv[a] * cv[b];
-    }
-  }
-#pragma unroll
-  for (int b = 0; b < 4; b++) {
-    const int j = j0 + tc * 4 + b;
-    if (j >= n) continue;  // column n does not exist (row n is the carried gradient)
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-      const int i = i0 + tr * 4 + a;
-      if (i <= n && i >= j) A_(i, j) -= acc[a][b];
-    }
-  }
-  (void)n_tiles_side;
-}
-
-// --- back substitution L^T x = y (y = row n), single CTA ---------------------------------------------
-__global__ void __launch_bounds__(1024) k_backsolve(const double *S, int ld, int n, double *x) {
-  __shared__ double Lb[NB][NB + 1];
-  __shared__ double rhs[NB];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nblk = (n + NB - 1) / NB;
-  for (int b = nblk - 1; b >= 0; b--) {
-    const int b0 = b * NB, nb = min(NB, n - b0), tail = b0 + nb;
-    // rhs_i = y_i - sum_{m >= tail} L(m, i) x_m   : one warp per column i, coalesced along m
-    for (int ii = warp; ii < nb; ii += 32) {
-      const int i = b0 + ii;
-      double s = 0;
-      for (int m = tail + lane; m < n; m += 32) s += A_(m, i) * x[m];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) rhs[ii] = A_(n, i) - s;
-    }
-    for (int t = tid; t < nb * nb; t += 1024) {
-      const int i = t % nb, j = t / nb;
-      Lb[i][j] = (i >= j) ? A_(b0 + i, b0 + j) : 0.0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      for (int i = nb - 1; i >= 0; i--) {
-        double s = 0;
-        for (int m = i + 1 + lane; m < nb; m += 32) s += Lb[m][i] * rhs[m];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) rhs[i] = (rhs[i] - s) / Lb[i][i];
-        __syncwarp();
+      for (int q = 0; q < KC / 4; q++) {
+        const int m = mb + 4 * q;
+        ra[q] = (m < mc && i0 + r <= n) ? A_(i0 + r, k + m0 + m) : 0.0;
+        rb[q] = (m < mc && j0 + r <= n) ? A_(j0 + r, k + m0 + m) : 0.0;
       }
-      for (int i = lane; i < nb; i += 32) x[b0 + i] = rhs[i];
+#pragma unroll
+      for (int q = 0; q < KC / 4; q++) sA[mb + 4 * q][r] = ra[q], sB[mb + 4 * q][r] = rb[q];
     }
-    __threadfence_block();
     __syncthreads();
+    tile_mma(sA, sB, (mc + 3) & ~3, acc);
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+  const int i = i0 + warp * 8 + (lane >> 2);
+  if (i <= n) {
+    double c[8][2];
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int j = j0 + q * 8 + 2 * (lane & 3) + h;
+        c[q][h] = (j < n && i >= j) ? A_(i, j) : 0.0;  // column n does not exist (row n is the carried gradient)
+      }
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int j = j0 + q * 8 + 2 * (lane & 3) + h;
+        if (j < n && i >= j) A_(i, j) = c[q][h] - acc[q][h];
+      }
   }
 }
 
-void dense_cholesky_solve(double *S, int n, int ld, double *x, int *not_spd, cudaStream_t st, long long *launches) {
+// --- back substitution L^T x = y (y = row n), one launch per 64-block, last block first ------------------------
+// every CTA recomputes x_B = W_BB^T y_B (64 x 64 mat-vec), CTA c then folds x_B into the 64 columns it owns:
+// y_i -= sum_r L(b0 + r, i) x_B[r].
+__global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n, int b0, int nb, const double *Winv, double *x) {
+  __shared__ double sW[NB][NB + 1];
+  __shared__ double xb[NB];
+  __shared__ double part[4][NB];
+  const int tid = threadIdx.x;
+  __shared__ double yb[NB];
+  {
+    double w[16];
+    const int i = tid & 63, jb = tid >> 6;
+#pragma unroll
+    for (int q = 0; q < 16; q++) w[q] = Winv[(size_t)(jb + 4 * q) * NB + i];
+    if (tid < NB) yb[tid] = tid < nb ? A_(n, b0 + tid) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) sW[i][jb + 4 * q] = w[q];
+  }
+  __syncthreads();
+  {
+    const int j = tid & 63, p = tid >> 6;
+    double s = 0.0;
+    for (int i = j + p; i < nb; i += 4) s += sW[i][j] * yb[i];
+    part[p][j] = s;
+  }
+  __syncthreads();
+  if (tid < NB) {
+    const double v = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+    xb[tid] = v;
+    if (blockIdx.x == 0 && tid < nb) x[b0 + tid] = v;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) return;  // CTA 0 only publishes x_B; CTAs 1.. own the columns [64 (c-1), 64 c)
+  {
+    const int i = (blockIdx.x - 1) * NB + (tid & 63), p = tid >> 6;
+    double s = 0.0;
+    if (i < b0) {
+      double l[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) l[q] = (p + 4 * q < nb) ? A_(b0 + p + 4 * q, i) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; q++) s += l[q] * xb[p + 4 * q];
+    }
+    part[p][tid & 63] = s;
+  }
+  __syncthreads();
+  if (tid < NB) {
+    const int i = (blockIdx.x - 1) * NB + tid;
+    if (i < b0) A_(n, i) -= part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+  }
+}
+
+void dense_cholesky_solve(double *S, int n, int ld, double *x, double *Winv, int *not_spd, cudaStream_t st, long long *launches) {
   if (n <= 0) return;
   const int rows_total = n + 1;  // rows 0..n (row n carries the gradient)
-  for (int k = 0; k < n; k += NB) {
+  for (int k = 0, blk = 0; k < n; k += NB, blk++) {
     const int nb = (n - k < NB) ? (n - k) : NB;
-    k_potrf_diag<<<1, 256, 0, st>>>(S, ld, k, nb, not_spd);
+    double *W = Winv + (size_t)blk * NB * NB;
+    k_potrf_inv<<<1, PF_THREADS, 0, st>>>(S, ld, k, nb, W, not_spd);
     (*launches)++;
     const int below = rows_total - (k + nb);
     if (below > 0) {
-      k_trsm_panel<<<(below + TRSM_ROWS - 1) / TRSM_ROWS, TRSM_ROWS, 0, st>>>(S, ld, k, nb, rows_total);
-      (*launches)++;
       const int T = (below + TS - 1) / TS;
-      k_syrk_update<<<T * (T + 1) / 2, 256, 0, st>>>(S, ld, k, nb, n, T);
-      (*launches)++;
+      k_panel_gemm<<<T, 256, 0, st>>>(S, ld, k, nb, rows_total, W);
+      k_syrk_update<<<T * (T + 1) / 2, 256, 0, st>>>(S, ld, k, nb, n);
+      (*launches) += 2;
     }
   }
-  k_backsolve<<<1, 1024, 0, st>>>(S, ld, n, x);
-  (*launches)++;
+  const int nblk = (n + NB - 1) / NB;
+  for (int b = nblk - 1; b >= 0; b--) {
+    const int b0 = b * NB, nb = (n - b0 < NB) ? (n - b0) : NB;
+    k_backsolve_step<<<1 + b, 256, 0, st>>>(S, ld, n, b0, nb, Winv + (size_t)b * NB * NB, x);
+    (*launches)++;
+  }
 }
+
+int dense_num_blocks(int n) { return (n + NB - 1) / NB; }
 
 }  // namespace ppo

@@ -56,6 +56,7 @@ struct DevGraph {
   uint8_t *cbe_flags;
   double *cbe_chi2, *cbe_norm;
   double *cbe_J;  // n_cbe x 15 columns x 16
+  double *cbe_err, *cbe_w;  // n_cbe x 16 residual, n_cbe robust weight x information (linearisation scratch)
   // point-cuboid edges
   const int *pce_cuboid, *pce_rowptr;
   const double *pce_pts;

@@ -83,6 +83,7 @@ struct ppo_ba_handle {
   int nb_lin = 0, nb_res = 0, nb_pl = 0, nb_cb = 0, nb_pc = 0, nb_bs = 0;
   Scalars *d_scal = nullptr, *h_scal = nullptr;
   int *d_not_spd = nullptr, *d_nout = nullptr;
+  double *d_Winv = nullptr;
   int *h_dims = nullptr;
   // current mapping
   int n_p = 0, n_kf_free = 0, n_l = 0, n_active_edges = 0;
@@ -390,7 +391,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   for (int p = 0; p < g.n_pl; p++) lm_rowptr[p + 1] += lm_rowptr[p];
   for (int p = 0; p < g.n_pt; p++) lm_rowptr[g.n_pl + p + 1] = g.n_slots + rowptr[p + 1];
   std::vector<int> lm_small, lm_big;
-  for (int L = 0; L < g.n_lm; L++) (lm_rowptr[L + 1] - lm_rowptr[L] > 24 ? lm_big : lm_small).push_back(L);
+  for (int L = 0; L < g.n_lm; L++) (lm_rowptr[L + 1] - lm_rowptr[L] > SCHUR_SMALL_MAX ? lm_big : lm_small).push_back(L);
   h->n_lm_small = (int)lm_small.size();
   h->n_lm_big = (int)lm_big.size();
   UP(h->d_lm_small, lm_small);
@@ -446,7 +447,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
 #define DA(ptr, n) if ((rc = h->dalloc(&(ptr), (n)))) return rc
   DA(g.pe_flags, (size_t)g.n_pe); DA(g.ple_flags, (size_t)g.n_ple); DA(g.cbe_flags, (size_t)g.n_cbe); DA(g.pce_flags, (size_t)g.n_pce);
   DA(g.pe_chi2, (size_t)g.n_pe); DA(g.ple_chi2, (size_t)g.n_ple); DA(g.cbe_chi2, (size_t)g.n_cbe); DA(g.cbe_norm, (size_t)g.n_cbe); DA(g.pce_chi2, (size_t)g.n_pce);
-  DA(g.ple_J, 27 * (size_t)g.n_ple); DA(g.cbe_J, 240 * (size_t)g.n_cbe); DA(g.pce_J, 27 * (size_t)g.n_pce);
+  DA(g.ple_J, 27 * (size_t)g.n_ple); DA(g.cbe_J, 240 * (size_t)g.n_cbe); DA(g.cbe_err, 16 * (size_t)g.n_cbe); DA(g.cbe_w, (size_t)g.n_cbe); DA(g.pce_J, 27 * (size_t)g.n_pce);
   DA(g.kf_act, (size_t)g.n_kf); DA(g.cu_act, (size_t)g.n_cu); DA(g.pl_act, (size_t)g.n_pl); DA(g.pt_act, (size_t)g.n_pt);
   DA(g.kf_idx, (size_t)g.n_kf); DA(g.cu_off, (size_t)g.n_cu); DA(g.ent_pidx, (size_t)g.n_ent); DA(g.dims, 8);
   int n_free = 0;
@@ -461,6 +462,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   h->nb_bs = cdiv(g.n_lm, BS_WARPS);
   DA(h->d_chi_pt, (size_t)std::max(h->nb_lin, h->nb_res)); DA(h->d_chi_pl, (size_t)h->nb_pl); DA(h->d_chi_cb, (size_t)h->nb_cb); DA(h->d_chi_pc, (size_t)h->nb_pc);
   DA(h->d_scale_part, (size_t)h->nb_bs);
+  DA(h->d_Winv, (size_t)dense_num_blocks(h->max_np) * 64 * 64);
   DA(h->d_scal, 1); DA(h->d_not_spd, 1); DA(h->d_nout, 4); DA(h->d_red, 4);
   CK(cudaMemsetAsync(g.pe_chi2, 0, 8 * (size_t)g.n_pe, h->st));
   CK(cudaMemsetAsync(g.ple_chi2, 0, 8 * (size_t)g.n_ple, h->st));
@@ -582,7 +584,8 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
   if (g.n_cbe) {
     k_cuboid_jac<<<cdiv(g.n_cbe * 15, 128), 128, 0, st>>>(g, s);
     k_cuboid_edges<true><<<h->nb_cb, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_cb);
-    h->launches += 2;
+    k_cuboid_assemble<<<cdiv(g.n_cbe * 15, 128), 128, 0, st>>>(g);
+    h->launches += 3;
   }
   if (g.n_pce) {
     k_ptcu_jac<<<cdiv(g.n_pce * 9, 128), 128, 0, st>>>(g, s);
@@ -628,7 +631,7 @@ static int schur_system(ppo_ba_handle *h, double lambda) {
 }
 static int solve_and_backsub(ppo_ba_handle *h, double lambda) {
   DevGraph &g = h->g;
-  dense_cholesky_solve(g.S, h->n_p, h->ld, g.xp, h->d_not_spd, h->st, &h->launches);
+  dense_cholesky_solve(g.S, h->n_p, h->ld, g.xp, h->d_Winv, h->d_not_spd, h->st, &h->launches);
   if (g.n_lm) { k_backsub<<<h->nb_bs, BS_WARPS * 32, 0, h->st>>>(g, lambda, h->d_scale_part); h->launches++; }
   return PPO_OK;
 }

@@ -530,7 +530,8 @@ __global__ void k_cuboid_jac(DevGraph g, DevState s) {
   }
   for (int r = 0; r < 16; r++) J[r] = r < D ? NUM_SCALAR * (ep[r] - em[r]) : 0.0;
 }
-template <bool ASSEMBLE>
+// residual of the camera-cuboid edges; with STORE also the error vector and the robust weight for k_cuboid_assemble
+template <bool STORE>
 __global__ void __launch_bounds__(SMALL_THREADS) k_cuboid_edges(DevGraph g, DevState s, double *chi_part) {
   __shared__ double sm[SMALL_THREADS / 32];
   const int e = blockIdx.x * SMALL_THREADS + threadIdx.x;
@@ -554,31 +555,42 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_cuboid_edges(DevGraph g, DevS
     rho0 = chi2;
     double w = 1.0;
     if (g.cbe_flags[e] & PPO_EF_ROBUST_) w = huber_w(chi2, kind == 0 ? g.huber_bbox : g.huber_corner, &rho0);
-    if (ASSEMBLE) {
-      const double wi = w * info;
-      const double *J = g.cbe_J + 240 * (size_t)e;  // [col][row16]
-      const int idx = g.kf_idx[kf], off = g.cu_off[cu];
-      const int a0 = idx >= 0 ? 0 : 6;
-      for (int a = a0; a < 15; a++) {
-        double ga = 0;
-        for (int r = 0; r < D; r++) ga += J[16 * a + r] * err[r];
-        ga *= -wi;
-        if (a < 6) atomicAdd(&g.bp[6 * idx + a], ga);
-        else atomicAdd(&g.bp[off + a - 6], ga);
-        for (int b = (a < 6 ? a0 : 6); b < 15; b++) {
-          if (a >= 6 && b < 6) continue;
-          double h = 0;
-          for (int r = 0; r < D; r++) h += J[16 * a + r] * J[16 * b + r];
-          h *= wi;
-          if (a < 6 && b < 6) atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * a + b], h);
-          else if (a < 6) g.Hpc[54 * (size_t)e + 9 * a + (b - 6)] = h;
-          else atomicAdd(&g.Hpp_cu[81 * (size_t)cu + 9 * (a - 6) + (b - 6)], h);
-        }
-      }
+    if (STORE) {
+      for (int r = 0; r < 16; r++) g.cbe_err[16 * (size_t)e + r] = r < D ? err[r] : 0.0;
+      g.cbe_w[e] = w * info;
     }
   }
   const double t = block_sum<SMALL_THREADS>(rho0, sm);
   if (threadIdx.x == 0) chi_part[blockIdx.x] = t;
+}
+// quadratic form of the camera-cuboid edges: one thread per (edge, row a of the 15 x 15 block)
+__global__ void k_cuboid_assemble(DevGraph g) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t / 15, a = t % 15;
+  if (e >= g.n_cbe || (g.cbe_flags[e] & PPO_EF_LEVEL1_)) return;
+  const int kf = g.cbe_kf[e], cu = g.cbe_cuboid[e];
+  const int idx = g.kf_idx[kf], off = g.cu_off[cu];
+  if (a < 6 && idx < 0) return;
+  const double wi = g.cbe_w[e];
+  const double *J = g.cbe_J + 240 * (size_t)e;  // [col][row16], rows >= D are zero
+  double ja[16];
+#pragma unroll
+  for (int r = 0; r < 16; r++) ja[r] = J[16 * a + r];
+  double ga = 0;
+#pragma unroll
+  for (int r = 0; r < 16; r++) ga += ja[r] * g.cbe_err[16 * (size_t)e + r];
+  ga *= -wi;
+  if (a < 6) atomicAdd(&g.bp[6 * idx + a], ga);
+  else atomicAdd(&g.bp[off + a - 6], ga);
+  for (int b = (a < 6 ? (idx >= 0 ? 0 : 6) : 6); b < 15; b++) {
+    double hv = 0;
+#pragma unroll
+    for (int r = 0; r < 16; r++) hv += ja[r] * J[16 * b + r];
+    hv *= wi;
+    if (a < 6 && b < 6) atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * a + b], hv);
+    else if (a < 6) g.Hpc[54 * (size_t)e + 9 * a + (b - 6)] = hv;
+    else atomicAdd(&g.Hpp_cu[81 * (size_t)cu + 9 * (a - 6) + (b - 6)], hv);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -657,10 +669,15 @@ PPO_D bool landmark_active(const DevGraph &g, int L) {
   return L < g.n_pl ? g.pl_act[L] != 0 : (g.pt_act[L - g.n_pl] != 0 && !g.pt_fixed[L - g.n_pl]);
 }
 constexpr int SCHUR_WARPS = 8;
-// lm_list: landmarks handled by this launch; WHOLE_CTA: one landmark per CTA instead of per warp
+constexpr int SCHUR_SMALL_MAX = 24;  // landmarks with more blocks than this take a whole CTA
+// lm_list: landmarks handled by this launch; WHOLE_CTA: one landmark per CTA instead of per warp.
+// Small landmarks stage their (contiguous) 6x3 blocks in shared memory once; the pair loop then walks the
+// (i2, entry) items with a carried counter (no divisions) and issues one RED.F64 per scalar of the 6x6 product.
 template <bool WHOLE_CTA>
 __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const int *lm_list, int n_list, double lambda, int n_p, int ld) {
   __shared__ double bd[SCHUR_WARPS][18];
+  __shared__ double blk[WHOLE_CTA ? 1 : SCHUR_WARPS][WHOLE_CTA ? 1 : SCHUR_SMALL_MAX * 18];
+  __shared__ int pid[WHOLE_CTA ? 1 : SCHUR_WARPS][WHOLE_CTA ? 1 : SCHUR_SMALL_MAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int li = WHOLE_CTA ? blockIdx.x : blockIdx.x * SCHUR_WARPS + warp;
   if (li >= n_list) return;
@@ -680,11 +697,19 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const in
     for (int i = 0; i < 6; i++) g.Dinv[6 * (size_t)L + i] = D[i];
   }
   const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
+  const double *Wg = g.Hpl + 18 * (size_t)b0;
+  if (!WHOLE_CTA) {
+    const int n = (b1 - b0) * 18;
+    for (int t = lane; t < n; t += 32) blk[warp][t] = Wg[t];
+    for (int t = lane; t < b1 - b0; t += 32) pid[warp][t] = g.ent_pidx[b0 + t];
+    __syncwarp();
+  }
   const int step = WHOLE_CTA ? SCHUR_WARPS : 1;
-  for (int i1 = b0 + (WHOLE_CTA ? warp : 0); i1 < b1; i1 += step) {
-    const int p1 = g.ent_pidx[i1];
+  const int nblk = b1 - b0;
+  for (int i1 = (WHOLE_CTA ? warp : 0); i1 < nblk; i1 += step) {
+    const int p1 = WHOLE_CTA ? g.ent_pidx[b0 + i1] : pid[warp][i1];
     if (p1 < 0) continue;  // warp-uniform
-    const double *W1 = g.Hpl + 18 * (size_t)i1;
+    const double *W1 = WHOLE_CTA ? Wg + 18 * (size_t)i1 : &blk[warp][18 * i1];
     // BD = W1 * Dinv (6 x 3), one lane per entry
     __syncwarp();
     if (lane < 18) {
@@ -695,26 +720,30 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const in
       bd[warp][lane] = W1[3 * r] * dc0 + W1[3 * r + 1] * dc1 + W1[3 * r + 2] * dc2;
     }
     __syncwarp();
+    double *Srow = g.S + (size_t)(6 * p1) * ld;
     if (lane < 6)  // reduced gradient: bschur_i -= W1 * Dinv * bl   (coefficients, :403-405)
-      atomicAdd(&g.S[(size_t)(6 * p1 + lane) * ld + n_p], -(W1[3 * lane] * db[0] + W1[3 * lane + 1] * db[1] + W1[3 * lane + 2] * db[2]));
-    const int n_items = (b1 - i1) * 36;
-    for (int it = lane; it < n_items; it += 32) {
-      const int i2 = i1 + it / 36, en = it % 36;
-      const int p2 = g.ent_pidx[i2];
-      if (p2 < 0) continue;
-      const int r = en / 6, c = en % 6;
-      const double *W2 = g.Hpl + 18 * (size_t)i2 + 3 * c;
-      const double v = bd[warp][3 * r] * W2[0] + bd[warp][3 * r + 1] * W2[1] + bd[warp][3 * r + 2] * W2[2];
-      // keep the upper block triangle (row-major): (p1,p2) if p1 <= p2 else the transposed entry
-      size_t row, colx;
-      if (p1 <= p2) row = 6 * (size_t)p1 + r, colx = 6 * (size_t)p2 + c;
-      else row = 6 * (size_t)p2 + c, colx = 6 * (size_t)p1 + r;
-      if (p1 == p2 && i1 != i2) {
-        // two different entries on the same key-frame: W1 D W2^T + W2 D W1^T lands on one diagonal block
-        atomicAdd(&g.S[(6 * (size_t)p1 + r) * ld + 6 * p1 + c], -v);
-        atomicAdd(&g.S[(6 * (size_t)p1 + c) * ld + 6 * p1 + r], -v);
-      } else {
-        atomicAdd(&g.S[row * ld + colx], -v);
+      atomicAdd(&Srow[(size_t)lane * ld + n_p], -(W1[3 * lane] * db[0] + W1[3 * lane + 1] * db[1] + W1[3 * lane + 2] * db[2]));
+    // items (i2 >= i1, entry 0..35), lane-strided with a carried (i2, en) counter
+    int i2 = i1, en = lane;
+    while (i2 < nblk) {
+      const int p2 = WHOLE_CTA ? g.ent_pidx[b0 + i2] : pid[warp][i2];
+      if (p2 >= 0) {
+        const int r = (en * 43) >> 8, c = en - 6 * r;  // en / 6, en % 6 for en < 36
+        const double *W2 = (WHOLE_CTA ? Wg + 18 * (size_t)i2 : &blk[warp][18 * i2]) + 3 * c;
+        const double v = bd[warp][3 * r] * W2[0] + bd[warp][3 * r + 1] * W2[1] + bd[warp][3 * r + 2] * W2[2];
+        if (p1 < p2 || i1 == i2) {
+          atomicAdd(&Srow[(size_t)r * ld + 6 * p2 + c], -v);
+        } else if (p1 > p2) {  // keep the upper block triangle: write the transposed entry
+          atomicAdd(&g.S[(size_t)(6 * p2 + c) * ld + 6 * p1 + r], -v);
+        } else {  // two different entries on one key-frame: W1 D W2^T + W2 D W1^T on the diagonal block
+          atomicAdd(&Srow[(size_t)r * ld + 6 * p1 + c], -v);
+          atomicAdd(&Srow[(size_t)c * ld + 6 * p1 + r], -v);
+        }
+      }
+      en += 32;
+      if (en >= 36) {
+        en -= 36;
+        i2++;
       }
     }
   }
