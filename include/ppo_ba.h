@@ -269,6 +269,13 @@ int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, do
  * identical system.  nccl_comm is an ncclComm_t passed as void*; rank 0 alone accumulates the
  * non-point edges. */
 int ppo_ba_set_shard(ppo_ba_handle *h, void *nccl_comm, int rank, int world);
+/* NCCL plumbing without a link-time dependency (libnccl.so.2 is dlopen'ed; the torch wheel already maps it):
+ * rank 0 creates the 128-byte unique id, the host program broadcasts it (e.g. torch.distributed), every rank
+ * creates its communicator for `device`. */
+int ppo_ba_nccl_unique_id(char out[128]);
+int ppo_ba_nccl_init(const char id_bytes[128], int rank, int world, int device, void **comm);
+int ppo_ba_nccl_destroy(void *comm);
+long long ppo_ba_collective_count(const ppo_ba_handle *h);
 
 #ifdef __cplusplus
 }

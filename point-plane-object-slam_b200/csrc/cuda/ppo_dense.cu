@@ -25,25 +25,77 @@ constexpr int NB = 64;  // panel width
 // --- diagonal block: Cholesky + explicit inverse of the 64 x 64 factor --------------------------------
 // Gaussian elimination of [A | I] without scaling: A ends as L_u D (unit-lower factor times pivots), the
 // identity part as X = L_u^-1; then L = L_u D^1/2 and W = L^-1 = D^-1/2 X.
-// 128 threads: thread (i, h) keeps 32 entries of row i (columns c = h + 2 q) in REGISTERS.  Register V[c]
-// holds A(i,c) until column c is eliminated; at step j = c the finished L(i,j) is written out and the register
-// is recycled for X(i,j).  Per column only one 64-vector travels through (double-buffered) shared memory:
-// vec[r] = A(r,j) for r > j and vec[c] = X(j,c) for c < j.  One barrier and one reciprocal per column.
+// 128 threads: thread (i, h) keeps A(i, c) and X(i, c), c = 32 h + q, in REGISTERS.  Per column j two 64-vectors
+// travel through (double-buffered) shared memory: va[c] = A(c, j) (pivot column, symmetric) and vx[c] = X(j, c).
+// The 64 elimination steps are FULLY UNROLLED (per column half h), so every register index, every "is this column
+// still live" test and the shared-memory addresses are compile-time constants: one FMA per (row, column) and step,
+// one barrier and one reciprocal per column; square roots and the write-out happen after the loop.
 constexpr int PF_THREADS = 128;
+#ifdef PPO_POTRF_TIMING
+__device__ long long g_potrf_t[8];
+#define PF_STAMP(n) if (threadIdx.x == 0) g_potrf_t[n] = clock64()
+#else
+#define PF_STAMP(n)
+#endif
+template <int H>
+__device__ __forceinline__ void pf_eliminate(double (&V)[32], double (&X)[32], double (*va)[NB], double (*vx)[NB], double *rinv,
+                                             double (*Lu)[NB + 1], const int i, int *not_spd) {
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    __syncthreads();
+    if ((i | 31) >= j) {  // otherwise all rows of this warp are final (warp-uniform)
+      const int cur = j & 1, nxt = cur ^ 1;
+      const double aij = va[cur][i];
+      const double f = i > j ? aij * rinv[j] : 0.0;  // L_u(i,j); finished rows (and row j itself) do not move
+      if (H == 0 && i >= j) Lu[i][j] = aij;
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const int c = 32 * H + q;
+        if (c > j) V[q] = fma(-f, va[cur][c], V[q]);  // live column of A
+        else X[q] = fma(-f, vx[cur][c], X[q]);        // X(i,c) -= f X(j,c), X(j,j) = 1
+      }
+      const int jn = j + 1;
+      if (jn < NB) {
+        if (jn >= 32 * H && jn < 32 * H + 32 && i >= jn) {  // operand column of the next step: A(i, j+1)
+          const double v = V[(jn - 32 * H) & 31];
+          va[nxt][i] = v;
+          if (i == jn) {
+            double d = v;
+            if (!(d > 0.0)) {
+              *not_spd = 1;
+              d = 1.0;
+            }
+            rinv[jn] = __drcp_rn(d);
+          }
+        }
+        if (i == jn) {  // row j+1 of X is final (its unit diagonal is already in the register)
+#pragma unroll
+          for (int q = 0; q < 32; q++)
+            if (32 * H + q <= jn) vx[nxt][32 * H + q] = X[q];
+        }
+      }
+    }
+  }
+}
 __global__ void __launch_bounds__(PF_THREADS) k_potrf_inv(double *S, int ld, int k, int nb, double *Winv, int *not_spd) {
-  __shared__ double vec[2][NB];
-  __shared__ double rinv[NB];         // 1 / d_j
-  __shared__ double Lu[NB][NB + 1];   // finished columns A(i,j) = L_u(i,j) d_j, scaled and written out after the loop
+  PF_STAMP(0);
+  __shared__ __align__(16) double va[2][NB];
+  __shared__ __align__(16) double vx[2][NB];
+  __shared__ double rinv[NB];        // 1 / d_j
+  __shared__ double Lu[NB][NB + 1];  // finished columns A(i,j) = L_u(i,j) d_j
+  __shared__ double rs[NB], sq[NB];  // 1/sqrt(d_c), sqrt(d_c)
   const int tid = threadIdx.x;
   const int i = tid & 63, h = tid >> 6;
-  double V[32];
+  double V[32], X[32];
 #pragma unroll
   for (int q = 0; q < 32; q++) {
-    const int c = h + 2 * q;
+    const int c = 32 * h + q;
     V[q] = (i < nb && c < nb && i >= c) ? A_(k + i, k + c) : (i == c ? 1.0 : 0.0);
+    X[q] = i == c ? 1.0 : 0.0;
   }
   if (h == 0) {
-    vec[0][i] = V[0];
+    va[0][i] = V[0];
+    vx[0][i] = i == 0 ? 1.0 : 0.0;
     if (i == 0) {
       double d = V[0];
       if (!(d > 0.0)) {
@@ -53,56 +105,26 @@ __global__ void __launch_bounds__(PF_THREADS) k_potrf_inv(double *S, int ld, int
       rinv[0] = __drcp_rn(d);
     }
   }
-  for (int j = 0; j < NB; j++) {
-    __syncthreads();
-    if ((i | 31) < j) continue;  // all rows of this warp are final (warp-uniform)
-    const int cur = j & 1, nxt = cur ^ 1;
-    if (i >= j) {
-      const double rj = rinv[j];
-      const double aij = vec[cur][i];
-      const double f = aij * rj;  // L_u(i,j)
-      const bool below = i > j;
-      const double xj = below ? -f : 1.0;  // X(i,j) ; X(j,j) = 1
-      const bool rownext = i == j + 1;
-      // all operand loads first (the stores below alias the same shared array and would serialise them)
-      double T[32];
-#pragma unroll
-      for (int q = 0; q < 32; q++) T[q] = vec[cur][h + 2 * q];
-      // lean, fully predicated update (c is warp-uniform for a given q)
-#pragma unroll
-      for (int q = 0; q < 32; q++) {
-        const int c = h + 2 * q;
-        const double upd = V[q] - f * T[q];
-        V[q] = (c == j) ? xj : ((below && c <= i) ? upd : V[q]);
-      }
-#pragma unroll
-      for (int q = 0; q < 32; q++) {
-        const int c = h + 2 * q;
-        if (below && c == j + 1) vec[nxt][i] = V[q];   // A(i, j+1): operand column of the next step
-        if (rownext && c <= j) vec[nxt][c] = V[q];     // X(j+1, c): row j+1 is final after this step
-      }
-      if (h == (j & 1)) Lu[i][j] = aij;  // finished column j (kept unscaled: no sqrt / divide inside the loop)
-      if (rownext && h == ((j + 1) & 1)) {  // next pivot (this thread stored vec[nxt][j+1] itself)
-        double d = vec[nxt][j + 1];
-        if (!(d > 0.0)) {
-          *not_spd = 1;
-          d = 1.0;
-        }
-        rinv[j + 1] = __drcp_rn(d);
-      }
-    }
+  PF_STAMP(1);
+  if (h == 0) pf_eliminate<0>(V, X, va, vx, rinv, Lu, i, not_spd);
+  else pf_eliminate<1>(V, X, va, vx, rinv, Lu, i, not_spd);
+  __syncthreads();
+  PF_STAMP(2);
+  if (tid < NB) {
+    const double r = sqrt(rinv[tid]);
+    rs[tid] = r;
+    sq[tid] = 1.0 / r;
   }
   __syncthreads();
-  const double rsi = sqrt(rinv[i]);
+  const double rsi = rs[i];
 #pragma unroll
   for (int q = 0; q < 32; q++) {
-    const int c = h + 2 * q;
-    Winv[(size_t)c * NB + i] = c <= i ? V[q] * rsi : 0.0;  // W(i,c) = X(i,c) / sqrt(d_i)
-    if (i < nb && c < nb && i >= c) {                     // L(i,c) = A(i,c) / sqrt(d_c) ; L(c,c) = sqrt(d_c)
-      const double rsc = sqrt(rinv[c]);
-      A_(k + i, k + c) = i > c ? Lu[i][c] * rsc : 1.0 / rsc;
-    }
+    const int c = 32 * h + q;
+    Winv[(size_t)c * NB + i] = X[q] * rsi;  // W(i,c) = X(i,c) / sqrt(d_i)  (exact zeros above the diagonal)
+    if (i < nb && c < nb && i >= c)        // L(i,c) = A(i,c) / sqrt(d_c) ; L(c,c) = sqrt(d_c)
+      A_(k + i, k + c) = i > c ? Lu[i][c] * rs[c] : sq[c];
   }
+  PF_STAMP(3);
 }
 
 // --- 64 x 64 output tile of  C = sum_m A(i,m) B(j,m)  on the FP64 tensor cores ---------------------------

@@ -33,9 +33,13 @@ using namespace ppo;
 // ---- minimal NCCL binding (dlopen: the torch wheel already maps libnccl.so.2 into the process) -----
 typedef struct ncclComm *ncclComm_t;
 typedef enum { ncclSum_ = 0, ncclMax_ = 2 } ncclRedOp_t_;
-typedef enum { ncclFloat64_ = 8 } ncclDataType_t_;
+typedef enum { ncclInt32_ = 2, ncclFloat64_ = 8 } ncclDataType_t_;
+struct ncclUniqueId_ { char internal[128]; };
 struct NcclApi {
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_ *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool ok = false;
   void load() {
@@ -44,8 +48,11 @@ struct NcclApi {
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) return;
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    ok = AllReduce != nullptr;
+    ok = AllReduce && GetUniqueId && CommInitRank && CommDestroy;
   }
 };
 static NcclApi g_nccl;
@@ -94,6 +101,7 @@ struct ppo_ba_handle {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   double *d_red = nullptr;  // 4 doubles for scalar allreduce
+  long long collectives = 0;
 
   template <typename T>
   int dalloc(T **p, size_t n) {
@@ -101,7 +109,7 @@ struct ppo_ba_handle {
     *p = nullptr;
     if (n == 0) n = 1;
     void *q = nullptr;
-    CK(cudaMalloc(&q, n * sizeof(T)));
+    CK(cudaMallocAsync(&q, n * sizeof(T), st));  // stream-ordered pool: re-used across windows without OS calls
     allocs.push_back(q);
     *p = (T *)q;
     return PPO_OK;
@@ -111,11 +119,34 @@ struct ppo_ba_handle {
     ppo_ba_handle *h = this;
     int rc = dalloc(p, v.size());
     if (rc) return rc;
-    if (!v.empty()) CK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (!v.empty()) {
+      void *stage = nullptr;
+      if ((rc = pinned(&stage, v.size() * sizeof(T)))) return rc;
+      std::memcpy(stage, v.data(), v.size() * sizeof(T));
+      CK(cudaMemcpyAsync(*p, stage, v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    return PPO_OK;
+  }
+  // pinned host staging arena: every H2D / D2H copy of the C-ABI goes through page-locked memory
+  char *hstage = nullptr;
+  size_t hstage_cap = 0, hstage_off = 0;
+  int pinned(void **out, size_t bytes) {
+    ppo_ba_handle *h = this;
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (hstage_off + bytes > hstage_cap) {
+      // grow: the copies already enqueued read the old arena, so drain the stream before replacing it
+      CK(cudaStreamSynchronize(st));
+      if (hstage) cudaFreeHost(hstage);
+      hstage_cap = std::max(hstage_cap * 2, hstage_off + bytes + (size_t)(64u << 20));
+      hstage_off = 0;
+      CK(cudaMallocHost((void **)&hstage, hstage_cap));
+    }
+    *out = hstage + hstage_off;
+    hstage_off += bytes;
     return PPO_OK;
   }
   void free_graph() {
-    for (void *p : allocs) cudaFree(p);
+    for (void *p : allocs) cudaFreeAsync(p, st);
     allocs.clear();
     have_graph = false;
   }
@@ -169,6 +200,13 @@ int ppo_ba_create(const ppo_ba_params *params, int device, ppo_ba_handle **out) 
   cudaEventCreate(&h->ev1);
   for (auto &e : h->evp) cudaEventCreate(&e);
   for (auto &e : h->evm) cudaEventCreate(&e);
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;  // keep freed blocks cached in the pool
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaMallocHost((void **)&h->h_scal, sizeof(Scalars));
   cudaMallocHost((void **)&h->h_dims, 8 * sizeof(int));
   *out = h;
@@ -180,6 +218,8 @@ void ppo_ba_destroy(ppo_ba_handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
   h->free_graph();
+  cudaStreamSynchronize(h->st);
+  if (h->hstage) cudaFreeHost(h->hstage);
   cudaFreeHost(h->h_scal);
   cudaFreeHost(h->h_dims);
   cudaEventDestroy(h->ev0);
@@ -252,6 +292,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->st));
   h->free_graph();
+  h->hstage_off = 0;
   DevGraph &g = h->g;
   std::memset(&g, 0, sizeof g);
   if (gi->n_kf <= 0 || gi->n_pt < 0 || gi->n_pl < 0 || gi->n_cu < 0) { h->err = "bad vertex counts"; return PPO_E_INVALID; }
@@ -305,10 +346,16 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   }
   std::vector<double> pt(gi->pt_xyz, gi->pt_xyz + 3 * (size_t)g.n_pt);
   if ((rc = alloc_state(h, &h->sa)) || (rc = alloc_state(h, &h->sb)) || (rc = alloc_state(h, &h->s0))) return rc;
-  if (g.n_kf) CK(cudaMemcpyAsync(h->s0.kf_pose, kf_pose.data(), kf_pose.size() * 8, cudaMemcpyHostToDevice, h->st));
-  if (g.n_pt) CK(cudaMemcpyAsync(h->s0.pt, pt.data(), pt.size() * 8, cudaMemcpyHostToDevice, h->st));
-  if (g.n_pl) CK(cudaMemcpyAsync(h->s0.pl, pl.data(), pl.size() * 8, cudaMemcpyHostToDevice, h->st));
-  if (g.n_cu) CK(cudaMemcpyAsync(h->s0.cu, cu.data(), cu.size() * 8, cudaMemcpyHostToDevice, h->st));
+  auto stage_up = [&](double *dst, const std::vector<double> &v) -> int {
+    if (v.empty()) return PPO_OK;
+    void *stage = nullptr;
+    int r = h->pinned(&stage, v.size() * 8);
+    if (r) return r;
+    std::memcpy(stage, v.data(), v.size() * 8);
+    CK(cudaMemcpyAsync(dst, stage, v.size() * 8, cudaMemcpyHostToDevice, h->st));
+    return PPO_OK;
+  };
+  if ((rc = stage_up(h->s0.kf_pose, kf_pose)) || (rc = stage_up(h->s0.pt, pt)) || (rc = stage_up(h->s0.pl, pl)) || (rc = stage_up(h->s0.cu, cu))) return rc;
   k_pose_cache<<<cdiv(g.n_kf, 128), 128, 0, h->st>>>(g.n_kf, h->s0.kf_pose, h->s0.kf_Rt);
   h->launches++;
   if ((rc = copy_state(h, h->sa, h->s0))) return rc;
@@ -503,6 +550,17 @@ int ppo_ba_reset(ppo_ba_handle *h) {
   return PPO_OK;
 }
 
+static int allreduce(ppo_ba_handle *h, void *buf, size_t n, int dtype, int op) {
+  if (h->world <= 1 || n == 0) return PPO_OK;
+  int r = g_nccl.AllReduce(buf, buf, n, dtype, op, h->comm, h->st);
+  if (r != 0) {
+    h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    return PPO_E_NCCL;
+  }
+  h->collectives++;
+  return PPO_OK;
+}
+
 // ---- SparseOptimizer::initializeOptimization(0) ------------------------------------------------------
 static int init_mapping(ppo_ba_handle *h) {
   DevGraph &g = h->g;
@@ -519,6 +577,12 @@ static int init_mapping(ppo_ba_handle *h) {
   if (g.n_cpe) {
     k_mark_active_cpe<<<cdiv(g.n_cpe, 256), 256, 0, st>>>(g, h->d_cpe_cuboid, h->d_cpe_plane, h->d_cpe_flags);
     h->launches++;
+  }
+  if (h->world > 1) {  // a key-frame / cuboid / plane is active if ANY rank holds an active edge on it
+    int rc;
+    if ((rc = allreduce(h, g.kf_act, g.n_kf, ncclInt32_, ncclMax_)) || (rc = allreduce(h, g.cu_act, g.n_cu, ncclInt32_, ncclMax_)) ||
+        (rc = allreduce(h, g.pl_act, g.n_pl, ncclInt32_, ncclMax_)))
+      return rc;
   }
   k_build_index<<<1, 32, 0, st>>>(g);
   h->launches++;
@@ -537,16 +601,6 @@ static int init_mapping(ppo_ba_handle *h) {
   h->n_l = h->h_dims[2] + h->h_dims[3];
   h->n_active_edges = h->h_dims[4];
   for (size_t e = 0; e < h->cpe_flags.size(); e++) h->n_active_edges += !(h->cpe_flags[e] & PPO_EF_LEVEL1);
-  return PPO_OK;
-}
-
-static int allreduce(ppo_ba_handle *h, double *buf, size_t n, int op) {
-  if (h->world <= 1) return PPO_OK;
-  int r = g_nccl.AllReduce(buf, buf, n, ncclFloat64_, op, h->comm, h->st);
-  if (r != 0) {
-    h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
-    return PPO_E_NCCL;
-  }
   return PPO_OK;
 }
 
@@ -574,11 +628,13 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
     k_pose_reduce<<<cdiv(g.n_kf * 27, 128), 128, 0, st>>>(g, h->d_kf_chunk_ptr, h->d_chunk_part);
     h->launches += 2;
   }
-  const bool own = h->owner();
+  if (h->world > 1) {  // pose side of the point edges of all shards; the replicated edges below are added on every rank
+    int rc;
+    if ((rc = allreduce(h, g.Hpp_kf, 36 * (size_t)g.n_kf, ncclFloat64_, ncclSum_)) || (rc = allreduce(h, g.bp, h->max_np, ncclFloat64_, ncclSum_))) return rc;
+  }
   if (g.n_ple) {
     k_plane_jac<<<cdiv(g.n_ple * 9, 128), 128, 0, st>>>(g, s);
-    if (own) k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pl);
-    else k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pl);
+    k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pl);
     h->launches += 2;
   }
   if (g.n_cbe) {
@@ -593,12 +649,24 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
     h->launches += 2;
   }
   if (h->profiling) cudaEventRecord(h->evp[1], st);
-  k_scalars<<<1, 256, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, g.n_ple ? h->nb_pl : 0, h->d_chi_cb,
-                              g.n_cbe ? h->nb_cb : 0, h->d_chi_pc, g.n_pce ? h->nb_pc : 0, cpe_chi_const(h), nullptr, 0, 0.0, 0, nullptr);
+  const bool own = h->owner();  // replicated (non-point) edges count once: on rank 0
+  k_scalars<<<1, 256, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
+                              (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, cpe_chi_const(h), nullptr, 0, 0.0, 0,
+                              nullptr, h->d_red);
   h->launches++;
   if (want_max_diag) {
     k_max_diag<<<1, 256, 0, st>>>(g, h->d_scal);
     h->launches++;
+  }
+  if (h->world > 1) {
+    int rc;
+    if ((rc = allreduce(h, h->d_red, 2, ncclFloat64_, ncclSum_))) return rc;
+    k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 0);
+    if (want_max_diag) {
+      k_set_red_maxdiag<<<1, 32, 0, st>>>(h->d_scal, h->d_red);
+      if ((rc = allreduce(h, h->d_red + 2, 1, ncclFloat64_, ncclMax_))) return rc;
+      k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 1);
+    }
   }
   CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -623,16 +691,19 @@ static int schur_system(ppo_ba_handle *h, double lambda) {
   const int n_p = h->n_p, ld = h->ld;
   CK(cudaMemsetAsync(g.S, 0, 8 * (size_t)(n_p + 1) * ld, st));
   CK(cudaMemsetAsync(h->d_not_spd, 0, sizeof(int), st));
-  if (h->n_lm_small) { k_schur<false><<<cdiv(h->n_lm_small, SCHUR_WARPS), SCHUR_WARPS * 32, 0, st>>>(g, h->d_lm_small, h->n_lm_small, lambda, n_p, ld); h->launches++; }
-  if (h->n_lm_big) { k_schur<true><<<h->n_lm_big, SCHUR_WARPS * 32, 0, st>>>(g, h->d_lm_big, h->n_lm_big, lambda, n_p, ld); h->launches++; }
+  const int own = h->owner() ? 1 : 0;
+  if (h->n_lm_small) { k_schur<false><<<cdiv(h->n_lm_small, SCHUR_WARPS), SCHUR_WARPS * 32, 0, st>>>(g, h->d_lm_small, h->n_lm_small, lambda, n_p, ld, own); h->launches++; }
+  if (h->n_lm_big) { k_schur<true><<<h->n_lm_big, SCHUR_WARPS * 32, 0, st>>>(g, h->d_lm_big, h->n_lm_big, lambda, n_p, ld, own); h->launches++; }
   const int n_comp = g.n_kf * 36 + g.n_cu * 81 + g.n_cbe * 54 + n_p;
-  if (n_comp) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, lambda, n_p, ld); h->launches++; }
+  if (n_comp && own) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, lambda, n_p, ld); h->launches++; }
+  // single large window sharded over ranks: sum the partial reduced systems (Hschur | bschur) over NVLink
+  if (h->world > 1) return allreduce(h, g.S, (size_t)n_p * ld, ncclFloat64_, ncclSum_);
   return PPO_OK;
 }
 static int solve_and_backsub(ppo_ba_handle *h, double lambda) {
   DevGraph &g = h->g;
   dense_cholesky_solve(g.S, h->n_p, h->ld, g.xp, h->d_Winv, h->d_not_spd, h->st, &h->launches);
-  if (g.n_lm) { k_backsub<<<h->nb_bs, BS_WARPS * 32, 0, h->st>>>(g, lambda, h->d_scale_part); h->launches++; }
+  if (g.n_lm) { k_backsub<<<h->nb_bs, BS_WARPS * 32, 0, h->st>>>(g, lambda, h->d_scale_part, h->owner() ? 1 : 0); h->launches++; }
   return PPO_OK;
 }
 
@@ -679,10 +750,17 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
       k_update<<<cdiv(nv, 128), 128, 0, st>>>(g, h->sa, h->sb);
       h->launches++;
       residual_kernels(h, h->sb);
-      k_scalars<<<1, 256, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_pe ? h->nb_res : 0, h->d_chi_pl, g.n_ple ? h->nb_pl : 0, h->d_chi_cb,
-                                  g.n_cbe ? h->nb_cb : 0, h->d_chi_pc, g.n_pce ? h->nb_pc : 0, cpe_chi_const(h), h->d_scale_part,
-                                  g.n_lm ? h->nb_bs : 0, h->lambda, h->n_p, h->d_not_spd);
-      h->launches++;
+      {
+        const bool own = h->owner();
+        k_scalars<<<1, 256, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_pe ? h->nb_res : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
+                                    (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, cpe_chi_const(h), h->d_scale_part,
+                                    g.n_lm ? h->nb_bs : 0, h->lambda, own ? h->n_p : 0, h->d_not_spd, h->d_red);
+        h->launches++;
+        if (h->world > 1) {
+          if ((rc = allreduce(h, h->d_red, 2, ncclFloat64_, ncclSum_))) return rc;
+          k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 0);
+        }
+      }
       if (h->profiling) cudaEventRecord(h->evp[5], st);
       CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
@@ -872,11 +950,21 @@ int ppo_ba_get_state(ppo_ba_handle *h, ppo_ba_state *out) {
   if (!h || !h->have_graph || !out) return PPO_E_INVALID;
   CK(cudaSetDevice(h->device));
   DevGraph &g = h->g;
+  const size_t nb[4] = {56 * (size_t)g.n_kf, 24 * (size_t)g.n_pt, 32 * (size_t)g.n_pl, 80 * (size_t)g.n_cu};
+  const double *src[4] = {h->sa.kf_pose, h->sa.pt, h->sa.pl, h->sa.cu};
+  double *dst[4] = {out->kf_pose, out->pt_xyz, out->pl_coef, out->cu_state};
+  void *stage[4] = {nullptr, nullptr, nullptr, nullptr};
+  const size_t keep = h->hstage_off;
+  int rc;
+  for (int k = 0; k < 4; k++)
+    if (dst[k] && nb[k]) {
+      if ((rc = h->pinned(&stage[k], nb[k]))) return rc;
+      CK(cudaMemcpyAsync(stage[k], src[k], nb[k], cudaMemcpyDeviceToHost, h->st));
+    }
   CK(cudaStreamSynchronize(h->st));
-  if (out->kf_pose && g.n_kf) CK(cudaMemcpy(out->kf_pose, h->sa.kf_pose, 56 * (size_t)g.n_kf, cudaMemcpyDeviceToHost));
-  if (out->pt_xyz && g.n_pt) CK(cudaMemcpy(out->pt_xyz, h->sa.pt, 24 * (size_t)g.n_pt, cudaMemcpyDeviceToHost));
-  if (out->pl_coef && g.n_pl) CK(cudaMemcpy(out->pl_coef, h->sa.pl, 32 * (size_t)g.n_pl, cudaMemcpyDeviceToHost));
-  if (out->cu_state && g.n_cu) CK(cudaMemcpy(out->cu_state, h->sa.cu, 80 * (size_t)g.n_cu, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 4; k++)
+    if (stage[k]) std::memcpy(dst[k], stage[k], nb[k]);
+  h->hstage_off = keep;
   return PPO_OK;
 }
 
@@ -1040,6 +1128,32 @@ int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, do
 #undef DL
   return PPO_OK;
 }
+
+int ppo_ba_nccl_unique_id(char out[128]) {
+  g_nccl.load();
+  if (!g_nccl.ok || !out) return PPO_E_NCCL;
+  ncclUniqueId_ id;
+  if (g_nccl.GetUniqueId(&id) != 0) return PPO_E_NCCL;
+  std::memcpy(out, id.internal, 128);
+  return PPO_OK;
+}
+int ppo_ba_nccl_init(const char id_bytes[128], int rank, int world, int device, void **comm) {
+  g_nccl.load();
+  if (!g_nccl.ok || !id_bytes || !comm) return PPO_E_NCCL;
+  if (cudaSetDevice(device) != cudaSuccess) return PPO_E_CUDA;
+  ncclUniqueId_ id;
+  std::memcpy(id.internal, id_bytes, 128);
+  ncclComm_t c = nullptr;
+  if (g_nccl.CommInitRank(&c, world, id, rank) != 0) return PPO_E_NCCL;
+  *comm = c;
+  return PPO_OK;
+}
+int ppo_ba_nccl_destroy(void *comm) {
+  g_nccl.load();
+  if (!g_nccl.ok) return PPO_E_NCCL;
+  return comm ? (g_nccl.CommDestroy((ncclComm_t)comm) == 0 ? PPO_OK : PPO_E_NCCL) : PPO_OK;
+}
+long long ppo_ba_collective_count(const ppo_ba_handle *h) { return h ? h->collectives : 0; }
 
 int ppo_ba_set_shard(ppo_ba_handle *h, void *nccl_comm, int rank, int world) {
   if (!h || world < 1 || rank < 0 || rank >= world) return PPO_E_INVALID;

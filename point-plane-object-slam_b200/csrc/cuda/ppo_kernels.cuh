@@ -674,7 +674,7 @@ constexpr int SCHUR_SMALL_MAX = 24;  // landmarks with more blocks than this tak
 // Small landmarks stage their (contiguous) 6x3 blocks in shared memory once; the pair loop then walks the
 // (i2, entry) items with a carried counter (no divisions) and issues one RED.F64 per scalar of the 6x6 product.
 template <bool WHOLE_CTA>
-__global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const int *lm_list, int n_list, double lambda, int n_p, int ld) {
+__global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const int *lm_list, int n_list, double lambda, int n_p, int ld, int planes_write_S) {
   __shared__ double bd[SCHUR_WARPS][18];
   __shared__ double blk[WHOLE_CTA ? 1 : SCHUR_WARPS][WHOLE_CTA ? 1 : SCHUR_SMALL_MAX * 18];
   __shared__ int pid[WHOLE_CTA ? 1 : SCHUR_WARPS][WHOLE_CTA ? 1 : SCHUR_SMALL_MAX];
@@ -696,6 +696,7 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const in
 #pragma unroll
     for (int i = 0; i < 6; i++) g.Dinv[6 * (size_t)L + i] = D[i];
   }
+  if (L < g.n_pl && !planes_write_S) return;  // sharded window: plane landmarks are reduced by rank 0 only (Dinv is stored above)
   const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
   const double *Wg = g.Hpl + 18 * (size_t)b0;
   if (!WHOLE_CTA) {
@@ -785,7 +786,7 @@ __global__ void k_compose(DevGraph g, double lambda, int n_p, int ld) {
 // computeScale (levenberg.cpp:182-189).  One warp per landmark, lanes stride the contiguous blocks.
 // ---------------------------------------------------------------------------------------------
 constexpr int BS_WARPS = 8;
-__global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double lambda, double *scale_part) {
+__global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double lambda, double *scale_part, int planes_in_scale) {
   __shared__ double wsum[BS_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = blockIdx.x * BS_WARPS + warp;
@@ -820,7 +821,7 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double la
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           g.xl[3 * (size_t)L + i] = x[i];
-          sc += x[i] * (lambda * x[i] + bl[i]);
+          if (L >= g.n_pl || planes_in_scale) sc += x[i] * (lambda * x[i] + bl[i]);
         }
       }
     } else if (lane < 3) {
@@ -930,7 +931,7 @@ struct Scalars {
 // sums partial arrays in a fixed order; single block
 __global__ void k_scalars(DevGraph g, Scalars *out, const double *chi_a, int na, const double *chi_b, int nb, const double *chi_c, int nc,
                           const double *chi_d, int nd, double chi_const, const double *scale_part, int ns, double lambda, int n_p,
-                          const int *not_spd) {
+                          const int *not_spd, double *red /* [chi2, scale] for the cross-rank reduction, may be null */) {
   __shared__ double sm[8];
   double c = 0, s = 0;
   for (int i = threadIdx.x; i < na; i += 256) c += chi_a[i];
@@ -945,6 +946,10 @@ __global__ void k_scalars(DevGraph g, Scalars *out, const double *chi_a, int na,
     out->chi2 = c + chi_const;
     out->scale = s;
     out->not_spd = not_spd ? *not_spd : 0;
+    if (red) {
+      red[0] = out->chi2;
+      red[1] = out->scale;
+    }
   }
 }
 // max |diagonal| over the active blocks (computeLambdaInit, levenberg.cpp:166-180); single block
@@ -966,6 +971,20 @@ __global__ void k_max_diag(DevGraph g, Scalars *out) {
     __syncthreads();
   }
   if (threadIdx.x == 0) out->max_diag = sm[0];
+}
+// after the cross-rank reductions: copy the reduced scalars back into the Scalars block
+__global__ void k_scalars_from_red(Scalars *out, const double *red, int which) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (which == 0) {
+      out->chi2 = red[0];
+      out->scale = red[1];
+    } else {
+      out->max_diag = red[2];
+    }
+  }
+}
+__global__ void k_set_red_maxdiag(const Scalars *in, double *red) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) red[2] = in->max_diag;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -60,6 +60,11 @@ def load_library():
         lib.ppo_ba_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.ppo_ba_flush_l2.argtypes = [C.c_void_p]
         lib.ppo_ba_set_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.ppo_ba_nccl_unique_id.argtypes = [C.c_char_p]
+        lib.ppo_ba_nccl_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        lib.ppo_ba_nccl_destroy.argtypes = [C.c_void_p]
+        lib.ppo_ba_collective_count.argtypes = [C.c_void_p]
+        lib.ppo_ba_collective_count.restype = C.c_longlong
         lib.ppo_ba_debug_linearize.argtypes = [C.c_void_p, C.POINTER(C.c_int32 * 2), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ppo_ba_debug_solve.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         _LIB = lib
@@ -209,6 +214,12 @@ class LocalBA(Handle):
     def flush_l2(self):
         self._check(self.lib.ppo_ba_flush_l2(self.h), "flush_l2")
 
+    def set_shard(self, comm, rank, world):
+        self._check(self.lib.ppo_ba_set_shard(self.h, comm, rank, world), "set_shard")
+
+    def collective_count(self):
+        return int(self.lib.ppo_ba_collective_count(self.h))
+
     # reference-named entry points ---------------------------------------------------------------
     def LocalBACameraPlaneCuboids(self, graph, stop_flag=None):
         """Stages B-F of Optimizer::LocalBACameraPlaneCuboids on a flat graph; returns (state, result)."""
@@ -217,3 +228,23 @@ class LocalBA(Handle):
         return self.get_state(), res
 
     LocalBundleAdjustment = LocalBACameraPlaneCuboids
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    rc = load_library().ppo_ba_nccl_unique_id(buf)
+    if rc != A.PPO_OK:
+        raise EngineError(f"ppo_ba_nccl_unique_id rc={rc} (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
+def nccl_init(id_bytes, rank, world, device):
+    comm = C.c_void_p()
+    rc = load_library().ppo_ba_nccl_init(id_bytes, rank, world, device, C.byref(comm))
+    if rc != A.PPO_OK:
+        raise EngineError(f"ppo_ba_nccl_init rc={rc}")
+    return comm
+
+
+def nccl_destroy(comm):
+    load_library().ppo_ba_nccl_destroy(comm)
