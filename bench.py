@@ -91,7 +91,7 @@ def oracle_lm_rate(ppo, g, full_call):
     return iters / dt, iters, dt
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out_stream):
     """`--impl reference`: the reference's CPU path. It cannot be compiled here (Eigen3 missing),
     so the oracle port is timed, single-threaded like the reference (G2O_OPENMP off). Rank 0 only."""
     if rank != 0:
@@ -107,21 +107,31 @@ def run_reference(args, rank, world):
         tot_t += dt
     v = tot_it / tot_t
     sample = f"round 1 only (optimize({5}) = {tot_it // max(1, args.steps)} LM iterations) of the same window per step"
-    print(json.dumps({
+    print(file=out_stream, flush=True, *[json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": workload_name(args.config), "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})])
+
+
+def _protect_stdout():
+    """Libraries (NCCL version banner, ...) may print to fd 1; the contract is ONE JSON line on stdout.
+    fd 1 is pointed at stderr for the duration of the run and the JSON goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
 
 
 def main():
     args = parse()
+    out_stream = _protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out_stream)
         return
     import numpy as np
     import torch
@@ -241,7 +251,7 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                    "sample": f"one full local BA call ({it} LM iterations, {dt:.1f} s) of the same window on 1 host thread "
                                              f"(the reference runs g2o single-threaded); host has {os.cpu_count()} cores"}
-        print(json.dumps(out))
+        print(json.dumps(out), file=out_stream, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

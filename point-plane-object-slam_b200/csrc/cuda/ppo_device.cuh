@@ -38,7 +38,8 @@ struct DevGraph {
   double *pe_chi2;
   // linearisation work units: consecutive points packed so that a warp owns <= 32 edges
   int n_units;
-  const int *unit_pt0;  // n_units + 1
+  const int *unit_pt0;  // n_units + 1 (first point of each unit)
+  const int *unit_e0;   // n_units + 1 (first edge of each unit)
   // point edges grouped by key-frame, cut into chunks of <= 256 edges
   int n_chunks;
   const int *chunk_kf, *chunk_begin, *chunk_end, *kfe_edge;

@@ -396,6 +396,11 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   }
   g.n_units = (int)unit_pt0.size() - 1;
   { int *p; UP(p, unit_pt0); g.unit_pt0 = p; }
+  {
+    std::vector<int> unit_e0(unit_pt0.size());
+    for (size_t u = 0; u < unit_pt0.size(); u++) unit_e0[u] = rowptr[unit_pt0[u]];
+    int *p; UP(p, unit_e0); g.unit_e0 = p;
+  }
   // edges grouped by key-frame, chunks of <= POSE_THREADS
   std::vector<int> kf_cnt(g.n_kf + 1, 0), kfe(g.n_pe);
   for (int e = 0; e < g.n_pe; e++) kf_cnt[rec[e].kf + 1]++;

@@ -158,26 +158,23 @@ constexpr int STAGE_LD = 19;  // 18 doubles per 6x3 block + 1 pad: conflict-free
 // EdgeStereoSE3ProjectXYZ, landmark side): one warp owns a run of consecutive points with <= 32
 // edges, one lane per edge; Hll / bl come from a segmented warp-shuffle scan, the 6x3 Hpl blocks
 // are staged in shared memory and stored as one contiguous coalesced run.
-__global__ void __launch_bounds__(LIN_WARPS * 32) k_point_linearize(DevGraph g, DevState s, double *chi_part) {
+__global__ void __launch_bounds__(LIN_WARPS * 32, 4) k_point_linearize(DevGraph g, DevState s, double *chi_part) {
   __shared__ double stage[LIN_WARPS][32 * STAGE_LD];
   __shared__ double wsum[LIN_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * LIN_WARPS + warp;
   double rho_sum = 0;
   if (unit < g.n_units) {
-    const int p0 = g.unit_pt0[unit], p1 = g.unit_pt0[unit + 1];
-    const int e0 = g.pt_rowptr[p0], e1 = g.pt_rowptr[p1];
+    const int e0 = g.unit_e0[unit], e1 = g.unit_e0[unit + 1];
     for (int base = e0; base < e1; base += 32) {
       const int e = base + lane;
       const bool valid = e < e1;
       double acc[9];  // Hll xx xy xz yy yz zz, bl x y z
 #pragma unroll
       for (int i = 0; i < 9; i++) acc[i] = 0;
-      double hpl[18];
-#pragma unroll
-      for (int i = 0; i < 18; i++) hpl[i] = 0;
+      double *st = &stage[warp][lane * STAGE_LD];
       int key = -1;
-      bool lm_free = false;
+      bool lm_free = false, have_hpl = false;
       if (valid) {
         const PointEdgeRec rec = g.pe_rec[e];
         const int pt = g.pe_pt[e];
@@ -187,44 +184,76 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) k_point_linearize(DevGraph g, 
         lm_free = !ptfix;
         const bool active = !(fl & PPO_EF_LEVEL1_) && !(g.kf_fixed[rec.kf] && ptfix);
         if (active) {
-          double Rt[12], X[3];
+          double Rt[12], p[3], err[3];
           float intr[5];
 #pragma unroll
           for (int i = 0; i < 12; i++) Rt[i] = __ldg(&s.kf_Rt[12 * rec.kf + i]);
 #pragma unroll
-          for (int i = 0; i < 3; i++) X[i] = s.pt[3 * pt + i];
-#pragma unroll
           for (int i = 0; i < 5; i++) intr[i] = __ldg(&g.kf_intr[5 * rec.kf + i]);
-          PointEdgeLin L;
-          point_edge_linearize(Rt, X, intr, rec, L);
+          {
+            const double X0 = s.pt[3 * pt], X1 = s.pt[3 * pt + 1], X2 = s.pt[3 * pt + 2];
+            p[0] = Rt[0] * X0 + Rt[1] * X1 + Rt[2] * X2 + Rt[9];
+            p[1] = Rt[3] * X0 + Rt[4] * X1 + Rt[5] * X2 + Rt[10];
+            p[2] = Rt[6] * X0 + Rt[7] * X1 + Rt[8] * X2 + Rt[11];
+          }
+          const int D = point_edge_error(p, intr, rec.u, rec.v, rec.ur, err);
           const double is2 = (double)g.pe_is2[e];
-          const double chi2 = L.err[0] * (is2 * L.err[0]) + L.err[1] * (is2 * L.err[1]) + L.err[2] * (is2 * L.err[2]);
+          const double chi2 = err[0] * (is2 * err[0]) + err[1] * (is2 * err[1]) + err[2] * (is2 * err[2]);
           g.pe_chi2[e] = chi2;
           double rho0 = chi2, w = 1.0;
-          if (fl & PPO_EF_ROBUST_) w = huber_w(chi2, L.D == 2 ? g.huber_mono : g.huber_stereo, &rho0);
+          if (fl & PPO_EF_ROBUST_) w = huber_w(chi2, D == 2 ? g.huber_mono : g.huber_stereo, &rho0);
           rho_sum += rho0;
           const double ws = w * is2;
           if (!ptfix) {
-            // Hll += Jpt^T (w Omega) Jpt ; bl += -Jpt^T (w Omega) r
-            double wj[9];
+            const double fx = intr[0], fy = intr[1], bf = D == 3 ? (double)intr[4] : 0.0;
+            const double x = p[0], y = p[1], z = p[2], z_2 = z * z;
+            // weighted point Jacobian wj = (w Omega) * Jpt, Jpt = d(residual)/d(point) (types_six_dof_expmap.cpp:147-156,234-244)
+            double wj[9], Jpt[9];
+            {
+              const double a00 = -fx / z, a02 = fx * x / z_2, a11 = -fy / z, a12 = fy * y / z_2;
 #pragma unroll
-            for (int i = 0; i < 9; i++) wj[i] = ws * L.Jpt[i];
-            acc[0] = wj[0] * L.Jpt[0] + wj[3] * L.Jpt[3] + wj[6] * L.Jpt[6];
-            acc[1] = wj[0] * L.Jpt[1] + wj[3] * L.Jpt[4] + wj[6] * L.Jpt[7];
-            acc[2] = wj[0] * L.Jpt[2] + wj[3] * L.Jpt[5] + wj[6] * L.Jpt[8];
-            acc[3] = wj[1] * L.Jpt[1] + wj[4] * L.Jpt[4] + wj[7] * L.Jpt[7];
-            acc[4] = wj[1] * L.Jpt[2] + wj[4] * L.Jpt[5] + wj[7] * L.Jpt[8];
-            acc[5] = wj[2] * L.Jpt[2] + wj[5] * L.Jpt[5] + wj[8] * L.Jpt[8];
+              for (int j = 0; j < 3; j++) {
+                Jpt[j] = a00 * Rt[j] + a02 * Rt[6 + j];
+                Jpt[3 + j] = a11 * Rt[3 + j] + a12 * Rt[6 + j];
+                Jpt[6 + j] = D == 3 ? Jpt[j] - bf * Rt[6 + j] / z_2 : 0.0;
+              }
+            }
 #pragma unroll
-            for (int a = 0; a < 3; a++) acc[6 + a] = -(wj[a] * L.err[0] + wj[3 + a] * L.err[1] + wj[6 + a] * L.err[2]);
+            for (int i = 0; i < 9; i++) wj[i] = ws * Jpt[i];
+            acc[0] = wj[0] * Jpt[0] + wj[3] * Jpt[3] + wj[6] * Jpt[6];
+            acc[1] = wj[0] * Jpt[1] + wj[3] * Jpt[4] + wj[6] * Jpt[7];
+            acc[2] = wj[0] * Jpt[2] + wj[3] * Jpt[5] + wj[6] * Jpt[8];
+            acc[3] = wj[1] * Jpt[1] + wj[4] * Jpt[4] + wj[7] * Jpt[7];
+            acc[4] = wj[1] * Jpt[2] + wj[4] * Jpt[5] + wj[7] * Jpt[8];
+            acc[5] = wj[2] * Jpt[2] + wj[5] * Jpt[5] + wj[8] * Jpt[8];
+#pragma unroll
+            for (int a = 0; a < 3; a++) acc[6 + a] = -(wj[a] * err[0] + wj[3 + a] * err[1] + wj[6 + a] * err[2]);
             if (g.ent_pidx[g.n_slots + e] >= 0) {
-#pragma unroll
-              for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) hpl[a * 3 + c] = L.Jkf[a] * wj[c] + L.Jkf[6 + a] * wj[3 + c] + L.Jkf[12 + a] * wj[6 + c];
+              have_hpl = true;
+              // pose Jacobian one column at a time (types_six_dof_expmap.cpp:158-170,246-265): Hpl row a = Jkf(:,a)^T wj
+              const double sm = D == 3 ? 1.0 : 0.0;
+#define PPO_HPL_ROW(a, j0, j1, j2)                                   \
+  {                                                                  \
+    const double q0 = (j0), q1 = (j1), q2 = sm * (j2);               \
+    st[3 * (a)] = q0 * wj[0] + q1 * wj[3] + q2 * wj[6];              \
+    st[3 * (a) + 1] = q0 * wj[1] + q1 * wj[4] + q2 * wj[7];          \
+    st[3 * (a) + 2] = q0 * wj[2] + q1 * wj[5] + q2 * wj[8];          \
+  }
+              const double k00 = x * y / z_2 * fx, k01 = -(1 + (x * x / z_2)) * fx, k02 = y / z * fx, k03 = -1. / z * fx, k05 = x / z_2 * fx;
+              PPO_HPL_ROW(0, k00, (1 + y * y / z_2) * fy, k00 - bf * y / z_2)
+              PPO_HPL_ROW(1, k01, -x * y / z_2 * fy, k01 + bf * x / z_2)
+              PPO_HPL_ROW(2, k02, -x / z * fy, k02)
+              PPO_HPL_ROW(3, k03, 0.0, k03)
+              PPO_HPL_ROW(4, 0.0, -1. / z * fy, 0.0)
+              PPO_HPL_ROW(5, k05, y / z_2 * fy, k05 - bf / z_2)
+#undef PPO_HPL_ROW
             }
           }
         }
+      }
+      if (!have_hpl) {
+#pragma unroll
+        for (int i = 0; i < 18; i++) st[i] = 0.0;
       }
       // segmented inclusive scan over the lanes of one point
 #pragma unroll
@@ -246,9 +275,7 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) k_point_linearize(DevGraph g, 
 #pragma unroll
         for (int i = 0; i < 3; i++) atomicAdd(&g.bl[3 * (size_t)L + i], acc[6 + i]);
       }
-      // Hpl blocks of this run: stage and store contiguously
-#pragma unroll
-      for (int i = 0; i < 18; i++) stage[warp][lane * STAGE_LD + i] = hpl[i];
+      // Hpl blocks of this run: staged above, stored as one contiguous coalesced run
       __syncwarp();
       const int n = (min(e1, base + 32) - base) * 18;
       double *dst = g.Hpl + 18 * (size_t)(g.n_slots + base);
@@ -724,27 +751,41 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const in
     double *Srow = g.S + (size_t)(6 * p1) * ld;
     if (lane < 6)  // reduced gradient: bschur_i -= W1 * Dinv * bl   (coefficients, :403-405)
       atomicAdd(&Srow[(size_t)lane * ld + n_p], -(W1[3 * lane] * db[0] + W1[3 * lane + 1] * db[1] + W1[3 * lane + 2] * db[2]));
-    // items (i2 >= i1, entry 0..35), lane-strided with a carried (i2, en) counter
-    int i2 = i1, en = lane;
-    while (i2 < nblk) {
-      const int p2 = WHOLE_CTA ? g.ent_pidx[b0 + i2] : pid[warp][i2];
-      if (p2 >= 0) {
-        const int r = (en * 43) >> 8, c = en - 6 * r;  // en / 6, en % 6 for en < 36
-        const double *W2 = (WHOLE_CTA ? Wg + 18 * (size_t)i2 : &blk[warp][18 * i2]) + 3 * c;
-        const double v = bd[warp][3 * r] * W2[0] + bd[warp][3 * r + 1] * W2[1] + bd[warp][3 * r + 2] * W2[2];
-        if (p1 < p2 || i1 == i2) {
-          atomicAdd(&Srow[(size_t)r * ld + 6 * p2 + c], -v);
-        } else if (p1 > p2) {  // keep the upper block triangle: write the transposed entry
-          atomicAdd(&g.S[(size_t)(6 * p2 + c) * ld + 6 * p1 + r], -v);
-        } else {  // two different entries on one key-frame: W1 D W2^T + W2 D W1^T on the diagonal block
-          atomicAdd(&Srow[(size_t)r * ld + 6 * p1 + c], -v);
-          atomicAdd(&Srow[(size_t)c * ld + 6 * p1 + r], -v);
+    // 6x6 products for all i2 >= i1.  Entry (r,c) of a pair is fixed per lane: pass A covers entries 0..31 of one pair
+    // (lane = 6 r + c), pass B the remaining entries 32..35 (r = 5, c = 2..5) of EIGHT pairs at once (4 lanes per pair):
+    // no per-item index arithmetic, bd rows live in registers, one RED.F64 per scalar.
+    const int rA = lane / 6, cA = lane - 6 * rA, cB = 2 + (lane & 3), tB = lane >> 2;
+    const double bA0 = bd[warp][3 * rA], bA1 = bd[warp][3 * rA + 1], bA2 = bd[warp][3 * rA + 2];
+    const double bB0 = bd[warp][15], bB1 = bd[warp][16], bB2 = bd[warp][17];
+    double *SA = Srow + (size_t)rA * ld + cA, *SB = Srow + (size_t)5 * ld + cB;
+    for (int i2 = i1; i2 < nblk; i2 += 8) {
+      const int tmax = min(8, nblk - i2);
+      for (int t = 0; t < tmax; t++) {
+        const int j2 = i2 + t;
+        const int p2 = WHOLE_CTA ? g.ent_pidx[b0 + j2] : pid[warp][j2];
+        if (p2 < 0) continue;  // warp-uniform
+        const double *W2 = (WHOLE_CTA ? Wg + 18 * (size_t)j2 : &blk[warp][18 * j2]) + 3 * cA;
+        const double v = bA0 * W2[0] + bA1 * W2[1] + bA2 * W2[2];
+        if (p1 < p2 || j2 == i1) atomicAdd(SA + 6 * p2, -v);
+        else if (p1 > p2) atomicAdd(&g.S[(size_t)(6 * p2 + cA) * ld + 6 * p1 + rA], -v);  // keep the upper block triangle
+        else {  // two different entries on one key-frame: W1 D W2^T + W2 D W1^T on the diagonal block
+          atomicAdd(SA + 6 * p1, -v);
+          atomicAdd(&g.S[(size_t)(6 * p1 + cA) * ld + 6 * p1 + rA], -v);
         }
       }
-      en += 32;
-      if (en >= 36) {
-        en -= 36;
-        i2++;
+      if (tB < tmax) {
+        const int j2 = i2 + tB;
+        const int p2 = WHOLE_CTA ? g.ent_pidx[b0 + j2] : pid[warp][j2];
+        if (p2 >= 0) {
+          const double *W2 = (WHOLE_CTA ? Wg + 18 * (size_t)j2 : &blk[warp][18 * j2]) + 3 * cB;
+          const double v = bB0 * W2[0] + bB1 * W2[1] + bB2 * W2[2];
+          if (p1 < p2 || j2 == i1) atomicAdd(SB + 6 * p2, -v);
+          else if (p1 > p2) atomicAdd(&g.S[(size_t)(6 * p2 + cB) * ld + 6 * p1 + 5], -v);
+          else {
+            atomicAdd(SB + 6 * p1, -v);
+            atomicAdd(&g.S[(size_t)(6 * p1 + cB) * ld + 6 * p1 + 5], -v);
+          }
+        }
       }
     }
   }
