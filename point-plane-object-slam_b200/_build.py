@@ -97,8 +97,23 @@ def build_cuda(force=False):
     return out
 
 
+def build_shim(force=False):
+    """Optimizer.cc replacement (host shim) + the mock-map harness it is tested with; links the C-ABI library."""
+    os.makedirs(LIB, exist_ok=True)
+    out = os.path.join(LIB, "libppo_shim_mock.so")
+    host = os.path.join(CSRC, "host")
+    srcs = [os.path.join(host, "ppo_optimizer_shim.cpp"), os.path.join(host, "ppo_mock_world.cpp")]
+    deps = srcs + [os.path.join(host, "ppo_mock_slam.h"), os.path.join(host, "ppo_convert.h"), os.path.join(ROOT, "include", "ppo_ba.h"),
+                   os.path.join(LIB, "libppo_ba.so")]
+    if force or _newer(out, deps):
+        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out] + srcs + ["-L", LIB, "-lppo_ba", "-Wl,-rpath,$ORIGIN"])
+    return out
+
+
 def build_all(force=False):
-    return {"synth": build_synth(force), "oracle": build_oracle(force), "cuda": build_cuda(force)}
+    out = {"synth": build_synth(force), "oracle": build_oracle(force), "cuda": build_cuda(force)}
+    out["shim"] = build_shim(force)
+    return out
 
 
 if __name__ == "__main__":

@@ -1,0 +1,195 @@
+// Test harness for the Optimizer shim: builds a mock SLAM map (ppo_mock_slam.h) out of a flat synthetic graph —
+// the inverse of the flattening the shim performs — calls ORB_SLAM2::Optimizer::LocalBACameraPlaneCuboids /
+// LocalBundleAdjustment exactly like LocalMapping::Run does (src/LocalMapping.cc:100,107) and reads the written-back
+// map state out again.  Input generation / bookkeeping only.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../../include/ppo_ba.h"
+#include "ppo_convert.h"
+#include "ppo_mock_slam.h"
+
+namespace ORB_SLAM2 {
+// src/Parameters.cc:43-74 defaults relevant to the BA (flags are set per test from the graph content)
+bool optimize_with_cuboid_plane = false, optimize_with_plane_3d = false, optimize_with_cuboid_2d = false, optimize_with_corners_2d = false,
+     optimize_with_pt_obj_3d = false;
+double ba_weight_bbox = 1.0, ba_weight_corner = 1.0, thHuberBbox2d = 80.0, thHuberConer2d = 10.0;
+double plane_angle_info = 1.0, plane_dist_info = 100.0, plane_chi = 500.0, cuboid_plane_angle_info = 2.0, cuboid_plane_dist_info = 100.0,
+       cuboid_plane_chi = 500.0;
+}  // namespace ORB_SLAM2
+
+using namespace ORB_SLAM2;
+
+extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int fixPoint, unsigned char *stop, ppo_ba_state *out,
+                            int32_t counts[4] /* erased point obs, erased plane obs, SetPose calls, UpdateNormalAndDepth calls */) {
+  std::vector<std::unique_ptr<KeyFrame>> kfs;
+  std::vector<std::unique_ptr<MapPoint>> pts, extra_pts;
+  std::vector<std::unique_ptr<MapPlane>> pls;
+  std::vector<std::unique_ptr<MapCuboid>> cus, local_cus;
+  Map map;
+  float inv_sigma2[8];
+  {
+    float sf = 1.0f;
+    for (int i = 0; i < 8; i++) {
+      inv_sigma2[i] = 1.0f / (sf * sf);
+      sf *= 1.2f;
+    }
+  }
+  // ---- key-frames: slot i -> mnId i; local = not fixed or slot 0; pKF = first free local key-frame --------------
+  for (int i = 0; i < g->n_kf; i++) {
+    const float *in = &g->kf_intr[5 * i];
+    kfs.emplace_back(new KeyFrame(in[0], in[1], in[2], in[3], in[4]));
+    KeyFrame *kf = kfs.back().get();
+    kf->mnId = i;
+    float T[16];
+    ppo::pose7_to_tcw_float(&g->kf_pose[7 * i], T);
+    cv::Mat m(4, 4, CV_32F);
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) m.at<float>(r, c) = T[4 * r + c];
+    kf->Tcw = m;
+    kf->mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + 8);
+  }
+  auto is_local = [&](int i) { return i == 0 || !g->kf_fixed[i]; };
+  int pkf = -1;
+  for (int i = 0; i < g->n_kf; i++)
+    if (!g->kf_fixed[i]) { pkf = i; break; }
+  if (pkf < 0) pkf = 0;
+  for (int i = 0; i < g->n_kf; i++)
+    if (i != pkf && is_local(i)) kfs[pkf]->mvpOrderedConnectedKeyFrames.push_back(kfs[i].get());
+  // ---- map points and their observations ---------------------------------------------------------------------------
+  for (int p = 0; p < g->n_pt; p++) {
+    pts.emplace_back(new MapPoint());
+    MapPoint *mp = pts.back().get();
+    mp->mnId = p;
+    cv::Mat X(3, 1, CV_32F);
+    for (int k = 0; k < 3; k++) X.at<float>(k, 0) = (float)g->pt_xyz[3 * p + k];
+    mp->mWorldPos = X;
+    for (int e = g->pt_rowptr[p]; e < g->pt_rowptr[p + 1]; e++) {
+      KeyFrame *kf = kfs[g->pe_kf[e]].get();
+      const size_t idx = kf->mvKeysUn.size();
+      int oct = 0;
+      float best = 1e30f;
+      for (int l = 0; l < 8; l++)
+        if (std::fabs(inv_sigma2[l] - g->pe_invsigma2[e]) < best) best = std::fabs(inv_sigma2[l] - g->pe_invsigma2[e]), oct = l;
+      kf->mvKeysUn.push_back(cv::KeyPoint{{g->pe_obs[3 * e], g->pe_obs[3 * e + 1]}, oct});
+      kf->mvuRight.push_back(g->pe_obs[3 * e + 2]);
+      mp->mObservations[kf] = idx;
+      mp->nObs += g->pe_obs[3 * e + 2] >= 0 ? 2 : 1;  // MapPoint.cc:108-111
+      if (is_local(g->pe_kf[e])) kf->mvpMapPoints.push_back(mp);
+    }
+  }
+  // ---- planes -----------------------------------------------------------------------------------------------------------
+  for (int p = 0; p < g->n_pl; p++) {
+    pls.emplace_back(new MapPlane());
+    MapPlane *pl = pls.back().get();
+    pl->mnId = p;
+    cv::Mat m(4, 1, CV_32F);
+    for (int k = 0; k < 4; k++) m.at<float>(k, 0) = (float)g->pl_coef[4 * p + k];
+    pl->mWorldPos = m;
+  }
+  for (int e = 0; e < g->n_ple; e++) {
+    KeyFrame *kf = kfs[g->ple_kf[e]].get();
+    MapPlane *pl = pls[g->ple_plane[e]].get();
+    cv::Mat m(4, 1, CV_32F);
+    for (int k = 0; k < 4; k++) m.at<float>(k, 0) = (float)g->ple_meas[4 * e + k];
+    const int idx = (int)kf->mvPlaneCoefficients.size();
+    kf->mvPlaneCoefficients.push_back(m);
+    if (g->ple_kind[e] == PPO_PLANE_OBS) {
+      pl->mObservations[kf] = idx;
+      if (is_local(g->ple_kf[e])) kf->mvpMapPlanes.push_back(pl);
+    } else if (g->ple_kind[e] == PPO_PLANE_VER) pl->mVerObservations[kf] = idx;
+    else pl->mParObservations[kf] = idx;
+  }
+  // ---- cuboids --------------------------------------------------------------------------------------------------------------
+  for (int c = 0; c < g->n_cu; c++) {
+    cus.emplace_back(new MapCuboid());
+    MapCuboid *cu = cus.back().get();
+    cu->mnId = c;
+    const double *s = &g->cu_state[10 * c];
+    const double p7[7] = {s[3], s[4], s[5], s[6], s[0], s[1], s[2]};
+    std::memcpy(cu->cuboid_global_data.pose7, p7, sizeof p7);
+    for (int k = 0; k < 3; k++) cu->cuboid_global_data.scale[k] = s[7 + k];
+  }
+  bool any_bbox = false, any_corner = false;
+  for (int e = 0; e < g->n_cbe; e++) {
+    KeyFrame *kf = kfs[g->cbe_kf[e]].get();
+    MapCuboid *cu = cus[g->cbe_cuboid[e]].get();
+    MapCuboid *lo = nullptr;
+    auto it = cu->mObservations.find(kf);
+    if (it == cu->mObservations.end()) {
+      local_cus.emplace_back(new MapCuboid());
+      lo = local_cus.back().get();
+      lo->bbox_2d = cv::Rect{50, 50, 100, 100};  // inside the 5 px margin (the flat graph only holds edges that passed the test)
+      lo->meas_quality = std::sqrt(g->cbe_info[e]);
+      cu->mObservations[kf] = kf->local_cuboids.size();
+      kf->local_cuboids.push_back(lo);
+      if (is_local(g->cbe_kf[e])) kf->mvpMapCuboid.push_back(cu);
+    } else {
+      lo = kf->local_cuboids[it->second];
+    }
+    if (g->cbe_kind[e] == PPO_CUBOID_BBOX) {
+      any_bbox = true;
+      for (int k = 0; k < 4; k++) lo->bbox_vec(k) = g->cbe_meas[16 * e + k];
+    } else {
+      any_corner = true;
+      for (int k = 0; k < 8; k++) lo->box_corners_2d(0, k) = g->cbe_meas[16 * e + 2 * k], lo->box_corners_2d(1, k) = g->cbe_meas[16 * e + 2 * k + 1];
+    }
+  }
+  for (int e = 0; e < g->n_pce; e++) {
+    MapCuboid *cu = cus[g->pce_cuboid[e]].get();
+    for (int j = g->pce_rowptr[e]; j < g->pce_rowptr[e + 1]; j++) {
+      extra_pts.emplace_back(new MapPoint());
+      MapPoint *mp = extra_pts.back().get();
+      mp->mnId = 1000000 + j;
+      cv::Mat X(3, 1, CV_32F);
+      for (int k = 0; k < 3; k++) X.at<float>(k, 0) = (float)g->pce_pts[3 * j + k];
+      mp->mWorldPos = X;
+      mp->MapObjObservations[cu] = 3;  // > point_object_threshold (Optimizer.cc:2559,2573)
+      cu->mappoints_unique_own.push_back(mp);
+    }
+  }
+  for (int e = 0; e < g->n_cpe; e++) {
+    MapPlane *pl = pls[g->cpe_plane[e]].get();
+    pl->asso_cuboid_id = g->cpe_cuboid[e];
+    for (int k = 0; k < 3; k++) pl->asso_cuboid_meas(k) = g->cpe_meas[3 * e + k];
+  }
+  optimize_with_plane_3d = g->n_ple > 0;
+  optimize_with_cuboid_2d = any_bbox;
+  optimize_with_corners_2d = any_corner;
+  optimize_with_pt_obj_3d = g->n_pce > 0;
+  optimize_with_cuboid_plane = g->n_cpe > 0;
+
+  // ---- the call LocalMapping::Run makes ------------------------------------------------------------------------------------------
+  bool stop_flag = stop ? (*stop != 0) : false;
+  if (mixed) Optimizer::LocalBACameraPlaneCuboids(kfs[pkf].get(), &stop_flag, &map, fixCamera != 0, fixPoint != 0);
+  else Optimizer::LocalBundleAdjustment(kfs[pkf].get(), &stop_flag, &map);
+
+  // ---- read the map back ------------------------------------------------------------------------------------------------------------
+  counts[0] = counts[1] = counts[2] = counts[3] = 0;
+  for (int i = 0; i < g->n_kf; i++) {
+    float T[16];
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) T[4 * r + c] = kfs[i]->Tcw.at<float>(r, c);
+    ppo::tcw_float_to_pose7(T, &out->kf_pose[7 * i]);
+    counts[2] += kfs[i]->n_setpose;
+    counts[1] += (int)kfs[i]->erased_planes.size();
+  }
+  for (int p = 0; p < g->n_pt; p++) {
+    for (int k = 0; k < 3; k++) out->pt_xyz[3 * p + k] = pts[p]->mWorldPos.at<float>(k, 0);
+    counts[0] += (int)pts[p]->erased.size();
+    counts[3] += pts[p]->n_updates;
+  }
+  for (int p = 0; p < g->n_pl; p++)
+    for (int k = 0; k < 4; k++) out->pl_coef[4 * p + k] = pls[p]->mWorldPos.at<float>(k, 0);
+  for (int c = 0; c < g->n_cu; c++) {
+    const g2o::cuboid &q = cus[c]->obj_been_optimized ? cus[c]->cuboid_global_opti : cus[c]->cuboid_global_data;
+    double *s = &out->cu_state[10 * c];
+    s[0] = q.pose7[4]; s[1] = q.pose7[5]; s[2] = q.pose7[6];
+    s[3] = q.pose7[0]; s[4] = q.pose7[1]; s[5] = q.pose7[2]; s[6] = q.pose7[3];
+    s[7] = q.scale[0]; s[8] = q.scale[1]; s[9] = q.scale[2];
+  }
+  return 0;
+}

@@ -1,0 +1,481 @@
+// Drop-in replacement for the two local-BA entry points of src/Optimizer.cc:
+//   void Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*)                         (:461-786)
+//   void Optimizer::LocalBACameraPlaneCuboids(KeyFrame*, bool*, Map*, bool, bool)         (:1994-2967)
+// Stage A (window collection), stage B (graph flattening instead of g2o vertex/edge construction), stage F
+// (erase lists) and stage G (write-back) stay on the host and follow the reference statement by statement;
+// stages C-E (optimize(5), outlier pass, optimize(10)) run on the GPU through the C-ABI (include/ppo_ba.h).
+// Compiled against the real ORB-SLAM2 headers with -DPPO_WITH_ORB_SLAM2, otherwise against ppo_mock_slam.h.
+#ifdef PPO_WITH_ORB_SLAM2
+#include "Converter.h"
+#include "KeyFrame.h"
+#include "Map.h"
+#include "MapCuboid.h"
+#include "MapPlane.h"
+#include "MapPoint.h"
+#include "Optimizer.h"
+#include "Parameters.h"
+#else
+#include "ppo_mock_slam.h"
+#endif
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../../include/ppo_ba.h"
+#include "ppo_convert.h"
+
+namespace ppo_shim {
+
+// ---- adapters between the reference's value types and flat doubles ------------------------------------
+#ifdef PPO_WITH_ORB_SLAM2
+inline void cuboid_to10(const g2o::cuboid &c, double o[10]) {
+  auto v = c.toVector();  // [t(3) q(xyzw) scale(3)], g2o_cuboid.h:166-172
+  for (int i = 0; i < 10; i++) o[i] = v(i);
+}
+inline void cuboid_from10(const double v[10], g2o::cuboid &c) {
+  Eigen::Matrix<double, 10, 1> e;
+  for (int i = 0; i < 10; i++) e(i) = v[i];
+  c.fromVector(e);
+}
+#else
+inline void cuboid_to10(const g2o::cuboid &c, double o[10]) {
+  o[0] = c.pose7[4]; o[1] = c.pose7[5]; o[2] = c.pose7[6];
+  o[3] = c.pose7[0]; o[4] = c.pose7[1]; o[5] = c.pose7[2]; o[6] = c.pose7[3];
+  o[7] = c.scale[0]; o[8] = c.scale[1]; o[9] = c.scale[2];
+}
+inline void cuboid_from10(const double v[10], g2o::cuboid &c) {
+  c.pose7[4] = v[0]; c.pose7[5] = v[1]; c.pose7[6] = v[2];
+  c.pose7[0] = v[3]; c.pose7[1] = v[4]; c.pose7[2] = v[5]; c.pose7[3] = v[6];
+  c.scale[0] = v[7]; c.scale[1] = v[8]; c.scale[2] = v[9];
+}
+#endif
+inline void mat_to_float16(const cv::Mat &T, float o[16]) {
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) o[4 * r + c] = T.at<float>(r, c);
+}
+inline cv::Mat float16_to_mat(const float T[16]) {
+  cv::Mat m(4, 4, CV_32F);
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) m.at<float>(r, c) = T[4 * r + c];
+  return m;
+}
+
+// ---- the flat graph under construction ----------------------------------------------------------------------
+struct Flat {
+  std::vector<double> kf_pose, pt_xyz, pl_coef, cu_state, ple_meas, ple_info, cbe_meas, cbe_info, pce_pts, cpe_meas, cpe_info;
+  std::vector<uint8_t> kf_fixed, pt_fixed, cu_flags, ple_kind, cbe_kind;
+  std::vector<float> kf_intr, pe_obs, pe_invsigma2;
+  std::vector<int32_t> pt_rowptr, pe_kf, ple_plane, ple_kf, cbe_kf, cbe_cuboid, pce_cuboid, pce_rowptr, cpe_cuboid, cpe_plane;
+  ppo_ba_graph g;
+  void publish() {
+    std::memset(&g, 0, sizeof g);
+    g.n_kf = (int32_t)kf_fixed.size(); g.kf_pose = kf_pose.data(); g.kf_fixed = kf_fixed.data(); g.kf_intr = kf_intr.data();
+    g.n_pt = (int32_t)(pt_xyz.size() / 3); g.pt_xyz = pt_xyz.data(); g.pt_fixed = pt_fixed.data();
+    g.n_pl = (int32_t)(pl_coef.size() / 4); g.pl_coef = pl_coef.data();
+    g.n_cu = (int32_t)(cu_state.size() / 10); g.cu_state = cu_state.data(); g.cu_flags = cu_flags.data();
+    if (pt_rowptr.empty()) pt_rowptr.push_back(0);
+    g.pt_rowptr = pt_rowptr.data(); g.n_pe = (int32_t)pe_kf.size(); g.pe_kf = pe_kf.data(); g.pe_obs = pe_obs.data(); g.pe_invsigma2 = pe_invsigma2.data();
+    g.n_ple = (int32_t)ple_plane.size(); g.ple_plane = ple_plane.data(); g.ple_kf = ple_kf.data(); g.ple_kind = ple_kind.data();
+    g.ple_meas = ple_meas.data(); g.ple_info = ple_info.data();
+    g.n_cbe = (int32_t)cbe_kf.size(); g.cbe_kf = cbe_kf.data(); g.cbe_cuboid = cbe_cuboid.data(); g.cbe_kind = cbe_kind.data();
+    g.cbe_meas = cbe_meas.data(); g.cbe_info = cbe_info.data();
+    if (pce_rowptr.empty()) pce_rowptr.push_back(0);
+    g.n_pce = (int32_t)pce_cuboid.size(); g.pce_cuboid = pce_cuboid.data(); g.pce_rowptr = pce_rowptr.data(); g.pce_pts = pce_pts.data();
+    g.n_cpe = (int32_t)cpe_cuboid.size(); g.cpe_cuboid = cpe_cuboid.data(); g.cpe_plane = cpe_plane.data(); g.cpe_meas = cpe_meas.data();
+    g.cpe_info = cpe_info.data();
+  }
+};
+
+static std::mutex g_mutex;  // the reference calls the BA from the LocalMapping thread only; LoopClosing may race
+static ppo_ba_handle *g_handle = nullptr;
+static int g_device = 0;
+static Flat g_last;  // last flattened window (introspection for tests / logging)
+static ppo_ba_result g_last_result;
+static int g_last_rc = 0;
+
+static ppo_ba_handle *engine(const ppo_ba_params &P) {
+  if (g_handle) ppo_ba_destroy(g_handle), g_handle = nullptr;  // parameters are re-snapshotted per call like the reference's globals
+  if (ppo_ba_create(&P, g_device, &g_handle) != PPO_OK) g_handle = nullptr;
+  return g_handle;
+}
+
+using namespace ORB_SLAM2;
+
+struct Window {
+  std::vector<KeyFrame *> lLocalKeyFrames, lFixedCameras;
+  std::vector<MapPoint *> lLocalMapPoints;
+  std::vector<MapCuboid *> lLocalMapCuboids;
+  std::vector<MapPlane *> lLocalMapPlanes;
+};
+
+// stage A: Optimizer.cc:1997-2100 (mixed) / :463-514 (points only)
+static void collect(KeyFrame *pKF, bool mixed, Window &w) {
+  w.lLocalKeyFrames.push_back(pKF);
+  pKF->mnBALocalForKF = pKF->mnId;
+  const std::vector<KeyFrame *> vNeighKFs = pKF->GetVectorCovisibleKeyFrames();
+  for (KeyFrame *pKFi : vNeighKFs) {
+    pKFi->mnBALocalForKF = pKF->mnId;
+    if (!pKFi->isBad()) w.lLocalKeyFrames.push_back(pKFi);
+  }
+  for (KeyFrame *kf : w.lLocalKeyFrames) {
+    std::vector<MapPoint *> vpMPs = kf->GetMapPointMatches();
+    for (MapPoint *pMP : vpMPs)
+      if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) {
+        w.lLocalMapPoints.push_back(pMP);
+        pMP->mnBALocalForKF = pKF->mnId;
+      }
+  }
+  if (mixed) {
+    for (KeyFrame *kf : w.lLocalKeyFrames)
+      for (MapCuboid *pMC : kf->mvpMapCuboid)
+        if (pMC && !pMC->isBad() && pMC->mnBALocalForKF != pKF->mnId) {
+          w.lLocalMapCuboids.push_back(pMC);
+          pMC->mnBALocalForKF = pKF->mnId;
+        }
+    for (KeyFrame *kf : w.lLocalKeyFrames)
+      for (MapPlane *pMP : kf->mvpMapPlanes)
+        if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) {
+          w.lLocalMapPlanes.push_back(pMP);
+          pMP->mnBALocalForKF = pKF->mnId;
+        }
+  }
+  auto add_fixed = [&](KeyFrame *pKFi) {
+    if (pKFi->mnBALocalForKF != pKF->mnId && pKFi->mnBAFixedForKF != pKF->mnId) {
+      pKFi->mnBAFixedForKF = pKF->mnId;
+      if (!pKFi->isBad()) w.lFixedCameras.push_back(pKFi);
+    }
+  };
+  for (MapPoint *pMP : w.lLocalMapPoints) {
+    std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
+    for (auto &mit : observations) add_fixed(mit.first);
+  }
+  if (mixed)
+    for (MapCuboid *pMC : w.lLocalMapCuboids) {
+      std::unordered_map<KeyFrame *, size_t> observations = pMC->GetObservations();
+      for (auto &mit : observations) add_fixed(mit.first);
+    }
+}
+
+static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fixCamera, bool fixPoint) {
+  std::lock_guard<std::mutex> lk(g_mutex);
+  Window w;
+  collect(pKF, mixed, w);
+
+  // ---- stage B: flatten (vertices) ------------------------------------------------------------------
+  Flat &F = g_last;
+  F = Flat();
+  // key-frame slots ordered by mnId = g2o's Hessian order (core/sparse_optimizer.cpp:166-190,482-487)
+  struct Slot { KeyFrame *kf; bool fixed; };
+  std::vector<Slot> slots;
+  for (KeyFrame *kf : w.lLocalKeyFrames) slots.push_back({kf, kf->mnId == 0 || fixCamera});  // Optimizer.cc:2126-2128
+  for (KeyFrame *kf : w.lFixedCameras) slots.push_back({kf, true});                        // :2141
+  std::sort(slots.begin(), slots.end(), [](const Slot &a, const Slot &b) { return a.kf->mnId < b.kf->mnId; });
+  std::map<KeyFrame *, int> kf_slot;
+  for (size_t i = 0; i < slots.size(); i++) {
+    kf_slot[slots[i].kf] = (int)i;
+    float T[16];
+    double p7[7];
+    mat_to_float16(slots[i].kf->GetPose(), T);
+    ppo::tcw_float_to_pose7(T, p7);  // Converter::toSE3Quat
+    F.kf_pose.insert(F.kf_pose.end(), p7, p7 + 7);
+    F.kf_fixed.push_back(slots[i].fixed);
+    const float in[5] = {slots[i].kf->fx, slots[i].kf->fy, slots[i].kf->cx, slots[i].kf->cy, slots[i].kf->mbf};
+    F.kf_intr.insert(F.kf_intr.end(), in, in + 5);
+  }
+  std::map<MapCuboid *, int> cu_index;
+  for (MapCuboid *pMC : w.lLocalMapCuboids) {  // :2158-2178: estimate = cuboid_global_data, roll/pitch and height locked
+    cu_index[pMC] = (int)cu_index.size();
+    double c[10];
+    cuboid_to10(pMC->cuboid_global_data, c);
+    F.cu_state.insert(F.cu_state.end(), c, c + 10);
+    F.cu_flags.push_back(PPO_CU_FIXROLLPITCH | PPO_CU_FIXHEIGHT);
+  }
+  std::map<MapPlane *, int> pl_index;
+  for (MapPlane *pMP : w.lLocalMapPlanes) {  // :2208-2219
+    pl_index[pMP] = (int)pl_index.size();
+    cv::Mat m = pMP->GetWorldPos();
+    const float c4[4] = {m.at<float>(0, 0), m.at<float>(1, 0), m.at<float>(2, 0), m.at<float>(3, 0)};
+    double c[4];
+    ppo::plane_float_to_coef(c4, c);  // Converter::toPlane3D
+    F.pl_coef.insert(F.pl_coef.end(), c, c + 4);
+  }
+  // ---- plane edges :2222-2309 ---------------------------------------------------------------------------
+  ppo_ba_params P;
+  ppo_ba_default_params(&P);
+  std::vector<std::pair<KeyFrame *, MapPlane *>> plane_edge_owner;  // for EdgePlane edges only (vpEdgeKFPlane / vpMapPlane)
+  std::vector<int> plane_edge_is_obs;
+  if (mixed) {
+    const double angleInfo = 3282.8 / (plane_angle_info * plane_angle_info), disInfo = plane_dist_info * plane_dist_info;
+    const double pvInfo = 3282.8 / (0.5 * 0.5);
+    P.huber_plane = ppo::huber_delta(plane_chi);
+    P.chi2_plane = plane_chi;
+    P.huber_vp_plane = ppo::huber_delta(200.0);
+    P.chi2_vp_plane = 200.0;
+    P.huber_bbox = ppo::huber_delta(thHuberBbox2d);
+    P.norm_bbox = thHuberBbox2d;
+    P.huber_corner = ppo::huber_delta(thHuberConer2d);
+    P.norm_corner = thHuberConer2d;
+    P.huber_cuboid_plane = ppo::huber_delta(cuboid_plane_chi);
+    if (optimize_with_plane_3d)
+      for (MapPlane *pMP : w.lLocalMapPlanes) {
+        auto add = [&](const std::map<KeyFrame *, int> &obs, int kind) {
+          for (auto &mit : obs) {
+            KeyFrame *pKFi = mit.first;
+            if (pKFi->isBad()) continue;
+            auto it = kf_slot.find(pKFi);
+            if (it == kf_slot.end()) continue;  // optimizer.vertex(pKFi->mnId) == NULL -> continue (:2235-2236, q8)
+            cv::Mat m = pKFi->mvPlaneCoefficients[mit.second];
+            const float c4[4] = {m.at<float>(0, 0), m.at<float>(1, 0), m.at<float>(2, 0), m.at<float>(3, 0)};
+            double c[4];
+            ppo::plane_float_to_coef(c4, c);
+            F.ple_plane.push_back(pl_index[pMP]);
+            F.ple_kf.push_back(it->second);
+            F.ple_kind.push_back((uint8_t)kind);
+            F.ple_meas.insert(F.ple_meas.end(), c, c + 4);
+            const double info[3] = {kind == PPO_PLANE_OBS ? angleInfo : pvInfo, kind == PPO_PLANE_OBS ? angleInfo : pvInfo, kind == PPO_PLANE_OBS ? disInfo : 0.0};
+            F.ple_info.insert(F.ple_info.end(), info, info + 3);
+            plane_edge_owner.push_back({pKFi, pMP});
+            plane_edge_is_obs.push_back(kind == PPO_PLANE_OBS);
+          }
+        };
+        add(pMP->GetObservations(), PPO_PLANE_OBS);
+        add(pMP->GetVerObservations(), PPO_PLANE_VER);
+        add(pMP->GetParObservations(), PPO_PLANE_PAR);
+      }
+  } else {
+    P.solver = PPO_SOLVER_6_3;
+  }
+  // ---- points and reprojection edges :2332-2424 (mixed) / :560-650 (points only) ----------------------------
+  std::vector<MapPoint *> graph_points;  // points that got a vertex (mixed: Observations() != 1, q1)
+  std::vector<std::pair<KeyFrame *, MapPoint *>> point_edge_owner;
+  F.pt_rowptr.push_back(0);
+  for (MapPoint *pMP : w.lLocalMapPoints) {
+    if (mixed && pMP->Observations() == 1) continue;  // :2336
+    graph_points.push_back(pMP);
+    cv::Mat X = pMP->GetWorldPos();
+    for (int i = 0; i < 3; i++) F.pt_xyz.push_back((double)X.at<float>(i, 0));  // Converter::toVector3d
+    F.pt_fixed.push_back(mixed && fixPoint);
+    const std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
+    std::vector<std::pair<int, std::pair<KeyFrame *, size_t>>> obs;
+    for (auto &mit : observations)
+      if (!mit.first->isBad()) {
+        auto it = kf_slot.find(mit.first);
+        if (it != kf_slot.end()) obs.push_back({it->second, {mit.first, mit.second}});
+      }
+    std::sort(obs.begin(), obs.end(), [](auto &a, auto &b) { return a.first < b.first; });
+    for (auto &o : obs) {
+      KeyFrame *pKFi = o.second.first;
+      const size_t idx = o.second.second;
+      const cv::KeyPoint &kpUn = pKFi->mvKeysUn[idx];
+      F.pe_kf.push_back(o.first);
+      F.pe_obs.push_back(kpUn.pt.x);
+      F.pe_obs.push_back(kpUn.pt.y);
+      F.pe_obs.push_back(pKFi->mvuRight[idx] < 0 ? -1.0f : pKFi->mvuRight[idx]);
+      F.pe_invsigma2.push_back(pKFi->mvInvLevelSigma2[kpUn.octave]);
+      point_edge_owner.push_back({pKFi, pMP});
+    }
+    F.pt_rowptr.push_back((int32_t)F.pe_kf.size());
+  }
+  if (mixed) {
+    // ---- camera-cuboid edges :2433-2551 ------------------------------------------------------------------
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 0 ? !optimize_with_cuboid_2d : !optimize_with_corners_2d) continue;
+      for (MapCuboid *pMCuboid : w.lLocalMapCuboids) {
+        const std::unordered_map<KeyFrame *, size_t> observations = pMCuboid->GetObservations();
+        for (auto &mit : observations) {
+          KeyFrame *pKFi = mit.first;
+          if (pKFi->isBad()) continue;
+          auto it = kf_slot.find(pKFi);
+          if (it == kf_slot.end()) continue;
+          const MapCuboid *local_object = pKFi->local_cuboids[mit.second];
+          const int object_boundary_margin = 5;
+          const cv::Rect bbox_2d = local_object->bbox_2d;
+          if (!((bbox_2d.x > object_boundary_margin) && (bbox_2d.y > object_boundary_margin) &&
+                (bbox_2d.x + bbox_2d.width < 640 - object_boundary_margin) && (bbox_2d.y + bbox_2d.height < 480 - object_boundary_margin)))
+            continue;
+          double m[16] = {0};
+          if (pass == 0)
+            for (int i = 0; i < 4; i++) m[i] = local_object->bbox_vec(i);
+          else
+            for (int i = 0; i < 8; i++) m[2 * i] = local_object->box_corners_2d(0, i), m[2 * i + 1] = local_object->box_corners_2d(1, i);
+          const double s = (pass == 0 ? ba_weight_bbox : ba_weight_corner) * local_object->meas_quality;
+          F.cbe_kf.push_back(it->second);
+          F.cbe_cuboid.push_back(cu_index[pMCuboid]);
+          F.cbe_kind.push_back(pass == 0 ? PPO_CUBOID_BBOX : PPO_CUBOID_CORNER);
+          F.cbe_meas.insert(F.cbe_meas.end(), m, m + 16);
+          F.cbe_info.push_back(s * s);
+        }
+      }
+    }
+    // ---- point-cuboid edges :2556-2655 ----------------------------------------------------------------------
+    F.pce_rowptr.push_back(0);
+    if (optimize_with_pt_obj_3d) {
+      const int point_object_threshold = 2;
+      const double coarse_threshold = 4, fine_threshold = 3;
+      for (MapCuboid *pMC : w.lLocalMapCuboids) {
+        std::vector<MapPoint *> pts;
+        std::vector<std::array<double, 3>> xyz;
+        const std::vector<MapPoint *> &UniquePoints = pMC->GetUniqueMapPoints();
+        for (MapPoint *up : UniquePoints)
+          if (up && !up->isBad() && up->MapObjObservations[pMC] > point_object_threshold) {
+            cv::Mat X = up->GetWorldPos();
+            pts.push_back(up);
+            xyz.push_back({(double)X.at<float>(0, 0), (double)X.at<float>(1, 0), (double)X.at<float>(2, 0)});
+          }
+        pMC->used_points_in_BA_filtered.clear();
+        double mean[3] = {0, 0, 0}, mean2[3] = {0, 0, 0};
+        for (auto &p : xyz) for (int i = 0; i < 3; i++) mean[i] += p[i];
+        for (int i = 0; i < 3; i++) mean[i] /= (double)xyz.size();
+        int valid = 0;
+        auto dist = [](const double a[3], const std::array<double, 3> &b) {
+          return std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+        };
+        for (auto &p : xyz)
+          if (dist(mean, p) < coarse_threshold) {
+            for (int i = 0; i < 3; i++) mean2[i] += p[i];
+            valid++;
+          }
+        for (int i = 0; i < 3; i++) mean2[i] /= (double)valid;
+        std::vector<std::array<double, 3>> good;
+        for (size_t j = 0; j < xyz.size(); j++)
+          if (dist(mean2, xyz[j]) < fine_threshold) {
+            good.push_back(xyz[j]);
+            pMC->used_points_in_BA_filtered.push_back(pts[j]);
+          }
+        if (good.size() > 10) {
+          for (auto &p : good) F.pce_pts.insert(F.pce_pts.end(), p.begin(), p.end());
+          F.pce_cuboid.push_back(cu_index[pMC]);
+          F.pce_rowptr.push_back((int32_t)(F.pce_pts.size() / 3));
+        }
+      }
+    }
+    // ---- cuboid-plane edges :2662-2714 -------------------------------------------------------------------------
+    if (optimize_with_cuboid_plane) {
+      const double a = 3282.8 / (cuboid_plane_angle_info * cuboid_plane_angle_info), d = cuboid_plane_dist_info * cuboid_plane_dist_info;
+      for (MapPlane *pMP : w.lLocalMapPlanes) {
+        if (pMP->asso_cuboid_id == 999) continue;
+        int cu = -1;
+        for (MapCuboid *pMC : w.lLocalMapCuboids)
+          if ((long unsigned int)pMC->mnId == pMP->asso_cuboid_id) cu = cu_index[pMC];
+        if (cu < 0) continue;  // cuboid not in the graph (:2688-2690)
+        F.cpe_cuboid.push_back(cu);
+        F.cpe_plane.push_back(pl_index[pMP]);
+        for (int i = 0; i < 3; i++) F.cpe_meas.push_back(pMP->asso_cuboid_meas(i));
+        F.cpe_info.push_back(a); F.cpe_info.push_back(a); F.cpe_info.push_back(d);
+      }
+    }
+  }
+  F.publish();
+
+  if (pbStopFlag && *pbStopFlag) return;  // :2723-2725 — no optimisation, no write-back
+
+  // ---- stages C-E on the GPU ----------------------------------------------------------------------------------
+  ppo_ba_handle *h = engine(P);
+  g_last_rc = PPO_E_NOGPU;
+  if (!h) {
+    std::fprintf(stderr, "ppo shim: no CUDA engine available; map left untouched\n");
+    return;
+  }
+  std::memset(&g_last_result, 0, sizeof g_last_result);
+  if ((g_last_rc = ppo_ba_set_graph(h, &F.g)) != PPO_OK ||
+      (g_last_rc = ppo_ba_local_ba(h, reinterpret_cast<const volatile unsigned char *>(pbStopFlag), &g_last_result)) != PPO_OK) {
+    std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", g_last_rc, ppo_ba_last_error(h));
+    return;
+  }
+  // ---- stage F: erase lists :2840-2887 ---------------------------------------------------------------------------
+  std::vector<std::pair<KeyFrame *, MapPoint *>> vToErase;
+  std::vector<std::pair<KeyFrame *, MapPlane *>> vToErasePlane;
+  {
+    std::vector<double> chi2(F.g.n_pe);
+    std::vector<unsigned char> dpos(F.g.n_pe);
+    if (F.g.n_pe) ppo_ba_edge_chi2(h, PPO_EDGE_POINT, chi2.data(), dpos.data(), nullptr);
+    for (int e = 0; e < F.g.n_pe; e++) {
+      MapPoint *pMP = point_edge_owner[e].second;
+      if (pMP->isBad()) continue;
+      const bool mono = F.pe_obs[3 * (size_t)e + 2] < 0;
+      if (chi2[e] > (mono ? 5.991 : 7.815) || !dpos[e]) vToErase.push_back(point_edge_owner[e]);
+    }
+    if (F.g.n_ple) {
+      std::vector<double> pchi(F.g.n_ple);
+      ppo_ba_edge_chi2(h, PPO_EDGE_PLANE, pchi.data(), nullptr, nullptr);
+      for (int e = 0; e < F.g.n_ple; e++)
+        if (plane_edge_is_obs[e] && pchi[e] > P.chi2_plane) vToErasePlane.push_back(plane_edge_owner[e]);
+    }
+  }
+  ppo_ba_state st;
+  std::vector<double> o_kf(F.kf_pose.size()), o_pt(F.pt_xyz.size()), o_pl(F.pl_coef.size()), o_cu(F.cu_state.size());
+  st.kf_pose = o_kf.data(); st.pt_xyz = o_pt.data(); st.pl_coef = o_pl.data(); st.cu_state = o_cu.data();
+  if ((g_last_rc = ppo_ba_get_state(h, &st)) != PPO_OK) return;
+
+  // ---- stage G: write back under the map mutex :2892-2966 --------------------------------------------------------------
+  std::unique_lock<std::mutex> lock(pMap->mMutexMapUpdate);
+  for (auto &pr : vToErase) {
+    pr.first->EraseMapPointMatch(pr.second);
+    pr.second->EraseObservation(pr.first);
+  }
+  for (auto &pr : vToErasePlane) {
+    pr.first->EraseMapPlaneMatch(pr.second);
+    pr.second->EraseObservation(pr.first);
+  }
+  for (KeyFrame *kf : w.lLocalKeyFrames) {
+    if (mixed) kf->mnBALocalForKF = 0;
+    float T[16];
+    ppo::pose7_to_tcw_float(&o_kf[7 * (size_t)kf_slot[kf]], T);  // Converter::toCvMat(SE3Quat)
+    kf->SetPose(float16_to_mat(T));
+  }
+  for (size_t i = 0; i < graph_points.size(); i++) {  // points without a vertex are skipped (the reference dereferences NULL there, q1)
+    MapPoint *pMP = graph_points[i];
+    if (mixed) pMP->mnBALocalForKF = 0;
+    cv::Mat X(3, 1, CV_32F);
+    for (int k = 0; k < 3; k++) X.at<float>(k, 0) = (float)o_pt[3 * i + k];
+    pMP->SetWorldPos(X);
+    pMP->UpdateNormalAndDepth();
+  }
+  if (mixed) {
+    for (KeyFrame *kf : w.lFixedCameras) {
+      kf->mnBAFixedForKF = 0;
+      kf->mnBALocalForKF = 0;
+    }
+    for (MapCuboid *pMC : w.lLocalMapCuboids) {
+      pMC->mnBALocalForKF = 0;
+      pMC->obj_been_optimized = true;
+      const double *c = &o_cu[10 * (size_t)cu_index[pMC]];
+      const double p7[7] = {c[3], c[4], c[5], c[6], c[0], c[1], c[2]};
+      float T[16];
+      ppo::pose7_to_tcw_float(p7, T);
+      pMC->SetWorldPos(float16_to_mat(T));
+      cuboid_from10(c, pMC->cuboid_global_opti);
+    }
+    for (MapPlane *pMP : w.lLocalMapPlanes) {
+      cv::Mat m(4, 1, CV_32F);
+      for (int k = 0; k < 4; k++) m.at<float>(k, 0) = (float)o_pl[4 * (size_t)pl_index[pMP] + k];  // Converter::toCvMat(Plane3D)
+      pMP->SetWorldPos(m);
+    }
+  }
+}
+
+}  // namespace ppo_shim
+
+namespace ORB_SLAM2 {
+void Optimizer::LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap) { ppo_shim::run(pKF, pbStopFlag, pMap, false, false, false); }
+void Optimizer::LocalBACameraPlaneCuboids(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool fixCamera, bool fixPoint) {
+  ppo_shim::run(pKF, pbStopFlag, pMap, true, fixCamera, fixPoint);
+}
+}  // namespace ORB_SLAM2
+
+// introspection for tests and logging
+extern "C" {
+const ppo_ba_graph *ppo_shim_last_graph() { return &ppo_shim::g_last.g; }
+const ppo_ba_result *ppo_shim_last_result() { return &ppo_shim::g_last_result; }
+int ppo_shim_last_rc() { return ppo_shim::g_last_rc; }
+void ppo_shim_set_device(int device) { ppo_shim::g_device = device; }
+void ppo_shim_shutdown() {
+  if (ppo_shim::g_handle) ppo_ba_destroy(ppo_shim::g_handle), ppo_shim::g_handle = nullptr;
+}
+}

@@ -403,6 +403,8 @@ ppo_synth *ppo_synth_create(const ppo_synth_cfg *cfgp) {
   };
   std::vector<CamObs> cobs;
   S->pce_rowptr.push_back(0);
+  // MapPlane holds ONE asso_cuboid_id (MapPlane.h:67): distinct planes for distinct cuboids while planes last
+  const int cpe_plane0 = c.n_pl > 0 ? rng.below(c.n_pl) : 0;
   for (int i = 0; i < c.n_cu; i++) {
     double yaw = rng.uni(-M_PI, M_PI);
     double ctr[3] = {rng.uni(-1, 1), rng.uni(-0.5, 0.5), rng.uni(-1, 1)};
@@ -470,9 +472,9 @@ ppo_synth *ppo_synth_create(const ppo_synth_cfg *cfgp) {
       S->pce_cuboid.push_back(i);
       S->pce_rowptr.push_back((int32_t)(S->pce_pts.size() / 3));
     }
-    if (c.cuboid_plane && c.n_pl > 0) {
+    if (c.cuboid_plane && c.n_pl > 0 && i < c.n_pl) {
       S->cpe_cuboid.push_back(i);
-      S->cpe_plane.push_back(rng.below(c.n_pl));
+      S->cpe_plane.push_back((cpe_plane0 + i) % c.n_pl);
       S->cpe_meas.push_back(0.01 * rng.normal());
       S->cpe_meas.push_back(0.01 * rng.normal());
       S->cpe_meas.push_back(0.02 * rng.normal());

@@ -1,0 +1,89 @@
+"""The host shim that replaces Optimizer::LocalBACameraPlaneCuboids / LocalBundleAdjustment,
+exercised on a mock map with the reference's member names (csrc/host/ppo_mock_slam.h)."""
+import numpy as np
+import pytest
+
+
+def _graph(ppo, **kw):
+    return ppo.synth.make_graph(ppo.synth.config(1, n_kf=14, n_fixed=3, n_pt=900, n_pl=6, n_cu=3, **kw))
+
+
+def test_flattening_reproduces_the_flat_graph_cpu(ppo):
+    """With the stop flag set on entry the shim collects + flattens the window and returns before touching the GPU
+    (Optimizer.cc:2723-2725): the flattened graph must equal the flat graph the mock map was built from."""
+    import shim_lib
+    g = _graph(ppo, corners_2d=1)
+    st, counts, flat = shim_lib.run(g, stop=True)
+    assert counts == [0, 0, 0, 0]  # nothing written back, nothing erased
+    assert np.allclose(st.kf_pose, g["kf_pose"], atol=2e-7)  # untouched (float32 round trip of the pose)
+    # points seen by no local key-frame are not part of the reference's local window: compare the others
+    rp = g["pt_rowptr"]
+    n_loc = int((g["kf_fixed"] == 0).sum()) + 1
+    local_pts = [p for p in range(g.c.n_pt) if (g["pe_kf"][rp[p]:rp[p + 1]] < n_loc).any()]
+    assert flat.c.n_pt == len(local_pts) and flat.c.n_kf == g.c.n_kf
+    assert np.array_equal(flat["kf_fixed"], g["kf_fixed"]) and np.array_equal(flat["kf_intr"], g["kf_intr"])
+    assert np.allclose(flat["kf_pose"], g["kf_pose"], atol=2e-7)
+    # the shim orders points by discovery (key-frame by key-frame) — match them through their coordinates
+    key = lambda a: [tuple(np.round(r, 6)) for r in a]
+    order = {k: i for i, k in enumerate(key(flat["pt_xyz"]))}
+    frp = flat["pt_rowptr"]
+    for p in local_pts[::37]:
+        q = order[tuple(np.round(g["pt_xyz"][p], 6))]
+        assert np.array_equal(flat["pe_kf"][frp[q]:frp[q + 1]], g["pe_kf"][rp[p]:rp[p + 1]])
+        assert np.array_equal(flat["pe_obs"][frp[q]:frp[q + 1]], g["pe_obs"][rp[p]:rp[p + 1]])
+        assert np.allclose(flat["pe_invsigma2"][frp[q]:frp[q + 1]], g["pe_invsigma2"][rp[p]:rp[p + 1]], rtol=1e-6)
+    # planes / cuboids and their edges (order of edges may differ: compare as multisets)
+    assert flat.c.n_pl == g.c.n_pl and flat.c.n_cu == g.c.n_cu
+    assert np.allclose(np.sort(flat["pl_coef"], axis=0), np.sort(g["pl_coef"], axis=0), atol=1e-6)
+    assert np.allclose(np.sort(flat["cu_state"], axis=0), np.sort(g["cu_state"], axis=0), atol=1e-12)
+    assert (flat.c.n_ple, flat.c.n_cbe, flat.c.n_pce, flat.c.n_cpe) == (g.c.n_ple, g.c.n_cbe, g.c.n_pce, g.c.n_cpe)
+    assert sorted(flat["ple_kind"].tolist()) == sorted(g["ple_kind"].tolist())
+    assert np.allclose(np.sort(flat["ple_info"], axis=0), np.sort(g["ple_info"], axis=0))
+    assert np.allclose(np.sort(flat["cbe_meas"].ravel()), np.sort(g["cbe_meas"].ravel()))
+    assert np.allclose(np.sort(flat["cbe_info"]), np.sort(g["cbe_info"]))
+    assert np.allclose(np.sort(flat["cpe_info"].ravel()), np.sort(g["cpe_info"].ravel()))
+
+
+def test_points_only_entry_point_flattening_cpu(ppo):
+    import shim_lib
+    g = ppo.synth.make_graph(ppo.synth.config(0))
+    st, counts, flat = shim_lib.run(g, mixed=False, stop=True)
+    assert flat.c.n_pl == 0 and flat.c.n_cu == 0 and flat.c.n_ple == 0 and flat.c.n_kf == g.c.n_kf
+    assert abs(flat.c.n_pe - g.c.n_pe) < 0.02 * g.c.n_pe
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mixed", [True, False])
+def test_shim_end_to_end_matches_oracle_on_its_own_flat_graph(ppo, oracle_mod, mixed):
+    """LocalMapping-style call -> GPU engine -> write-back; compared with the oracle run on the graph the shim built."""
+    import shim_lib
+    g = _graph(ppo) if mixed else ppo.synth.make_graph(ppo.synth.config(0))
+    st, counts, flat = shim_lib.run(g, mixed=mixed)
+    assert shim_lib.lib().ppo_shim_last_rc() == 0
+    o = oracle_mod.Oracle()
+    if not mixed:
+        o.params.solver = ppo.abi.SOLVER_6_3
+    o.set_graph(flat)
+    ro = o.local_ba()
+    so = o.get_state()
+    res = shim_lib.lib().ppo_shim_last_result().contents
+    assert (res.round1.iterations, res.round2.iterations) == (ro.round1.iterations, ro.round2.iterations)
+    assert np.isclose(res.round2.chi2_final, ro.round2.chi2_final, rtol=1e-6)
+    # the map holds float32: compare at float32 resolution; key-frame slots are identical (sorted by mnId)
+    assert np.abs(st.kf_pose - so.kf_pose).max() < 5e-6
+    # every local key-frame got SetPose, every graph point UpdateNormalAndDepth
+    n_local = int((flat["kf_fixed"] == 0).sum()) + 1
+    assert counts[2] == n_local and counts[3] == flat.c.n_pt
+    # erase decisions = oracle's final chi2 / depth tests (Optimizer.cc:2840-2887)
+    chi2, dpos, _ = o.edge_chi2(ppo.abi.EDGE_POINT)
+    mono = flat["pe_obs"][:, 2] < 0
+    assert counts[0] == int(((chi2 > np.where(mono, 5.991, 7.815)) | (dpos == 0)).sum())
+    if mixed:
+        pchi, _, _ = o.edge_chi2(ppo.abi.EDGE_PLANE)
+        assert counts[1] == int(((flat["ple_kind"] == 0) & (pchi > 500.0)).sum())
+        # planes and cuboids keep their map index
+        assert np.abs(st.pl_coef - so.pl_coef).max() < 5e-6
+        assert np.abs(st.cu_state - so.cu_state).max() < 1e-5
+    # points: matched through the shim's ordering
+    moved = np.abs(st.pt_xyz - g["pt_xyz"]).max(axis=1) > 0
+    assert moved.sum() >= 0.95 * flat.c.n_pt
