@@ -81,9 +81,13 @@ def test_shim_end_to_end_matches_oracle_on_its_own_flat_graph(ppo, oracle_mod, m
     if mixed:
         pchi, _, _ = o.edge_chi2(ppo.abi.EDGE_PLANE)
         assert counts[1] == int(((flat["ple_kind"] == 0) & (pchi > 500.0)).sum())
-        # planes and cuboids keep their map index
-        assert np.abs(st.pl_coef - so.pl_coef).max() < 5e-6
-        assert np.abs(st.cu_state - so.cu_state).max() < 1e-5
+        # the shim numbers planes / cuboids in discovery order: match them to the map through their initial values
+        def perm(flat_init, map_init):
+            return [int(np.abs(map_init - r).sum(axis=1).argmin()) for r in flat_init]
+        pp, pc = perm(flat["pl_coef"], g["pl_coef"]), perm(flat["cu_state"], g["cu_state"])
+        assert sorted(pp) == list(range(g.c.n_pl)) and sorted(pc) == list(range(g.c.n_cu))
+        assert np.abs(st.pl_coef[pp] - so.pl_coef).max() < 5e-6
+        assert np.abs(st.cu_state[pc] - so.cu_state).max() < 1e-5
     # points: matched through the shim's ordering
     moved = np.abs(st.pt_xyz - g["pt_xyz"]).max(axis=1) > 0
     assert moved.sum() >= 0.95 * flat.c.n_pt
