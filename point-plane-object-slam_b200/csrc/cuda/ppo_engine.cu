@@ -17,6 +17,8 @@
 #include "ppo_dense.h"
 #include "ppo_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 using namespace ppo;
 
 #define CK(call)                                                                                   \
@@ -61,6 +63,8 @@ struct ppo_ba_handle {
   ppo_ba_params P;
   int device = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;  // non-point edges are linearised concurrently with the point edges
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t evm[2] = {nullptr, nullptr};
   void *d_flush = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -78,6 +82,9 @@ struct ppo_ba_handle {
   int *d_kf_chunk_ptr = nullptr;
   double *d_chunk_part = nullptr;
   int *d_lm_small = nullptr, *d_lm_big = nullptr;
+  unsigned *d_pair_keys = nullptr;            // sorted key-frame-pair keys of the Schur contributions
+  unsigned long long *d_pair_vals = nullptr;  // (entry A << 32 | entry B)
+  int n_pairs = 0;
   int n_lm_small = 0, n_lm_big = 0;
   // cuboid-plane edges (constant residual): host side
   std::vector<int> cpe_cuboid, cpe_plane;
@@ -196,6 +203,9 @@ int ppo_ba_create(const ppo_ba_params *params, int device, ppo_ba_handle **out) 
     delete h;
     return PPO_E_CUDA;
   }
+  cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   for (auto &e : h->evp) cudaEventCreate(&e);
@@ -222,6 +232,10 @@ void ppo_ba_destroy(ppo_ba_handle *h) {
   if (h->hstage) cudaFreeHost(h->hstage);
   cudaFreeHost(h->h_scal);
   cudaFreeHost(h->h_dims);
+  cudaStreamSynchronize(h->st2);
+  cudaStreamDestroy(h->st2);
+  cudaEventDestroy(h->ev_fork);
+  cudaEventDestroy(h->ev_join);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   for (auto &e : h->evp) cudaEventDestroy(e);
@@ -470,6 +484,51 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
     UP(d, meas); g.ple_meas = d;
     std::vector<double> info(gi->ple_info, gi->ple_info + 3 * (size_t)g.n_ple); UP(d, info); g.ple_info = d;
   }
+  // ---- Schur contribution list: one record per pair of free-key-frame blocks of a landmark, sorted by key-frame pair ----
+  {
+    if ((unsigned long long)g.n_kf * (unsigned long long)g.n_kf >= 0xffffffffull) { h->err = "too many key-frames for 32-bit pair keys"; return PPO_E_INVALID; }
+    std::vector<int> pair_off(g.n_lm + 1, 0);
+    long long total = 0;
+    std::vector<int> seen;
+    for (int L = 0; L < g.n_lm; L++) {
+      long long kfree = 0;
+      seen.clear();
+      for (int en = lm_rowptr[L]; en < lm_rowptr[L + 1]; en++) {
+        const int sl = en < g.n_slots ? slot_kf[en] : rec[en - g.n_slots].kf;
+        seen.push_back(sl);
+        kfree += !kf_fixed[sl];
+      }
+      std::sort(seen.begin(), seen.end());
+      if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) {  // MapPoint::mObservations is a map keyed by KeyFrame*
+        h->err = "a landmark is observed twice by the same key-frame";
+        return PPO_E_INVALID;
+      }
+      pair_off[L] = (int)total;
+      total += kfree * (kfree + 1) / 2;
+      if (total > 0x7fffffffll) { h->err = "Schur contribution list exceeds 2^31 entries"; return PPO_E_INVALID; }
+    }
+    pair_off[g.n_lm] = (int)total;
+    h->n_pairs = (int)total;
+    int *d_off = nullptr;
+    UP(d_off, pair_off);
+    unsigned *k_in = nullptr;
+    unsigned long long *v_in = nullptr;
+    if ((rc = h->dalloc(&k_in, (size_t)total)) || (rc = h->dalloc(&v_in, (size_t)total)) || (rc = h->dalloc(&h->d_pair_keys, (size_t)total)) ||
+        (rc = h->dalloc(&h->d_pair_vals, (size_t)total)))
+      return rc;
+    if (total > 0) {
+      k_gen_pairs<<<cdiv(g.n_lm, 4), 128, 0, h->st>>>(g, d_off, k_in, v_in);
+      h->launches++;
+      int bits = 1;
+      while (bits < 32 && (1ull << bits) < (unsigned long long)g.n_kf * (unsigned long long)g.n_kf) bits++;
+      size_t tmp_bytes = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, h->d_pair_keys, v_in, h->d_pair_vals, (int)total, 0, bits, h->st));
+      char *tmp = nullptr;
+      if ((rc = h->dalloc(&tmp, tmp_bytes))) return rc;
+      CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, h->d_pair_keys, v_in, h->d_pair_vals, (int)total, 0, bits, h->st));
+      h->launches += 4;
+    }
+  }
   // ---- camera-cuboid / point-cuboid / cuboid-plane edges ---------------------------------------------
   {
     int *p; uint8_t *q; double *d;
@@ -507,7 +566,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   h->max_np = 6 * n_free + 9 * g.n_cu;
   h->ld = h->max_np + 1;
   DA(g.Hpp_kf, 36 * (size_t)g.n_kf); DA(g.Hpp_cu, 81 * (size_t)g.n_cu); DA(g.Hpc, 54 * (size_t)g.n_cbe); DA(g.bp, (size_t)h->max_np);
-  DA(g.Hll, 6 * (size_t)g.n_lm); DA(g.bl, 3 * (size_t)g.n_lm); DA(g.Hpl, 18 * (size_t)g.n_ent); DA(g.Dinv, 6 * (size_t)g.n_lm);
+  DA(g.Hll, 6 * (size_t)g.n_lm); DA(g.bl, 3 * (size_t)g.n_lm); DA(g.Hpl, 18 * (size_t)g.n_ent); DA(g.BD, 18 * (size_t)g.n_ent); DA(g.Dinv, 6 * (size_t)g.n_lm);
   DA(g.xl, 3 * (size_t)g.n_lm); DA(g.S, (size_t)(h->max_np + 1) * h->ld); DA(g.xp, (size_t)h->max_np);
   h->nb_lin = cdiv(g.n_units, LIN_WARPS); h->nb_res = cdiv(g.n_pe, RES_THREADS);
   h->nb_pl = cdiv(g.n_ple, SMALL_THREADS); h->nb_cb = cdiv(g.n_cbe, SMALL_THREADS); h->nb_pc = cdiv(g.n_pce, SMALL_THREADS);
@@ -522,6 +581,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   CK(cudaMemsetAsync(g.cbe_norm, 0, 8 * (size_t)g.n_cbe, h->st));
   CK(cudaMemsetAsync(g.pce_chi2, 0, 8 * (size_t)g.n_pce, h->st));
   CK(cudaMemsetAsync(g.Hpl, 0, 8 * 18 * (size_t)g.n_ent, h->st));
+  CK(cudaMemsetAsync(g.BD, 0, 8 * 18 * (size_t)g.n_ent, h->st));
   CK(cudaMemsetAsync(g.xl, 0, 8 * 3 * (size_t)g.n_lm, h->st));
   CK(cudaMemsetAsync(g.pe_flags, PPO_EF_ROBUST, (size_t)g.n_pe, h->st));
   CK(cudaMemsetAsync(g.ple_flags, PPO_EF_ROBUST, (size_t)g.n_ple, h->st));
@@ -623,6 +683,14 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
     CK(cudaMemsetAsync(g.Hpl, 0, 8 * 18 * (size_t)g.n_slots, st));
   }
   if (h->profiling) cudaEventRecord(h->evp[0], st);
+  // single GPU: the plane / cuboid / point-cuboid edges (numeric Jacobians, few 10^4 threads, latency-bound) run on a
+  // second stream next to the point kernels; both sides only meet in atomically-updated accumulators.
+  const bool fork = h->world == 1 && !only_points_kernel && (g.n_ple || g.n_cbe || g.n_pce);
+  cudaStream_t so = fork ? h->st2 : st;
+  if (fork) {
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
+  }
   if (g.n_units) {
     k_point_linearize<<<h->nb_lin, LIN_WARPS * 32, 0, st>>>(g, s, h->d_chi_pt);
     h->launches++;
@@ -638,20 +706,24 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
     if ((rc = allreduce(h, g.Hpp_kf, 36 * (size_t)g.n_kf, ncclFloat64_, ncclSum_)) || (rc = allreduce(h, g.bp, h->max_np, ncclFloat64_, ncclSum_))) return rc;
   }
   if (g.n_ple) {
-    k_plane_jac<<<cdiv(g.n_ple * 9, 128), 128, 0, st>>>(g, s);
-    k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pl);
+    k_plane_jac<<<cdiv(g.n_ple * 9, 128), 128, 0, so>>>(g, s);
+    k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, so>>>(g, s, h->d_chi_pl);
     h->launches += 2;
   }
   if (g.n_cbe) {
-    k_cuboid_jac<<<cdiv(g.n_cbe * 15, 128), 128, 0, st>>>(g, s);
-    k_cuboid_edges<true><<<h->nb_cb, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_cb);
-    k_cuboid_assemble<<<cdiv(g.n_cbe * 15, 128), 128, 0, st>>>(g);
+    k_cuboid_jac<<<cdiv(g.n_cbe * 15, 128), 128, 0, so>>>(g, s);
+    k_cuboid_edges<true><<<h->nb_cb, SMALL_THREADS, 0, so>>>(g, s, h->d_chi_cb);
+    k_cuboid_assemble<<<cdiv(g.n_cbe * 15, 128), 128, 0, so>>>(g);
     h->launches += 3;
   }
   if (g.n_pce) {
-    k_ptcu_jac<<<cdiv(g.n_pce * 9, 128), 128, 0, st>>>(g, s);
-    k_ptcu_edges<true><<<h->nb_pc, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pc);
+    k_ptcu_jac<<<cdiv(g.n_pce * 9, 128), 128, 0, so>>>(g, s);
+    k_ptcu_edges<true><<<h->nb_pc, SMALL_THREADS, 0, so>>>(g, s, h->d_chi_pc);
     h->launches += 2;
+  }
+  if (fork) {
+    CK(cudaEventRecord(h->ev_join, h->st2));
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
   if (h->profiling) cudaEventRecord(h->evp[1], st);
   const bool own = h->owner();  // replicated (non-point) edges count once: on rank 0
@@ -697,8 +769,12 @@ static int schur_system(ppo_ba_handle *h, double lambda) {
   CK(cudaMemsetAsync(g.S, 0, 8 * (size_t)(n_p + 1) * ld, st));
   CK(cudaMemsetAsync(h->d_not_spd, 0, sizeof(int), st));
   const int own = h->owner() ? 1 : 0;
-  if (h->n_lm_small) { k_schur<false><<<cdiv(h->n_lm_small, SCHUR_WARPS), SCHUR_WARPS * 32, 0, st>>>(g, h->d_lm_small, h->n_lm_small, lambda, n_p, ld, own); h->launches++; }
-  if (h->n_lm_big) { k_schur<true><<<h->n_lm_big, SCHUR_WARPS * 32, 0, st>>>(g, h->d_lm_big, h->n_lm_big, lambda, n_p, ld, own); h->launches++; }
+  if (g.n_lm) { k_schur_bd<<<cdiv(g.n_lm, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, lambda, n_p, ld, own); h->launches++; }
+  if (h->n_pairs) {
+    const int n_warps = cdiv(h->n_pairs, PAIR_CHUNK);
+    k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld);
+    h->launches++;
+  }
   const int n_comp = g.n_kf * 36 + g.n_cu * 81 + g.n_cbe * 54 + n_p;
   if (n_comp && own) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, lambda, n_p, ld); h->launches++; }
   // single large window sharded over ranks: sum the partial reduced systems (Hschur | bschur) over NVLink

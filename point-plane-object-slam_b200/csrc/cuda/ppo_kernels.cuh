@@ -114,34 +114,37 @@ PPO_D void point_edge_linearize(const double Rt[12], const double X[3], const fl
   cam_point(Rt, X, p);
   L.D = point_edge_error(p, intr, rec.u, rec.v, rec.ur, L.err);
   const double fx = intr[0], fy = intr[1], bf = intr[4];
-  const double x = p[0], y = p[1], z = p[2], z_2 = z * z;
+  const double x = p[0], y = p[1];
+  // one reciprocal instead of the reference's ~15 divisions by z / z^2 (same values to 1 ulp)
+  const double iz = 1.0 / p[2], iz2 = iz * iz;
+  const double fxz = fx * iz, fyz = fy * iz, xz2 = x * iz2, yz2 = y * iz2;
   // d(residual)/d(camera-frame point), rows 0..2
-  const double a0[3] = {-fx / z, 0.0, fx * x / z_2};
-  const double a1[3] = {0.0, -fy / z, fy * y / z_2};
+  const double a0[3] = {-fxz, 0.0, fx * xz2};
+  const double a1[3] = {0.0, -fyz, fy * yz2};
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     L.Jpt[j] = a0[0] * Rt[j] + a0[2] * Rt[6 + j];
     L.Jpt[3 + j] = a1[1] * Rt[3 + j] + a1[2] * Rt[6 + j];
-    L.Jpt[6 + j] = L.Jpt[j] - bf * Rt[6 + j] / z_2;
+    L.Jpt[6 + j] = L.Jpt[j] - bf * iz2 * Rt[6 + j];
   }
-  L.Jkf[0] = x * y / z_2 * fx;
-  L.Jkf[1] = -(1 + (x * x / z_2)) * fx;
-  L.Jkf[2] = y / z * fx;
-  L.Jkf[3] = -1. / z * fx;
+  L.Jkf[0] = x * yz2 * fx;
+  L.Jkf[1] = -(1 + x * xz2) * fx;
+  L.Jkf[2] = y * fxz;
+  L.Jkf[3] = -fxz;
   L.Jkf[4] = 0;
-  L.Jkf[5] = x / z_2 * fx;
-  L.Jkf[6] = (1 + y * y / z_2) * fy;
-  L.Jkf[7] = -x * y / z_2 * fy;
-  L.Jkf[8] = -x / z * fy;
+  L.Jkf[5] = xz2 * fx;
+  L.Jkf[6] = (1 + y * yz2) * fy;
+  L.Jkf[7] = -x * yz2 * fy;
+  L.Jkf[8] = -x * fyz;
   L.Jkf[9] = 0;
-  L.Jkf[10] = -1. / z * fy;
-  L.Jkf[11] = y / z_2 * fy;
-  L.Jkf[12] = L.Jkf[0] - bf * y / z_2;
-  L.Jkf[13] = L.Jkf[1] + bf * x / z_2;
+  L.Jkf[10] = -fyz;
+  L.Jkf[11] = yz2 * fy;
+  L.Jkf[12] = L.Jkf[0] - bf * yz2;
+  L.Jkf[13] = L.Jkf[1] + bf * xz2;
   L.Jkf[14] = L.Jkf[2];
   L.Jkf[15] = L.Jkf[3];
   L.Jkf[16] = 0;
-  L.Jkf[17] = L.Jkf[5] - bf / z_2;
+  L.Jkf[17] = L.Jkf[5] - bf * iz2;
   if (L.D == 2) {
 #pragma unroll
     for (int j = 0; j < 3; j++) L.Jpt[6 + j] = 0;
@@ -206,16 +209,19 @@ __global__ void __launch_bounds__(LIN_WARPS * 32, 4) k_point_linearize(DevGraph 
           const double ws = w * is2;
           if (!ptfix) {
             const double fx = intr[0], fy = intr[1], bf = D == 3 ? (double)intr[4] : 0.0;
-            const double x = p[0], y = p[1], z = p[2], z_2 = z * z;
+            const double x = p[0], y = p[1];
+            // one reciprocal instead of the reference's ~15 divisions by z / z^2 (same values to 1 ulp)
+            const double iz = 1.0 / p[2], iz2 = iz * iz;
+            const double fxz = fx * iz, fyz = fy * iz, xz2 = x * iz2, yz2 = y * iz2;
             // weighted point Jacobian wj = (w Omega) * Jpt, Jpt = d(residual)/d(point) (types_six_dof_expmap.cpp:147-156,234-244)
             double wj[9], Jpt[9];
             {
-              const double a00 = -fx / z, a02 = fx * x / z_2, a11 = -fy / z, a12 = fy * y / z_2;
+              const double a02 = fx * xz2, a12 = fy * yz2, bz = bf * iz2;
 #pragma unroll
               for (int j = 0; j < 3; j++) {
-                Jpt[j] = a00 * Rt[j] + a02 * Rt[6 + j];
-                Jpt[3 + j] = a11 * Rt[3 + j] + a12 * Rt[6 + j];
-                Jpt[6 + j] = D == 3 ? Jpt[j] - bf * Rt[6 + j] / z_2 : 0.0;
+                Jpt[j] = a02 * Rt[6 + j] - fxz * Rt[j];
+                Jpt[3 + j] = a12 * Rt[6 + j] - fyz * Rt[3 + j];
+                Jpt[6 + j] = D == 3 ? Jpt[j] - bz * Rt[6 + j] : 0.0;
               }
             }
 #pragma unroll
@@ -239,13 +245,13 @@ __global__ void __launch_bounds__(LIN_WARPS * 32, 4) k_point_linearize(DevGraph 
     st[3 * (a) + 1] = q0 * wj[1] + q1 * wj[4] + q2 * wj[7];          \
     st[3 * (a) + 2] = q0 * wj[2] + q1 * wj[5] + q2 * wj[8];          \
   }
-              const double k00 = x * y / z_2 * fx, k01 = -(1 + (x * x / z_2)) * fx, k02 = y / z * fx, k03 = -1. / z * fx, k05 = x / z_2 * fx;
-              PPO_HPL_ROW(0, k00, (1 + y * y / z_2) * fy, k00 - bf * y / z_2)
-              PPO_HPL_ROW(1, k01, -x * y / z_2 * fy, k01 + bf * x / z_2)
-              PPO_HPL_ROW(2, k02, -x / z * fy, k02)
+              const double k00 = x * yz2 * fx, k01 = -(1 + x * xz2) * fx, k02 = y * fxz, k03 = -fxz, k05 = xz2 * fx;
+              PPO_HPL_ROW(0, k00, (1 + y * yz2) * fy, k00 - bf * yz2)
+              PPO_HPL_ROW(1, k01, -x * yz2 * fy, k01 + bf * xz2)
+              PPO_HPL_ROW(2, k02, -x * fyz, k02)
               PPO_HPL_ROW(3, k03, 0.0, k03)
-              PPO_HPL_ROW(4, 0.0, -1. / z * fy, 0.0)
-              PPO_HPL_ROW(5, k05, y / z_2 * fy, k05 - bf / z_2)
+              PPO_HPL_ROW(4, 0.0, -fyz, 0.0)
+              PPO_HPL_ROW(5, k05, yz2 * fy, k05 - bf * iz2)
 #undef PPO_HPL_ROW
             }
           }
@@ -790,6 +796,119 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const in
     }
   }
 }
+// ---------------------------------------------------------------------------------------------
+// Pair-major Schur complement (no per-scalar atomics).  At set_graph every landmark emits one contribution per
+// pair of its (free key-frame) blocks, keyed by the key-frame pair; the list is radix-sorted by key once.  Per
+// damped trial  k_schur_bd  forms Dinv and the 6x3 products W Dinv of every block, and  k_schur_pairs  streams the
+// sorted list: a warp owns 64 consecutive contributions, lane (r,c) accumulates entry (r,c) of the current
+// key-frame pair in a register and flushes 36 REDs only when the key changes.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gen_pairs(DevGraph g, const int *lm_pair_off, unsigned *keys, unsigned long long *vals) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= g.n_lm) return;
+  const int b0 = g.lm_rowptr[warp], b1 = g.lm_rowptr[warp + 1];
+  int out = lm_pair_off[warp];
+  // free-key-frame entries of this landmark, in entry order; pairs (i1 <= i2) are numbered row by row
+  for (int i1 = b0; i1 < b1; i1++) {
+    const int s1 = i1 < g.n_slots ? g.slot_kf[i1] : g.pe_rec[i1 - g.n_slots].kf;
+    if (g.kf_fixed[s1]) continue;  // warp-uniform
+    int cnt = 0;
+    for (int base = i1; base < b1; base += 32) {
+      const int i2 = base + lane;
+      int s2 = -1;
+      bool ok = false;
+      if (i2 < b1) {
+        s2 = i2 < g.n_slots ? g.slot_kf[i2] : g.pe_rec[i2 - g.n_slots].kf;
+        ok = !g.kf_fixed[s2];
+      }
+      const unsigned m = __ballot_sync(FULL, ok);
+      if (ok) {
+        const int pos = out + cnt + __popc(m & ((1u << lane) - 1));
+        const bool sw = s1 > s2;
+        const unsigned a = sw ? s2 : s1, b = sw ? s1 : s2;
+        keys[pos] = a * (unsigned)g.n_kf + b;
+        vals[pos] = ((unsigned long long)(unsigned)(sw ? i2 : i1) << 32) | (unsigned)(sw ? i1 : i2);
+      }
+      cnt += __popc(m);
+    }
+    out += cnt;
+  }
+}
+constexpr int BD_WARPS = 8;
+__global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double lambda, int n_p, int ld, int planes_write_S) {
+  const int lane = threadIdx.x & 31;
+  const int L = blockIdx.x * BD_WARPS + (threadIdx.x >> 5);
+  if (L >= g.n_lm) return;
+  if (!landmark_active(g, L)) {  // inactive landmark: its blocks must not carry products of an earlier trial
+    const int a0 = g.lm_rowptr[L] * 18, a1 = g.lm_rowptr[L + 1] * 18;
+    for (int it = a0 + lane; it < a1; it += 32) g.BD[it] = 0.0;
+    return;
+  }
+  double h[6], D[6], bl[3], db[3];
+#pragma unroll
+  for (int i = 0; i < 6; i++) h[i] = g.Hll[6 * (size_t)L + i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) bl[i] = g.bl[3 * (size_t)L + i];
+  inv_sym3(h, lambda, D);
+  db[0] = D[0] * bl[0] + D[1] * bl[1] + D[2] * bl[2];
+  db[1] = D[1] * bl[0] + D[3] * bl[1] + D[4] * bl[2];
+  db[2] = D[2] * bl[0] + D[4] * bl[1] + D[5] * bl[2];
+  if (lane < 6) g.Dinv[6 * (size_t)L + lane] = D[lane];
+  const bool to_S = L >= g.n_pl || planes_write_S;  // sharded window: planes are reduced by rank 0 only
+  const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
+  const double *W = g.Hpl + 18 * (size_t)b0;
+  double *BD = g.BD + 18 * (size_t)b0;
+  const int n = (b1 - b0) * 18;
+  for (int it = lane; it < n; it += 32) {
+    const int e = it / 18, q = it - 18 * e, r = q / 3, c = q - 3 * r;
+    const double w0 = W[18 * e + 3 * r], w1 = W[18 * e + 3 * r + 1], w2 = W[18 * e + 3 * r + 2];
+    const double dc0 = c == 0 ? D[0] : (c == 1 ? D[1] : D[2]);
+    const double dc1 = c == 0 ? D[1] : (c == 1 ? D[3] : D[4]);
+    const double dc2 = c == 0 ? D[2] : (c == 1 ? D[4] : D[5]);
+    BD[it] = to_S ? w0 * dc0 + w1 * dc1 + w2 * dc2 : 0.0;
+    if (c == 0 && to_S) {  // reduced gradient: bschur_i -= W Dinv bl   (coefficients, core/block_solver.hpp:403-405)
+      const int p = g.ent_pidx[b0 + e];
+      if (p >= 0) atomicAdd(&g.S[(size_t)(6 * p + r) * ld + n_p], -(w0 * db[0] + w1 * db[1] + w2 * db[2]));
+    }
+  }
+}
+constexpr int PAIR_CHUNK = 64;
+constexpr int PAIR_WARPS = 8;
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, const unsigned *keys, const unsigned long long *vals, int n_pairs, int ld) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+  const long long c0 = w * PAIR_CHUNK;
+  if (c0 >= n_pairs) return;
+  const int c1 = (int)min((long long)n_pairs, c0 + PAIR_CHUNK);
+  const int r0 = lane / 6, q0 = lane - 6 * r0;  // entry owned by this lane: (r0, q0); lanes 0..3 also own (5, 2 + lane)
+  unsigned cur = 0xffffffffu;
+  int p1 = -1, p2 = -1;
+  double acc0 = 0.0, acc1 = 0.0;
+  auto flush = [&]() {
+    if (p1 >= 0 && p2 >= 0) {
+      atomicAdd(&g.S[(size_t)(6 * p1 + r0) * ld + 6 * p2 + q0], -acc0);
+      if (lane < 4) atomicAdd(&g.S[(size_t)(6 * p1 + 5) * ld + 6 * p2 + 2 + lane], -acc1);
+    }
+    acc0 = acc1 = 0.0;
+  };
+  for (int c = (int)c0; c < c1; c++) {
+    const unsigned key = keys[c];
+    if (key != cur) {
+      flush();
+      cur = key;
+      p1 = g.kf_idx[key / (unsigned)g.n_kf];
+      p2 = g.kf_idx[key % (unsigned)g.n_kf];
+    }
+    if (p1 < 0 || p2 < 0) continue;  // inactive key-frame
+    const unsigned long long v = vals[c];
+    const double *B = g.BD + 18 * (size_t)(unsigned)(v >> 32);
+    const double *W = g.Hpl + 18 * (size_t)(unsigned)(v & 0xffffffffu);
+    acc0 += B[3 * r0] * W[3 * q0] + B[3 * r0 + 1] * W[3 * q0 + 1] + B[3 * r0 + 2] * W[3 * q0 + 2];
+    if (lane < 4) acc1 += B[15] * W[3 * (2 + lane)] + B[16] * W[3 * (2 + lane) + 1] + B[17] * W[3 * (2 + lane) + 2];
+  }
+  flush();
+}
+
 // S += Hpp (+ lambda on the diagonal), rhs column += bp.  One thread per scalar of each block.
 __global__ void k_compose(DevGraph g, double lambda, int n_p, int ld) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
