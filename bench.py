@@ -23,6 +23,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+FP64_TFLOPS = 37.2  # measured on this pool's B200 with tools/ubench/fp64.cu (DMMA == DFMA rate)
 METRIC = "LM iterations/sec"
 UNIT = "LM it/s"
 
@@ -35,6 +36,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the extra concurrent-windows throughput measurement")
     return ap.parse_args()
 
 
@@ -89,6 +91,45 @@ def oracle_lm_rate(ppo, g, full_call):
         iters = o.optimize(o.params.iters_round1).iterations
     dt = time.perf_counter() - t0
     return iters / dt, iters, dt
+
+
+def batched_throughput(ppo, ci, params, device, n_win=8, n_thr=8):
+    """Extra: W independent windows of the same size on ONE GPU, T host threads / handles / streams (configs[3] style):
+    the latency-bound phases of different windows overlap on the device."""
+    graphs = [ppo.synth.make_graph(ppo.synth.config(ci, window=100 + w)) for w in range(n_win)]
+    engines = [ppo.LocalBA(params, device=device) for _ in range(n_win)]
+    for e, g in zip(engines, graphs):
+        e.set_graph(g)
+    iters = [0] * n_win
+
+    def run_all():
+        nxt, lock = [0], threading.Lock()
+
+        def worker():
+            while True:
+                with lock:
+                    w = nxt[0]
+                    nxt[0] += 1
+                if w >= n_win:
+                    return
+                engines[w].reset()
+                r = engines[w].local_ba()
+                iters[w] = r.round1.iterations + r.round2.iterations
+
+        ts = [threading.Thread(target=worker) for _ in range(n_thr)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    run_all()
+    dt = min(run_all() for _ in range(3))
+    for e in engines:
+        e.close()
+    return {"windows": n_win, "host_threads": n_thr, "lm_it_per_s": sum(iters) / dt, "kf_windows_per_sec": n_win / dt,
+            "note": "wall clock around the whole batch, graphs resident"}
 
 
 def run_reference(args, rank, world, out_stream):
@@ -202,6 +243,8 @@ def main():
     # roofline of the Jacobian / assembly kernel (cold L2 each launch, CUDA events on the engine's stream)
     eng.reset()
     asm_ms, asm_bytes = eng.time_assembly(20)
+    eng.reset()
+    sol_ms, sol_flops, sol_n = eng.time_solve(10)
     prof = None
     if rank == 0:
         eng.reset()
@@ -210,6 +253,9 @@ def main():
         eng.set_profiling(False)
         prof = {k: getattr(pr.round1, k) + getattr(pr.round2, k) for k in ("ms_linearize", "ms_schur", "ms_solve", "ms_update", "ms_total")}
 
+    batched = None
+    if rank == 0 and world == 1 and not args.no_batched:
+        batched = batched_throughput(ppo, ci, params, local_rank)
     vals = torch.tensor([ms, float(iters), e2e_s, float(e2e_iters)], dtype=torch.float64, device="cuda")
     if dist is not None:
         mx = vals.clone()
@@ -225,6 +271,11 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = {}
+        try:  # dram__bytes_read+write per launch from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        except Exception:
+            pass
         achieved = asm_bytes / (asm_ms * 1e-3) / 1e9
         value = iters / (ms * 1e-3)
         state_bytes = 8 * (7 * g.c.n_kf + 3 * g.c.n_pt + 4 * g.c.n_pl + 10 * g.c.n_cu)
@@ -239,10 +290,20 @@ def main():
             "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": g.nbytes(), "d2h_bytes_per_step": state_bytes,
                     "ms_per_step": 1e3 * e2e_s / n_e2e},
             "gpu_launches": launches,
-            "roofline": {"kernel": "k_point_linearize (point-edge Jacobian/assembly)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "ms": asm_ms, "algo_bytes": asm_bytes,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            # the time-dominant phase of a step is the dense solve of the reduced pose system: FP64 tensor
+            # pipe (DMMA) for the trailing updates, latency-bound panel chain.  Peak: FP64 DMMA/DFMA rate measured with
+            # tools/ubench/fp64.cu (64 FMA/clk/SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s); MEASURED_PEAKS.json has no FP64 figure.
+            "roofline": {"kernel": "dense Hschur solve: k_potrf_inv + k_panel_gemm + k_syrk_update (DMMA) + k_backsolve_step", "bound": "tensor",
+                         "achieved": sol_flops / (sol_ms * 1e-3) / 1e12, "peak": FP64_TFLOPS, "unit": "TFLOP/s",
+                         "frac": sol_flops / (sol_ms * 1e-3) / 1e12 / FP64_TFLOPS, "traffic": None, "ms": sol_ms, "algo_flops": sol_flops,
+                         "n_p": sol_n, "peak_source": "measured FP64 DMMA rate, tools/ubench/fp64.cu (of measured; bf16 peak in MEASURED_PEAKS.json does not apply to an FP64 solve)"},
+            # the kernel the north_star names: Jacobian / assembly over the point edges, HBM-bound
+            "roofline_assembly": {"kernel": "k_point_linearize (point-edge Jacobian/assembly)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                                  "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("k_point_linearize"), "ms": asm_ms,
+                                  "algo_bytes": asm_bytes,
+                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "phases_ms_per_call": prof,
+            "batched": batched,
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:

@@ -245,6 +245,8 @@ long long ppo_ba_launch_count(const ppo_ba_handle *h);
  * bytes one launch moves.  Used by bench.py for the roofline object. */
 int ppo_ba_time_assembly(ppo_ba_handle *h, int reps, double *ms_mean, double *algo_bytes);
 
+/* Same for the dense solve of the reduced pose system (factorisation + substitutions); flops = n_p^3/3 + 2 n_p^2. */
+int ppo_ba_time_solve(ppo_ba_handle *h, int reps, double *ms_mean, double *flops, int *n_p);
 /* Device-side stopwatch on the handle's stream: mark(0) ... mark(1), elapsed = ms between the two
  * CUDA events (includes every gap in which the stream idles waiting for the host LM controller). */
 int ppo_ba_mark(ppo_ba_handle *h, int which);

@@ -489,19 +489,17 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
     if ((unsigned long long)g.n_kf * (unsigned long long)g.n_kf >= 0xffffffffull) { h->err = "too many key-frames for 32-bit pair keys"; return PPO_E_INVALID; }
     std::vector<int> pair_off(g.n_lm + 1, 0);
     long long total = 0;
-    std::vector<int> seen;
+    std::vector<int> stamp(g.n_kf, -1);  // last landmark that touched a key-frame slot: O(1) duplicate test
     for (int L = 0; L < g.n_lm; L++) {
       long long kfree = 0;
-      seen.clear();
       for (int en = lm_rowptr[L]; en < lm_rowptr[L + 1]; en++) {
         const int sl = en < g.n_slots ? slot_kf[en] : rec[en - g.n_slots].kf;
-        seen.push_back(sl);
+        if (stamp[sl] == L) {  // MapPoint::mObservations is a map keyed by KeyFrame*: one observation per key-frame
+          h->err = "a landmark is observed twice by the same key-frame";
+          return PPO_E_INVALID;
+        }
+        stamp[sl] = L;
         kfree += !kf_fixed[sl];
-      }
-      std::sort(seen.begin(), seen.end());
-      if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) {  // MapPoint::mObservations is a map keyed by KeyFrame*
-        h->err = "a landmark is observed twice by the same key-frame";
-        return PPO_E_INVALID;
       }
       pair_off[L] = (int)total;
       total += kfree * (kfree + 1) / 2;
@@ -1111,6 +1109,33 @@ int ppo_ba_time_assembly(ppo_ba_handle *h, int reps, double *ms_mean, double *al
   // + 1 B flags read, 144 B Hpl + 8 B chi2 written; per point 4 B rowptr + 24 B xyz read, 72 B Hll/bl written;
   // per key-frame 96 B pose cache + 20 B intrinsics read.
   if (algo_bytes) *algo_bytes = (double)g.n_pe * (16 + 4 + 4 + 1 + 144 + 8) + (double)g.n_pt * (4 + 24 + 72) + (double)g.n_kf * (96 + 20);
+  return PPO_OK;
+}
+
+// Times the dense solve of the reduced pose system (factorisation + both substitutions) on the current linearisation:
+// the Schur system is rebuilt (untimed) before every timed solve because the factorisation is in place.
+int ppo_ba_time_solve(ppo_ba_handle *h, int reps, double *ms_mean, double *flops, int *n_p_out) {
+  if (!h || !h->have_graph || reps <= 0) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  int rc = init_mapping(h);
+  if (rc) return rc;
+  if ((rc = linearize(h, true))) return rc;
+  const double lambda = h->P.lm_tau * h->h_scal->max_diag;
+  double total = 0;
+  for (int i = 0; i < reps + 2; i++) {
+    if ((rc = schur_system(h, lambda))) return rc;
+    CK(cudaEventRecord(h->ev0, h->st));
+    dense_cholesky_solve(h->g.S, h->n_p, h->ld, h->g.xp, h->d_Winv, h->d_not_spd, h->st, &h->launches);
+    CK(cudaEventRecord(h->ev1, h->st));
+    CK(cudaEventSynchronize(h->ev1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (i >= 2) total += ms;
+  }
+  if (ms_mean) *ms_mean = total / reps;
+  const double n = h->n_p;
+  if (flops) *flops = n * n * n / 3.0 + 2.0 * n * n;  // Cholesky + two triangular solves
+  if (n_p_out) *n_p_out = h->n_p;
   return PPO_OK;
 }
 

@@ -153,7 +153,7 @@ PPO_D void point_edge_linearize(const double Rt[12], const double X[3], const fl
   }
 }
 
-constexpr int LIN_WARPS = 4;
+constexpr int LIN_WARPS = 1;  // one warp per CTA: the unit bounds come from a block-uniform address, so the scan shuffles need no convergence barriers
 constexpr int STAGE_LD = 19;  // 18 doubles per 6x3 block + 1 pad: conflict-free half-warp stores
 
 // The Jacobian / assembly pass over the point edges (computeActiveErrors + linearizeOplus +
@@ -161,7 +161,7 @@ constexpr int STAGE_LD = 19;  // 18 doubles per 6x3 block + 1 pad: conflict-free
 // EdgeStereoSE3ProjectXYZ, landmark side): one warp owns a run of consecutive points with <= 32
 // edges, one lane per edge; Hll / bl come from a segmented warp-shuffle scan, the 6x3 Hpl blocks
 // are staged in shared memory and stored as one contiguous coalesced run.
-__global__ void __launch_bounds__(LIN_WARPS * 32, 4) k_point_linearize(DevGraph g, DevState s, double *chi_part) {
+__global__ void __launch_bounds__(LIN_WARPS * 32, 20) k_point_linearize(DevGraph g, DevState s, double *chi_part) {
   __shared__ double stage[LIN_WARPS][32 * STAGE_LD];
   __shared__ double wsum[LIN_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -951,42 +951,43 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double la
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = blockIdx.x * BS_WARPS + warp;
   double sc = 0;
-  if (L < g.n_lm) {
-    if (landmark_active(g, L)) {
-      const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
-      double c[3] = {0, 0, 0};
-      const int n = (b1 - b0) * 18;
-      const double *W = g.Hpl + 18 * (size_t)b0;
-      for (int i = lane; i < n; i += 32) {
-        const int ent = b0 + i / 18, a = (i % 18) / 3, col = i % 3;
-        const int p = g.ent_pidx[ent];
-        if (p >= 0) {
-          const double t = W[i] * g.xp[6 * p + a];
-          if (col == 0) c[0] += t;
-          else if (col == 1) c[1] += t;
-          else c[2] += t;
-        }
+  const bool in_range = L < g.n_lm;
+  const bool act = in_range && landmark_active(g, L);
+  double c[3] = {0, 0, 0};
+  if (act) {
+    const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
+    const int n = (b1 - b0) * 18;
+    const double *W = g.Hpl + 18 * (size_t)b0;
+    for (int i = lane; i < n; i += 32) {
+      const int ent = b0 + i / 18, a = (i % 18) / 3, col = i % 3;
+      const int p = g.ent_pidx[ent];
+      if (p >= 0) {
+        const double t = W[i] * g.xp[6 * p + a];
+        if (col == 0) c[0] += t;
+        else if (col == 1) c[1] += t;
+        else c[2] += t;
       }
-#pragma unroll
-      for (int k = 0; k < 3; k++) c[k] = warp_sum(c[k]);
-      if (lane == 0) {
-        double D[6], bl[3], cl[3], x[3];
-#pragma unroll
-        for (int i = 0; i < 6; i++) D[i] = g.Dinv[6 * (size_t)L + i];
-#pragma unroll
-        for (int i = 0; i < 3; i++) bl[i] = g.bl[3 * (size_t)L + i], cl[i] = bl[i] - c[i];
-        x[0] = D[0] * cl[0] + D[1] * cl[1] + D[2] * cl[2];
-        x[1] = D[1] * cl[0] + D[3] * cl[1] + D[4] * cl[2];
-        x[2] = D[2] * cl[0] + D[4] * cl[1] + D[5] * cl[2];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          g.xl[3 * (size_t)L + i] = x[i];
-          if (L >= g.n_pl || planes_in_scale) sc += x[i] * (lambda * x[i] + bl[i]);
-        }
-      }
-    } else if (lane < 3) {
-      g.xl[3 * (size_t)L + lane] = 0.0;
     }
+  }
+  // reductions in warp-uniform control flow (no convergence barriers around the shuffles)
+#pragma unroll
+  for (int k = 0; k < 3; k++) c[k] = warp_sum(c[k]);
+  if (act && lane == 0) {
+    double D[6], bl[3], cl[3], x[3];
+#pragma unroll
+    for (int i = 0; i < 6; i++) D[i] = g.Dinv[6 * (size_t)L + i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) bl[i] = g.bl[3 * (size_t)L + i], cl[i] = bl[i] - c[i];
+    x[0] = D[0] * cl[0] + D[1] * cl[1] + D[2] * cl[2];
+    x[1] = D[1] * cl[0] + D[3] * cl[1] + D[4] * cl[2];
+    x[2] = D[2] * cl[0] + D[4] * cl[1] + D[5] * cl[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      g.xl[3 * (size_t)L + i] = x[i];
+      if (L >= g.n_pl || planes_in_scale) sc += x[i] * (lambda * x[i] + bl[i]);
+    }
+  } else if (in_range && !act && lane < 3) {
+    g.xl[3 * (size_t)L + lane] = 0.0;
   }
   if (lane == 0) wsum[warp] = sc;
   __syncthreads();

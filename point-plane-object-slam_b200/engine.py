@@ -56,6 +56,7 @@ def load_library():
         lib.ppo_ba_launch_count.argtypes = [C.c_void_p]
         lib.ppo_ba_launch_count.restype = C.c_longlong
         lib.ppo_ba_time_assembly.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.ppo_ba_time_solve.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         lib.ppo_ba_mark.argtypes = [C.c_void_p, C.c_int]
         lib.ppo_ba_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.ppo_ba_flush_l2.argtypes = [C.c_void_p]
@@ -202,6 +203,11 @@ class LocalBA(Handle):
         ms, by = C.c_double(), C.c_double()
         self._check(self.lib.ppo_ba_time_assembly(self.h, reps, C.byref(ms), C.byref(by)), "time_assembly")
         return ms.value, by.value
+
+    def time_solve(self, reps=10):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int()
+        self._check(self.lib.ppo_ba_time_solve(self.h, reps, C.byref(ms), C.byref(fl), C.byref(n)), "time_solve")
+        return ms.value, fl.value, n.value
 
     def mark(self, which):
         self._check(self.lib.ppo_ba_mark(self.h, which), "mark")
