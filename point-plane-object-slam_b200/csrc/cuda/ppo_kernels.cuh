@@ -874,37 +874,65 @@ __global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double l
 }
 constexpr int PAIR_CHUNK = 64;
 constexpr int PAIR_WARPS = 8;
-__global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, const unsigned *keys, const unsigned long long *vals, int n_pairs, int ld) {
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, const unsigned *__restrict__ keys, const unsigned long long *__restrict__ vals,
+                                                                 int n_pairs, int ld) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
   const long long c0 = w * PAIR_CHUNK;
-  if (c0 >= n_pairs) return;
-  const int c1 = (int)min((long long)n_pairs, c0 + PAIR_CHUNK);
+  if (c0 >= n_pairs) return;  // warp-uniform
+  const int cnt = (int)min((long long)PAIR_CHUNK, (long long)n_pairs - c0);
+  // the chunk's keys / values: two coalesced loads per lane, then warp broadcasts (no dependent global loads in the loop)
+  unsigned kl[2];
+  unsigned long long vl[2];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int c = 32 * q + lane;
+    kl[q] = c < cnt ? keys[c0 + c] : 0xffffffffu;
+    vl[q] = c < cnt ? vals[c0 + c] : 0ull;
+  }
   const int r0 = lane / 6, q0 = lane - 6 * r0;  // entry owned by this lane: (r0, q0); lanes 0..3 also own (5, 2 + lane)
+  const int offB0 = 3 * r0, offW0 = 3 * q0, offW1 = 3 * (2 + (lane & 3));
+  const bool extra = lane < 4;
   unsigned cur = 0xffffffffu;
   int p1 = -1, p2 = -1;
   double acc0 = 0.0, acc1 = 0.0;
   auto flush = [&]() {
     if (p1 >= 0 && p2 >= 0) {
       atomicAdd(&g.S[(size_t)(6 * p1 + r0) * ld + 6 * p2 + q0], -acc0);
-      if (lane < 4) atomicAdd(&g.S[(size_t)(6 * p1 + 5) * ld + 6 * p2 + 2 + lane], -acc1);
+      if (extra) atomicAdd(&g.S[(size_t)(6 * p1 + 5) * ld + 6 * p2 + 2 + lane], -acc1);
     }
     acc0 = acc1 = 0.0;
   };
-  for (int c = (int)c0; c < c1; c++) {
-    const unsigned key = keys[c];
-    if (key != cur) {
-      flush();
-      cur = key;
-      p1 = g.kf_idx[key / (unsigned)g.n_kf];
-      p2 = g.kf_idx[key % (unsigned)g.n_kf];
+  constexpr int U = 4;  // contributions whose 6 + 6 operand loads are in flight together
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    for (int cb = 0; cb < 32; cb += U) {
+      if (32 * q + cb >= cnt) break;  // warp-uniform
+      unsigned key[U];
+      double d0[U], d1[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        key[u] = __shfl_sync(FULL, kl[q], cb + u);
+        const unsigned long long v = __shfl_sync(FULL, vl[q], cb + u);
+        const bool ok = key[u] != 0xffffffffu;
+        const double *B = g.BD + 18 * (size_t)(unsigned)(v >> 32);
+        const double *W = g.Hpl + 18 * (size_t)(unsigned)(v & 0xffffffffu);
+        d0[u] = ok ? B[offB0] * W[offW0] + B[offB0 + 1] * W[offW0 + 1] + B[offB0 + 2] * W[offW0 + 2] : 0.0;
+        d1[u] = (ok && extra) ? B[15] * W[offW1] + B[16] * W[offW1 + 1] + B[17] * W[offW1 + 2] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (key[u] == 0xffffffffu) continue;
+        if (key[u] != cur) {
+          flush();
+          cur = key[u];
+          p1 = g.kf_idx[cur / (unsigned)g.n_kf];
+          p2 = g.kf_idx[cur % (unsigned)g.n_kf];
+        }
+        acc0 += d0[u];
+        acc1 += d1[u];
+      }
     }
-    if (p1 < 0 || p2 < 0) continue;  // inactive key-frame
-    const unsigned long long v = vals[c];
-    const double *B = g.BD + 18 * (size_t)(unsigned)(v >> 32);
-    const double *W = g.Hpl + 18 * (size_t)(unsigned)(v & 0xffffffffu);
-    acc0 += B[3 * r0] * W[3 * q0] + B[3 * r0 + 1] * W[3 * q0 + 1] + B[3 * r0 + 2] * W[3 * q0 + 2];
-    if (lane < 4) acc1 += B[15] * W[3 * (2 + lane)] + B[16] * W[3 * (2 + lane) + 1] + B[17] * W[3 * (2 + lane) + 2];
   }
   flush();
 }
