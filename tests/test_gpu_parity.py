@@ -237,3 +237,41 @@ def test_invalid_graph_is_rejected(ppo):
     e = ppo.LocalBA()
     with pytest.raises(ppo.EngineError):
         e.set_graph(A.GraphArrays(**a))
+
+
+def test_degenerate_graphs(ppo, oracle_mod):
+    """Empty / ragged inputs: no points at all, points without edges, a window whose every vertex is fixed."""
+    A = ppo.abi
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=8, n_fixed=2, n_pt=200, n_pl=4, n_cu=2))
+    # (1) planes and cuboids only (n_pt = 0)
+    a = {k: v.copy() for k, v in g.a.items()}
+    for k in ("pt_xyz", "pe_kf", "pe_obs", "pe_invsigma2"):
+        a[k] = a[k][:0]
+    a["pt_rowptr"] = np.zeros(1, np.int32)
+    full_parity(ppo, oracle_mod, A.GraphArrays(**a), strict=False)
+    # (2) half of the points have no observation at all (inactive vertices keep their estimate)
+    a = {k: v.copy() for k, v in g.a.items()}
+    rp = a["pt_rowptr"].astype(np.int64)
+    keep = np.zeros(g.c.n_pe, bool)
+    new_rp = [0]
+    for p in range(g.c.n_pt):
+        if p % 2 == 0:
+            keep[rp[p]:rp[p + 1]] = True
+        new_rp.append(int(keep.sum()))
+    a["pe_kf"], a["pe_obs"], a["pe_invsigma2"] = a["pe_kf"][keep], a["pe_obs"][keep], a["pe_invsigma2"][keep]
+    a["pt_rowptr"] = np.array(new_rp, np.int32)
+    g2 = A.GraphArrays(**a)
+    o, e = run_both(ppo, oracle_mod, g2)
+    o.local_ba(); e.local_ba()
+    se, so = e.get_state(), o.get_state()
+    assert np.array_equal(se.pt_xyz[1::2], g["pt_xyz"][1::2])  # untouched
+    assert all(v <= TOL for v in state_errors(se, so).values())
+    # (3) every key-frame and every point fixed, no planes / cuboids: nothing to optimise -> PPO_E_EMPTY, estimates untouched
+    a = {k: v.copy() for k, v in g.a.items() if k.startswith(("kf_", "pt_", "pe_"))}
+    a["kf_fixed"][:] = 1
+    a["pt_fixed"] = np.ones(g.c.n_pt, np.uint8)
+    e3 = ppo.LocalBA()
+    e3.set_graph(A.GraphArrays(**a))
+    st = e3.optimize(5)
+    assert st.iterations == 0
+    assert np.array_equal(e3.get_state().pt_xyz, g["pt_xyz"])
