@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the extra concurrent-windows throughput measurement")
+    ap.add_argument("--shard", action="store_true",
+                    help="ONE window for the whole job, its points sharded over the ranks (NCCL all-reduce of the reduced system): strong scaling")
     return ap.parse_args()
 
 
@@ -192,11 +194,20 @@ def main():
             torch.cuda.synchronize()
 
     ci = args.config
-    g = ppo.synth.make_graph(ppo.synth.config(ci, window=rank))  # one independent window per rank
+    shard = args.shard and world > 1
+    g = ppo.synth.make_graph(ppo.synth.config(ci, window=0 if shard else rank))  # one independent window per rank unless sharded
     params = ppo.default_params()
     if ci == 0:
         params.solver = ppo.abi.SOLVER_6_3  # points-only LocalBundleAdjustment stack (Optimizer.cc:516-522)
     eng = ppo.LocalBA(params, device=local_rank)
+    comm = None
+    if shard:
+        uid = [ppo.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = ppo.nccl_init(uid[0], rank, world, local_rank)
+        eng.set_shard(comm, rank, world)
+        g_full = g
+        g = ppo.sharding.shard_graph(g_full, rank, world)[0]
     eng.set_graph(g)
 
     def step_resident():
@@ -246,7 +257,7 @@ def main():
     eng.reset()
     sol_ms, sol_flops, sol_n = eng.time_solve(10)
     prof = None
-    if rank == 0:
+    if rank == 0 or shard:  # sharded: every rank takes part in the collectives of the profiled call
         eng.reset()
         eng.set_profiling(True)
         pr = eng.local_ba()
@@ -264,6 +275,8 @@ def main():
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, e2e_s = float(mx[0]), float(mx[2])
         iters, e2e_iters = float(sm[1]), float(sm[3])
+        if shard:  # every rank executes the same LM iterations of the one window
+            iters, e2e_iters = iters / world, e2e_iters / world
     if rank == 0:
         peaks = {}
         try:
@@ -281,12 +294,13 @@ def main():
         state_bytes = 8 * (7 * g.c.n_kf + 3 * g.c.n_pt + 4 * g.c.n_pl + 10 * g.c.n_cu)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(ci), "windows_per_gpu": 1, "schedule": "optimize(5)+outlier pass+optimize(10)",
+                       "partition": "one window, points sharded over ranks, ncclAllReduce of Hschur|bschur per damped trial" if shard else "independent windows, no data-path collective",
                        "l2": "flushed between timed steps (256 MiB memset)", "lm_iterations_per_step": iters / max(1, args.steps) / world,
                        "n_pose_dim": last.round1.n_pose_dim, "n_point_edges": g.c.n_pe},
-            "kf_windows_per_sec": world * args.steps / (ms * 1e-3),
+            "kf_windows_per_sec": (1 if shard else world) * args.steps / (ms * 1e-3),
             "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": g.nbytes(), "d2h_bytes_per_step": state_bytes,
                     "ms_per_step": 1e3 * e2e_s / n_e2e},
             "gpu_launches": launches,
@@ -306,7 +320,7 @@ def main():
             "batched": batched,
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and not shard and ci != 4:
             g0 = g if world == 1 else ppo.synth.make_graph(ppo.synth.config(ci))
             v, it, dt = oracle_lm_rate(ppo, g0, True)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
@@ -315,6 +329,9 @@ def main():
         print(json.dumps(out), file=out_stream, flush=True)
     if dist is not None:
         dist.barrier()
+        if comm is not None:
+            eng.close()
+            ppo.nccl_destroy(comm)
         dist.destroy_process_group()
 
 

@@ -22,6 +22,25 @@ constexpr int NB = 64;  // panel width
 
 #define A_(i, j) S[(size_t)(j) * ld + (i)]
 
+// Programmatic dependent launch: every kernel of the panel chain is launched with the programmatic-stream-serialisation
+// attribute and waits here for its predecessor; launch processing of kernel N+1 overlaps the tail of kernel N.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // --- diagonal block: Cholesky + explicit inverse of the 64 x 64 factor --------------------------------
 // Gaussian elimination of [A | I] without scaling: A ends as L_u D (unit-lower factor times pivots), the
 // identity part as X = L_u^-1; then L = L_u D^1/2 and W = L^-1 = D^-1/2 X.
@@ -78,6 +97,8 @@ __device__ __forceinline__ void pf_eliminate(double (&V)[32], double (&X)[32], d
   }
 }
 __global__ void __launch_bounds__(PF_THREADS) k_potrf_inv(double *S, int ld, int k, int nb, double *Winv, int *not_spd) {
+  pdl_launch_dependents();
+  pdl_wait();
   PF_STAMP(0);
   __shared__ __align__(16) double va[2][NB];
   __shared__ __align__(16) double vx[2][NB];
@@ -155,6 +176,8 @@ __device__ __forceinline__ void tile_mma(const double (*sA)[SLD], const double (
 __global__ void __launch_bounds__(256) k_panel_gemm(double *S, int ld, int k, int nb, int n_rows_total, const double *Winv) {
   __shared__ double sA[KC][SLD];
   __shared__ double sB[KC][SLD];
+  pdl_launch_dependents();
+  pdl_wait();
   const int i0 = k + nb + blockIdx.x * TS;
   const int tid = threadIdx.x;
   double acc[8][2];
@@ -194,6 +217,7 @@ __global__ void __launch_bounds__(256) k_panel_gemm(double *S, int ld, int k, in
 __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, int nb, int n) {
   __shared__ double sA[KC][SLD];
   __shared__ double sB[KC][SLD];
+  pdl_launch_dependents();
   // map linear block id -> (bi, bj), bj <= bi
   int bid = blockIdx.x, bi = 0;
   while (bid >= bi + 1) {
@@ -204,6 +228,7 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
   const int k2 = k + nb;
   const int i0 = k2 + bi * TS, j0 = k2 + bj * TS;
   const int tid = threadIdx.x;
+  pdl_wait();
   double acc[8][2];
 #pragma unroll
   for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
@@ -250,6 +275,8 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
 // every CTA recomputes x_B = W_BB^T y_B (64 x 64 mat-vec), CTA c then folds x_B into the 64 columns it owns:
 // y_i -= sum_r L(b0 + r, i) x_B[r].
 __global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n, int b0, int nb, const double *Winv, double *x) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double sW[NB][NB + 1];
   __shared__ double xb[NB];
   __shared__ double part[4][NB];
@@ -304,20 +331,20 @@ void dense_cholesky_solve(double *S, int n, int ld, double *x, double *Winv, int
   for (int k = 0, blk = 0; k < n; k += NB, blk++) {
     const int nb = (n - k < NB) ? (n - k) : NB;
     double *W = Winv + (size_t)blk * NB * NB;
-    k_potrf_inv<<<1, PF_THREADS, 0, st>>>(S, ld, k, nb, W, not_spd);
+    launch_pdl(k_potrf_inv, dim3(1), dim3(PF_THREADS), st, S, ld, k, nb, W, not_spd);
     (*launches)++;
     const int below = rows_total - (k + nb);
     if (below > 0) {
       const int T = (below + TS - 1) / TS;
-      k_panel_gemm<<<T, 256, 0, st>>>(S, ld, k, nb, rows_total, W);
-      k_syrk_update<<<T * (T + 1) / 2, 256, 0, st>>>(S, ld, k, nb, n);
+      launch_pdl(k_panel_gemm, dim3(T), dim3(256), st, S, ld, k, nb, rows_total, (const double *)W);
+      launch_pdl(k_syrk_update, dim3(T * (T + 1) / 2), dim3(256), st, S, ld, k, nb, n);
       (*launches) += 2;
     }
   }
   const int nblk = (n + NB - 1) / NB;
   for (int b = nblk - 1; b >= 0; b--) {
     const int b0 = b * NB, nb = (n - b0 < NB) ? (n - b0) : NB;
-    k_backsolve_step<<<1 + b, 256, 0, st>>>(S, ld, n, b0, nb, Winv + (size_t)b * NB * NB, x);
+    launch_pdl(k_backsolve_step, dim3(1 + b), dim3(256), st, S, ld, n, b0, nb, (const double *)(Winv + (size_t)b * NB * NB), x);
     (*launches)++;
   }
 }
