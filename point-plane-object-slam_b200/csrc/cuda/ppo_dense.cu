@@ -8,7 +8,8 @@
 // gradient as an extra row n.  Factoring the lower triangle while carrying row n through the panel
 // solves and trailing updates turns row n into y = L^-1 b (forward substitution for free).
 //
-// Per 64-column panel:  k_potrf_inv   (1 CTA)   L_kk = chol(A_kk) and W_kk = L_kk^-1
+// Per 64-column panel:  pf_factor               L_kk = chol(A_kk) and W_kk = L_kk^-1  (one CTA: k_potrf_inv for panel 0,
+//                                               afterwards CTA 0 of the previous panel's k_syrk_update)
 //                       k_panel_gemm  (rows/64) A_ik <- A_ik W_kk^T           (TRSM as a GEMM)
 //                       k_syrk_update (tiles)   A_ij -= A_ik A_jk^T           (FP64 tensor cores, DMMA)
 // then per 64-block, last to first:  k_backsolve_step   x_B = W_BB^T y_B ; y_A -= L_BA^T x_B
@@ -42,13 +43,14 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
 }
 
 // --- diagonal block: Cholesky + explicit inverse of the 64 x 64 factor --------------------------------
-// Gaussian elimination of [A | I] without scaling: A ends as L_u D (unit-lower factor times pivots), the
-// identity part as X = L_u^-1; then L = L_u D^1/2 and W = L^-1 = D^-1/2 X.
-// 128 threads: thread (i, h) keeps A(i, c) and X(i, c), c = 32 h + q, in REGISTERS.  Per column j two 64-vectors
-// travel through (double-buffered) shared memory: va[c] = A(c, j) (pivot column, symmetric) and vx[c] = X(j, c).
-// The 64 elimination steps are FULLY UNROLLED (per column half h), so every register index, every "is this column
-// still live" test and the shared-memory addresses are compile-time constants: one FMA per (row, column) and step,
-// one barrier and one reciprocal per column; square roots and the write-out happen after the loop.
+// In-place Gaussian elimination of [A | I] without pivoting or scaling: when column j of A has been eliminated it is
+// dead, and exactly then column j of the identity part starts to fill in, so a single 64 x 64 array holds the live
+// window.  Step j:  u = column j below the pivot (saved: L(:,j) = u / sqrt(d_j)),  v = row j / d_j,  column j := e_j,
+// then the rank-1 update  M -= u v^T.  At the end M = X = L_u^-1 (unit lower), and W = L^-1 = D^-1/2 X.
+// 128 threads, thread (tr, tc) keeps the 8 x 4 block M(8 tr .. , 4 tc ..) in registers: per step 12 operands come
+// through shared memory for 32 FMAs (a 1-D row or column distribution needs one operand per FMA and is bound by the
+// 128 B/clk shared-memory return path).  The step loop is unrolled by 8 only, so that the pivot's position INSIDE a
+// register block is a compile-time constant while the code stays instruction-cache resident.
 constexpr int PF_THREADS = 128;
 #ifdef PPO_POTRF_TIMING
 __device__ long long g_potrf_t[8];
@@ -56,96 +58,185 @@ __device__ long long g_potrf_t[8];
 #else
 #define PF_STAMP(n)
 #endif
-template <int H>
-__device__ __forceinline__ void pf_eliminate(double (&V)[32], double (&X)[32], double (*va)[NB], double (*vx)[NB], double *rinv,
-                                             double (*Lu)[NB + 1], const int i, int *not_spd) {
-#pragma unroll
-  for (int j = 0; j < NB; j++) {
-    __syncthreads();
-    if ((i | 31) >= j) {  // otherwise all rows of this warp are final (warp-uniform)
-      const int cur = j & 1, nxt = cur ^ 1;
-      const double aij = va[cur][i];
-      const double f = i > j ? aij * rinv[j] : 0.0;  // L_u(i,j); finished rows (and row j itself) do not move
-      if (H == 0 && i >= j) Lu[i][j] = aij;
-#pragma unroll
-      for (int q = 0; q < 32; q++) {
-        const int c = 32 * H + q;
-        if (c > j) V[q] = fma(-f, va[cur][c], V[q]);  // live column of A
-        else X[q] = fma(-f, vx[cur][c], X[q]);        // X(i,c) -= f X(j,c), X(j,j) = 1
-      }
-      const int jn = j + 1;
-      if (jn < NB) {
-        if (jn >= 32 * H && jn < 32 * H + 32 && i >= jn) {  // operand column of the next step: A(i, j+1)
-          const double v = V[(jn - 32 * H) & 31];
-          va[nxt][i] = v;
-          if (i == jn) {
-            double d = v;
-            if (!(d > 0.0)) {
-              *not_spd = 1;
-              d = 1.0;
-            }
-            rinv[jn] = __drcp_rn(d);
-          }
-        }
-        if (i == jn) {  // row j+1 of X is final (its unit diagonal is already in the register)
-#pragma unroll
-          for (int q = 0; q < 32; q++)
-            if (32 * H + q <= jn) vx[nxt][32 * H + q] = X[q];
-        }
-      }
-    }
-  }
+// branch-free reciprocal / reciprocal square root of a normal positive double (hardware seed + one cubic step [+ one
+// Newton step]); anything else yields garbage, which the caller has already flagged as "not positive definite".
+__device__ __forceinline__ double pf_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-d, y, 1.0);  // y (1 + e + e^2 + e^3): one quartic step from the >= 17-bit seed
+  return fma(y, fma(fma(e, e, e), e, e), y);
 }
-__global__ void __launch_bounds__(PF_THREADS) k_potrf_inv(double *S, int ld, int k, int nb, double *Winv, int *not_spd) {
-  pdl_launch_dependents();
-  pdl_wait();
+__device__ __forceinline__ double pf_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);
+  y = fma(y * e, fma(0.375, e, 0.5), y);
+  return fma(y, fma(-0.5 * x * y, y, 0.5), y);
+}
+// Shared-memory accesses of the step loop by explicit 32-bit address (computed once, outside the loop) and with
+// predicated stores: the publishing threads differ per step and branches would serialise their warps.
+__device__ __forceinline__ void sts_if(bool p, unsigned addr, double x) {
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %0, 0; @q st.shared.f64 [%1], %2; }" ::"r"((int)p), "r"(addr), "d"(x) : "memory");
+}
+__device__ __forceinline__ void sts2_if(bool p, unsigned addr, double x, double y) {
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %0, 0; @q st.shared.v2.f64 [%1], {%2, %3}; }" ::"r"((int)p), "r"(addr), "d"(x), "d"(y)
+               : "memory");
+}
+__device__ __forceinline__ double lds1(unsigned addr) {
+  double x;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr) : "memory");
+  return x;
+}
+__device__ __forceinline__ void lds2(unsigned addr, double &x, double &y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr) : "memory");
+}
+constexpr int LDL = NB + 2;  // 16-byte aligned rows
+struct PfSmem {
+  double Lu[NB][LDL];           // first the staged symmetric tile; then Lu[j][i] = column j at step j
+  double rowb[2][NB];           // pivot row (double buffered)
+  double rinv[NB], dpiv[NB];    // 1 / d_j, d_j
+  double rs[NB], sq[NB];        // 1/sqrt(d_j), sqrt(d_j)
+};
+// barrier of the PF_THREADS threads that run the factorisation (the fused caller has more threads in its CTA)
+__device__ __forceinline__ void pf_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PF_THREADS) : "memory"); }
+__device__ __forceinline__ void pf_factor(PfSmem &sm, double *S, int ld, int k, int nb, double *Winv, int *not_spd) {
   PF_STAMP(0);
-  __shared__ __align__(16) double va[2][NB];
-  __shared__ __align__(16) double vx[2][NB];
-  __shared__ double rinv[NB];        // 1 / d_j
-  __shared__ double Lu[NB][NB + 1];  // finished columns A(i,j) = L_u(i,j) d_j
-  __shared__ double rs[NB], sq[NB];  // 1/sqrt(d_c), sqrt(d_c)
-  const int tid = threadIdx.x;
-  const int i = tid & 63, h = tid >> 6;
-  double V[32], X[32];
+  double(*Lu)[LDL] = sm.Lu;
+  double(*rowb)[NB] = sm.rowb;
+  double *rinv = sm.rinv, *dpiv = sm.dpiv, *rs = sm.rs, *sq = sm.sq;
+  const int t = threadIdx.x, tr = t >> 4, tc = t & 15;
+  {
+    const int i = t & 63, c0 = t >> 6;
+    double v[NB / 2];
 #pragma unroll
-  for (int q = 0; q < 32; q++) {
-    const int c = 32 * h + q;
-    V[q] = (i < nb && c < nb && i >= c) ? A_(k + i, k + c) : (i == c ? 1.0 : 0.0);
-    X[q] = i == c ? 1.0 : 0.0;
-  }
-  if (h == 0) {
-    va[0][i] = V[0];
-    vx[0][i] = i == 0 ? 1.0 : 0.0;
-    if (i == 0) {
-      double d = V[0];
-      if (!(d > 0.0)) {
-        *not_spd = 1;
-        d = 1.0;
-      }
-      rinv[0] = __drcp_rn(d);
+    for (int q = 0; q < NB / 2; q++) {
+      const int c = c0 + 2 * q;
+      v[q] = (i < nb && c < nb && i >= c) ? A_(k + i, k + c) : (i == c ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < NB / 2; q++) {
+      const int c = c0 + 2 * q;
+      if (i >= c) Lu[c][i] = v[q], Lu[i][c] = v[q];
     }
   }
-  PF_STAMP(1);
-  if (h == 0) pf_eliminate<0>(V, X, va, vx, rinv, Lu, i, not_spd);
-  else pf_eliminate<1>(V, X, va, vx, rinv, Lu, i, not_spd);
-  __syncthreads();
-  PF_STAMP(2);
-  if (tid < NB) {
-    const double r = sqrt(rinv[tid]);
-    rs[tid] = r;
-    sq[tid] = 1.0 / r;
-  }
-  __syncthreads();
-  const double rsi = rs[i];
+  pf_bar();
+  double a[8][4];
 #pragma unroll
-  for (int q = 0; q < 32; q++) {
-    const int c = 32 * h + q;
-    Winv[(size_t)c * NB + i] = X[q] * rsi;  // W(i,c) = X(i,c) / sqrt(d_i)  (exact zeros above the diagonal)
-    if (i < nb && c < nb && i >= c)        // L(i,c) = A(i,c) / sqrt(d_c) ; L(c,c) = sqrt(d_c)
-      A_(k + i, k + c) = i > c ? Lu[i][c] * rs[c] : sq[c];
+  for (int r = 0; r < 8; r++) {
+    const double2 lo = *reinterpret_cast<const double2 *>(&Lu[8 * tr + r][4 * tc]);
+    const double2 hi = *reinterpret_cast<const double2 *>(&Lu[8 * tr + r][4 * tc + 2]);
+    a[r][0] = lo.x, a[r][1] = lo.y, a[r][2] = hi.x, a[r][3] = hi.y;
+  }
+  pf_bar();
+  // operands of step 0
+  if (tc == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) Lu[0][8 * tr + r] = a[r][0];
+  }
+  if (tr == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) rowb[0][4 * tc + c] = a[0][c];
+  }
+  if (t == 0) {
+    double d = a[0][0];
+    if (!(d > 0.0)) {
+      *not_spd = 1;
+      d = 1.0;
+    }
+    dpiv[0] = d;
+    rinv[0] = pf_rcp(d);
+  }
+  pf_bar();
+  PF_STAMP(1);
+  unsigned s_col = (unsigned)__cvta_generic_to_shared(&Lu[0][8 * tr]);    // + j * LDL * 8: column j, my 8 rows
+  unsigned s_row = (unsigned)__cvta_generic_to_shared(&rowb[0][4 * tc]);  // + (j & 1) * NB * 8: pivot row, my 4 columns
+  unsigned s_rinv = (unsigned)__cvta_generic_to_shared(&rinv[0]), s_dpiv = (unsigned)__cvta_generic_to_shared(&dpiv[0]);
+  // opaque to the compiler: otherwise it re-derives the shared window base (a slow special-register read) in every step
+  asm volatile("" : "+r"(s_col), "+r"(s_row), "+r"(s_rinv), "+r"(s_dpiv));
+#pragma unroll 1
+  for (int jb = 0; jb < NB / 8; jb++) {
+    const unsigned c_col = s_col + jb * (8 * LDL * 8), c_rinv = s_rinv + jb * 64, c_dpiv = s_dpiv + jb * 64;
+    const bool act = tr >= jb, prow = tr == jb;
+#pragma unroll
+    for (int js = 0; js < 8; js++) {
+      const int pc = 2 * jb + (js >> 2), lc = js & 3;                 // thread column / register column of matrix column j = 8 jb + js
+      const int rn = (js + 1) & 7, lcn = (js + 1) & 3;                // register row / column of the next pivot
+      const int jbn = jb + (js == 7), pcn = 2 * jb + ((js + 1) >> 2);  // its thread row / column (none after the last step)
+      if (act) {  // rows above the pivot block are final
+        const double ri = lds1(c_rinv + 8 * js);
+        double u[8], v[4];
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) lds2(s_row + (js & 1) * (NB * 8) + 8 * c, v[c], v[c + 1]);
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) lds2(c_col + js * (LDL * 8) + 8 * r, u[r], u[r + 1]);
+#pragma unroll
+        for (int c = 0; c < 4; c++) v[c] *= -ri;  // v = -(row j) / d_j
+        const bool pcol = tc == pc;
+#pragma unroll
+        for (int r = 0; r <= js; r++) u[r] = prow ? 0.0 : u[r];  // rows up to the pivot do not move
+        v[lc] = pcol ? -ri : v[lc];                              // column j restarts as e_j: X(i,j) = -u_i / d_j below the pivot
+#pragma unroll
+        for (int r = 0; r < 8; r++) a[r][lc] = pcol ? 0.0 : a[r][lc];
+        // the next pivot row and column first: they are published while the rest of the update runs
+#pragma unroll
+        for (int c = 0; c < 4; c++) a[rn][c] = fma(u[rn], v[c], a[rn][c]);
+        const bool piv = tr == jbn && tc == pcn;
+        const double d = a[rn][lcn];
+        const double rd = pf_rcp(d);  // every thread computes it on its own element (straight-line code), the owner publishes
+        if (piv && !(d > 0.0)) *not_spd = 1;  // everything computed from here on is garbage and will be discarded
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+          if (r != rn) a[r][lcn] = fma(u[r], v[lcn], a[r][lcn]);
+        // (js + 1) * 8 wraps into the next block of eight when js == 7; nobody matches the predicates after step 63
+        sts_if(piv, c_rinv + 8 * (js + 1), rd);
+        sts_if(piv, c_dpiv + 8 * (js + 1), d);
+        sts2_if(tr == jbn, s_row + ((js + 1) & 1) * (NB * 8), a[rn][0], a[rn][1]);
+        sts2_if(tr == jbn, s_row + ((js + 1) & 1) * (NB * 8) + 16, a[rn][2], a[rn][3]);
+#pragma unroll
+        for (int r = 0; r < 8; r++) sts_if(tc == pcn, c_col + (js + 1) * (LDL * 8) + 8 * r, a[r][lcn]);
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+            if (r != rn && c != lcn) a[r][c] = fma(u[r], v[c], a[r][c]);
+      }
+      pf_bar();
+    }
+  }
+  PF_STAMP(2);
+  if (t < NB) {
+    const double d = dpiv[t], r = pf_rsqrt(d);
+    rs[t] = r;
+    sq[t] = d * r;
+  }
+  pf_bar();
+  {  // L(i,c) = u_c(i) / sqrt(d_c), L(c,c) = sqrt(d_c): coalesced from shared memory
+    const int i = t & 63;
+#pragma unroll 8
+    for (int c = t >> 6; c < nb; c += 2)
+      if (i < nb && i >= c) A_(k + i, k + c) = i > c ? Lu[c][i] * rs[c] : sq[c];
+  }
+  // W(i,j) = X(i,j) / sqrt(d_i) below the diagonal, 1/sqrt(d_i) on it, exact zeros above
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int j = 4 * tc + c;
+#pragma unroll
+    for (int r = 0; r < 8; r += 2) {
+      const int i = 8 * tr + r;
+      const double r0 = rs[i], r1 = rs[i + 1];
+      const double w0 = i > j ? a[r][c] * r0 : (i == j ? r0 : 0.0);
+      const double w1 = i + 1 > j ? a[r + 1][c] * r1 : (i + 1 == j ? r1 : 0.0);
+      *reinterpret_cast<double2 *>(&Winv[(size_t)j * NB + i]) = make_double2(w0, w1);
+    }
   }
   PF_STAMP(3);
+}
+
+__global__ void __launch_bounds__(PF_THREADS) k_potrf_inv(double *S, int ld, int k, int nb, double *Winv, int *not_spd) {
+  __shared__ __align__(16) PfSmem sm;
+  pdl_launch_dependents();
+  pdl_wait();
+  pf_factor(sm, S, ld, k, nb, Winv, not_spd);
 }
 
 // --- 64 x 64 output tile of  C = sum_m A(i,m) B(j,m)  on the FP64 tensor cores ---------------------------
@@ -214,9 +305,20 @@ __global__ void __launch_bounds__(256) k_panel_gemm(double *S, int ld, int k, in
 }
 
 // --- trailing update: C(i,j) -= sum_m P(i,m) P(j,m) over 64x64 tiles of the lower triangle ----------------
-__global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, int nb, int n) {
-  __shared__ double sA[KC][SLD];
-  __shared__ double sB[KC][SLD];
+// CTA 0 owns the next diagonal tile: once it is updated the CTA goes straight on to factorise it (pf_factor), so the
+// 64-step latency-bound factorisation of panel k+1 overlaps the rest of the trailing update of panel k.
+struct TileSmem {
+  double sA[KC][SLD];
+  double sB[KC][SLD];
+};
+union SyrkSmem {
+  TileSmem t;
+  PfSmem pf;
+};
+__global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, int nb, int n, double *Wnext, int *not_spd) {
+  __shared__ __align__(16) SyrkSmem sm;
+  double(*sA)[SLD] = sm.t.sA;
+  double(*sB)[SLD] = sm.t.sB;
   pdl_launch_dependents();
   // map linear block id -> (bi, bj), bj <= bi
   int bid = blockIdx.x, bi = 0;
@@ -268,6 +370,10 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
         const int j = j0 + q * 8 + 2 * (lane & 3) + h;
         if (j < n && i >= j) A_(i, j) = c[q][h] - acc[q][h];
       }
+  }
+  if (blockIdx.x == 0 && k2 < n) {
+    __syncthreads();  // the tile is complete (and the staging buffers are free)
+    if (tid < PF_THREADS) pf_factor(sm.pf, S, ld, k2, min(NB, n - k2), Wnext, not_spd);
   }
 }
 
@@ -328,18 +434,15 @@ __global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n
 void dense_cholesky_solve(double *S, int n, int ld, double *x, double *Winv, int *not_spd, cudaStream_t st, long long *launches) {
   if (n <= 0) return;
   const int rows_total = n + 1;  // rows 0..n (row n carries the gradient)
-  for (int k = 0, blk = 0; k < n; k += NB, blk++) {
+  launch_pdl(k_potrf_inv, dim3(1), dim3(PF_THREADS), st, S, ld, 0, n < NB ? n : NB, Winv, not_spd);
+  (*launches)++;
+  for (int k = 0, blk = 0; k < n; k += NB, blk++) {  // the diagonal block of panel k is already factorised
     const int nb = (n - k < NB) ? (n - k) : NB;
     double *W = Winv + (size_t)blk * NB * NB;
-    launch_pdl(k_potrf_inv, dim3(1), dim3(PF_THREADS), st, S, ld, k, nb, W, not_spd);
-    (*launches)++;
-    const int below = rows_total - (k + nb);
-    if (below > 0) {
-      const int T = (below + TS - 1) / TS;
-      launch_pdl(k_panel_gemm, dim3(T), dim3(256), st, S, ld, k, nb, rows_total, (const double *)W);
-      launch_pdl(k_syrk_update, dim3(T * (T + 1) / 2), dim3(256), st, S, ld, k, nb, n);
-      (*launches) += 2;
-    }
+    const int T = (rows_total - (k + nb) + TS - 1) / TS;  // >= 1: row n
+    launch_pdl(k_panel_gemm, dim3(T), dim3(256), st, S, ld, k, nb, rows_total, (const double *)W);
+    launch_pdl(k_syrk_update, dim3(T * (T + 1) / 2), dim3(256), st, S, ld, k, nb, n, W + NB * NB, not_spd);
+    (*launches) += 2;
   }
   const int nblk = (n + NB - 1) / NB;
   for (int b = nblk - 1; b >= 0; b--) {
