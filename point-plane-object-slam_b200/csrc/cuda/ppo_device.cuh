@@ -81,7 +81,7 @@ struct DevGraph {
   double *Hll;     // n_lm x 6 (xx xy xz yy yz zz)
   double *bl;      // n_lm x 3
   double *Hpl;     // n_ent x 18 (6 x 3 row-major)
-  double *BD;      // n_ent x 18 : Hpl * Dinv of the current damped trial
+  double *BD;      // n_ent x 18 : Y = Hpl * C of the current damped trial, C C^T = (Hll + lambda)^-1
   double *Dinv;    // n_lm x 6
   double *xl;      // n_lm x 3
   double *S;       // (n_p + 1) x ld, row-major upper = column-major lower; last column = reduced rhs

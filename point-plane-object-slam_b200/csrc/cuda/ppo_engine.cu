@@ -3,6 +3,10 @@
 // (OptimizationAlgorithmLevenberg::solve, core/optimization_algorithm_levenberg.cpp:61-164) runs on
 // the host and reads back three scalars per damped trial; everything else stays on the device.
 #include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -18,6 +22,7 @@
 #include "ppo_kernels.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 using namespace ppo;
 
@@ -81,11 +86,10 @@ struct ppo_ba_handle {
   int n_chunks = 0;
   int *d_kf_chunk_ptr = nullptr;
   double *d_chunk_part = nullptr;
-  int *d_lm_small = nullptr, *d_lm_big = nullptr;
   unsigned *d_pair_keys = nullptr;            // sorted key-frame-pair keys of the Schur contributions
   unsigned long long *d_pair_vals = nullptr;  // (entry A << 32 | entry B)
-  int n_pairs = 0;
-  int n_lm_small = 0, n_lm_big = 0;
+  int n_pairs = 0;                            // upper bound (padding at the end of the sorted list)
+  int *d_dup = nullptr;                       // set by k_pair_count: a landmark observed twice by one key-frame
   // cuboid-plane edges (constant residual): host side
   std::vector<int> cpe_cuboid, cpe_plane;
   std::vector<double> cpe_chi2, cpe_norm;
@@ -131,6 +135,20 @@ struct ppo_ba_handle {
       if ((rc = pinned(&stage, v.size() * sizeof(T)))) return rc;
       std::memcpy(stage, v.data(), v.size() * sizeof(T));
       CK(cudaMemcpyAsync(*p, stage, v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    return PPO_OK;
+  }
+  // caller's array -> pinned staging -> device: one host pass, no intermediate std::vector
+  template <typename T>
+  int upload_raw(T **p, const T *src, size_t n) {
+    ppo_ba_handle *h = this;
+    int rc = dalloc(p, n);
+    if (rc) return rc;
+    if (n) {
+      void *stage = nullptr;
+      if ((rc = pinned(&stage, n * sizeof(T)))) return rc;
+      std::memcpy(stage, src, n * sizeof(T));
+      CK(cudaMemcpyAsync(*p, stage, n * sizeof(T), cudaMemcpyHostToDevice, st));
     }
     return PPO_OK;
   }
@@ -309,12 +327,20 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   h->hstage_off = 0;
   DevGraph &g = h->g;
   std::memset(&g, 0, sizeof g);
+  // PPO_BA_TIMING=1: host-side phase times of this call on stderr (diagnostics only)
+  static const bool timing = std::getenv("PPO_BA_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto tick = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ppo_ba_set_graph] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   if (gi->n_kf <= 0 || gi->n_pt < 0 || gi->n_pl < 0 || gi->n_cu < 0) { h->err = "bad vertex counts"; return PPO_E_INVALID; }
   g.n_kf = gi->n_kf; g.n_pt = gi->n_pt; g.n_pl = gi->n_pl; g.n_cu = gi->n_cu;
   g.n_pe = gi->n_pe; g.n_ple = gi->n_ple; g.n_cbe = gi->n_cbe; g.n_pce = gi->n_pce; g.n_cpe = gi->n_cpe;
   if (g.n_pt > 0 && (!gi->pt_rowptr || gi->pt_rowptr[0] != 0 || gi->pt_rowptr[g.n_pt] != g.n_pe)) { h->err = "pt_rowptr inconsistent with n_pe"; return PPO_E_INVALID; }
   if (g.n_pt == 0 && g.n_pe != 0) { h->err = "point edges without points"; return PPO_E_INVALID; }
-  for (int e = 0; e < g.n_pe; e++) if (gi->pe_kf[e] < 0 || gi->pe_kf[e] >= g.n_kf) { h->err = "pe_kf out of range"; return PPO_E_INVALID; }
   for (int p = 0; p < g.n_pt; p++) if (gi->pt_rowptr[p + 1] < gi->pt_rowptr[p]) { h->err = "pt_rowptr not monotone"; return PPO_E_INVALID; }
   for (int e = 0; e < g.n_ple; e++)
     if (gi->ple_kf[e] < 0 || gi->ple_kf[e] >= g.n_kf || gi->ple_plane[e] < 0 || gi->ple_plane[e] >= g.n_pl || gi->ple_kind[e] > 2) { h->err = "plane edge out of range"; return PPO_E_INVALID; }
@@ -326,6 +352,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
     if (gi->cpe_cuboid[e] < 0 || gi->cpe_cuboid[e] >= g.n_cu || gi->cpe_plane[e] < 0 || gi->cpe_plane[e] >= g.n_pl) { h->err = "cuboid-plane edge out of range"; return PPO_E_INVALID; }
 
   int rc;
+  tick("validate");
 #define UP(dst, vec) if ((rc = h->upload(&(dst), (vec)))) return rc
   // ---- vertices: constants ------------------------------------------------------------------------
   std::vector<uint8_t> kf_fixed(gi->kf_fixed, gi->kf_fixed + g.n_kf), pt_fixed(g.n_pt, 0), cu_flags(g.n_cu, 0);
@@ -358,41 +385,63 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
     for (int k = 0; k < 10; k++) cu[10 * (size_t)i + k] = gi->cu_state[10 * (size_t)i + k];
     norm_q(&cu[10 * (size_t)i + 3]);
   }
-  std::vector<double> pt(gi->pt_xyz, gi->pt_xyz + 3 * (size_t)g.n_pt);
   if ((rc = alloc_state(h, &h->sa)) || (rc = alloc_state(h, &h->sb)) || (rc = alloc_state(h, &h->s0))) return rc;
-  auto stage_up = [&](double *dst, const std::vector<double> &v) -> int {
-    if (v.empty()) return PPO_OK;
+  auto stage_up = [&](double *dst, const double *src, size_t n) -> int {
+    if (n == 0) return PPO_OK;
     void *stage = nullptr;
-    int r = h->pinned(&stage, v.size() * 8);
+    int r = h->pinned(&stage, n * 8);
     if (r) return r;
-    std::memcpy(stage, v.data(), v.size() * 8);
-    CK(cudaMemcpyAsync(dst, stage, v.size() * 8, cudaMemcpyHostToDevice, h->st));
+    std::memcpy(stage, src, n * 8);
+    CK(cudaMemcpyAsync(dst, stage, n * 8, cudaMemcpyHostToDevice, h->st));
     return PPO_OK;
   };
-  if ((rc = stage_up(h->s0.kf_pose, kf_pose)) || (rc = stage_up(h->s0.pt, pt)) || (rc = stage_up(h->s0.pl, pl)) || (rc = stage_up(h->s0.cu, cu))) return rc;
+  if ((rc = stage_up(h->s0.kf_pose, kf_pose.data(), kf_pose.size())) || (rc = stage_up(h->s0.pt, gi->pt_xyz, 3 * (size_t)g.n_pt)) ||
+      (rc = stage_up(h->s0.pl, pl.data(), pl.size())) || (rc = stage_up(h->s0.cu, cu.data(), cu.size())))
+    return rc;
   k_pose_cache<<<cdiv(g.n_kf, 128), 128, 0, h->st>>>(g.n_kf, h->s0.kf_pose, h->s0.kf_Rt);
   h->launches++;
   if ((rc = copy_state(h, h->sa, h->s0))) return rc;
   if ((rc = copy_state(h, h->sb, h->s0))) return rc;
 
+  tick("vertices");
   // ---- point edges --------------------------------------------------------------------------------
-  std::vector<PointEdgeRec> rec(g.n_pe);
-  std::vector<int> pe_pt(g.n_pe);
-  std::vector<int> rowptr(g.n_pt + 1, 0);
-  for (int p = 0; p < g.n_pt; p++) {
-    rowptr[p + 1] = gi->pt_rowptr[p + 1];
-    for (int e = gi->pt_rowptr[p]; e < gi->pt_rowptr[p + 1]; e++) {
-      pe_pt[e] = p;
-      rec[e].kf = gi->pe_kf[e];
-      rec[e].u = gi->pe_obs[3 * (size_t)e];
-      rec[e].v = gi->pe_obs[3 * (size_t)e + 1];
-      rec[e].ur = gi->pe_obs[3 * (size_t)e + 2];
+  // The caller's arrays go to the device as they are (one memcpy into pinned staging each); the packed edge
+  // records, the edge -> point map and the per-key-frame edge lists are built there.  The host only makes one
+  // pass over the key-frame ids (range check + histogram, which sizes the per-key-frame chunk lists).
+  std::vector<int> kf_cnt(g.n_kf + 1, 0);
+  for (int e = 0; e < g.n_pe; e++) {
+    const unsigned kf = (unsigned)gi->pe_kf[e];
+    if (kf >= (unsigned)g.n_kf) { h->err = "pe_kf out of range"; return PPO_E_INVALID; }
+    kf_cnt[kf + 1]++;
+  }
+  const int *rowptr = gi->pt_rowptr;
+  {
+    int *d_rowptr = nullptr, *d_pe_kf = nullptr, *d_pe_pt = nullptr, *d_iota = nullptr, *d_kfe = nullptr;
+    unsigned *d_kf_sorted = nullptr;
+    float *d_obs = nullptr, *d_is2 = nullptr;
+    PointEdgeRec *d_rec = nullptr;
+    const int one_zero[1] = {0};
+    if ((rc = h->upload_raw(&d_rowptr, g.n_pt ? rowptr : one_zero, (size_t)g.n_pt + 1)) || (rc = h->upload_raw(&d_pe_kf, gi->pe_kf, (size_t)g.n_pe)) ||
+        (rc = h->upload_raw(&d_obs, gi->pe_obs, 3 * (size_t)g.n_pe)) || (rc = h->upload_raw(&d_is2, gi->pe_invsigma2, (size_t)g.n_pe)) ||
+        (rc = h->dalloc(&d_pe_pt, (size_t)g.n_pe)) || (rc = h->dalloc(&d_rec, (size_t)g.n_pe)) || (rc = h->dalloc(&d_iota, (size_t)g.n_pe)) ||
+        (rc = h->dalloc(&d_kfe, (size_t)g.n_pe)) || (rc = h->dalloc(&d_kf_sorted, (size_t)g.n_pe)))
+      return rc;
+    g.pt_rowptr = d_rowptr; g.pe_pt = d_pe_pt; g.pe_rec = d_rec; g.pe_is2 = d_is2; g.kfe_edge = d_kfe;
+    if (g.n_pe) {
+      k_pack_point_edges<<<cdiv(g.n_pe, 256), 256, 0, h->st>>>(g.n_pe, d_pe_kf, d_obs, d_rec, d_iota);
+      k_fill_pe_pt<<<cdiv(g.n_pt, 256), 256, 0, h->st>>>(g.n_pt, d_rowptr, d_pe_pt);
+      // edges grouped by key-frame: stable radix sort of the edge ids by key-frame id (same order as a counting sort)
+      int bits = 1;
+      while ((1 << bits) < g.n_kf) bits++;
+      size_t tmp_bytes = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned *)d_pe_kf, d_kf_sorted, (const int *)d_iota, d_kfe, g.n_pe, 0, bits, h->st));
+      char *tmp = nullptr;
+      if ((rc = h->dalloc(&tmp, tmp_bytes))) return rc;
+      CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const unsigned *)d_pe_kf, d_kf_sorted, (const int *)d_iota, d_kfe, g.n_pe, 0, bits, h->st));
+      h->launches += 4;
     }
   }
-  std::vector<float> is2(gi->pe_invsigma2, gi->pe_invsigma2 + g.n_pe);
-  { int *p; UP(p, rowptr); g.pt_rowptr = p; UP(p, pe_pt); g.pe_pt = p; }
-  { PointEdgeRec *p; UP(p, rec); g.pe_rec = p; }
-  { float *p; UP(p, is2); g.pe_is2 = p; }
+  tick("point edge uploads");
   // work units: consecutive points, <= 32 edges per warp (a point with > 32 edges is its own unit)
   std::vector<int> unit_pt0;
   unit_pt0.push_back(0);
@@ -412,17 +461,12 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   { int *p; UP(p, unit_pt0); g.unit_pt0 = p; }
   {
     std::vector<int> unit_e0(unit_pt0.size());
-    for (size_t u = 0; u < unit_pt0.size(); u++) unit_e0[u] = rowptr[unit_pt0[u]];
+    for (size_t u = 0; u < unit_pt0.size(); u++) unit_e0[u] = g.n_pt ? rowptr[unit_pt0[u]] : 0;
     int *p; UP(p, unit_e0); g.unit_e0 = p;
   }
-  // edges grouped by key-frame, chunks of <= POSE_THREADS
-  std::vector<int> kf_cnt(g.n_kf + 1, 0), kfe(g.n_pe);
-  for (int e = 0; e < g.n_pe; e++) kf_cnt[rec[e].kf + 1]++;
+  tick("work units");
+  // per-key-frame chunks of <= POSE_THREADS edges of the sorted list
   for (int i = 0; i < g.n_kf; i++) kf_cnt[i + 1] += kf_cnt[i];
-  {
-    std::vector<int> pos(kf_cnt.begin(), kf_cnt.end() - 1);
-    for (int e = 0; e < g.n_pe; e++) kfe[pos[rec[e].kf]++] = e;
-  }
   std::vector<int> chunk_kf, chunk_b, chunk_e, kf_chunk_ptr(g.n_kf + 1, 0);
   for (int i = 0; i < g.n_kf; i++) {
     kf_chunk_ptr[i] = (int)chunk_kf.size();
@@ -435,15 +479,16 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   }
   kf_chunk_ptr[g.n_kf] = (int)chunk_kf.size();
   g.n_chunks = h->n_chunks = (int)chunk_kf.size();
-  { int *p; UP(p, chunk_kf); g.chunk_kf = p; UP(p, chunk_b); g.chunk_begin = p; UP(p, chunk_e); g.chunk_end = p; UP(p, kfe); g.kfe_edge = p; }
+  { int *p; UP(p, chunk_kf); g.chunk_kf = p; UP(p, chunk_b); g.chunk_begin = p; UP(p, chunk_e); g.chunk_end = p; }
   UP(h->d_kf_chunk_ptr, kf_chunk_ptr);
   if ((rc = h->dalloc(&h->d_chunk_part, 27 * (size_t)g.n_chunks))) return rc;
 
+  tick("edges by key-frame");
   // ---- plane edges: slots = unique (plane, key-frame) pairs, sorted by (plane, kf) ---------------------
-  std::vector<std::pair<int, int>> pairs(g.n_ple);
-  for (int e = 0; e < g.n_ple; e++) pairs[e] = {gi->ple_plane[e], gi->ple_kf[e]};
-  std::vector<std::pair<int, int>> uniq = pairs;
-  std::sort(uniq.begin(), uniq.end());
+  std::vector<long long> pairs(g.n_ple);  // plane * n_kf + key-frame
+  for (int e = 0; e < g.n_ple; e++) pairs[e] = (long long)gi->ple_plane[e] * g.n_kf + gi->ple_kf[e];
+  std::vector<long long> uniq = pairs;
+  if (!std::is_sorted(uniq.begin(), uniq.end())) std::sort(uniq.begin(), uniq.end());
   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
   g.n_slots = (int)uniq.size();
   g.n_ent = g.n_slots + g.n_pe;
@@ -451,17 +496,11 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   std::vector<int> ple_slot(g.n_ple), slot_kf(g.n_slots), lm_rowptr(g.n_lm + 1, 0);
   for (int e = 0; e < g.n_ple; e++) ple_slot[e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), pairs[e]) - uniq.begin());
   for (int s = 0; s < g.n_slots; s++) {
-    slot_kf[s] = uniq[s].second;
-    lm_rowptr[uniq[s].first + 1]++;
+    slot_kf[s] = (int)(uniq[s] % g.n_kf);
+    lm_rowptr[uniq[s] / g.n_kf + 1]++;
   }
   for (int p = 0; p < g.n_pl; p++) lm_rowptr[p + 1] += lm_rowptr[p];
   for (int p = 0; p < g.n_pt; p++) lm_rowptr[g.n_pl + p + 1] = g.n_slots + rowptr[p + 1];
-  std::vector<int> lm_small, lm_big;
-  for (int L = 0; L < g.n_lm; L++) (lm_rowptr[L + 1] - lm_rowptr[L] > SCHUR_SMALL_MAX ? lm_big : lm_small).push_back(L);
-  h->n_lm_small = (int)lm_small.size();
-  h->n_lm_big = (int)lm_big.size();
-  UP(h->d_lm_small, lm_small);
-  UP(h->d_lm_big, lm_big);
   {
     int *p;
     std::vector<int> v(gi->ple_plane, gi->ple_plane + g.n_ple); UP(p, v); g.ple_plane = p;
@@ -484,49 +523,45 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
     UP(d, meas); g.ple_meas = d;
     std::vector<double> info(gi->ple_info, gi->ple_info + 3 * (size_t)g.n_ple); UP(d, info); g.ple_info = d;
   }
+  tick("plane edges");
   // ---- Schur contribution list: one record per pair of free-key-frame blocks of a landmark, sorted by key-frame pair ----
   {
     if ((unsigned long long)g.n_kf * (unsigned long long)g.n_kf >= 0xffffffffull) { h->err = "too many key-frames for 32-bit pair keys"; return PPO_E_INVALID; }
-    std::vector<int> pair_off(g.n_lm + 1, 0);
+    // Upper bound of the list length from the block counts alone; pairs that involve a FIXED key-frame are not
+    // emitted, their slots stay as end-of-list padding (key 0xffffffff sorts last, k_schur_pairs skips it).
     long long total = 0;
-    std::vector<int> stamp(g.n_kf, -1);  // last landmark that touched a key-frame slot: O(1) duplicate test
     for (int L = 0; L < g.n_lm; L++) {
-      long long kfree = 0;
-      for (int en = lm_rowptr[L]; en < lm_rowptr[L + 1]; en++) {
-        const int sl = en < g.n_slots ? slot_kf[en] : rec[en - g.n_slots].kf;
-        if (stamp[sl] == L) {  // MapPoint::mObservations is a map keyed by KeyFrame*: one observation per key-frame
-          h->err = "a landmark is observed twice by the same key-frame";
-          return PPO_E_INVALID;
-        }
-        stamp[sl] = L;
-        kfree += !kf_fixed[sl];
-      }
-      pair_off[L] = (int)total;
-      total += kfree * (kfree + 1) / 2;
+      const long long k = lm_rowptr[L + 1] - lm_rowptr[L];
+      total += k * (k + 1) / 2;
       if (total > 0x7fffffffll) { h->err = "Schur contribution list exceeds 2^31 entries"; return PPO_E_INVALID; }
     }
-    pair_off[g.n_lm] = (int)total;
     h->n_pairs = (int)total;
-    int *d_off = nullptr;
-    UP(d_off, pair_off);
+    int *d_cnt = nullptr, *d_off = nullptr;
     unsigned *k_in = nullptr;
     unsigned long long *v_in = nullptr;
-    if ((rc = h->dalloc(&k_in, (size_t)total)) || (rc = h->dalloc(&v_in, (size_t)total)) || (rc = h->dalloc(&h->d_pair_keys, (size_t)total)) ||
+    if ((rc = h->dalloc(&d_cnt, (size_t)g.n_lm + 1)) || (rc = h->dalloc(&d_off, (size_t)g.n_lm + 1)) || (rc = h->dalloc(&h->d_dup, 1)) ||
+        (rc = h->dalloc(&k_in, (size_t)total)) || (rc = h->dalloc(&v_in, (size_t)total)) || (rc = h->dalloc(&h->d_pair_keys, (size_t)total)) ||
         (rc = h->dalloc(&h->d_pair_vals, (size_t)total)))
       return rc;
+    CK(cudaMemsetAsync(h->d_dup, 0, sizeof(int), h->st));
     if (total > 0) {
-      k_gen_pairs<<<cdiv(g.n_lm, 4), 128, 0, h->st>>>(g, d_off, k_in, v_in);
-      h->launches++;
+      CK(cudaMemsetAsync(k_in, 0xff, 4 * (size_t)total, h->st));
+      CK(cudaMemsetAsync(d_cnt, 0, 4 * ((size_t)g.n_lm + 1), h->st));
+      k_pair_count<<<cdiv(g.n_lm, 128), 128, 0, h->st>>>(g, d_cnt, h->d_dup);
+      size_t scan_bytes = 0, sort_bytes = 0;
       int bits = 1;
-      while (bits < 32 && (1ull << bits) < (unsigned long long)g.n_kf * (unsigned long long)g.n_kf) bits++;
-      size_t tmp_bytes = 0;
-      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, h->d_pair_keys, v_in, h->d_pair_vals, (int)total, 0, bits, h->st));
+      while (bits < 32 && (1ull << bits) <= (unsigned long long)g.n_kf * (unsigned long long)g.n_kf) bits++;  // padding > every key
+      CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_cnt, d_off, g.n_lm + 1, h->st));
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k_in, h->d_pair_keys, v_in, h->d_pair_vals, (int)total, 0, bits, h->st));
       char *tmp = nullptr;
-      if ((rc = h->dalloc(&tmp, tmp_bytes))) return rc;
-      CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, h->d_pair_keys, v_in, h->d_pair_vals, (int)total, 0, bits, h->st));
-      h->launches += 4;
+      if ((rc = h->dalloc(&tmp, std::max(scan_bytes, sort_bytes)))) return rc;
+      CK(cub::DeviceScan::ExclusiveSum(tmp, scan_bytes, d_cnt, d_off, g.n_lm + 1, h->st));
+      k_gen_pairs<<<cdiv(g.n_lm, 4), 128, 0, h->st>>>(g, d_off, k_in, v_in);
+      CK(cub::DeviceRadixSort::SortPairs(tmp, sort_bytes, k_in, h->d_pair_keys, v_in, h->d_pair_vals, (int)total, 0, bits, h->st));
+      h->launches += 7;
     }
   }
+  tick("Schur pair list");
   // ---- camera-cuboid / point-cuboid / cuboid-plane edges ---------------------------------------------
   {
     int *p; uint8_t *q; double *d;
@@ -552,6 +587,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   UP(h->d_cpe_plane, h->cpe_plane);
   UP(h->d_cpe_flags, h->cpe_flags);
 
+  tick("cuboid edges");
   // ---- flags, per-edge outputs, scratch -----------------------------------------------------------------
 #define DA(ptr, n) if ((rc = h->dalloc(&(ptr), (n)))) return rc
   DA(g.pe_flags, (size_t)g.n_pe); DA(g.ple_flags, (size_t)g.n_ple); DA(g.cbe_flags, (size_t)g.n_cbe); DA(g.pce_flags, (size_t)g.n_pce);
@@ -588,8 +624,18 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   g.huber_mono = h->P.huber_mono; g.huber_stereo = h->P.huber_stereo; g.huber_plane = h->P.huber_plane; g.huber_vp = h->P.huber_vp_plane;
   g.huber_bbox = h->P.huber_bbox; g.huber_corner = h->P.huber_corner;
   g.ptcu_ratio = h->P.ptcu_max_outside_margin_ratio; g.ptcu_prior = h->P.ptcu_prior_weight;
+  tick("scratch alloc + memsets");
   CK(cudaStreamSynchronize(h->st));  // host vectors go out of scope
+  tick("drain stream");
   CK(cudaGetLastError());
+  {
+    int dup = 0;
+    CK(cudaMemcpy(&dup, h->d_dup, sizeof(int), cudaMemcpyDeviceToHost));
+    if (dup) {  // MapPoint::mObservations is a map keyed by KeyFrame*: one observation per key-frame
+      h->err = "a landmark is observed twice by the same key-frame";
+      return PPO_E_INVALID;
+    }
+  }
   h->have_graph = true;
   h->lambda = -1;
   return PPO_OK;

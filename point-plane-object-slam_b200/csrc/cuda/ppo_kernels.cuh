@@ -684,7 +684,6 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_ptcu_edges(DevGraph g, DevSta
 // ---------------------------------------------------------------------------------------------
 // Schur complement (BlockSolver::solve, core/block_solver.hpp:376-431) with lambda on the diagonal of
 // Hll as setLambda adds it (:582-587).  S is zero on entry; k_compose adds Hpp afterwards.
-// Work unit = (landmark, first-block stride): small landmarks take one warp, big ones a whole CTA.
 // ---------------------------------------------------------------------------------------------
 PPO_D void inv_sym3(const double h[6], double lam, double d[6]) {
   const double a = h[0] + lam, b = h[1], c = h[2], e = h[3] + lam, f = h[4], i = h[5] + lam;
@@ -701,108 +700,45 @@ PPO_D void inv_sym3(const double h[6], double lam, double d[6]) {
 PPO_D bool landmark_active(const DevGraph &g, int L) {
   return L < g.n_pl ? g.pl_act[L] != 0 : (g.pt_act[L - g.n_pl] != 0 && !g.pt_fixed[L - g.n_pl]);
 }
-constexpr int SCHUR_WARPS = 8;
-constexpr int SCHUR_SMALL_MAX = 24;  // landmarks with more blocks than this take a whole CTA
-// lm_list: landmarks handled by this launch; WHOLE_CTA: one landmark per CTA instead of per warp.
-// Small landmarks stage their (contiguous) 6x3 blocks in shared memory once; the pair loop then walks the
-// (i2, entry) items with a carried counter (no divisions) and issues one RED.F64 per scalar of the 6x6 product.
-template <bool WHOLE_CTA>
-__global__ void __launch_bounds__(SCHUR_WARPS * 32) k_schur(DevGraph g, const int *lm_list, int n_list, double lambda, int n_p, int ld, int planes_write_S) {
-  __shared__ double bd[SCHUR_WARPS][18];
-  __shared__ double blk[WHOLE_CTA ? 1 : SCHUR_WARPS][WHOLE_CTA ? 1 : SCHUR_SMALL_MAX * 18];
-  __shared__ int pid[WHOLE_CTA ? 1 : SCHUR_WARPS][WHOLE_CTA ? 1 : SCHUR_SMALL_MAX];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int li = WHOLE_CTA ? blockIdx.x : blockIdx.x * SCHUR_WARPS + warp;
-  if (li >= n_list) return;
-  const int L = lm_list ? lm_list[li] : li;
-  if (!landmark_active(g, L)) return;
-  double h[6], D[6], bl[3], db[3];
-#pragma unroll
-  for (int i = 0; i < 6; i++) h[i] = g.Hll[6 * (size_t)L + i];
-#pragma unroll
-  for (int i = 0; i < 3; i++) bl[i] = g.bl[3 * (size_t)L + i];
-  inv_sym3(h, lambda, D);
-  db[0] = D[0] * bl[0] + D[1] * bl[1] + D[2] * bl[2];
-  db[1] = D[1] * bl[0] + D[3] * bl[1] + D[4] * bl[2];
-  db[2] = D[2] * bl[0] + D[4] * bl[1] + D[5] * bl[2];
-  if (lane == 0 && (!WHOLE_CTA || warp == 0)) {
-#pragma unroll
-    for (int i = 0; i < 6; i++) g.Dinv[6 * (size_t)L + i] = D[i];
-  }
-  if (L < g.n_pl && !planes_write_S) return;  // sharded window: plane landmarks are reduced by rank 0 only (Dinv is stored above)
-  const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
-  const double *Wg = g.Hpl + 18 * (size_t)b0;
-  if (!WHOLE_CTA) {
-    const int n = (b1 - b0) * 18;
-    for (int t = lane; t < n; t += 32) blk[warp][t] = Wg[t];
-    for (int t = lane; t < b1 - b0; t += 32) pid[warp][t] = g.ent_pidx[b0 + t];
-    __syncwarp();
-  }
-  const int step = WHOLE_CTA ? SCHUR_WARPS : 1;
-  const int nblk = b1 - b0;
-  for (int i1 = (WHOLE_CTA ? warp : 0); i1 < nblk; i1 += step) {
-    const int p1 = WHOLE_CTA ? g.ent_pidx[b0 + i1] : pid[warp][i1];
-    if (p1 < 0) continue;  // warp-uniform
-    const double *W1 = WHOLE_CTA ? Wg + 18 * (size_t)i1 : &blk[warp][18 * i1];
-    // BD = W1 * Dinv (6 x 3), one lane per entry
-    __syncwarp();
-    if (lane < 18) {
-      const int r = lane / 3, c = lane % 3;
-      const double dc0 = c == 0 ? D[0] : (c == 1 ? D[1] : D[2]);
-      const double dc1 = c == 0 ? D[1] : (c == 1 ? D[3] : D[4]);
-      const double dc2 = c == 0 ? D[2] : (c == 1 ? D[4] : D[5]);
-      bd[warp][lane] = W1[3 * r] * dc0 + W1[3 * r + 1] * dc1 + W1[3 * r + 2] * dc2;
-    }
-    __syncwarp();
-    double *Srow = g.S + (size_t)(6 * p1) * ld;
-    if (lane < 6)  // reduced gradient: bschur_i -= W1 * Dinv * bl   (coefficients, :403-405)
-      atomicAdd(&Srow[(size_t)lane * ld + n_p], -(W1[3 * lane] * db[0] + W1[3 * lane + 1] * db[1] + W1[3 * lane + 2] * db[2]));
-    // 6x6 products for all i2 >= i1.  Entry (r,c) of a pair is fixed per lane: pass A covers entries 0..31 of one pair
-    // (lane = 6 r + c), pass B the remaining entries 32..35 (r = 5, c = 2..5) of EIGHT pairs at once (4 lanes per pair):
-    // no per-item index arithmetic, bd rows live in registers, one RED.F64 per scalar.
-    const int rA = lane / 6, cA = lane - 6 * rA, cB = 2 + (lane & 3), tB = lane >> 2;
-    const double bA0 = bd[warp][3 * rA], bA1 = bd[warp][3 * rA + 1], bA2 = bd[warp][3 * rA + 2];
-    const double bB0 = bd[warp][15], bB1 = bd[warp][16], bB2 = bd[warp][17];
-    double *SA = Srow + (size_t)rA * ld + cA, *SB = Srow + (size_t)5 * ld + cB;
-    for (int i2 = i1; i2 < nblk; i2 += 8) {
-      const int tmax = min(8, nblk - i2);
-      for (int t = 0; t < tmax; t++) {
-        const int j2 = i2 + t;
-        const int p2 = WHOLE_CTA ? g.ent_pidx[b0 + j2] : pid[warp][j2];
-        if (p2 < 0) continue;  // warp-uniform
-        const double *W2 = (WHOLE_CTA ? Wg + 18 * (size_t)j2 : &blk[warp][18 * j2]) + 3 * cA;
-        const double v = bA0 * W2[0] + bA1 * W2[1] + bA2 * W2[2];
-        if (p1 < p2 || j2 == i1) atomicAdd(SA + 6 * p2, -v);
-        else if (p1 > p2) atomicAdd(&g.S[(size_t)(6 * p2 + cA) * ld + 6 * p1 + rA], -v);  // keep the upper block triangle
-        else {  // two different entries on one key-frame: W1 D W2^T + W2 D W1^T on the diagonal block
-          atomicAdd(SA + 6 * p1, -v);
-          atomicAdd(&g.S[(size_t)(6 * p1 + cA) * ld + 6 * p1 + rA], -v);
-        }
-      }
-      if (tB < tmax) {
-        const int j2 = i2 + tB;
-        const int p2 = WHOLE_CTA ? g.ent_pidx[b0 + j2] : pid[warp][j2];
-        if (p2 >= 0) {
-          const double *W2 = (WHOLE_CTA ? Wg + 18 * (size_t)j2 : &blk[warp][18 * j2]) + 3 * cB;
-          const double v = bB0 * W2[0] + bB1 * W2[1] + bB2 * W2[2];
-          if (p1 < p2 || j2 == i1) atomicAdd(SB + 6 * p2, -v);
-          else if (p1 > p2) atomicAdd(&g.S[(size_t)(6 * p2 + cB) * ld + 6 * p1 + 5], -v);
-          else {
-            atomicAdd(SB + 6 * p1, -v);
-            atomicAdd(&g.S[(size_t)(6 * p1 + cB) * ld + 6 * p1 + 5], -v);
-          }
-        }
-      }
-    }
-  }
-}
 // ---------------------------------------------------------------------------------------------
 // Pair-major Schur complement (no per-scalar atomics).  At set_graph every landmark emits one contribution per
 // pair of its (free key-frame) blocks, keyed by the key-frame pair; the list is radix-sorted by key once.  Per
-// damped trial  k_schur_bd  forms Dinv and the 6x3 products W Dinv of every block, and  k_schur_pairs  streams the
+// damped trial  k_schur_bd  forms Dinv = C C^T and the 6x3 products Y = W C of every block, and  k_schur_pairs  streams the
 // sorted list: a warp owns 64 consecutive contributions, lane (r,c) accumulates entry (r,c) of the current
 // key-frame pair in a register and flushes 36 REDs only when the key changes.
 // ---------------------------------------------------------------------------------------------
+// set_graph: packed point-edge records / edge ids (payload of the by-key-frame sort) and the edge -> point map
+__global__ void k_pack_point_edges(int n_pe, const int *__restrict__ pe_kf, const float *__restrict__ obs, PointEdgeRec *rec, int *iota) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pe) return;
+  PointEdgeRec r;
+  r.kf = pe_kf[e];
+  r.u = obs[3 * (size_t)e];
+  r.v = obs[3 * (size_t)e + 1];
+  r.ur = obs[3 * (size_t)e + 2];
+  rec[e] = r;
+  iota[e] = e;
+}
+__global__ void k_fill_pe_pt(int n_pt, const int *__restrict__ rowptr, int *pe_pt) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pt) return;
+  for (int e = rowptr[p]; e < rowptr[p + 1]; e++) pe_pt[e] = p;
+}
+// contributions of landmark L: pairs (i1 <= i2) of its free-key-frame blocks; also the one-observation-per-key-frame check
+__global__ void k_pair_count(DevGraph g, int *cnt, int *dup) {
+  const int L = blockIdx.x * blockDim.x + threadIdx.x;
+  if (L >= g.n_lm) return;
+  const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
+  int kfree = 0;
+  bool twice = false;
+  for (int i = b0; i < b1; i++) {
+    const int s = i < g.n_slots ? g.slot_kf[i] : g.pe_rec[i - g.n_slots].kf;
+    kfree += !g.kf_fixed[s];
+    for (int j = b0; j < i; j++) twice |= (j < g.n_slots ? g.slot_kf[j] : g.pe_rec[j - g.n_slots].kf) == s;
+  }
+  cnt[L] = kfree * (kfree + 1) / 2;
+  if (twice) *dup = 1;
+}
 __global__ void k_gen_pairs(DevGraph g, const int *lm_pair_off, unsigned *keys, unsigned long long *vals) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= g.n_lm) return;
@@ -855,18 +791,25 @@ __global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double l
   db[2] = D[2] * bl[0] + D[4] * bl[1] + D[5] * bl[2];
   if (lane < 6) g.Dinv[6 * (size_t)L + lane] = D[lane];
   const bool to_S = L >= g.n_pl || planes_write_S;  // sharded window: planes are reduced by rank 0 only
+  // Dinv = (Hll + lambda)^-1 = C C^T with C = chol(Hll + lambda)^-T: the Schur product W Dinv W'^T of two blocks of this
+  // landmark is then Y Y'^T with Y = W C, so k_schur_pairs gathers from ONE array (half the working set: L2 resident).
+  const double l00 = sqrt(h[0] + lambda), i00 = 1.0 / l00;
+  const double l10 = h[1] * i00, l20 = h[2] * i00;
+  const double l11 = sqrt(fmax(h[3] + lambda - l10 * l10, 1e-300)), i11 = 1.0 / l11;
+  const double l21 = (h[4] - l20 * l10) * i11;
+  const double i22 = rsqrt(fmax(h[5] + lambda - l20 * l20 - l21 * l21, 1e-300));
   const int b0 = g.lm_rowptr[L], b1 = g.lm_rowptr[L + 1];
   const double *W = g.Hpl + 18 * (size_t)b0;
-  double *BD = g.BD + 18 * (size_t)b0;
-  const int n = (b1 - b0) * 18;
-  for (int it = lane; it < n; it += 32) {
-    const int e = it / 18, q = it - 18 * e, r = q / 3, c = q - 3 * r;
-    const double w0 = W[18 * e + 3 * r], w1 = W[18 * e + 3 * r + 1], w2 = W[18 * e + 3 * r + 2];
-    const double dc0 = c == 0 ? D[0] : (c == 1 ? D[1] : D[2]);
-    const double dc1 = c == 0 ? D[1] : (c == 1 ? D[3] : D[4]);
-    const double dc2 = c == 0 ? D[2] : (c == 1 ? D[4] : D[5]);
-    BD[it] = to_S ? w0 * dc0 + w1 * dc1 + w2 * dc2 : 0.0;
-    if (c == 0 && to_S) {  // reduced gradient: bschur_i -= W Dinv bl   (coefficients, core/block_solver.hpp:403-405)
+  double *Y = g.BD + 18 * (size_t)b0;
+  const int n = (b1 - b0) * 6;
+  for (int it = lane; it < n; it += 32) {  // one row (e, r) of a 6 x 3 block per lane
+    const int e = it / 6, r = it - 6 * e;
+    const double w0 = W[3 * it], w1 = W[3 * it + 1], w2 = W[3 * it + 2];
+    const double y0 = w0 * i00, y1 = (w1 - y0 * l10) * i11, y2 = (w2 - y0 * l20 - y1 * l21) * i22;  // y C^-1 = w
+    Y[3 * it] = to_S ? y0 : 0.0;
+    Y[3 * it + 1] = to_S ? y1 : 0.0;
+    Y[3 * it + 2] = to_S ? y2 : 0.0;
+    if (to_S) {  // reduced gradient: bschur_i -= W Dinv bl   (coefficients, core/block_solver.hpp:403-405)
       const int p = g.ent_pidx[b0 + e];
       if (p >= 0) atomicAdd(&g.S[(size_t)(6 * p + r) * ld + n_p], -(w0 * db[0] + w1 * db[1] + w2 * db[2]));
     }
@@ -887,7 +830,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
 #pragma unroll
   for (int q = 0; q < 2; q++) {
     const int c = 32 * q + lane;
-    kl[q] = c < cnt ? keys[c0 + c] : 0xffffffffu;
+    kl[q] = c < cnt ? keys[c0 + c] : 0xffffffffu;  // (the list ends with 0xffffffff padding)
     vl[q] = c < cnt ? vals[c0 + c] : 0ull;
   }
   const int r0 = lane / 6, q0 = lane - 6 * r0;  // entry owned by this lane: (r0, q0); lanes 0..3 also own (5, 2 + lane)
@@ -916,7 +859,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
         const unsigned long long v = __shfl_sync(FULL, vl[q], cb + u);
         const bool ok = key[u] != 0xffffffffu;
         const double *B = g.BD + 18 * (size_t)(unsigned)(v >> 32);
-        const double *W = g.Hpl + 18 * (size_t)(unsigned)(v & 0xffffffffu);
+        const double *W = g.BD + 18 * (size_t)(unsigned)(v & 0xffffffffu);
         d0[u] = ok ? B[offB0] * W[offW0] + B[offB0 + 1] * W[offW0 + 1] + B[offB0 + 2] * W[offW0 + 2] : 0.0;
         d1[u] = (ok && extra) ? B[15] * W[offW1] + B[16] * W[offW1 + 1] + B[17] * W[offW1 + 2] : 0.0;
       }
