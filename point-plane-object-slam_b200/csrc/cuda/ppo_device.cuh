@@ -82,6 +82,7 @@ struct DevGraph {
   double *bl;      // n_lm x 3
   double *Hpl;     // n_ent x 18 (6 x 3 row-major)
   double *BD;      // n_ent x 18 : Y = Hpl * C of the current damped trial, C C^T = (Hll + lambda)^-1
+  double *Zent;    // n_ent x 3  : z = C^T bl of the entry's landmark (reduced-gradient operand of k_schur_pairs)
   double *Dinv;    // n_lm x 6
   double *xl;      // n_lm x 3
   double *S;       // (n_p + 1) x ld, row-major upper = column-major lower; last column = reduced rhs

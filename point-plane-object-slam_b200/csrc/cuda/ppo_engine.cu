@@ -600,7 +600,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   h->max_np = 6 * n_free + 9 * g.n_cu;
   h->ld = h->max_np + 1;
   DA(g.Hpp_kf, 36 * (size_t)g.n_kf); DA(g.Hpp_cu, 81 * (size_t)g.n_cu); DA(g.Hpc, 54 * (size_t)g.n_cbe); DA(g.bp, (size_t)h->max_np);
-  DA(g.Hll, 6 * (size_t)g.n_lm); DA(g.bl, 3 * (size_t)g.n_lm); DA(g.Hpl, 18 * (size_t)g.n_ent); DA(g.BD, 18 * (size_t)g.n_ent); DA(g.Dinv, 6 * (size_t)g.n_lm);
+  DA(g.Hll, 6 * (size_t)g.n_lm); DA(g.bl, 3 * (size_t)g.n_lm); DA(g.Hpl, 18 * (size_t)g.n_ent); DA(g.BD, 18 * (size_t)g.n_ent); DA(g.Zent, 3 * (size_t)g.n_ent); DA(g.Dinv, 6 * (size_t)g.n_lm);
   DA(g.xl, 3 * (size_t)g.n_lm); DA(g.S, (size_t)(h->max_np + 1) * h->ld); DA(g.xp, (size_t)h->max_np);
   h->nb_lin = cdiv(g.n_units, LIN_WARPS); h->nb_res = cdiv(g.n_pe, RES_THREADS);
   h->nb_pl = cdiv(g.n_ple, SMALL_THREADS); h->nb_cb = cdiv(g.n_cbe, SMALL_THREADS); h->nb_pc = cdiv(g.n_pce, SMALL_THREADS);
@@ -616,6 +616,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   CK(cudaMemsetAsync(g.pce_chi2, 0, 8 * (size_t)g.n_pce, h->st));
   CK(cudaMemsetAsync(g.Hpl, 0, 8 * 18 * (size_t)g.n_ent, h->st));
   CK(cudaMemsetAsync(g.BD, 0, 8 * 18 * (size_t)g.n_ent, h->st));
+  CK(cudaMemsetAsync(g.Zent, 0, 8 * 3 * (size_t)g.n_ent, h->st));
   CK(cudaMemsetAsync(g.xl, 0, 8 * 3 * (size_t)g.n_lm, h->st));
   CK(cudaMemsetAsync(g.pe_flags, PPO_EF_ROBUST, (size_t)g.n_pe, h->st));
   CK(cudaMemsetAsync(g.ple_flags, PPO_EF_ROBUST, (size_t)g.n_ple, h->st));
@@ -816,7 +817,7 @@ static int schur_system(ppo_ba_handle *h, double lambda) {
   if (g.n_lm) { k_schur_bd<<<cdiv(g.n_lm, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, lambda, n_p, ld, own); h->launches++; }
   if (h->n_pairs) {
     const int n_warps = cdiv(h->n_pairs, PAIR_CHUNK);
-    k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld);
+    k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld, n_p);
     h->launches++;
   }
   const int n_comp = g.n_kf * 36 + g.n_cu * 81 + g.n_cbe * 54 + n_p;

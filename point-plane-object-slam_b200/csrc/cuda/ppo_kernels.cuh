@@ -780,15 +780,12 @@ __global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double l
     for (int it = a0 + lane; it < a1; it += 32) g.BD[it] = 0.0;
     return;
   }
-  double h[6], D[6], bl[3], db[3];
+  double h[6], D[6], bl[3];
 #pragma unroll
   for (int i = 0; i < 6; i++) h[i] = g.Hll[6 * (size_t)L + i];
 #pragma unroll
   for (int i = 0; i < 3; i++) bl[i] = g.bl[3 * (size_t)L + i];
   inv_sym3(h, lambda, D);
-  db[0] = D[0] * bl[0] + D[1] * bl[1] + D[2] * bl[2];
-  db[1] = D[1] * bl[0] + D[3] * bl[1] + D[4] * bl[2];
-  db[2] = D[2] * bl[0] + D[4] * bl[1] + D[5] * bl[2];
   if (lane < 6) g.Dinv[6 * (size_t)L + lane] = D[lane];
   const bool to_S = L >= g.n_pl || planes_write_S;  // sharded window: planes are reduced by rank 0 only
   // Dinv = (Hll + lambda)^-1 = C C^T with C = chol(Hll + lambda)^-T: the Schur product W Dinv W'^T of two blocks of this
@@ -803,77 +800,85 @@ __global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double l
   double *Y = g.BD + 18 * (size_t)b0;
   const int n = (b1 - b0) * 6;
   for (int it = lane; it < n; it += 32) {  // one row (e, r) of a 6 x 3 block per lane
-    const int e = it / 6, r = it - 6 * e;
     const double w0 = W[3 * it], w1 = W[3 * it + 1], w2 = W[3 * it + 2];
     const double y0 = w0 * i00, y1 = (w1 - y0 * l10) * i11, y2 = (w2 - y0 * l20 - y1 * l21) * i22;  // y C^-1 = w
     Y[3 * it] = to_S ? y0 : 0.0;
     Y[3 * it + 1] = to_S ? y1 : 0.0;
     Y[3 * it + 2] = to_S ? y2 : 0.0;
-    if (to_S) {  // reduced gradient: bschur_i -= W Dinv bl   (coefficients, core/block_solver.hpp:403-405)
-      const int p = g.ent_pidx[b0 + e];
-      if (p >= 0) atomicAdd(&g.S[(size_t)(6 * p + r) * ld + n_p], -(w0 * db[0] + w1 * db[1] + w2 * db[2]));
-    }
+  }
+  // z = C^T bl per block: the reduced gradient term  W Dinv bl = Y z  (core/block_solver.hpp:403-405) is accumulated by
+  // k_schur_pairs together with the diagonal Schur blocks (no atomics here)
+  const double z0 = bl[0] * i00, z1 = (bl[1] - l10 * z0) * i11, z2 = (bl[2] - l20 * z0 - l21 * z1) * i22;
+  double *Z = g.Zent + 3 * (size_t)b0;
+  for (int it = lane; it < 3 * (b1 - b0); it += 32) {
+    const int c = it % 3;
+    Z[it] = c == 0 ? z0 : (c == 1 ? z1 : z2);
   }
 }
-constexpr int PAIR_CHUNK = 64;
+// Every contribution is a 6x3 by 3x6 product Y1 Y2^T: exactly one FP64 tensor-core instruction (mma.m8n8k4, rows/columns
+// 6..7 and k = 3 zero padded), accumulated in the instruction's own C registers while the key-frame pair stays the same.
+// Column 6 of the B operand carries z of the landmark for the self pairs (Y1 == Y2), so C(:, 6) is the reduced-gradient
+// term Y z of the key-frame.  Per contribution a warp issues two predicated 8-byte loads per lane and one DMMA.
+constexpr int PAIR_CHUNK = 128;
 constexpr int PAIR_WARPS = 8;
+PPO_D void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, const unsigned *__restrict__ keys, const unsigned long long *__restrict__ vals,
-                                                                 int n_pairs, int ld) {
+                                                                 int n_pairs, int ld, int n_p) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
   const long long c0 = w * PAIR_CHUNK;
   if (c0 >= n_pairs) return;  // warp-uniform
   const int cnt = (int)min((long long)PAIR_CHUNK, (long long)n_pairs - c0);
-  // the chunk's keys / values: two coalesced loads per lane, then warp broadcasts (no dependent global loads in the loop)
-  unsigned kl[2];
-  unsigned long long vl[2];
-#pragma unroll
-  for (int q = 0; q < 2; q++) {
-    const int c = 32 * q + lane;
-    kl[q] = c < cnt ? keys[c0 + c] : 0xffffffffu;  // (the list ends with 0xffffffff padding)
-    vl[q] = c < cnt ? vals[c0 + c] : 0ull;
-  }
-  const int r0 = lane / 6, q0 = lane - 6 * r0;  // entry owned by this lane: (r0, q0); lanes 0..3 also own (5, 2 + lane)
-  const int offB0 = 3 * r0, offW0 = 3 * q0, offW1 = 3 * (2 + (lane & 3));
-  const bool extra = lane < 4;
+  // fragment layout: A element (row = lane/4, k = lane%4), B element (k = lane%4, col = lane/4), C elements (row = lane/4, col = 2 (lane%4) + {0,1})
+  const int row = lane >> 2, kk = lane & 3;
+  const bool in_blk = row < 6 && kk < 3, z_lane = row == 6 && kk < 3;
+  const int idx = 3 * row + kk;
   unsigned cur = 0xffffffffu;
-  int p1 = -1, p2 = -1;
   double acc0 = 0.0, acc1 = 0.0;
   auto flush = [&]() {
-    if (p1 >= 0 && p2 >= 0) {
-      atomicAdd(&g.S[(size_t)(6 * p1 + r0) * ld + 6 * p2 + q0], -acc0);
-      if (extra) atomicAdd(&g.S[(size_t)(6 * p1 + 5) * ld + 6 * p2 + 2 + lane], -acc1);
+    if (cur != 0xffffffffu) {
+      const unsigned ka = cur / (unsigned)g.n_kf, kb = cur - ka * (unsigned)g.n_kf;
+      const int p1 = g.kf_idx[ka], p2 = g.kf_idx[kb];
+      if (p1 >= 0 && p2 >= 0 && row < 6) {
+        double *dst = &g.S[(size_t)(6 * p1 + row) * ld];
+        if (kk < 3) {
+          atomicAdd(dst + 6 * p2 + 2 * kk, -acc0);
+          atomicAdd(dst + 6 * p2 + 2 * kk + 1, -acc1);
+        } else if (ka == kb) {
+          atomicAdd(dst + n_p, -acc0);  // bschur -= W Dinv bl
+        }
+      }
     }
     acc0 = acc1 = 0.0;
   };
-  constexpr int U = 4;  // contributions whose 6 + 6 operand loads are in flight together
-#pragma unroll
-  for (int q = 0; q < 2; q++) {
+  constexpr int U = 8;  // contributions whose operand loads are in flight together
+  for (int base = 0; base < cnt; base += 32) {
+    const int c = base + lane;
+    const unsigned kl = c < cnt ? keys[c0 + c] : 0xffffffffu;  // (the list ends with 0xffffffff padding)
+    const unsigned long long vl = c < cnt ? vals[c0 + c] : 0ull;
     for (int cb = 0; cb < 32; cb += U) {
-      if (32 * q + cb >= cnt) break;  // warp-uniform
+      if (base + cb >= cnt) break;  // warp-uniform
       unsigned key[U];
-      double d0[U], d1[U];
+      double av[U], bv[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        key[u] = __shfl_sync(FULL, kl[q], cb + u);
-        const unsigned long long v = __shfl_sync(FULL, vl[q], cb + u);
+        key[u] = __shfl_sync(FULL, kl, cb + u);
+        const unsigned long long v = __shfl_sync(FULL, vl, cb + u);
+        const unsigned e1 = (unsigned)(v >> 32), e2 = (unsigned)(v & 0xffffffffu);
         const bool ok = key[u] != 0xffffffffu;
-        const double *B = g.BD + 18 * (size_t)(unsigned)(v >> 32);
-        const double *W = g.BD + 18 * (size_t)(unsigned)(v & 0xffffffffu);
-        d0[u] = ok ? B[offB0] * W[offW0] + B[offB0 + 1] * W[offW0 + 1] + B[offB0 + 2] * W[offW0 + 2] : 0.0;
-        d1[u] = (ok && extra) ? B[15] * W[offW1] + B[16] * W[offW1 + 1] + B[17] * W[offW1 + 2] : 0.0;
+        av[u] = (ok && in_blk) ? g.BD[18 * (size_t)e1 + idx] : 0.0;
+        bv[u] = (ok && in_blk) ? g.BD[18 * (size_t)e2 + idx] : ((ok && z_lane && e1 == e2) ? g.Zent[3 * (size_t)e1 + kk] : 0.0);
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        if (key[u] == 0xffffffffu) continue;
+        if (key[u] == 0xffffffffu) continue;  // warp-uniform
         if (key[u] != cur) {
           flush();
           cur = key[u];
-          p1 = g.kf_idx[cur / (unsigned)g.n_kf];
-          p2 = g.kf_idx[cur % (unsigned)g.n_kf];
         }
-        acc0 += d0[u];
-        acc1 += d1[u];
+        dmma884(acc0, acc1, av[u], bv[u]);
       }
     }
   }
