@@ -68,8 +68,8 @@ struct ppo_ba_handle {
   ppo_ba_params P;
   int device = 0;
   cudaStream_t st = nullptr;
-  cudaStream_t st2 = nullptr;  // non-point edges are linearised concurrently with the point edges
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // plane / cuboid / point-cuboid edges are linearised next to the point edges
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t evm[2] = {nullptr, nullptr};
   void *d_flush = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -221,9 +221,9 @@ int ppo_ba_create(const ppo_ba_params *params, int device, ppo_ba_handle **out) 
     delete h;
     return PPO_E_CUDA;
   }
-  cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking);
+  for (auto &q : h->side) cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  for (auto &e : h->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   for (auto &e : h->evp) cudaEventCreate(&e);
@@ -250,10 +250,12 @@ void ppo_ba_destroy(ppo_ba_handle *h) {
   if (h->hstage) cudaFreeHost(h->hstage);
   cudaFreeHost(h->h_scal);
   cudaFreeHost(h->h_dims);
-  cudaStreamSynchronize(h->st2);
-  cudaStreamDestroy(h->st2);
+  for (auto &q : h->side) {
+    cudaStreamSynchronize(q);
+    cudaStreamDestroy(q);
+  }
   cudaEventDestroy(h->ev_fork);
-  cudaEventDestroy(h->ev_join);
+  for (auto &e : h->ev_join) cudaEventDestroy(e);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   for (auto &e : h->evp) cudaEventDestroy(e);
@@ -728,13 +730,15 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
     CK(cudaMemsetAsync(g.Hpl, 0, 8 * 18 * (size_t)g.n_slots, st));
   }
   if (h->profiling) cudaEventRecord(h->evp[0], st);
-  // single GPU: the plane / cuboid / point-cuboid edges (numeric Jacobians, few 10^4 threads, latency-bound) run on a
-  // second stream next to the point kernels; both sides only meet in atomically-updated accumulators.
+  // single GPU: the plane / cuboid / point-cuboid edges (numeric Jacobians, few 10^4 threads, latency-bound) run on
+  // three side streams next to the point kernels; all sides only meet in atomically-updated accumulators.
   const bool fork = h->world == 1 && !only_points_kernel && (g.n_ple || g.n_cbe || g.n_pce);
-  cudaStream_t so = fork ? h->st2 : st;
+  const bool use_side[3] = {fork && g.n_ple > 0, fork && g.n_cbe > 0, fork && g.n_pce > 0};
+  cudaStream_t s_pl = use_side[0] ? h->side[0] : st, s_cb = use_side[1] ? h->side[1] : st, s_pc = use_side[2] ? h->side[2] : st;
   if (fork) {
     CK(cudaEventRecord(h->ev_fork, st));
-    CK(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
+    for (int q = 0; q < 3; q++)
+      if (use_side[q]) CK(cudaStreamWaitEvent(h->side[q], h->ev_fork, 0));
   }
   if (g.n_units) {
     k_point_linearize<<<h->nb_lin, LIN_WARPS * 32, 0, st>>>(g, s, h->d_chi_pt);
@@ -751,25 +755,26 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
     if ((rc = allreduce(h, g.Hpp_kf, 36 * (size_t)g.n_kf, ncclFloat64_, ncclSum_)) || (rc = allreduce(h, g.bp, h->max_np, ncclFloat64_, ncclSum_))) return rc;
   }
   if (g.n_ple) {
-    k_plane_jac<<<cdiv(g.n_ple * 9, 128), 128, 0, so>>>(g, s);
-    k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, so>>>(g, s, h->d_chi_pl);
+    k_plane_jac<<<cdiv(g.n_ple * 9, 128), 128, 0, s_pl>>>(g, s);
+    k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, s_pl>>>(g, s, h->d_chi_pl);
     h->launches += 2;
   }
   if (g.n_cbe) {
-    k_cuboid_jac<<<cdiv(g.n_cbe * 15, 128), 128, 0, so>>>(g, s);
-    k_cuboid_edges<true><<<h->nb_cb, SMALL_THREADS, 0, so>>>(g, s, h->d_chi_cb);
-    k_cuboid_assemble<<<cdiv(g.n_cbe * 15, 128), 128, 0, so>>>(g);
+    k_cuboid_jac<<<cdiv(g.n_cbe * 15, 128), 128, 0, s_cb>>>(g, s);
+    k_cuboid_edges<true><<<h->nb_cb, SMALL_THREADS, 0, s_cb>>>(g, s, h->d_chi_cb);
+    k_cuboid_assemble<<<cdiv(g.n_cbe * 15, 128), 128, 0, s_cb>>>(g);
     h->launches += 3;
   }
   if (g.n_pce) {
-    k_ptcu_jac<<<cdiv(g.n_pce * 9, 128), 128, 0, so>>>(g, s);
-    k_ptcu_edges<true><<<h->nb_pc, SMALL_THREADS, 0, so>>>(g, s, h->d_chi_pc);
+    k_ptcu_jac<<<cdiv(g.n_pce * 9, 128), 128, 0, s_pc>>>(g, s);
+    k_ptcu_edges<true><<<h->nb_pc, SMALL_THREADS, 0, s_pc>>>(g, s, h->d_chi_pc);
     h->launches += 2;
   }
-  if (fork) {
-    CK(cudaEventRecord(h->ev_join, h->st2));
-    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
-  }
+  for (int q = 0; q < 3; q++)
+    if (use_side[q]) {
+      CK(cudaEventRecord(h->ev_join[q], h->side[q]));
+      CK(cudaStreamWaitEvent(st, h->ev_join[q], 0));
+    }
   if (h->profiling) cudaEventRecord(h->evp[1], st);
   const bool own = h->owner();  // replicated (non-point) edges count once: on rank 0
   k_scalars<<<1, 256, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,

@@ -414,8 +414,8 @@ __global__ void k_pose_reduce(DevGraph g, const int *kf_chunk_ptr, const double 
 // ---------------------------------------------------------------------------------------------
 __global__ void k_plane_jac(DevGraph g, DevState s) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = t / 9, col = t % 9;
-  if (e >= g.n_ple) return;
+  const int col = t / g.n_ple, e = t - col * g.n_ple;  // column-major: a warp differentiates ONE variable of 32 edges (no branch divergence)
+  if (col >= 9) return;
   if (g.ple_flags[e] & PPO_EF_LEVEL1_) return;
   const int kf = g.ple_kf[e], pl = g.ple_plane[e], kind = g.ple_kind[e];
   double meas[4], pc[4], ep[3], em[3];
@@ -520,8 +520,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_plane_edges(DevGraph g, DevSt
 // ---------------------------------------------------------------------------------------------
 __global__ void k_cuboid_jac(DevGraph g, DevState s) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = t / 15, col = t % 15;
-  if (e >= g.n_cbe) return;
+  const int col = t / g.n_cbe, e = t - col * g.n_cbe;  // column-major (see k_plane_jac)
+  if (col >= 15) return;
   if (g.cbe_flags[e] & PPO_EF_LEVEL1_) return;
   const int kf = g.cbe_kf[e], cu = g.cbe_cuboid[e], kind = g.cbe_kind[e];
   const double *meas = g.cbe_meas + 16 * (size_t)e;
