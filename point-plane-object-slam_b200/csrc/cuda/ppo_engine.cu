@@ -606,7 +606,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   DA(g.xl, 3 * (size_t)g.n_lm); DA(g.S, (size_t)(h->max_np + 1) * h->ld); DA(g.xp, (size_t)h->max_np);
   h->nb_lin = cdiv(g.n_units, LIN_WARPS); h->nb_res = cdiv(g.n_pe, RES_THREADS);
   h->nb_pl = cdiv(g.n_ple, SMALL_THREADS); h->nb_cb = cdiv(g.n_cbe, SMALL_THREADS); h->nb_pc = cdiv(g.n_pce, SMALL_THREADS);
-  h->nb_bs = cdiv(g.n_lm, BS_WARPS);
+  h->nb_bs = cdiv(g.n_pl, BS_WARPS) + g.n_units;  // partial sums of k_backsub (planes) + k_backsub_points
   DA(h->d_chi_pt, (size_t)std::max(h->nb_lin, h->nb_res)); DA(h->d_chi_pl, (size_t)h->nb_pl); DA(h->d_chi_cb, (size_t)h->nb_cb); DA(h->d_chi_pc, (size_t)h->nb_pc);
   DA(h->d_scale_part, (size_t)h->nb_bs);
   DA(h->d_Winv, (size_t)dense_num_blocks(h->max_np) * 64 * 64);
@@ -782,7 +782,8 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
                               nullptr, h->d_red);
   h->launches++;
   if (want_max_diag) {
-    k_max_diag<<<1, 256, 0, st>>>(g, h->d_scal);
+    CK(cudaMemsetAsync(&h->d_scal->max_diag, 0, sizeof(double), st));
+    k_max_diag<<<std::max(1, std::min(148, cdiv(3 * g.n_lm, 2048))), 256, 0, st>>>(g, h->d_scal);
     h->launches++;
   }
   if (h->world > 1) {
@@ -834,7 +835,11 @@ static int schur_system(ppo_ba_handle *h, double lambda) {
 static int solve_and_backsub(ppo_ba_handle *h, double lambda) {
   DevGraph &g = h->g;
   dense_cholesky_solve(g.S, h->n_p, h->ld, g.xp, h->d_Winv, h->d_not_spd, h->st, &h->launches);
-  if (g.n_lm) { k_backsub<<<h->nb_bs, BS_WARPS * 32, 0, h->st>>>(g, lambda, h->d_scale_part, h->owner() ? 1 : 0); h->launches++; }
+  // planes: one warp per landmark; points: one lane per 6x3 block (work units of the linearisation); partial sums of the
+  // LM scale go to disjoint ranges of d_scale_part
+  const int nbp = cdiv(g.n_pl, BS_WARPS);
+  if (g.n_pl) { k_backsub<<<nbp, BS_WARPS * 32, 0, h->st>>>(g, lambda, h->d_scale_part, h->owner() ? 1 : 0, g.n_pl); h->launches++; }
+  if (g.n_units) { k_backsub_points<<<g.n_units, 32, 0, h->st>>>(g, lambda, h->d_scale_part + nbp); h->launches++; }
   return PPO_OK;
 }
 

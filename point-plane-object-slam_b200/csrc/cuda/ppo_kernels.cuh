@@ -285,7 +285,15 @@ __global__ void __launch_bounds__(LIN_WARPS * 32, 20) k_point_linearize(DevGraph
       __syncwarp();
       const int n = (min(e1, base + 32) - base) * 18;
       double *dst = g.Hpl + 18 * (size_t)(g.n_slots + base);
-      for (int i = lane; i < n; i += 32) dst[i] = stage[warp][(i / 18) * STAGE_LD + (i % 18)];
+      {  // element i = lane + 32 k of the run sits at stage[(i / 18) * STAGE_LD + i % 18]: (quotient, remainder) advanced incrementally
+        int q = lane / 18, r = lane - 18 * q;
+        for (int i = lane; i < n; i += 32) {
+          dst[i] = stage[warp][q * STAGE_LD + r];
+          r += 14;  // 32 = 18 + 14
+          q += 1;
+          if (r >= 18) r -= 18, q += 1;
+        }
+      }
       __syncwarp();
     }
   }
@@ -922,12 +930,12 @@ __global__ void k_compose(DevGraph g, double lambda, int n_p, int ld) {
 // computeScale (levenberg.cpp:182-189).  One warp per landmark, lanes stride the contiguous blocks.
 // ---------------------------------------------------------------------------------------------
 constexpr int BS_WARPS = 8;
-__global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double lambda, double *scale_part, int planes_in_scale) {
+__global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double lambda, double *scale_part, int planes_in_scale, int n_first) {
   __shared__ double wsum[BS_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = blockIdx.x * BS_WARPS + warp;
   double sc = 0;
-  const bool in_range = L < g.n_lm;
+  const bool in_range = L < n_first;  // one warp per landmark: used for the planes (tens of blocks each)
   const bool act = in_range && landmark_active(g, L);
   double c[3] = {0, 0, 0};
   if (act) {
@@ -972,6 +980,90 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double la
     for (int i = 0; i < BS_WARPS; i++) t += wsum[i];
     scale_part[blockIdx.x] = t;
   }
+}
+// Point landmarks: same work units as k_point_linearize (a run of consecutive points with <= 32 blocks per warp), one
+// lane per 6x3 block: the lane reads its 144 contiguous bytes and the 6 pose increments, forms Hpl^T x_p, and a
+// segmented warp scan sums the blocks of each point; the last lane of a point applies Dinv.
+__global__ void __launch_bounds__(32) k_backsub_points(DevGraph g, double lambda, double *scale_part) {
+  const int lane = threadIdx.x;
+  const int unit = blockIdx.x;
+  double sc = 0;
+  const int e0 = g.unit_e0[unit], e1 = g.unit_e0[unit + 1];
+  const bool big = e1 - e0 > 32;  // a single point with more than 32 blocks: partial sums carried from chunk to chunk
+  double carry[3] = {0, 0, 0};
+  for (int base = e0; base < e1; base += 32) {
+    const int e = base + lane;
+    const bool valid = e < e1;
+    double c[3] = {0, 0, 0};
+    int key = -1;
+    if (valid) {
+      key = g.pe_pt[e];
+      const int p = g.ent_pidx[g.n_slots + e];
+      if (p >= 0) {
+        const double2 *W = reinterpret_cast<const double2 *>(g.Hpl + 18 * (size_t)(g.n_slots + e));
+        double w[18], x[6];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+          const double2 t = W[i];
+          w[2 * i] = t.x, w[2 * i + 1] = t.y;
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) x[a] = g.xp[6 * p + a];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          c[0] = fma(w[3 * a], x[a], c[0]);
+          c[1] = fma(w[3 * a + 1], x[a], c[1]);
+          c[2] = fma(w[3 * a + 2], x[a], c[2]);
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int ku = __shfl_up_sync(FULL, key, d);
+      const bool take = lane >= d && ku == key;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double t = __shfl_up_sync(FULL, c[i], d);
+        if (take) c[i] += t;
+      }
+    }
+    const int kn = __shfl_down_sync(FULL, key, 1);
+    const bool seg_end = valid && (lane == 31 || kn != key);
+    const bool final_chunk = base + 32 >= e1;
+    if (big) {
+      const int last = min(32, e1 - base) - 1;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double t = __shfl_sync(FULL, c[i], last);
+        if (!final_chunk) carry[i] += t;
+      }
+    }
+    if (seg_end) {
+      const int L = g.n_pl + key;
+      if (final_chunk) {  // (units of several points are a single chunk)
+        if (landmark_active(g, L)) {
+          double D[6], bl[3], cl[3], x[3];
+#pragma unroll
+          for (int i = 0; i < 6; i++) D[i] = g.Dinv[6 * (size_t)L + i];
+#pragma unroll
+          for (int i = 0; i < 3; i++) bl[i] = g.bl[3 * (size_t)L + i], cl[i] = bl[i] - (c[i] + carry[i]);
+          x[0] = D[0] * cl[0] + D[1] * cl[1] + D[2] * cl[2];
+          x[1] = D[1] * cl[0] + D[3] * cl[1] + D[4] * cl[2];
+          x[2] = D[2] * cl[0] + D[4] * cl[1] + D[5] * cl[2];
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            g.xl[3 * (size_t)L + i] = x[i];
+            sc += x[i] * (lambda * x[i] + bl[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 3; i++) g.xl[3 * (size_t)L + i] = 0.0;
+        }
+      }
+    }
+  }
+  sc = warp_sum(sc);
+  if (lane == 0) scale_part[blockIdx.x] = sc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1089,15 +1181,17 @@ __global__ void k_scalars(DevGraph g, Scalars *out, const double *chi_a, int na,
     }
   }
 }
-// max |diagonal| over the active blocks (computeLambdaInit, levenberg.cpp:166-180); single block
-__global__ void k_max_diag(DevGraph g, Scalars *out) {
+// max |diagonal| over the active blocks (computeLambdaInit, levenberg.cpp:166-180).  Grid-stride; the values are
+// non-negative, so the maximum of their bit patterns is the maximum of the values (out->max_diag is zeroed before).
+__global__ void __launch_bounds__(256) k_max_diag(DevGraph g, Scalars *out) {
   __shared__ double sm[256];
   double m = 0;
   const int nb = g.dims[0];
-  for (int i = threadIdx.x; i < nb * 6; i += 256) m = fmax(m, fabs(g.Hpp_kf[36 * (size_t)(i / 6) + 7 * (i % 6)]));
-  for (int i = threadIdx.x; i < g.n_cu * 9; i += 256)
+  const int t0 = blockIdx.x * 256 + threadIdx.x, stride = gridDim.x * 256;
+  for (int i = t0; i < nb * 6; i += stride) m = fmax(m, fabs(g.Hpp_kf[36 * (size_t)(i / 6) + 7 * (i % 6)]));
+  for (int i = t0; i < g.n_cu * 9; i += stride)
     if (g.cu_off[i / 9] >= 0) m = fmax(m, fabs(g.Hpp_cu[81 * (size_t)(i / 9) + 10 * (i % 9)]));
-  for (int i = threadIdx.x; i < g.n_lm * 3; i += 256) {
+  for (int i = t0; i < g.n_lm * 3; i += stride) {
     const int L = i / 3, j = i % 3;
     m = fmax(m, fabs(g.Hll[6 * (size_t)L + (j == 0 ? 0 : (j == 1 ? 3 : 5))]));
   }
@@ -1107,7 +1201,7 @@ __global__ void k_max_diag(DevGraph g, Scalars *out) {
     if (threadIdx.x < o) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) out->max_diag = sm[0];
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long *>(&out->max_diag), (unsigned long long)__double_as_longlong(sm[0]));
 }
 // after the cross-rank reductions: copy the reduced scalars back into the Scalars block
 __global__ void k_scalars_from_red(Scalars *out, const double *red, int which) {
