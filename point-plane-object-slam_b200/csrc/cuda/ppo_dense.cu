@@ -28,11 +28,11 @@ constexpr int NB = 64;  // panel width
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 template <typename... KArgs, typename... Args>
-static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -246,7 +246,7 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 constexpr int TS = 64;
-constexpr int KC = 32;       // K staged per pass
+constexpr int KC = 64;       // the whole panel width is staged at once (dynamic shared memory, > 48 KB)
 constexpr int SLD = TS + 4;  // padded leading dimension of the staged tiles (bank-conflict-free fragment loads)
 // 8 warps; warp w owns rows 8w..8w+7 of the tile and all 64 columns (8 DMMA column blocks).
 // sA[m][r] = A(i0 + r, m), sB[m][r] = B(j0 + r, m)
@@ -265,8 +265,9 @@ __device__ __forceinline__ void tile_mma(const double (*sA)[SLD], const double (
 
 // --- panel: X = A(rows, k:k+nb) * W^T  (W = inverse of the diagonal factor) --------------------------------
 __global__ void __launch_bounds__(256) k_panel_gemm(double *S, int ld, int k, int nb, int n_rows_total, const double *Winv) {
-  __shared__ double sA[KC][SLD];
-  __shared__ double sB[KC][SLD];
+  extern __shared__ __align__(16) unsigned char dsm[];
+  double(*sA)[SLD] = reinterpret_cast<double(*)[SLD]>(dsm);
+  double(*sB)[SLD] = sA + KC;
   pdl_launch_dependents();
   pdl_wait();
   const int i0 = k + nb + blockIdx.x * TS;
@@ -316,7 +317,8 @@ union SyrkSmem {
   PfSmem pf;
 };
 __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, int nb, int n, double *Wnext, int *not_spd) {
-  __shared__ __align__(16) SyrkSmem sm;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  SyrkSmem &sm = *reinterpret_cast<SyrkSmem *>(dsm);
   double(*sA)[SLD] = sm.t.sA;
   double(*sB)[SLD] = sm.t.sB;
   pdl_launch_dependents();
@@ -433,21 +435,27 @@ __global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n
 
 void dense_cholesky_solve(double *S, int n, int ld, double *x, double *Winv, int *not_spd, cudaStream_t st, long long *launches) {
   if (n <= 0) return;
+  static bool attr_set = false;  // per process; opting in is idempotent
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_panel_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyrkSmem));
+    attr_set = true;
+  }
   const int rows_total = n + 1;  // rows 0..n (row n carries the gradient)
-  launch_pdl(k_potrf_inv, dim3(1), dim3(PF_THREADS), st, S, ld, 0, n < NB ? n : NB, Winv, not_spd);
+  launch_pdl(k_potrf_inv, dim3(1), dim3(PF_THREADS), 0, st, S, ld, 0, n < NB ? n : NB, Winv, not_spd);
   (*launches)++;
   for (int k = 0, blk = 0; k < n; k += NB, blk++) {  // the diagonal block of panel k is already factorised
     const int nb = (n - k < NB) ? (n - k) : NB;
     double *W = Winv + (size_t)blk * NB * NB;
     const int T = (rows_total - (k + nb) + TS - 1) / TS;  // >= 1: row n
-    launch_pdl(k_panel_gemm, dim3(T), dim3(256), st, S, ld, k, nb, rows_total, (const double *)W);
-    launch_pdl(k_syrk_update, dim3(T * (T + 1) / 2), dim3(256), st, S, ld, k, nb, n, W + NB * NB, not_spd);
+    launch_pdl(k_panel_gemm, dim3(T), dim3(256), sizeof(TileSmem), st, S, ld, k, nb, rows_total, (const double *)W);
+    launch_pdl(k_syrk_update, dim3(T * (T + 1) / 2), dim3(256), sizeof(SyrkSmem), st, S, ld, k, nb, n, W + NB * NB, not_spd);
     (*launches) += 2;
   }
   const int nblk = (n + NB - 1) / NB;
   for (int b = nblk - 1; b >= 0; b--) {
     const int b0 = b * NB, nb = (n - b0 < NB) ? (n - b0) : NB;
-    launch_pdl(k_backsolve_step, dim3(1 + b), dim3(256), st, S, ld, n, b0, nb, (const double *)(Winv + (size_t)b * NB * NB), x);
+    launch_pdl(k_backsolve_step, dim3(1 + b), dim3(256), 0, st, S, ld, n, b0, nb, (const double *)(Winv + (size_t)b * NB * NB), x);
     (*launches)++;
   }
 }

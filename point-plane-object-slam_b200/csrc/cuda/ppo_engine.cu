@@ -806,10 +806,26 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
 static void residual_kernels(ppo_ba_handle *h, const DevState &s) {
   DevGraph &g = h->g;
   cudaStream_t st = h->st;
+  // four independent kernels (they read the state and write their own per-edge chi2 / partial sums): the three small
+  // ones run on the side streams next to the point residuals
+  const bool use_side[3] = {g.n_ple > 0, g.n_cbe > 0, g.n_pce > 0};
+  const bool fork = g.n_pe > 0 && (use_side[0] || use_side[1] || use_side[2]);
+  if (fork) {
+    cudaEventRecord(h->ev_fork, st);
+    for (int q = 0; q < 3; q++)
+      if (use_side[q]) cudaStreamWaitEvent(h->side[q], h->ev_fork, 0);
+  }
+  cudaStream_t s_pl = fork ? h->side[0] : st, s_cb = fork ? h->side[1] : st, s_pc = fork ? h->side[2] : st;
   if (g.n_pe) { k_point_residual<<<h->nb_res, RES_THREADS, 0, st>>>(g, s, h->d_chi_pt); h->launches++; }
-  if (g.n_ple) { k_plane_edges<false><<<h->nb_pl, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pl); h->launches++; }
-  if (g.n_cbe) { k_cuboid_edges<false><<<h->nb_cb, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_cb); h->launches++; }
-  if (g.n_pce) { k_ptcu_edges<false><<<h->nb_pc, SMALL_THREADS, 0, st>>>(g, s, h->d_chi_pc); h->launches++; }
+  if (g.n_ple) { k_plane_edges<false><<<h->nb_pl, SMALL_THREADS, 0, s_pl>>>(g, s, h->d_chi_pl); h->launches++; }
+  if (g.n_cbe) { k_cuboid_edges<false><<<h->nb_cb, SMALL_THREADS, 0, s_cb>>>(g, s, h->d_chi_cb); h->launches++; }
+  if (g.n_pce) { k_ptcu_edges<false><<<h->nb_pc, SMALL_THREADS, 0, s_pc>>>(g, s, h->d_chi_pc); h->launches++; }
+  if (fork)
+    for (int q = 0; q < 3; q++)
+      if (use_side[q]) {
+        cudaEventRecord(h->ev_join[q], h->side[q]);
+        cudaStreamWaitEvent(st, h->ev_join[q], 0);
+      }
 }
 
 // ---- setLambda + Schur complement (+ optional factorisation / back-substitution) ----------------------------
