@@ -99,13 +99,15 @@ struct PfSmem {
 };
 // barrier of the PF_THREADS threads that run the factorisation (the fused caller has more threads in its CTA)
 __device__ __forceinline__ void pf_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PF_THREADS) : "memory"); }
+// STAGED: the caller has already put the symmetric tile (identity padded beyond nb) into sm.Lu and synchronised.
+template <bool STAGED>
 __device__ __forceinline__ void pf_factor(PfSmem &sm, double *S, int ld, int k, int nb, double *Winv, int *not_spd) {
   PF_STAMP(0);
   double(*Lu)[LDL] = sm.Lu;
   double(*rowb)[NB] = sm.rowb;
   double *rinv = sm.rinv, *dpiv = sm.dpiv, *rs = sm.rs, *sq = sm.sq;
   const int t = threadIdx.x, tr = t >> 4, tc = t & 15;
-  {
+  if (!STAGED) {
     const int i = t & 63, c0 = t >> 6;
     double v[NB / 2];
 #pragma unroll
@@ -118,8 +120,8 @@ __device__ __forceinline__ void pf_factor(PfSmem &sm, double *S, int ld, int k, 
       const int c = c0 + 2 * q;
       if (i >= c) Lu[c][i] = v[q], Lu[i][c] = v[q];
     }
+    pf_bar();
   }
-  pf_bar();
   double a[8][4];
 #pragma unroll
   for (int r = 0; r < 8; r++) {
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_potrf_inv(double *S, int ld, int
   __shared__ __align__(16) PfSmem sm;
   pdl_launch_dependents();
   pdl_wait();
-  pf_factor(sm, S, ld, k, nb, Winv, not_spd);
+  pf_factor<false>(sm, S, ld, k, nb, Winv, not_spd);
 }
 
 // --- 64 x 64 output tile of  C = sum_m A(i,m) B(j,m)  on the FP64 tensor cores ---------------------------
@@ -333,9 +335,19 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
   const int i0 = k2 + bi * TS, j0 = k2 + bj * TS;
   const int tid = threadIdx.x;
   pdl_wait();
-  double acc[8][2];
+  const int lane = tid & 31, warp = tid >> 5;
+  const int il = warp * 8 + (lane >> 2), i = i0 + il;  // my row of the tile; my columns: q * 8 + 2 (lane % 4) + h
+  double acc[8][2], c[8][2];
 #pragma unroll
   for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
+  // the C tile is read up front, together with the panel operands (one global-memory latency instead of two)
+#pragma unroll
+  for (int q = 0; q < 8; q++)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int j = j0 + q * 8 + 2 * (lane & 3) + h;
+      c[q][h] = (i <= n && j < n && i >= j) ? A_(i, j) : 0.0;  // column n does not exist (row n is the carried gradient)
+    }
   for (int m0 = 0; m0 < nb; m0 += KC) {
     const int mc = min(KC, nb - m0);
     __syncthreads();
@@ -354,28 +366,33 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
     __syncthreads();
     tile_mma(sA, sB, (mc + 3) & ~3, acc);
   }
-  const int lane = tid & 31, warp = tid >> 5;
-  const int i = i0 + warp * 8 + (lane >> 2);
+  const bool next_diag = blockIdx.x == 0 && k2 < n;  // this tile is the diagonal block of the next panel
+  const int nb2 = min(NB, n - k2);
   if (i <= n) {
-    double c[8][2];
 #pragma unroll
     for (int q = 0; q < 8; q++)
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int j = j0 + q * 8 + 2 * (lane & 3) + h;
-        c[q][h] = (j < n && i >= j) ? A_(i, j) : 0.0;  // column n does not exist (row n is the carried gradient)
-      }
-#pragma unroll
-    for (int q = 0; q < 8; q++)
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int j = j0 + q * 8 + 2 * (lane & 3) + h;
-        if (j < n && i >= j) A_(i, j) = c[q][h] - acc[q][h];
+        // (rows of the next diagonal block stay on chip: pf_factor overwrites them with the factor anyway)
+        if (j < n && i >= j && !(next_diag && il < nb2)) A_(i, j) = c[q][h] - acc[q][h];
       }
   }
-  if (blockIdx.x == 0 && k2 < n) {
-    __syncthreads();  // the tile is complete (and the staging buffers are free)
-    if (tid < PF_THREADS) pf_factor(sm.pf, S, ld, k2, min(NB, n - k2), Wnext, not_spd);
+  if (next_diag) {
+    __syncthreads();  // everybody is done with the staging buffers, which the factorisation's tile aliases
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int jl = q * 8 + 2 * (lane & 3) + h;
+        if (il >= jl) {
+          const double v = (il < nb2 && jl < nb2) ? c[q][h] - acc[q][h] : (il == jl ? 1.0 : 0.0);
+          sm.pf.Lu[jl][il] = v;
+          sm.pf.Lu[il][jl] = v;
+        }
+      }
+    __syncthreads();
+    if (tid < PF_THREADS) pf_factor<true>(sm.pf, S, ld, k2, nb2, Wnext, not_spd);
   }
 }
 
