@@ -405,22 +405,25 @@ __global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n
   __shared__ double sW[NB][NB + 1];
   __shared__ double xb[NB];
   __shared__ double part[4][NB];
-  const int tid = threadIdx.x;
   __shared__ double yb[NB];
-  {
-    double w[16];
-    const int i = tid & 63, jb = tid >> 6;
+  const int tid = threadIdx.x;
+  const int i = tid & 63, p = tid >> 6;
+  // all global operands are requested up front: W_BB, y_B and (CTAs 1..) this CTA's 64 columns of the block row L(B, :)
+  double w[16], l[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) w[q] = Winv[(size_t)(jb + 4 * q) * NB + i];
-    if (tid < NB) yb[tid] = tid < nb ? A_(n, b0 + tid) : 0.0;
+  for (int q = 0; q < 16; q++) w[q] = Winv[(size_t)(p + 4 * q) * NB + i];
+  const int col = ((int)blockIdx.x - 1) * NB + i;
+  const bool fold = blockIdx.x > 0 && col < b0;
 #pragma unroll
-    for (int q = 0; q < 16; q++) sW[i][jb + 4 * q] = w[q];
-  }
+  for (int q = 0; q < 16; q++) l[q] = (fold && p + 4 * q < nb) ? A_(b0 + p + 4 * q, col) : 0.0;
+  if (tid < NB) yb[tid] = tid < nb ? A_(n, b0 + tid) : 0.0;
+#pragma unroll
+  for (int q = 0; q < 16; q++) sW[i][p + 4 * q] = w[q];
   __syncthreads();
   {
-    const int j = tid & 63, p = tid >> 6;
+    const int j = i;
     double s = 0.0;
-    for (int i = j + p; i < nb; i += 4) s += sW[i][j] * yb[i];
+    for (int r = j + p; r < nb; r += 4) s += sW[r][j] * yb[r];
     part[p][j] = s;
   }
   __syncthreads();
@@ -432,21 +435,15 @@ __global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n
   __syncthreads();
   if (blockIdx.x == 0) return;  // CTA 0 only publishes x_B; CTAs 1.. own the columns [64 (c-1), 64 c)
   {
-    const int i = (blockIdx.x - 1) * NB + (tid & 63), p = tid >> 6;
     double s = 0.0;
-    if (i < b0) {
-      double l[16];
 #pragma unroll
-      for (int q = 0; q < 16; q++) l[q] = (p + 4 * q < nb) ? A_(b0 + p + 4 * q, i) : 0.0;
-#pragma unroll
-      for (int q = 0; q < 16; q++) s += l[q] * xb[p + 4 * q];
-    }
-    part[p][tid & 63] = s;
+    for (int q = 0; q < 16; q++) s += l[q] * xb[p + 4 * q];
+    part[p][i] = s;
   }
   __syncthreads();
   if (tid < NB) {
-    const int i = (blockIdx.x - 1) * NB + tid;
-    if (i < b0) A_(n, i) -= part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+    const int c = ((int)blockIdx.x - 1) * NB + tid;
+    if (c < b0) A_(n, c) -= part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
   }
 }
 
