@@ -307,7 +307,7 @@ def main():
             # the time-dominant phase of a step is the dense solve of the reduced pose system: FP64 tensor
             # pipe (DMMA) for the trailing updates, latency-bound panel chain.  Peak: FP64 DMMA/DFMA rate measured with
             # tools/ubench/fp64.cu (64 FMA/clk/SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s); MEASURED_PEAKS.json has no FP64 figure.
-            "roofline": {"kernel": "dense Hschur solve: k_potrf_inv + k_panel_gemm + k_syrk_update (DMMA) + k_backsolve_step", "bound": "tensor",
+            "roofline": {"kernel": "dense Hschur solve: k_panel_gemm + k_syrk_update (DMMA trailing update, CTA 0 factorises the next diagonal block) + k_backsolve_step", "bound": "tensor",
                          "achieved": sol_flops / (sol_ms * 1e-3) / 1e12, "peak": FP64_TFLOPS, "unit": "TFLOP/s",
                          "frac": sol_flops / (sol_ms * 1e-3) / 1e12 / FP64_TFLOPS, "traffic": None, "ms": sol_ms, "algo_flops": sol_flops,
                          "n_p": sol_n, "peak_source": "measured FP64 DMMA rate, tools/ubench/fp64.cu (of measured; bf16 peak in MEASURED_PEAKS.json does not apply to an FP64 solve)"},

@@ -854,8 +854,18 @@ static int solve_and_backsub(ppo_ba_handle *h, double lambda) {
   // planes: one warp per landmark; points: one lane per 6x3 block (work units of the linearisation); partial sums of the
   // LM scale go to disjoint ranges of d_scale_part
   const int nbp = cdiv(g.n_pl, BS_WARPS);
-  if (g.n_pl) { k_backsub<<<nbp, BS_WARPS * 32, 0, h->st>>>(g, lambda, h->d_scale_part, h->owner() ? 1 : 0, g.n_pl); h->launches++; }
+  const bool fork = g.n_pl > 0 && g.n_units > 0;  // the (few, long) plane landmarks next to the points
+  cudaStream_t s_pl = fork ? h->side[0] : h->st;
+  if (fork) {
+    CK(cudaEventRecord(h->ev_fork, h->st));
+    CK(cudaStreamWaitEvent(s_pl, h->ev_fork, 0));
+  }
+  if (g.n_pl) { k_backsub<<<nbp, BS_WARPS * 32, 0, s_pl>>>(g, lambda, h->d_scale_part, h->owner() ? 1 : 0, g.n_pl); h->launches++; }
   if (g.n_units) { k_backsub_points<<<g.n_units, 32, 0, h->st>>>(g, lambda, h->d_scale_part + nbp); h->launches++; }
+  if (fork) {
+    CK(cudaEventRecord(h->ev_join[0], s_pl));
+    CK(cudaStreamWaitEvent(h->st, h->ev_join[0], 0));
+  }
   return PPO_OK;
 }
 

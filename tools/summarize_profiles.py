@@ -59,14 +59,26 @@ def main():
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`), one local BA call on config 2\n\n")
-        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv python tools/profile_one.py 2`.\n")
+        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv python tools/profile_one.py 2`.\n")
         f.write("Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
         f.write(f"total kernel time {tot / 1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches\n\n| kernel | launches | total us | avg us | max us | share |\n|---|---|---|---|---|---|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {k} | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.2f} | {v[2]:.2f} | {100 * v[1] / tot:.1f}% |\n")
+    traffic = {}
     for rp in reps:
         res = ncu_raw(rp)
         base = os.path.splitext(os.path.basename(rp))[0]
+        if base.startswith(tag + "_"):
+            base = base[len(tag) + 1:]
+        for k, d in res.items():  # dram__bytes_read.sum + dram__bytes_write.sum per launch, in bytes (bench.py: roofline.traffic)
+            try:
+                tot_b = 0.0
+                for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = d[m].split()
+                    tot_b += float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+                traffic[k.replace("ppo::", "")] = tot_b
+            except Exception:
+                pass
         with open(os.path.join(ROOT, "profiles", f"{tag}_{base}.md"), "w") as f:
             f.write(f"# {tag}: ncu --set full summary from {os.path.basename(rp)} (first launch of each kernel)\n\n")
             for k, d in res.items():
@@ -75,6 +87,8 @@ def main():
                     f.write(f"- `{m}` = {v}\n")
                 f.write("\n")
         json.dump(res, open(os.path.join(ROOT, "profiles", f"{tag}_{base}.json"), "w"), indent=1)
+    if traffic:
+        json.dump(traffic, open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
