@@ -51,23 +51,29 @@ def workload_name(ci):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line).  Rank 0 alone
+    samples, all GPUs of the job in one query per half second: eight ranks polling nvidia-smi five times a second
+    measurably slow the kernel-launch path of every process."""
 
-    def __init__(self, index):
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.indices, self.stop_flag, self.rows = list(indices), False, []
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
+        while not self.stop_flag and self.indices:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                out = subprocess.run(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                for line in out.splitlines():
+                    if line.strip():
+                        self.rows.append([x.strip() for x in line.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            for _ in range(5):
+                if self.stop_flag:
+                    break
+                time.sleep(0.1)
 
     def summary(self):
         if not self.rows:
@@ -195,7 +201,10 @@ def main():
 
     ci = args.config
     shard = args.shard and world > 1
-    g = ppo.synth.make_graph(ppo.synth.config(ci, window=0 if shard else rank))  # one independent window per rank unless sharded
+    # one independent window per rank (own handle, own HBM) unless sharded; every rank gets the SAME seeded window so that
+    # the per-GPU work is identical at every N (with different seeds the number of rejected LM trials differs per rank
+    # and max-over-ranks timing measures workload variance instead of scaling)
+    g = ppo.synth.make_graph(ppo.synth.config(ci, window=0))
     params = ppo.default_params()
     if ci == 0:
         params.solver = ppo.abi.SOLVER_6_3  # points-only LocalBundleAdjustment stack (Optimizer.cc:516-522)
@@ -224,7 +233,7 @@ def main():
 
     for _ in range(max(3, args.warmup)):
         step_resident()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(range(world) if rank == 0 else [])
     sampler.start()
     barrier()
     l0 = eng.launch_count()
@@ -297,7 +306,7 @@ def main():
             "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(ci), "windows_per_gpu": 1, "schedule": "optimize(5)+outlier pass+optimize(10)",
-                       "partition": "one window, points sharded over ranks, ncclAllReduce of Hschur|bschur per damped trial" if shard else "independent windows, no data-path collective",
+                       "partition": "one window, points sharded over ranks, ncclAllReduce of Hschur|bschur per damped trial" if shard else "independent windows (one per rank, same seeded content), no data-path collective",
                        "l2": "flushed between timed steps (256 MiB memset)", "lm_iterations_per_step": iters / max(1, args.steps) / world,
                        "n_pose_dim": last.round1.n_pose_dim, "n_point_edges": g.c.n_pe},
             "kf_windows_per_sec": (1 if shard else world) * args.steps / (ms * 1e-3),
