@@ -27,6 +27,8 @@ class Mat {
   template <typename T> const T &at(int r, int c = 0) const { return d[r * cols + c]; }
   Mat clone() const { return *this; }
   bool empty() const { return rows == 0; }
+  void create(int r, int c, int /*type*/) { rows = r, cols = c; }
+  void copyTo(Mat &dst) const { dst = *this; }
   int rows, cols;
   float d[16];
 };
@@ -65,6 +67,8 @@ class MapPoint {
   std::map<MapCuboid *, int> MapObjObservations;
   long unsigned int mnId = 0;
   long unsigned int mnBALocalForKF = 0;
+  cv::Mat mPosGBA;                        // MapPoint.h:120-121 (global BA results when nLoopKF != 0)
+  long unsigned int mnBAGlobalForKF = 0;
   // test bookkeeping
   cv::Mat mWorldPos;
   std::map<KeyFrame *, size_t> mObservations;
@@ -127,6 +131,8 @@ class KeyFrame {
   long unsigned int mnId = 0;
   long unsigned int mnBALocalForKF = 0;
   long unsigned int mnBAFixedForKF = 0;
+  cv::Mat mTcwGBA;                        // KeyFrame.h:179-181
+  long unsigned int mnBAGlobalForKF = 0;
   const float fx, fy, cx, cy, mbf;
   std::vector<cv::KeyPoint> mvKeysUn;
   std::vector<float> mvuRight;
@@ -147,7 +153,12 @@ class KeyFrame {
 
 class Map {
  public:
+  std::vector<KeyFrame *> GetAllKeyFrames() { return mvpKeyFrames; }  // Map.h:54-55
+  std::vector<MapPoint *> GetAllMapPoints() { return mvpMapPoints; }
   std::mutex mMutexMapUpdate;
+  // test bookkeeping
+  std::vector<KeyFrame *> mvpKeyFrames;
+  std::vector<MapPoint *> mvpMapPoints;
 };
 
 // include/Parameters.h:45-76 (only what the local BA reads)
@@ -155,9 +166,12 @@ extern bool optimize_with_cuboid_plane, optimize_with_plane_3d, optimize_with_cu
 extern double ba_weight_bbox, ba_weight_corner, thHuberBbox2d, thHuberConer2d;
 extern double plane_angle_info, plane_dist_info, plane_chi, cuboid_plane_angle_info, cuboid_plane_dist_info, cuboid_plane_chi;
 
-// include/Optimizer.h:45,62 — the two entry points the shim re-implements, signatures unchanged
+// include/Optimizer.h:40-45,62 — the entry points the shim re-implements, signatures unchanged
 class Optimizer {
  public:
+  void static BundleAdjustment(const std::vector<KeyFrame *> &vpKF, const std::vector<MapPoint *> &vpMP, int nIterations = 5, bool *pbStopFlag = NULL,
+                               const unsigned long nLoopKF = 0, const bool bRobust = true);
+  void static GlobalBundleAdjustemnt(Map *pMap, int nIterations = 5, bool *pbStopFlag = NULL, const unsigned long nLoopKF = 0, const bool bRobust = true);
   void static LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap);
   void static LocalBACameraPlaneCuboids(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool fixCamera = false, bool fixPoint = false);
 };

@@ -193,3 +193,79 @@ extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int
   }
   return 0;
 }
+
+// Global BA (Optimizer::GlobalBundleAdjustemnt, src/Optimizer.cc:46-241) on a mock map made of the key-frames and points
+// of a flat graph: slot i -> mnId i (mnId 0 is the fixed one, whatever kf_fixed says), every key-frame and point registered
+// in the Map.  Results are read from the map (nLoopKF == 0) or from mTcwGBA / mPosGBA (nLoopKF != 0).
+extern "C" int ppo_mock_run_global(const ppo_ba_graph *g, int nIterations, unsigned long nLoopKF, int bRobust, unsigned char *stop, ppo_ba_state *out,
+                                   int32_t counts[4] /* KFs tagged, points tagged, SetPose calls, UpdateNormalAndDepth calls */) {
+  std::vector<std::unique_ptr<KeyFrame>> kfs;
+  std::vector<std::unique_ptr<MapPoint>> pts;
+  Map map;
+  float inv_sigma2[8];
+  {
+    float sf = 1.0f;
+    for (int i = 0; i < 8; i++) {
+      inv_sigma2[i] = 1.0f / (sf * sf);
+      sf *= 1.2f;
+    }
+  }
+  for (int i = 0; i < g->n_kf; i++) {
+    const float *in = &g->kf_intr[5 * i];
+    kfs.emplace_back(new KeyFrame(in[0], in[1], in[2], in[3], in[4]));
+    KeyFrame *kf = kfs.back().get();
+    kf->mnId = i;
+    float T[16];
+    ppo::pose7_to_tcw_float(&g->kf_pose[7 * i], T);
+    cv::Mat m(4, 4, CV_32F);
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) m.at<float>(r, c) = T[4 * r + c];
+    kf->Tcw = m;
+    kf->mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + 8);
+    map.mvpKeyFrames.push_back(kf);
+  }
+  for (int p = 0; p < g->n_pt; p++) {
+    pts.emplace_back(new MapPoint());
+    MapPoint *mp = pts.back().get();
+    mp->mnId = p;
+    cv::Mat X(3, 1, CV_32F);
+    for (int k = 0; k < 3; k++) X.at<float>(k, 0) = (float)g->pt_xyz[3 * p + k];
+    mp->mWorldPos = X;
+    for (int e = g->pt_rowptr[p]; e < g->pt_rowptr[p + 1]; e++) {
+      KeyFrame *kf = kfs[g->pe_kf[e]].get();
+      const size_t idx = kf->mvKeysUn.size();
+      int oct = 0;
+      float best = 1e30f;
+      for (int l = 0; l < 8; l++)
+        if (std::fabs(inv_sigma2[l] - g->pe_invsigma2[e]) < best) best = std::fabs(inv_sigma2[l] - g->pe_invsigma2[e]), oct = l;
+      kf->mvKeysUn.push_back(cv::KeyPoint{{g->pe_obs[3 * e], g->pe_obs[3 * e + 1]}, oct});
+      kf->mvuRight.push_back(g->pe_obs[3 * e + 2]);
+      mp->mObservations[kf] = idx;
+    }
+    map.mvpMapPoints.push_back(mp);
+  }
+  bool stop_flag = stop ? (*stop != 0) : false;
+  Optimizer::GlobalBundleAdjustemnt(&map, nIterations, &stop_flag, nLoopKF, bRobust != 0);
+
+  counts[0] = counts[1] = counts[2] = counts[3] = 0;
+  for (int i = 0; i < g->n_kf; i++) {
+    const cv::Mat &M = nLoopKF ? kfs[i]->mTcwGBA : kfs[i]->Tcw;
+    float T[16];
+    if (M.empty()) {  // not written (engine unavailable): report the input
+      for (int k = 0; k < 7; k++) out->kf_pose[7 * i + k] = g->kf_pose[7 * i + k];
+    } else {
+      for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) T[4 * r + c] = M.at<float>(r, c);
+      ppo::tcw_float_to_pose7(T, &out->kf_pose[7 * i]);
+    }
+    counts[0] += nLoopKF && kfs[i]->mnBAGlobalForKF == nLoopKF;
+    counts[2] += kfs[i]->n_setpose;
+  }
+  for (int p = 0; p < g->n_pt; p++) {
+    const cv::Mat &X = (nLoopKF && !pts[p]->mPosGBA.empty()) ? pts[p]->mPosGBA : pts[p]->mWorldPos;
+    for (int k = 0; k < 3; k++) out->pt_xyz[3 * p + k] = X.at<float>(k, 0);
+    counts[1] += nLoopKF && pts[p]->mnBAGlobalForKF == nLoopKF;
+    counts[3] += pts[p]->n_updates;
+  }
+  return 0;
+}

@@ -460,9 +460,137 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   }
 }
 
+// ---- Optimizer::BundleAdjustment (global BA after map initialisation / loop closure), Optimizer.cc:54-241 ------------------
+// Same projection edges as the local BA, every non-bad key-frame free except mnId == 0, one optimize(nIterations) and no
+// outlier pass; results go to the map directly (nLoopKF == 0) or to mTcwGBA / mPosGBA for LoopClosing to merge.
+static void run_global(const std::vector<KeyFrame *> &vpKFs, const std::vector<MapPoint *> &vpMP, int nIterations, bool *pbStopFlag,
+                       unsigned long nLoopKF, bool bRobust) {
+  std::lock_guard<std::mutex> lk(g_mutex);
+  Flat &F = g_last;
+  F = Flat();
+  // key-frame vertices :73-86, slots ordered by mnId = g2o's Hessian order
+  std::vector<KeyFrame *> kfs;
+  for (KeyFrame *pKF : vpKFs)
+    if (!pKF->isBad()) kfs.push_back(pKF);
+  std::sort(kfs.begin(), kfs.end(), [](KeyFrame *a, KeyFrame *b) { return a->mnId < b->mnId; });
+  long unsigned int maxKFid = 0;
+  std::map<KeyFrame *, int> kf_slot;
+  for (size_t i = 0; i < kfs.size(); i++) {
+    KeyFrame *pKF = kfs[i];
+    kf_slot[pKF] = (int)i;
+    float T[16];
+    double p7[7];
+    mat_to_float16(pKF->GetPose(), T);
+    ppo::tcw_float_to_pose7(T, p7);
+    F.kf_pose.insert(F.kf_pose.end(), p7, p7 + 7);
+    F.kf_fixed.push_back(pKF->mnId == 0);  // :81
+    const float in[5] = {pKF->fx, pKF->fy, pKF->cx, pKF->cy, pKF->mbf};
+    F.kf_intr.insert(F.kf_intr.end(), in, in + 5);
+    if (pKF->mnId > maxKFid) maxKFid = pKF->mnId;
+  }
+  // map-point vertices and their projection edges :92-178
+  std::vector<bool> vbNotIncludedMP(vpMP.size(), true);
+  std::vector<MapPoint *> graph_points;
+  for (size_t i = 0; i < vpMP.size(); i++) {
+    MapPoint *pMP = vpMP[i];
+    if (pMP->isBad()) continue;
+    const std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
+    int nEdges = 0;
+    for (auto mit = observations.begin(); mit != observations.end(); mit++) {
+      KeyFrame *pKF = mit->first;
+      if (pKF->isBad() || pKF->mnId > maxKFid) continue;  // :113-114
+      auto slot = kf_slot.find(pKF);
+      if (slot == kf_slot.end()) continue;  // key-frame without a vertex: the reference would add an edge to NULL
+      nEdges++;
+      const cv::KeyPoint &kpUn = pKF->mvKeysUn[mit->second];
+      F.pe_kf.push_back(slot->second);
+      F.pe_obs.push_back(kpUn.pt.x);
+      F.pe_obs.push_back(kpUn.pt.y);
+      F.pe_obs.push_back(pKF->mvuRight[mit->second]);  // < 0: monocular edge (:120)
+      F.pe_invsigma2.push_back(pKF->mvInvLevelSigma2[kpUn.octave]);
+    }
+    if (nEdges == 0) continue;  // :168-172 (vertex removed again)
+    vbNotIncludedMP[i] = false;
+    if (F.pt_rowptr.empty()) F.pt_rowptr.push_back(0);
+    cv::Mat X = pMP->GetWorldPos();
+    for (int k = 0; k < 3; k++) F.pt_xyz.push_back((double)X.at<float>(k, 0));
+    F.pt_fixed.push_back(0);
+    F.pt_rowptr.push_back((int32_t)F.pe_kf.size());
+    graph_points.push_back(pMP);
+  }
+  F.publish();
+
+  ppo_ba_params P;
+  ppo_ba_default_params(&P);
+  P.solver = PPO_SOLVER_6_3;                // :62-66 (BlockSolver_6_3; the linear solver is the engine's dense Cholesky)
+  P.huber_mono = ppo::huber_delta(5.99);    // :88  "sqrt(5.99)", not the 5.991 of the local BA
+  P.huber_stereo = ppo::huber_delta(7.815);  // :89
+  ppo_ba_handle *h = engine(P);
+  g_last_rc = PPO_E_NOGPU;
+  if (!h) {
+    std::fprintf(stderr, "ppo shim: no CUDA engine available; map left untouched\n");
+    return;
+  }
+  std::memset(&g_last_result, 0, sizeof g_last_result);
+  if ((g_last_rc = ppo_ba_set_graph(h, &F.g)) != PPO_OK) {
+    std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", g_last_rc, ppo_ba_last_error(h));
+    return;
+  }
+  if (!bRobust && F.g.n_pe) {  // :132-137,152-157: no robust kernel on any edge
+    std::vector<unsigned char> flags(F.g.n_pe, 0);
+    if ((g_last_rc = ppo_ba_set_edge_flags(h, PPO_EDGE_POINT, flags.data())) != PPO_OK) return;
+  }
+  // :180-183 initializeOptimization() + optimize(nIterations); the force-stop flag is polled inside (:69-70)
+  if ((g_last_rc = ppo_ba_optimize(h, nIterations, reinterpret_cast<const volatile unsigned char *>(pbStopFlag), &g_last_result.round1)) != PPO_OK) {
+    std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", g_last_rc, ppo_ba_last_error(h));
+    return;
+  }
+  ppo_ba_state st;
+  std::vector<double> o_kf(F.kf_pose.size()), o_pt(F.pt_xyz.size());
+  st.kf_pose = o_kf.data(); st.pt_xyz = o_pt.data(); st.pl_coef = nullptr; st.cu_state = nullptr;
+  if ((g_last_rc = ppo_ba_get_state(h, &st)) != PPO_OK) return;
+  // ---- recover optimised data :187-239 --------------------------------------------------------------------------------------
+  for (KeyFrame *pKF : kfs) {
+    float T[16];
+    ppo::pose7_to_tcw_float(&o_kf[7 * (size_t)kf_slot[pKF]], T);
+    if (nLoopKF == 0) {
+      pKF->SetPose(float16_to_mat(T));
+    } else {
+      pKF->mTcwGBA.create(4, 4, CV_32F);
+      float16_to_mat(T).copyTo(pKF->mTcwGBA);
+      pKF->mnBAGlobalForKF = nLoopKF;
+    }
+  }
+  size_t gp = 0;
+  for (size_t i = 0; i < vpMP.size(); i++) {
+    if (vbNotIncludedMP[i]) continue;
+    MapPoint *pMP = vpMP[i];
+    cv::Mat X(3, 1, CV_32F);
+    for (int k = 0; k < 3; k++) X.at<float>(k, 0) = (float)o_pt[3 * gp + k];
+    gp++;
+    if (nLoopKF == 0) {
+      pMP->SetWorldPos(X);
+      pMP->UpdateNormalAndDepth();
+    } else {
+      pMP->mPosGBA.create(3, 1, CV_32F);
+      X.copyTo(pMP->mPosGBA);
+      pMP->mnBAGlobalForKF = nLoopKF;
+    }
+  }
+}
+
 }  // namespace ppo_shim
 
 namespace ORB_SLAM2 {
+void Optimizer::BundleAdjustment(const std::vector<KeyFrame *> &vpKFs, const std::vector<MapPoint *> &vpMP, int nIterations, bool *pbStopFlag,
+                                 const unsigned long nLoopKF, const bool bRobust) {
+  ppo_shim::run_global(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust);
+}
+void Optimizer::GlobalBundleAdjustemnt(Map *pMap, int nIterations, bool *pbStopFlag, const unsigned long nLoopKF, const bool bRobust) {
+  std::vector<KeyFrame *> vpKFs = pMap->GetAllKeyFrames();  // Optimizer.cc:46-51
+  std::vector<MapPoint *> vpMP = pMap->GetAllMapPoints();
+  BundleAdjustment(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust);
+}
 void Optimizer::LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap) { ppo_shim::run(pKF, pbStopFlag, pMap, false, false, false); }
 void Optimizer::LocalBACameraPlaneCuboids(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool fixCamera, bool fixPoint) {
   ppo_shim::run(pKF, pbStopFlag, pMap, true, fixCamera, fixPoint);

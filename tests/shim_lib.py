@@ -18,6 +18,7 @@ def lib():
         path = os.path.join(A.PKG, "lib", "libppo_shim_mock.so")
         L = C.CDLL(path)
         L.ppo_mock_run.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
+        L.ppo_mock_run_global.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_ulong, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
         L.ppo_shim_last_graph.restype = C.POINTER(A.Graph)
         L.ppo_shim_last_result.restype = C.POINTER(A.Result)
         L.ppo_shim_last_rc.restype = C.c_int
@@ -35,3 +36,15 @@ def run(g, mixed=True, fix_camera=False, fix_point=False, stop=False):
     assert rc == 0
     flat = A.GraphArrays.from_c(L.ppo_shim_last_graph().contents)
     return st, list(counts), flat
+
+
+def run_global(g, n_iterations=10, n_loop_kf=0, robust=True, stop=False):
+    """LoopClosing / Tracking-style Optimizer::GlobalBundleAdjustemnt call on a mock map made of g's key-frames and points."""
+    L = lib()
+    st = A.StateArrays(g.c)
+    counts = (C.c_int32 * 4)()
+    flag = np.array([1 if stop else 0], np.uint8)
+    rc = L.ppo_mock_run_global(C.byref(g.c), int(n_iterations), int(n_loop_kf), int(robust), flag.ctypes.data, C.byref(st.c), C.byref(counts))
+    assert rc == 0
+    flat = A.GraphArrays.from_c(L.ppo_shim_last_graph().contents)
+    return st, list(counts), flat, L.ppo_shim_last_rc()

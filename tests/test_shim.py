@@ -91,3 +91,61 @@ def test_shim_end_to_end_matches_oracle_on_its_own_flat_graph(ppo, oracle_mod, m
     # points: matched through the shim's ordering
     moved = np.abs(st.pt_xyz - g["pt_xyz"]).max(axis=1) > 0
     assert moved.sum() >= 0.95 * flat.c.n_pt
+
+
+# ---- Optimizer::GlobalBundleAdjustemnt / BundleAdjustment ------------------------------------------------
+def _global_graph(ppo):
+    # points-only map; key-frame 0 (mnId 0) is the only fixed one, as in Optimizer.cc:81
+    return ppo.synth.make_graph(ppo.synth.config(0, n_kf=12, n_fixed=1, n_pt=700))
+
+
+def test_global_ba_flattening_cpu(ppo):
+    """Without a GPU the shim still flattens the whole map, reports PPO_E_NOGPU and leaves the map untouched (no CPU
+    fallback); with a GPU this test only checks the flattening."""
+    import shim_lib
+    g = _global_graph(ppo)
+    st, counts, flat, rc = shim_lib.run_global(g, n_iterations=0, stop=True)
+    assert flat.c.n_kf == g.c.n_kf and flat.c.n_pt == g.c.n_pt and flat.c.n_pe == g.c.n_pe
+    assert flat.c.n_pl == 0 and flat.c.n_cu == 0 and flat.c.n_ple == 0 and flat.c.n_cbe == 0
+    assert flat["kf_fixed"].tolist() == [1] + [0] * (g.c.n_kf - 1)
+    assert np.allclose(flat["kf_pose"], g["kf_pose"], atol=2e-7) and np.array_equal(flat["kf_intr"], g["kf_intr"])
+    assert np.allclose(flat["pt_xyz"], g["pt_xyz"].astype(np.float32), atol=0) and np.array_equal(flat["pt_rowptr"], g["pt_rowptr"])
+    # observations of a point come out of a std::map keyed by KeyFrame*: same multiset per point
+    rp = g["pt_rowptr"]
+    for p in range(0, g.c.n_pt, 53):
+        a = sorted(zip(flat["pe_kf"][rp[p]:rp[p + 1]].tolist(), map(tuple, flat["pe_obs"][rp[p]:rp[p + 1]].tolist())))
+        b = sorted(zip(g["pe_kf"][rp[p]:rp[p + 1]].tolist(), map(tuple, g["pe_obs"][rp[p]:rp[p + 1]].tolist())))
+        assert a == b
+    import torch
+    if not torch.cuda.is_available():
+        assert rc == ppo.abi.PPO_E_NOGPU and counts == [0, 0, 0, 0]
+        assert np.allclose(st.pt_xyz, g["pt_xyz"].astype(np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_loop_kf,robust", [(0, True), (7, True), (0, False)])
+def test_global_ba_end_to_end_matches_oracle(ppo, oracle_mod, n_loop_kf, robust):
+    """LoopClosing-style call (Optimizer.cc:46-241): one optimize(nIterations), no outlier pass, Huber delta sqrt(5.99),
+    results in the map (nLoopKF == 0) or in mTcwGBA / mPosGBA."""
+    import shim_lib
+    g = _global_graph(ppo)
+    n_it = 10
+    st, counts, flat, rc = shim_lib.run_global(g, n_iterations=n_it, n_loop_kf=n_loop_kf, robust=robust)
+    assert rc == 0
+    p = oracle_mod.default_params()
+    p.solver = ppo.abi.SOLVER_6_3
+    p.huber_mono = float(np.float32(np.sqrt(5.99)))
+    o = oracle_mod.Oracle(p)
+    o.set_graph(flat)
+    if not robust:
+        o.set_edge_flags(ppo.abi.EDGE_POINT, np.zeros(flat.c.n_pe, np.uint8))
+    so_stats = o.optimize(n_it)
+    so = o.get_state()
+    res = shim_lib.lib().ppo_shim_last_result().contents.round1
+    assert res.iterations == so_stats.iterations and np.isclose(res.chi2_final, so_stats.chi2_final, rtol=1e-6)
+    assert np.abs(st.kf_pose - so.kf_pose).max() < 5e-6  # the map holds float32
+    assert np.abs(st.pt_xyz - so.pt_xyz).max() < 5e-5
+    if n_loop_kf:
+        assert counts == [g.c.n_kf, g.c.n_pt, 0, 0]  # tagged with nLoopKF, map itself untouched
+    else:
+        assert counts == [0, 0, g.c.n_kf, g.c.n_pt]  # SetPose on every key-frame, UpdateNormalAndDepth on every point
