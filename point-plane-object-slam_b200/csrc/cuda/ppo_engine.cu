@@ -487,20 +487,34 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
 
   tick("edges by key-frame");
   // ---- plane edges: slots = unique (plane, key-frame) pairs, sorted by (plane, kf) ---------------------
-  std::vector<long long> pairs(g.n_ple);  // plane * n_kf + key-frame
-  for (int e = 0; e < g.n_ple; e++) pairs[e] = (long long)gi->ple_plane[e] * g.n_kf + gi->ple_kf[e];
-  std::vector<long long> uniq = pairs;
-  if (!std::is_sorted(uniq.begin(), uniq.end())) std::sort(uniq.begin(), uniq.end());
-  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-  g.n_slots = (int)uniq.size();
-  g.n_ent = g.n_slots + g.n_pe;
+  // bucket the edges by plane (counting sort), then sort / deduplicate the few key-frames of each plane
   g.n_lm = g.n_pl + g.n_pt;
-  std::vector<int> ple_slot(g.n_ple), slot_kf(g.n_slots), lm_rowptr(g.n_lm + 1, 0);
-  for (int e = 0; e < g.n_ple; e++) ple_slot[e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), pairs[e]) - uniq.begin());
-  for (int s = 0; s < g.n_slots; s++) {
-    slot_kf[s] = (int)(uniq[s] % g.n_kf);
-    lm_rowptr[uniq[s] / g.n_kf + 1]++;
+  std::vector<int> ple_slot(g.n_ple), slot_kf, lm_rowptr(g.n_lm + 1, 0);
+  {
+    std::vector<int> first(g.n_pl + 1, 0), kfs(g.n_ple);
+    for (int e = 0; e < g.n_ple; e++) first[gi->ple_plane[e] + 1]++;
+    for (int p = 0; p < g.n_pl; p++) first[p + 1] += first[p];
+    {
+      std::vector<int> pos(first.begin(), first.end() - 1);
+      for (int e = 0; e < g.n_ple; e++) kfs[pos[gi->ple_plane[e]]++] = gi->ple_kf[e];
+    }
+    std::vector<int> slot0(g.n_pl + 1, 0);
+    slot_kf.reserve(g.n_ple);
+    for (int p = 0; p < g.n_pl; p++) {
+      std::sort(kfs.begin() + first[p], kfs.begin() + first[p + 1]);
+      slot0[p] = (int)slot_kf.size();
+      for (int i = first[p]; i < first[p + 1]; i++)
+        if (i == first[p] || kfs[i] != kfs[i - 1]) slot_kf.push_back(kfs[i]);
+      lm_rowptr[p + 1] = (int)slot_kf.size() - slot0[p];
+    }
+    slot0[g.n_pl] = (int)slot_kf.size();
+    for (int e = 0; e < g.n_ple; e++) {
+      const int p = gi->ple_plane[e];
+      ple_slot[e] = (int)(std::lower_bound(slot_kf.begin() + slot0[p], slot_kf.begin() + slot0[p + 1], gi->ple_kf[e]) - slot_kf.begin());
+    }
   }
+  g.n_slots = (int)slot_kf.size();
+  g.n_ent = g.n_slots + g.n_pe;
   for (int p = 0; p < g.n_pl; p++) lm_rowptr[p + 1] += lm_rowptr[p];
   for (int p = 0; p < g.n_pt; p++) lm_rowptr[g.n_pl + p + 1] = g.n_slots + rowptr[p + 1];
   {
@@ -717,7 +731,9 @@ static int init_mapping(ppo_ba_handle *h) {
 }
 
 // ---- computeActiveErrors + buildSystem at the current estimates -------------------------------------------
-static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kernel = false) {
+// wait == false: the scalars are not read by the caller (LM iterations after the first know chi2 of the current estimate
+// from the accepted trial), so the host goes straight on to enqueue the damped solve behind the linearisation.
+static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kernel = false, bool wait = true) {
   DevGraph &g = h->g;
   cudaStream_t st = h->st;
   const DevState &s = h->sa;
@@ -796,6 +812,7 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
       k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 1);
     }
   }
+  if (!wait) return PPO_OK;
   CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
@@ -885,9 +902,11 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
   int done = 0, term = 0;
   bool ok = true;
   float ms;
+  double chi_state = 0;  // robust chi2 of the current estimate: from the linearisation (first iteration), then from the accepted trials
   for (int it = 0; it < iters && !terminate() && ok; it++) {
-    if ((rc = linearize(h, it == 0))) return rc;
-    double currentChi = h->h_scal->chi2, tempChi = currentChi;
+    const bool wait = it == 0 || h->profiling;
+    if ((rc = linearize(h, it == 0, false, wait))) return rc;
+    double currentChi = wait ? h->h_scal->chi2 : chi_state, tempChi = currentChi;
     const double iniChi = currentChi;
     if (stats && it == 0) stats->chi2_initial = currentChi;
     if (it == 0) {
@@ -956,6 +975,7 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
       qmax++;
     } while (rho < 0 && qmax < P.lm_max_trials && !terminate());
     done++;
+    chi_state = currentChi;
     if (stats) {
       stats->total_trials += qmax;
       if (it < PPO_TRACE_MAX) {
