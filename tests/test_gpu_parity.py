@@ -275,3 +275,52 @@ def test_degenerate_graphs(ppo, oracle_mod):
     st = e3.optimize(5)
     assert st.iterations == 0
     assert np.array_equal(e3.get_state().pt_xyz, g["pt_xyz"])
+
+
+def _permute_points(ppo, g, perm):
+    """The same window with its points (and their CSR edge runs) listed in another order."""
+    a = {k: v.copy() for k, v in g.a.items()}
+    rp = g["pt_rowptr"]
+    order = np.concatenate([np.arange(rp[p], rp[p + 1]) for p in perm]) if len(perm) else np.zeros(0, np.int64)
+    for k in ("pe_kf", "pe_obs", "pe_invsigma2"):
+        a[k] = g[k][order]
+    a["pt_xyz"] = g["pt_xyz"][perm]
+    if "pt_fixed" in a and len(a["pt_fixed"]):
+        a["pt_fixed"] = g["pt_fixed"][perm]
+    cnt = (rp[1:] - rp[:-1])[perm]
+    a["pt_rowptr"] = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    return ppo.abi.GraphArrays(**a)
+
+
+def test_size_independent_properties_at_full_size(ppo):
+    """Properties that need no oracle, on BASELINE configs[2] (the bench workload): the accepted LM iterations never
+    increase the robust cost; re-running from the same input reproduces the run; listing the map points in another
+    order changes nothing beyond summation-order rounding (the engine's work units, Schur pair list and per-key-frame
+    edge lists are all rebuilt from the new order)."""
+    g = ppo.synth.make_graph(ppo.synth.config(2))
+    e = ppo.LocalBA()
+    e.set_graph(g)
+    r = e.local_ba()
+    for rd in (r.round1, r.round2):
+        for t in rd.trace_list():
+            assert t["chi2_after"] <= t["chi2_before"] * (1 + 1e-12)
+            assert t["accepted"] == 1 or t["chi2_after"] == t["chi2_before"]
+    s1 = e.get_state()
+    e.reset()
+    r2 = e.local_ba()
+    s2 = e.get_state()
+    assert (r2.round1.iterations, r2.round2.iterations) == (r.round1.iterations, r.round2.iterations)
+    assert np.isclose(r2.round2.chi2_final, r.round2.chi2_final, rtol=1e-7)  # atomics reorder sums: not bit-exact
+    assert np.abs(s2.kf_pose - s1.kf_pose).max() < 1e-7 and np.abs(s2.pt_xyz - s1.pt_xyz).max() < 1e-6
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(g.c.n_pt)
+    gp = _permute_points(ppo, g, perm)
+    e2 = ppo.LocalBA()
+    e2.set_graph(gp)
+    rp_ = e2.local_ba()
+    sp = e2.get_state()
+    assert (rp_.round1.iterations, rp_.round2.iterations) == (r.round1.iterations, r.round2.iterations)
+    assert (rp_.n_outlier_point_edges, rp_.n_outlier_plane_edges) == (r.n_outlier_point_edges, r.n_outlier_plane_edges)
+    assert np.isclose(rp_.round2.chi2_final, r.round2.chi2_final, rtol=1e-6)
+    assert np.abs(sp.kf_pose - s1.kf_pose).max() < 1e-6
+    assert np.abs(sp.pt_xyz - s1.pt_xyz[perm]).max() < 1e-5
