@@ -793,7 +793,7 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
     }
   if (h->profiling) cudaEventRecord(h->evp[1], st);
   const bool own = h->owner();  // replicated (non-point) edges count once: on rank 0
-  k_scalars<<<1, 256, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
+  k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
                               (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, cpe_chi_const(h), nullptr, 0, 0.0, 0,
                               nullptr, h->d_red);
   h->launches++;
@@ -853,7 +853,8 @@ static int schur_system(ppo_ba_handle *h, double lambda) {
   CK(cudaMemsetAsync(g.S, 0, 8 * (size_t)(n_p + 1) * ld, st));
   CK(cudaMemsetAsync(h->d_not_spd, 0, sizeof(int), st));
   const int own = h->owner() ? 1 : 0;
-  if (g.n_lm) { k_schur_bd<<<cdiv(g.n_lm, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, lambda, n_p, ld, own); h->launches++; }
+  if (g.n_pl) { k_schur_bd<<<cdiv(g.n_pl, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, lambda, n_p, ld, own, g.n_pl); h->launches++; }
+  if (g.n_units) { k_schur_bd_points<<<g.n_units, 32, 0, st>>>(g, lambda); h->launches++; }
   if (h->n_pairs) {
     const int n_warps = cdiv(h->n_pairs, PAIR_CHUNK);
     k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld, n_p);
@@ -933,7 +934,7 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
       residual_kernels(h, h->sb);
       {
         const bool own = h->owner();
-        k_scalars<<<1, 256, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_pe ? h->nb_res : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
+        k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_pe ? h->nb_res : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
                                     (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, cpe_chi_const(h), h->d_scale_part,
                                     g.n_lm ? h->nb_bs : 0, h->lambda, own ? h->n_p : 0, h->d_not_spd, h->d_red);
         h->launches++;

@@ -779,10 +779,10 @@ __global__ void k_gen_pairs(DevGraph g, const int *lm_pair_off, unsigned *keys, 
   }
 }
 constexpr int BD_WARPS = 8;
-__global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double lambda, int n_p, int ld, int planes_write_S) {
+__global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double lambda, int n_p, int ld, int planes_write_S, int n_first) {
   const int lane = threadIdx.x & 31;
   const int L = blockIdx.x * BD_WARPS + (threadIdx.x >> 5);
-  if (L >= g.n_lm) return;
+  if (L >= n_first) return;  // one warp per landmark: used for the planes (tens of blocks each)
   if (!landmark_active(g, L)) {  // inactive landmark: its blocks must not carry products of an earlier trial
     const int a0 = g.lm_rowptr[L] * 18, a1 = g.lm_rowptr[L + 1] * 18;
     for (int it = a0 + lane; it < a1; it += 32) g.BD[it] = 0.0;
@@ -821,6 +821,56 @@ __global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double l
   for (int it = lane; it < 3 * (b1 - b0); it += 32) {
     const int c = it % 3;
     Z[it] = c == 0 ? z0 : (c == 1 ? z1 : z2);
+  }
+}
+// Point landmarks: one lane per 6x3 block (the work units of k_point_linearize: every lane moves 144 contiguous bytes in and
+// out with 16-byte accesses); the 3x3 factorisation of the landmark is recomputed by each of its lanes.
+__global__ void __launch_bounds__(32) k_schur_bd_points(DevGraph g, double lambda) {
+  const int lane = threadIdx.x;
+  const int e0 = g.unit_e0[blockIdx.x], e1 = g.unit_e0[blockIdx.x + 1];
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int pt = g.pe_pt[e];
+    const int L = g.n_pl + pt;
+    const size_t ent = (size_t)g.n_slots + e;
+    double2 *Y = reinterpret_cast<double2 *>(g.BD + 18 * ent);
+    double *Z = g.Zent + 3 * ent;
+    if (!landmark_active(g, L)) {  // its blocks must not carry products of an earlier trial
+#pragma unroll
+      for (int i = 0; i < 9; i++) Y[i] = make_double2(0.0, 0.0);
+      continue;
+    }
+    double h[6], bl[3];
+#pragma unroll
+    for (int i = 0; i < 6; i++) h[i] = g.Hll[6 * (size_t)L + i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) bl[i] = g.bl[3 * (size_t)L + i];
+    if (e == g.pt_rowptr[pt]) {  // first block of the point: publish Dinv for the back-substitution
+      double D[6];
+      inv_sym3(h, lambda, D);
+#pragma unroll
+      for (int i = 0; i < 6; i++) g.Dinv[6 * (size_t)L + i] = D[i];
+    }
+    const double l00 = sqrt(h[0] + lambda), i00 = 1.0 / l00;
+    const double l10 = h[1] * i00, l20 = h[2] * i00;
+    const double l11 = sqrt(fmax(h[3] + lambda - l10 * l10, 1e-300)), i11 = 1.0 / l11;
+    const double l21 = (h[4] - l20 * l10) * i11;
+    const double i22 = rsqrt(fmax(h[5] + lambda - l20 * l20 - l21 * l21, 1e-300));
+    const double2 *W = reinterpret_cast<const double2 *>(g.Hpl + 18 * ent);
+    double w[18];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      const double2 t = W[i];
+      w[2 * i] = t.x, w[2 * i + 1] = t.y;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {  // y C^-1 = w, row by row
+      const double y0 = w[3 * r] * i00, y1 = (w[3 * r + 1] - y0 * l10) * i11, y2 = (w[3 * r + 2] - y0 * l20 - y1 * l21) * i22;
+      w[3 * r] = y0, w[3 * r + 1] = y1, w[3 * r + 2] = y2;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) Y[i] = make_double2(w[2 * i], w[2 * i + 1]);
+    const double z0 = bl[0] * i00, z1 = (bl[1] - l10 * z0) * i11, z2 = (bl[2] - l20 * z0 - l21 * z1) * i22;
+    Z[0] = z0, Z[1] = z1, Z[2] = z2;
   }
 }
 // Every contribution is a 6x3 by 3x6 product Y1 Y2^T: exactly one FP64 tensor-core instruction (mma.m8n8k4, rows/columns
@@ -1158,19 +1208,20 @@ struct Scalars {
   int pad;
 };
 // sums partial arrays in a fixed order; single block
-__global__ void k_scalars(DevGraph g, Scalars *out, const double *chi_a, int na, const double *chi_b, int nb, const double *chi_c, int nc,
+constexpr int SCAL_THREADS = 1024;  // one CTA, fixed summation order (deterministic)
+__global__ void __launch_bounds__(SCAL_THREADS) k_scalars(DevGraph g, Scalars *out, const double *chi_a, int na, const double *chi_b, int nb, const double *chi_c, int nc,
                           const double *chi_d, int nd, double chi_const, const double *scale_part, int ns, double lambda, int n_p,
                           const int *not_spd, double *red /* [chi2, scale] for the cross-rank reduction, may be null */) {
-  __shared__ double sm[8];
+  __shared__ double sm[SCAL_THREADS / 32];
   double c = 0, s = 0;
-  for (int i = threadIdx.x; i < na; i += 256) c += chi_a[i];
-  for (int i = threadIdx.x; i < nb; i += 256) c += chi_b[i];
-  for (int i = threadIdx.x; i < nc; i += 256) c += chi_c[i];
-  for (int i = threadIdx.x; i < nd; i += 256) c += chi_d[i];
-  for (int i = threadIdx.x; i < ns; i += 256) s += scale_part[i];
-  for (int i = threadIdx.x; i < n_p; i += 256) s += g.xp[i] * (lambda * g.xp[i] + g.bp[i]);
-  c = block_sum<256>(c, sm);
-  s = block_sum<256>(s, sm);
+  for (int i = threadIdx.x; i < na; i += SCAL_THREADS) c += chi_a[i];
+  for (int i = threadIdx.x; i < nb; i += SCAL_THREADS) c += chi_b[i];
+  for (int i = threadIdx.x; i < nc; i += SCAL_THREADS) c += chi_c[i];
+  for (int i = threadIdx.x; i < nd; i += SCAL_THREADS) c += chi_d[i];
+  for (int i = threadIdx.x; i < ns; i += SCAL_THREADS) s += scale_part[i];
+  for (int i = threadIdx.x; i < n_p; i += SCAL_THREADS) s += g.xp[i] * (lambda * g.xp[i] + g.bp[i]);
+  c = block_sum<SCAL_THREADS>(c, sm);
+  s = block_sum<SCAL_THREADS>(s, sm);
   if (threadIdx.x == 0) {
     out->chi2 = c + chi_const;
     out->scale = s;
