@@ -266,41 +266,56 @@ __device__ __forceinline__ void tile_mma(const double (*sA)[SLD], const double (
 }
 
 // --- panel: X = A(rows, k:k+nb) * W^T  (W = inverse of the diagonal factor) --------------------------------
+// One CTA per 16 rows of the panel (in place: a CTA reads and writes only its own rows), so that the 64 x 64 x 64 product
+// that sits on the critical path of every panel is spread over four SMs: warp w owns the 8 x 16 block
+// (rows 8 (w & 1).., columns 16 (w >> 1)..) and issues 2 DMMAs per k-step instead of 8.
+constexpr int GR = 16;        // rows per CTA
+constexpr int GLD = GR + 4;   // padded leading dimension of the staged A rows
 __global__ void __launch_bounds__(256) k_panel_gemm(double *S, int ld, int k, int nb, int n_rows_total, const double *Winv) {
-  extern __shared__ __align__(16) unsigned char dsm[];
-  double(*sA)[SLD] = reinterpret_cast<double(*)[SLD]>(dsm);
-  double(*sB)[SLD] = sA + KC;
+  __shared__ double sA[NB][GLD];  // sA[m][r] = A(i0 + r, k + m)
+  __shared__ double sB[NB][SLD];  // sB[m][j] = W(j, m)
   pdl_launch_dependents();
   pdl_wait();
-  const int i0 = k + nb + blockIdx.x * TS;
+  const int i0 = k + nb + blockIdx.x * GR;
   const int tid = threadIdx.x;
-  double acc[8][2];
+  {
+    double ra[4], rb[16];
+    const int r = tid % GR, ma = tid / GR;  // 16 rows x 16 column groups
 #pragma unroll
-  for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
-  for (int m0 = 0; m0 < nb; m0 += KC) {
-    const int mc = min(KC, nb - m0);
-    __syncthreads();
-    {
-      const int r = tid % TS, mb = tid / TS;  // 8 independent loads per operand in flight
-      double ra[KC / 4], rb[KC / 4];
-#pragma unroll
-      for (int q = 0; q < KC / 4; q++) {
-        const int m = mb + 4 * q;
-        ra[q] = (m < mc && i0 + r < n_rows_total) ? A_(i0 + r, k + m0 + m) : 0.0;
-        rb[q] = (m < mc) ? Winv[(size_t)(m0 + m) * NB + r] : 0.0;  // W(j = r, m)
-      }
-#pragma unroll
-      for (int q = 0; q < KC / 4; q++) sA[mb + 4 * q][r] = ra[q], sB[mb + 4 * q][r] = rb[q];
+    for (int q = 0; q < 4; q++) {
+      const int m = ma + 16 * q;
+      ra[q] = (m < nb && i0 + r < n_rows_total) ? A_(i0 + r, k + m) : 0.0;
     }
-    __syncthreads();
-    tile_mma(sA, sB, (mc + 3) & ~3, acc);
+    const int j = tid % NB, mb = tid / NB;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int m = mb + 4 * q;
+      rb[q] = (m < nb) ? Winv[(size_t)m * NB + j] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) sA[ma + 16 * q][r] = ra[q];
+#pragma unroll
+    for (int q = 0; q < 16; q++) sB[mb + 4 * q][j] = rb[q];
   }
+  __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
-  const int i = i0 + warp * 8 + (lane >> 2);
+  const int rblk = warp & 1, cg = warp >> 1;
+  const int row = rblk * 8 + (lane >> 2), kk = lane & 3;
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  const int mc = (nb + 3) & ~3;
+  for (int m0 = 0; m0 < mc; m0 += 4) {
+    const double a = sA[m0 + kk][row];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const double b = sB[m0 + kk][(2 * cg + q) * 8 + (lane >> 2)];
+      dmma(acc[q][0], acc[q][1], a, b);
+    }
+  }
+  const int i = i0 + row;
   if (i < n_rows_total) {
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int j = q * 8 + 2 * (lane & 3);
+    for (int q = 0; q < 2; q++) {
+      const int j = (2 * cg + q) * 8 + 2 * (lane & 3);
       if (j < nb) A_(i, k + j) = acc[q][0];
       if (j + 1 < nb) A_(i, k + j + 1) = acc[q][1];
     }
@@ -451,7 +466,6 @@ void dense_cholesky_solve(double *S, int n, int ld, double *x, double *Winv, int
   if (n <= 0) return;
   static bool attr_set = false;  // per process; opting in is idempotent
   if (!attr_set) {
-    cudaFuncSetAttribute(k_panel_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
     cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyrkSmem));
     attr_set = true;
   }
@@ -462,7 +476,7 @@ void dense_cholesky_solve(double *S, int n, int ld, double *x, double *Winv, int
     const int nb = (n - k < NB) ? (n - k) : NB;
     double *W = Winv + (size_t)blk * NB * NB;
     const int T = (rows_total - (k + nb) + TS - 1) / TS;  // >= 1: row n
-    launch_pdl(k_panel_gemm, dim3(T), dim3(256), sizeof(TileSmem), st, S, ld, k, nb, rows_total, (const double *)W);
+    launch_pdl(k_panel_gemm, dim3((rows_total - (k + nb) + GR - 1) / GR), dim3(256), 0, st, S, ld, k, nb, rows_total, (const double *)W);
     launch_pdl(k_syrk_update, dim3(T * (T + 1) / 2), dim3(256), sizeof(SyrkSmem), st, S, ld, k, nb, n, W + NB * NB, not_spd);
     (*launches) += 2;
   }

@@ -237,6 +237,17 @@ def test_invalid_graph_is_rejected(ppo):
     e = ppo.LocalBA()
     with pytest.raises(ppo.EngineError):
         e.set_graph(A.GraphArrays(**a))
+    # a map point observed twice by one key-frame cannot exist in MapPoint::mObservations (a std::map keyed by KeyFrame*);
+    # the check runs on the device (k_pair_count) and must surface as an error of set_graph
+    b = {k: v.copy() for k, v in g.a.items()}
+    rp = b["pt_rowptr"]
+    p = int(np.argmax(rp[1:] - rp[:-1] >= 2))
+    b["pe_kf"][rp[p] + 1] = b["pe_kf"][rp[p]]
+    with pytest.raises(ppo.EngineError, match="twice"):
+        e.set_graph(A.GraphArrays(**b))
+    # the handle stays usable after a rejected graph
+    e.set_graph(g)
+    assert e.local_ba().round1.iterations > 0
 
 
 def test_degenerate_graphs(ppo, oracle_mod):
