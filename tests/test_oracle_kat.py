@@ -243,9 +243,11 @@ def test_dense_ldlt(L):
 
 
 # ----- whole-system algebra re-derived densely in numpy -------------------------------------------
-def _np_system(g, P, A):
+def _np_system(g, P, A, flags=None, rec=None):
     """Builds the full (un-reduced) Gauss-Newton system of a tiny graph with np_ref residuals and
-    central differences (step 1e-6), ordering [free KFs | cuboids | planes | points]."""
+    central differences (step 1e-6), ordering [free KFs | cuboids | planes | points].
+    flags: optional {edge kind: uint8 array of EF_LEVEL1 | EF_ROBUST} (default: every edge active and robust);
+    rec: optional dict that receives per-edge (chi2, ||error||, depth positive) lists per kind."""
     a = g.a
     n_kf, n_pt, n_pl, n_cu = g.c.n_kf, g.c.n_pt, g.c.n_pl, g.c.n_cu
     free_kf = [i for i in range(n_kf) if not a["kf_fixed"][i]]
@@ -268,14 +270,19 @@ def _np_system(g, P, A):
         Rd, td = R.se3_exp(u); R0, t0 = R.pose_to_Rt(p)
         return Rd @ R0, Rd @ t0 + td
 
-    def add(res_fn, verts, W, delta_h):
+    def add(res_fn, verts, W, delta_h, kind=None, idx=None, extra=None):
         # verts: list of (key, dim, oplus_fn(u) -> replacement value), res_fn(values dict) -> residual
         nonlocal chi_tot
+        fl = A.EF_ROBUST if flags is None or kind is None else int(flags[kind][idx])
+        if fl & A.EF_LEVEL1:
+            return
         r0 = res_fn({})
         chi = float(r0 @ (W * r0))
+        if rec is not None and kind is not None:
+            rec.setdefault(kind, {})[idx] = (chi, float(np.linalg.norm(r0)), extra() if extra else True)
         w = 1.0
         rho0 = chi
-        if delta_h is not None:
+        if delta_h is not None and (fl & A.EF_ROBUST):
             rho0, w = R.huber(chi, delta_h)
         chi_tot += rho0
         Js = []
@@ -307,7 +314,11 @@ def _np_system(g, P, A):
                 X = a["pt_xyz"][p] + pert.get(("pt", p), np.zeros(3))
                 return R.project(Rk @ X + tk, intr, obs)
             W = np.full(D, float(a["pe_invsigma2"][e]))
-            add(res, [(("kf", k), 6, None), (("pt", p), 3, None)], W, P.huber_mono if D == 2 else P.huber_stereo)
+
+            def depth_pos(k=k, p=p):  # isDepthPositive(): z of the point in the camera frame
+                Rk, tk = R.pose_to_Rt(a["kf_pose"][k])
+                return bool((Rk @ a["pt_xyz"][p] + tk)[2] > 0)
+            add(res, [(("kf", k), 6, None), (("pt", p), 3, None)], W, P.huber_mono if D == 2 else P.huber_stereo, A.EDGE_POINT, e, depth_pos)
     for e in range(g.c.n_ple):
         k = int(a["ple_kf"][e]); pl = int(a["ple_plane"][e]); kind = int(a["ple_kind"][e]); meas = a["ple_meas"][e]
         D = 3 if kind == 0 else 2
@@ -318,7 +329,7 @@ def _np_system(g, P, A):
             n2 = Rk @ c[:3]; d2 = c[3] - tk @ n2
             loc = R.plane_normalize(np.r_[n2, d2] if d2 >= 0 else -np.r_[n2, d2])
             return (R.plane_ominus, R.plane_ominus_ver, R.plane_ominus_par)[kind](loc, meas)
-        add(res, [(("pl", pl), 3, None), (("kf", k), 6, None)], a["ple_info"][e][:D], P.huber_plane if kind == 0 else P.huber_vp_plane)
+        add(res, [(("pl", pl), 3, None), (("kf", k), 6, None)], a["ple_info"][e][:D], P.huber_plane if kind == 0 else P.huber_vp_plane, A.EDGE_PLANE, e)
     for e in range(g.c.n_cbe):
         k = int(a["cbe_kf"][e]); cu = int(a["cbe_cuboid"][e]); kind = int(a["cbe_kind"][e])
         D = 4 if kind == 0 else 16
@@ -333,7 +344,7 @@ def _np_system(g, P, A):
                 mn, mx = uv.min(axis=1), uv.max(axis=1)
                 return np.r_[(mn + mx) / 2, mx - mn] - meas
             return uv.T.ravel() - meas
-        add(res, [(("kf", k), 6, None), (("cu", cu), 9, None)], np.full(D, a["cbe_info"][e]), P.huber_bbox if kind == 0 else P.huber_corner)
+        add(res, [(("kf", k), 6, None), (("cu", cu), 9, None)], np.full(D, a["cbe_info"][e]), P.huber_bbox if kind == 0 else P.huber_corner, A.EDGE_CUBOID_CAM, e)
     for e in range(g.c.n_pce):
         cu = int(a["pce_cuboid"][e]); pts = a["pce_pts"][a["pce_rowptr"][e]:a["pce_rowptr"][e + 1]]
 
@@ -342,11 +353,16 @@ def _np_system(g, P, A):
             lp = np.abs((pts - tc) @ Rc)
             er = np.where(lp < sc, 0.0, np.where(lp < 2 * sc, lp - sc, sc))
             return er.mean(axis=0) / sc + 0.2 * sc
-        add(res, [(("cu", cu), 9, None)], np.ones(3), None)
+        add(res, [(("cu", cu), 9, None)], np.ones(3), None, A.EDGE_POINT_CUBOID, e)
     for e in range(g.c.n_cpe):
+        fl = A.EF_ROBUST if flags is None else int(flags[A.EDGE_CUBOID_PLANE][e])
+        if fl & A.EF_LEVEL1:
+            continue
         r0 = a["cpe_meas"][e]
         chi = float(r0 @ (a["cpe_info"][e] * r0))
-        chi_tot += R.huber(chi, P.huber_cuboid_plane)[0]
+        if rec is not None:
+            rec.setdefault(A.EDGE_CUBOID_PLANE, {})[e] = (chi, float(np.linalg.norm(r0)), True)
+        chi_tot += R.huber(chi, P.huber_cuboid_plane)[0] if (fl & A.EF_ROBUST) else chi
     return H, b, n_p, N, chi_tot
 
 
@@ -400,3 +416,164 @@ def test_lm_schedule_converges_and_matches_reference_rules(ppo, oracle_mod):
     stop = np.ones(1, np.uint8)
     res2 = o.local_ba(stop)
     assert res2.skipped == 1 and np.allclose(o.get_state().kf_pose, g["kf_pose"], rtol=0, atol=1e-15)
+
+
+# ----- the whole LM loop re-implemented in numpy on the dense, un-reduced system -----------------------------------
+def _R_to_quat(Rm):
+    """rotation matrix -> [x y z w], w >= 0 (branch on the trace; any valid branch gives the same rotation)."""
+    tr = np.trace(Rm)
+    if tr > 0:
+        s = 2 * np.sqrt(tr + 1)
+        q = np.array([(Rm[2, 1] - Rm[1, 2]) / s, (Rm[0, 2] - Rm[2, 0]) / s, (Rm[1, 0] - Rm[0, 1]) / s, s / 4])
+    else:
+        i = int(np.argmax(np.diag(Rm)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = 2 * np.sqrt(1 + Rm[i, i] - Rm[j, j] - Rm[k, k])
+        q = np.zeros(4)
+        q[i] = s / 4
+        q[j] = (Rm[j, i] + Rm[i, j]) / s
+        q[k] = (Rm[k, i] + Rm[i, k]) / s
+        q[3] = (Rm[k, j] - Rm[j, k]) / s
+    q /= np.linalg.norm(q)
+    return -q if q[3] < 0 else q
+
+
+def _np_apply(A, g, x, n_p):
+    """x (ordering of _np_system) applied with the vertices' oplus; returns a new GraphArrays."""
+    a = {k: v.copy() for k, v in g.a.items()}
+    o = 0
+    for i in range(g.c.n_kf):
+        if a["kf_fixed"][i]:
+            continue
+        Rd, td = R.se3_exp(x[o:o + 6]); R0, t0 = R.pose_to_Rt(a["kf_pose"][i])
+        a["kf_pose"][i] = np.r_[_R_to_quat(Rd @ R0), Rd @ t0 + td]
+        o += 6
+    for i in range(g.c.n_cu):
+        Rc, tc, sc = R.cuboid_oplus_yaw(a["cu_state"][i], x[o:o + 9])
+        a["cu_state"][i] = np.r_[tc, _R_to_quat(Rc), sc]
+        o += 9
+    assert o == n_p
+    for i in range(g.c.n_pl):
+        a["pl_coef"][i] = R.plane_oplus(a["pl_coef"][i], x[o:o + 3])
+        o += 3
+    for i in range(g.c.n_pt):
+        a["pt_xyz"][i] = a["pt_xyz"][i] + x[o:o + 3]
+        o += 3
+    return A.GraphArrays(**a)
+
+
+def test_lm_iterations_against_numpy_reimplementation(ppo, oracle_mod):
+    """optimize(3) of the oracle against a numpy Levenberg-Marquardt written from levenberg.cpp:61-180 on the dense,
+    un-reduced Gauss-Newton system of np_ref (no Schur complement, no block structure, rotation matrices, its own
+    central differences): lambda_0 = tau max diag, rho = (chi - chi') / (x.(lambda x + b) + 1e-3), accept factor
+    max(1/3, min(1 - (2 rho - 1)^3, 2/3)), reject factor ni (doubling)."""
+    A = ppo.abi
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=5, n_fixed=2, n_pt=40, n_pl=3, n_cu=2, corners_2d=1))
+    o = oracle_mod.Oracle()
+    o.set_graph(g)
+    stats = o.optimize(3)
+    tr = stats.trace_list()
+    P = o.params
+    cur = g
+    lam, ni = None, 2.0
+    for it in range(3):
+        H, b, n_p, N, chi = _np_system(cur, P, A)
+        if it == 0:
+            lam = P.lm_tau * np.abs(np.diag(H)).max()
+        assert np.isclose(chi, tr[it]["chi2_before"], rtol=1e-6)
+        trials = 0
+        while True:
+            x = np.linalg.solve(H + lam * np.eye(N), b)
+            trial = _np_apply(A, cur, x, n_p)
+            chi_new = _np_system(trial, P, A)[4]
+            rho = (chi - chi_new) / (float(x @ (lam * x + b)) + 1e-3)
+            trials += 1
+            if rho > 0 and np.isfinite(chi_new):
+                lam *= max(1 / 3, min(1 - (2 * rho - 1) ** 3, 2 / 3))
+                ni = 2.0
+                cur, chi = trial, chi_new
+                break
+            lam *= ni
+            ni *= 2
+            assert trials < 10
+        assert trials == tr[it]["trials"] and tr[it]["accepted"] == 1
+        assert np.isclose(chi, tr[it]["chi2_after"], rtol=1e-5)
+        assert np.isclose(lam, tr[it]["lam"], rtol=1e-3)
+    s = o.get_state()
+    assert np.abs(s.kf_pose - cur["kf_pose"]).max() < 1e-6
+    assert np.abs(s.pt_xyz - cur["pt_xyz"]).max() < 1e-5
+    assert np.abs(s.pl_coef - cur["pl_coef"]).max() < 1e-6
+    assert np.abs(s.cu_state - cur["cu_state"]).max() < 1e-5
+
+
+def _np_lm(A, g, P, iters, flags, trace):
+    """levenberg.cpp:61-180 on the dense system; checks every iteration against the oracle's trace; returns the final graph."""
+    cur, lam, ni = g, None, 2.0
+    for it in range(iters):
+        H, b, n_p, N, chi = _np_system(cur, P, A, flags)
+        if it == 0:
+            lam = P.lm_tau * np.abs(np.diag(H)).max()
+        assert np.isclose(chi, trace[it]["chi2_before"], rtol=1e-6), it
+        trials = 0
+        while True:
+            x = np.linalg.solve(H + lam * np.eye(N), b)
+            trial = _np_apply(A, cur, x, n_p)
+            chi_new = _np_system(trial, P, A, flags)[4]
+            rho = (chi - chi_new) / (float(x @ (lam * x + b)) + 1e-3)
+            trials += 1
+            if rho > 0 and np.isfinite(chi_new):
+                lam *= max(1 / 3, min(1 - (2 * rho - 1) ** 3, 2 / 3))
+                ni = 2.0
+                cur, chi = trial, chi_new
+                break
+            lam *= ni
+            ni *= 2
+            assert trials < 10
+        assert trials == trace[it]["trials"] and trace[it]["accepted"] == 1, it
+        assert np.isclose(chi, trace[it]["chi2_after"], rtol=2e-5), it
+        assert np.isclose(lam, trace[it]["lam"], rtol=5e-3), it
+    return cur
+
+
+def test_full_schedule_against_numpy_reimplementation(ppo, oracle_mod):
+    """The complete LocalBACameraPlaneCuboids schedule, optimize(5) -> outlier pass -> optimize(10), in numpy: the
+    re-levelling rules are written from Optimizer.cc:2736-2833 (points: chi2 > 5.991 / 7.815 or negative depth -> level 1,
+    robust kernel off for all; bbox / corner edges: ||error|| > 80 / 10 -> level 1, kernel kept; plane / ver / par edges:
+    chi2 > 500 / 200 -> level 1, kernel off; cuboid-plane: ||error|| > 500 -> level 1; point-cuboid: untouched)."""
+    A = ppo.abi
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=5, n_fixed=2, n_pt=40, n_pl=3, n_cu=2, corners_2d=1))
+    o = oracle_mod.Oracle()
+    o.set_graph(g)
+    res = o.local_ba()
+    P = o.params
+    n_edges = {A.EDGE_POINT: g.c.n_pe, A.EDGE_PLANE: g.c.n_ple, A.EDGE_CUBOID_CAM: g.c.n_cbe, A.EDGE_POINT_CUBOID: g.c.n_pce,
+               A.EDGE_CUBOID_PLANE: g.c.n_cpe}
+    flags = {k: np.full(n, A.EF_ROBUST, np.uint8) for k, n in n_edges.items()}
+    flags[A.EDGE_POINT_CUBOID][:] = 0  # EdgePointCuboidOnlyObject never gets a robust kernel (Optimizer.cc:2630-2650)
+    r1 = res.round1.trace_list()
+    assert all(t["accepted"] for t in r1)  # otherwise the per-edge errors would be those of a rejected trial (SURVEY q3)
+    cur = _np_lm(A, g, P, res.round1.iterations, flags, r1)
+    rec = {}
+    _np_system(cur, P, A, flags, rec)
+    for e, (chi, _, dpos) in rec[A.EDGE_POINT].items():
+        mono = cur["pe_obs"][e][2] < 0
+        flags[A.EDGE_POINT][e] = A.EF_LEVEL1 if (chi > (5.991 if mono else 7.815) or not dpos) else 0
+    for e, (_, nrm, _) in rec[A.EDGE_CUBOID_CAM].items():
+        th = 80.0 if cur["cbe_kind"][e] == 0 else 10.0
+        flags[A.EDGE_CUBOID_CAM][e] = A.EF_ROBUST | (A.EF_LEVEL1 if nrm > th else 0)
+    for e, (chi, _, _) in rec[A.EDGE_PLANE].items():
+        th = 500.0 if cur["ple_kind"][e] == 0 else 200.0
+        flags[A.EDGE_PLANE][e] = A.EF_LEVEL1 if chi > th else 0
+    for e, (_, nrm, _) in rec.get(A.EDGE_CUBOID_PLANE, {}).items():
+        flags[A.EDGE_CUBOID_PLANE][e] = A.EF_ROBUST | (A.EF_LEVEL1 if nrm > 500.0 else 0)
+    for kind in (A.EDGE_POINT, A.EDGE_PLANE, A.EDGE_CUBOID_CAM):
+        assert np.array_equal(flags[kind], o.get_edge_flags(kind)), kind
+    assert int((flags[A.EDGE_POINT] & A.EF_LEVEL1).sum()) == res.n_outlier_point_edges
+    r2 = res.round2.trace_list()
+    assert all(t["accepted"] for t in r2)
+    cur = _np_lm(A, cur, P, res.round2.iterations, flags, r2)
+    s = o.get_state()
+    assert np.abs(s.kf_pose - cur["kf_pose"]).max() < 5e-6
+    assert np.abs(s.pt_xyz - cur["pt_xyz"]).max() < 5e-5
+    assert np.abs(s.pl_coef - cur["pl_coef"]).max() < 5e-6
+    assert np.abs(s.cu_state - cur["cu_state"]).max() < 5e-5
