@@ -535,16 +535,25 @@ def _np_lm(A, g, P, iters, flags, trace):
     return cur
 
 
-def test_full_schedule_against_numpy_reimplementation(ppo, oracle_mod):
+@pytest.mark.parametrize("inject", [False, True])
+def test_full_schedule_against_numpy_reimplementation(ppo, oracle_mod, inject):
     """The complete LocalBACameraPlaneCuboids schedule, optimize(5) -> outlier pass -> optimize(10), in numpy: the
     re-levelling rules are written from Optimizer.cc:2736-2833 (points: chi2 > 5.991 / 7.815 or negative depth -> level 1,
     robust kernel off for all; bbox / corner edges: ||error|| > 80 / 10 -> level 1, kernel kept; plane / ver / par edges:
     chi2 > 500 / 200 -> level 1, kernel off; cuboid-plane: ||error|| > 500 -> level 1; point-cuboid: untouched)."""
     A = ppo.abi
     g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=5, n_fixed=2, n_pt=40, n_pl=3, n_cu=2, corners_2d=1))
+    if inject:  # one gross plane observation and one gross cuboid-corner observation, so that those rules fire too
+        a = {k: v.copy() for k, v in g.a.items()}
+        e = int(np.argmax(a["ple_kind"] == 0))
+        a["ple_meas"][e] = R.plane_normalize(a["ple_meas"][e] + np.array([0.9, -0.7, 0.4, 1.5]))
+        a["cbe_meas"][int(np.argmax(a["cbe_kind"] == 1))][:16] += 60.0
+        g = A.GraphArrays(**a)
     o = oracle_mod.Oracle()
     o.set_graph(g)
     res = o.local_ba()
+    if inject:
+        assert res.n_outlier_plane_edges >= 1 and res.n_outlier_cuboid_edges >= 1
     P = o.params
     n_edges = {A.EDGE_POINT: g.c.n_pe, A.EDGE_PLANE: g.c.n_ple, A.EDGE_CUBOID_CAM: g.c.n_cbe, A.EDGE_POINT_CUBOID: g.c.n_pce,
                A.EDGE_CUBOID_PLANE: g.c.n_cpe}
