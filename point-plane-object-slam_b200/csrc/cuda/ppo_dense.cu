@@ -10,7 +10,7 @@
 //
 // Per 64-column panel:  pf_factor               L_kk = chol(A_kk) and W_kk = L_kk^-1  (one CTA: k_potrf_inv for panel 0,
 //                                               afterwards CTA 0 of the previous panel's k_syrk_update)
-//                       k_panel_gemm  (rows/64) A_ik <- A_ik W_kk^T           (TRSM as a GEMM)
+//                       k_panel_gemm  (rows/16) A_ik <- A_ik W_kk^T           (TRSM as a GEMM, 16 panel rows per CTA)
 //                       k_syrk_update (tiles)   A_ij -= A_ik A_jk^T           (FP64 tensor cores, DMMA)
 // then per 64-block, last to first:  k_backsolve_step   x_B = W_BB^T y_B ; y_A -= L_BA^T x_B
 #include <cuda_runtime.h>
