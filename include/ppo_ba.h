@@ -216,6 +216,12 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
 int ppo_ba_edge_chi2(ppo_ba_handle *h, int kind, double *chi2, unsigned char *depth_positive,
                      double *err_norm);
 
+/* e->computeError() at the current estimates for every LEVEL-1 edge of a kind (the optimiser skips those, so their
+ * stored error is stale); afterwards ppo_ba_edge_chi2 reports a fresh chi2 for them.  This is what
+ * Optimizer::PoseOptimization does before re-classifying its outliers (Optimizer.cc:400-403,431-434).
+ * Point edges only (PPO_EDGE_POINT); other kinds return PPO_E_INVALID. */
+int ppo_ba_recompute_edge_errors(ppo_ba_handle *h, int kind);
+
 /* e->setLevel(level) / e->setRobustKernel(0) for all edges of a kind.  flags[i] = PPO_EF_* bits. */
 int ppo_ba_set_edge_flags(ppo_ba_handle *h, int kind, const unsigned char *flags);
 int ppo_ba_get_edge_flags(ppo_ba_handle *h, int kind, unsigned char *flags);

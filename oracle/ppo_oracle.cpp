@@ -994,6 +994,14 @@ int ppo_oracle_edge_chi2(ppo_oracle_handle *h, int kind, double *chi2, unsigned 
   return PPO_OK;
 }
 
+// e->computeError() on the level-1 point edges (Optimizer.cc:400-403,431-434)
+int ppo_oracle_recompute_edge_errors(ppo_oracle_handle *h, int kind) {
+  if (!h || kind != PPO_EDGE_POINT) return PPO_E_INVALID;
+  for (int e = 0; e < h->n_pe; e++)
+    if (!h->lvl0(PPO_EDGE_POINT, e)) h->pe_eval(e, &h->pe_err[3 * e]);
+  return PPO_OK;
+}
+
 int ppo_oracle_set_edge_flags(ppo_oracle_handle *h, int kind, const unsigned char *flags) {
   int n = h->edge_count(kind);
   if (n < 0) return PPO_E_INVALID;

@@ -1016,6 +1016,17 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
   return PPO_OK;
 }
 
+int ppo_ba_recompute_edge_errors(ppo_ba_handle *h, int kind) {
+  if (!h || !h->have_graph || kind != PPO_EDGE_POINT) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (h->g.n_pe) {
+    k_point_error_level1<<<cdiv(h->g.n_pe, 256), 256, 0, h->st>>>(h->g, h->sa);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  return PPO_OK;
+}
+
 int ppo_ba_edge_chi2(ppo_ba_handle *h, int kind, double *chi2, unsigned char *depth_positive, double *err_norm) {
   if (!h || !h->have_graph) return PPO_E_INVALID;
   CK(cudaSetDevice(h->device));

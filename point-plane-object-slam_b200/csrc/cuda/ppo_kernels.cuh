@@ -339,6 +339,26 @@ __global__ void __launch_bounds__(RES_THREADS) k_point_residual(DevGraph g, DevS
   if (threadIdx.x == 0) chi_part[blockIdx.x] = t;
 }
 
+// e->computeError() of the level-1 point edges only (the residual pass above skips them): Optimizer.cc:400-403,431-434
+__global__ void k_point_error_level1(DevGraph g, DevState s) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.n_pe || !(g.pe_flags[e] & PPO_EF_LEVEL1_)) return;
+  const PointEdgeRec rec = g.pe_rec[e];
+  const int pt = g.pe_pt[e];
+  double Rt[12], X[3], p[3], err[3];
+  float intr[5];
+#pragma unroll
+  for (int i = 0; i < 12; i++) Rt[i] = s.kf_Rt[12 * rec.kf + i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) X[i] = s.pt[3 * pt + i];
+#pragma unroll
+  for (int i = 0; i < 5; i++) intr[i] = g.kf_intr[5 * rec.kf + i];
+  cam_point(Rt, X, p);
+  point_edge_error(p, intr, rec.u, rec.v, rec.ur, err);
+  const double is2 = (double)g.pe_is2[e];
+  g.pe_chi2[e] = err[0] * (is2 * err[0]) + err[1] * (is2 * err[1]) + err[2] * (is2 * err[2]);
+}
+
 // pose side of the point edges: Hpp_jj += Jkf^T (w Omega) Jkf, bp_j += -Jkf^T (w Omega) r.
 // Edges are grouped by key-frame and cut into chunks; every chunk writes a 27-value partial
 // (21 upper entries + 6 gradient) that k_pose_reduce sums in a fixed order (deterministic, no atomics).

@@ -151,6 +151,22 @@ class KeyFrame {
   int n_setpose = 0;
 };
 
+// Frame.h:100-190 (only what Optimizer::PoseOptimization touches)
+class Frame {
+ public:
+  Frame(float fx_, float fy_, float cx_, float cy_, float bf_) : fx(fx_), fy(fy_), cx(cx_), cy(cy_), mbf(bf_) {}
+  void SetPose(cv::Mat Tcw) { mTcw = Tcw.clone(); n_setpose++; }
+  int N = 0;
+  std::vector<cv::KeyPoint> mvKeysUn;
+  std::vector<float> mvuRight;
+  std::vector<float> mvInvLevelSigma2;
+  std::vector<MapPoint *> mvpMapPoints;  // NULL: no association
+  std::vector<bool> mvbOutlier;
+  float fx, fy, cx, cy, mbf;
+  cv::Mat mTcw;
+  int n_setpose = 0;  // test bookkeeping
+};
+
 class Map {
  public:
   std::vector<KeyFrame *> GetAllKeyFrames() { return mvpKeyFrames; }  // Map.h:54-55
@@ -172,6 +188,7 @@ class Optimizer {
   void static BundleAdjustment(const std::vector<KeyFrame *> &vpKF, const std::vector<MapPoint *> &vpMP, int nIterations = 5, bool *pbStopFlag = NULL,
                                const unsigned long nLoopKF = 0, const bool bRobust = true);
   void static GlobalBundleAdjustemnt(Map *pMap, int nIterations = 5, bool *pbStopFlag = NULL, const unsigned long nLoopKF = 0, const bool bRobust = true);
+  int static PoseOptimization(Frame *pFrame);
   void static LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap);
   void static LocalBACameraPlaneCuboids(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool fixCamera = false, bool fixPoint = false);
 };

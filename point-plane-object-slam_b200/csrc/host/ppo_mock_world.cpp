@@ -269,3 +269,65 @@ extern "C" int ppo_mock_run_global(const ppo_ba_graph *g, int nIterations, unsig
   }
   return 0;
 }
+
+// Tracking-style Optimizer::PoseOptimization call (src/Optimizer.cc:247-459; callers Tracking.cc:1006,1130,1173) on a
+// mock Frame made of key-frame slot `kf` of a flat graph: one feature per point edge of that key-frame (its map point at
+// the graph's position, rounded to float like MapPoint::GetWorldPos), plus a feature WITHOUT a map point after every
+// seventh one.  outlier[] receives mvbOutlier of the associated features in edge order.
+extern "C" int ppo_mock_run_pose(const ppo_ba_graph *g, int kf, double out_pose[7], unsigned char *outlier, int32_t counts[3] /* return value, SetPose calls, associated features */) {
+  const float *in = &g->kf_intr[5 * kf];
+  Frame frame(in[0], in[1], in[2], in[3], in[4]);
+  float inv_sigma2[8];
+  {
+    float sf = 1.0f;
+    for (int i = 0; i < 8; i++) {
+      inv_sigma2[i] = 1.0f / (sf * sf);
+      sf *= 1.2f;
+    }
+  }
+  frame.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + 8);
+  {
+    float T[16];
+    ppo::pose7_to_tcw_float(&g->kf_pose[7 * kf], T);
+    cv::Mat m(4, 4, CV_32F);
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) m.at<float>(r, c) = T[4 * r + c];
+    frame.mTcw = m;
+  }
+  std::vector<std::unique_ptr<MapPoint>> pts;
+  std::vector<int> assoc;  // feature index of every associated feature, in edge order
+  for (int p = 0; p < g->n_pt; p++)
+    for (int e = g->pt_rowptr[p]; e < g->pt_rowptr[p + 1]; e++) {
+      if (g->pe_kf[e] != kf) continue;
+      pts.emplace_back(new MapPoint());
+      MapPoint *mp = pts.back().get();
+      cv::Mat X(3, 1, CV_32F);
+      for (int k = 0; k < 3; k++) X.at<float>(k, 0) = (float)g->pt_xyz[3 * p + k];
+      mp->mWorldPos = X;
+      int oct = 0;
+      float best = 1e30f;
+      for (int l = 0; l < 8; l++)
+        if (std::fabs(inv_sigma2[l] - g->pe_invsigma2[e]) < best) best = std::fabs(inv_sigma2[l] - g->pe_invsigma2[e]), oct = l;
+      assoc.push_back((int)frame.mvKeysUn.size());
+      frame.mvKeysUn.push_back(cv::KeyPoint{{g->pe_obs[3 * e], g->pe_obs[3 * e + 1]}, oct});
+      frame.mvuRight.push_back(g->pe_obs[3 * e + 2]);
+      frame.mvpMapPoints.push_back(mp);
+      frame.mvbOutlier.push_back(true);  // must be cleared by the call (:296,332)
+      if (assoc.size() % 7 == 0) {  // a feature without a map point
+        frame.mvKeysUn.push_back(cv::KeyPoint{{1.0f, 2.0f}, 0});
+        frame.mvuRight.push_back(-1.0f);
+        frame.mvpMapPoints.push_back(nullptr);
+        frame.mvbOutlier.push_back(false);
+      }
+    }
+  frame.N = (int)frame.mvKeysUn.size();
+  counts[0] = Optimizer::PoseOptimization(&frame);
+  counts[1] = frame.n_setpose;
+  counts[2] = (int)assoc.size();
+  float T[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) T[4 * r + c] = frame.mTcw.at<float>(r, c);
+  ppo::tcw_float_to_pose7(T, out_pose);
+  for (size_t i = 0; i < assoc.size(); i++) outlier[i] = frame.mvbOutlier[assoc[i]] ? 1 : 0;
+  return 0;
+}

@@ -30,6 +30,38 @@
 #include "../../../include/ppo_ba.h"
 #include "ppo_convert.h"
 
+#ifdef PPO_SHIM_ON_ORACLE
+// TEST BUILD ONLY (tests/shim_lib.py): the same shim source bound to the CPU oracle, so that the host logic (flattening,
+// re-levelling loops, write-back) can be exercised end to end without a GPU.  Never part of the product libraries.
+extern "C" {
+struct ppo_oracle_handle;
+void ppo_oracle_default_params(ppo_ba_params *);
+int ppo_oracle_create(const ppo_ba_params *, ppo_oracle_handle **);
+void ppo_oracle_destroy(ppo_oracle_handle *);
+int ppo_oracle_set_graph(ppo_oracle_handle *, const ppo_ba_graph *);
+int ppo_oracle_reset(ppo_oracle_handle *);
+int ppo_oracle_optimize(ppo_oracle_handle *, int, const volatile unsigned char *, ppo_ba_stats *);
+int ppo_oracle_edge_chi2(ppo_oracle_handle *, int, double *, unsigned char *, double *);
+int ppo_oracle_recompute_edge_errors(ppo_oracle_handle *, int);
+int ppo_oracle_set_edge_flags(ppo_oracle_handle *, int, const unsigned char *);
+int ppo_oracle_local_ba(ppo_oracle_handle *, const volatile unsigned char *, ppo_ba_result *);
+int ppo_oracle_get_state(ppo_oracle_handle *, ppo_ba_state *);
+}
+#define ppo_ba_handle ppo_oracle_handle
+#define ppo_ba_default_params ppo_oracle_default_params
+#define ppo_ba_create(P, dev, out) ppo_oracle_create((P), (out))
+#define ppo_ba_destroy ppo_oracle_destroy
+#define ppo_ba_set_graph ppo_oracle_set_graph
+#define ppo_ba_reset ppo_oracle_reset
+#define ppo_ba_optimize ppo_oracle_optimize
+#define ppo_ba_edge_chi2 ppo_oracle_edge_chi2
+#define ppo_ba_recompute_edge_errors ppo_oracle_recompute_edge_errors
+#define ppo_ba_set_edge_flags ppo_oracle_set_edge_flags
+#define ppo_ba_local_ba ppo_oracle_local_ba
+#define ppo_ba_get_state ppo_oracle_get_state
+#define ppo_ba_last_error(h) "oracle backend"
+#endif
+
 namespace ppo_shim {
 
 // ---- adapters between the reference's value types and flat doubles ------------------------------------
@@ -579,9 +611,103 @@ static void run_global(const std::vector<KeyFrame *> &vpKFs, const std::vector<M
   }
 }
 
+// ---- Optimizer::PoseOptimization (per tracked frame), Optimizer.cc:247-459 -------------------------------------------------------
+// One free pose, every associated map point as a FIXED point with one projection edge (EdgeSE3ProjectXYZOnlyPose is the
+// binary projection edge with its point held constant).  Four rounds of optimize(10) that each restart from pFrame->mTcw;
+// after each round every edge is re-classified by chi2 (level-1 edges are re-evaluated first), the robust kernels go
+// after the third round.  Returns the number of inliers.
+static int run_pose(Frame *pFrame) {
+  std::lock_guard<std::mutex> lk(g_mutex);
+  Flat &F = g_last;
+  F = Flat();
+  {
+    float T[16];
+    double p7[7];
+    mat_to_float16(pFrame->mTcw, T);
+    ppo::tcw_float_to_pose7(T, p7);
+    F.kf_pose.insert(F.kf_pose.end(), p7, p7 + 7);
+    F.kf_fixed.push_back(0);  // :263 vSE3->setFixed(false)
+    const float in[5] = {pFrame->fx, pFrame->fy, pFrame->cx, pFrame->cy, pFrame->mbf};
+    F.kf_intr.insert(F.kf_intr.end(), in, in + 5);
+  }
+  int nInitialCorrespondences = 0;
+  std::vector<int> vnIndexEdge;  // edge -> feature index (vnIndexEdgeMono / vnIndexEdgeStereo, :270-279)
+  F.pt_rowptr.push_back(0);
+  for (int i = 0; i < pFrame->N; i++) {
+    MapPoint *pMP = pFrame->mvpMapPoints[i];
+    if (!pMP) continue;
+    nInitialCorrespondences++;
+    pFrame->mvbOutlier[i] = false;  // :296,332
+    const cv::KeyPoint &kpUn = pFrame->mvKeysUn[i];
+    cv::Mat Xw = pMP->GetWorldPos();
+    for (int k = 0; k < 3; k++) F.pt_xyz.push_back((double)Xw.at<float>(k, 0));  // e->Xw (:317-320)
+    F.pt_fixed.push_back(1);
+    F.pe_kf.push_back(0);
+    F.pe_obs.push_back(kpUn.pt.x);
+    F.pe_obs.push_back(kpUn.pt.y);
+    F.pe_obs.push_back(pFrame->mvuRight[i]);  // < 0: monocular (:293)
+    F.pe_invsigma2.push_back(pFrame->mvInvLevelSigma2[kpUn.octave]);
+    F.pt_rowptr.push_back((int32_t)F.pe_kf.size());
+    vnIndexEdge.push_back(i);
+  }
+  F.publish();
+  if (nInitialCorrespondences < 3) return 0;  // :371-372
+
+  ppo_ba_params P;
+  ppo_ba_default_params(&P);  // deltaMono = sqrt(5.991), deltaStereo = sqrt(7.815) (:281-282)
+  P.solver = PPO_SOLVER_6_3;
+  ppo_ba_handle *h = engine(P);
+  g_last_rc = PPO_E_NOGPU;
+  if (!h) {
+    std::fprintf(stderr, "ppo shim: no CUDA engine available; frame pose left untouched\n");
+    return 0;
+  }
+  std::memset(&g_last_result, 0, sizeof g_last_result);
+  if ((g_last_rc = ppo_ba_set_graph(h, &F.g)) != PPO_OK) {
+    std::fprintf(stderr, "ppo shim: engine error %d (%s); frame pose left untouched\n", g_last_rc, ppo_ba_last_error(h));
+    return 0;
+  }
+  const int n_e = F.g.n_pe;
+  std::vector<unsigned char> flags(n_e, PPO_EF_ROBUST);
+  std::vector<double> chi2(n_e);
+  const float chi2Mono[4] = {5.991f, 5.991f, 5.991f, 5.991f}, chi2Stereo[4] = {7.815f, 7.815f, 7.815f, 7.815f};  // :376-377
+  const int its[4] = {10, 10, 10, 10};
+  int nBad = 0;
+  for (size_t it = 0; it < 4; it++) {
+    // :383-385  vSE3->setEstimate(toSE3Quat(pFrame->mTcw)); initializeOptimization(0); optimize(its[it])
+    if ((g_last_rc = ppo_ba_reset(h)) != PPO_OK || (g_last_rc = ppo_ba_set_edge_flags(h, PPO_EDGE_POINT, flags.data())) != PPO_OK) return 0;
+    g_last_rc = ppo_ba_optimize(h, its[it], nullptr, it < 2 ? &g_last_result.round1 : &g_last_result.round2);
+    if (g_last_rc != PPO_OK && g_last_rc != PPO_E_EMPTY) return 0;  // (every edge an outlier: nothing to optimise)
+    // :396-403 / :427-434  e->computeError() for the current outliers, then chi2 of every edge
+    if ((g_last_rc = ppo_ba_recompute_edge_errors(h, PPO_EDGE_POINT)) != PPO_OK ||
+        (g_last_rc = ppo_ba_edge_chi2(h, PPO_EDGE_POINT, chi2.data(), nullptr, nullptr)) != PPO_OK)
+      return 0;
+    nBad = 0;
+    for (int e = 0; e < n_e; e++) {
+      const bool mono = F.pe_obs[3 * (size_t)e + 2] < 0;
+      const float c = (float)chi2[e];  // "const float chi2 = e->chi2();"
+      const bool out = c > (mono ? chi2Mono[it] : chi2Stereo[it]);
+      pFrame->mvbOutlier[vnIndexEdge[e]] = out;
+      flags[e] = (unsigned char)((flags[e] & PPO_EF_ROBUST) | (out ? PPO_EF_LEVEL1 : 0));
+      nBad += out;
+      if (it == 2) flags[e] &= (unsigned char)~PPO_EF_ROBUST;  // :419-420
+    }
+    if (n_e < 10) break;  // :448-449
+  }
+  ppo_ba_state st;
+  double o_kf[7];
+  st.kf_pose = o_kf; st.pt_xyz = nullptr; st.pl_coef = nullptr; st.cu_state = nullptr;
+  if ((g_last_rc = ppo_ba_get_state(h, &st)) != PPO_OK) return 0;
+  float T[16];
+  ppo::pose7_to_tcw_float(o_kf, T);
+  pFrame->SetPose(float16_to_mat(T));  // :452-456
+  return nInitialCorrespondences - nBad;
+}
+
 }  // namespace ppo_shim
 
 namespace ORB_SLAM2 {
+int Optimizer::PoseOptimization(Frame *pFrame) { return ppo_shim::run_pose(pFrame); }
 void Optimizer::BundleAdjustment(const std::vector<KeyFrame *> &vpKFs, const std::vector<MapPoint *> &vpMP, int nIterations, bool *pbStopFlag,
                                  const unsigned long nLoopKF, const bool bRobust) {
   ppo_shim::run_global(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust);

@@ -30,6 +30,7 @@ def _bind(lib, prefix):
     f("set_edge_flags").argtypes = [H, C.c_int, C.c_void_p]
     f("get_edge_flags").argtypes = [H, C.c_int, C.c_void_p]
     f("edge_count").argtypes = [H, C.c_int]
+    f("recompute_edge_errors").argtypes = [H, C.c_int]
     f("outlier_pass").argtypes = [H, C.POINTER(C.c_int32 * 3)]
     f("local_ba").argtypes = [H, C.c_void_p, C.POINTER(A.Result)]
     f("get_state").argtypes = [H, C.POINTER(A.State)]
@@ -128,6 +129,10 @@ class Handle:
         flags = np.ascontiguousarray(flags, np.uint8)
         assert len(flags) == self.edge_count(kind)
         self._check(self._f("set_edge_flags")(self.h, kind, flags.ctypes.data), "set_edge_flags")
+
+    def recompute_edge_errors(self, kind):
+        """e->computeError() on the level-1 edges of a kind (Optimizer::PoseOptimization, Optimizer.cc:400-403)."""
+        self._check(self._f("recompute_edge_errors")(self.h, kind), "recompute_edge_errors")
 
     def outlier_pass(self):
         n = (C.c_int32 * 3)()

@@ -12,11 +12,46 @@ A = ppo.abi
 _LIB = None
 
 
+_ORACLE_LIB = None
+
+
+def _declare(L):
+    L.ppo_mock_run.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
+    L.ppo_mock_run_global.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_ulong, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
+    L.ppo_shim_last_result.restype = C.POINTER(A.Result)
+    L.ppo_mock_run_pose.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32 * 3)]
+
+
+def oracle_backed_lib():
+    """TEST BUILD: the shim source compiled with -DPPO_SHIM_ON_ORACLE and linked to the CPU oracle, so that the shim's host
+    logic runs end to end without a GPU.  Lives under oracle/_build (test infrastructure), never in the product lib/."""
+    global _ORACLE_LIB
+    if _ORACLE_LIB is None:
+        import subprocess
+        import oracle_lib
+        oracle_lib.lib()
+        bdir = os.path.join(A.ROOT, "oracle", "_build")
+        out = os.path.join(bdir, "libppo_shim_mock_oracle.so")
+        host = os.path.join(A.PKG, "csrc", "host")
+        srcs = [os.path.join(host, "ppo_optimizer_shim.cpp"), os.path.join(host, "ppo_mock_world.cpp")]
+        deps = srcs + [os.path.join(host, f) for f in ("ppo_mock_slam.h", "ppo_convert.h")] + [os.path.join(bdir, "libppo_oracle.so")]
+        if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DPPO_SHIM_ON_ORACLE", "-o", out] + srcs +
+                                  ["-L", bdir, "-lppo_oracle", "-Wl,-rpath,$ORIGIN"])
+        L = C.CDLL(out)
+        _declare(L)
+        L.ppo_shim_last_graph.restype = C.POINTER(A.Graph)
+        L.ppo_shim_last_rc.restype = C.c_int
+        _ORACLE_LIB = L
+    return _ORACLE_LIB
+
+
 def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(A.PKG, "lib", "libppo_shim_mock.so")
         L = C.CDLL(path)
+        _declare(L)
         L.ppo_mock_run.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
         L.ppo_mock_run_global.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_ulong, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
         L.ppo_shim_last_graph.restype = C.POINTER(A.Graph)
@@ -26,9 +61,9 @@ def lib():
     return _LIB
 
 
-def run(g, mixed=True, fix_camera=False, fix_point=False, stop=False):
+def run(g, mixed=True, fix_camera=False, fix_point=False, stop=False, backend=None):
     """LocalMapping-style call on a mock map built from the flat graph g. Returns (state, counts, flattened graph)."""
-    L = lib()
+    L = backend or lib()
     st = A.StateArrays(g.c)
     counts = (C.c_int32 * 4)()
     flag = np.array([1 if stop else 0], np.uint8)
@@ -38,9 +73,9 @@ def run(g, mixed=True, fix_camera=False, fix_point=False, stop=False):
     return st, list(counts), flat
 
 
-def run_global(g, n_iterations=10, n_loop_kf=0, robust=True, stop=False):
+def run_global(g, n_iterations=10, n_loop_kf=0, robust=True, stop=False, backend=None):
     """LoopClosing / Tracking-style Optimizer::GlobalBundleAdjustemnt call on a mock map made of g's key-frames and points."""
-    L = lib()
+    L = backend or lib()
     st = A.StateArrays(g.c)
     counts = (C.c_int32 * 4)()
     flag = np.array([1 if stop else 0], np.uint8)
@@ -48,3 +83,18 @@ def run_global(g, n_iterations=10, n_loop_kf=0, robust=True, stop=False):
     assert rc == 0
     flat = A.GraphArrays.from_c(L.ppo_shim_last_graph().contents)
     return st, list(counts), flat, L.ppo_shim_last_rc()
+
+
+def run_pose(g, kf, backend=None):
+    """Tracking-style Optimizer::PoseOptimization on a mock Frame made of key-frame slot kf of g.
+    Returns (pose7, outlier flags per associated feature, [return value, SetPose calls, associated features], flat graph, rc)."""
+    L = backend or lib()
+    pose = np.zeros(7)
+    rp = g["pt_rowptr"]
+    n = int((g["pe_kf"] == kf).sum())
+    out = np.zeros(max(n, 1), np.uint8)
+    counts = (C.c_int32 * 3)()
+    rc = L.ppo_mock_run_pose(C.byref(g.c), int(kf), pose.ctypes.data, out.ctypes.data, C.byref(counts))
+    assert rc == 0
+    flat = A.GraphArrays.from_c(L.ppo_shim_last_graph().contents)
+    return pose, out[:n], list(counts), flat, L.ppo_shim_last_rc()

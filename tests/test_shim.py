@@ -52,21 +52,30 @@ def test_points_only_entry_point_flattening_cpu(ppo):
     assert abs(flat.c.n_pe - g.c.n_pe) < 0.02 * g.c.n_pe
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("mixed", [True, False])
-def test_shim_end_to_end_matches_oracle_on_its_own_flat_graph(ppo, oracle_mod, mixed):
-    """LocalMapping-style call -> GPU engine -> write-back; compared with the oracle run on the graph the shim built."""
+def _backend(name):
     import shim_lib
+    return shim_lib.lib() if name == "engine" else shim_lib.oracle_backed_lib()
+
+
+BACKENDS = [pytest.param("engine", marks=pytest.mark.gpu), "oracle"]  # "oracle": the shim's host logic, CPU only (test build)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("mixed", [True, False])
+def test_shim_end_to_end_matches_oracle_on_its_own_flat_graph(ppo, oracle_mod, mixed, backend):
+    """LocalMapping-style call -> engine -> write-back; compared with the oracle run on the graph the shim built."""
+    import shim_lib
+    L = _backend(backend)
     g = _graph(ppo) if mixed else ppo.synth.make_graph(ppo.synth.config(0))
-    st, counts, flat = shim_lib.run(g, mixed=mixed)
-    assert shim_lib.lib().ppo_shim_last_rc() == 0
+    st, counts, flat = shim_lib.run(g, mixed=mixed, backend=L)
+    assert L.ppo_shim_last_rc() == 0
     o = oracle_mod.Oracle()
     if not mixed:
         o.params.solver = ppo.abi.SOLVER_6_3
     o.set_graph(flat)
     ro = o.local_ba()
     so = o.get_state()
-    res = shim_lib.lib().ppo_shim_last_result().contents
+    res = L.ppo_shim_last_result().contents
     assert (res.round1.iterations, res.round2.iterations) == (ro.round1.iterations, ro.round2.iterations)
     assert np.isclose(res.round2.chi2_final, ro.round2.chi2_final, rtol=1e-6)
     # the map holds float32: compare at float32 resolution; key-frame slots are identical (sorted by mnId)
@@ -122,15 +131,16 @@ def test_global_ba_flattening_cpu(ppo):
         assert np.allclose(st.pt_xyz, g["pt_xyz"].astype(np.float32))
 
 
-@pytest.mark.gpu
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("n_loop_kf,robust", [(0, True), (7, True), (0, False)])
-def test_global_ba_end_to_end_matches_oracle(ppo, oracle_mod, n_loop_kf, robust):
+def test_global_ba_end_to_end_matches_oracle(ppo, oracle_mod, n_loop_kf, robust, backend):
     """LoopClosing-style call (Optimizer.cc:46-241): one optimize(nIterations), no outlier pass, Huber delta sqrt(5.99),
     results in the map (nLoopKF == 0) or in mTcwGBA / mPosGBA."""
     import shim_lib
     g = _global_graph(ppo)
     n_it = 10
-    st, counts, flat, rc = shim_lib.run_global(g, n_iterations=n_it, n_loop_kf=n_loop_kf, robust=robust)
+    L = _backend(backend)
+    st, counts, flat, rc = shim_lib.run_global(g, n_iterations=n_it, n_loop_kf=n_loop_kf, robust=robust, backend=L)
     assert rc == 0
     p = oracle_mod.default_params()
     p.solver = ppo.abi.SOLVER_6_3
@@ -141,7 +151,7 @@ def test_global_ba_end_to_end_matches_oracle(ppo, oracle_mod, n_loop_kf, robust)
         o.set_edge_flags(ppo.abi.EDGE_POINT, np.zeros(flat.c.n_pe, np.uint8))
     so_stats = o.optimize(n_it)
     so = o.get_state()
-    res = shim_lib.lib().ppo_shim_last_result().contents.round1
+    res = L.ppo_shim_last_result().contents.round1
     assert res.iterations == so_stats.iterations and np.isclose(res.chi2_final, so_stats.chi2_final, rtol=1e-6)
     assert np.abs(st.kf_pose - so.kf_pose).max() < 5e-6  # the map holds float32
     assert np.abs(st.pt_xyz - so.pt_xyz).max() < 5e-5
@@ -149,3 +159,59 @@ def test_global_ba_end_to_end_matches_oracle(ppo, oracle_mod, n_loop_kf, robust)
         assert counts == [g.c.n_kf, g.c.n_pt, 0, 0]  # tagged with nLoopKF, map itself untouched
     else:
         assert counts == [0, 0, g.c.n_kf, g.c.n_pt]  # SetPose on every key-frame, UpdateNormalAndDepth on every point
+
+
+# ---- Optimizer::PoseOptimization ------------------------------------------------------------------------------
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_pose_optimization_matches_the_reference_schedule(ppo, oracle_mod, backend):
+    """Tracking-style call (Optimizer.cc:247-459).  The reference's schedule is restated here in Python on top of the
+    oracle's fine-grained API (4 x [restart from mTcw, optimize(10), computeError on the outliers, float chi2 test],
+    robust kernels dropped after the third round) and run on the graph the shim flattened."""
+    import shim_lib
+    A = ppo.abi
+    L = _backend(backend)
+    g, truth = ppo.synth.make_graph(ppo.synth.config(0, n_kf=10, n_fixed=2, n_pt=1500), with_truth=True)
+    a = {k: v.copy() for k, v in g.a.items()}
+    a["pt_xyz"] = truth.pt_xyz.copy()  # a tracked frame sees an already optimised map; its own pose is the noisy prediction
+    g = A.GraphArrays(**a)
+    kf = 6
+    pose, outl, counts, flat, rc = shim_lib.run_pose(g, kf, backend=L)
+    assert rc == 0
+    n = int((g["pe_kf"] == kf).sum())
+    assert n > 100 and counts[2] == n and counts[1] == 1
+    # the flattened problem: one free pose, every associated map point fixed, one edge each (features without a point skipped)
+    assert (flat.c.n_kf, flat.c.n_pt, flat.c.n_pe) == (1, n, n) and flat["pt_fixed"].all() and not flat["kf_fixed"].any()
+    sel = np.flatnonzero(g["pe_kf"] == kf)
+    assert np.array_equal(flat["pe_obs"], g["pe_obs"][sel])
+    o = oracle_mod.Oracle()
+    o.params.solver = A.SOLVER_6_3
+    o.set_graph(flat)
+    flags = np.full(n, A.EF_ROBUST, np.uint8)
+    mono = flat["pe_obs"][:, 2] < 0
+    th = np.where(mono, np.float32(5.991), np.float32(7.815))
+    n_bad = 0
+    for it in range(4):
+        o.reset()
+        o.set_edge_flags(A.EDGE_POINT, flags)
+        o.optimize(10)
+        o.recompute_edge_errors(A.EDGE_POINT)
+        chi2, _, _ = o.edge_chi2(A.EDGE_POINT)
+        out = chi2.astype(np.float32) > th
+        n_bad = int(out.sum())
+        flags = ((flags & A.EF_ROBUST) | np.where(out, A.EF_LEVEL1, 0)).astype(np.uint8)
+        if it == 2:
+            flags &= np.uint8(~A.EF_ROBUST & 0xFF)
+    want = o.get_state().kf_pose[0]
+    assert np.array_equal(outl.astype(bool), out)
+    assert counts[0] == n - n_bad
+    assert np.abs(pose - want).max() < 5e-6  # Frame::mTcw is float32
+    # and it does what it is for: the gross outliers of the synthetic window are rejected, the pose moves
+    assert 0.01 < n_bad / n < 0.2
+    assert np.abs(pose - truth.kf_pose[kf]).max() < 0.2 * np.abs(g["kf_pose"][kf] - truth.kf_pose[kf]).max()
+
+
+def test_pose_optimization_needs_three_correspondences(ppo):
+    import shim_lib
+    g = ppo.synth.make_graph(ppo.synth.config(0, n_kf=4, n_fixed=1, n_pt=2))
+    pose, outl, counts, flat, rc = shim_lib.run_pose(g, 1, backend=shim_lib.oracle_backed_lib())
+    assert counts[0] == 0 and counts[1] == 0  # Optimizer.cc:371-372: returns 0, no SetPose
