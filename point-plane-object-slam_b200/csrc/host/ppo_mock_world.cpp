@@ -23,6 +23,11 @@ double plane_angle_info = 1.0, plane_dist_info = 100.0, plane_chi = 500.0, cuboi
 
 using namespace ORB_SLAM2;
 
+// test options of the mock map: every `bad_point_every`-th map point and key-frame slot `bad_kf` are flagged isBad()
+// (0 / -1: none); they must be left out of the graph and untouched by the write-back
+static int g_bad_point_every = 0, g_bad_kf = -1;
+extern "C" void ppo_mock_set_options(int bad_point_every, int bad_kf) { g_bad_point_every = bad_point_every, g_bad_kf = bad_kf; }
+
 extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int fixPoint, unsigned char *stop, ppo_ba_state *out,
                             int32_t counts[4] /* erased point obs, erased plane obs, SetPose calls, UpdateNormalAndDepth calls */) {
   std::vector<std::unique_ptr<KeyFrame>> kfs;
@@ -51,6 +56,7 @@ extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int
       for (int c = 0; c < 4; c++) m.at<float>(r, c) = T[4 * r + c];
     kf->Tcw = m;
     kf->mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + 8);
+    kf->mbBad = i == g_bad_kf;
   }
   auto is_local = [&](int i) { return i == 0 || !g->kf_fixed[i]; };
   int pkf = -1;
@@ -64,6 +70,7 @@ extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int
     pts.emplace_back(new MapPoint());
     MapPoint *mp = pts.back().get();
     mp->mnId = p;
+    mp->mbBad = g_bad_point_every > 0 && p % g_bad_point_every == g_bad_point_every - 1;
     cv::Mat X(3, 1, CV_32F);
     for (int k = 0; k < 3; k++) X.at<float>(k, 0) = (float)g->pt_xyz[3 * p + k];
     mp->mWorldPos = X;

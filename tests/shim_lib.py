@@ -16,6 +16,8 @@ _ORACLE_LIB = None
 
 
 def _declare(L):
+    L.ppo_mock_set_options.argtypes = [C.c_int, C.c_int]
+    L.ppo_mock_set_options.restype = None
     L.ppo_mock_run.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
     L.ppo_mock_run_global.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_ulong, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
     L.ppo_shim_last_result.restype = C.POINTER(A.Result)

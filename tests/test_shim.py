@@ -215,3 +215,33 @@ def test_pose_optimization_needs_three_correspondences(ppo):
     g = ppo.synth.make_graph(ppo.synth.config(0, n_kf=4, n_fixed=1, n_pt=2))
     pose, outl, counts, flat, rc = shim_lib.run_pose(g, 1, backend=shim_lib.oracle_backed_lib())
     assert counts[0] == 0 and counts[1] == 0  # Optimizer.cc:371-372: returns 0, no SetPose
+
+
+def test_bad_points_and_keyframes_are_left_out_and_untouched(ppo, oracle_mod):
+    """isBad() map points (Optimizer.cc:2040-2047) and key-frames (:2008-2010, :2063-2068, :2352) never reach the graph and are
+    not written back; the run equals the oracle on the graph the shim flattened.  Oracle-backed shim: CPU only."""
+    import shim_lib
+    L = shim_lib.oracle_backed_lib()
+    g = _graph(ppo)
+    bad_kf = int(np.flatnonzero(g["kf_fixed"] == 0)[3])  # a free (local) key-frame, not the one the BA is called for
+    L.ppo_mock_set_options(5, bad_kf)
+    try:
+        st, counts, flat = shim_lib.run(g, backend=L)
+    finally:
+        L.ppo_mock_set_options(0, -1)
+    assert L.ppo_shim_last_rc() == 0
+    assert flat.c.n_kf == g.c.n_kf - 1  # the bad key-frame has no vertex
+    bad_pts = np.arange(g.c.n_pt) % 5 == 4
+    good_xyz = {tuple(np.round(r, 6)) for r in g["pt_xyz"][~bad_pts].astype(np.float32)}
+    assert all(tuple(np.round(r, 6)) in good_xyz for r in flat["pt_xyz"].astype(np.float32))  # no bad point in the graph
+    assert np.array_equal(st.pt_xyz[bad_pts], g["pt_xyz"][bad_pts].astype(np.float32))      # and none was moved
+    assert np.allclose(st.kf_pose[bad_kf], g["kf_pose"][bad_kf], atol=2e-7)                 # nor the bad key-frame
+    assert (flat["pe_kf"] < flat.c.n_kf).all()
+    o = oracle_mod.Oracle()
+    o.set_graph(flat)
+    ro = o.local_ba()
+    res = L.ppo_shim_last_result().contents
+    assert (res.round1.iterations, res.round2.iterations) == (ro.round1.iterations, ro.round2.iterations)
+    assert np.isclose(res.round2.chi2_final, ro.round2.chi2_final, rtol=1e-9)
+    keep = np.arange(g.c.n_kf) != bad_kf
+    assert np.abs(st.kf_pose[keep] - o.get_state().kf_pose).max() < 5e-6
