@@ -245,3 +245,29 @@ def test_bad_points_and_keyframes_are_left_out_and_untouched(ppo, oracle_mod):
     assert np.isclose(res.round2.chi2_final, ro.round2.chi2_final, rtol=1e-9)
     keep = np.arange(g.c.n_kf) != bad_kf
     assert np.abs(st.kf_pose[keep] - o.get_state().kf_pose).max() < 5e-6
+
+
+@pytest.mark.parametrize("fix_camera,fix_point", [(True, False), (False, True)])
+def test_fix_camera_and_fix_point_arguments(ppo, oracle_mod, fix_camera, fix_point):
+    """LocalBACameraPlaneCuboids(pKF, stop, map, fixCamera, fixPoint) (Optimizer.cc:2126-2128, 2155): the flag fixes every
+    local key-frame / every map point vertex; the other side is still optimised.  Oracle-backed shim: CPU only."""
+    import shim_lib
+    L = shim_lib.oracle_backed_lib()
+    g = _graph(ppo)
+    st, counts, flat = shim_lib.run(g, fix_camera=fix_camera, fix_point=fix_point, backend=L)
+    assert L.ppo_shim_last_rc() == 0
+    if fix_camera:
+        assert flat["kf_fixed"].all()
+        assert np.allclose(st.kf_pose, g["kf_pose"], atol=2e-7)  # SetPose with the unchanged estimate (float32 round trip)
+        assert (np.abs(st.pt_xyz - g["pt_xyz"]).max(axis=1) > 1e-6).mean() > 0.9  # the points are still optimised
+    else:
+        assert flat["pt_fixed"].all()
+        assert np.allclose(st.pt_xyz, g["pt_xyz"].astype(np.float32), atol=0)
+        n_free = int((flat["kf_fixed"] == 0).sum())
+        assert (np.abs(st.kf_pose - g["kf_pose"]).max(axis=1) > 1e-6).sum() >= n_free - 1
+    o = oracle_mod.Oracle()
+    o.set_graph(flat)
+    ro = o.local_ba()
+    res = L.ppo_shim_last_result().contents
+    assert (res.round1.iterations, res.round2.iterations) == (ro.round1.iterations, ro.round2.iterations)
+    assert np.abs(st.kf_pose - o.get_state().kf_pose).max() < 5e-6
