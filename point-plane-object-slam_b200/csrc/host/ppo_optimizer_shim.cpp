@@ -131,9 +131,16 @@ static Flat g_last;  // last flattened window (introspection for tests / logging
 static ppo_ba_result g_last_result;
 static int g_last_rc = 0;
 
+// The reference's tuning globals are re-snapshotted on every call; the engine handle (streams, events, pinned staging,
+// the device memory pool) is kept across calls and only re-created when a parameter or the device actually changed.
+static ppo_ba_params g_handle_params;
+static int g_handle_device = -1;
 static ppo_ba_handle *engine(const ppo_ba_params &P) {
-  if (g_handle) ppo_ba_destroy(g_handle), g_handle = nullptr;  // parameters are re-snapshotted per call like the reference's globals
+  if (g_handle && g_handle_device == g_device && std::memcmp(&g_handle_params, &P, sizeof P) == 0) return g_handle;
+  if (g_handle) ppo_ba_destroy(g_handle), g_handle = nullptr;
   if (ppo_ba_create(&P, g_device, &g_handle) != PPO_OK) g_handle = nullptr;
+  g_handle_params = P;
+  g_handle_device = g_device;
   return g_handle;
 }
 
