@@ -464,10 +464,13 @@ __global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n
 
 void dense_cholesky_solve(double *S, int n, int ld, double *x, double *Winv, int *not_spd, cudaStream_t st, long long *launches) {
   if (n <= 0) return;
-  static bool attr_set = false;  // per process; opting in is idempotent
-  if (!attr_set) {
+  // opting in to > 48 KB of dynamic shared memory is a per-device function attribute
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyrkSmem));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int rows_total = n + 1;  // rows 0..n (row n carries the gradient)
   launch_pdl(k_potrf_inv, dim3(1), dim3(PF_THREADS), 0, st, S, ld, 0, n < NB ? n : NB, Winv, not_spd);
