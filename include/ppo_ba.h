@@ -209,6 +209,13 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *g);
 int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *stop_flag,
                     ppo_ba_stats *stats);
 
+/* Batch variants: n independent windows (one handle each, possibly on different devices) optimised concurrently;
+ * every handle runs its own host-driven LM loop on its own stream, so the latency-bound phases of one window
+ * overlap the others (BASELINE configs[3]: many independent key-frame windows).  stats / res are arrays of n.
+ * Returns the first non-zero error code of any window (all windows are always run to completion). */
+int ppo_ba_optimize_batch(ppo_ba_handle **h, int n, int iters, const volatile unsigned char *stop_flag, ppo_ba_stats *stats);
+int ppo_ba_local_ba_batch(ppo_ba_handle **h, int n, const volatile unsigned char *stop_flag, ppo_ba_result *res);
+
 /* e->chi2() of every edge of a kind as g2o holds it after the last computeActiveErrors
  * (stale for level-1 edges and after a rejected last trial), and
  * e->isDepthPositive() from the current estimates (point edges; plane edges: distance()>0).

@@ -93,7 +93,7 @@ def build_cuda(force=False):
                     nccl_link = ["-L", lib, "-l:" + so[0], "-Xlinker", "-rpath=" + lib]
         except Exception:
             pass
-        _run([nvcc] + NVCC_FLAGS + nccl_inc + ["-shared", "-o", out] + cu + nccl_link + ["-lcudart"])
+        _run([nvcc] + NVCC_FLAGS + nccl_inc + ["-shared", "-o", out] + cu + nccl_link + ["-lcudart", "-lpthread"])
     return out
 
 

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/ppo_ba.h"
@@ -179,6 +180,21 @@ struct ppo_ba_handle {
 };
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- batch variants: one host thread per window drives that window's LM loop on its own stream ------------------
+template <typename F>
+static int run_batch(int n, F &&one) {
+  if (n < 0) return PPO_E_INVALID;
+  std::vector<int> rc((size_t)std::max(n, 1), PPO_OK);
+  std::vector<std::thread> th;
+  th.reserve((size_t)std::max(n - 1, 0));
+  for (int i = 1; i < n; i++) th.emplace_back([&rc, &one, i] { rc[i] = one(i); });
+  if (n > 0) rc[0] = one(0);
+  for (auto &t : th) t.join();
+  for (int i = 0; i < n; i++)
+    if (rc[i] != PPO_OK) return rc[i];
+  return PPO_OK;
+}
 
 extern "C" {
 
@@ -1014,6 +1030,16 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
     stats->n_active_edges = h->n_active_edges;
   }
   return PPO_OK;
+}
+
+// ---- batch variants (run_batch above): one host thread per window drives that window's LM loop on its own stream --------
+int ppo_ba_optimize_batch(ppo_ba_handle **h, int n, int iters, const volatile unsigned char *stop, ppo_ba_stats *stats) {
+  if (!h || (n > 0 && !stats)) return PPO_E_INVALID;
+  return run_batch(n, [=](int i) { return ppo_ba_optimize(h[i], iters, stop, &stats[i]); });
+}
+int ppo_ba_local_ba_batch(ppo_ba_handle **h, int n, const volatile unsigned char *stop, ppo_ba_result *res) {
+  if (!h || (n > 0 && !res)) return PPO_E_INVALID;
+  return run_batch(n, [=](int i) { return ppo_ba_local_ba(h[i], stop, &res[i]); });
 }
 
 int ppo_ba_recompute_edge_errors(ppo_ba_handle *h, int kind) {

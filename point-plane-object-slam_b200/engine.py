@@ -241,6 +241,21 @@ class LocalBA(Handle):
     LocalBundleAdjustment = LocalBACameraPlaneCuboids
 
 
+def local_ba_batch(engines, stop_flag=None):
+    """ppo_ba_local_ba_batch: the windows of several LocalBA handles optimised concurrently (one host thread each inside
+    the library).  Returns the list of ppo_ba_result."""
+    lib = load_library()
+    n = len(engines)
+    hs = (C.c_void_p * n)(*[e.h for e in engines])
+    res = (A.Result * n)()
+    lib.ppo_ba_local_ba_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(A.Result)]
+    sp = stop_flag.ctypes.data if stop_flag is not None else None
+    rc = lib.ppo_ba_local_ba_batch(hs, n, sp, res)
+    if rc != A.PPO_OK:
+        raise EngineError(f"ppo_ba_local_ba_batch failed: rc={rc}")
+    return list(res)
+
+
 def nccl_unique_id():
     buf = C.create_string_buffer(128)
     rc = load_library().ppo_ba_nccl_unique_id(buf)

@@ -340,3 +340,23 @@ def test_size_independent_properties_at_full_size(ppo):
     assert np.isclose(rp_.round2.chi2_final, r.round2.chi2_final, rtol=1e-6)
     assert np.abs(sp.kf_pose - s1.kf_pose).max() < 1e-6
     assert close_points(sp.pt_xyz, s1.pt_xyz[perm])
+
+
+def test_batch_variant_equals_one_window_at_a_time(ppo):
+    """ppo_ba_local_ba_batch (batch variant of the C-ABI): three different windows optimised concurrently give
+    what each gives alone."""
+    graphs = [ppo.synth.make_graph(ppo.synth.config(1, window=w, n_kf=12 + 2 * w, n_pt=1500 + 300 * w, n_pl=6, n_cu=3)) for w in range(3)]
+    alone = []
+    for g in graphs:
+        e = ppo.LocalBA()
+        e.set_graph(g)
+        r = e.local_ba()
+        alone.append((r.round1.iterations, r.round2.iterations, r.round2.chi2_final, r.n_outlier_point_edges, e.get_state().kf_pose.copy()))
+    engines = [ppo.LocalBA() for _ in graphs]
+    for e, g in zip(engines, graphs):
+        e.set_graph(g)
+    res = ppo.local_ba_batch(engines)
+    for e, r, a in zip(engines, res, alone):
+        assert (r.round1.iterations, r.round2.iterations, r.n_outlier_point_edges) == (a[0], a[1], a[3])
+        assert np.isclose(r.round2.chi2_final, a[2], rtol=1e-7)
+        assert np.abs(e.get_state().kf_pose - a[4]).max() < 1e-6
