@@ -586,3 +586,35 @@ def test_full_schedule_against_numpy_reimplementation(ppo, oracle_mod, inject):
     assert np.abs(s.pt_xyz - cur["pt_xyz"]).max() < 5e-5
     assert np.abs(s.pl_coef - cur["pl_coef"]).max() < 5e-6
     assert np.abs(s.cu_state - cur["cu_state"]).max() < 5e-5
+
+
+def test_levelled_out_edges_keep_their_round1_error(ppo, oracle_mod):
+    """level-1 edges are inactive in round 2, computeActiveErrors never refreshes them, so the erase test
+    of Optimizer.cc:2856-2881 reads their ROUND-1 chi2; active edges are refreshed.  isDepthPositive uses the final
+    estimates.  Points whose every edge was levelled out keep their round-1 position (dropped from the index mapping)."""
+    A = ppo.abi
+    g = ppo.synth.make_graph(ppo.synth.config(0, n_kf=8, n_fixed=2, n_pt=400))
+    o = oracle_mod.Oracle()
+    o.params.solver = A.SOLVER_6_3
+    o.set_graph(g)
+    o.optimize(5)
+    chi_r1, _, _ = o.edge_chi2(A.EDGE_POINT)
+    pts_r1 = o.get_state().pt_xyz.copy()
+    n_out = o.outlier_pass()
+    flags = o.get_edge_flags(A.EDGE_POINT)
+    lvl1 = (flags & A.EF_LEVEL1) != 0
+    assert lvl1.sum() == n_out[0] > 0 and not (flags & A.EF_ROBUST).any()  # kernels dropped on every point edge (:2752,2768)
+    mono = g["pe_obs"][:, 2] < 0
+    assert np.array_equal(lvl1, (chi_r1 > np.where(mono, 5.991, 7.815)) | (o.edge_chi2(A.EDGE_POINT)[1] == 0))
+    o.optimize(10)
+    chi_r2, _, _ = o.edge_chi2(A.EDGE_POINT)
+    assert np.array_equal(chi_r2[lvl1], chi_r1[lvl1])                 # stale: exactly the round-1 values
+    assert (chi_r2[~lvl1] != chi_r1[~lvl1]).mean() > 0.99             # refreshed
+    # a point that lost all its edges is no longer a vertex of round 2: it keeps its round-1 estimate
+    rp = g["pt_rowptr"]
+    dropped = [p for p in range(g.c.n_pt) if lvl1[rp[p]:rp[p + 1]].all()]
+    pts_r2 = o.get_state().pt_xyz
+    for p in dropped:
+        assert np.array_equal(pts_r2[p], pts_r1[p])
+    moved = np.abs(pts_r2 - pts_r1).max(axis=1) > 0
+    assert moved.sum() >= g.c.n_pt - len(dropped) - 5
