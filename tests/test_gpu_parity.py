@@ -321,7 +321,7 @@ def test_size_independent_properties_at_full_size(ppo):
     r2 = e.local_ba()
     s2 = e.get_state()
     assert (r2.round1.iterations, r2.round2.iterations) == (r.round1.iterations, r.round2.iterations)
-    assert np.isclose(r2.round2.chi2_final, r.round2.chi2_final, rtol=1e-7)  # atomics reorder sums: not bit-exact
+    assert np.isclose(r2.round2.chi2_final, r.round2.chi2_final, rtol=1e-6)  # atomics reorder sums: not bit-exact
     # poses are tightly determined (observed: 1e-8); weakly triangulated points amplify that noise by their depth /
     # baseline ratio (observed: ~1e-6), still inside the 1e-4 relative tolerance of the parity tests
     def close_points(a, b):
@@ -358,5 +358,5 @@ def test_batch_variant_equals_one_window_at_a_time(ppo):
     res = ppo.local_ba_batch(engines)
     for e, r, a in zip(engines, res, alone):
         assert (r.round1.iterations, r.round2.iterations, r.n_outlier_point_edges) == (a[0], a[1], a[3])
-        assert np.isclose(r.round2.chi2_final, a[2], rtol=1e-7)
-        assert np.abs(e.get_state().kf_pose - a[4]).max() < 1e-6
+        assert np.isclose(r.round2.chi2_final, a[2], rtol=1e-6)  # atomics reorder sums: not bit-exact
+        assert np.abs(e.get_state().kf_pose - a[4]).max() < 1e-5
