@@ -74,3 +74,15 @@ def test_synth_is_deterministic_and_matches_survey_sizes(ppo):
     assert g1.c.n_kf == 12 and g1.c.n_pt == 2000 and abs(g1.c.n_pe - 12000) < 100
     assert g1["kf_fixed"].sum() == 3  # id 0 + 2 fixed cameras
     assert not np.array_equal(ppo.synth.make_graph(ppo.synth.config(3, window=1))["pt_xyz"], ppo.synth.make_graph(ppo.synth.config(3, window=2))["pt_xyz"])
+
+
+def test_product_libraries_never_reference_the_oracle(built):
+    """The oracle is test infrastructure: no product library may link it or import one of its symbols (the oracle-backed
+    shim of tests/shim_lib.py lives under oracle/_build, not under the package's lib/)."""
+    for key in ("cuda", "shim", "synth"):
+        path = built[key]
+        syms = subprocess.check_output(["nm", "-D", path], text=True)
+        assert "ppo_oracle" not in syms, path
+        needed = subprocess.check_output(["readelf", "-d", path], text=True)
+        assert "libppo_oracle" not in needed, path
+    assert not any("oracle" in f for f in os.listdir(os.path.dirname(built["cuda"])))
