@@ -24,6 +24,9 @@
 #include <cstdlib>
 #include <limits>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../include/ppo_ba.h"
 #include "ppo_oracle_math.h"
@@ -219,6 +222,11 @@ struct ppo_oracle_handle {
     }
     return -1;
   }
+  // Host threads (OpenMP).  1 = the reference's configuration (g2o is built without OpenMP, Thirdparty/g2o/config.h:4): every
+  // loop then runs in the original order and all results are bit-reproducible.  > 1 is a reported variant only
+  // ("not the reference configuration"): errors, point-edge linearisation, Schur rows, the dense factorisation's
+  // row updates and the back-substitution run in parallel; partial sums are combined in thread order.
+  int threads = 1;
   bool lvl0(int kind, int e) const { return !(ef[kind][e] & PPO_EF_LEVEL1); }
   bool robust(int kind, int e) const { return ef[kind][e] & PPO_EF_ROBUST; }
   bool pe_active(int e) const { return lvl0(PPO_EDGE_POINT, e) && !(kf_fixed[pe_kf[e]] && pt_fixed[pe_pt[e]]); }
@@ -352,6 +360,7 @@ struct ppo_oracle_handle {
   }
   // core/sparse_optimizer.cpp:61-76
   void compute_active_errors() {
+#pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
     for (int e = 0; e < n_pe; e++)
       if (pe_active(e)) pe_eval(e, &pe_err[3 * e]);
     for (int e = 0; e < n_ple; e++)
@@ -407,6 +416,76 @@ struct ppo_oracle_handle {
       bv[a] += s;
     }
   }
+  // threaded variant of the point-edge part of build_system: a thread owns whole points (their Hll / b_l / Hpl blocks are
+  // private to the point); the pose-side 6x6 diagonal blocks and gradients go to per-thread buffers summed in thread order
+  void build_system_points_mt() {
+    const int T = threads;
+    std::vector<std::vector<double>> Hk(T, std::vector<double>(36 * (size_t)n_kf, 0.0)), bk(T, std::vector<double>(6 * (size_t)n_kf, 0.0));
+#pragma omp parallel num_threads(T)
+    {
+      int t = 0;
+#ifdef _OPENMP
+      t = omp_get_thread_num();
+#endif
+      double *Ht = Hk[t].data(), *bt = bk[t].data();
+#pragma omp for schedule(static)
+      for (int p = 0; p < n_pt; p++) {
+        for (int e = pt_rowptr[p]; e < pt_rowptr[p + 1]; e++) {
+          if (!pe_active(e)) continue;
+          const int k = pe_kf[e];
+          const bool stereo = pe_obs[3 * e + 2] >= 0;
+          const int D = stereo ? 3 : 2;
+          double Jpt[9], Jkf[18];
+          point_edge_jacobian(kf[k], pt[p], &kf_intr[5 * k], stereo, Jpt, Jkf);
+          double w[3], rho1 = 1.0;
+          if (robust(PPO_EDGE_POINT, e)) {
+            double rho[3];
+            huber(chi2_of(PPO_EDGE_POINT, e), delta_of(PPO_EDGE_POINT, e), rho);
+            rho1 = rho[1];
+          }
+          for (int i = 0; i < 3; i++) w[i] = rho1 * (double)pe_invsigma2[e];
+          const double *err = &pe_err[3 * e];
+          const int l = pt_l[p], ko = kf_off[k];
+          if (l >= 0) {
+            for (int a = 0; a < 3; a++)
+              for (int c = 0; c < 3; c++) {
+                double sacc = 0;
+                for (int r = 0; r < D; r++) sacc += Jpt[r * 3 + a] * w[r] * Jpt[r * 3 + c];
+                Hll[9 * (size_t)l + 3 * a + c] += sacc;
+              }
+            add_b(&b[n_p + 3 * (size_t)l], 3, Jpt, D, w, err);
+          }
+          if (ko >= 0) {
+            for (int a = 0; a < 6; a++)
+              for (int c = 0; c < 6; c++) {
+                double sacc = 0;
+                for (int r = 0; r < D; r++) sacc += Jkf[r * 6 + a] * w[r] * Jkf[r * 6 + c];
+                Ht[36 * (size_t)k + 6 * a + c] += sacc;
+              }
+            add_b(&bt[6 * (size_t)k], 6, Jkf, D, w, err);
+            if (l >= 0) {
+              double *m = Hpl[l][pe_blk[e]].m;
+              for (int a = 0; a < 6; a++)
+                for (int c = 0; c < 3; c++) {
+                  double sacc = 0;
+                  for (int r = 0; r < D; r++) sacc += Jkf[r * 6 + a] * w[r] * Jpt[r * 3 + c];
+                  m[a * 3 + c] += sacc;
+                }
+            }
+          }
+        }
+      }
+    }
+    for (int t = 0; t < T; t++)
+      for (int k = 0; k < n_kf; k++) {
+        const int ko = kf_off[k];
+        if (ko < 0) continue;
+        for (int a = 0; a < 6; a++) {
+          for (int c = 0; c < 6; c++) Hpp[(size_t)(ko + a) * n_p + (ko + c)] += Hk[t][36 * (size_t)k + 6 * a + c];
+          b[ko + a] += bk[t][6 * (size_t)k + a];
+        }
+      }
+  }
   // ---- BlockSolver::buildSystem core/block_solver.hpp:502-560 -----------------------------------
   void build_system() {
     std::fill(Hpp.begin(), Hpp.end(), 0.0);
@@ -415,8 +494,9 @@ struct ppo_oracle_handle {
     for (auto &v : Hpl)
       for (auto &bk : v) std::memset(bk.m, 0, sizeof bk.m);
     const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+    if (threads > 1) build_system_points_mt();
     // point edges: analytic Jacobians
-    for (int e = 0; e < n_pe; e++) {
+    for (int e = 0; e < (threads > 1 ? 0 : n_pe); e++) {
       if (!pe_active(e)) continue;
       int k = pe_kf[e], p = pe_pt[e];
       bool stereo = pe_obs[3 * e + 2] >= 0;
@@ -610,6 +690,7 @@ struct ppo_oracle_handle {
       if (!(dj > 0.0)) return false;
       d[j] = dj;
       double inv = 1.0 / dj;
+#pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1 && n - j > 64)
       for (int i = j + 1; i < n; i++) {
         double *Ai = &A[(size_t)i * n];
         double s = Ai[j];
@@ -631,12 +712,57 @@ struct ppo_oracle_handle {
     }
     return true;
   }
+  // threaded Schur complement: Dinv per landmark in parallel, then every thread owns the pose block rows i1 with
+  // (pose index % T == t) and scans all landmarks for them: no two threads write the same entry, no reduction needed
+  void schur_mt(double lam, std::vector<double> &coeff) {
+    const int T = threads;
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int l = 0; l < n_l; l++) {
+      double D[9];
+      for (int i = 0; i < 9; i++) D[i] = Hll[9 * (size_t)l + i];
+      D[0] += lam;
+      D[4] += lam;
+      D[8] += lam;
+      inv3(D, &Dinv[9 * (size_t)l]);
+    }
+#pragma omp parallel num_threads(T)
+    {
+      int t = 0;
+#ifdef _OPENMP
+      t = omp_get_thread_num();
+#endif
+      for (int l = 0; l < n_l; l++) {
+        const double *Di = &Dinv[9 * (size_t)l];
+        const double *bl = &b[n_p + 3 * (size_t)l];
+        auto &blocks = Hpl[l];
+        for (size_t i1 = 0; i1 < blocks.size(); i1++) {
+          if (blocks[i1].pose % T != t) continue;
+          double db[3];
+          for (int i = 0; i < 3; i++) db[i] = Di[3 * i] * bl[0] + Di[3 * i + 1] * bl[1] + Di[3 * i + 2] * bl[2];
+          const double *Bi = blocks[i1].m;
+          double BDinv[18];
+          for (int a = 0; a < 6; a++)
+            for (int c = 0; c < 3; c++) BDinv[a * 3 + c] = Bi[a * 3] * Di[c] + Bi[a * 3 + 1] * Di[3 + c] + Bi[a * 3 + 2] * Di[6 + c];
+          const int o1 = blocks[i1].pose * 6;
+          for (int a = 0; a < 6; a++) coeff[o1 + a] += Bi[a * 3] * db[0] + Bi[a * 3 + 1] * db[1] + Bi[a * 3 + 2] * db[2];
+          for (size_t i2 = i1; i2 < blocks.size(); i2++) {
+            const double *Bj = blocks[i2].m;
+            const int o2 = blocks[i2].pose * 6;
+            for (int a = 0; a < 6; a++)
+              for (int c = 0; c < 6; c++)
+                Hschur[(size_t)(o1 + a) * n_p + (o2 + c)] -= BDinv[a * 3] * Bj[c * 3] + BDinv[a * 3 + 1] * Bj[c * 3 + 1] + BDinv[a * 3 + 2] * Bj[c * 3 + 2];
+          }
+        }
+      }
+    }
+  }
   // ---- setLambda + BlockSolver::solve + restoreDiagonal (core/block_solver.hpp:354-486,564-604) --
   bool solve_damped(double lam) {
     Hschur = Hpp;
     for (int i = 0; i < n_p; i++) Hschur[(size_t)i * n_p + i] += lam;
     std::vector<double> coeff(n_p, 0.0);
-    for (int l = 0; l < n_l; l++) {
+    if (threads > 1) schur_mt(lam, coeff);
+    for (int l = 0; l < (threads > 1 ? 0 : n_l); l++) {
       double D[9];
       for (int i = 0; i < 9; i++) D[i] = Hll[9 * (size_t)l + i];
       D[0] += lam;
@@ -667,6 +793,7 @@ struct ppo_oracle_handle {
     for (int i = 0; i < n_p; i++) bschur[i] = b[i] - coeff[i];
     if (n_p > 0 && !dense_solve(Hschur, bschur.data(), x.data())) return false;
     // xl = Dinv (bl - Hpl^T xp)
+#pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
     for (int l = 0; l < n_l; l++) {
       double cl[3] = {b[n_p + 3 * (size_t)l], b[n_p + 3 * (size_t)l + 1], b[n_p + 3 * (size_t)l + 2]};
       for (auto &bk : Hpl[l]) {
@@ -991,6 +1118,13 @@ int ppo_oracle_edge_chi2(ppo_oracle_handle *h, int kind, double *chi2, unsigned 
       err_norm[e] = std::sqrt(s);
     }
   }
+  return PPO_OK;
+}
+
+// host threads of this handle (1 = reference configuration, the default)
+int ppo_oracle_set_threads(ppo_oracle_handle *h, int n) {
+  if (!h || n < 1) return PPO_E_INVALID;
+  h->threads = n;
   return PPO_OK;
 }
 

@@ -65,7 +65,7 @@ def build_oracle(force=False):
     deps = srcs + [os.path.join(ORACLE, "ppo_oracle_math.h"), os.path.join(ROOT, "include", "ppo_ba.h")]
     if force or _newer(out, deps):
         # -ffp-contract=off: same arithmetic as the reference build (no FMA contraction on x86-64 -O2/-O3 without -march)
-        _run(["g++", "-O3", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", out] + srcs)
+        _run(["g++", "-O3", "-std=c++17", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", out] + srcs)
     return out
 
 

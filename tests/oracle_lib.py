@@ -21,6 +21,7 @@ def lib():
         ppo.engine._bind(L, "ppo_oracle_")
         L.ppo_oracle_create.argtypes = [C.POINTER(A.Params), C.POINTER(C.c_void_p)]
         L.ppo_oracle_debug_linearize.argtypes = [C.c_void_p, C.POINTER(C.c_int32 * 2), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ppo_oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
         L.ppo_oracle_debug_solve.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         _LIB = L
     return _LIB
@@ -38,3 +39,7 @@ class Oracle(ppo.Handle):
         assert L.ppo_oracle_create(C.byref(p), C.byref(h)) == 0
         super().__init__(L, "ppo_oracle_", h)
         self.params = p
+
+    def set_threads(self, n):
+        """Host threads of the oracle (1 = the reference's single-threaded g2o configuration, the default)."""
+        assert self.lib.ppo_oracle_set_threads(self.h, int(n)) == 0

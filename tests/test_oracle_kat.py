@@ -618,3 +618,22 @@ def test_levelled_out_edges_keep_their_round1_error(ppo, oracle_mod):
         assert np.array_equal(pts_r2[p], pts_r1[p])
     moved = np.abs(pts_r2 - pts_r1).max(axis=1) > 0
     assert moved.sum() >= g.c.n_pt - len(dropped) - 5
+
+
+def test_threaded_oracle_variant_agrees_with_the_single_threaded_one(ppo, oracle_mod):
+    """The OpenMP variant (reported next to the reference-configuration baseline) must give the single-threaded
+    oracle's answer up to summation order: same schedule and outlier sets, estimates within 1e-6."""
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=16, n_pt=3000, n_pl=8, n_cu=4))
+    runs = []
+    for threads in (1, 4):
+        o = oracle_mod.Oracle()
+        o.set_threads(threads)
+        o.set_graph(g)
+        r = o.local_ba()
+        runs.append((r, o.get_state(), [o.get_edge_flags(k) for k in range(ppo.abi.EDGE_KINDS)]))
+    (ra, sa, fa), (rb, sb, fb) = runs
+    assert (ra.round1.iterations, ra.round2.iterations) == (rb.round1.iterations, rb.round2.iterations)
+    assert all(np.array_equal(x, y) for x, y in zip(fa, fb))
+    assert np.isclose(ra.round2.chi2_final, rb.round2.chi2_final, rtol=1e-7)
+    assert np.abs(sa.kf_pose - sb.kf_pose).max() < 1e-7 and np.abs(sa.pt_xyz - sb.pt_xyz).max() < 1e-4
+    assert np.abs(sa.pl_coef - sb.pl_coef).max() < 1e-6 and np.abs(sa.cu_state - sb.cu_state).max() < 1e-6
