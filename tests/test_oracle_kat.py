@@ -636,4 +636,4 @@ def test_threaded_oracle_variant_agrees_with_the_single_threaded_one(ppo, oracle
     assert all(np.array_equal(x, y) for x, y in zip(fa, fb))
     assert np.isclose(ra.round2.chi2_final, rb.round2.chi2_final, rtol=1e-7)
     assert np.abs(sa.kf_pose - sb.kf_pose).max() < 1e-7 and np.abs(sa.pt_xyz - sb.pt_xyz).max() < 1e-4
-    assert np.abs(sa.pl_coef - sb.pl_coef).max() < 1e-6 and np.abs(sa.cu_state - sb.cu_state).max() < 1e-6
+    assert np.abs(sa.pl_coef - sb.pl_coef).max() < 1e-6 and np.abs(sa.cu_state - sb.cu_state).max() < 1e-4  # cuboids: numeric Jacobians
