@@ -159,11 +159,18 @@ def run_reference(args, rank, world, out_stream):
         tot_t += dt
     v = tot_it / tot_t
     sample = f"round 1 only (optimize({5}) = {tot_it // max(1, args.steps)} LM iterations) of the same window per step"
+    mt = None
+    try:  # for information: the oracle's OpenMP variant on all host cores (NOT the reference's configuration), one sample
+        nthr = os.cpu_count() or 1
+        v2, it2, dt2 = oracle_lm_rate(ppo, g, False, threads=nthr)
+        mt = {"value": v2, "unit": UNIT, "cores": nthr, "kind": "port, OpenMP variant (not the reference configuration)", "sample": sample}
+    except Exception as exc:
+        mt = {"error": str(exc)}
     print(file=out_stream, flush=True, *[json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": workload_name(args.config), "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}, "cpu_baseline_mt": mt,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})])
 
 
