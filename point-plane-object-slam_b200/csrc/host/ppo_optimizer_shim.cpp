@@ -20,6 +20,8 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <cstdio>
@@ -149,6 +151,10 @@ using namespace ORB_SLAM2;
 struct Window {
   std::vector<KeyFrame *> lLocalKeyFrames, lFixedCameras;
   std::vector<MapPoint *> lLocalMapPoints;
+  // one GetObservations() snapshot per local map point (the getter copies a std::map under a mutex: 80 k copies are a
+  // third of the host time of a 200-key-frame window), shared by the fixed-camera search and the edge flattening
+  std::vector<int> obs_ptr;                              // CSR over lLocalMapPoints
+  std::vector<std::pair<KeyFrame *, size_t>> obs;        // (key-frame, feature index) in std::map (pointer) order
   std::vector<MapCuboid *> lLocalMapCuboids;
   std::vector<MapPlane *> lLocalMapPlanes;
 };
@@ -190,9 +196,16 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w) {
       if (!pKFi->isBad()) w.lFixedCameras.push_back(pKFi);
     }
   };
+  w.obs_ptr.reserve(w.lLocalMapPoints.size() + 1);
+  w.obs.reserve(8 * w.lLocalMapPoints.size());
+  w.obs_ptr.push_back(0);
   for (MapPoint *pMP : w.lLocalMapPoints) {
-    std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
-    for (auto &mit : observations) add_fixed(mit.first);
+    const std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
+    for (auto &mit : observations) {
+      add_fixed(mit.first);
+      w.obs.push_back({mit.first, mit.second});
+    }
+    w.obs_ptr.push_back((int)w.obs.size());
   }
   if (mixed)
     for (MapCuboid *pMC : w.lLocalMapCuboids) {
@@ -203,8 +216,18 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w) {
 
 static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fixCamera, bool fixPoint) {
   std::lock_guard<std::mutex> lk(g_mutex);
+  // PPO_BA_TIMING=1: host-side phase times of this call on stderr (diagnostics only)
+  static const bool timing = std::getenv("PPO_BA_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto tick = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ppo shim] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   Window w;
   collect(pKF, mixed, w);
+  tick("collect window (stage A)");
 
   // ---- stage B: flatten (vertices) ------------------------------------------------------------------
   Flat &F = g_last;
@@ -216,8 +239,12 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   for (KeyFrame *kf : w.lFixedCameras) slots.push_back({kf, true});                        // :2141
   std::sort(slots.begin(), slots.end(), [](const Slot &a, const Slot &b) { return a.kf->mnId < b.kf->mnId; });
   std::map<KeyFrame *, int> kf_slot;
+  long unsigned int max_id = 0;
+  for (const Slot &sl : slots) max_id = std::max(max_id, sl.kf->mnId);
+  std::vector<int> slot_of_id(slots.empty() ? 0 : max_id + 1, -1);  // O(1) key-frame -> slot for the 10^5..10^6 point edges
   for (size_t i = 0; i < slots.size(); i++) {
     kf_slot[slots[i].kf] = (int)i;
+    slot_of_id[slots[i].kf->mnId] = (int)i;
     float T[16];
     double p7[7];
     mat_to_float16(slots[i].kf->GetPose(), T);
@@ -293,20 +320,26 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   // ---- points and reprojection edges :2332-2424 (mixed) / :560-650 (points only) ----------------------------
   std::vector<MapPoint *> graph_points;  // points that got a vertex (mixed: Observations() != 1, q1)
   std::vector<std::pair<KeyFrame *, MapPoint *>> point_edge_owner;
+  point_edge_owner.reserve(w.obs.size());
+  F.pe_kf.reserve(w.obs.size()); F.pe_obs.reserve(3 * w.obs.size()); F.pe_invsigma2.reserve(w.obs.size());
+  F.pt_xyz.reserve(3 * w.lLocalMapPoints.size()); F.pt_fixed.reserve(w.lLocalMapPoints.size()); F.pt_rowptr.reserve(w.lLocalMapPoints.size() + 1);
+  graph_points.reserve(w.lLocalMapPoints.size());
   F.pt_rowptr.push_back(0);
-  for (MapPoint *pMP : w.lLocalMapPoints) {
+  std::vector<std::pair<int, std::pair<KeyFrame *, size_t>>> obs;
+  for (size_t ip = 0; ip < w.lLocalMapPoints.size(); ip++) {
+    MapPoint *pMP = w.lLocalMapPoints[ip];
     if (mixed && pMP->Observations() == 1) continue;  // :2336
     graph_points.push_back(pMP);
     cv::Mat X = pMP->GetWorldPos();
     for (int i = 0; i < 3; i++) F.pt_xyz.push_back((double)X.at<float>(i, 0));  // Converter::toVector3d
     F.pt_fixed.push_back(mixed && fixPoint);
-    const std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
-    std::vector<std::pair<int, std::pair<KeyFrame *, size_t>>> obs;
-    for (auto &mit : observations)
-      if (!mit.first->isBad()) {
-        auto it = kf_slot.find(mit.first);
-        if (it != kf_slot.end()) obs.push_back({it->second, {mit.first, mit.second}});
-      }
+    obs.clear();
+    for (int q = w.obs_ptr[ip]; q < w.obs_ptr[ip + 1]; q++) {  // the snapshot taken in stage A
+      KeyFrame *pKFi = w.obs[q].first;
+      if (pKFi->isBad() || pKFi->mnId >= slot_of_id.size()) continue;
+      const int sl = slot_of_id[pKFi->mnId];
+      if (sl >= 0 && slots[sl].kf == pKFi) obs.push_back({sl, {pKFi, w.obs[q].second}});
+    }
     std::sort(obs.begin(), obs.end(), [](auto &a, auto &b) { return a.first < b.first; });
     for (auto &o : obs) {
       KeyFrame *pKFi = o.second.first;
@@ -411,6 +444,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     }
   }
   F.publish();
+  tick("flatten graph (stage B)");
 
   if (pbStopFlag && *pbStopFlag) return;  // :2723-2725 — no optimisation, no write-back
 
@@ -427,6 +461,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", g_last_rc, ppo_ba_last_error(h));
     return;
   }
+  tick("engine (stages C-E)");
   // ---- stage F: erase lists :2840-2887 ---------------------------------------------------------------------------
   std::vector<std::pair<KeyFrame *, MapPoint *>> vToErase;
   std::vector<std::pair<KeyFrame *, MapPlane *>> vToErasePlane;
@@ -452,6 +487,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   st.kf_pose = o_kf.data(); st.pt_xyz = o_pt.data(); st.pl_coef = o_pl.data(); st.cu_state = o_cu.data();
   if ((g_last_rc = ppo_ba_get_state(h, &st)) != PPO_OK) return;
 
+  tick("erase lists + read-back (F)");
   // ---- stage G: write back under the map mutex :2892-2966 --------------------------------------------------------------
   std::unique_lock<std::mutex> lock(pMap->mMutexMapUpdate);
   for (auto &pr : vToErase) {
