@@ -271,3 +271,25 @@ def test_fix_camera_and_fix_point_arguments(ppo, oracle_mod, fix_camera, fix_poi
     res = L.ppo_shim_last_result().contents
     assert (res.round1.iterations, res.round2.iterations) == (ro.round1.iterations, ro.round2.iterations)
     assert np.abs(st.kf_pose - o.get_state().kf_pose).max() < 5e-6
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_windows_through_the_oracle_backed_shim(ppo, oracle_mod, seed):
+    """Differential test on random window shapes: mock map -> shim (flatten, engine = oracle, write-back) against the oracle
+    run directly on the graph the shim flattened."""
+    import shim_lib
+    L = shim_lib.oracle_backed_lib()
+    rng = np.random.default_rng(100 + seed)
+    cfg = dict(n_kf=int(rng.integers(6, 20)), n_fixed=int(rng.integers(1, 4)), n_pt=int(rng.integers(200, 1500)),
+               n_pl=int(rng.integers(1, 8)), n_cu=int(rng.integers(1, 4)), corners_2d=int(rng.integers(0, 2)), cuboid_2d=int(rng.integers(0, 2)))
+    g = ppo.synth.make_graph(ppo.synth.config(1, window=seed, **cfg))
+    st, counts, flat = shim_lib.run(g, backend=L)
+    assert L.ppo_shim_last_rc() == 0, cfg
+    o = oracle_mod.Oracle()
+    o.set_graph(flat)
+    ro = o.local_ba()
+    res = L.ppo_shim_last_result().contents
+    assert (res.round1.iterations, res.round2.iterations) == (ro.round1.iterations, ro.round2.iterations), cfg
+    assert np.isclose(res.round2.chi2_final, ro.round2.chi2_final, rtol=1e-9)
+    assert np.abs(st.kf_pose - o.get_state().kf_pose).max() < 5e-6
+    assert counts[3] == flat.c.n_pt
