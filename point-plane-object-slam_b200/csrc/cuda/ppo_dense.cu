@@ -15,6 +15,8 @@
 // then per 64-block, last to first:  k_backsolve_step   x_B = W_BB^T y_B ; y_A -= L_BA^T x_B
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "ppo_dense.h"
 
 namespace ppo {
@@ -333,7 +335,7 @@ union SyrkSmem {
   TileSmem t;
   PfSmem pf;
 };
-__global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, int nb, int n, double *Wnext, int *not_spd) {
+__global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, int nb, int n, int gr, double *Wnext, int *not_spd) {
   extern __shared__ __align__(16) unsigned char dsm[];
   SyrkSmem &sm = *reinterpret_cast<SyrkSmem *>(dsm);
   double(*sA)[SLD] = sm.t.sA;
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int j = j0 + q * 8 + 2 * (lane & 3) + h;
-      c[q][h] = (i <= n && j < n && i >= j) ? A_(i, j) : 0.0;  // column n does not exist (row n is the carried gradient)
+      c[q][h] = (i <= gr && j < n && i >= j) ? A_(i, j) : 0.0;  // columns >= n do not exist (row gr is the carried gradient)
     }
   for (int m0 = 0; m0 < nb; m0 += KC) {
     const int mc = min(KC, nb - m0);
@@ -372,8 +374,8 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
 #pragma unroll
       for (int q = 0; q < KC / 4; q++) {
         const int m = mb + 4 * q;
-        ra[q] = (m < mc && i0 + r <= n) ? A_(i0 + r, k + m0 + m) : 0.0;
-        rb[q] = (m < mc && j0 + r <= n) ? A_(j0 + r, k + m0 + m) : 0.0;
+        ra[q] = (m < mc && i0 + r <= gr) ? A_(i0 + r, k + m0 + m) : 0.0;
+        rb[q] = (m < mc && j0 + r <= gr) ? A_(j0 + r, k + m0 + m) : 0.0;
       }
 #pragma unroll
       for (int q = 0; q < KC / 4; q++) sA[mb + 4 * q][r] = ra[q], sB[mb + 4 * q][r] = rb[q];
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
   }
   const bool next_diag = blockIdx.x == 0 && k2 < n;  // this tile is the diagonal block of the next panel
   const int nb2 = min(NB, n - k2);
-  if (i <= n) {
+  if (i <= gr) {
 #pragma unroll
     for (int q = 0; q < 8; q++)
 #pragma unroll
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *S, int ld, int k, i
 // --- back substitution L^T x = y (y = row n), one launch per 64-block, last block first ------------------------
 // every CTA recomputes x_B = W_BB^T y_B (64 x 64 mat-vec), CTA c then folds x_B into the 64 columns it owns:
 // y_i -= sum_r L(b0 + r, i) x_B[r].
-__global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n, int b0, int nb, const double *Winv, double *x) {
+__global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int gr, int b0, int nb, const double *Winv, double *x) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double sW[NB][NB + 1];
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n
   const bool fold = blockIdx.x > 0 && col < b0;
 #pragma unroll
   for (int q = 0; q < 16; q++) l[q] = (fold && p + 4 * q < nb) ? A_(b0 + p + 4 * q, col) : 0.0;
-  if (tid < NB) yb[tid] = tid < nb ? A_(n, b0 + tid) : 0.0;
+  if (tid < NB) yb[tid] = tid < nb ? A_(gr, b0 + tid) : 0.0;
 #pragma unroll
   for (int q = 0; q < 16; q++) sW[i][p + 4 * q] = w[q];
   __syncthreads();
@@ -458,39 +460,556 @@ __global__ void __launch_bounds__(256) k_backsolve_step(double *S, int ld, int n
   __syncthreads();
   if (tid < NB) {
     const int c = ((int)blockIdx.x - 1) * NB + tid;
-    if (c < b0) A_(n, c) -= part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+    if (c < b0) A_(gr, c) -= part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
   }
 }
 
-void dense_cholesky_solve(double *S, int n, int ld, double *x, double *Winv, int *not_spd, cudaStream_t st, long long *launches) {
+// =====================================================================================================================
+// Persistent dataflow factorisation (default path).  ONE launch factorises the whole reduced system; a second launch
+// does the backward substitution.  The matrix is cut into 64 x 64 tiles; every tile (i, j) goes through the operations
+//      U_0 .. U_{j-1}   C_ij -= P_ik P_jk^T                         (trailing updates, any CTA)
+//      F_j   (i == j)   L_jj = chol(C_jj), W_j = L_jj^-1            (critical-path CTA)
+//      T_j   (i >  j)   P_ij = C_ij W_j^T                           (any CTA; the tile right below the diagonal: critical-path CTA)
+// and carries a version counter ver[i][j] = number of operations applied (tagged with the launch epoch, so the counters
+// are never cleared).  The first CTA to start takes the critical path  F_k -> T_k(k+1) -> U_k(k+1,k+1) -> F_{k+1}  and keeps
+// the diagonal tile in shared memory between steps; all other CTAs pull the remaining operations from a global queue that
+// is ordered level by level (T_k first, then U_k by column), i.e. topologically: an operation only waits for operations
+// that were claimed before it, by CTAs that are therefore running -- the kernel cannot deadlock whatever number of CTAs
+// is resident, and it needs no cooperative launch.  Operand tiles are staged by the TMA engine (cp.async.bulk, one 512-byte
+// column per copy into a padded, bank-conflict-free layout, completion on an mbarrier); the products run on the FP64
+// tensor cores (DMMA).  Every wait is bounded: on a time-out the kernel raises ctrl->err and all CTAs leave.
+// =====================================================================================================================
+struct CholCtrl {
+  int ticket;  // role tickets of the running launch (first CTA to arrive = critical-path CTA)
+  int qhead;   // next operation of the worker queue
+  int done;    // CTAs that have left the kernel; the last one resets the block for the next launch
+  int epoch;   // launch counter: flag values are epoch * 256 + level
+  int err;     // 1: a wait timed out
+  int bticket, bdone, bepoch;  // the same for the back-substitution kernel
+};
+constexpr int CLD = NB + 4;  // padded leading dimension of a staged tile (doubles): 544-byte columns, 16-byte aligned
+constexpr long long CHOL_TIMEOUT = 1ll << 32;  // cycles (~2 s)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// one warp stages the 64 x 64 tile whose top-left element is `src` (column stride ld_src) into dst[col][row]
+__device__ __forceinline__ void tile_load(double (*dst)[CLD], const double *src, size_t ld_src, unsigned long long *bar) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = lane; c < NB; c += 32) bulk_g2s(&dst[c][0], src + (size_t)c * ld_src, NB * 8, bar);
+}
+
+// bounded wait until *flag >= want; false (and ctrl->err raised) on time-out or when another CTA has raised it
+__device__ __forceinline__ bool flag_wait(const int *flag, int want, CholCtrl *ctrl) {
+  if (ld_acquire(flag) >= want) return true;
+  const long long t0 = clock64();
+  for (int it = 1;; it++) {
+    if (ld_acquire(flag) >= want) return true;
+    if ((it & 63) == 0) {
+      if (*(volatile int *)&ctrl->err) return false;
+      if (clock64() - t0 > CHOL_TIMEOUT) {
+        atomicExch(&ctrl->err, 1);
+        return false;
+      }
+    }
+    __nanosleep(20);
+  }
+}
+
+struct ChSmem {
+  double A[NB][CLD];  // operand tile / result tile
+  double B[NB][CLD];  // second operand / W
+  PfSmem pf;          // diagonal tile of the critical-path CTA
+  unsigned long long mbar;
+  int op[4];          // broadcast of the decoded queue entry {type, k, i, j}
+  int ok;
+};
+struct CholArgs {
+  double *S;
+  int ld, n, Tc;  // Tc column tiles; row tiles 0 .. Tc, the last one holds the carried gradient (row 64 Tc)
+  double *Winv;
+  int *ver;
+  int vs;  // row stride of ver
+  CholCtrl *ctrl;
+  int *not_spd;
+};
+// acc(i, j) += sum_m sA[m][i] sB[m][j] on a 64 x 64 x 64 tile; warp w owns rows 8w..8w+7.
+// MODE 0: full; 1: lower triangle only (column blocks <= row block); 2: sB = W^T of a lower-triangular W (m <= j)
+template <int MODE>
+__device__ __forceinline__ void tile_mma64(const double (*sA)[CLD], const double (*sB)[CLD], double acc[8][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = warp * 8 + (lane >> 2), kk = lane & 3;
+#pragma unroll 4
+  for (int m0 = 0; m0 < NB; m0 += 4) {
+    const double a = sA[m0 + kk][row];
+#pragma unroll
+    for (int nbk = 0; nbk < 8; nbk++) {
+      if (MODE == 1 && nbk > warp) continue;
+      if (MODE == 2 && m0 > 8 * nbk + 7) continue;
+      const double b = sB[m0 + kk][nbk * 8 + (lane >> 2)];
+      dmma(acc[nbk][0], acc[nbk][1], a, b);
+    }
+  }
+}
+__device__ __forceinline__ size_t tile_off(int ld, int i, int j) { return (size_t)(NB * j) * ld + (size_t)NB * i; }
+
+__global__ void __launch_bounds__(256) k_chol_dataflow(CholArgs a) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  ChSmem &sm = *reinterpret_cast<ChSmem *>(dsm);
+  __shared__ int s_role, s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *S = a.S;
+  const int ld = a.ld, Tc = a.Tc, vs = a.vs;
+  CholCtrl *ctrl = a.ctrl;
+  if (tid == 0) {
+    s_role = atomicAdd(&ctrl->ticket, 1);
+    s_base = ld_acquire(&ctrl->epoch) * 256;
+    mbar_init(&sm.mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int role = s_role, base = s_base;
+  unsigned phase = 0;
+  const int il = warp * 8 + (lane >> 2);  // my row of a tile in the DMMA C-fragment layout; my columns: 8 q + 2 (lane & 3) + h
+  if (role == 0) {
+    // ------------------------------- critical path -------------------------------------------------------------
+    for (int k = 0; k < Tc; k++) {
+      const int nb = min(NB, a.n - NB * k);
+      if (tid < PF_THREADS) {
+        if (k == 0) pf_factor<false>(sm.pf, S, ld, 0, nb, a.Winv, a.not_spd);
+        else pf_factor<true>(sm.pf, S, ld, NB * k, nb, a.Winv + (size_t)k * NB * NB, a.not_spd);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release(&a.ver[k * vs + k], base + k + 1);  // W_k is published
+        sm.ok = (k == 0) ? 1 : (int)flag_wait(&a.ver[(k + 1) * vs + k], base + k, ctrl);
+      }
+      // W_k (written by this CTA a moment ago) -> sm.B, generic loads
+      {
+        const double *W = a.Winv + (size_t)k * NB * NB;
+        const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+        for (int q = 0; q < 16; q++) sm.B[c0 + 4 * q][r] = W[(size_t)(c0 + 4 * q) * NB + r];
+      }
+      __syncthreads();
+      if (!sm.ok) break;
+      // T_k(k+1): the tile right below the diagonal
+      if (warp == 0) {
+        if (lane == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(&sm.mbar, NB * NB * 8);
+        }
+        __syncwarp();
+        tile_load(sm.A, S + tile_off(ld, k + 1, k), ld, &sm.mbar);
+      }
+      mbar_wait(&sm.mbar, phase);
+      phase ^= 1;
+      double acc[8][2];
+#pragma unroll
+      for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
+      const bool grad_tile = (k + 1 == Tc);  // the gradient tile has one valid row
+      if (!grad_tile || warp == 0) tile_mma64<2>(sm.A, sm.B, acc);
+      __syncthreads();  // everybody has read sm.A
+      {
+        double *dst = S + tile_off(ld, k + 1, k);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int jl = q * 8 + 2 * (lane & 3) + h;
+            dst[(size_t)jl * ld + il] = acc[q][h];
+            sm.A[jl][il] = acc[q][h];
+          }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release(&a.ver[(k + 1) * vs + k], base + k + 1);  // P_{k+1,k} is published
+        if (k + 1 < Tc) sm.ok = (k == 0) ? 1 : (int)flag_wait(&a.ver[(k + 1) * vs + k + 1], base + k, ctrl);
+      }
+      if (k + 1 >= Tc) break;
+      __syncthreads();
+      if (!sm.ok) break;
+      // U_k(k+1,k+1) on the next diagonal tile, which then stays in shared memory for F_{k+1}
+      {
+        const int nb2 = min(NB, a.n - NB * (k + 1));
+        const double *src = S + tile_off(ld, k + 1, k + 1);
+        double c[8][2];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int jl = q * 8 + 2 * (lane & 3) + h;
+            c[q][h] = (il >= jl) ? __ldcg(src + (size_t)jl * ld + il) : 0.0;
+            acc[q][h] = 0.0;
+          }
+        tile_mma64<1>(sm.A, sm.A, acc);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int jl = q * 8 + 2 * (lane & 3) + h;
+            if (il >= jl) {
+              const double v = (il < nb2 && jl < nb2) ? c[q][h] - acc[q][h] : (il == jl ? 1.0 : 0.0);
+              sm.pf.Lu[jl][il] = v;
+              sm.pf.Lu[il][jl] = v;
+            }
+          }
+      }
+      __syncthreads();
+    }
+  } else {
+    // ------------------------------- workers: operations from the queue ---------------------------------------------
+    int lvl = 0, lvl_start = 0;  // (thread 0) level of the last decoded entry and index of its first entry
+    for (;;) {
+      if (tid == 0) {
+        const int idx = atomicAdd(&ctrl->qhead, 1);
+        int type = -1, k = 0, i = 0, j = 0;
+        for (; lvl < Tc; lvl++) {
+          const int m = Tc - 1 - lvl;
+          const int size = m + (m >= 1 ? (m + 1) * (m + 2) / 2 - 2 : 0);
+          if (idx < lvl_start + size) break;
+          lvl_start += size;
+        }
+        if (lvl < Tc) {
+          k = lvl;
+          const int m = Tc - 1 - k;
+          int u = idx - lvl_start;
+          if (u < m) {  // T_k(i), i = k+2 .. Tc
+            type = 0, i = k + 2 + u, j = k;
+          } else {      // U_k(i, j): column k+1 rows k+2..Tc, then columns j >= k+2 rows j..Tc
+            type = 1;
+            u -= m;
+            if (u < m) {
+              i = k + 2 + u, j = k + 1;
+            } else {
+              u -= m;
+              for (j = k + 2;; j++) {
+                const int cnt = Tc - j + 1;
+                if (u < cnt) break;
+                u -= cnt;
+              }
+              i = j + u;
+            }
+          }
+        }
+        bool ok = true;
+        if (type == 0) {
+          ok = flag_wait(&a.ver[k * vs + k], base + k + 1, ctrl);
+          if (ok && k > 0) ok = flag_wait(&a.ver[i * vs + k], base + k, ctrl);
+        } else if (type == 1) {
+          ok = flag_wait(&a.ver[i * vs + k], base + k + 1, ctrl);
+          if (ok && j != i) ok = flag_wait(&a.ver[j * vs + k], base + k + 1, ctrl);
+          if (ok && k > 0) ok = flag_wait(&a.ver[i * vs + j], base + k, ctrl);
+        }
+        sm.op[0] = ok ? type : -1, sm.op[1] = k, sm.op[2] = i, sm.op[3] = j;
+      }
+      __syncthreads();
+      const int type = sm.op[0], k = sm.op[1], i = sm.op[2], j = sm.op[3];
+      if (type < 0) break;
+      const bool one_row = (i == Tc);  // gradient tile: only row 0 carries data (the rest is zero padding)
+      double acc[8][2];
+#pragma unroll
+      for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
+      if (type == 0) {
+        if (warp == 0) {
+          if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.mbar, 2 * NB * NB * 8);
+          }
+          __syncwarp();
+          tile_load(sm.A, S + tile_off(ld, i, k), ld, &sm.mbar);
+          tile_load(sm.B, a.Winv + (size_t)k * NB * NB, NB, &sm.mbar);
+        }
+        mbar_wait(&sm.mbar, phase);
+        phase ^= 1;
+        if (!one_row || warp == 0) {
+          tile_mma64<2>(sm.A, sm.B, acc);
+          double *dst = S + tile_off(ld, i, k);
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) dst[(size_t)(q * 8 + 2 * (lane & 3) + h) * ld + il] = acc[q][h];
+        }
+      } else {
+        const bool diag = (i == j);
+        if (warp == 0) {
+          if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.mbar, (diag ? 1 : 2) * NB * NB * 8);
+          }
+          __syncwarp();
+          tile_load(sm.A, S + tile_off(ld, i, k), ld, &sm.mbar);
+          if (!diag) tile_load(sm.B, S + tile_off(ld, j, k), ld, &sm.mbar);
+        }
+        double *ct = S + tile_off(ld, i, j);
+        double c[8][2];
+        if (!one_row || warp == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int jl = q * 8 + 2 * (lane & 3) + h;
+              c[q][h] = (!diag || il >= jl) ? __ldcg(ct + (size_t)jl * ld + il) : 0.0;
+            }
+        }
+        mbar_wait(&sm.mbar, phase);
+        phase ^= 1;
+        if (!one_row || warp == 0) {
+          if (diag) tile_mma64<1>(sm.A, sm.A, acc);
+          else tile_mma64<0>(sm.A, sm.B, acc);
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int jl = q * 8 + 2 * (lane & 3) + h;
+              if (!diag || il >= jl) ct[(size_t)jl * ld + il] = c[q][h] - acc[q][h];
+            }
+        }
+      }
+      __syncthreads();  // all stores of the tile issued; the staging buffers are free again
+      if (tid == 0) {
+        __threadfence();
+        st_release(&a.ver[i * vs + j], base + k + 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&ctrl->done, 1) == (int)gridDim.x - 1) {  // last CTA out: arm the control block for the next launch
+      if (*(volatile int *)&ctrl->err) *a.not_spd = 1;      // a timed-out factorisation counts as a failed solve
+      ctrl->ticket = 0;
+      ctrl->qhead = 0;
+      ctrl->done = 0;
+      ctrl->epoch = ctrl->epoch + 1;
+      __threadfence();
+    }
+  }
+}
+
+// ---- backward substitution L^T x = y in ONE launch --------------------------------------------------------------------
+// CTA (by start ticket r) owns block column b = Tc-1-r: it folds x_c of the later blocks into its right-hand side as they
+// are published ( acc -= L_cb^T x_c, tiles prefetched by TMA one ahead ) and finishes with x_b = W_b^T acc.  A CTA only waits
+// for CTAs that started before it.  Chain per block: flag -> 64 x 64 mat-vec -> warp reduction -> 64 x 64 mat-vec -> flag.
+struct BsSmem {
+  double L[2][NB][CLD];
+  double W[NB][NB + 1];
+  double xc[NB];
+  double accv[NB];
+  double part[4][NB];
+  unsigned long long mbar[2];
+  int ok;
+};
+__global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int ld, int n, int Tc, const double *Winv, double *x, int *xrdy, CholCtrl *ctrl) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  BsSmem &sm = *reinterpret_cast<BsSmem *>(dsm);
+  __shared__ int s_b, s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    s_b = Tc - 1 - atomicAdd(&ctrl->bticket, 1);
+    s_base = ld_acquire(&ctrl->bepoch);
+    mbar_init(&sm.mbar[0], 1);
+    mbar_init(&sm.mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int b = s_b, want = s_base + 1;
+  const int grow = NB * Tc;
+  if (b >= 0) {
+    unsigned ph[2] = {0, 0};
+    int buf = 0;
+    if (Tc - 1 > b && warp == 0) {  // first tile of the sweep: (Tc-1, b)
+      if (lane == 0) mbar_expect_tx(&sm.mbar[0], NB * NB * 8);
+      __syncwarp();
+      tile_load(sm.L[0], S + tile_off(ld, Tc - 1, b), ld, &sm.mbar[0]);
+    }
+    {  // W_b, column-major with an odd stride (conflict-free column reads)
+      const double *W = Winv + (size_t)b * NB * NB;
+      const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+      for (int q = 0; q < 16; q++) sm.W[c0 + 4 * q][r] = __ldcg(W + (size_t)(c0 + 4 * q) * NB + r);
+    }
+    double s[8];  // lane-partial sums of  sum_r L(r, 8 warp + jj) x_c[r]  over all tiles so far
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) s[jj] = 0.0;
+    bool ok = true;
+    for (int c = Tc - 1; c > b; c--) {
+      if (tid == 0) sm.ok = (int)flag_wait(&xrdy[c], want, ctrl);
+      if (c - 1 > b && warp == 0) {  // prefetch the next tile into the other buffer (its last readers are two barriers back)
+        if (lane == 0) mbar_expect_tx(&sm.mbar[buf ^ 1], NB * NB * 8);
+        __syncwarp();
+        tile_load(sm.L[buf ^ 1], S + tile_off(ld, c - 1, b), ld, &sm.mbar[buf ^ 1]);
+      }
+      __syncthreads();
+      if (!sm.ok) {
+        ok = false;
+        break;
+      }
+      if (tid < NB) sm.xc[tid] = __ldcg(x + NB * c + tid);
+      mbar_wait(&sm.mbar[buf], ph[buf]);
+      ph[buf] ^= 1;
+      __syncthreads();
+      const double x0 = sm.xc[lane], x1 = sm.xc[lane + 32];
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) s[jj] = fma(sm.L[buf][8 * warp + jj][lane], x0, fma(sm.L[buf][8 * warp + jj][lane + 32], x1, s[jj]));
+      buf ^= 1;
+      __syncthreads();  // the buffer may be refilled by the next prefetch
+    }
+    if (ok) {
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) {
+        double v = s[jj];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+          const int col = NB * b + 8 * warp + jj;
+          sm.accv[8 * warp + jj] = (col < n ? __ldcg(S + (size_t)col * ld + grow) : 0.0) - v;
+        }
+      }
+      __syncthreads();
+      {  // x_b = W^T acc  (W lower triangular: rows r >= i)
+        const int i = tid & 63, p = tid >> 6;
+        double t = 0.0;
+        for (int r = i + p; r < NB; r += 4) t = fma(sm.W[i][r], sm.accv[r], t);
+        sm.part[p][i] = t;
+      }
+      __syncthreads();
+      if (tid < NB) {
+        const double v = sm.part[0][tid] + sm.part[1][tid] + sm.part[2][tid] + sm.part[3][tid];
+        x[NB * b + tid] = (NB * b + tid < n) ? v : 0.0;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release(&xrdy[b], want);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&ctrl->bdone, 1) == (int)gridDim.x - 1) {
+      ctrl->bticket = 0;
+      ctrl->bdone = 0;
+      ctrl->bepoch = ctrl->bepoch + 1;
+      __threadfence();
+    }
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+int dense_num_blocks(int n) { return (n + NB - 1) / NB; }
+int dense_ld(int max_n) { return NB * (dense_num_blocks(max_n) + 1); }
+size_t dense_matrix_doubles(int max_n) { return (size_t)NB * dense_num_blocks(max_n) * dense_ld(max_n); }
+size_t dense_x_doubles(int max_n) { return (size_t)NB * dense_num_blocks(max_n); }
+size_t dense_workspace_bytes(int max_n) {
+  const size_t T = dense_num_blocks(max_n);
+  return 256 + sizeof(int) * ((T + 1) * T + T);
+}
+void dense_workspace_init(void *ws, int max_n, cudaStream_t st) {
+  cudaMemsetAsync(ws, 0, dense_workspace_bytes(max_n), st);
+  const int one = 1;
+  CholCtrl *c = reinterpret_cast<CholCtrl *>(ws);
+  cudaMemcpyAsync(&c->epoch, &one, sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(&c->bepoch, &one, sizeof(int), cudaMemcpyHostToDevice, st);
+}
+
+static bool legacy_path() {
+  static const bool v = std::getenv("PPO_DENSE_LEGACY") != nullptr;
+  return v;
+}
+static int sm_count(int dev) {
+  static int cache[64] = {};
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  int v = 0;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  if (v <= 0) v = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = v;
+  return v;
+}
+void dense_setup_device(int dev) {  // per-device function attributes (> 48 KB of dynamic shared memory); called from ppo_ba_create
+  (void)dev;
+  cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyrkSmem));
+  cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem));
+  cudaFuncSetAttribute(k_backsolve_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BsSmem));
+}
+
+void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, void *ws, int *not_spd, cudaStream_t st, long long *launches) {
   if (n <= 0) return;
-  // opting in to > 48 KB of dynamic shared memory is a per-device function attribute
-  static bool attr_set[64] = {};
+  const int ld = dense_ld(max_n);
+  const int Tc = dense_num_blocks(n), gr = NB * Tc;
+  if (legacy_path()) {
+    const int rows_total = gr + 1;  // rows 0..gr (row gr carries the gradient; rows n..gr-1 are zero padding)
+    launch_pdl(k_potrf_inv, dim3(1), dim3(PF_THREADS), 0, st, S, ld, 0, n < NB ? n : NB, Winv, not_spd);
+    (*launches)++;
+    for (int k = 0, blk = 0; k < n; k += NB, blk++) {  // the diagonal block of panel k is already factorised
+      const int nb = (n - k < NB) ? (n - k) : NB;
+      double *W = Winv + (size_t)blk * NB * NB;
+      const int T = (rows_total - (k + nb) + TS - 1) / TS;  // >= 1: row gr
+      launch_pdl(k_panel_gemm, dim3((rows_total - (k + nb) + GR - 1) / GR), dim3(256), 0, st, S, ld, k, nb, rows_total, (const double *)W);
+      launch_pdl(k_syrk_update, dim3(T * (T + 1) / 2), dim3(256), sizeof(SyrkSmem), st, S, ld, k, nb, n, gr, W + NB * NB, not_spd);
+      (*launches) += 2;
+    }
+    for (int b = Tc - 1; b >= 0; b--) {
+      const int b0 = b * NB, nb = (n - b0 < NB) ? (n - b0) : NB;
+      launch_pdl(k_backsolve_step, dim3(1 + b), dim3(256), 0, st, S, ld, gr, b0, nb, (const double *)(Winv + (size_t)b * NB * NB), x);
+      (*launches)++;
+    }
+    return;
+  }
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyrkSmem));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  CholCtrl *ctrl = reinterpret_cast<CholCtrl *>(ws);
+  int *ver = reinterpret_cast<int *>(reinterpret_cast<char *>(ws) + 256);
+  const int Tm = dense_num_blocks(max_n);
+  int *xrdy = ver + (size_t)(Tm + 1) * Tm;
+  long long ops = 0;
+  for (int k = 0; k < Tc; k++) {
+    const long long m = Tc - 1 - k;
+    ops += m + (m >= 1 ? (m + 1) * (m + 2) / 2 - 2 : 0);
   }
-  const int rows_total = n + 1;  // rows 0..n (row n carries the gradient)
-  launch_pdl(k_potrf_inv, dim3(1), dim3(PF_THREADS), 0, st, S, ld, 0, n < NB ? n : NB, Winv, not_spd);
-  (*launches)++;
-  for (int k = 0, blk = 0; k < n; k += NB, blk++) {  // the diagonal block of panel k is already factorised
-    const int nb = (n - k < NB) ? (n - k) : NB;
-    double *W = Winv + (size_t)blk * NB * NB;
-    const int T = (rows_total - (k + nb) + TS - 1) / TS;  // >= 1: row n
-    launch_pdl(k_panel_gemm, dim3((rows_total - (k + nb) + GR - 1) / GR), dim3(256), 0, st, S, ld, k, nb, rows_total, (const double *)W);
-    launch_pdl(k_syrk_update, dim3(T * (T + 1) / 2), dim3(256), sizeof(SyrkSmem), st, S, ld, k, nb, n, W + NB * NB, not_spd);
-    (*launches) += 2;
+  static int occ[64] = {};  // resident CTAs per SM of the persistent kernel (registers / shared memory)
+  if (dev >= 0 && dev < 64 && !occ[dev]) {
+    int v = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_chol_dataflow, 256, sizeof(ChSmem));
+    occ[dev] = v > 0 ? v : 1;
   }
-  const int nblk = (n + NB - 1) / NB;
-  for (int b = nblk - 1; b >= 0; b--) {
-    const int b0 = b * NB, nb = (n - b0 < NB) ? (n - b0) : NB;
-    launch_pdl(k_backsolve_step, dim3(1 + b), dim3(256), 0, st, S, ld, n, b0, nb, (const double *)(Winv + (size_t)b * NB * NB), x);
-    (*launches)++;
-  }
+  const long long cap = (long long)(dev >= 0 && dev < 64 ? occ[dev] : 1) * sm_count(dev);
+  const int grid = (int)(1 + (ops < cap - 1 ? ops : cap - 1));
+  CholArgs a;
+  a.S = S, a.ld = ld, a.n = n, a.Tc = Tc, a.Winv = Winv, a.ver = ver, a.vs = Tm, a.ctrl = ctrl, a.not_spd = not_spd;
+  k_chol_dataflow<<<grid, 256, sizeof(ChSmem), st>>>(a);
+  k_backsolve_chain<<<Tc, 256, sizeof(BsSmem), st>>>(S, ld, n, Tc, Winv, x, xrdy, ctrl);
+  (*launches) += 2;
 }
-
-int dense_num_blocks(int n) { return (n + NB - 1) / NB; }
 
 }  // namespace ppo

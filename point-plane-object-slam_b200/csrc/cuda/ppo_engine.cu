@@ -103,6 +103,7 @@ struct ppo_ba_handle {
   Scalars *d_scal = nullptr, *h_scal = nullptr;
   int *d_not_spd = nullptr, *d_nout = nullptr;
   double *d_Winv = nullptr;
+  void *d_dense_ws = nullptr;  // control block + tile version counters of the persistent factorisation
   int *h_dims = nullptr;
   // current mapping
   int n_p = 0, n_kf_free = 0, n_l = 0, n_active_edges = 0;
@@ -251,6 +252,7 @@ int ppo_ba_create(const ppo_ba_params *params, int device, ppo_ba_handle **out) 
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
+  dense_setup_device(device);
   cudaMallocHost((void **)&h->h_scal, sizeof(Scalars));
   cudaMallocHost((void **)&h->h_dims, 8 * sizeof(int));
   *out = h;
@@ -630,16 +632,22 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   int n_free = 0;
   for (int i = 0; i < g.n_kf; i++) n_free += !kf_fixed[i];
   h->max_np = 6 * n_free + 9 * g.n_cu;
-  h->ld = h->max_np + 1;
+  h->ld = dense_ld(h->max_np);  // tile-aligned layout of the reduced system (ppo_dense.h)
   DA(g.Hpp_kf, 36 * (size_t)g.n_kf); DA(g.Hpp_cu, 81 * (size_t)g.n_cu); DA(g.Hpc, 54 * (size_t)g.n_cbe); DA(g.bp, (size_t)h->max_np);
   DA(g.Hll, 6 * (size_t)g.n_lm); DA(g.bl, 3 * (size_t)g.n_lm); DA(g.Hpl, 18 * (size_t)g.n_ent); DA(g.BD, 18 * (size_t)g.n_ent); DA(g.Zent, 3 * (size_t)g.n_ent); DA(g.Dinv, 6 * (size_t)g.n_lm);
-  DA(g.xl, 3 * (size_t)g.n_lm); DA(g.S, (size_t)(h->max_np + 1) * h->ld); DA(g.xp, (size_t)h->max_np);
+  DA(g.xl, 3 * (size_t)g.n_lm); DA(g.S, dense_matrix_doubles(h->max_np)); DA(g.xp, dense_x_doubles(h->max_np));
   h->nb_lin = cdiv(g.n_units, LIN_WARPS); h->nb_res = cdiv(g.n_pe, RES_THREADS);
   h->nb_pl = cdiv(g.n_ple, SMALL_THREADS); h->nb_cb = cdiv(g.n_cbe, SMALL_THREADS); h->nb_pc = cdiv(g.n_pce, SMALL_THREADS);
   h->nb_bs = cdiv(g.n_pl, BS_WARPS) + g.n_units;  // partial sums of k_backsub (planes) + k_backsub_points
   DA(h->d_chi_pt, (size_t)std::max(h->nb_lin, h->nb_res)); DA(h->d_chi_pl, (size_t)h->nb_pl); DA(h->d_chi_cb, (size_t)h->nb_cb); DA(h->d_chi_pc, (size_t)h->nb_pc);
   DA(h->d_scale_part, (size_t)h->nb_bs);
   DA(h->d_Winv, (size_t)dense_num_blocks(h->max_np) * 64 * 64);
+  {
+    char *ws = nullptr;
+    DA(ws, dense_workspace_bytes(h->max_np));
+    h->d_dense_ws = ws;
+    dense_workspace_init(ws, h->max_np, h->st);
+  }
   DA(h->d_scal, 1); DA(h->d_not_spd, 1); DA(h->d_nout, 4); DA(h->d_red, 4);
   CK(cudaMemsetAsync(g.pe_chi2, 0, 8 * (size_t)g.n_pe, h->st));
   CK(cudaMemsetAsync(g.ple_chi2, 0, 8 * (size_t)g.n_ple, h->st));
@@ -866,25 +874,26 @@ static int schur_system(ppo_ba_handle *h, double lambda) {
   DevGraph &g = h->g;
   cudaStream_t st = h->st;
   const int n_p = h->n_p, ld = h->ld;
-  CK(cudaMemsetAsync(g.S, 0, 8 * (size_t)(n_p + 1) * ld, st));
+  const int grow = 64 * dense_num_blocks(n_p);  // row of the reduced gradient (tile aligned); 64-column tiles 0 .. grow/64 - 1
+  CK(cudaMemsetAsync(g.S, 0, 8 * (size_t)grow * ld, st));
   CK(cudaMemsetAsync(h->d_not_spd, 0, sizeof(int), st));
   const int own = h->owner() ? 1 : 0;
   if (g.n_pl) { k_schur_bd<<<cdiv(g.n_pl, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, lambda, n_p, ld, own, g.n_pl); h->launches++; }
   if (g.n_units) { k_schur_bd_points<<<g.n_units, 32, 0, st>>>(g, lambda); h->launches++; }
   if (h->n_pairs) {
     const int n_warps = cdiv(h->n_pairs, PAIR_CHUNK);
-    k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld, n_p);
+    k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld, grow);
     h->launches++;
   }
   const int n_comp = g.n_kf * 36 + g.n_cu * 81 + g.n_cbe * 54 + n_p;
-  if (n_comp && own) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, lambda, n_p, ld); h->launches++; }
+  if (n_comp && own) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, lambda, n_p, ld, grow); h->launches++; }
   // single large window sharded over ranks: sum the partial reduced systems (Hschur | bschur) over NVLink
-  if (h->world > 1) return allreduce(h, g.S, (size_t)n_p * ld, ncclFloat64_, ncclSum_);
+  if (h->world > 1) return allreduce(h, g.S, (size_t)grow * ld, ncclFloat64_, ncclSum_);
   return PPO_OK;
 }
 static int solve_and_backsub(ppo_ba_handle *h, double lambda) {
   DevGraph &g = h->g;
-  dense_cholesky_solve(g.S, h->n_p, h->ld, g.xp, h->d_Winv, h->d_not_spd, h->st, &h->launches);
+  dense_cholesky_solve(g.S, h->n_p, h->max_np, g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches);
   // planes: one warp per landmark; points: one lane per 6x3 block (work units of the linearisation); partial sums of the
   // LM scale go to disjoint ranges of d_scale_part
   const int nbp = cdiv(g.n_pl, BS_WARPS);
@@ -1266,7 +1275,7 @@ int ppo_ba_time_solve(ppo_ba_handle *h, int reps, double *ms_mean, double *flops
   for (int i = 0; i < reps + 2; i++) {
     if ((rc = schur_system(h, lambda))) return rc;
     CK(cudaEventRecord(h->ev0, h->st));
-    dense_cholesky_solve(h->g.S, h->n_p, h->ld, h->g.xp, h->d_Winv, h->d_not_spd, h->st, &h->launches);
+    dense_cholesky_solve(h->g.S, h->n_p, h->max_np, h->g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches);
     CK(cudaEventRecord(h->ev1, h->st));
     CK(cudaEventSynchronize(h->ev1));
     float ms;
@@ -1344,12 +1353,13 @@ int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, do
   if ((rc = schur_system(h, lambda))) return rc;
   CK(cudaStreamSynchronize(h->st));
   if (Hschur_upper || bschur) {
+    const int grow = 64 * dense_num_blocks(n_p);
     std::vector<double> S((size_t)(n_p + 1) * ld);
     if (n_p) CK(cudaMemcpy(S.data(), g.S, 8 * (size_t)n_p * ld, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n_p; i++) {
       if (Hschur_upper)
         for (int j = 0; j < n_p; j++) Hschur_upper[(size_t)i * n_p + j] = j >= i ? S[(size_t)i * ld + j] : 0.0;
-      if (bschur) bschur[i] = S[(size_t)i * ld + n_p];
+      if (bschur) bschur[i] = S[(size_t)i * ld + grow];
     }
   }
   if ((rc = solve_and_backsub(h, lambda))) return rc;

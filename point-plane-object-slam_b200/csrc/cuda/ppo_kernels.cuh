@@ -903,7 +903,7 @@ PPO_D void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, const unsigned *__restrict__ keys, const unsigned long long *__restrict__ vals,
-                                                                 int n_pairs, int ld, int n_p) {
+                                                                 int n_pairs, int ld, int grow) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
   const long long c0 = w * PAIR_CHUNK;
@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
           atomicAdd(dst + 6 * p2 + 2 * kk, -acc0);
           atomicAdd(dst + 6 * p2 + 2 * kk + 1, -acc1);
         } else if (ka == kb) {
-          atomicAdd(dst + n_p, -acc0);  // bschur -= W Dinv bl
+          atomicAdd(dst + grow, -acc0);  // bschur -= W Dinv bl
         }
       }
     }
@@ -964,7 +964,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
 }
 
 // S += Hpp (+ lambda on the diagonal), rhs column += bp.  One thread per scalar of each block.
-__global__ void k_compose(DevGraph g, double lambda, int n_p, int ld) {
+__global__ void k_compose(DevGraph g, double lambda, int n_p, int ld, int grow) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int nkf = g.n_kf * 36, ncu = g.n_cu * 81, nhpc = g.n_cbe * 54;
   if (t < nkf) {
@@ -991,7 +991,7 @@ __global__ void k_compose(DevGraph g, double lambda, int n_p, int ld) {
     }
   } else if (t < nkf + ncu + nhpc + n_p) {
     const int j = t - nkf - ncu - nhpc;
-    atomicAdd(&g.S[(size_t)j * ld + n_p], g.bp[j]);
+    atomicAdd(&g.S[(size_t)j * ld + grow], g.bp[j]);
   }
 }
 
