@@ -439,7 +439,9 @@ inline void cuboid_to_minimal(const Cuboid &c, double v[9]) {
 
 // ---- RobustKernelHuber::robustify: core/robust_kernel_impl.cpp:76-90 ---------------------------
 inline void huber(double e, double delta, double rho[3]) {
-  double dsqr = delta * delta;
+  // "float dsqr;" in the reference's (ORB-SLAM2-modified) RobustKernelHuber, core/robust_kernel_impl.h:84: delta^2 is rounded to
+  // float32 at setDelta() (robust_kernel_impl.cpp:64-68) and that rounded value is what the inlier test and rho(e) use
+  double dsqr = (double)(float)(delta * delta);
   if (e <= dsqr) {
     rho[0] = e;
     rho[1] = 1.;

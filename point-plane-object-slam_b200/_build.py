@@ -110,9 +110,27 @@ def build_shim(force=False):
     return out
 
 
+def build_ref(force=False):
+    """oracle/_ref/libppo_g2o_ref.so: the reference's own g2o + vertex/edge sources compiled where they lie under /root/reference
+    (oracle/Makefile.ref, Eigen stand-in oracle/ref_stub).  Only possible where /root/reference exists (this container); on the GPU
+    box the prebuilt file is used.  Test infrastructure: building the checker is not using it."""
+    out = os.path.join(ORACLE, "_ref", "libppo_g2o_ref.so")
+    if not os.path.isdir("/root/reference/Thirdparty/g2o"):
+        return out if os.path.exists(out) else None
+    cmd = ["make", "-f", os.path.join("oracle", "Makefile.ref"), "-j8"]
+    if force:
+        cmd.insert(1, "-B")
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-4000:] + "\n")
+        raise RuntimeError("build failed: oracle/Makefile.ref")
+    return out
+
+
 def build_all(force=False):
     out = {"synth": build_synth(force), "oracle": build_oracle(force), "cuda": build_cuda(force)}
     out["shim"] = build_shim(force)
+    out["ref"] = build_ref(force)
     return out
 
 

@@ -3,18 +3,31 @@
 #include <cstddef>
 namespace ppo {
 // Dense solve of the reduced pose system (LinearSolverDense::solve, solvers/linear_solver_dense.h:65-113).
-// Layout of S, for a handle whose pose block has at most max_n scalars: column-major lower triangle (= row-major upper
-// triangle) with leading dimension ld = dense_ld(max_n) = 64 (T + 1), T = ceil(max_n / 64); 64 T columns are allocated
-// (dense_matrix_doubles).  For the current system of n <= max_n scalars the right-hand side is row 64 ceil(n / 64) (tile
-// aligned), rows / columns n .. 64 ceil(n / 64) - 1 must be zero.  The factorisation is in place; x receives
-// 64 ceil(n / 64) doubles (zeros beyond n).  *not_spd is set on a non-positive pivot.  All work is enqueued on `st`.
-// Winv: dense_num_blocks(max_n) * 64 * 64 doubles; ws: dense_workspace_bytes(max_n), initialised once by dense_workspace_init.
+//
+// Layout of S for a handle whose pose block has at most max_n scalars (Tm = ceil(max_n / 64) tile columns): the LOWER
+// triangle of Hschur in 64 x 64 tiles, packed column by column (tile column j holds tile rows j .. Tm), every tile
+// contiguous: 64 columns of DENSE_CLD = 68 doubles (64 rows + 4 padding).  For the current system of n <= max_n scalars
+// (Tc = ceil(n / 64)) the reduced gradient is row 0 of tile row Tc; everything else in tile columns 0 .. Tc-1 beyond the
+// n x n matrix must be zero.  The factorisation is in place; x receives 64 Tc doubles (zeros beyond n).  *not_spd is set
+// on a non-positive pivot.  All work is enqueued on `st`.
+constexpr int DENSE_NB = 64;
+constexpr int DENSE_CLD = 68;
+constexpr int DENSE_TILE = DENSE_NB * DENSE_CLD;
+__host__ __device__ inline size_t dense_tile_index(int Tm, int i, int j) { return (size_t)j * (Tm + 1) - (size_t)j * (j - 1) / 2 + (size_t)(i - j); }
+// element (r, c), r >= c, of the lower triangle (r may also address the gradient row 64 Tc)
+__host__ __device__ inline size_t dense_elem_index(int Tm, int r, int c) {
+  return dense_tile_index(Tm, r >> 6, c >> 6) * (size_t)DENSE_TILE + (size_t)(c & 63) * DENSE_CLD + (size_t)(r & 63);
+}
+// Winv: dense_num_blocks(max_n) * DENSE_TILE doubles; ws: dense_workspace_bytes(max_n), initialised once by dense_workspace_init.
 void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, void *ws, int *not_spd, cudaStream_t st, long long *launches);
 int dense_num_blocks(int n);
-int dense_ld(int max_n);
 size_t dense_matrix_doubles(int max_n);
 size_t dense_x_doubles(int max_n);
 size_t dense_workspace_bytes(int max_n);
 void dense_workspace_init(void *ws, int max_n, cudaStream_t st);
 void dense_setup_device(int dev);
+void dense_debug_set_mid_event(cudaEvent_t e);  // test hook (tools/ubench/chol_test.cu): times the two kernels separately
+#ifdef PPO_CHOL_TIMING
+void dense_timing_fetch(long long out[16], bool reset);
+#endif
 }  // namespace ppo

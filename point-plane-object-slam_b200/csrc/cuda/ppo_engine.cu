@@ -331,7 +331,7 @@ static double cpe_chi_const(const ppo_ba_handle *h) {
     if (h->cpe_flags[e] & PPO_EF_LEVEL1) continue;
     double c = h->cpe_chi2[e];
     if (h->cpe_flags[e] & PPO_EF_ROBUST) {
-      const double d = h->P.huber_cuboid_plane, dsqr = d * d;
+      const double d = h->P.huber_cuboid_plane, dsqr = (double)(float)(d * d);  // float dsqr of RobustKernelHuber (robust_kernel_impl.h:84)
       if (c > dsqr) c = 2 * std::sqrt(c) * d - dsqr;
     }
     s += c;
@@ -632,7 +632,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   int n_free = 0;
   for (int i = 0; i < g.n_kf; i++) n_free += !kf_fixed[i];
   h->max_np = 6 * n_free + 9 * g.n_cu;
-  h->ld = dense_ld(h->max_np);  // tile-aligned layout of the reduced system (ppo_dense.h)
+  h->ld = dense_num_blocks(h->max_np);  // Tm: tile columns of the (tiled, packed lower) reduced system, see ppo_dense.h
   DA(g.Hpp_kf, 36 * (size_t)g.n_kf); DA(g.Hpp_cu, 81 * (size_t)g.n_cu); DA(g.Hpc, 54 * (size_t)g.n_cbe); DA(g.bp, (size_t)h->max_np);
   DA(g.Hll, 6 * (size_t)g.n_lm); DA(g.bl, 3 * (size_t)g.n_lm); DA(g.Hpl, 18 * (size_t)g.n_ent); DA(g.BD, 18 * (size_t)g.n_ent); DA(g.Zent, 3 * (size_t)g.n_ent); DA(g.Dinv, 6 * (size_t)g.n_lm);
   DA(g.xl, 3 * (size_t)g.n_lm); DA(g.S, dense_matrix_doubles(h->max_np)); DA(g.xp, dense_x_doubles(h->max_np));
@@ -641,7 +641,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   h->nb_bs = cdiv(g.n_pl, BS_WARPS) + g.n_units;  // partial sums of k_backsub (planes) + k_backsub_points
   DA(h->d_chi_pt, (size_t)std::max(h->nb_lin, h->nb_res)); DA(h->d_chi_pl, (size_t)h->nb_pl); DA(h->d_chi_cb, (size_t)h->nb_cb); DA(h->d_chi_pc, (size_t)h->nb_pc);
   DA(h->d_scale_part, (size_t)h->nb_bs);
-  DA(h->d_Winv, (size_t)dense_num_blocks(h->max_np) * 64 * 64);
+  DA(h->d_Winv, (size_t)dense_num_blocks(h->max_np) * DENSE_TILE);
   {
     char *ws = nullptr;
     DA(ws, dense_workspace_bytes(h->max_np));
@@ -873,9 +873,10 @@ static void residual_kernels(ppo_ba_handle *h, const DevState &s) {
 static int schur_system(ppo_ba_handle *h, double lambda) {
   DevGraph &g = h->g;
   cudaStream_t st = h->st;
-  const int n_p = h->n_p, ld = h->ld;
-  const int grow = 64 * dense_num_blocks(n_p);  // row of the reduced gradient (tile aligned); 64-column tiles 0 .. grow/64 - 1
-  CK(cudaMemsetAsync(g.S, 0, 8 * (size_t)grow * ld, st));
+  const int n_p = h->n_p, ld = h->ld;  // ld = Tm (tile columns of the allocation)
+  const int Tc = dense_num_blocks(n_p), grow = 64 * Tc;  // row of the reduced gradient: first row of tile row Tc
+  const size_t s_used = dense_tile_index(ld, Tc, Tc) * (size_t)DENSE_TILE;  // tile columns 0 .. Tc-1 are one contiguous range
+  CK(cudaMemsetAsync(g.S, 0, 8 * s_used, st));
   CK(cudaMemsetAsync(h->d_not_spd, 0, sizeof(int), st));
   const int own = h->owner() ? 1 : 0;
   if (g.n_pl) { k_schur_bd<<<cdiv(g.n_pl, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, lambda, n_p, ld, own, g.n_pl); h->launches++; }
@@ -888,7 +889,7 @@ static int schur_system(ppo_ba_handle *h, double lambda) {
   const int n_comp = g.n_kf * 36 + g.n_cu * 81 + g.n_cbe * 54 + n_p;
   if (n_comp && own) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, lambda, n_p, ld, grow); h->launches++; }
   // single large window sharded over ranks: sum the partial reduced systems (Hschur | bschur) over NVLink
-  if (h->world > 1) return allreduce(h, g.S, (size_t)grow * ld, ncclFloat64_, ncclSum_);
+  if (h->world > 1) return allreduce(h, g.S, s_used, ncclFloat64_, ncclSum_);  // packed lower triangle + gradient row only
   return PPO_OK;
 }
 static int solve_and_backsub(ppo_ba_handle *h, double lambda) {
@@ -1353,13 +1354,14 @@ int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, do
   if ((rc = schur_system(h, lambda))) return rc;
   CK(cudaStreamSynchronize(h->st));
   if (Hschur_upper || bschur) {
-    const int grow = 64 * dense_num_blocks(n_p);
-    std::vector<double> S((size_t)(n_p + 1) * ld);
-    if (n_p) CK(cudaMemcpy(S.data(), g.S, 8 * (size_t)n_p * ld, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < n_p; i++) {
+    const int Tc = dense_num_blocks(n_p), grow = 64 * Tc;
+    const size_t s_used = dense_tile_index(ld, Tc, Tc) * (size_t)DENSE_TILE;
+    std::vector<double> S(s_used + 1);
+    if (n_p) CK(cudaMemcpy(S.data(), g.S, 8 * s_used, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n_p; i++) {  // upper (i, j) of the symmetric matrix = lower (j, i) of the tiled storage
       if (Hschur_upper)
-        for (int j = 0; j < n_p; j++) Hschur_upper[(size_t)i * n_p + j] = j >= i ? S[(size_t)i * ld + j] : 0.0;
-      if (bschur) bschur[i] = S[(size_t)i * ld + grow];
+        for (int j = 0; j < n_p; j++) Hschur_upper[(size_t)i * n_p + j] = j >= i ? S[dense_elem_index(ld, j, i)] : 0.0;
+      if (bschur) bschur[i] = S[dense_elem_index(ld, grow, i)];
     }
   }
   if ((rc = solve_and_backsub(h, lambda))) return rc;

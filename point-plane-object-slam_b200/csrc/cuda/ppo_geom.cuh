@@ -349,8 +349,9 @@ PPO_D int point_edge_error(const double p[3], const float intr[5], float ou, flo
   return 3;
 }
 // Huber weight rho'(e) (robust_kernel_impl.cpp:76-90); returns rho(e) through *rho0
+// (the reference keeps delta^2 in a float member, core/robust_kernel_impl.h:84: the rounded value enters the inlier test and rho)
 PPO_D double huber_w(double e, double delta, double *rho0) {
-  const double dsqr = delta * delta;
+  const double dsqr = (double)(float)(delta * delta);
   if (e <= dsqr) {
     *rho0 = e;
     return 1.0;

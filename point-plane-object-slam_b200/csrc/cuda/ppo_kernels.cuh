@@ -1,6 +1,7 @@
 // CUDA kernels of the local-BA engine (sm_100a).  All arithmetic is IEEE double like g2o.
 // Kernel inventory and the roofline that bounds each: DESIGN.md section 5.
 #pragma once
+#include "ppo_dense.h"
 #include "ppo_device.cuh"
 #include "ppo_geom.cuh"
 
@@ -919,13 +920,14 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
     if (cur != 0xffffffffu) {
       const unsigned ka = cur / (unsigned)g.n_kf, kb = cur - ka * (unsigned)g.n_kf;
       const int p1 = g.kf_idx[ka], p2 = g.kf_idx[kb];
-      if (p1 >= 0 && p2 >= 0 && row < 6) {
-        double *dst = &g.S[(size_t)(6 * p1 + row) * ld];
-        if (kk < 3) {
-          atomicAdd(dst + 6 * p2 + 2 * kk, -acc0);
-          atomicAdd(dst + 6 * p2 + 2 * kk + 1, -acc1);
+      if (p1 >= 0 && p2 >= 0 && row < 6) {  // upper (6 p1 + row, 6 p2 + col) = lower element (6 p2 + col, 6 p1 + row) of the tiled storage; ld = Tm
+        const int c = 6 * p1 + row;
+        if (kk < 3) {  // (diagonal blocks: the mirrored half is not stored)
+          const int r = 6 * p2 + 2 * kk;
+          if (r >= c) atomicAdd(&g.S[dense_elem_index(ld, r, c)], -acc0);
+          if (r + 1 >= c) atomicAdd(&g.S[dense_elem_index(ld, r + 1, c)], -acc1);
         } else if (ka == kb) {
-          atomicAdd(dst + grow, -acc0);  // bschur -= W Dinv bl
+          atomicAdd(&g.S[dense_elem_index(ld, grow, c)], -acc0);  // bschur -= W Dinv bl
         }
       }
     }
@@ -973,7 +975,7 @@ __global__ void k_compose(DevGraph g, double lambda, int n_p, int ld, int grow) 
     if (idx >= 0 && a <= b) {
       double v = g.Hpp_kf[36 * (size_t)idx + 6 * a + b];
       if (a == b) v += lambda;
-      atomicAdd(&g.S[(size_t)(6 * idx + a) * ld + 6 * idx + b], v);
+      atomicAdd(&g.S[dense_elem_index(ld, 6 * idx + b, 6 * idx + a)], v);
     }
   } else if (t < nkf + ncu) {
     const int u = t - nkf, cu = u / 81, a = (u % 81) / 9, b = u % 9;
@@ -981,17 +983,17 @@ __global__ void k_compose(DevGraph g, double lambda, int n_p, int ld, int grow) 
     if (off >= 0 && a <= b) {
       double v = g.Hpp_cu[81 * (size_t)cu + 9 * a + b];
       if (a == b) v += lambda;
-      atomicAdd(&g.S[(size_t)(off + a) * ld + off + b], v);
+      atomicAdd(&g.S[dense_elem_index(ld, off + b, off + a)], v);
     }
   } else if (t < nkf + ncu + nhpc) {
     const int u = t - nkf - ncu, e = u / 54, a = (u % 54) / 9, b = u % 9;
     if (!(g.cbe_flags[e] & PPO_EF_LEVEL1_)) {
       const int idx = g.kf_idx[g.cbe_kf[e]], off = g.cu_off[g.cbe_cuboid[e]];
-      if (idx >= 0 && off >= 0) atomicAdd(&g.S[(size_t)(6 * idx + a) * ld + off + b], g.Hpc[54 * (size_t)e + 9 * a + b]);
+      if (idx >= 0 && off >= 0) atomicAdd(&g.S[dense_elem_index(ld, off + b, 6 * idx + a)], g.Hpc[54 * (size_t)e + 9 * a + b]);
     }
   } else if (t < nkf + ncu + nhpc + n_p) {
     const int j = t - nkf - ncu - nhpc;
-    atomicAdd(&g.S[(size_t)j * ld + grow], g.bp[j]);
+    atomicAdd(&g.S[dense_elem_index(ld, grow, j)], g.bp[j]);
   }
 }
 

@@ -152,6 +152,7 @@ def point_cuboid_error(c, pts, ratio=1.0, prior=0.2):
 
 
 def huber(e, delta):
-    if e <= delta * delta:
+    dsqr = float(np.float32(delta * delta))  # "float dsqr" of the reference's RobustKernelHuber (core/robust_kernel_impl.h:84)
+    if e <= dsqr:
         return e, 1.0
-    return 2 * np.sqrt(e) * delta - delta * delta, delta / np.sqrt(e)
+    return 2 * np.sqrt(e) * delta - dsqr, delta / np.sqrt(e)

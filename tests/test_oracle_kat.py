@@ -181,10 +181,11 @@ def test_huber_at_threshold(L):
     d = float(np.float32(np.sqrt(5.991)))
     rho = _d(3)
     L.ppo_oracle_huber.argtypes = [C.c_double, C.c_double, C.c_void_p]
-    L.ppo_oracle_huber(d * d, d, rho)
-    assert rho[0] == d * d and rho[1] == 1.0
-    L.ppo_oracle_huber(d * d * (1 + 1e-12), d, rho)
-    assert rho[1] < 1.0 and abs(rho[0] - d * d) < 1e-9
+    dsqr = float(np.float32(d * d))  # the reference stores delta^2 in a float member (robust_kernel_impl.h:84); found by tests/test_ref_pin.py
+    L.ppo_oracle_huber(dsqr, d, rho)
+    assert rho[0] == dsqr and rho[1] == 1.0
+    L.ppo_oracle_huber(dsqr * (1 + 1e-12), d, rho)
+    assert rho[1] < 1.0 and abs(rho[0] - d * d) < 1e-6
     L.ppo_oracle_huber(100.0, 2.0, rho)
     assert np.allclose(list(rho), [2 * 10 * 2 - 4, 0.2, -0.5 * 0.2 / 100])
 
