@@ -251,8 +251,15 @@ int ppo_ba_reset(ppo_ba_handle *h);
 /* Device timing of individual phases of the last linearisation (CUDA events on the handle's
  * stream).  enable != 0 adds per-phase events to ppo_ba_optimize. */
 int ppo_ba_set_profiling(ppo_ba_handle *h, int enable);
-/* Number of kernel launches issued by this handle since creation. */
+/* Number of kernel launches issued by this handle since creation (kernels replayed by the captured LM graph are counted per replay). */
 long long ppo_ba_launch_count(const ppo_ba_handle *h);
+/* Number of times the host blocked on the device inside ppo_ba_optimize since creation.  With the LM controller on the device
+ * (default: the whole loop of core/optimization_algorithm_levenberg.cpp:61-164 runs as one CUDA graph with conditional WHILE nodes)
+ * an optimize() call blocks twice: once for the sizes of the index mapping, once for the result. */
+long long ppo_ba_host_sync_count(const ppo_ba_handle *h);
+/* enable = 0: drive the same device-side controller kernels from a host loop (one blocking read of two loop flags per damped trial)
+ * instead of the captured graph.  Profiling and sharded windows always use the host loop.  Default: enabled (env PPO_BA_NO_GRAPH=1 disables). */
+int ppo_ba_set_graph_mode(ppo_ba_handle *h, int enable);
 /* Runs ONLY the point-edge Jacobian/assembly kernel `reps` times on the current state and
  * returns its mean device time in ms (CUDA events on the handle's stream) and the algorithmic
  * bytes one launch moves.  Used by bench.py for the roofline object. */

@@ -107,9 +107,23 @@ struct ppo_ba_handle {
   int *h_dims = nullptr;
   // current mapping
   int n_p = 0, n_kf_free = 0, n_l = 0, n_active_edges = 0;
-  // LM state
-  double lambda = -1, ni = 2;
-  int nBad = 0;
+  // LM controller: state on the device (LmDev), inputs of a call (LmIn), host mirror of the final state
+  LmDev *d_lm = nullptr;
+  LmIn *d_lm_in = nullptr;
+  LmDev *h_lm = nullptr;   // pinned
+  LmIn *h_lm_in = nullptr; // pinned
+  int *h_stop = nullptr;   // pinned + mapped: the caller's stop flag is forwarded here while a graph runs
+  int *d_stop = nullptr;   // device view of h_stop
+  // captured LM loops (one per (n_p, n_l) of a window): nested conditional WHILE nodes over the iteration / trial bodies
+  struct LmGraph {
+    int n_p, n_l;
+    cudaGraphExec_t exec;
+    cudaGraph_t graph;
+    int nodes_iter, nodes_trial;
+  };
+  std::vector<LmGraph> lm_graphs;
+  bool use_graph = true;
+  long long host_syncs = 0;
   // sharding (multi-GPU, single window)
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -172,7 +186,15 @@ struct ppo_ba_handle {
     hstage_off += bytes;
     return PPO_OK;
   }
+  void drop_lm_graphs() {
+    for (auto &q : lm_graphs) {
+      cudaGraphExecDestroy(q.exec);
+      cudaGraphDestroy(q.graph);
+    }
+    lm_graphs.clear();
+  }
   void free_graph() {
+    drop_lm_graphs();  // they hold the device pointers of the window
     for (void *p : allocs) cudaFreeAsync(p, st);
     allocs.clear();
     have_graph = false;
@@ -229,6 +251,7 @@ void ppo_ba_default_params(ppo_ba_params *p) {
 int ppo_ba_create(const ppo_ba_params *params, int device, ppo_ba_handle **out) {
   if (!params || !out) return PPO_E_INVALID;
   int ndev = 0;
+  if (device < 0) return PPO_E_INVALID;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return PPO_E_NOGPU;
   ppo_ba_handle *h = new ppo_ba_handle();
   h->P = *params;
@@ -255,6 +278,14 @@ int ppo_ba_create(const ppo_ba_params *params, int device, ppo_ba_handle **out) 
   dense_setup_device(device);
   cudaMallocHost((void **)&h->h_scal, sizeof(Scalars));
   cudaMallocHost((void **)&h->h_dims, 8 * sizeof(int));
+  cudaMallocHost((void **)&h->h_lm, sizeof(LmDev));
+  cudaMallocHost((void **)&h->h_lm_in, sizeof(LmIn));
+  cudaHostAlloc((void **)&h->h_stop, sizeof(int), cudaHostAllocMapped);
+  if (h->h_stop) {
+    *h->h_stop = 0;
+    cudaHostGetDevicePointer((void **)&h->d_stop, h->h_stop, 0);
+  }
+  h->use_graph = std::getenv("PPO_BA_NO_GRAPH") == nullptr;
   *out = h;
   return PPO_OK;
 }
@@ -268,6 +299,9 @@ void ppo_ba_destroy(ppo_ba_handle *h) {
   if (h->hstage) cudaFreeHost(h->hstage);
   cudaFreeHost(h->h_scal);
   cudaFreeHost(h->h_dims);
+  cudaFreeHost(h->h_lm);
+  cudaFreeHost(h->h_lm_in);
+  if (h->h_stop) cudaFreeHost(h->h_stop);
   for (auto &q : h->side) {
     cudaStreamSynchronize(q);
     cudaStreamDestroy(q);
@@ -648,7 +682,8 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
     h->d_dense_ws = ws;
     dense_workspace_init(ws, h->max_np, h->st);
   }
-  DA(h->d_scal, 1); DA(h->d_not_spd, 1); DA(h->d_nout, 4); DA(h->d_red, 4);
+  DA(h->d_scal, 1); DA(h->d_not_spd, 1); DA(h->d_nout, 4); DA(h->d_red, 4); DA(h->d_lm, 1); DA(h->d_lm_in, 1);
+  CK(cudaMemsetAsync(h->d_lm, 0, sizeof(LmDev), h->st));
   CK(cudaMemsetAsync(g.pe_chi2, 0, 8 * (size_t)g.n_pe, h->st));
   CK(cudaMemsetAsync(g.ple_chi2, 0, 8 * (size_t)g.n_ple, h->st));
   CK(cudaMemsetAsync(g.cbe_chi2, 0, 8 * (size_t)g.n_cbe, h->st));
@@ -678,7 +713,6 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
     }
   }
   h->have_graph = true;
-  h->lambda = -1;
   return PPO_OK;
 #undef UP
 #undef DA
@@ -755,9 +789,8 @@ static int init_mapping(ppo_ba_handle *h) {
 }
 
 // ---- computeActiveErrors + buildSystem at the current estimates -------------------------------------------
-// wait == false: the scalars are not read by the caller (LM iterations after the first know chi2 of the current estimate
-// from the accepted trial), so the host goes straight on to enqueue the damped solve behind the linearisation.
-static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kernel = false, bool wait = true) {
+// Enqueues only (capturable in a CUDA graph): the scalars {chi2, max diagonal} stay in d_scal for the LM controller kernel.
+static int linearize(ppo_ba_handle *h, bool only_points_kernel = false) {
   DevGraph &g = h->g;
   cudaStream_t st = h->st;
   const DevState &s = h->sa;
@@ -770,8 +803,9 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
     CK(cudaMemsetAsync(g.Hpl, 0, 8 * 18 * (size_t)g.n_slots, st));
   }
   if (h->profiling) cudaEventRecord(h->evp[0], st);
-  // single GPU: the plane / cuboid / point-cuboid edges (numeric Jacobians, few 10^4 threads, latency-bound) run on
-  // three side streams next to the point kernels; all sides only meet in atomically-updated accumulators.
+  // the plane / cuboid / point-cuboid edges (numeric Jacobians, few 10^4 threads, latency-bound) run on three side streams next
+  // to the point kernels; all sides only meet in atomically-updated accumulators.  Sharded: the cross-rank sum of the point
+  // edges' pose blocks sits between the point kernels and the replicated edges on the main stream, so those stay there.
   const bool fork = h->world == 1 && !only_points_kernel && (g.n_ple || g.n_cbe || g.n_pce);
   const bool use_side[3] = {fork && g.n_ple > 0, fork && g.n_cbe > 0, fork && g.n_pce > 0};
   cudaStream_t s_pl = use_side[0] ? h->side[0] : st, s_cb = use_side[1] ? h->side[1] : st, s_pc = use_side[2] ? h->side[2] : st;
@@ -818,28 +852,34 @@ static int linearize(ppo_ba_handle *h, bool want_max_diag, bool only_points_kern
   if (h->profiling) cudaEventRecord(h->evp[1], st);
   const bool own = h->owner();  // replicated (non-point) edges count once: on rank 0
   k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
-                              (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, cpe_chi_const(h), nullptr, 0, 0.0, 0,
-                              nullptr, h->d_red);
+                              (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, h->d_lm, own ? 1 : 0, nullptr, 0, 0, nullptr,
+                              h->d_red);
   h->launches++;
-  if (want_max_diag) {
-    CK(cudaMemsetAsync(&h->d_scal->max_diag, 0, sizeof(double), st));
-    k_max_diag<<<std::max(1, std::min(148, cdiv(3 * g.n_lm, 2048))), 256, 0, st>>>(g, h->d_scal);
-    h->launches++;
-  }
+  CK(cudaMemsetAsync(&h->d_scal->max_diag, 0, sizeof(double), st));
+  k_max_diag<<<std::max(1, std::min(148, cdiv(3 * g.n_lm, 2048))), 256, 0, st>>>(g, h->d_scal);
+  h->launches++;
   if (h->world > 1) {
     int rc;
     if ((rc = allreduce(h, h->d_red, 2, ncclFloat64_, ncclSum_))) return rc;
     k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 0);
-    if (want_max_diag) {
-      k_set_red_maxdiag<<<1, 32, 0, st>>>(h->d_scal, h->d_red);
-      if ((rc = allreduce(h, h->d_red + 2, 1, ncclFloat64_, ncclMax_))) return rc;
-      k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 1);
-    }
+    k_set_red_maxdiag<<<1, 32, 0, st>>>(h->d_scal, h->d_red);
+    if ((rc = allreduce(h, h->d_red + 2, 1, ncclFloat64_, ncclMax_))) return rc;
+    k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 1);
   }
-  if (!wait) return PPO_OK;
-  CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  return PPO_OK;
+}
+// linearisation + scalars on the host (debug / timing entry points)
+static int linearize_sync(ppo_ba_handle *h) {
+  int rc = linearize(h);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
   CK(cudaGetLastError());
+  return PPO_OK;
+}
+// writes the LM inputs of a call / an explicit damping (debug entry points) into the device-side controller state
+static int set_device_lambda(ppo_ba_handle *h, double lambda) {
+  CK(cudaMemcpyAsync(&h->d_lm->lambda, &lambda, sizeof(double), cudaMemcpyHostToDevice, h->st));
   return PPO_OK;
 }
 
@@ -870,7 +910,7 @@ static void residual_kernels(ppo_ba_handle *h, const DevState &s) {
 }
 
 // ---- setLambda + Schur complement (+ optional factorisation / back-substitution) ----------------------------
-static int schur_system(ppo_ba_handle *h, double lambda) {
+static int schur_system(ppo_ba_handle *h) {
   DevGraph &g = h->g;
   cudaStream_t st = h->st;
   const int n_p = h->n_p, ld = h->ld;  // ld = Tm (tile columns of the allocation)
@@ -879,20 +919,20 @@ static int schur_system(ppo_ba_handle *h, double lambda) {
   CK(cudaMemsetAsync(g.S, 0, 8 * s_used, st));
   CK(cudaMemsetAsync(h->d_not_spd, 0, sizeof(int), st));
   const int own = h->owner() ? 1 : 0;
-  if (g.n_pl) { k_schur_bd<<<cdiv(g.n_pl, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, lambda, n_p, ld, own, g.n_pl); h->launches++; }
-  if (g.n_units) { k_schur_bd_points<<<g.n_units, 32, 0, st>>>(g, lambda); h->launches++; }
+  if (g.n_pl) { k_schur_bd<<<cdiv(g.n_pl, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, h->d_lm, n_p, ld, own, g.n_pl); h->launches++; }
+  if (g.n_units) { k_schur_bd_points<<<g.n_units, 32, 0, st>>>(g, h->d_lm); h->launches++; }
   if (h->n_pairs) {
     const int n_warps = cdiv(h->n_pairs, PAIR_CHUNK);
     k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld, grow);
     h->launches++;
   }
   const int n_comp = g.n_kf * 36 + g.n_cu * 81 + g.n_cbe * 54 + n_p;
-  if (n_comp && own) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, lambda, n_p, ld, grow); h->launches++; }
+  if (n_comp && own) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, h->d_lm, n_p, ld, grow); h->launches++; }
   // single large window sharded over ranks: sum the partial reduced systems (Hschur | bschur) over NVLink
   if (h->world > 1) return allreduce(h, g.S, s_used, ncclFloat64_, ncclSum_);  // packed lower triangle + gradient row only
   return PPO_OK;
 }
-static int solve_and_backsub(ppo_ba_handle *h, double lambda) {
+static int solve_and_backsub(ppo_ba_handle *h) {
   DevGraph &g = h->g;
   dense_cholesky_solve(g.S, h->n_p, h->max_np, g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches);
   // planes: one warp per landmark; points: one lane per 6x3 block (work units of the linearisation); partial sums of the
@@ -904,12 +944,100 @@ static int solve_and_backsub(ppo_ba_handle *h, double lambda) {
     CK(cudaEventRecord(h->ev_fork, h->st));
     CK(cudaStreamWaitEvent(s_pl, h->ev_fork, 0));
   }
-  if (g.n_pl) { k_backsub<<<nbp, BS_WARPS * 32, 0, s_pl>>>(g, lambda, h->d_scale_part, h->owner() ? 1 : 0, g.n_pl); h->launches++; }
-  if (g.n_units) { k_backsub_points<<<g.n_units, 32, 0, h->st>>>(g, lambda, h->d_scale_part + nbp); h->launches++; }
+  if (g.n_pl) { k_backsub<<<nbp, BS_WARPS * 32, 0, s_pl>>>(g, h->d_lm, h->d_scale_part, h->owner() ? 1 : 0, g.n_pl); h->launches++; }
+  if (g.n_units) { k_backsub_points<<<g.n_units, 32, 0, h->st>>>(g, h->d_lm, h->d_scale_part + nbp); h->launches++; }
   if (fork) {
     CK(cudaEventRecord(h->ev_join[0], s_pl));
     CK(cudaStreamWaitEvent(h->st, h->ev_join[0], 0));
   }
+  return PPO_OK;
+}
+
+// ---- one damped trial: setLambda + Schur + solve + back-substitution + update + computeActiveErrors + scalars (enqueue only) ----
+static int enqueue_trial(ppo_ba_handle *h) {
+  DevGraph &g = h->g;
+  cudaStream_t st = h->st;
+  int rc;
+  if (h->profiling) cudaEventRecord(h->evp[2], st);
+  if ((rc = schur_system(h))) return rc;
+  if (h->profiling) cudaEventRecord(h->evp[3], st);
+  if ((rc = solve_and_backsub(h))) return rc;
+  if (h->profiling) cudaEventRecord(h->evp[4], st);
+  const int nv = g.n_kf + g.n_cu + g.n_pl + g.n_pt;
+  k_update<<<cdiv(nv, 128), 128, 0, st>>>(g, h->sa, h->sb);
+  h->launches++;
+  residual_kernels(h, h->sb);
+  const bool own = h->owner();
+  k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_pe ? h->nb_res : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
+                              (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, h->d_lm, own ? 1 : 0, h->d_scale_part,
+                              g.n_lm ? h->nb_bs : 0, own ? h->n_p : 0, h->d_not_spd, h->d_red);
+  h->launches++;
+  if (h->world > 1) {
+    if ((rc = allreduce(h, h->d_red, 2, ncclFloat64_, ncclSum_))) return rc;
+    k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 0);
+  }
+  if (h->profiling) cudaEventRecord(h->evp[5], st);
+  return PPO_OK;
+}
+static void enqueue_decide(ppo_ba_handle *h, int graph, cudaGraphConditionalHandle h_trial, cudaGraphConditionalHandle h_iter) {
+  DevGraph &g = h->g;
+  k_lm_decide<<<1, 32, 0, h->st>>>(h->d_lm, h->d_scal, h->d_stop, graph, h_trial, h_iter);
+  const size_t n = 3 * (size_t)g.n_pt + 19 * (size_t)g.n_kf;
+  k_accept<<<(int)std::max<size_t>(1, std::min<size_t>(592, (n + 255) / 256)), 256, 0, h->st>>>(g, h->sa, h->sb, h->d_lm);
+  h->launches += 2;
+}
+
+// The whole LM loop of one optimize() as ONE graph:  k_lm_begin -> WHILE(iteration){ linearise, k_lm_iter_begin, WHILE(trial){ trial,
+// k_lm_decide, k_accept } }.  Bodies are stream-captured from the same enqueue functions the host-driven path uses.
+static int build_lm_graph(ppo_ba_handle *h, ppo_ba_handle::LmGraph *out) {
+  cudaStream_t st = h->st;
+  cudaGraph_t G = nullptr, tmp = nullptr;
+  CK(cudaGraphCreate(&G, 0));
+  cudaGraphConditionalHandle h_iter, h_trial;
+  CK(cudaGraphConditionalHandleCreate(&h_iter, G, 0, 0));
+  auto add_while = [&](cudaGraph_t parent, cudaGraphConditionalHandle hd, cudaGraph_t *body) -> int {
+    cudaStreamCaptureStatus cs;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t ndeps = 0;
+    CK(cudaStreamGetCaptureInfo(st, &cs, nullptr, nullptr, &deps, &ndeps));
+    cudaGraphNodeParams p = {};
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = hd;
+    p.conditional.type = cudaGraphCondTypeWhile;
+    p.conditional.size = 1;
+    cudaGraphNode_t node;
+    CK(cudaGraphAddNode(&node, parent, deps, ndeps, &p));
+    *body = p.conditional.phGraph_out[0];
+    CK(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+    return PPO_OK;
+  };
+  const long long l0 = h->launches;
+  int rc;
+  cudaGraph_t body_iter = nullptr, body_trial = nullptr;
+  CK(cudaStreamBeginCaptureToGraph(st, G, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  k_lm_begin<<<1, 32, 0, st>>>(h->d_lm, h->d_lm_in, 1, h_iter);
+  rc = add_while(G, h_iter, &body_iter);
+  cudaStreamEndCapture(st, &tmp);
+  if (rc) return rc;
+  CK(cudaGraphConditionalHandleCreate(&h_trial, body_iter, 0, 0));
+  CK(cudaStreamBeginCaptureToGraph(st, body_iter, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  rc = linearize(h);
+  k_lm_iter_begin<<<1, 32, 0, st>>>(h->d_lm, h->d_scal, 1, h_trial);
+  h->launches++;
+  if (!rc) rc = add_while(body_iter, h_trial, &body_trial);
+  cudaStreamEndCapture(st, &tmp);
+  if (rc) return rc;
+  const long long l1 = h->launches;
+  CK(cudaStreamBeginCaptureToGraph(st, body_trial, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  rc = enqueue_trial(h);
+  enqueue_decide(h, 1, h_trial, h_iter);
+  cudaStreamEndCapture(st, &tmp);
+  if (rc) return rc;
+  const long long l2 = h->launches;
+  h->launches = l0;  // nothing ran yet: launches are counted per replay
+  out->graph = G;
+  out->nodes_iter = (int)(l1 - l0), out->nodes_trial = (int)(l2 - l1);
+  CK(cudaGraphInstantiate(&out->exec, G, 0));
   return PPO_OK;
 }
 
@@ -918,126 +1046,106 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
   if (!h || !h->have_graph) return PPO_E_INVALID;
   CK(cudaSetDevice(h->device));
   if (stats) std::memset(stats, 0, sizeof *stats);
-  DevGraph &g = h->g;
   cudaStream_t st = h->st;
   CK(cudaEventRecord(h->ev0, st));
-  int rc = init_mapping(h);
+  int rc = init_mapping(h);  // (host sync 1: the sizes of the reduced system decide the launch shapes)
   if (rc) return rc;
-  if (h->n_p + h->n_l == 0) return PPO_E_EMPTY;
-  auto terminate = [&]() { return stop && *stop; };
-  const ppo_ba_params &P = h->P;
-  int done = 0, term = 0;
-  bool ok = true;
-  float ms;
-  double chi_state = 0;  // robust chi2 of the current estimate: from the linearisation (first iteration), then from the accepted trials
-  for (int it = 0; it < iters && !terminate() && ok; it++) {
-    const bool wait = it == 0 || h->profiling;
-    if ((rc = linearize(h, it == 0, false, wait))) return rc;
-    double currentChi = wait ? h->h_scal->chi2 : chi_state, tempChi = currentChi;
-    const double iniChi = currentChi;
-    if (stats && it == 0) stats->chi2_initial = currentChi;
-    if (it == 0) {
-      h->lambda = P.lm_tau * h->h_scal->max_diag;  // computeLambdaInit
-      h->ni = 2;
-      h->nBad = 0;
-    }
-    if (h->profiling && stats) {
-      cudaEventElapsedTime(&ms, h->evp[0], h->evp[1]);
-      stats->ms_linearize += ms;
-    }
-    double rho = 0;
-    int qmax = 0;
-    bool accepted = false;
-    do {
-      if (h->profiling) cudaEventRecord(h->evp[2], st);
-      if ((rc = schur_system(h, h->lambda))) return rc;
-      if (h->profiling) cudaEventRecord(h->evp[3], st);
-      if ((rc = solve_and_backsub(h, h->lambda))) return rc;
-      if (h->profiling) cudaEventRecord(h->evp[4], st);
-      const int nv = g.n_kf + g.n_cu + g.n_pl + g.n_pt;
-      k_update<<<cdiv(nv, 128), 128, 0, st>>>(g, h->sa, h->sb);
-      h->launches++;
-      residual_kernels(h, h->sb);
-      {
-        const bool own = h->owner();
-        k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_pe ? h->nb_res : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
-                                    (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, cpe_chi_const(h), h->d_scale_part,
-                                    g.n_lm ? h->nb_bs : 0, h->lambda, own ? h->n_p : 0, h->d_not_spd, h->d_red);
-        h->launches++;
-        if (h->world > 1) {
-          if ((rc = allreduce(h, h->d_red, 2, ncclFloat64_, ncclSum_))) return rc;
-          k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 0);
-        }
-      }
-      if (h->profiling) cudaEventRecord(h->evp[5], st);
-      CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(Scalars), cudaMemcpyDeviceToHost, st));
+  h->host_syncs++;
+  {  // all ranks of a sharded window must take the same branch: emptiness of the UNION of the shards
+    int n_l_all = h->n_l;
+    if (h->world > 1) {
+      int *d = reinterpret_cast<int *>(h->d_red + 3);
+      CK(cudaMemcpyAsync(d, &n_l_all, sizeof(int), cudaMemcpyHostToDevice, st));
+      if ((rc = allreduce(h, d, 1, ncclInt32_, ncclSum_))) return rc;
+      CK(cudaMemcpyAsync(&n_l_all, d, sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      CK(cudaGetLastError());
-      if (h->profiling && stats) {
-        cudaEventElapsedTime(&ms, h->evp[2], h->evp[3]); stats->ms_schur += ms;
-        cudaEventElapsedTime(&ms, h->evp[3], h->evp[4]); stats->ms_solve += ms;
-        cudaEventElapsedTime(&ms, h->evp[4], h->evp[5]); stats->ms_update += ms;
-      }
-      const bool ok2 = !h->h_scal->not_spd;
-      tempChi = h->h_scal->chi2;
-      if (!ok2) tempChi = std::numeric_limits<double>::max();
-      rho = (currentChi - tempChi);
-      double scale = h->h_scal->scale;
-      scale += 1e-3;
-      rho /= scale;
-      if (rho > 0 && std::isfinite(tempChi)) {
-        double alpha = 1. - std::pow((2 * rho - 1), 3);
-        alpha = std::min(alpha, P.lm_good_upper);
-        const double scaleFactor = std::max(P.lm_good_lower, alpha);
-        h->lambda *= scaleFactor;
-        h->ni = 2;
-        currentChi = tempChi;
-        std::swap(h->sa, h->sb);  // discardTop: the trial becomes the estimate
-        accepted = true;
-      } else {
-        h->lambda *= h->ni;
-        h->ni *= 2;
-        accepted = false;  // pop: sa is untouched
-      }
-      qmax++;
-    } while (rho < 0 && qmax < P.lm_max_trials && !terminate());
-    done++;
-    chi_state = currentChi;
-    if (stats) {
-      stats->total_trials += qmax;
-      if (it < PPO_TRACE_MAX) {
-        ppo_ba_iter &r = stats->trace[it];
-        r.chi2_before = iniChi;
-        r.chi2_after = currentChi;
-        r.lambda = h->lambda;
-        r.rho = rho;
-        r.trials = qmax;
-        r.accepted = accepted;
-      }
-      stats->chi2_final = currentChi;
     }
-    if (qmax == P.lm_max_trials || rho == 0) {
-      ok = false;
-      term = 1;
-    } else {
-      if ((iniChi - currentChi) * 1e3 < iniChi) h->nBad++;
-      else h->nBad = 0;
-      if (h->nBad >= 3) {
-        ok = false;
-        term = 1;
-      }
-    }
+    if (h->n_p + n_l_all == 0) return PPO_E_EMPTY;
   }
-  CK(cudaEventRecord(h->ev1, st));
-  CK(cudaEventSynchronize(h->ev1));
+  const ppo_ba_params &P = h->P;
+  LmIn &in = *h->h_lm_in;
+  in.iters = (stop && *stop) ? 0 : iters;  // SparseOptimizer::optimize tests terminate() at the loop head
+  in.max_trials = P.lm_max_trials, in.tau = P.lm_tau, in.good_upper = P.lm_good_upper, in.good_lower = P.lm_good_lower;
+  in.chi_const = cpe_chi_const(h);
+  CK(cudaMemcpyAsync(h->d_lm_in, h->h_lm_in, sizeof(LmIn), cudaMemcpyHostToDevice, st));
+  *h->h_stop = (stop && *stop) ? 1 : 0;
+  const bool graph = h->use_graph && h->world == 1 && !h->profiling;
+  float ms;
+  if (graph) {
+    ppo_ba_handle::LmGraph *G = nullptr;
+    for (auto &q : h->lm_graphs)
+      if (q.n_p == h->n_p && q.n_l == h->n_l) G = &q;
+    if (!G) {
+      ppo_ba_handle::LmGraph q;
+      q.n_p = h->n_p, q.n_l = h->n_l;
+      if ((rc = build_lm_graph(h, &q))) return rc;
+      h->lm_graphs.push_back(q);
+      G = &h->lm_graphs.back();
+    }
+    CK(cudaGraphLaunch(G->exec, st));
+    CK(cudaMemcpyAsync(h->h_lm, h->d_lm, sizeof(LmDev), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->ev1, st));
+    if (stop) {  // forward the caller's flag to the device while the loop runs (polled by k_lm_decide, like g2o between trials)
+      while (cudaEventQuery(h->ev1) == cudaErrorNotReady)
+        if (*stop) *(volatile int *)h->h_stop = 1;
+    }
+    CK(cudaEventSynchronize(h->ev1));  // (host sync 2)
+    h->host_syncs++;
+    CK(cudaGetLastError());
+    h->launches += 1 + (long long)h->h_lm->done * G->nodes_iter + (long long)h->h_lm->total_trials * G->nodes_trial;
+  } else {
+    // host-driven loop over the same kernels (profiling with per-phase events; sharded windows, whose collectives sit between
+    // the kernels): the host only mirrors the two loop flags of the device-side controller
+    k_lm_begin<<<1, 32, 0, st>>>(h->d_lm, h->d_lm_in, 0, 0);
+    h->launches++;
+    int *flags = reinterpret_cast<int *>(h->h_scal);  // pinned scratch: {trial_continue, iter_continue}
+    bool iter_continue = in.iters > 0;
+    while (iter_continue) {
+      if ((rc = linearize(h))) return rc;
+      k_lm_iter_begin<<<1, 32, 0, st>>>(h->d_lm, h->d_scal, 0, 0);
+      h->launches++;
+      bool first = true;
+      bool trial_continue = true;
+      while (trial_continue) {
+        if (stop && *stop) *(volatile int *)h->h_stop = 1;
+        if ((rc = enqueue_trial(h))) return rc;
+        enqueue_decide(h, 0, 0, 0);
+        CK(cudaMemcpyAsync(flags, &h->d_lm->trial_continue, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        h->host_syncs++;
+        CK(cudaGetLastError());
+        if (h->profiling && stats) {
+          if (first) {
+            cudaEventElapsedTime(&ms, h->evp[0], h->evp[1]);
+            stats->ms_linearize += ms;
+          }
+          cudaEventElapsedTime(&ms, h->evp[2], h->evp[3]); stats->ms_schur += ms;
+          cudaEventElapsedTime(&ms, h->evp[3], h->evp[4]); stats->ms_solve += ms;
+          cudaEventElapsedTime(&ms, h->evp[4], h->evp[5]); stats->ms_update += ms;
+        }
+        first = false;
+        trial_continue = flags[0] != 0;
+        iter_continue = flags[1] != 0;
+      }
+    }
+    CK(cudaMemcpyAsync(h->h_lm, h->d_lm, sizeof(LmDev), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->ev1, st));
+    CK(cudaEventSynchronize(h->ev1));
+    h->host_syncs++;
+  }
   if (stats) {
+    const LmDev &lm = *h->h_lm;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     stats->ms_total = ms;
-    stats->iterations = done;
-    stats->terminated = term ? term : (terminate() ? 2 : 0);
+    stats->iterations = lm.done;
+    stats->terminated = lm.term ? lm.term : ((lm.stop_seen || (stop && *stop)) ? 2 : 0);
     stats->n_pose_dim = h->n_p;
     stats->n_landmarks = h->n_l;
     stats->n_active_edges = h->n_active_edges;
+    stats->total_trials = lm.total_trials;
+    stats->chi2_initial = lm.chi2_initial;
+    stats->chi2_final = lm.done ? lm.currentChi : 0.0;
+    for (int i = 0; i < lm.done && i < PPO_TRACE_MAX; i++) stats->trace[i] = lm.trace[i];
   }
   return PPO_OK;
 }
@@ -1163,6 +1271,7 @@ int ppo_ba_local_ba(ppo_ba_handle *h, const volatile unsigned char *stop, ppo_ba
     return PPO_OK;
   }
   int rc = ppo_ba_optimize(h, h->P.iters_round1, stop, &res->round1);
+  if (rc == PPO_E_EMPTY) rc = PPO_OK;  // g2o only logs "0 vertices to optimize" (core/sparse_optimizer.cpp:356-359); the caller's outlier pass, erase lists and write-back still run
   if (rc != PPO_OK) return rc;
   if (!(stop && *stop)) {
     int32_t n_out[3];
@@ -1204,6 +1313,12 @@ int ppo_ba_set_profiling(ppo_ba_handle *h, int enable) {
   return PPO_OK;
 }
 long long ppo_ba_launch_count(const ppo_ba_handle *h) { return h ? h->launches : 0; }
+long long ppo_ba_host_sync_count(const ppo_ba_handle *h) { return h ? h->host_syncs : 0; }
+int ppo_ba_set_graph_mode(ppo_ba_handle *h, int enable) {
+  if (!h) return PPO_E_INVALID;
+  h->use_graph = enable != 0;
+  return PPO_OK;
+}
 
 static const size_t FLUSH_BYTES = 256ull << 20;
 int ppo_ba_flush_l2(ppo_ba_handle *h) {
@@ -1239,7 +1354,7 @@ int ppo_ba_time_assembly(ppo_ba_handle *h, int reps, double *ms_mean, double *al
   for (int i = 0; i < 3; i++) {
     CK(cudaMemsetAsync(g.Hll, 0, 8 * 6 * (size_t)g.n_lm, h->st));
     CK(cudaMemsetAsync(g.bl, 0, 8 * 3 * (size_t)g.n_lm, h->st));
-    if ((rc = linearize(h, false, true))) return rc;
+    if ((rc = linearize(h, true))) return rc;
   }
   double total = 0;
   for (int i = 0; i < reps; i++) {
@@ -1270,11 +1385,12 @@ int ppo_ba_time_solve(ppo_ba_handle *h, int reps, double *ms_mean, double *flops
   CK(cudaSetDevice(h->device));
   int rc = init_mapping(h);
   if (rc) return rc;
-  if ((rc = linearize(h, true))) return rc;
+  if ((rc = linearize_sync(h))) return rc;
   const double lambda = h->P.lm_tau * h->h_scal->max_diag;
+  if ((rc = set_device_lambda(h, lambda))) return rc;
   double total = 0;
   for (int i = 0; i < reps + 2; i++) {
-    if ((rc = schur_system(h, lambda))) return rc;
+    if ((rc = schur_system(h))) return rc;
     CK(cudaEventRecord(h->ev0, h->st));
     dense_cholesky_solve(h->g.S, h->n_p, h->max_np, h->g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches);
     CK(cudaEventRecord(h->ev1, h->st));
@@ -1297,7 +1413,11 @@ int ppo_ba_debug_linearize(ppo_ba_handle *h, int32_t dims[2], double *Hpp, doubl
   DevGraph &g = h->g;
   int rc = init_mapping(h);
   if (rc) return rc;
-  if ((rc = linearize(h, true))) return rc;
+  {  // chi2 includes the constant cuboid-plane term: hand it to the device-side controller state
+    const double cc = cpe_chi_const(h);
+    CK(cudaMemcpyAsync(&h->d_lm->chi_const, &cc, sizeof(double), cudaMemcpyHostToDevice, h->st));
+  }
+  if ((rc = linearize_sync(h))) return rc;
   const int n_p = h->n_p;
   dims[0] = n_p;
   dims[1] = h->n_l;
@@ -1351,7 +1471,8 @@ int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, do
   DevGraph &g = h->g;
   const int n_p = h->n_p, ld = h->ld;
   int rc;
-  if ((rc = schur_system(h, lambda))) return rc;
+  if ((rc = set_device_lambda(h, lambda))) return rc;
+  if ((rc = schur_system(h))) return rc;
   CK(cudaStreamSynchronize(h->st));
   if (Hschur_upper || bschur) {
     const int Tc = dense_num_blocks(n_p), grow = 64 * Tc;
@@ -1364,7 +1485,7 @@ int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, do
       if (bschur) bschur[i] = S[dense_elem_index(ld, grow, i)];
     }
   }
-  if ((rc = solve_and_backsub(h, lambda))) return rc;
+  if ((rc = solve_and_backsub(h))) return rc;
   int ns = 0;
   CK(cudaMemcpyAsync(&ns, h->d_not_spd, sizeof(int), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));

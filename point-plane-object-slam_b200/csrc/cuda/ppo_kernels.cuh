@@ -1,6 +1,7 @@
 // CUDA kernels of the local-BA engine (sm_100a).  All arithmetic is IEEE double like g2o.
 // Kernel inventory and the roofline that bounds each: DESIGN.md section 5.
 #pragma once
+#include "../../../include/ppo_ba.h"
 #include "ppo_dense.h"
 #include "ppo_device.cuh"
 #include "ppo_geom.cuh"
@@ -10,6 +11,23 @@ namespace ppo {
 #define PPO_EF_LEVEL1_ 1u
 #define PPO_EF_ROBUST_ 2u
 constexpr unsigned FULL = 0xffffffffu;
+
+// State of the Levenberg-Marquardt controller (OptimizationAlgorithmLevenberg::solve, core/optimization_algorithm_levenberg.cpp:61-164)
+// lives on the device: lambda, nu, the chi2 bookkeeping, the accept / reject decision, the trial and iteration counters, the
+// termination rules and the per-iteration trace.  Kernels that need the damping read it from here, so one damped trial is a
+// fixed sequence of launches that can be captured in a CUDA graph and replayed under conditional WHILE nodes.
+struct LmIn {  // written by the host before an optimize() call
+  int iters, max_trials;
+  double tau, good_upper, good_lower;
+  double chi_const;  // robust chi2 of the constant-residual cuboid-plane edges (they take no part in the linearisation)
+};
+struct LmDev {
+  double lambda, ni, currentChi, iniChi, tempChi, rho, chi_const, chi2_initial;
+  double tau, good_upper, good_lower;
+  int it, iters, qmax, max_trials, nBad, done, term, accepted, total_trials, stop_seen;
+  int trial_continue, iter_continue;  // loop flags (mirrored into the conditional handles when the loop runs as a graph)
+  ppo_ba_iter trace[PPO_TRACE_MAX];
+};
 constexpr double NUM_DELTA = 1e-9;                      // base_binary_edge.hpp:232
 constexpr double NUM_SCALAR = 1.0 / (2 * NUM_DELTA);    // :233
 
@@ -800,7 +818,8 @@ __global__ void k_gen_pairs(DevGraph g, const int *lm_pair_off, unsigned *keys, 
   }
 }
 constexpr int BD_WARPS = 8;
-__global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double lambda, int n_p, int ld, int planes_write_S, int n_first) {
+__global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, const LmDev *lm, int n_p, int ld, int planes_write_S, int n_first) {
+  const double lambda = lm->lambda;
   const int lane = threadIdx.x & 31;
   const int L = blockIdx.x * BD_WARPS + (threadIdx.x >> 5);
   if (L >= n_first) return;  // one warp per landmark: used for the planes (tens of blocks each)
@@ -846,7 +865,8 @@ __global__ void __launch_bounds__(BD_WARPS * 32) k_schur_bd(DevGraph g, double l
 }
 // Point landmarks: one lane per 6x3 block (the work units of k_point_linearize: every lane moves 144 contiguous bytes in and
 // out with 16-byte accesses); the 3x3 factorisation of the landmark is recomputed by each of its lanes.
-__global__ void __launch_bounds__(32) k_schur_bd_points(DevGraph g, double lambda) {
+__global__ void __launch_bounds__(32) k_schur_bd_points(DevGraph g, const LmDev *lm) {
+  const double lambda = lm->lambda;
   const int lane = threadIdx.x;
   const int e0 = g.unit_e0[blockIdx.x], e1 = g.unit_e0[blockIdx.x + 1];
   for (int e = e0 + lane; e < e1; e += 32) {
@@ -966,7 +986,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
 }
 
 // S += Hpp (+ lambda on the diagonal), rhs column += bp.  One thread per scalar of each block.
-__global__ void k_compose(DevGraph g, double lambda, int n_p, int ld, int grow) {
+__global__ void k_compose(DevGraph g, const LmDev *lm, int n_p, int ld, int grow) {
+  const double lambda = lm->lambda;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int nkf = g.n_kf * 36, ncu = g.n_cu * 81, nhpc = g.n_cbe * 54;
   if (t < nkf) {
@@ -1002,8 +1023,9 @@ __global__ void k_compose(DevGraph g, double lambda, int n_p, int ld, int grow) 
 // computeScale (levenberg.cpp:182-189).  One warp per landmark, lanes stride the contiguous blocks.
 // ---------------------------------------------------------------------------------------------
 constexpr int BS_WARPS = 8;
-__global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double lambda, double *scale_part, int planes_in_scale, int n_first) {
+__global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, const LmDev *lm, double *scale_part, int planes_in_scale, int n_first) {
   __shared__ double wsum[BS_WARPS];
+  const double lambda = lm->lambda;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = blockIdx.x * BS_WARPS + warp;
   double sc = 0;
@@ -1056,7 +1078,8 @@ __global__ void __launch_bounds__(BS_WARPS * 32) k_backsub(DevGraph g, double la
 // Point landmarks: same work units as k_point_linearize (a run of consecutive points with <= 32 blocks per warp), one
 // lane per 6x3 block: the lane reads its 144 contiguous bytes and the 6 pose increments, forms Hpl^T x_p, and a
 // segmented warp scan sums the blocks of each point; the last lane of a point applies Dinv.
-__global__ void __launch_bounds__(32) k_backsub_points(DevGraph g, double lambda, double *scale_part) {
+__global__ void __launch_bounds__(32) k_backsub_points(DevGraph g, const LmDev *lm, double *scale_part) {
+  const double lambda = lm->lambda;
   const int lane = threadIdx.x;
   const int unit = blockIdx.x;
   double sc = 0;
@@ -1232,9 +1255,10 @@ struct Scalars {
 // sums partial arrays in a fixed order; single block
 constexpr int SCAL_THREADS = 1024;  // one CTA, fixed summation order (deterministic)
 __global__ void __launch_bounds__(SCAL_THREADS) k_scalars(DevGraph g, Scalars *out, const double *chi_a, int na, const double *chi_b, int nb, const double *chi_c, int nc,
-                          const double *chi_d, int nd, double chi_const, const double *scale_part, int ns, double lambda, int n_p,
+                          const double *chi_d, int nd, const LmDev *lm, int with_const, const double *scale_part, int ns, int n_p,
                           const int *not_spd, double *red /* [chi2, scale] for the cross-rank reduction, may be null */) {
   __shared__ double sm[SCAL_THREADS / 32];
+  const double lambda = lm->lambda, chi_const = with_const ? lm->chi_const : 0.0;
   double c = 0, s = 0;
   for (int i = threadIdx.x; i < na; i += SCAL_THREADS) c += chi_a[i];
   for (int i = threadIdx.x; i < nb; i += SCAL_THREADS) c += chi_b[i];
@@ -1289,6 +1313,109 @@ __global__ void k_scalars_from_red(Scalars *out, const double *red, int which) {
 }
 __global__ void k_set_red_maxdiag(const Scalars *in, double *red) {
   if (threadIdx.x == 0 && blockIdx.x == 0) red[2] = in->max_diag;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Levenberg-Marquardt controller on the device (levenberg.cpp:61-164).  One thread each; `graph` != 0: the loop flags are
+// also written into the conditional handles of the WHILE nodes that replay the captured iteration / trial bodies.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_lm_begin(LmDev *lm, const LmIn *in, int graph, cudaGraphConditionalHandle h_iter) {
+  if (threadIdx.x || blockIdx.x) return;
+  lm->iters = in->iters, lm->max_trials = in->max_trials;
+  lm->tau = in->tau, lm->good_upper = in->good_upper, lm->good_lower = in->good_lower, lm->chi_const = in->chi_const;
+  lm->it = 0, lm->done = 0, lm->term = 0, lm->total_trials = 0, lm->stop_seen = 0, lm->accepted = 0, lm->qmax = 0;
+  lm->lambda = -1.0, lm->ni = 2.0, lm->nBad = 0;
+  lm->currentChi = lm->iniChi = lm->tempChi = lm->rho = lm->chi2_initial = 0.0;
+  lm->iter_continue = in->iters > 0;
+  lm->trial_continue = 0;
+  if (graph) cudaGraphSetConditional(h_iter, lm->iter_continue);
+}
+// start of an outer iteration, after the linearisation: currentChi = activeRobustChi2() (:76), computeLambdaInit at iteration 0 (:93-97)
+__global__ void k_lm_iter_begin(LmDev *lm, const Scalars *scal, int graph, cudaGraphConditionalHandle h_trial) {
+  if (threadIdx.x || blockIdx.x) return;
+  lm->currentChi = scal->chi2;
+  lm->iniChi = lm->currentChi;
+  if (lm->it == 0) {
+    lm->chi2_initial = lm->currentChi;
+    lm->lambda = lm->tau * scal->max_diag;
+    lm->ni = 2.0;
+    lm->nBad = 0;
+  }
+  lm->qmax = 0;
+  lm->rho = 0.0;
+  lm->accepted = 0;
+  lm->trial_continue = 1;
+  if (graph) cudaGraphSetConditional(h_trial, 1);
+}
+// end of a damped trial (:126-152) and, when the trial loop ends, of the outer iteration (:154-161; SparseOptimizer::optimize loop head)
+__global__ void k_lm_decide(LmDev *lm, const Scalars *scal, const volatile int *stop, int graph, cudaGraphConditionalHandle h_trial,
+                            cudaGraphConditionalHandle h_iter) {
+  if (threadIdx.x || blockIdx.x) return;
+  const bool stopped = stop && *stop;
+  double tempChi = scal->chi2;
+  if (scal->not_spd) tempChi = 1.7976931348623157e308;  // solve failed: std::numeric_limits<double>::max() (:126-127)
+  double rho = lm->currentChi - tempChi;
+  const double scale = scal->scale + 1e-3;  // (:129-131)
+  rho /= scale;
+  lm->tempChi = tempChi;
+  if (rho > 0 && isfinite(tempChi)) {  // (:133-142)
+    double alpha = 1. - pow((2 * rho - 1), 3);
+    alpha = fmin(alpha, lm->good_upper);
+    const double scaleFactor = fmax(lm->good_lower, alpha);
+    lm->lambda *= scaleFactor;
+    lm->ni = 2;
+    lm->currentChi = tempChi;
+    lm->accepted = 1;  // discardTop: the trial becomes the estimate (k_accept)
+  } else {             // (:143-147)
+    lm->lambda *= lm->ni;
+    lm->ni *= 2;
+    lm->accepted = 0;  // pop
+  }
+  lm->rho = rho;
+  lm->qmax++;
+  const bool again = rho < 0 && lm->qmax < lm->max_trials && !stopped;  // (:149)
+  lm->trial_continue = again;
+  if (graph) cudaGraphSetConditional(h_trial, again);
+  if (again) return;
+  // ---- the outer iteration is over ----
+  const int it = lm->it;
+  lm->done++;
+  lm->total_trials += lm->qmax;
+  if (it < PPO_TRACE_MAX) {
+    ppo_ba_iter &r = lm->trace[it];
+    r.chi2_before = lm->iniChi;
+    r.chi2_after = lm->currentChi;
+    r.lambda = lm->lambda;
+    r.rho = rho;
+    r.trials = lm->qmax;
+    r.accepted = lm->accepted;
+  }
+  bool ok = true;
+  if (lm->qmax == lm->max_trials || rho == 0) {  // Terminate (:151-152)
+    ok = false;
+    lm->term = 1;
+  } else {  // Raul's rule (:155-161)
+    if ((lm->iniChi - lm->currentChi) * 1e3 < lm->iniChi) lm->nBad++;
+    else lm->nBad = 0;
+    if (lm->nBad >= 3) {
+      ok = false;
+      lm->term = 1;
+    }
+  }
+  lm->it = it + 1;
+  if (stopped) lm->stop_seen = 1;
+  lm->iter_continue = ok && lm->it < lm->iters && !stopped;
+  if (graph) cudaGraphSetConditional(h_iter, lm->iter_continue);
+}
+// discardTop / pop of the estimate stack: an accepted trial is copied over the current estimates
+__global__ void k_accept(DevGraph g, DevState cur, DevState tr, const LmDev *lm) {
+  if (!lm->accepted) return;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = t0; i < 7 * (size_t)g.n_kf; i += stride) cur.kf_pose[i] = tr.kf_pose[i];
+  for (size_t i = t0; i < 12 * (size_t)g.n_kf; i += stride) cur.kf_Rt[i] = tr.kf_Rt[i];
+  for (size_t i = t0; i < 3 * (size_t)g.n_pt; i += stride) cur.pt[i] = tr.pt[i];
+  for (size_t i = t0; i < 4 * (size_t)g.n_pl; i += stride) cur.pl[i] = tr.pl[i];
+  for (size_t i = t0; i < 10 * (size_t)g.n_cu; i += stride) cur.cu[i] = tr.cu[i];
 }
 
 // ---------------------------------------------------------------------------------------------

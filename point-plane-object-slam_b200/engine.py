@@ -56,6 +56,9 @@ def load_library():
         lib.ppo_ba_set_profiling.argtypes = [C.c_void_p, C.c_int]
         lib.ppo_ba_launch_count.argtypes = [C.c_void_p]
         lib.ppo_ba_launch_count.restype = C.c_longlong
+        lib.ppo_ba_host_sync_count.argtypes = [C.c_void_p]
+        lib.ppo_ba_host_sync_count.restype = C.c_longlong
+        lib.ppo_ba_set_graph_mode.argtypes = [C.c_void_p, C.c_int]
         lib.ppo_ba_time_assembly.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.ppo_ba_time_solve.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         lib.ppo_ba_mark.argtypes = [C.c_void_p, C.c_int]
@@ -203,6 +206,12 @@ class LocalBA(Handle):
 
     def launch_count(self):
         return int(self.lib.ppo_ba_launch_count(self.h))
+
+    def host_sync_count(self):
+        return int(self.lib.ppo_ba_host_sync_count(self.h))
+
+    def set_graph_mode(self, enable):
+        self._check(self.lib.ppo_ba_set_graph_mode(self.h, int(bool(enable))), "set_graph_mode")
 
     def time_assembly(self, reps=20):
         ms, by = C.c_double(), C.c_double()

@@ -360,3 +360,33 @@ def test_batch_variant_equals_one_window_at_a_time(ppo):
         assert (r.round1.iterations, r.round2.iterations, r.n_outlier_point_edges) == (a[0], a[1], a[3])
         assert np.isclose(r.round2.chi2_final, a[2], rtol=1e-6)  # atomics reorder sums: not bit-exact
         assert np.abs(e.get_state().kf_pose - a[4]).max() < 1e-5
+
+
+def test_lm_controller_on_device_graph_equals_host_loop(ppo):
+    """North star: "iterate Levenberg-Marquardt on device".  The LM controller (levenberg.cpp:61-164) is a set of device kernels;
+    by default one optimize() replays them as ONE CUDA graph with nested conditional WHILE nodes (two blocking host reads per
+    optimize(): index-mapping sizes + result), alternatively a host loop launches the same kernels and reads two loop flags per
+    trial.  Both must produce the same trace, and the graph path must not block per trial."""
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=14, n_pt=900, n_pl=6, n_cu=3))
+    out = []
+    for graph in (True, False):
+        e = ppo.LocalBA(ppo.default_params())
+        e.set_graph_mode(graph)
+        e.set_graph(g)
+        s0, l0 = e.host_sync_count(), e.launch_count()
+        r = e.local_ba()
+        out.append((r, e.get_state(), e.host_sync_count() - s0, e.launch_count() - l0))
+        e.close()
+    (rg, sg, syncs_g, launches_g), (rh, sh, syncs_h, launches_h) = out
+    trials = rg.round1.total_trials + rg.round2.total_trials
+    assert syncs_g == 4, syncs_g                      # 2 per optimize(), independent of the number of iterations / trials
+    assert syncs_h >= trials + 4                      # the host loop blocks once per damped trial
+    assert launches_g == launches_h                   # the same kernels ran
+    for a, b in ((rg.round1, rh.round1), (rg.round2, rh.round2)):
+        assert a.iterations == b.iterations and a.total_trials == b.total_trials and a.terminated == b.terminated
+        for x, y in zip(a.trace_list(), b.trace_list()):
+            assert x["trials"] == y["trials"] and x["accepted"] == y["accepted"]
+            # (two runs of the same path differ by this much too: order of the fp64 atomics in the Schur / plane / cuboid accumulators)
+            assert np.isclose(x["chi2_after"], y["chi2_after"], rtol=1e-7) and np.isclose(x["lam"], y["lam"], rtol=1e-4)
+    errs = state_errors(sg, sh)
+    assert all(v <= 1e-6 for v in errs.values()), errs
