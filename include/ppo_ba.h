@@ -196,6 +196,9 @@ void ppo_ba_default_params(ppo_ba_params *p);
 int ppo_ba_create(const ppo_ba_params *params, int device, ppo_ba_handle **out);
 void ppo_ba_destroy(ppo_ba_handle *h);
 const char *ppo_ba_last_error(const ppo_ba_handle *h);
+/* Replaces the configuration of an existing handle (the reference re-reads its globals, include/Parameters.h:45-76, on every
+ * call); cheaper than destroy + create: streams, pinned staging and the device memory pool are kept. */
+int ppo_ba_set_params(ppo_ba_handle *h, const ppo_ba_params *params);
 
 /* Replaces every optimizer.addVertex / addEdge of Optimizer.cc:2120-2714 (and :526-650).
  * Copies the graph to the device; all edges start at level 0 with their Huber kernel on

@@ -1004,6 +1004,11 @@ int ppo_oracle_create(const ppo_ba_params *params, ppo_oracle_handle **out) {
   return PPO_OK;
 }
 void ppo_oracle_destroy(ppo_oracle_handle *h) { delete h; }
+int ppo_oracle_set_params(ppo_oracle_handle *h, const ppo_ba_params *params) {
+  if (!h || !params) return PPO_E_INVALID;
+  h->P = *params;
+  return PPO_OK;
+}
 
 int ppo_oracle_set_graph(ppo_oracle_handle *h, const ppo_ba_graph *g) {
   if (!h || !g) return PPO_E_INVALID;

@@ -319,6 +319,19 @@ void ppo_ba_destroy(ppo_ba_handle *h) {
 
 const char *ppo_ba_last_error(const ppo_ba_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
+int ppo_ba_set_params(ppo_ba_handle *h, const ppo_ba_params *params) {
+  if (!h || !params) return PPO_E_INVALID;
+  h->P = *params;
+  if (h->have_graph) {  // constants the resident window carries (ppo_ba_set_graph copies them)
+    DevGraph &g = h->g;
+    g.huber_mono = h->P.huber_mono; g.huber_stereo = h->P.huber_stereo; g.huber_plane = h->P.huber_plane; g.huber_vp = h->P.huber_vp_plane;
+    g.huber_bbox = h->P.huber_bbox; g.huber_corner = h->P.huber_corner;
+    g.ptcu_ratio = h->P.ptcu_max_outside_margin_ratio; g.ptcu_prior = h->P.ptcu_prior_weight;
+    h->drop_lm_graphs();  // the captured kernels hold the old constants by value
+  }
+  return PPO_OK;
+}
+
 int ppo_ba_edge_count(const ppo_ba_handle *h, int kind) {
   switch (kind) {
     case PPO_EDGE_POINT: return h->g.n_pe;
@@ -1292,18 +1305,26 @@ int ppo_ba_get_state(ppo_ba_handle *h, ppo_ba_state *out) {
   const size_t nb[4] = {56 * (size_t)g.n_kf, 24 * (size_t)g.n_pt, 32 * (size_t)g.n_pl, 80 * (size_t)g.n_cu};
   const double *src[4] = {h->sa.kf_pose, h->sa.pt, h->sa.pl, h->sa.cu};
   double *dst[4] = {out->kf_pose, out->pt_xyz, out->pl_coef, out->cu_state};
-  void *stage[4] = {nullptr, nullptr, nullptr, nullptr};
-  const size_t keep = h->hstage_off;
-  int rc;
+  // ONE reservation for all requested members: growing the arena frees the old block, so pointers into it taken before a
+  // second reservation would dangle (the uploads of set_graph are drained by now, so the arena is re-used from its start)
+  CK(cudaStreamSynchronize(h->st));
+  size_t total = 0, off[4] = {0, 0, 0, 0};
   for (int k = 0; k < 4; k++)
     if (dst[k] && nb[k]) {
-      if ((rc = h->pinned(&stage[k], nb[k]))) return rc;
-      CK(cudaMemcpyAsync(stage[k], src[k], nb[k], cudaMemcpyDeviceToHost, h->st));
+      off[k] = total;
+      total += (nb[k] + 255) & ~(size_t)255;
     }
+  if (total == 0) return PPO_OK;
+  h->hstage_off = 0;
+  void *base = nullptr;
+  int rc;
+  if ((rc = h->pinned(&base, total))) return rc;
+  for (int k = 0; k < 4; k++)
+    if (dst[k] && nb[k]) CK(cudaMemcpyAsync((char *)base + off[k], src[k], nb[k], cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   for (int k = 0; k < 4; k++)
-    if (stage[k]) std::memcpy(dst[k], stage[k], nb[k]);
-  h->hstage_off = keep;
+    if (dst[k] && nb[k]) std::memcpy(dst[k], (char *)base + off[k], nb[k]);
+  h->hstage_off = 0;
   return PPO_OK;
 }
 

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cmath>
@@ -48,11 +49,13 @@ int ppo_oracle_recompute_edge_errors(ppo_oracle_handle *, int);
 int ppo_oracle_set_edge_flags(ppo_oracle_handle *, int, const unsigned char *);
 int ppo_oracle_local_ba(ppo_oracle_handle *, const volatile unsigned char *, ppo_ba_result *);
 int ppo_oracle_get_state(ppo_oracle_handle *, ppo_ba_state *);
+int ppo_oracle_set_params(ppo_oracle_handle *, const ppo_ba_params *);
 }
 #define ppo_ba_handle ppo_oracle_handle
 #define ppo_ba_default_params ppo_oracle_default_params
 #define ppo_ba_create(P, dev, out) ppo_oracle_create((P), (out))
 #define ppo_ba_destroy ppo_oracle_destroy
+#define ppo_ba_set_params ppo_oracle_set_params
 #define ppo_ba_set_graph ppo_oracle_set_graph
 #define ppo_ba_reset ppo_oracle_reset
 #define ppo_ba_optimize ppo_oracle_optimize
@@ -126,24 +129,37 @@ struct Flat {
   }
 };
 
-static std::mutex g_mutex;  // the reference calls the BA from the LocalMapping thread only; LoopClosing may race
-static ppo_ba_handle *g_handle = nullptr;
+// One engine handle, one flattened window and one mutex PER ENTRY POINT: in ORB-SLAM2 Tracking calls PoseOptimization on every
+// frame while LocalMapping runs the local BA and LoopClosing may run the global BA; with a single shared handle
+// Tracking would block for a whole local BA.  The handle of a slot (streams, events, pinned staging, the device memory pool) is
+// kept across calls; the reference's tuning globals are re-snapshotted on every call and, when they changed, set on the existing
+// handle (ppo_ba_set_params) instead of re-creating it.
+struct Slot {
+  std::mutex m;
+  ppo_ba_handle *h = nullptr;
+  ppo_ba_params P;
+  int device = -1;
+  Flat last;  // last flattened window (introspection for tests / logging)
+  ppo_ba_result res;
+  int rc = 0;
+};
+enum { SLOT_LOCAL = 0, SLOT_GLOBAL = 1, SLOT_POSE = 2 };
+static Slot g_slots[3];
+static std::atomic<Slot *> g_last_slot{&g_slots[SLOT_LOCAL]};
 static int g_device = 0;
-static Flat g_last;  // last flattened window (introspection for tests / logging)
-static ppo_ba_result g_last_result;
-static int g_last_rc = 0;
-
-// The reference's tuning globals are re-snapshotted on every call; the engine handle (streams, events, pinned staging,
-// the device memory pool) is kept across calls and only re-created when a parameter or the device actually changed.
-static ppo_ba_params g_handle_params;
-static int g_handle_device = -1;
-static ppo_ba_handle *engine(const ppo_ba_params &P) {
-  if (g_handle && g_handle_device == g_device && std::memcmp(&g_handle_params, &P, sizeof P) == 0) return g_handle;
-  if (g_handle) ppo_ba_destroy(g_handle), g_handle = nullptr;
-  if (ppo_ba_create(&P, g_device, &g_handle) != PPO_OK) g_handle = nullptr;
-  g_handle_params = P;
-  g_handle_device = g_device;
-  return g_handle;
+static ppo_ba_handle *engine(Slot &S, const ppo_ba_params &P) {
+  if (S.h && S.device == g_device) {
+    if (std::memcmp(&S.P, &P, sizeof P) != 0) {
+      if (ppo_ba_set_params(S.h, &P) != PPO_OK) return nullptr;
+      S.P = P;
+    }
+    return S.h;
+  }
+  if (S.h) ppo_ba_destroy(S.h), S.h = nullptr;
+  if (ppo_ba_create(&P, g_device, &S.h) != PPO_OK) S.h = nullptr;
+  S.P = P;
+  S.device = g_device;
+  return S.h;
 }
 
 using namespace ORB_SLAM2;
@@ -215,7 +231,9 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w) {
 }
 
 static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fixCamera, bool fixPoint) {
-  std::lock_guard<std::mutex> lk(g_mutex);
+  Slot &S = g_slots[0];
+  g_last_slot = &S;
+  std::lock_guard<std::mutex> lk(S.m);
   // PPO_BA_TIMING=1: host-side phase times of this call on stderr (diagnostics only)
   static const bool timing = std::getenv("PPO_BA_TIMING") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
@@ -230,7 +248,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   tick("collect window (stage A)");
 
   // ---- stage B: flatten (vertices) ------------------------------------------------------------------
-  Flat &F = g_last;
+  Flat &F = S.last;
   F = Flat();
   // key-frame slots ordered by mnId = g2o's Hessian order (core/sparse_optimizer.cpp:166-190,482-487)
   struct Slot { KeyFrame *kf; bool fixed; };
@@ -449,19 +467,20 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   if (pbStopFlag && *pbStopFlag) return;  // :2723-2725 — no optimisation, no write-back
 
   // ---- stages C-E on the GPU ----------------------------------------------------------------------------------
-  ppo_ba_handle *h = engine(P);
-  g_last_rc = PPO_E_NOGPU;
+  ppo_ba_handle *h = engine(S, P);
+  S.rc = PPO_E_NOGPU;
   if (!h) {
     std::fprintf(stderr, "ppo shim: no CUDA engine available; map left untouched\n");
     return;
   }
-  std::memset(&g_last_result, 0, sizeof g_last_result);
-  if ((g_last_rc = ppo_ba_set_graph(h, &F.g)) != PPO_OK ||
-      (g_last_rc = ppo_ba_local_ba(h, reinterpret_cast<const volatile unsigned char *>(pbStopFlag), &g_last_result)) != PPO_OK) {
-    std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", g_last_rc, ppo_ba_last_error(h));
+  std::memset(&S.res, 0, sizeof S.res);
+  if ((S.rc = ppo_ba_set_graph(h, &F.g)) != PPO_OK ||
+      (S.rc = ppo_ba_local_ba(h, reinterpret_cast<const volatile unsigned char *>(pbStopFlag), &S.res)) != PPO_OK) {
+    std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", S.rc, ppo_ba_last_error(h));
     return;
   }
   tick("engine (stages C-E)");
+  if (S.res.skipped) return;  // the stop flag was raised between our test and the engine's: the reference returns before any write-back (:2723-2725)
   // ---- stage F: erase lists :2840-2887 ---------------------------------------------------------------------------
   std::vector<std::pair<KeyFrame *, MapPoint *>> vToErase;
   std::vector<std::pair<KeyFrame *, MapPlane *>> vToErasePlane;
@@ -485,7 +504,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   ppo_ba_state st;
   std::vector<double> o_kf(F.kf_pose.size()), o_pt(F.pt_xyz.size()), o_pl(F.pl_coef.size()), o_cu(F.cu_state.size());
   st.kf_pose = o_kf.data(); st.pt_xyz = o_pt.data(); st.pl_coef = o_pl.data(); st.cu_state = o_cu.data();
-  if ((g_last_rc = ppo_ba_get_state(h, &st)) != PPO_OK) return;
+  if ((S.rc = ppo_ba_get_state(h, &st)) != PPO_OK) return;
 
   tick("erase lists + read-back (F)");
   // ---- stage G: write back under the map mutex :2892-2966 --------------------------------------------------------------
@@ -540,8 +559,10 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
 // outlier pass; results go to the map directly (nLoopKF == 0) or to mTcwGBA / mPosGBA for LoopClosing to merge.
 static void run_global(const std::vector<KeyFrame *> &vpKFs, const std::vector<MapPoint *> &vpMP, int nIterations, bool *pbStopFlag,
                        unsigned long nLoopKF, bool bRobust) {
-  std::lock_guard<std::mutex> lk(g_mutex);
-  Flat &F = g_last;
+  Slot &S = g_slots[1];
+  g_last_slot = &S;
+  std::lock_guard<std::mutex> lk(S.m);
+  Flat &F = S.last;
   F = Flat();
   // key-frame vertices :73-86, slots ordered by mnId = g2o's Hessian order
   std::vector<KeyFrame *> kfs;
@@ -600,30 +621,30 @@ static void run_global(const std::vector<KeyFrame *> &vpKFs, const std::vector<M
   P.solver = PPO_SOLVER_6_3;                // :62-66 (BlockSolver_6_3; the linear solver is the engine's dense Cholesky)
   P.huber_mono = ppo::huber_delta(5.99);    // :88  "sqrt(5.99)", not the 5.991 of the local BA
   P.huber_stereo = ppo::huber_delta(7.815);  // :89
-  ppo_ba_handle *h = engine(P);
-  g_last_rc = PPO_E_NOGPU;
+  ppo_ba_handle *h = engine(S, P);
+  S.rc = PPO_E_NOGPU;
   if (!h) {
     std::fprintf(stderr, "ppo shim: no CUDA engine available; map left untouched\n");
     return;
   }
-  std::memset(&g_last_result, 0, sizeof g_last_result);
-  if ((g_last_rc = ppo_ba_set_graph(h, &F.g)) != PPO_OK) {
-    std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", g_last_rc, ppo_ba_last_error(h));
+  std::memset(&S.res, 0, sizeof S.res);
+  if ((S.rc = ppo_ba_set_graph(h, &F.g)) != PPO_OK) {
+    std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", S.rc, ppo_ba_last_error(h));
     return;
   }
   if (!bRobust && F.g.n_pe) {  // :132-137,152-157: no robust kernel on any edge
     std::vector<unsigned char> flags(F.g.n_pe, 0);
-    if ((g_last_rc = ppo_ba_set_edge_flags(h, PPO_EDGE_POINT, flags.data())) != PPO_OK) return;
+    if ((S.rc = ppo_ba_set_edge_flags(h, PPO_EDGE_POINT, flags.data())) != PPO_OK) return;
   }
   // :180-183 initializeOptimization() + optimize(nIterations); the force-stop flag is polled inside (:69-70)
-  if ((g_last_rc = ppo_ba_optimize(h, nIterations, reinterpret_cast<const volatile unsigned char *>(pbStopFlag), &g_last_result.round1)) != PPO_OK) {
-    std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", g_last_rc, ppo_ba_last_error(h));
+  if ((S.rc = ppo_ba_optimize(h, nIterations, reinterpret_cast<const volatile unsigned char *>(pbStopFlag), &S.res.round1)) != PPO_OK) {
+    std::fprintf(stderr, "ppo shim: engine error %d (%s); map left untouched\n", S.rc, ppo_ba_last_error(h));
     return;
   }
   ppo_ba_state st;
   std::vector<double> o_kf(F.kf_pose.size()), o_pt(F.pt_xyz.size());
   st.kf_pose = o_kf.data(); st.pt_xyz = o_pt.data(); st.pl_coef = nullptr; st.cu_state = nullptr;
-  if ((g_last_rc = ppo_ba_get_state(h, &st)) != PPO_OK) return;
+  if ((S.rc = ppo_ba_get_state(h, &st)) != PPO_OK) return;
   // ---- recover optimised data :187-239 --------------------------------------------------------------------------------------
   for (KeyFrame *pKF : kfs) {
     float T[16];
@@ -660,8 +681,10 @@ static void run_global(const std::vector<KeyFrame *> &vpKFs, const std::vector<M
 // after each round every edge is re-classified by chi2 (level-1 edges are re-evaluated first), the robust kernels go
 // after the third round.  Returns the number of inliers.
 static int run_pose(Frame *pFrame) {
-  std::lock_guard<std::mutex> lk(g_mutex);
-  Flat &F = g_last;
+  Slot &S = g_slots[2];
+  g_last_slot = &S;
+  std::lock_guard<std::mutex> lk(S.m);
+  Flat &F = S.last;
   F = Flat();
   {
     float T[16];
@@ -699,15 +722,15 @@ static int run_pose(Frame *pFrame) {
   ppo_ba_params P;
   ppo_ba_default_params(&P);  // deltaMono = sqrt(5.991), deltaStereo = sqrt(7.815) (:281-282)
   P.solver = PPO_SOLVER_6_3;
-  ppo_ba_handle *h = engine(P);
-  g_last_rc = PPO_E_NOGPU;
+  ppo_ba_handle *h = engine(S, P);
+  S.rc = PPO_E_NOGPU;
   if (!h) {
     std::fprintf(stderr, "ppo shim: no CUDA engine available; frame pose left untouched\n");
     return 0;
   }
-  std::memset(&g_last_result, 0, sizeof g_last_result);
-  if ((g_last_rc = ppo_ba_set_graph(h, &F.g)) != PPO_OK) {
-    std::fprintf(stderr, "ppo shim: engine error %d (%s); frame pose left untouched\n", g_last_rc, ppo_ba_last_error(h));
+  std::memset(&S.res, 0, sizeof S.res);
+  if ((S.rc = ppo_ba_set_graph(h, &F.g)) != PPO_OK) {
+    std::fprintf(stderr, "ppo shim: engine error %d (%s); frame pose left untouched\n", S.rc, ppo_ba_last_error(h));
     return 0;
   }
   const int n_e = F.g.n_pe;
@@ -718,12 +741,12 @@ static int run_pose(Frame *pFrame) {
   int nBad = 0;
   for (size_t it = 0; it < 4; it++) {
     // :383-385  vSE3->setEstimate(toSE3Quat(pFrame->mTcw)); initializeOptimization(0); optimize(its[it])
-    if ((g_last_rc = ppo_ba_reset(h)) != PPO_OK || (g_last_rc = ppo_ba_set_edge_flags(h, PPO_EDGE_POINT, flags.data())) != PPO_OK) return 0;
-    g_last_rc = ppo_ba_optimize(h, its[it], nullptr, it < 2 ? &g_last_result.round1 : &g_last_result.round2);
-    if (g_last_rc != PPO_OK && g_last_rc != PPO_E_EMPTY) return 0;  // (every edge an outlier: nothing to optimise)
+    if ((S.rc = ppo_ba_reset(h)) != PPO_OK || (S.rc = ppo_ba_set_edge_flags(h, PPO_EDGE_POINT, flags.data())) != PPO_OK) return 0;
+    S.rc = ppo_ba_optimize(h, its[it], nullptr, it < 2 ? &S.res.round1 : &S.res.round2);
+    if (S.rc != PPO_OK && S.rc != PPO_E_EMPTY) return 0;  // (every edge an outlier: nothing to optimise)
     // :396-403 / :427-434  e->computeError() for the current outliers, then chi2 of every edge
-    if ((g_last_rc = ppo_ba_recompute_edge_errors(h, PPO_EDGE_POINT)) != PPO_OK ||
-        (g_last_rc = ppo_ba_edge_chi2(h, PPO_EDGE_POINT, chi2.data(), nullptr, nullptr)) != PPO_OK)
+    if ((S.rc = ppo_ba_recompute_edge_errors(h, PPO_EDGE_POINT)) != PPO_OK ||
+        (S.rc = ppo_ba_edge_chi2(h, PPO_EDGE_POINT, chi2.data(), nullptr, nullptr)) != PPO_OK)
       return 0;
     nBad = 0;
     for (int e = 0; e < n_e; e++) {
@@ -740,7 +763,7 @@ static int run_pose(Frame *pFrame) {
   ppo_ba_state st;
   double o_kf[7];
   st.kf_pose = o_kf; st.pt_xyz = nullptr; st.pl_coef = nullptr; st.cu_state = nullptr;
-  if ((g_last_rc = ppo_ba_get_state(h, &st)) != PPO_OK) return 0;
+  if ((S.rc = ppo_ba_get_state(h, &st)) != PPO_OK) return 0;
   float T[16];
   ppo::pose7_to_tcw_float(o_kf, T);
   pFrame->SetPose(float16_to_mat(T));  // :452-456
@@ -768,11 +791,12 @@ void Optimizer::LocalBACameraPlaneCuboids(KeyFrame *pKF, bool *pbStopFlag, Map *
 
 // introspection for tests and logging
 extern "C" {
-const ppo_ba_graph *ppo_shim_last_graph() { return &ppo_shim::g_last.g; }
-const ppo_ba_result *ppo_shim_last_result() { return &ppo_shim::g_last_result; }
-int ppo_shim_last_rc() { return ppo_shim::g_last_rc; }
+const ppo_ba_graph *ppo_shim_last_graph() { return &ppo_shim::g_last_slot.load()->last.g; }
+const ppo_ba_result *ppo_shim_last_result() { return &ppo_shim::g_last_slot.load()->res; }
+int ppo_shim_last_rc() { return ppo_shim::g_last_slot.load()->rc; }
 void ppo_shim_set_device(int device) { ppo_shim::g_device = device; }
 void ppo_shim_shutdown() {
-  if (ppo_shim::g_handle) ppo_ba_destroy(ppo_shim::g_handle), ppo_shim::g_handle = nullptr;
+  for (auto &S : ppo_shim::g_slots)
+    if (S.h) ppo_ba_destroy(S.h), S.h = nullptr;
 }
 }

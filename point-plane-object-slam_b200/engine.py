@@ -59,6 +59,7 @@ def load_library():
         lib.ppo_ba_host_sync_count.argtypes = [C.c_void_p]
         lib.ppo_ba_host_sync_count.restype = C.c_longlong
         lib.ppo_ba_set_graph_mode.argtypes = [C.c_void_p, C.c_int]
+        lib.ppo_ba_set_params.argtypes = [C.c_void_p, C.POINTER(A.Params)]
         lib.ppo_ba_time_assembly.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.ppo_ba_time_solve.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         lib.ppo_ba_mark.argtypes = [C.c_void_p, C.c_int]
