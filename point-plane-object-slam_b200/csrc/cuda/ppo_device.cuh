@@ -64,6 +64,16 @@ struct DevGraph {
   uint8_t *pce_flags;
   double *pce_chi2;
   double *pce_J;  // n_pce x 9 columns x 3
+  // fixed-order assembly of the non-point edges: per-edge contributions + gather lists (built once per window); no atomics
+  double *ple_part;  // n_ple x 54: [0..26] key-frame block (21 upper + 6 gradient), [27..35] plane Hll (6) + bl (3), [36..53] Hpl block 6 x 3
+  double *cbe_part;  // n_cbe x 81: [0..26] key-frame block, [27..80] cuboid block (45 upper + 9 gradient)
+  double *pce_part;  // n_pce x 54: cuboid block
+  const int *kf_ple_ptr, *kf_ple_idx;      // plane edges of a key-frame
+  const int *kf_cbe_ptr, *kf_cbe_idx;      // camera-cuboid edges of a key-frame
+  const int *cu_cbe_ptr, *cu_cbe_idx;      // camera-cuboid edges of a cuboid
+  const int *cu_pce_ptr, *cu_pce_idx;      // point-cuboid edges of a cuboid
+  const int *pl_ple_ptr, *pl_ple_idx;      // plane edges of a plane
+  const int *slot_ple_ptr, *slot_ple_idx;  // plane edges of a (plane, key-frame) slot
   // landmark -> entries CSR (planes: slots; points: edges)
   const int *lm_rowptr;  // n_lm + 1
   const int *slot_kf;    // n_slots

@@ -87,10 +87,15 @@ struct ppo_ba_handle {
   int n_chunks = 0;
   int *d_kf_chunk_ptr = nullptr;
   double *d_chunk_part = nullptr;
+  int *d_kf_iota_ptr = nullptr;  // 0, 1, 2, .. n_kf: "one chunk per key-frame" view of d_kf_part (sharded windows)
+  double *d_kf_part = nullptr;   // n_kf x 27: per-key-frame sums of the chunk partials, summed across ranks
   unsigned *d_pair_keys = nullptr;            // sorted key-frame-pair keys of the Schur contributions
   unsigned long long *d_pair_vals = nullptr;  // (entry A << 32 | entry B)
   int n_pairs = 0;                            // upper bound (padding at the end of the sorted list)
   int *d_dup = nullptr;                       // set by k_pair_count: a landmark observed twice by one key-frame
+  double *d_pair_bnd = nullptr;               // boundary records of the Schur pair list: 2 per 128-record chunk x 64 doubles (a C fragment)
+  unsigned *d_pair_bnd_key = nullptr;
+  int *d_pair_bnd_flag = nullptr;
   // cuboid-plane edges (constant residual): host side
   std::vector<int> cpe_cuboid, cpe_plane;
   std::vector<double> cpe_chi2, cpe_norm;
@@ -549,6 +554,12 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   { int *p; UP(p, chunk_kf); g.chunk_kf = p; UP(p, chunk_b); g.chunk_begin = p; UP(p, chunk_e); g.chunk_end = p; }
   UP(h->d_kf_chunk_ptr, kf_chunk_ptr);
   if ((rc = h->dalloc(&h->d_chunk_part, 27 * (size_t)g.n_chunks))) return rc;
+  if ((rc = h->dalloc(&h->d_kf_part, 27 * (size_t)g.n_kf))) return rc;
+  {
+    std::vector<int> iota((size_t)g.n_kf + 1);
+    for (int i = 0; i <= g.n_kf; i++) iota[i] = i;
+    UP(h->d_kf_iota_ptr, iota);
+  }
 
   tick("edges by key-frame");
   // ---- plane edges: slots = unique (plane, key-frame) pairs, sorted by (plane, kf) ---------------------
@@ -617,6 +628,10 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
       if (total > 0x7fffffffll) { h->err = "Schur contribution list exceeds 2^31 entries"; return PPO_E_INVALID; }
     }
     h->n_pairs = (int)total;
+    {
+      const size_t nch = (size_t)cdiv((int)total, PAIR_CHUNK) + 1;
+      if ((rc = h->dalloc(&h->d_pair_bnd, nch * 2 * 64)) || (rc = h->dalloc(&h->d_pair_bnd_key, nch * 2)) || (rc = h->dalloc(&h->d_pair_bnd_flag, nch))) return rc;
+    }
     int *d_cnt = nullptr, *d_off = nullptr;
     unsigned *k_in = nullptr;
     unsigned long long *v_in = nullptr;
@@ -668,12 +683,34 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   UP(h->d_cpe_plane, h->cpe_plane);
   UP(h->d_cpe_flags, h->cpe_flags);
 
+  {  // gather lists of the non-point edges (counting sorts; a few 10^4 entries): the assembly reduces per-edge contributions in list order
+    auto csr = [&](int n_rows, int n, auto row_of, const int **ptr_out, const int **idx_out) -> int {
+      std::vector<int> ptr((size_t)n_rows + 1, 0), idx((size_t)n);
+      for (int e = 0; e < n; e++) ptr[(size_t)row_of(e) + 1]++;
+      for (int r = 0; r < n_rows; r++) ptr[(size_t)r + 1] += ptr[r];
+      std::vector<int> pos(ptr.begin(), ptr.end() - 1);
+      for (int e = 0; e < n; e++) idx[pos[row_of(e)]++] = e;
+      int *p = nullptr, *q = nullptr;
+      int r2;
+      if ((r2 = h->upload(&p, ptr)) || (r2 = h->upload(&q, idx))) return r2;
+      *ptr_out = p, *idx_out = q;
+      return PPO_OK;
+    };
+    if ((rc = csr(g.n_kf, g.n_ple, [&](int e) { return gi->ple_kf[e]; }, &g.kf_ple_ptr, &g.kf_ple_idx)) ||
+        (rc = csr(g.n_kf, g.n_cbe, [&](int e) { return gi->cbe_kf[e]; }, &g.kf_cbe_ptr, &g.kf_cbe_idx)) ||
+        (rc = csr(g.n_cu, g.n_cbe, [&](int e) { return gi->cbe_cuboid[e]; }, &g.cu_cbe_ptr, &g.cu_cbe_idx)) ||
+        (rc = csr(g.n_cu, g.n_pce, [&](int e) { return gi->pce_cuboid[e]; }, &g.cu_pce_ptr, &g.cu_pce_idx)) ||
+        (rc = csr(g.n_pl, g.n_ple, [&](int e) { return gi->ple_plane[e]; }, &g.pl_ple_ptr, &g.pl_ple_idx)) ||
+        (rc = csr(g.n_slots, g.n_ple, [&](int e) { return ple_slot[e]; }, &g.slot_ple_ptr, &g.slot_ple_idx)))
+      return rc;
+  }
   tick("cuboid edges");
   // ---- flags, per-edge outputs, scratch -----------------------------------------------------------------
 #define DA(ptr, n) if ((rc = h->dalloc(&(ptr), (n)))) return rc
   DA(g.pe_flags, (size_t)g.n_pe); DA(g.ple_flags, (size_t)g.n_ple); DA(g.cbe_flags, (size_t)g.n_cbe); DA(g.pce_flags, (size_t)g.n_pce);
   DA(g.pe_chi2, (size_t)g.n_pe); DA(g.ple_chi2, (size_t)g.n_ple); DA(g.cbe_chi2, (size_t)g.n_cbe); DA(g.cbe_norm, (size_t)g.n_cbe); DA(g.pce_chi2, (size_t)g.n_pce);
   DA(g.ple_J, 27 * (size_t)g.n_ple); DA(g.cbe_J, 240 * (size_t)g.n_cbe); DA(g.cbe_err, 16 * (size_t)g.n_cbe); DA(g.cbe_w, (size_t)g.n_cbe); DA(g.pce_J, 27 * (size_t)g.n_pce);
+  DA(g.ple_part, 54 * (size_t)g.n_ple); DA(g.cbe_part, 81 * (size_t)g.n_cbe); DA(g.pce_part, 54 * (size_t)g.n_pce);
   DA(g.kf_act, (size_t)g.n_kf); DA(g.cu_act, (size_t)g.n_cu); DA(g.pl_act, (size_t)g.n_pl); DA(g.pt_act, (size_t)g.n_pt);
   DA(g.kf_idx, (size_t)g.n_kf); DA(g.cu_off, (size_t)g.n_cu); DA(g.ent_pidx, (size_t)g.n_ent); DA(g.dims, 8);
   int n_free = 0;
@@ -807,19 +844,14 @@ static int linearize(ppo_ba_handle *h, bool only_points_kernel = false) {
   DevGraph &g = h->g;
   cudaStream_t st = h->st;
   const DevState &s = h->sa;
-  if (!only_points_kernel) {
-    CK(cudaMemsetAsync(g.Hpp_kf, 0, 8 * 36 * (size_t)g.n_kf, st));
-    CK(cudaMemsetAsync(g.Hpp_cu, 0, 8 * 81 * (size_t)g.n_cu, st));
-    CK(cudaMemsetAsync(g.bp, 0, 8 * (size_t)h->max_np, st));
-    CK(cudaMemsetAsync(g.Hll, 0, 8 * 6 * (size_t)g.n_lm, st));
-    CK(cudaMemsetAsync(g.bl, 0, 8 * 3 * (size_t)g.n_lm, st));
-    CK(cudaMemsetAsync(g.Hpl, 0, 8 * 18 * (size_t)g.n_slots, st));
+  if (!only_points_kernel) {  // point landmarks accumulate into zeroed Hll / bl (one add per value); everything else is written by k_combine
+    CK(cudaMemsetAsync(g.Hll + 6 * (size_t)g.n_pl, 0, 8 * 6 * (size_t)g.n_pt, st));
+    CK(cudaMemsetAsync(g.bl + 3 * (size_t)g.n_pl, 0, 8 * 3 * (size_t)g.n_pt, st));
   }
   if (h->profiling) cudaEventRecord(h->evp[0], st);
   // the plane / cuboid / point-cuboid edges (numeric Jacobians, few 10^4 threads, latency-bound) run on three side streams next
-  // to the point kernels; all sides only meet in atomically-updated accumulators.  Sharded: the cross-rank sum of the point
-  // edges' pose blocks sits between the point kernels and the replicated edges on the main stream, so those stay there.
-  const bool fork = h->world == 1 && !only_points_kernel && (g.n_ple || g.n_cbe || g.n_pce);
+  // to the point kernels; every edge writes its own record, the sides meet in k_combine
+  const bool fork = !only_points_kernel && (g.n_ple || g.n_cbe || g.n_pce);
   const bool use_side[3] = {fork && g.n_ple > 0, fork && g.n_cbe > 0, fork && g.n_pce > 0};
   cudaStream_t s_pl = use_side[0] ? h->side[0] : st, s_cb = use_side[1] ? h->side[1] : st, s_pc = use_side[2] ? h->side[2] : st;
   if (fork) {
@@ -834,12 +866,14 @@ static int linearize(ppo_ba_handle *h, bool only_points_kernel = false) {
   if (only_points_kernel) return PPO_OK;
   if (g.n_chunks) {
     k_pose_accumulate<<<g.n_chunks, POSE_THREADS, 0, st>>>(g, s, h->d_chunk_part);
-    k_pose_reduce<<<cdiv(g.n_kf * 27, 128), 128, 0, st>>>(g, h->d_kf_chunk_ptr, h->d_chunk_part);
-    h->launches += 2;
+    h->launches++;
   }
-  if (h->world > 1) {  // pose side of the point edges of all shards; the replicated edges below are added on every rank
+  if (h->world > 1 && g.n_chunks) {  // pose side of the point edges of all shards (every rank has the same chunk layout? no: chunks are per shard, so the
+    // partials are first reduced per key-frame into a compact array, summed across ranks and fed back as a single chunk per key-frame)
     int rc;
-    if ((rc = allreduce(h, g.Hpp_kf, 36 * (size_t)g.n_kf, ncclFloat64_, ncclSum_)) || (rc = allreduce(h, g.bp, h->max_np, ncclFloat64_, ncclSum_))) return rc;
+    k_chunk_reduce<<<cdiv(g.n_kf * 27, 128), 128, 0, st>>>(g.n_kf, h->d_kf_chunk_ptr, h->d_chunk_part, h->d_kf_part);
+    h->launches++;
+    if ((rc = allreduce(h, h->d_kf_part, 27 * (size_t)g.n_kf, ncclFloat64_, ncclSum_))) return rc;
   }
   if (g.n_ple) {
     k_plane_jac<<<cdiv(g.n_ple * 9, 128), 128, 0, s_pl>>>(g, s);
@@ -862,6 +896,12 @@ static int linearize(ppo_ba_handle *h, bool only_points_kernel = false) {
       CK(cudaEventRecord(h->ev_join[q], h->side[q]));
       CK(cudaStreamWaitEvent(st, h->ev_join[q], 0));
     }
+  {  // fixed-order assembly of the key-frame / cuboid / plane blocks from the per-edge records
+    const int n = g.n_kf * 27 + g.n_cu * 54 + g.n_pl * 9 + g.n_slots * 18;
+    if (h->world > 1) k_combine<<<cdiv(n, 128), 128, 0, st>>>(g, h->d_kf_iota_ptr, h->d_kf_part);
+    else k_combine<<<cdiv(n, 128), 128, 0, st>>>(g, h->d_kf_chunk_ptr, h->d_chunk_part);
+    h->launches++;
+  }
   if (h->profiling) cudaEventRecord(h->evp[1], st);
   const bool own = h->owner();  // replicated (non-point) edges count once: on rank 0
   k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
@@ -936,8 +976,10 @@ static int schur_system(ppo_ba_handle *h) {
   if (g.n_units) { k_schur_bd_points<<<g.n_units, 32, 0, st>>>(g, h->d_lm); h->launches++; }
   if (h->n_pairs) {
     const int n_warps = cdiv(h->n_pairs, PAIR_CHUNK);
-    k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld, grow);
-    h->launches++;
+    k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld, grow, h->d_pair_bnd, h->d_pair_bnd_key,
+                                                                            h->d_pair_bnd_flag);
+    k_schur_pairs_fix<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, n_warps, ld, grow, h->d_pair_bnd, h->d_pair_bnd_key, h->d_pair_bnd_flag);
+    h->launches += 2;
   }
   const int n_comp = g.n_kf * 36 + g.n_cu * 81 + g.n_cbe * 54 + n_p;
   if (n_comp && own) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, h->d_lm, n_p, ld, grow); h->launches++; }

@@ -434,25 +434,100 @@ __global__ void __launch_bounds__(POSE_THREADS) k_pose_accumulate(DevGraph g, De
     chunk_part[27 * (size_t)c + threadIdx.x] = t;
   }
 }
-__global__ void k_pose_reduce(DevGraph g, const int *kf_chunk_ptr, const double *chunk_part) {
+// per-key-frame sums of the chunk partials (sharded windows: summed across ranks before k_combine)
+__global__ void k_chunk_reduce(int n_kf, const int *kf_chunk_ptr, const double *chunk_part, double *kf_part) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_kf * 27) return;
   const int kf = t / 27, i = t % 27;
-  if (kf >= g.n_kf) return;
-  const int idx = g.kf_idx[kf];
-  if (idx < 0) return;
   double sum = 0;
   for (int c = kf_chunk_ptr[kf]; c < kf_chunk_ptr[kf + 1]; c++) sum += chunk_part[27 * (size_t)c + i];
-  if (i < 21) {
-    int a = 0, rem = i;  // unpack upper-triangular index
-    while (rem >= 6 - a) {
-      rem -= 6 - a;
-      a++;
+  kf_part[t] = sum;
+}
+// Fixed-order assembly of everything that is not a point landmark: one thread per scalar of
+//   a key-frame block   (27: 21 upper + 6 gradient)  = point-edge chunk partials, then its plane edges, then its cuboid edges
+//   a cuboid block      (54: 45 upper + 9 gradient)  = its camera-cuboid edges, then its point-cuboid edges
+//   a plane landmark    ( 9: Hll + bl)               = its plane edges
+//   a (plane, KF) slot  (18: Hpl block)              = its plane edges
+// summed in list order and written with plain stores: no atomics, bit-reproducible, and no clearing of the targets beforehand.
+__global__ void k_combine(DevGraph g, const int *kf_chunk_ptr, const double *chunk_part) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < g.n_kf * 27) {
+    const int kf = t / 27, i = t % 27;
+    const int idx = g.kf_idx[kf];
+    if (idx < 0) return;
+    double sum = 0;
+    for (int c = kf_chunk_ptr[kf]; c < kf_chunk_ptr[kf + 1]; c++) sum += chunk_part[27 * (size_t)c + i];
+    for (int q = g.kf_ple_ptr[kf]; q < g.kf_ple_ptr[kf + 1]; q++) {
+      const int e = g.kf_ple_idx[q];
+      if (!(g.ple_flags[e] & PPO_EF_LEVEL1_)) sum += g.ple_part[54 * (size_t)e + i];
     }
-    const int b = a + rem;
-    atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * a + b], sum);
-    if (a != b) atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * b + a], sum);
-  } else {
-    atomicAdd(&g.bp[6 * idx + (i - 21)], sum);
+    for (int q = g.kf_cbe_ptr[kf]; q < g.kf_cbe_ptr[kf + 1]; q++) {
+      const int e = g.kf_cbe_idx[q];
+      if (!(g.cbe_flags[e] & PPO_EF_LEVEL1_)) sum += g.cbe_part[81 * (size_t)e + i];
+    }
+    if (i < 21) {
+      int a = 0, rem = i;  // unpack upper-triangular index
+      while (rem >= 6 - a) {
+        rem -= 6 - a;
+        a++;
+      }
+      const int b = a + rem;
+      g.Hpp_kf[36 * (size_t)idx + 6 * a + b] = sum;
+      g.Hpp_kf[36 * (size_t)idx + 6 * b + a] = sum;
+    } else {
+      g.bp[6 * idx + (i - 21)] = sum;
+    }
+    return;
+  }
+  t -= g.n_kf * 27;
+  if (t < g.n_cu * 54) {
+    const int cu = t / 54, i = t % 54;
+    const int off = g.cu_off[cu];
+    if (off < 0) return;
+    double sum = 0;
+    for (int q = g.cu_cbe_ptr[cu]; q < g.cu_cbe_ptr[cu + 1]; q++) {
+      const int e = g.cu_cbe_idx[q];
+      if (!(g.cbe_flags[e] & PPO_EF_LEVEL1_)) sum += g.cbe_part[81 * (size_t)e + 27 + i];
+    }
+    for (int q = g.cu_pce_ptr[cu]; q < g.cu_pce_ptr[cu + 1]; q++) {
+      const int e = g.cu_pce_idx[q];
+      if (!(g.pce_flags[e] & PPO_EF_LEVEL1_)) sum += g.pce_part[54 * (size_t)e + i];
+    }
+    if (i < 45) {
+      int a = 0, rem = i;
+      while (rem >= 9 - a) {
+        rem -= 9 - a;
+        a++;
+      }
+      const int b = a + rem;
+      g.Hpp_cu[81 * (size_t)cu + 9 * a + b] = sum;
+      g.Hpp_cu[81 * (size_t)cu + 9 * b + a] = sum;
+    } else {
+      g.bp[off + (i - 45)] = sum;
+    }
+    return;
+  }
+  t -= g.n_cu * 54;
+  if (t < g.n_pl * 9) {
+    const int pl = t / 9, i = t % 9;
+    double sum = 0;
+    for (int q = g.pl_ple_ptr[pl]; q < g.pl_ple_ptr[pl + 1]; q++) {
+      const int e = g.pl_ple_idx[q];
+      if (!(g.ple_flags[e] & PPO_EF_LEVEL1_)) sum += g.ple_part[54 * (size_t)e + 27 + i];
+    }
+    if (i < 6) g.Hll[6 * (size_t)pl + i] = sum;
+    else g.bl[3 * (size_t)pl + (i - 6)] = sum;
+    return;
+  }
+  t -= g.n_pl * 9;
+  if (t < g.n_slots * 18) {
+    const int slot = t / 18, i = t % 18;
+    double sum = 0;
+    for (int q = g.slot_ple_ptr[slot]; q < g.slot_ple_ptr[slot + 1]; q++) {
+      const int e = g.slot_ple_idx[q];
+      if (!(g.ple_flags[e] & PPO_EF_LEVEL1_) && g.kf_idx[g.ple_kf[e]] >= 0) sum += g.ple_part[54 * (size_t)e + 36 + i];
+    }
+    g.Hpl[18 * (size_t)slot + i] = sum;
   }
 }
 
@@ -529,33 +604,30 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_plane_edges(DevGraph g, DevSt
 #pragma unroll
         for (int c = 0; c < 9; c++) J[3 * c + 2] = 0;
       }
-      double wi[3] = {w * info[0], w * info[1], w * info[2]};
-      // landmark (plane) block
+      const double wi[3] = {w * info[0], w * info[1], w * info[2]};
+      // the edge's contribution to the normal equations (constructQuadraticForm, base_binary_edge.hpp:54-120) goes to its own
+      // record; k_combine sums the records of a vertex in a fixed order (no atomics: bit-reproducible)
+      double *out = g.ple_part + 54 * (size_t)e;
+      const double *Jk = J + 9;  // key-frame columns
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = a; b < 6; b++) out[q++] = Jk[3 * a] * wi[0] * Jk[3 * b] + Jk[3 * a + 1] * wi[1] * Jk[3 * b + 1] + Jk[3 * a + 2] * wi[2] * Jk[3 * b + 2];
+#pragma unroll
+      for (int a = 0; a < 6; a++) out[21 + a] = -(Jk[3 * a] * wi[0] * err[0] + Jk[3 * a + 1] * wi[1] * err[1] + Jk[3 * a + 2] * wi[2] * err[2]);
       const int q6[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
 #pragma unroll
       for (int i = 0; i < 6; i++) {
         const int a = q6[i][0], b = q6[i][1];
-        atomicAdd(&g.Hll[6 * (size_t)pl + i], J[3 * a] * wi[0] * J[3 * b] + J[3 * a + 1] * wi[1] * J[3 * b + 1] + J[3 * a + 2] * wi[2] * J[3 * b + 2]);
+        out[27 + i] = J[3 * a] * wi[0] * J[3 * b] + J[3 * a + 1] * wi[1] * J[3 * b + 1] + J[3 * a + 2] * wi[2] * J[3 * b + 2];
       }
 #pragma unroll
-      for (int a = 0; a < 3; a++)
-        atomicAdd(&g.bl[3 * (size_t)pl + a], -(J[3 * a] * wi[0] * err[0] + J[3 * a + 1] * wi[1] * err[1] + J[3 * a + 2] * wi[2] * err[2]));
-      const int idx = g.kf_idx[kf];
-      if (idx >= 0) {
-        const double *Jk = J + 9;  // KF columns
+      for (int a = 0; a < 3; a++) out[33 + a] = -(J[3 * a] * wi[0] * err[0] + J[3 * a + 1] * wi[1] * err[1] + J[3 * a + 2] * wi[2] * err[2]);
 #pragma unroll
-        for (int a = 0; a < 6; a++) {
+      for (int a = 0; a < 6; a++)
 #pragma unroll
-          for (int b = 0; b < 6; b++)
-            atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * a + b],
-                      Jk[3 * a] * wi[0] * Jk[3 * b] + Jk[3 * a + 1] * wi[1] * Jk[3 * b + 1] + Jk[3 * a + 2] * wi[2] * Jk[3 * b + 2]);
-          atomicAdd(&g.bp[6 * idx + a], -(Jk[3 * a] * wi[0] * err[0] + Jk[3 * a + 1] * wi[1] * err[1] + Jk[3 * a + 2] * wi[2] * err[2]));
-#pragma unroll
-          for (int c = 0; c < 3; c++)
-            atomicAdd(&g.Hpl[18 * (size_t)g.ple_slot[e] + 3 * a + c],
-                      Jk[3 * a] * wi[0] * J[3 * c] + Jk[3 * a + 1] * wi[1] * J[3 * c + 1] + Jk[3 * a + 2] * wi[2] * J[3 * c + 2]);
-        }
-      }
+        for (int c = 0; c < 3; c++) out[36 + 3 * a + c] = Jk[3 * a] * wi[0] * J[3 * c] + Jk[3 * a + 1] * wi[1] * J[3 * c + 1] + Jk[3 * a + 2] * wi[2] * J[3 * c + 2];
     }
   }
   const double t = block_sum<SMALL_THREADS>(rho0, sm);
@@ -643,16 +715,17 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_cuboid_edges(DevGraph g, DevS
   const double t = block_sum<SMALL_THREADS>(rho0, sm);
   if (threadIdx.x == 0) chi_part[blockIdx.x] = t;
 }
-// quadratic form of the camera-cuboid edges: one thread per (edge, row a of the 15 x 15 block)
+// quadratic form of the camera-cuboid edges: one thread per (edge, row a of the 15 x 15 block); the key-frame block (21 upper
+// entries + 6 gradient) and the cuboid block (45 + 9) go to the edge's own record (summed per vertex by k_combine), the 6 x 9
+// off-diagonal block to Hpc
+__device__ __forceinline__ int upper_index(int n, int a, int b) { return a * n - a * (a - 1) / 2 + (b - a); }  // b >= a
 __global__ void k_cuboid_assemble(DevGraph g) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int e = t / 15, a = t % 15;
   if (e >= g.n_cbe || (g.cbe_flags[e] & PPO_EF_LEVEL1_)) return;
-  const int kf = g.cbe_kf[e], cu = g.cbe_cuboid[e];
-  const int idx = g.kf_idx[kf], off = g.cu_off[cu];
-  if (a < 6 && idx < 0) return;
   const double wi = g.cbe_w[e];
   const double *J = g.cbe_J + 240 * (size_t)e;  // [col][row16], rows >= D are zero
+  double *out = g.cbe_part + 81 * (size_t)e;
   double ja[16];
 #pragma unroll
   for (int r = 0; r < 16; r++) ja[r] = J[16 * a + r];
@@ -660,16 +733,16 @@ __global__ void k_cuboid_assemble(DevGraph g) {
 #pragma unroll
   for (int r = 0; r < 16; r++) ga += ja[r] * g.cbe_err[16 * (size_t)e + r];
   ga *= -wi;
-  if (a < 6) atomicAdd(&g.bp[6 * idx + a], ga);
-  else atomicAdd(&g.bp[off + a - 6], ga);
-  for (int b = (a < 6 ? (idx >= 0 ? 0 : 6) : 6); b < 15; b++) {
+  if (a < 6) out[21 + a] = ga;
+  else out[27 + 45 + (a - 6)] = ga;
+  for (int b = a; b < 15; b++) {
     double hv = 0;
 #pragma unroll
     for (int r = 0; r < 16; r++) hv += ja[r] * J[16 * b + r];
     hv *= wi;
-    if (a < 6 && b < 6) atomicAdd(&g.Hpp_kf[36 * (size_t)idx + 6 * a + b], hv);
+    if (a < 6 && b < 6) out[upper_index(6, a, b)] = hv;
     else if (a < 6) g.Hpc[54 * (size_t)e + 9 * a + (b - 6)] = hv;
-    else atomicAdd(&g.Hpp_cu[81 * (size_t)cu + 9 * (a - 6) + (b - 6)], hv);
+    else out[27 + upper_index(9, a - 6, b - 6)] = hv;
   }
 }
 
@@ -714,13 +787,13 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_ptcu_edges(DevGraph g, DevSta
     rho0 = chi2;
     double w = 1.0;
     if (g.pce_flags[e] & PPO_EF_ROBUST_) w = huber_w(chi2, 1.0, &rho0);
-    if (ASSEMBLE) {
+    if (ASSEMBLE) {  // the edge's cuboid block (45 upper entries + 9 gradient) goes to its own record, summed by k_combine
       const double *J = g.pce_J + 27 * (size_t)e;
-      const int off = g.cu_off[cu];
+      double *out = g.pce_part + 54 * (size_t)e;
+      int q = 0;
       for (int a = 0; a < 9; a++) {
-        atomicAdd(&g.bp[off + a], -w * (J[3 * a] * err[0] + J[3 * a + 1] * err[1] + J[3 * a + 2] * err[2]));
-        for (int b = 0; b < 9; b++)
-          atomicAdd(&g.Hpp_cu[81 * (size_t)cu + 9 * a + b], w * (J[3 * a] * J[3 * b] + J[3 * a + 1] * J[3 * b + 1] + J[3 * a + 2] * J[3 * b + 2]));
+        out[45 + a] = -w * (J[3 * a] * err[0] + J[3 * a + 1] * err[1] + J[3 * a + 2] * err[2]);
+        for (int b = a; b < 9; b++) out[q++] = w * (J[3 * a] * J[3 * b] + J[3 * a + 1] * J[3 * b + 1] + J[3 * a + 2] * J[3 * b + 2]);
       }
     }
   }
@@ -923,8 +996,31 @@ constexpr int PAIR_WARPS = 8;
 PPO_D void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// Writes the accumulated 6 x 6 block (+ reduced-gradient column) of key-frame pair `key` into S: S is zero on entry and every block
+// has exactly one writer, so these are plain stores (bit-reproducible); k_compose adds Hpp afterwards.
+// upper (6 p1 + row, 6 p2 + col) = lower element (6 p2 + col, 6 p1 + row) of the tiled storage; ld = Tm
+PPO_D void schur_store(const DevGraph &g, unsigned key, int lane, double acc0, double acc1, int ld, int grow) {
+  const int row = lane >> 2, kk = lane & 3;
+  const unsigned ka = key / (unsigned)g.n_kf, kb = key - ka * (unsigned)g.n_kf;
+  const int p1 = g.kf_idx[ka], p2 = g.kf_idx[kb];
+  if (p1 >= 0 && p2 >= 0 && row < 6) {
+    const int c = 6 * p1 + row;
+    if (kk < 3) {  // (diagonal blocks: the mirrored half is not stored)
+      const int r = 6 * p2 + 2 * kk;
+      if (r >= c) g.S[dense_elem_index(ld, r, c)] = -acc0;
+      if (r + 1 >= c) g.S[dense_elem_index(ld, r + 1, c)] = -acc1;
+    } else if (ka == kb) {
+      g.S[dense_elem_index(ld, grow, c)] = -acc0;  // bschur -= W Dinv bl
+    }
+  }
+}
+// A warp streams PAIR_CHUNK consecutive records of the sorted list.  A key-frame pair whose records lie inside one chunk is
+// finished by that warp.  A pair that crosses a chunk boundary leaves its partial C fragment in the chunk's boundary record
+// (slot 0: the chunk's first pair continues from the previous chunk, slot 1: its last pair continues into the next one) and
+// k_schur_pairs_fix adds the partials of such a pair in chunk order: no atomics, the result does not depend on scheduling.
+// bnd_flag[chunk]: bit 0 slot 0 valid, bit 1 slot 1 valid, bit 2 the whole chunk is one pair that continues on both sides.
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, const unsigned *__restrict__ keys, const unsigned long long *__restrict__ vals,
-                                                                 int n_pairs, int ld, int grow) {
+                                                                 int n_pairs, int ld, int grow, double *bnd, unsigned *bnd_key, int *bnd_flag) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
   const long long c0 = w * PAIR_CHUNK;
@@ -934,21 +1030,24 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
   const int row = lane >> 2, kk = lane & 3;
   const bool in_blk = row < 6 && kk < 3, z_lane = row == 6 && kk < 3;
   const int idx = 3 * row + kk;
-  unsigned cur = 0xffffffffu;
+  const unsigned PAD = 0xffffffffu;
+  const unsigned first_key = keys[c0], last_key = keys[c0 + cnt - 1];
+  const bool cont_prev = c0 > 0 && first_key != PAD && keys[c0 - 1] == first_key;
+  const bool cont_next = c0 + cnt < n_pairs && last_key != PAD && keys[c0 + cnt] == last_key;
+  int flags = 0;
+  unsigned cur = PAD;
   double acc0 = 0.0, acc1 = 0.0;
   auto flush = [&]() {
-    if (cur != 0xffffffffu) {
-      const unsigned ka = cur / (unsigned)g.n_kf, kb = cur - ka * (unsigned)g.n_kf;
-      const int p1 = g.kf_idx[ka], p2 = g.kf_idx[kb];
-      if (p1 >= 0 && p2 >= 0 && row < 6) {  // upper (6 p1 + row, 6 p2 + col) = lower element (6 p2 + col, 6 p1 + row) of the tiled storage; ld = Tm
-        const int c = 6 * p1 + row;
-        if (kk < 3) {  // (diagonal blocks: the mirrored half is not stored)
-          const int r = 6 * p2 + 2 * kk;
-          if (r >= c) atomicAdd(&g.S[dense_elem_index(ld, r, c)], -acc0);
-          if (r + 1 >= c) atomicAdd(&g.S[dense_elem_index(ld, r + 1, c)], -acc1);
-        } else if (ka == kb) {
-          atomicAdd(&g.S[dense_elem_index(ld, grow, c)], -acc0);  // bschur -= W Dinv bl
-        }
+    if (cur != PAD) {
+      const bool from_prev = cont_prev && cur == first_key, to_next = cont_next && cur == last_key;
+      if (!from_prev && !to_next) {
+        schur_store(g, cur, lane, acc0, acc1, ld, grow);
+      } else {
+        const int slot = from_prev ? 0 : 1;
+        double *dst = bnd + ((size_t)(2 * w + slot) * 32 + lane) * 2;
+        dst[0] = acc0, dst[1] = acc1;
+        if (lane == 0) bnd_key[2 * w + slot] = cur;
+        flags |= from_prev ? (to_next ? 5 : 1) : 2;
       }
     }
     acc0 = acc1 = 0.0;
@@ -956,7 +1055,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
   constexpr int U = 8;  // contributions whose operand loads are in flight together
   for (int base = 0; base < cnt; base += 32) {
     const int c = base + lane;
-    const unsigned kl = c < cnt ? keys[c0 + c] : 0xffffffffu;  // (the list ends with 0xffffffff padding)
+    const unsigned kl = c < cnt ? keys[c0 + c] : PAD;  // (the list ends with 0xffffffff padding)
     const unsigned long long vl = c < cnt ? vals[c0 + c] : 0ull;
     for (int cb = 0; cb < 32; cb += U) {
       if (base + cb >= cnt) break;  // warp-uniform
@@ -967,13 +1066,13 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
         key[u] = __shfl_sync(FULL, kl, cb + u);
         const unsigned long long v = __shfl_sync(FULL, vl, cb + u);
         const unsigned e1 = (unsigned)(v >> 32), e2 = (unsigned)(v & 0xffffffffu);
-        const bool ok = key[u] != 0xffffffffu;
+        const bool ok = key[u] != PAD;
         av[u] = (ok && in_blk) ? g.BD[18 * (size_t)e1 + idx] : 0.0;
         bv[u] = (ok && in_blk) ? g.BD[18 * (size_t)e2 + idx] : ((ok && z_lane && e1 == e2) ? g.Zent[3 * (size_t)e1 + kk] : 0.0);
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        if (key[u] == 0xffffffffu) continue;  // warp-uniform
+        if (key[u] == PAD) continue;  // warp-uniform
         if (key[u] != cur) {
           flush();
           cur = key[u];
@@ -983,6 +1082,25 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
     }
   }
   flush();
+  if (lane == 0) bnd_flag[w] = flags;
+}
+// One warp per chunk whose LAST pair continues into the next chunk (it is the head of that pair's run of boundary records)
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs_fix(DevGraph g, int n_chunks, int ld, int grow, const double *bnd, const unsigned *bnd_key,
+                                                                     const int *bnd_flag) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+  if (w >= n_chunks || !(bnd_flag[w] & 2)) return;
+  const unsigned key = bnd_key[2 * w + 1];
+  const double *p = bnd + ((size_t)(2 * w + 1) * 32 + lane) * 2;
+  double a0 = p[0], a1 = p[1];
+  for (int u = w + 1; u < n_chunks; u++) {
+    const int f = bnd_flag[u];
+    if (!(f & 1) || bnd_key[2 * u] != key) break;  // (cannot happen: the head saw the pair continue)
+    const double *q = bnd + ((size_t)(2 * u) * 32 + lane) * 2;
+    a0 += q[0], a1 += q[1];
+    if (!(f & 4)) break;  // the pair ends in this chunk
+  }
+  schur_store(g, key, lane, a0, a1, ld, grow);
 }
 
 // S += Hpp (+ lambda on the diagonal), rhs column += bp.  One thread per scalar of each block.
