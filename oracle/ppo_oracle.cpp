@@ -757,6 +757,7 @@ struct ppo_oracle_handle {
     }
   }
   // ---- setLambda + BlockSolver::solve + restoreDiagonal (core/block_solver.hpp:354-486,564-604) --
+  bool schur_only = false;
   bool solve_damped(double lam) {
     Hschur = Hpp;
     for (int i = 0; i < n_p; i++) Hschur[(size_t)i * n_p + i] += lam;
@@ -791,6 +792,7 @@ struct ppo_oracle_handle {
       }
     }
     for (int i = 0; i < n_p; i++) bschur[i] = b[i] - coeff[i];
+    if (schur_only) return true;  // (tests on very large windows check the reduced system itself; its solution is checked against LAPACK)
     if (n_p > 0 && !dense_solve(Hschur, bschur.data(), x.data())) return false;
     // xl = Dinv (bl - Hpl^T xp)
 #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1)
@@ -1223,9 +1225,19 @@ int ppo_oracle_debug_linearize(ppo_oracle_handle *h, int32_t dims[2], double *Hp
   return PPO_OK;
 }
 // After debug_linearize: Schur complement + solve for a given lambda. Hschur n_p x n_p (upper), x full.
+// x == NULL: the reduced system only (no factorisation: n_p^3/3 flops on one core is minutes for a 1000-key-frame window)
 int ppo_oracle_debug_solve(ppo_oracle_handle *h, double lambda, double *Hschur_upper, double *bschur, double *x, int32_t *ok) {
   // reproduce solve_damped but keep a copy of Hschur before the factorisation overwrites it
   h->lambda = lambda;
+  h->schur_only = x == nullptr;
+  if (h->schur_only) {  // Hschur is not overwritten in this mode: hand it out directly
+    bool good = h->solve_damped(lambda);
+    h->schur_only = false;
+    if (ok) *ok = good;
+    if (Hschur_upper) std::copy(h->Hschur.begin(), h->Hschur.end(), Hschur_upper);
+    if (bschur) std::copy(h->bschur.begin(), h->bschur.end(), bschur);
+    return PPO_OK;
+  }
   std::vector<double> Hpp_keep = h->Hpp;
   bool good = h->solve_damped(lambda);
   if (ok) *ok = good;

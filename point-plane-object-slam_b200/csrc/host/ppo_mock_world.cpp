@@ -2,6 +2,7 @@
 // the inverse of the flattening the shim performs — calls ORB_SLAM2::Optimizer::LocalBACameraPlaneCuboids /
 // LocalBundleAdjustment exactly like LocalMapping::Run does (src/LocalMapping.cc:100,107) and reads the written-back
 // map state out again.  Input generation / bookkeeping only.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,9 @@ using namespace ORB_SLAM2;
 // test options of the mock map: every `bad_point_every`-th map point and key-frame slot `bad_kf` are flagged isBad()
 // (0 / -1: none); they must be left out of the graph and untouched by the write-back
 static int g_bad_point_every = 0, g_bad_kf = -1;
+static double g_last_call_ms = 0;
+// wall clock of the last Optimizer:: call itself (window collection + flattening + engine + write-back), without the mock map's construction
+extern "C" double ppo_mock_last_call_ms() { return g_last_call_ms; }
 extern "C" void ppo_mock_set_options(int bad_point_every, int bad_kf) { g_bad_point_every = bad_point_every, g_bad_kf = bad_kf; }
 
 extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int fixPoint, unsigned char *stop, ppo_ba_state *out,
@@ -171,8 +175,10 @@ extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int
 
   // ---- the call LocalMapping::Run makes ------------------------------------------------------------------------------------------
   bool stop_flag = stop ? (*stop != 0) : false;
+  const auto t_call = std::chrono::steady_clock::now();
   if (mixed) Optimizer::LocalBACameraPlaneCuboids(kfs[pkf].get(), &stop_flag, &map, fixCamera != 0, fixPoint != 0);
   else Optimizer::LocalBundleAdjustment(kfs[pkf].get(), &stop_flag, &map);
+  g_last_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
 
   // ---- read the map back ------------------------------------------------------------------------------------------------------------
   counts[0] = counts[1] = counts[2] = counts[3] = 0;

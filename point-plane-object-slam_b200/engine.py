@@ -169,12 +169,12 @@ class Handle:
         self._check(f(self.h, C.byref(dims), Hpp.ctypes.data, b.ctypes.data, Hll.ctypes.data, C.addressof(chi2)), "debug_linearize")
         return dict(n_p=n_p, n_l=n_l, Hpp=Hpp, b=b, Hll=Hll, chi2=chi2.value)
 
-    def debug_solve(self, lam, n_p, n_l):
+    def debug_solve(self, lam, n_p, n_l, solve=True):
         S = np.zeros((n_p, n_p))
         bs = np.zeros(n_p)
-        x = np.zeros(n_p + 3 * n_l)
+        x = np.zeros(n_p + 3 * n_l) if solve else None
         ok = C.c_int32()
-        self._check(self._f("debug_solve")(self.h, C.c_double(lam), S.ctypes.data, bs.ctypes.data, x.ctypes.data, C.byref(ok)), "debug_solve")
+        self._check(self._f("debug_solve")(self.h, C.c_double(lam), S.ctypes.data, bs.ctypes.data, x.ctypes.data if solve else None, C.byref(ok)), "debug_solve")
         return dict(Hschur=S, bschur=bs, x=x, ok=ok.value)
 
     def close(self):

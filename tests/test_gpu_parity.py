@@ -395,3 +395,32 @@ def test_lm_controller_on_device_graph_equals_host_loop(ppo):
             assert x == y  # the same kernels in the same order, every reduction in a fixed order: bit-identical
     for name in ("kf_pose", "pt_xyz", "pl_coef", "cu_state"):
         assert np.array_equal(getattr(sg, name), getattr(sh, name)), name
+
+
+def test_config4_single_gpu_linearisation_schur_and_solve(ppo, oracle_mod):
+    """BASELINE configs[4] (1000 KF / 400k points / 1k planes / 200 cuboids, n_p = 7794) on ONE GPU: the full 15-iteration oracle run
+    is too slow for a test, one linearisation is not.  Engine vs oracle: chi2, Hpp / Hll / b blocks, the reduced system
+    Hschur | bschur; and the engine's dense solve (persistent tiled Cholesky, 122 x 122 tiles) against LAPACK on its own Hschur."""
+    import os
+    g = ppo.synth.make_graph(ppo.synth.config(4))
+    o, e = run_both(ppo, oracle_mod, g)
+    o.set_threads(os.cpu_count() or 1)
+    lo, le = o.debug_linearize(), e.debug_linearize()
+    assert (lo["n_p"], lo["n_l"]) == (le["n_p"], le["n_l"]) == (7794, 401000)
+    assert np.isclose(le["chi2"], lo["chi2"], rtol=1e-10)
+
+    def close(a, b, tol):
+        return np.abs(a - b).max() <= tol * np.abs(b).max()
+    assert close(np.triu(le["Hpp"]), np.triu(lo["Hpp"]), 1e-6)
+    assert close(le["Hll"], lo["Hll"], 1e-6) and close(le["b"], lo["b"], 1e-6)
+    lam = 1e-5 * max(np.abs(np.diag(lo["Hpp"])).max(), np.abs(lo["Hll"][:, [0, 4, 8]]).max())
+    so = o.debug_solve(lam, lo["n_p"], lo["n_l"], solve=False)
+    se = e.debug_solve(lam, le["n_p"], le["n_l"])
+    assert se["ok"] == 1
+    assert close(np.triu(se["Hschur"]), np.triu(so["Hschur"]), 1e-6)
+    assert close(se["bschur"], so["bschur"], 1e-6)
+    S = np.triu(se["Hschur"])
+    S = S + np.triu(S, 1).T
+    x_ref = np.linalg.solve(S, se["bschur"])  # LAPACK
+    n_p = le["n_p"]
+    assert np.abs(se["x"][:n_p] - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
