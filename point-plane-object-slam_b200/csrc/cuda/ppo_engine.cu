@@ -720,7 +720,12 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   DA(g.Hpp_kf, 36 * (size_t)g.n_kf); DA(g.Hpp_cu, 81 * (size_t)g.n_cu); DA(g.Hpc, 54 * (size_t)g.n_cbe); DA(g.bp, (size_t)h->max_np);
   DA(g.Hll, 6 * (size_t)g.n_lm); DA(g.bl, 3 * (size_t)g.n_lm); DA(g.Hpl, 18 * (size_t)g.n_ent); DA(g.BD, 18 * (size_t)g.n_ent); DA(g.Zent, 3 * (size_t)g.n_ent); DA(g.Dinv, 6 * (size_t)g.n_lm);
   DA(g.xl, 3 * (size_t)g.n_lm); DA(g.S, dense_matrix_doubles(h->max_np)); DA(g.xp, dense_x_doubles(h->max_np));
-  h->nb_lin = cdiv(g.n_units, LIN_WARPS); h->nb_res = cdiv(g.n_pe, RES_THREADS);
+  {  // linearisation: a grid-stride loop over the work units, sized to fill the device once
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    h->nb_lin = std::max(1, std::min(cdiv(g.n_units, LIN_WARPS), sms * LIN_CTAS_PER_SM));
+  }
+  h->nb_res = cdiv(g.n_pe, RES_THREADS);
   h->nb_pl = cdiv(g.n_ple, SMALL_THREADS); h->nb_cb = cdiv(g.n_cbe, SMALL_THREADS); h->nb_pc = cdiv(g.n_pce, SMALL_THREADS);
   h->nb_bs = cdiv(g.n_pl, BS_WARPS) + g.n_units;  // partial sums of k_backsub (planes) + k_backsub_points
   DA(h->d_chi_pt, (size_t)std::max(h->nb_lin, h->nb_res)); DA(h->d_chi_pl, (size_t)h->nb_pl); DA(h->d_chi_cb, (size_t)h->nb_cb); DA(h->d_chi_pc, (size_t)h->nb_pc);

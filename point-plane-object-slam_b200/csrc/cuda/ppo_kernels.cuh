@@ -172,7 +172,8 @@ PPO_D void point_edge_linearize(const double Rt[12], const double X[3], const fl
   }
 }
 
-constexpr int LIN_WARPS = 1;  // one warp per CTA: the unit bounds come from a block-uniform address, so the scan shuffles need no convergence barriers
+constexpr int LIN_WARPS = 4;     // warps per CTA; every warp walks over work units with a grid stride (all control flow is warp-uniform)
+constexpr int LIN_CTAS_PER_SM = 5;  // 20 warps per SM at 94 registers
 constexpr int STAGE_LD = 19;  // 18 doubles per 6x3 block + 1 pad: conflict-free half-warp stores
 
 // The Jacobian / assembly pass over the point edges (computeActiveErrors + linearizeOplus +
@@ -180,14 +181,22 @@ constexpr int STAGE_LD = 19;  // 18 doubles per 6x3 block + 1 pad: conflict-free
 // EdgeStereoSE3ProjectXYZ, landmark side): one warp owns a run of consecutive points with <= 32
 // edges, one lane per edge; Hll / bl come from a segmented warp-shuffle scan, the 6x3 Hpl blocks
 // are staged in shared memory and stored as one contiguous coalesced run.
-__global__ void __launch_bounds__(LIN_WARPS * 32, 20) k_point_linearize(DevGraph g, DevState s, double *chi_part) {
+__global__ void __launch_bounds__(LIN_WARPS * 32, LIN_CTAS_PER_SM) k_point_linearize(DevGraph g, DevState s, double *chi_part) {
   __shared__ double stage[LIN_WARPS][32 * STAGE_LD];
   __shared__ double wsum[LIN_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * LIN_WARPS + warp;
+  const int stride = gridDim.x * LIN_WARPS;
   double rho_sum = 0;
-  if (unit < g.n_units) {
-    const int e0 = g.unit_e0[unit], e1 = g.unit_e0[unit + 1];
+  int unit = blockIdx.x * LIN_WARPS + warp;
+  // the bounds of the NEXT unit are requested while the current one is processed: one dependent memory round trip less per unit
+  int e0n = unit < g.n_units ? g.unit_e0[unit] : 0, e1n = unit < g.n_units ? g.unit_e0[unit + 1] : 0;
+  for (; unit < g.n_units; unit += stride) {
+    const int e0 = e0n, e1 = e1n;
+    {
+      const int un = unit + stride;
+      e0n = un < g.n_units ? g.unit_e0[un] : 0;
+      e1n = un < g.n_units ? g.unit_e0[un + 1] : 0;
+    }
     for (int base = e0; base < e1; base += 32) {
       const int e = base + lane;
       const bool valid = e < e1;
@@ -197,29 +206,37 @@ __global__ void __launch_bounds__(LIN_WARPS * 32, 20) k_point_linearize(DevGraph
       double *st = &stage[warp][lane * STAGE_LD];
       int key = -1;
       bool lm_free = false, have_hpl = false;
-      if (valid) {
-        const PointEdgeRec rec = g.pe_rec[e];
-        const int pt = g.pe_pt[e];
-        key = pt;
-        const unsigned fl = g.pe_flags[e];
-        const bool ptfix = g.pt_fixed[pt];
-        lm_free = !ptfix;
-        const bool active = !(fl & PPO_EF_LEVEL1_) && !(g.kf_fixed[rec.kf] && ptfix);
+      // All loads of the unit are issued up front in TWO dependent levels (ncu: the kernel is bound by the latency of its chain of
+      // global loads, not by bandwidth): level 1 everything indexed by the edge, level 2 everything indexed by its key-frame / point.
+      // Lanes beyond the end of the unit read the last edge again, so that no load sits behind a branch.
+      {
+        const int el = min(e, e1 - 1);
+        const PointEdgeRec rec = g.pe_rec[el];
+        const int pt = g.pe_pt[el];
+        const unsigned fl = g.pe_flags[el];
+        const float is2f = g.pe_is2[el];
+        const int pidx = g.ent_pidx[g.n_slots + el];
+        const bool ptfix = g.pt_fixed[pt], kffix = g.kf_fixed[rec.kf];
+        double Rt[12], p[3], err[3];
+        float intr[5];
+#pragma unroll
+        for (int i = 0; i < 12; i++) Rt[i] = __ldg(&s.kf_Rt[12 * rec.kf + i]);
+#pragma unroll
+        for (int i = 0; i < 5; i++) intr[i] = __ldg(&g.kf_intr[5 * rec.kf + i]);
+        const double X0 = s.pt[3 * pt], X1 = s.pt[3 * pt + 1], X2 = s.pt[3 * pt + 2];
+        p[0] = Rt[0] * X0 + Rt[1] * X1 + Rt[2] * X2 + Rt[9];
+        p[1] = Rt[3] * X0 + Rt[4] * X1 + Rt[5] * X2 + Rt[10];
+        p[2] = Rt[6] * X0 + Rt[7] * X1 + Rt[8] * X2 + Rt[11];
+        if (valid) key = pt;
+        lm_free = valid && !ptfix;
+        // The branch condition is made to depend on every loaded value (x == x is false only for a NaN and cannot be folded
+        // away): otherwise ptxas sinks those loads into the branch, which costs one more dependent memory round trip
+        const bool loaded = (is2f == is2f) & (intr[0] == intr[0]) & (intr[1] == intr[1]) & (intr[2] == intr[2]) & (intr[3] == intr[3]) & (intr[4] == intr[4]) &
+                            (pidx >= -2) & (p[0] == p[0]) & (p[1] == p[1]) & (p[2] == p[2]);
+        const bool active = valid && !(fl & PPO_EF_LEVEL1_) && !(kffix && ptfix) && loaded;
         if (active) {
-          double Rt[12], p[3], err[3];
-          float intr[5];
-#pragma unroll
-          for (int i = 0; i < 12; i++) Rt[i] = __ldg(&s.kf_Rt[12 * rec.kf + i]);
-#pragma unroll
-          for (int i = 0; i < 5; i++) intr[i] = __ldg(&g.kf_intr[5 * rec.kf + i]);
-          {
-            const double X0 = s.pt[3 * pt], X1 = s.pt[3 * pt + 1], X2 = s.pt[3 * pt + 2];
-            p[0] = Rt[0] * X0 + Rt[1] * X1 + Rt[2] * X2 + Rt[9];
-            p[1] = Rt[3] * X0 + Rt[4] * X1 + Rt[5] * X2 + Rt[10];
-            p[2] = Rt[6] * X0 + Rt[7] * X1 + Rt[8] * X2 + Rt[11];
-          }
           const int D = point_edge_error(p, intr, rec.u, rec.v, rec.ur, err);
-          const double is2 = (double)g.pe_is2[e];
+          const double is2 = (double)is2f;
           const double chi2 = err[0] * (is2 * err[0]) + err[1] * (is2 * err[1]) + err[2] * (is2 * err[2]);
           g.pe_chi2[e] = chi2;
           double rho0 = chi2, w = 1.0;
@@ -253,7 +270,7 @@ __global__ void __launch_bounds__(LIN_WARPS * 32, 20) k_point_linearize(DevGraph
             acc[5] = wj[2] * Jpt[2] + wj[5] * Jpt[5] + wj[8] * Jpt[8];
 #pragma unroll
             for (int a = 0; a < 3; a++) acc[6 + a] = -(wj[a] * err[0] + wj[3 + a] * err[1] + wj[6 + a] * err[2]);
-            if (g.ent_pidx[g.n_slots + e] >= 0) {
+            if (pidx >= 0) {
               have_hpl = true;
               // pose Jacobian one column at a time (types_six_dof_expmap.cpp:158-170,246-265): Hpl row a = Jkf(:,a)^T wj
               const double sm = D == 3 ? 1.0 : 0.0;
