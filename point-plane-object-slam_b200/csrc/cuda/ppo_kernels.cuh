@@ -174,7 +174,7 @@ PPO_D void point_edge_linearize(const double Rt[12], const double X[3], const fl
 
 constexpr int LIN_WARPS = 4;     // warps per CTA; every warp walks over work units with a grid stride (all control flow is warp-uniform)
 constexpr int LIN_CTAS_PER_SM = 5;  // 20 warps per SM at 94 registers
-constexpr int STAGE_LD = 19;  // 18 doubles per 6x3 block + 1 pad: conflict-free half-warp stores
+constexpr int STAGE_LD = 18;  // the staged 6x3 blocks are dense (144 bytes each): the run leaves shared memory as ONE TMA bulk store
 
 // The Jacobian / assembly pass over the point edges (computeActiveErrors + linearizeOplus +
 // constructQuadraticForm of core/block_solver.hpp:502-560 for EdgeSE3ProjectXYZ /
@@ -182,7 +182,7 @@ constexpr int STAGE_LD = 19;  // 18 doubles per 6x3 block + 1 pad: conflict-free
 // edges, one lane per edge; Hll / bl come from a segmented warp-shuffle scan, the 6x3 Hpl blocks
 // are staged in shared memory and stored as one contiguous coalesced run.
 __global__ void __launch_bounds__(LIN_WARPS * 32, LIN_CTAS_PER_SM) k_point_linearize(DevGraph g, DevState s, double *chi_part) {
-  __shared__ double stage[LIN_WARPS][32 * STAGE_LD];
+  __shared__ __align__(16) double stage[LIN_WARPS][32 * STAGE_LD];
   __shared__ double wsum[LIN_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stride = gridDim.x * LIN_WARPS;
@@ -274,28 +274,42 @@ __global__ void __launch_bounds__(LIN_WARPS * 32, LIN_CTAS_PER_SM) k_point_linea
               have_hpl = true;
               // pose Jacobian one column at a time (types_six_dof_expmap.cpp:158-170,246-265): Hpl row a = Jkf(:,a)^T wj
               const double sm = D == 3 ? 1.0 : 0.0;
-#define PPO_HPL_ROW(a, j0, j1, j2)                                   \
-  {                                                                  \
-    const double q0 = (j0), q1 = (j1), q2 = sm * (j2);               \
-    st[3 * (a)] = q0 * wj[0] + q1 * wj[3] + q2 * wj[6];              \
-    st[3 * (a) + 1] = q0 * wj[1] + q1 * wj[4] + q2 * wj[7];          \
-    st[3 * (a) + 2] = q0 * wj[2] + q1 * wj[5] + q2 * wj[8];          \
+              // two rows = six values = three 16-byte stores (lane stride 144 bytes: conflict-free per quarter warp)
+#define PPO_HPL_ROW(h, j0, j1, j2)                             \
+  {                                                            \
+    const double q0 = (j0), q1 = (j1), q2 = sm * (j2);         \
+    h[0] = q0 * wj[0] + q1 * wj[3] + q2 * wj[6];               \
+    h[1] = q0 * wj[1] + q1 * wj[4] + q2 * wj[7];               \
+    h[2] = q0 * wj[2] + q1 * wj[5] + q2 * wj[8];               \
+  }
+#define PPO_HPL_STORE2(a, h)                                                \
+  {                                                                         \
+    double2 *d2 = reinterpret_cast<double2 *>(st + 3 * (a));               \
+    d2[0] = make_double2(h[0], h[1]);                                       \
+    d2[1] = make_double2(h[2], h[3]);                                       \
+    d2[2] = make_double2(h[4], h[5]);                                       \
   }
               const double k00 = x * yz2 * fx, k01 = -(1 + x * xz2) * fx, k02 = y * fxz, k03 = -fxz, k05 = xz2 * fx;
-              PPO_HPL_ROW(0, k00, (1 + y * yz2) * fy, k00 - bf * yz2)
-              PPO_HPL_ROW(1, k01, -x * yz2 * fy, k01 + bf * xz2)
-              PPO_HPL_ROW(2, k02, -x * fyz, k02)
-              PPO_HPL_ROW(3, k03, 0.0, k03)
-              PPO_HPL_ROW(4, 0.0, -fyz, 0.0)
-              PPO_HPL_ROW(5, k05, yz2 * fy, k05 - bf * iz2)
+              double hh[6];
+              double *h0 = hh, *h1 = hh + 3;
+              PPO_HPL_ROW(h0, k00, (1 + y * yz2) * fy, k00 - bf * yz2)
+              PPO_HPL_ROW(h1, k01, -x * yz2 * fy, k01 + bf * xz2)
+              PPO_HPL_STORE2(0, hh)
+              PPO_HPL_ROW(h0, k02, -x * fyz, k02)
+              PPO_HPL_ROW(h1, k03, 0.0, k03)
+              PPO_HPL_STORE2(2, hh)
+              PPO_HPL_ROW(h0, 0.0, -fyz, 0.0)
+              PPO_HPL_ROW(h1, k05, yz2 * fy, k05 - bf * iz2)
+              PPO_HPL_STORE2(4, hh)
 #undef PPO_HPL_ROW
+#undef PPO_HPL_STORE2
             }
           }
         }
       }
       if (!have_hpl) {
 #pragma unroll
-        for (int i = 0; i < 18; i++) st[i] = 0.0;
+        for (int i = 0; i < 9; i++) reinterpret_cast<double2 *>(st)[i] = make_double2(0.0, 0.0);
       }
       // segmented inclusive scan over the lanes of one point
 #pragma unroll
@@ -317,18 +331,16 @@ __global__ void __launch_bounds__(LIN_WARPS * 32, LIN_CTAS_PER_SM) k_point_linea
 #pragma unroll
         for (int i = 0; i < 3; i++) atomicAdd(&g.bl[3 * (size_t)L + i], acc[6 + i]);
       }
-      // Hpl blocks of this run: staged above, stored as one contiguous coalesced run
+      // Hpl blocks of this run: staged above, written to global memory by ONE TMA bulk store (cp.async.bulk shared -> global)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my generic-proxy stores to the staging buffer, before the async proxy reads it
       __syncwarp();
-      const int n = (min(e1, base + 32) - base) * 18;
-      double *dst = g.Hpl + 18 * (size_t)(g.n_slots + base);
-      {  // element i = lane + 32 k of the run sits at stage[(i / 18) * STAGE_LD + i % 18]: (quotient, remainder) advanced incrementally
-        int q = lane / 18, r = lane - 18 * q;
-        for (int i = lane; i < n; i += 32) {
-          dst[i] = stage[warp][q * STAGE_LD + r];
-          r += 14;  // 32 = 18 + 14
-          q += 1;
-          if (r >= 18) r -= 18, q += 1;
-        }
+      if (lane == 0) {
+        const unsigned bytes = (unsigned)(min(e1, base + 32) - base) * 144u;
+        double *dst = g.Hpl + 18 * (size_t)(g.n_slots + base);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((unsigned)__cvta_generic_to_shared(&stage[warp][0])), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer may be overwritten (the global writes complete on their own)
       }
       __syncwarp();
     }
