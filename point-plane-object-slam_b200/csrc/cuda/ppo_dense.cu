@@ -160,32 +160,36 @@ __device__ __forceinline__ void tile_mma64(const double (*sA)[CLD], const double
 //   (b) L_is = A_is V^T (rows below), X_s,: = V X_s,: (columns left)              -- DMMA, all warps
 //   (c) A_ij -= L_is L_js^T, X_i,: -= L_is X_s,:                                  -- DMMA, all warps
 struct FacSmem {
-  double vbuf[2][2][SB];  // [double buffer][pivot of the pair][row]: the two pivot columns of A
-  double tbuf[2][2][SB];  // the two multiplier vectors of the step (consumed by the identity half one step later)
-  double rs[SB];          // 1 / sqrt(d_i)
+  // buf[half][slot][vector][index]: half 0 = the two pivot columns of A (read by the row lanes), half 1 = the two multiplier
+  // vectors (read by the column lanes one step later).  The multipliers of step j go to slot (j/2 + 1) & 1, so that in every step
+  // BOTH halves read slot (j/2) & 1 of their own half: one per-lane base address, no selects in the loop.
+  double buf[2][2][2][SB];
+  double rs[SB];  // 1 / sqrt(d_i)
 };
 __device__ __forceinline__ void sub_factor16(TilePtr D, TilePtr X, int s, FacSmem &fs, int *not_spd) {
   // Two pivots per step (2 x 2 block elimination): the serial chain per step is  shared-memory round trip -> determinant ->
   // reciprocal -> two multipliers -> update.  Lane i < 16 owns ROW i of A_ss; lane 16 + c owns COLUMN c of the identity part
   // X, so its pivot entries are its own registers and all it needs per step are the two multiplier vectors, which the row
   // lanes publish; the column lanes run one step behind, off the serial chain.  Both halves execute the same instruction
-  // r[k] += vec0[k] * s0 + vec1[k] * s1   (rows: vec = pivot columns, s = own multipliers; columns: vec = multipliers, s = own pivots).
+  // r[k] += vec0[k] * s0 + vec1[k] * s1   (rows: vec = pivot columns, s = own multipliers; columns: vec = multipliers, s = own pivots),
+  // and only for the indices a step can still change (k >= j - 2).
   const int lane = threadIdx.x & 31, li = lane & 15;
   const bool lo = lane < 16;
   const int o = SB * s;
   double r[SB];
 #pragma unroll
   for (int c = 0; c < SB; c++) r[c] = lo ? D[o + c][o + li] : (c == li ? 1.0 : 0.0);
+  (&fs.buf[1][0][0][0])[lane] = 0.0, (&fs.buf[1][0][0][0])[lane + 32] = 0.0;  // the column lanes read their half before it is first written (times zero)
   double my_d = 1.0;
+  const double *mine = &fs.buf[lo ? 0 : 1][0][0][0];
 #pragma unroll
   for (int j = 0; j <= SB; j += 2) {  // (the last round only flushes the lagging identity half)
     const int bi = (j >> 1) & 1;
-    if (j < SB && lo) fs.vbuf[bi][0][li] = r[j], fs.vbuf[bi][1][li] = r[j + 1];  // columns j, j+1 of the current A (= rows, by symmetry)
+    if (j < SB && lo) fs.buf[0][bi][0][li] = r[j], fs.buf[0][bi][1][li] = r[j + 1];  // columns j, j+1 of the current A (= rows, by symmetry)
     __syncwarp();
     double s0 = 0.0, s1 = 0.0;
-    const double *vec0 = fs.vbuf[0][0], *vec1 = fs.vbuf[0][1];  // (finite placeholders for the lanes that have nothing to apply: s0 = s1 = 0)
     if (j < SB) {
-      const double *v0 = fs.vbuf[bi][0], *v1 = fs.vbuf[bi][1];
+      const double *v0 = fs.buf[0][bi][0], *v1 = fs.buf[0][bi][1];
       double b00 = v0[j], b10 = v0[j + 1], b11 = v1[j + 1];
       const double c0 = v0[li], c1 = v1[li];
       double det = fma(b00, b11, -b10 * b10);
@@ -200,16 +204,14 @@ __device__ __forceinline__ void sub_factor16(TilePtr D, TilePtr X, int s, FacSme
       t0 = li == j + 1 ? -b10 * i00 : t0, t1 = li == j + 1 ? 0.0 : t1;
       t0 = li <= j ? 0.0 : t0, t1 = li <= j ? 0.0 : t1;
       if (lo) {
-        fs.tbuf[bi][0][li] = t0, fs.tbuf[bi][1][li] = t1;
-        s0 = t0, s1 = t1, vec0 = v0, vec1 = v1;
+        fs.buf[1][bi ^ 1][0][li] = t0, fs.buf[1][bi ^ 1][1][li] = t1;
+        s0 = t0, s1 = t1;
       }
     }
-    if (!lo && j >= 2) {  // the identity half applies the PREVIOUS step (pivots j-2, j-1): its multipliers were published one round ago
-      vec0 = fs.tbuf[bi ^ 1][0], vec1 = fs.tbuf[bi ^ 1][1];
-      s0 = r[j >= 2 ? j - 2 : 0], s1 = r[j >= 2 ? j - 1 : 1];  // X(j-2, c), X(j-1, c) of my column c, before this step touches them
-    }
+    if (!lo && j >= 2) s0 = r[j >= 2 ? j - 2 : 0], s1 = r[j >= 2 ? j - 1 : 1];  // X(j-2, c), X(j-1, c) of my column c, before this step touches them
+    const double *vec0 = mine + bi * 2 * SB, *vec1 = vec0 + SB;
 #pragma unroll
-    for (int c = 0; c < SB; c += 2) {
+    for (int c = (j >= 2 ? j - 2 : 2); c < SB; c += 2) {
       const double2 p = *reinterpret_cast<const double2 *>(&vec0[c]);
       const double2 q = *reinterpret_cast<const double2 *>(&vec1[c]);
       r[c] = fma(q.x, s1, fma(p.x, s0, r[c]));
@@ -698,6 +700,15 @@ __global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int Tm
       const double *W = Winv + (size_t)b * TILE;
       for (int e = tid; e < NB * NB; e += 256) sm.W[e >> 6][e & 63] = __ldcg(W + (e >> 6) * CLD + (e & 63));
     }
+    // my slice of y (the carried gradient row, final since the factorisation ended): requested now, consumed after the sweep
+    double yv = 0.0;
+    if (lane < 8) {
+      const int cl = 8 * warp + lane;
+      yv = NB * b + cl < n ? __ldcg(tile(Tc, b) + cl * CLD) : 0.0;
+    }
+#ifdef PPO_CHOL_TIMING
+    long long t_detect = clock64();
+#endif
     double s[8];  // lane-partial sums of  sum_r L(r, 8 warp + jj) x_c[r]  over all tiles so far
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) s[jj] = 0.0;
@@ -725,6 +736,9 @@ __global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int Tm
         const unsigned hi = __shfl_down_sync(0xffffffffu, (unsigned)w, 1);
         if (!(tid & 1)) sm.xc[tid >> 1] = __hiloint2double((int)hi, (int)(unsigned)w);
       }
+#ifdef PPO_CHOL_TIMING
+      if (c == b + 1) t_detect = clock64();
+#endif
       __syncthreads();
       if (!sm.ok) {
         ok = false;
@@ -739,16 +753,13 @@ __global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int Tm
       __syncthreads();  // the buffer may be refilled by the next prefetch
     }
     if (ok) {
-      const double *yrow = tile(Tc, b);  // gradient tile of this block column: row 0
 #pragma unroll
       for (int jj = 0; jj < 8; jj++) {
         double v = s[jj];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) {
-          const int cl = 8 * warp + jj;
-          sm.accv[cl] = (NB * b + cl < n ? __ldcg(yrow + cl * CLD) : 0.0) - v;
-        }
+        const double yj = __shfl_sync(0xffffffffu, yv, jj);
+        if (lane == 0) sm.accv[8 * warp + jj] = yj - v;
       }
       __syncthreads();
       {  // x_b = W^T acc  (W lower triangular: rows r >= i)
@@ -766,6 +777,12 @@ __global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int Tm
         p[1] = ((unsigned long long)want << 32) | (unsigned)__double2hiint(v);
         x[NB * b + tid] = v;
       }
+#ifdef PPO_CHOL_TIMING
+      if (tid == 0 && b < Tc - 1) {
+        atomicAdd((unsigned long long *)&g_chol_t[8], (unsigned long long)(clock64() - t_detect));
+        atomicAdd((unsigned long long *)&g_chol_t[9], 1ull);
+      }
+#endif
     }
   }
   __syncthreads();

@@ -82,6 +82,7 @@ static int run(int n, int max_n, int reps) {
     dense_timing_fetch(t, true);
     const double per = 1.0 / ((reps + 2) * (double)Tc);
     printf("   critical path, cycles per panel: factor %.0f  publish+operands %.0f  T-op %.0f  U-op %.0f\n", t[0] * per, t[1] * per, t[2] * per, t[3] * per);
+    printf("   back-substitution: cycles from 'x of the next block seen' to 'own x stored', mean over blocks: %.0f\n", t[9] ? (double)t[8] / (double)t[9] : 0.0);
     printf("   inside the factorisation, cycles per panel: (a) 4 x 16x16 %.0f  (b) %.0f  (c, warp 0 part) %.0f  (c, whole incl. next (a)) %.0f\n", t[4] * per, t[5] * per, t[6] * per,
            t[7] * per);
   }
