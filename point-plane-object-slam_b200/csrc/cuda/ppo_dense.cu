@@ -133,20 +133,35 @@ __device__ __forceinline__ int warp_row_block() {
   return warp < 4 ? warp : 11 - warp;
 }
 // acc(i, j) += sum_m sA[m][i] sB[m][j] on a 64 x 64 x 64 tile; a warp owns the 8 rows of its row block.
-// MODE 0: full; 1: lower triangle only (column blocks <= row block); 2: sB = W^T of a lower-triangular W (m <= j)
+// MODE 0: full; 1: lower triangle only (column blocks <= row block); 2: sB = W^T of a lower-triangular W (m <= j).
+// Fully unrolled and software-pipelined by hand: the fragments of k-step m0 + 4 are loaded from shared memory while the DMMAs
+// of step m0 issue (a DMMA that waits for its own operand load stalls the FP64 pipe for the shared-memory latency).
 template <int MODE>
 __device__ __forceinline__ void tile_mma64(const double (*sA)[CLD], const double (*sB)[CLD], double acc[8][2]) {
   const int lane = threadIdx.x & 31, rb = warp_row_block();
-  const int row = rb * 8 + (lane >> 2), kk = lane & 3;
-#pragma unroll 4
+  const int row = rb * 8 + (lane >> 2), kk = lane & 3, lc = lane >> 2;
+  const int nmax = MODE == 1 ? rb : 7;  // last column block of this warp (warp-uniform)
+  double a_n = sA[kk][row], b_n[8];
+#pragma unroll
+  for (int nbk = 0; nbk < 8; nbk++) b_n[nbk] = (nbk <= nmax) ? sB[kk][nbk * 8 + lc] : 0.0;
+#pragma unroll
   for (int m0 = 0; m0 < NB; m0 += 4) {
-    const double a = sA[m0 + kk][row];
+    const double a = a_n;
+    double b[8];
+#pragma unroll
+    for (int nbk = 0; nbk < 8; nbk++) b[nbk] = b_n[nbk];
+    if (m0 + 4 < NB) {
+      a_n = sA[m0 + 4 + kk][row];
+#pragma unroll
+      for (int nbk = 0; nbk < 8; nbk++) {
+        if (MODE == 2 && m0 + 4 > 8 * nbk + 7) continue;  // (compile time)
+        if (nbk <= nmax) b_n[nbk] = sB[m0 + 4 + kk][nbk * 8 + lc];
+      }
+    }
 #pragma unroll
     for (int nbk = 0; nbk < 8; nbk++) {
-      if (MODE == 1 && nbk > rb) continue;
-      if (MODE == 2 && m0 > 8 * nbk + 7) continue;
-      const double b = sB[m0 + kk][nbk * 8 + (lane >> 2)];
-      dmma(acc[nbk][0], acc[nbk][1], a, b);
+      if (MODE == 2 && m0 > 8 * nbk + 7) continue;  // (compile time)
+      if (nbk <= nmax) dmma(acc[nbk][0], acc[nbk][1], a, b[nbk]);
     }
   }
 }
