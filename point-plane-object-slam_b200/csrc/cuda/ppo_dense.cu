@@ -174,7 +174,7 @@ __device__ __forceinline__ void tile_mma64(const double (*sA)[CLD], const double
 //       16 FMAs per lane; no block barrier inside the 16 pivots.
 //   (b) L_is = A_is V^T (rows below), X_s,: = V X_s,: (columns left)              -- DMMA, all warps
 //   (c) A_ij -= L_is L_js^T, X_i,: -= L_is X_s,:                                  -- DMMA, all warps
-struct FacSmem {
+struct __align__(16) FacSmem {
   // buf[half][slot][vector][index]: half 0 = the two pivot columns of A (read by the row lanes), half 1 = the two multiplier
   // vectors (read by the column lanes one step later).  The multipliers of step j go to slot (j/2 + 1) & 1, so that in every step
   // BOTH halves read slot (j/2) & 1 of their own half: one per-lane base address, no selects in the loop.
@@ -249,8 +249,9 @@ __device__ __forceinline__ void blk_mma16(FA aop, FB bop, double &c0, double &c1
 #pragma unroll
   for (int ks = 0; ks < SB; ks += 4) dmma(c0, c1, aop(rr, ks + kk), bop(ks + kk, rr));
 }
-template <typename Poll>
-__device__ __forceinline__ void diag_factor(TilePtr D, TilePtr X, FacSmem &fs, int *not_spd, Poll poll) {
+// barrier of the 8 compute warps (the 9th warp of the CTA only talks to the rest of the device)
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void diag_factor(TilePtr D, TilePtr X, FacSmem &fs, int *not_spd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rr = lane >> 2, cc = 2 * (lane & 3);
   // trailing update of one 8 x 8 block (rb, cb <= rb) of A after sub-block s, mirrored
@@ -270,7 +271,7 @@ __device__ __forceinline__ void diag_factor(TilePtr D, TilePtr X, FacSmem &fs, i
   if (warp == 0) sub_factor16(D, X, 0, fs, not_spd);
   CH_STAMP(ta1);
   CH_ACC(4, ta0, ta1);
-  __syncthreads();
+  cbar();
   for (int s = 0; s < NB / SB; s++) {
     const int o = SB * s, R0 = o + SB;
     CH_STAMP(tb0);
@@ -304,7 +305,7 @@ __device__ __forceinline__ void diag_factor(TilePtr D, TilePtr X, FacSmem &fs, i
         }
       }
     }
-    __syncthreads();
+    cbar();
     CH_STAMP(tb1);
     CH_ACC(5, tb0, tb1);
     // (c) warp 0: the three blocks of the next diagonal sub-block, then straight on to factorise it (look-ahead);
@@ -355,23 +356,27 @@ __device__ __forceinline__ void diag_factor(TilePtr D, TilePtr X, FacSmem &fs, i
             X[c0 + cc + 1][r0 + rr] -= a1;
           }
         }
-        if (tid == 255) poll();  // (the last warp idles here while warp 0 factorises the next sub-block)
       }
     }
-    __syncthreads();
+    cbar();
     CH_STAMP(tc3);
     CH_ACC(7, tb1, tc3);
   }
 }
 
 // ---- persistent factorisation ----------------------------------------------------------------------------------------------
+// Every CTA has 8 compute warps and one COMMUNICATION warp (one active thread).  The compute warps only ever touch shared memory,
+// the tensor cores and plain global stores; everything that waits on the rest of the device -- claiming queue entries, polling
+// version counters, issuing the TMA loads, and the device-scope fence + release that publishes a finished tile (~3000 cycles) --
+// is done by the communication thread.  The two sides talk through mbarriers: full[s] (operands of buffer set s have landed;
+// completed by the TMA engine), done[s] (all compute warps have stored their part of the result and no longer read set s).
 struct ChSmem {
   double T[6][NB][CLD];  // critical path: 0 diagonal tile, 1 W, 2 tile below the diagonal, 3 next diagonal tile; workers: two sets {A, B, C}
-  unsigned long long mbar[2];
+  unsigned long long full[2];  // workers: per buffer set; critical path: [0] first diagonal tile, [1] operands of T / U
+  unsigned long long done[3];  // workers: per buffer set; critical path: [0] W stored, [1] P stored, [2] A / C free again
   FacSmem fs;
   int op[2][4];  // decoded queue entries {type, k, i, j}
-  int issued;
-  int ok;
+  int abort;     // a wait timed out somewhere on the device
 };
 struct CholArgs {
   double *S;
@@ -382,8 +387,32 @@ struct CholArgs {
   CholCtrl *ctrl;
   int *not_spd;
 };
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// communication thread: bounded wait for an mbarrier phase
+__device__ __forceinline__ bool mbar_wait_bounded(unsigned long long *bar, unsigned parity, CholCtrl *ctrl) {
+  if (mbar_test(bar, parity)) return true;
+  const long long t0 = clock64();
+  for (int it = 1;; it++) {
+    if (mbar_test(bar, parity)) return true;
+    if ((it & 1023) == 0) {
+      if (*(volatile int *)&ctrl->err) return false;
+      if (clock64() - t0 > CHOL_TIMEOUT) {
+        atomicExch(&ctrl->err, 1);
+        return false;
+      }
+    }
+  }
+}
+constexpr int CH_THREADS = 288;  // 8 compute warps + the communication warp
 
-__global__ void __launch_bounds__(256, 1) k_chol_dataflow(CholArgs a) {
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dataflow(CholArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   ChSmem &sm = *reinterpret_cast<ChSmem *>(dsm);
   __shared__ int s_role, s_base;
@@ -394,233 +423,264 @@ __global__ void __launch_bounds__(256, 1) k_chol_dataflow(CholArgs a) {
   if (tid == 0) {
     s_role = atomicAdd(&ctrl->ticket, 1);
     s_base = ld_acquire(&ctrl->epoch) * 256;
-    mbar_init(&sm.mbar[0], 1);
-    mbar_init(&sm.mbar[1], 1);
+    mbar_init(&sm.full[0], 1);
+    mbar_init(&sm.full[1], 1);
+    mbar_init(&sm.done[0], 8);
+    mbar_init(&sm.done[1], 8);
+    mbar_init(&sm.done[2], 8);
+    sm.abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int role = s_role, base = s_base;
-  const int il = warp_row_block() * 8 + (lane >> 2);  // my row of a tile in the DMMA C-fragment layout; my columns: 8 q + 2 (lane & 3) + h
+  const bool comm = warp == 8;
+  const int il = warp_row_block() * 8 + (lane >> 2);  // (compute warps) my row of a tile in the DMMA C-fragment layout; my columns: 8 q + 2 (lane & 3) + h
   const int jc = 2 * (lane & 3);
   auto tile = [&](int i, int j) { return S + dense_tile_index(Tm, i, j) * (size_t)TILE; };
+  // one elected lane per compute warp tells the communication thread that the warp's stores are issued / its reads are over
+  auto warp_arrive = [&](unsigned long long *bar) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  };
+  auto publish = [&](int *flag, int value) {  // communication thread: the tile behind `flag` is complete in global memory
+    __threadfence();
+    st_release(flag, value);
+  };
   if (role == 0) {
-    // ------------------------------- critical path -------------------------------------------------------------
+    // =============================== critical path ===============================================================
     TilePtr D = sm.T[0], W = sm.T[1], A = sm.T[2], C = sm.T[3];
-    unsigned ph0 = 0, ph1 = 0;
-    if (tid == 0) {
-      mbar_expect_tx(&sm.mbar[0], TILE_BYTES);
-      bulk_g2s(D, tile(0, 0), TILE_BYTES, &sm.mbar[0]);
-    }
-    mbar_wait(&sm.mbar[0], ph0);
-    ph0 ^= 1;
-    {  // symmetric fill + identity padding of the first diagonal tile
-      const int nb = min(NB, a.n);
-      __syncthreads();
-      for (int e = tid; e < NB * NB; e += 256) {
-        const int c = e >> 6, r = e & 63;
-        if (r >= c) {
-          const double v = (r < nb && c < nb) ? D[c][r] : (r == c ? 1.0 : 0.0);
-          D[c][r] = v;
-          D[r][c] = v;
-        }
-      }
-    }
-    for (int k = 0; k < Tc; k++) {
-      CH_STAMP(t0);
-      for (int e = tid; e < TILE; e += 256) (&W[0][0])[e] = 0.0;
-      // operands of the two follow-up operations: requested as soon as their producers are done -- polled (by one thread of
-      // the last warp) between the sub-steps of the factorisation, otherwise waited for afterwards
-      auto request = [&]() {
-        if (sm.issued) return;
-        const bool more = k + 1 < Tc;
-        const bool rdy = k == 0 || (flag_ready(&a.ver[(k + 1) * vs + k], base + k) && (!more || flag_ready(&a.ver[(k + 1) * vs + k + 1], base + k)));
-        if (rdy) {
-          fence_proxy_async();
-          mbar_expect_tx(&sm.mbar[1], (more ? 2 : 1) * TILE_BYTES);
-          bulk_g2s(A, tile(k + 1, k), TILE_BYTES, &sm.mbar[1]);
-          if (more) bulk_g2s(C, tile(k + 1, k + 1), TILE_BYTES, &sm.mbar[1]);
-          sm.issued = 1;
-        }
-      };
-      if (tid == 255) {
-        sm.issued = 0;
-        request();
-      }
-      __syncthreads();
-      diag_factor(D, W, sm.fs, a.not_spd, request);  // ends with a block barrier
-      CH_STAMP(t1);
-      {  // publish W_k (tile layout, so that workers fetch it with one bulk copy)
-        double *Wg = a.Winv + (size_t)k * TILE;
-        for (int e = tid; e < TILE; e += 256) Wg[e] = (&W[0][0])[e];
-      }
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        st_release(&a.ver[k * vs + k], base + k + 1);
-        bool ok = true;
-        if (!sm.issued) {
+    if (comm) {
+      if (lane == 0) {
+        mbar_expect_tx(&sm.full[0], TILE_BYTES);
+        bulk_g2s(D, tile(0, 0), TILE_BYTES, &sm.full[0]);
+        unsigned pd[3] = {0, 0, 0};
+        for (int k = 0; k < Tc; k++) {
           const bool more = k + 1 < Tc;
-          ok = flag_wait(&a.ver[(k + 1) * vs + k], base + k, ctrl);
-          if (ok && more) ok = flag_wait(&a.ver[(k + 1) * vs + k + 1], base + k, ctrl);
-          if (ok) request();
-        }
-        sm.ok = ok;
-      }
-      __syncthreads();
-      if (!sm.ok) break;
-      mbar_wait(&sm.mbar[1], ph1);
-      ph1 ^= 1;
-      CH_STAMP(t2);
-      // T_k(k+1): the tile right below the diagonal
-      double acc[8][2];
-#pragma unroll
-      for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
-      const bool grad_tile = (k + 1 == Tc);  // the gradient tile has one valid row
-      if (!grad_tile || warp == 0) tile_mma64<2>(A, W, acc);
-      __syncthreads();  // everybody has read A
-      {
-        double *dst = tile(k + 1, k);
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int jl = q * 8 + jc + h;
-            dst[jl * CLD + il] = acc[q][h];
-            A[jl][il] = acc[q][h];
+          // operands of T_k(k+1) and U_k(k+1,k+1): as soon as their producers are done and the buffers are free again
+          bool ok = k == 0 || mbar_wait_bounded(&sm.done[2], pd[2], ctrl);
+          if (k > 0) pd[2] ^= 1;
+          if (ok && k > 0) ok = flag_wait(&a.ver[(k + 1) * vs + k], base + k, ctrl) && (!more || flag_wait(&a.ver[(k + 1) * vs + k + 1], base + k, ctrl));
+          if (ok) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.full[1], (more ? 2 : 1) * TILE_BYTES);
+            bulk_g2s(A, tile(k + 1, k), TILE_BYTES, &sm.full[1]);
+            if (more) bulk_g2s(C, tile(k + 1, k + 1), TILE_BYTES, &sm.full[1]);
           }
+          // W_k, then P_{k+1,k}: published the moment the compute warps have stored them
+          ok = ok && mbar_wait_bounded(&sm.done[0], pd[0], ctrl);
+          pd[0] ^= 1;
+          if (ok) publish(&a.ver[k * vs + k], base + k + 1);
+          ok = ok && mbar_wait_bounded(&sm.done[1], pd[1], ctrl);
+          pd[1] ^= 1;
+          if (ok) publish(&a.ver[(k + 1) * vs + k], base + k + 1);
+          if (!ok) {  // timed out (or another CTA did): release the compute warps, which may sit in an mbarrier wait
+            sm.abort = 1;
+            mbar_arrive(&sm.full[1]);
+            break;
+          }
+        }
       }
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        st_release(&a.ver[(k + 1) * vs + k], base + k + 1);  // P_{k+1,k} is published
+    } else {
+      unsigned pf1 = 0;
+      mbar_wait(&sm.full[0], 0);
+      {  // symmetric fill + identity padding of the first diagonal tile
+        const int nb = min(NB, a.n);
+        cbar();
+        for (int e = tid; e < NB * NB; e += 256) {
+          const int c = e >> 6, r = e & 63;
+          if (r >= c) {
+            const double v = (r < nb && c < nb) ? D[c][r] : (r == c ? 1.0 : 0.0);
+            D[c][r] = v;
+            D[r][c] = v;
+          }
+        }
+        for (int e = tid; e < TILE; e += 256) (&W[0][0])[e] = 0.0;
+        cbar();
       }
-      CH_STAMP(t3);
-      if (k + 1 >= Tc) {
+      for (int k = 0; k < Tc; k++) {
+        CH_STAMP(t0);
+        diag_factor(D, W, sm.fs, a.not_spd);  // ends with a barrier of the compute warps
+        CH_STAMP(t1);
+        {  // W_k to global memory (tile layout, so that workers fetch it with one bulk copy)
+          double *Wg = a.Winv + (size_t)k * TILE;
+          for (int e = tid; e < TILE; e += 256) Wg[e] = (&W[0][0])[e];
+        }
+        warp_arrive(&sm.done[0]);
+        mbar_wait(&sm.full[1], pf1);
+        pf1 ^= 1;
+        if (*(volatile int *)&sm.abort) break;
+        CH_STAMP(t2);
+        // T_k(k+1): the tile right below the diagonal
+        double acc[8][2];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
+        const bool grad_tile = (k + 1 == Tc);  // the gradient tile has one valid row
+        if (!grad_tile || warp == 0) tile_mma64<2>(A, W, acc);
+        cbar();  // everybody has read A and W
+        {
+          double *dst = tile(k + 1, k);
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int jl = q * 8 + jc + h;
+              dst[jl * CLD + il] = acc[q][h];
+              A[jl][il] = acc[q][h];
+            }
+          for (int e = tid; e < TILE; e += 256) (&W[0][0])[e] = 0.0;  // cleared for the next panel
+        }
+        warp_arrive(&sm.done[1]);
+        CH_STAMP(t3);
+        if (k + 1 >= Tc) {
+          CH_ACC(0, t0, t1);
+          CH_ACC(1, t1, t2);
+          CH_ACC(2, t2, t3);
+          break;
+        }
+        cbar();  // P is complete in shared memory
+        // U_k(k+1,k+1) on the next diagonal tile, which then stays in shared memory for F_{k+1}
+        {
+          const int nb2 = min(NB, a.n - NB * (k + 1));
+#pragma unroll
+          for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
+          tile_mma64<1>(A, A, acc);
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int jl = q * 8 + jc + h;
+              if (il >= jl) {
+                const double v = (il < nb2 && jl < nb2) ? C[jl][il] - acc[q][h] : (il == jl ? 1.0 : 0.0);
+                D[jl][il] = v;
+                D[il][jl] = v;
+              }
+            }
+        }
+        warp_arrive(&sm.done[2]);  // A and C may be refilled
+        cbar();
+        CH_STAMP(t4);
         CH_ACC(0, t0, t1);
         CH_ACC(1, t1, t2);
         CH_ACC(2, t2, t3);
-        break;
+        CH_ACC(3, t3, t4);
       }
-      // U_k(k+1,k+1) on the next diagonal tile, which then stays in shared memory for F_{k+1}
-      {
-        const int nb2 = min(NB, a.n - NB * (k + 1));
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
-        tile_mma64<1>(A, A, acc);
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int jl = q * 8 + jc + h;
-            if (il >= jl) {
-              const double v = (il < nb2 && jl < nb2) ? C[jl][il] - acc[q][h] : (il == jl ? 1.0 : 0.0);
-              D[jl][il] = v;
-              D[il][jl] = v;
+    }
+  } else if (comm) {
+    // =============================== workers, communication thread ===============================================
+    if (lane == 0) {
+      int lvl = 0, lvl_start = 0;  // level of the last decoded entry and index of its first entry
+      auto claim = [&](int slot) -> bool {  // next queue entry -> sm.op[slot]; false: the queue is exhausted
+        const int idx = atomicAdd(&ctrl->qhead, 1);
+        int type = -1, k = 0, i = 0, j = 0;
+        for (; lvl < Tc; lvl++) {
+          const int m = Tc - 1 - lvl;
+          const int size = m + (m >= 1 ? (m + 1) * (m + 2) / 2 - 2 : 0);
+          if (idx < lvl_start + size) break;
+          lvl_start += size;
+        }
+        if (lvl < Tc) {
+          k = lvl;
+          const int m = Tc - 1 - k;
+          int u = idx - lvl_start;
+          if (u < m) {  // T_k(i), i = k+2 .. Tc
+            type = 0, i = k + 2 + u, j = k;
+          } else {      // U_k(i, j): column k+1 rows k+2..Tc, then columns j >= k+2 rows j..Tc
+            type = 1;
+            u -= m;
+            if (u < m) {
+              i = k + 2 + u, j = k + 1;
+            } else {
+              u -= m;
+              for (j = k + 2;; j++) {
+                const int cnt = Tc - j + 1;
+                if (u < cnt) break;
+                u -= cnt;
+              }
+              i = j + u;
             }
           }
+        }
+        sm.op[slot][0] = type, sm.op[slot][1] = k, sm.op[slot][2] = i, sm.op[slot][3] = j;
+        return type >= 0;
+      };
+      auto deps_ready = [&](int slot) -> bool {  // are the producers of the entry done?
+        const int type = sm.op[slot][0], k = sm.op[slot][1], i = sm.op[slot][2], j = sm.op[slot][3];
+        if (type == 0) return flag_ready(&a.ver[k * vs + k], base + k + 1) && (k == 0 || flag_ready(&a.ver[i * vs + k], base + k));
+        return flag_ready(&a.ver[i * vs + k], base + k + 1) && (j == i || flag_ready(&a.ver[j * vs + k], base + k + 1)) &&
+               (k == 0 || flag_ready(&a.ver[i * vs + j], base + k));
+      };
+      auto issue = [&](int slot) {  // TMA loads of the entry's operands into buffer set `slot`
+        const int type = sm.op[slot][0], k = sm.op[slot][1], i = sm.op[slot][2], j = sm.op[slot][3];
+        fence_proxy_async();
+        if (type == 0) {
+          mbar_expect_tx(&sm.full[slot], 2 * TILE_BYTES);
+          bulk_g2s(sm.T[3 * slot], tile(i, k), TILE_BYTES, &sm.full[slot]);
+          bulk_g2s(sm.T[3 * slot + 1], a.Winv + (size_t)k * TILE, TILE_BYTES, &sm.full[slot]);
+        } else {
+          const bool diag = i == j;
+          mbar_expect_tx(&sm.full[slot], (diag ? 2 : 3) * TILE_BYTES);
+          bulk_g2s(sm.T[3 * slot], tile(i, k), TILE_BYTES, &sm.full[slot]);
+          if (!diag) bulk_g2s(sm.T[3 * slot + 1], tile(j, k), TILE_BYTES, &sm.full[slot]);
+          bulk_g2s(sm.T[3 * slot + 2], tile(i, j), TILE_BYTES, &sm.full[slot]);
+        }
+      };
+      // ring of two buffer sets: `head` is filled next, `tail` retired next; the descriptor of an entry in flight stays in sm.op[slot]
+      int head = 0, tail = 0, inflight = 0;
+      bool claimed = false, exhausted = false;
+      unsigned pd[2] = {0, 0};
+      int rel_i[2] = {0, 0}, rel_j[2] = {0, 0}, rel_v[2] = {0, 0};
+      long long t_idle = clock64();
+      for (;;) {
+        bool progress = false;
+        if (inflight > 0 && mbar_test(&sm.done[tail], pd[tail])) {  // the oldest entry is computed and stored: publish its tile
+          pd[tail] ^= 1;
+          publish(&a.ver[rel_i[tail] * vs + rel_j[tail]], rel_v[tail]);
+          tail ^= 1;
+          inflight--;
+          progress = true;
+        }
+        if (!claimed && !exhausted && inflight < 2) {
+          if (claim(head)) claimed = true;
+          else exhausted = true;
+          progress = true;
+        }
+        if (claimed && deps_ready(head)) {
+          rel_i[head] = sm.op[head][2], rel_j[head] = sm.op[head][3], rel_v[head] = base + sm.op[head][1] + 1;
+          issue(head);
+          head ^= 1;
+          inflight++;
+          claimed = false;
+          progress = true;
+        }
+        if (exhausted && inflight == 0) {  // (sm.op[head][0] is -1: written by the failed claim) wake the compute warps for the last time
+          mbar_arrive(&sm.full[head]);
+          break;
+        }
+        if (progress) {
+          t_idle = clock64();
+        } else {
+          __nanosleep(20);
+          if (*(volatile int *)&ctrl->err || clock64() - t_idle > CHOL_TIMEOUT) {
+            atomicExch(&ctrl->err, 1);
+            sm.abort = 1;
+            sm.op[head][0] = -1, sm.op[head ^ 1][0] = -1;
+            mbar_arrive(&sm.full[0]);
+            mbar_arrive(&sm.full[1]);
+            break;
+          }
+        }
       }
-      __syncthreads();
-      CH_STAMP(t4);
-      CH_ACC(0, t0, t1);
-      CH_ACC(1, t1, t2);
-      CH_ACC(2, t2, t3);
-      CH_ACC(3, t3, t4);
     }
   } else {
-    // ------------------------------- workers: operations from the queue ---------------------------------------------
-    int lvl = 0, lvl_start = 0;  // (thread 0) level of the last decoded entry and index of its first entry
-    auto claim = [&](int slot) {  // thread 0: next queue entry -> sm.op[slot]
-      const int idx = atomicAdd(&ctrl->qhead, 1);
-      int type = -1, k = 0, i = 0, j = 0;
-      for (; lvl < Tc; lvl++) {
-        const int m = Tc - 1 - lvl;
-        const int size = m + (m >= 1 ? (m + 1) * (m + 2) / 2 - 2 : 0);
-        if (idx < lvl_start + size) break;
-        lvl_start += size;
-      }
-      if (lvl < Tc) {
-        k = lvl;
-        const int m = Tc - 1 - k;
-        int u = idx - lvl_start;
-        if (u < m) {  // T_k(i), i = k+2 .. Tc
-          type = 0, i = k + 2 + u, j = k;
-        } else {      // U_k(i, j): column k+1 rows k+2..Tc, then columns j >= k+2 rows j..Tc
-          type = 1;
-          u -= m;
-          if (u < m) {
-            i = k + 2 + u, j = k + 1;
-          } else {
-            u -= m;
-            for (j = k + 2;; j++) {
-              const int cnt = Tc - j + 1;
-              if (u < cnt) break;
-              u -= cnt;
-            }
-            i = j + u;
-          }
-        }
-      }
-      sm.op[slot][0] = type, sm.op[slot][1] = k, sm.op[slot][2] = i, sm.op[slot][3] = j;
-    };
-    auto deps = [&](int slot, bool block) -> bool {  // thread 0: are the producers of the entry done?
-      const int type = sm.op[slot][0], k = sm.op[slot][1], i = sm.op[slot][2], j = sm.op[slot][3];
-      const int *f[3];
-      int w[3], nf = 0;
-      if (type == 0) {
-        f[nf] = &a.ver[k * vs + k], w[nf++] = base + k + 1;
-        if (k > 0) f[nf] = &a.ver[i * vs + k], w[nf++] = base + k;
-      } else {
-        f[nf] = &a.ver[i * vs + k], w[nf++] = base + k + 1;
-        if (j != i) f[nf] = &a.ver[j * vs + k], w[nf++] = base + k + 1;
-        if (k > 0) f[nf] = &a.ver[i * vs + j], w[nf++] = base + k;
-      }
-      for (int q = 0; q < nf; q++) {
-        if (block) {
-          if (!flag_wait(f[q], w[q], ctrl)) return false;
-        } else if (!flag_ready(f[q], w[q])) {
-          return false;
-        }
-      }
-      return true;
-    };
-    auto issue = [&](int slot) {  // thread 0: TMA loads of the entry's operands into buffer set `slot`
-      const int type = sm.op[slot][0], k = sm.op[slot][1], i = sm.op[slot][2], j = sm.op[slot][3];
-      fence_proxy_async();
-      if (type == 0) {
-        mbar_expect_tx(&sm.mbar[slot], 2 * TILE_BYTES);
-        bulk_g2s(sm.T[3 * slot], tile(i, k), TILE_BYTES, &sm.mbar[slot]);
-        bulk_g2s(sm.T[3 * slot + 1], a.Winv + (size_t)k * TILE, TILE_BYTES, &sm.mbar[slot]);
-      } else {
-        const bool diag = i == j;
-        mbar_expect_tx(&sm.mbar[slot], (diag ? 2 : 3) * TILE_BYTES);
-        bulk_g2s(sm.T[3 * slot], tile(i, k), TILE_BYTES, &sm.mbar[slot]);
-        if (!diag) bulk_g2s(sm.T[3 * slot + 1], tile(j, k), TILE_BYTES, &sm.mbar[slot]);
-        bulk_g2s(sm.T[3 * slot + 2], tile(i, j), TILE_BYTES, &sm.mbar[slot]);
-      }
-    };
-    unsigned ph[2] = {0, 0};
-    int cur = 0;
-    if (tid == 0) {
-      claim(0);
-      if (sm.op[0][0] >= 0) {
-        if (deps(0, true)) issue(0);
-        else sm.op[0][0] = -1;
-      }
-    }
-    __syncthreads();
-    while (sm.op[cur][0] >= 0) {
+    // =============================== workers, compute warps ======================================================
+    unsigned pf[2] = {0, 0};
+    for (int cur = 0;; cur ^= 1) {
+      mbar_wait(&sm.full[cur], pf[cur]);
+      pf[cur] ^= 1;
       const int type = sm.op[cur][0], k = sm.op[cur][1], i = sm.op[cur][2], j = sm.op[cur][3];
-      if (tid == 0) {  // look ahead: claim the next entry and, if its producers are already done, start its loads now
-        claim(cur ^ 1);
-        sm.issued = 0;
-        if (sm.op[cur ^ 1][0] >= 0 && deps(cur ^ 1, false)) {
-          issue(cur ^ 1);
-          sm.issued = 1;
-        }
-      }
+      if (type < 0 || *(volatile int *)&sm.abort) break;
+      (void)k;
       TilePtr A = sm.T[3 * cur], B = sm.T[3 * cur + 1], C = sm.T[3 * cur + 2];
-      mbar_wait(&sm.mbar[cur], ph[cur]);
-      ph[cur] ^= 1;
       const bool one_row = (i == Tc);  // gradient tile: only row 0 carries data (the rest is zero padding)
       if (!one_row || warp == 0) {
         double acc[8][2];
@@ -646,17 +706,7 @@ __global__ void __launch_bounds__(256, 1) k_chol_dataflow(CholArgs a) {
             }
         }
       }
-      __syncthreads();  // all stores of the tile issued; buffer set `cur` is free again
-      if (tid == 0) {
-        __threadfence();
-        st_release(&a.ver[i * vs + j], base + k + 1);
-        if (sm.op[cur ^ 1][0] >= 0 && !sm.issued) {
-          if (deps(cur ^ 1, true)) issue(cur ^ 1);
-          else sm.op[cur ^ 1][0] = -1;
-        }
-      }
-      __syncthreads();
-      cur ^= 1;
+      warp_arrive(&sm.done[cur]);  // my stores are issued, my reads of this buffer set are over
     }
   }
   __syncthreads();
@@ -865,7 +915,7 @@ void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, 
   const int grid = (int)(1 + (ops < cap - 1 ? ops : cap - 1));
   CholArgs a;
   a.S = S, a.Tm = Tm, a.n = n, a.Tc = Tc, a.Winv = Winv, a.ver = ver, a.ctrl = ctrl, a.not_spd = not_spd;
-  k_chol_dataflow<<<grid, 256, sizeof(ChSmem), st>>>(a);
+  k_chol_dataflow<<<grid, CH_THREADS, sizeof(ChSmem), st>>>(a);
   if (g_mid_event) cudaEventRecord(g_mid_event, st);
   k_backsolve_chain<<<Tc, 256, sizeof(BsSmem), st>>>(S, Tm, n, Tc, Winv, x, xll, ctrl);
   (*launches) += 2;
