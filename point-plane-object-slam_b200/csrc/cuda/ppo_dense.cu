@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <vector>
 
 #include "ppo_dense.h"
 
@@ -34,7 +35,10 @@ constexpr int CLD = DENSE_CLD;      // padded column length of a tile (doubles):
 constexpr int TILE = DENSE_TILE;    // doubles per tile
 constexpr unsigned TILE_BYTES = TILE * 8;
 constexpr int SB = 16;              // sub-block of the diagonal-tile factorisation
-constexpr long long CHOL_TIMEOUT = 1ll << 32;  // cycles (~2 s)
+#ifndef PPO_CHOL_TIMEOUT_SHIFT
+#define PPO_CHOL_TIMEOUT_SHIFT 32
+#endif
+constexpr long long CHOL_TIMEOUT = 1ll << PPO_CHOL_TIMEOUT_SHIFT;  // cycles (~2 s)
 
 #ifdef PPO_CHOL_TIMING
 __device__ long long g_chol_t[16];
@@ -113,6 +117,29 @@ __device__ __forceinline__ bool flag_wait(const int *flag, int want, CholCtrl *c
   const long long t0 = clock64();
   for (int it = 1;; it++) {
     if (ld_acquire(flag) >= want) return true;
+    if ((it & 63) == 0) {
+      if (*(volatile int *)&ctrl->err) return false;
+      if (clock64() - t0 > CHOL_TIMEOUT) {
+        atomicExch(&ctrl->err, 1);
+        return false;
+      }
+    }
+    __nanosleep(20);
+  }
+}
+
+// system-scope variants: counters written by another GPU over NVLink (distributed factorisation below)
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ bool flag_wait_sys(const int *flag, int want, CholCtrl *ctrl) {
+  if (ld_acquire_sys(flag) >= want) return true;
+  const long long t0 = clock64();
+  for (int it = 1;; it++) {
+    if (ld_acquire_sys(flag) >= want) return true;
     if ((it & 63) == 0) {
       if (*(volatile int *)&ctrl->err) return false;
       if (clock64() - t0 > CHOL_TIMEOUT) {
@@ -738,7 +765,11 @@ struct BsSmem {
   unsigned long long mbar[2];
   int ok;
 };
-__global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int Tm, int n, int Tc, const double *Winv, double *x, unsigned long long *xll, CholCtrl *ctrl) {
+// DIST: the factor was assembled from tiles pushed by the other ranks (k_chol_dist); every tile is read only after its version
+// counter `ver` shows the final value base + column + 1.
+template <bool DIST>
+__global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int Tm, int n, int Tc, const double *Winv, double *x, unsigned long long *xll, CholCtrl *ctrl,
+                                                         const int *ver, int base, int *not_spd) {
   extern __shared__ __align__(16) unsigned char dsm[];
   BsSmem &sm = *reinterpret_cast<BsSmem *>(dsm);
   __shared__ int s_b, s_base;
@@ -757,9 +788,23 @@ __global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int Tm
   if (b >= 0) {
     unsigned ph[2] = {0, 0};
     int buf = 0;
+    auto tile_final = [&](int i, int j) {  // (thread 0) tile (i, j) of the factor has arrived
+      if (DIST) {
+        flag_wait_sys(&ver[i * Tm + j], base + j + 1, ctrl);
+        fence_proxy_async();
+      }
+    };
     if (Tc - 1 > b && tid == 0) {  // first tile of the sweep: (Tc-1, b)
+      tile_final(Tc - 1, b);
       mbar_expect_tx(&sm.mbar[0], TILE_BYTES);
       bulk_g2s(sm.L[0], tile(Tc - 1, b), TILE_BYTES, &sm.mbar[0]);
+    }
+    if (DIST) {  // W_b and the carried gradient tile
+      if (tid == 0) {
+        flag_wait_sys(&ver[b * Tm + b], base + b + 1, ctrl);
+        flag_wait_sys(&ver[Tc * Tm + b], base + b + 1, ctrl);
+      }
+      __syncthreads();
     }
     {
       const double *W = Winv + (size_t)b * TILE;
@@ -781,6 +826,7 @@ __global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int Tm
     if (tid == 0) sm.ok = 1;
     for (int c = Tc - 1; c > b; c--) {
       if (tid == 0 && c - 1 > b) {  // prefetch the next tile into the other buffer (its last readers are behind the barrier that ended the previous round)
+        tile_final(c - 1, b);
         mbar_expect_tx(&sm.mbar[buf ^ 1], TILE_BYTES);
         bulk_g2s(sm.L[buf ^ 1], tile(c - 1, b), TILE_BYTES, &sm.mbar[buf ^ 1]);
       }
@@ -854,11 +900,378 @@ __global__ void __launch_bounds__(256) k_backsolve_chain(const double *S, int Tm
   if (tid == 0) {
     __threadfence();
     if (atomicAdd(&ctrl->bdone, 1) == (int)gridDim.x - 1) {
+      if (*(volatile int *)&ctrl->err) {  // a wait of this solve timed out: the solve counts as failed; the next one starts clean
+        *not_spd = 1;
+        ctrl->err = 0;
+      }
       ctrl->bticket = 0;
       ctrl->bdone = 0;
       ctrl->bepoch = ctrl->bepoch + 1;
       __threadfence();
     }
+  }
+}
+
+// ---- one window on several GPUs: distributed factorisation over NVLink peer memory ----------------------------------------
+// Tile column j of the reduced system belongs to rank j mod world (1-D block-cyclic).  Every rank holds a full-size copy of S in
+// peer-mapped memory (cudaIpc); only the owner's copy of a column is ever updated, the other copies receive the FINAL tiles.
+//   k_dist_signal / k_dist_reduce   the partial Schur complements of the ranks (each rank summed its own landmarks into its own
+//                                   S) are pulled over NVLink and added up by the owner of each column, in rank order
+//                                   (a reduce-scatter whose chunks are the block-cyclic columns; no staging, no NCCL);
+//   k_chol_dist                     the same dataflow factorisation as k_chol_dataflow, every rank executing the operations that
+//                                   write ITS columns: F_k, T_k(i) on owner(k); U_k(i, j) on owner(j).  The finished panel tiles
+//                                   P_ik = T_k(i) and W_k are staged in shared memory and PUSHED to all ranks by TMA bulk stores
+//                                   (cp.async.bulk shared -> peer global), followed by a system-scope release of the tile's
+//                                   version counter on every rank: consumers poll their LOCAL counter and fetch the tile from
+//                                   their LOCAL copy.  The critical path F_k -> T_k(k+1) -> [NVLink] -> U_k(k+1,k+1) -> F_k+1
+//                                   hops from rank to rank; the next owner is served first.
+//   k_backsolve_chain<true>         every rank ends up with the whole factor and runs the backward substitution redundantly
+//                                   (0.2 ms at n = 7794); it waits for the version counter of every tile it reads, which also
+//                                   guarantees that no push into this rank's memory is still in flight when the solve returns.
+__device__ __forceinline__ double2 ld_peer_v2(const double2 *p) {  // never from L1: the peer rewrites the location every solve
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct CholDistArgs {
+  CholArgs a;           // this rank's pointers
+  DistPeers p;
+  const unsigned *ops;  // this rank's worker queue: type << 24 | k << 16 | i << 8 | j, level-major (topological) order
+  int n_ops;
+  int base;             // version-counter tag of this solve (the same on every rank)
+};
+
+// communication thread: the tile staged at `src` goes to offset `off` of every rank's copy (rank `first` is served first and
+// sees its counter before the others are waited for), then counter `flag` of every rank is released with `value`
+__device__ __forceinline__ void dist_push_publish(const DistPeers &p, double *const *bases, size_t off, const void *src, int flag, int value, int first) {
+  if (first >= 0) {
+    bulk_s2g(bases[first] + off, src, TILE_BYTES);
+    bulk_commit();
+  }
+  for (int q = 0; q < p.world; q++)
+    if (q != first) bulk_s2g(bases[q] + off, src, TILE_BYTES);
+  bulk_commit();
+  if (first >= 0) {
+    bulk_wait<1>();
+    fence_proxy_async();
+    __threadfence_system();
+    st_release_sys(p.ver[first] + flag, value);
+  }
+  bulk_wait<0>();
+  fence_proxy_async();
+  __threadfence_system();
+  for (int q = 0; q < p.world; q++)
+    if (q != first) st_release_sys(p.ver[q] + flag, value);
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  ChSmem &sm = *reinterpret_cast<ChSmem *>(dsm);
+  __shared__ int s_role;
+  const CholArgs &a = d.a;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *S = a.S;
+  const int Tm = a.Tm, Tc = a.Tc, vs = a.Tm, base = d.base;
+  const int R = d.p.rank, Wd = d.p.world;
+  CholCtrl *ctrl = a.ctrl;
+  if (tid == 0) {
+    s_role = atomicAdd(&ctrl->ticket, 1);
+    mbar_init(&sm.full[0], 1);
+    mbar_init(&sm.full[1], 1);
+    mbar_init(&sm.done[0], 8);
+    mbar_init(&sm.done[1], 8);
+    mbar_init(&sm.done[2], 8);
+    sm.abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int role = s_role;
+  const bool comm = warp == 8;
+  const int il = warp_row_block() * 8 + (lane >> 2);
+  const int jc = 2 * (lane & 3);
+  auto tile_off = [&](int i, int j) { return dense_tile_index(Tm, i, j) * (size_t)TILE; };
+  auto tile = [&](int i, int j) { return S + tile_off(i, j); };
+  auto warp_arrive = [&](unsigned long long *bar) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  };
+  if (role == 0) {
+    // =============================== critical path of my columns k = R, R + world, .. ================================
+    TilePtr D = sm.T[0], W = sm.T[1], A = sm.T[2], C = sm.T[3], Pp = sm.T[4];
+    if (comm) {
+      if (lane == 0) {
+        unsigned pd0 = 0, pd1 = 0;
+        bool ok = true;
+        for (int k = R; k < Tc; k += Wd) {
+          // operands of U_{k-1}(k,k): P_{k,k-1} (pushed by the owner of column k-1) and my tile (k,k) after the updates U_0 .. U_{k-2}
+          if (k > 0) {
+            ok = flag_wait_sys(&a.ver[k * vs + k - 1], base + k, ctrl);
+            if (ok && k >= 2) ok = flag_wait_sys(&a.ver[k * vs + k], base + k - 1, ctrl);
+          }
+          if (ok) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.full[0], (k > 0 ? 2 : 1) * TILE_BYTES);
+            if (k > 0) bulk_g2s(Pp, tile(k, k - 1), TILE_BYTES, &sm.full[0]);
+            bulk_g2s(C, tile(k, k), TILE_BYTES, &sm.full[0]);
+            // operand of T_k(k+1): my tile (k+1,k) after U_0 .. U_{k-1}
+            if (k > 0) ok = flag_wait_sys(&a.ver[(k + 1) * vs + k], base + k, ctrl);
+          }
+          if (ok) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.full[1], TILE_BYTES);
+            bulk_g2s(A, tile(k + 1, k), TILE_BYTES, &sm.full[1]);
+          }
+          ok = ok && mbar_wait_bounded(&sm.done[0], pd0, ctrl);
+          pd0 ^= 1;
+          if (ok) dist_push_publish(d.p, d.p.Winv, (size_t)k * TILE, W, k * vs + k, base + k + 1, -1);
+          ok = ok && mbar_wait_bounded(&sm.done[1], pd1, ctrl);
+          pd1 ^= 1;
+          if (ok) dist_push_publish(d.p, d.p.S, tile_off(k + 1, k), A, (k + 1) * vs + k, base + k + 1, (k + 1) % Wd);
+          if (!ok) {  // timed out (here or elsewhere): release the compute warps from whichever wait they sit in
+            atomicExch(&ctrl->err, 1);
+            sm.abort = 1;
+            mbar_arrive(&sm.full[0]);
+            mbar_arrive(&sm.full[1]);
+            break;
+          }
+        }
+      }
+    } else {
+      unsigned pf0 = 0, pf1 = 0;
+      for (int k = R; k < Tc; k += Wd) {
+        mbar_wait(&sm.full[0], pf0);
+        pf0 ^= 1;
+        if (*(volatile int *)&sm.abort) break;
+        for (int e = tid; e < TILE; e += 256) (&W[0][0])[e] = 0.0;
+        {  // D = C - P P^T (last update of the diagonal tile), symmetric, identity beyond the valid size
+          const int nb = min(NB, a.n - NB * k);
+          double acc[8][2];
+#pragma unroll
+          for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
+          if (k > 0) tile_mma64<1>(Pp, Pp, acc);
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int jl = q * 8 + jc + h;
+              if (il >= jl) {
+                const double v = (il < nb && jl < nb) ? C[jl][il] - acc[q][h] : (il == jl ? 1.0 : 0.0);
+                D[jl][il] = v;
+                D[il][jl] = v;
+              }
+            }
+        }
+        cbar();
+        diag_factor(D, W, sm.fs, a.not_spd);  // ends with a barrier of the compute warps
+        fence_proxy_async_smem();             // W is read by the TMA stores of the communication thread
+        warp_arrive(&sm.done[0]);
+        mbar_wait(&sm.full[1], pf1);
+        pf1 ^= 1;
+        if (*(volatile int *)&sm.abort) break;
+        {  // T_k(k+1) in place: a warp reads and writes only its own 8 rows of A
+          double acc[8][2];
+#pragma unroll
+          for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
+          const bool grad_tile = (k + 1 == Tc);
+          if (!grad_tile || warp == 0) {
+            tile_mma64<2>(A, W, acc);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+#pragma unroll
+              for (int h = 0; h < 2; h++) A[q * 8 + jc + h][il] = acc[q][h];
+          }
+        }
+        fence_proxy_async_smem();
+        warp_arrive(&sm.done[1]);
+      }
+    }
+  } else if (comm) {
+    // =============================== workers, communication thread ===============================================
+    if (lane == 0) {
+      auto claim = [&](int slot) -> bool {
+        const int idx = atomicAdd(&ctrl->qhead, 1);
+        if (idx >= d.n_ops) {
+          sm.op[slot][0] = -1;
+          return false;
+        }
+        const unsigned o = d.ops[idx];
+        sm.op[slot][0] = (int)(o >> 24), sm.op[slot][1] = (int)((o >> 16) & 255), sm.op[slot][2] = (int)((o >> 8) & 255), sm.op[slot][3] = (int)(o & 255);
+        return true;
+      };
+      auto ready = [&](int i, int j, int want) { return ld_acquire_sys(&a.ver[i * vs + j]) >= want; };
+      auto deps_ready = [&](int slot) -> bool {
+        const int type = sm.op[slot][0], k = sm.op[slot][1], i = sm.op[slot][2], j = sm.op[slot][3];
+        if (type == 0) return ready(k, k, base + k + 1) && (k == 0 || ready(i, k, base + k));
+        return ready(i, k, base + k + 1) && (j == i || ready(j, k, base + k + 1)) && (k == 0 || ready(i, j, base + k));
+      };
+      auto issue = [&](int slot) {
+        const int type = sm.op[slot][0], k = sm.op[slot][1], i = sm.op[slot][2], j = sm.op[slot][3];
+        fence_proxy_async();
+        if (type == 0) {
+          mbar_expect_tx(&sm.full[slot], 2 * TILE_BYTES);
+          bulk_g2s(sm.T[3 * slot], tile(i, k), TILE_BYTES, &sm.full[slot]);
+          bulk_g2s(sm.T[3 * slot + 1], a.Winv + (size_t)k * TILE, TILE_BYTES, &sm.full[slot]);
+        } else {
+          const bool diag = i == j;
+          mbar_expect_tx(&sm.full[slot], (diag ? 2 : 3) * TILE_BYTES);
+          bulk_g2s(sm.T[3 * slot], tile(i, k), TILE_BYTES, &sm.full[slot]);
+          if (!diag) bulk_g2s(sm.T[3 * slot + 1], tile(j, k), TILE_BYTES, &sm.full[slot]);
+          bulk_g2s(sm.T[3 * slot + 2], tile(i, j), TILE_BYTES, &sm.full[slot]);
+        }
+      };
+      int head = 0, tail = 0, inflight = 0;
+      bool claimed = false, exhausted = false;
+      unsigned pd[2] = {0, 0};
+      int rel_t[2] = {0, 0}, rel_i[2] = {0, 0}, rel_j[2] = {0, 0}, rel_v[2] = {0, 0};
+      long long t_idle = clock64();
+      for (;;) {
+        bool progress = false;
+        if (inflight > 0 && mbar_test(&sm.done[tail], pd[tail])) {
+          pd[tail] ^= 1;
+          if (rel_t[tail] == 0) {  // a panel tile: staged in the first buffer of the set -> every rank
+            dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail], -1);
+          } else {                 // a trailing update of one of my tiles: stays here
+            __threadfence();
+            st_release(&a.ver[rel_i[tail] * vs + rel_j[tail]], rel_v[tail]);
+          }
+          tail ^= 1;
+          inflight--;
+          progress = true;
+        }
+        if (!claimed && !exhausted && inflight < 2) {
+          if (claim(head)) claimed = true;
+          else exhausted = true;
+          progress = true;
+        }
+        if (claimed && deps_ready(head)) {
+          rel_t[head] = sm.op[head][0], rel_i[head] = sm.op[head][2], rel_j[head] = sm.op[head][3], rel_v[head] = base + sm.op[head][1] + 1;
+          issue(head);
+          head ^= 1;
+          inflight++;
+          claimed = false;
+          progress = true;
+        }
+        if (exhausted && inflight == 0) {
+          mbar_arrive(&sm.full[head]);
+          break;
+        }
+        if (progress) {
+          t_idle = clock64();
+        } else {
+          __nanosleep(20);
+          if (*(volatile int *)&ctrl->err || clock64() - t_idle > CHOL_TIMEOUT) {
+            atomicExch(&ctrl->err, 1);
+            sm.abort = 1;
+            sm.op[head][0] = -1, sm.op[head ^ 1][0] = -1;
+            mbar_arrive(&sm.full[0]);
+            mbar_arrive(&sm.full[1]);
+            break;
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== workers, compute warps ======================================================
+    unsigned pf[2] = {0, 0};
+    for (int cur = 0;; cur ^= 1) {
+      mbar_wait(&sm.full[cur], pf[cur]);
+      pf[cur] ^= 1;
+      const int type = sm.op[cur][0], i = sm.op[cur][2], j = sm.op[cur][3];
+      if (type < 0 || *(volatile int *)&sm.abort) break;
+      TilePtr A = sm.T[3 * cur], B = sm.T[3 * cur + 1], C = sm.T[3 * cur + 2];
+      const bool one_row = (i == Tc);
+      if (!one_row || warp == 0) {
+        double acc[8][2];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
+        if (type == 0) {  // result staged in place of A (a warp touches only its own rows), pushed by the communication thread
+          tile_mma64<2>(A, B, acc);
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) A[q * 8 + jc + h][il] = acc[q][h];
+        } else {
+          double *dst = tile(i, j);
+          const bool diag = (i == j);
+          if (diag) tile_mma64<1>(A, A, acc);
+          else tile_mma64<0>(A, B, acc);
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int jl = q * 8 + jc + h;
+              if (!diag || il >= jl) dst[jl * CLD + il] = C[jl][il] - acc[q][h];
+            }
+        }
+      }
+      if (type == 0) fence_proxy_async_smem();
+      warp_arrive(&sm.done[cur]);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&ctrl->done, 1) == (int)gridDim.x - 1) {
+      if (*(volatile int *)&ctrl->err) *a.not_spd = 1;
+      ctrl->ticket = 0;
+      ctrl->qhead = 0;
+      ctrl->done = 0;
+      ctrl->epoch = ctrl->epoch + 1;
+      __threadfence();
+    }
+  }
+}
+
+// "my partial Schur complement is complete": one system-scope release per peer (the kernel boundary before this launch ordered
+// the accumulation kernels' writes)
+__global__ void k_dist_signal(DistPeers p, int value) {
+  if (threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.sig[threadIdx.x] + p.rank, value);
+  }
+}
+// owner-side sum of the partial systems: tile columns j = rank, rank + world, .. (tile rows j .. Tc), 16 bytes per lane and peer
+__global__ void __launch_bounds__(256) k_dist_reduce(DistPeers p, int Tm, int Tc, int value, CholCtrl *ctrl) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < p.world) {
+    if (!flag_wait_sys(p.sig[p.rank] + threadIdx.x, value, ctrl)) s_ok = 0;
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  // flatten my columns into one index space of double2 elements, block-cyclic over the CTAs
+  size_t total = 0;
+  for (int j = p.rank; j < Tc; j += p.world) total += (size_t)(Tc - j + 1) * (TILE / 2);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  int j = p.rank;
+  size_t col_start = 0, col_len = j < Tc ? (size_t)(Tc - j + 1) * (TILE / 2) : 0;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    while (e >= col_start + col_len) {
+      col_start += col_len;
+      j += p.world;
+      col_len = (size_t)(Tc - j + 1) * (TILE / 2);
+    }
+    const size_t off = dense_tile_index(Tm, j, j) * (size_t)(TILE / 2) + (e - col_start);
+    double2 v[DIST_MAX];
+#pragma unroll
+    for (int q = 0; q < DIST_MAX; q++)
+      if (q < p.world) v[q] = ld_peer_v2(reinterpret_cast<const double2 *>(p.S[q]) + off);
+    double2 s = v[0];
+#pragma unroll
+    for (int q = 1; q < DIST_MAX; q++)
+      if (q < p.world) s.x += v[q].x, s.y += v[q].y;
+    reinterpret_cast<double2 *>(p.S[p.rank])[off] = s;
   }
 }
 
@@ -892,7 +1305,9 @@ static int sm_count(int dev) {
 void dense_setup_device(int dev) {  // per-device function attributes (> 48 KB of dynamic shared memory); called from ppo_ba_create
   (void)dev;
   cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem));
-  cudaFuncSetAttribute(k_backsolve_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BsSmem));
+  cudaFuncSetAttribute(k_backsolve_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BsSmem));
+  cudaFuncSetAttribute(k_backsolve_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BsSmem));
+  cudaFuncSetAttribute(k_chol_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem));
 }
 
 static cudaEvent_t g_mid_event = nullptr;  // test hook: recorded between the factorisation and the back-substitution
@@ -917,7 +1332,54 @@ void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, 
   a.S = S, a.Tm = Tm, a.n = n, a.Tc = Tc, a.Winv = Winv, a.ver = ver, a.ctrl = ctrl, a.not_spd = not_spd;
   k_chol_dataflow<<<grid, CH_THREADS, sizeof(ChSmem), st>>>(a);
   if (g_mid_event) cudaEventRecord(g_mid_event, st);
-  k_backsolve_chain<<<Tc, 256, sizeof(BsSmem), st>>>(S, Tm, n, Tc, Winv, x, xll, ctrl);
+  k_backsolve_chain<false><<<Tc, 256, sizeof(BsSmem), st>>>(S, Tm, n, Tc, Winv, x, xll, ctrl, nullptr, 0, not_spd);
+  (*launches) += 2;
+}
+
+// ---- distributed variant ------------------------------------------------------------------------------------------------------
+// worker queue of one rank, level by level: T_k(i) for i = k+2 .. Tc when the rank owns column k, then U_k(i, j) for its columns
+// j > k (the diagonal update U_k(k+1,k+1) and T_k(k+1) belong to the critical-path CTA of the owner)
+void dense_dist_build_ops(int Tc, int rank, int world, std::vector<unsigned> *ops) {
+  ops->clear();
+  auto pack = [](int type, int k, int i, int j) { return (unsigned)type << 24 | (unsigned)k << 16 | (unsigned)i << 8 | (unsigned)j; };
+  for (int k = 0; k < Tc; k++) {
+    if (k % world == rank)
+      for (int i = k + 2; i <= Tc; i++) ops->push_back(pack(0, k, i, k));
+    for (int j = k + 1; j < Tc; j++) {
+      if (j % world != rank) continue;
+      for (int i = (j == k + 1 ? j + 1 : j); i <= Tc; i++) ops->push_back(pack(1, k, i, j));
+    }
+  }
+}
+void dense_dist_reduce(const DistPeers &p, int n, int max_n, void *ws, int seq, cudaStream_t st, long long *launches, int sm_cap) {
+  if (n <= 0) return;
+  const int Tm = dense_num_blocks(max_n), Tc = dense_num_blocks(n);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int cap = sm_cap > 0 ? sm_cap : sm_count(dev);
+  k_dist_signal<<<1, 32, 0, st>>>(p, seq);
+  // (sm_cap > 0: several ranks share one device in the protocol test -- one CTA per SM at most, so that the other ranks' kernels
+  // find idle SMs while this one waits for their signals)
+  k_dist_reduce<<<sm_cap > 0 ? cap : cap * 4, 256, 0, st>>>(p, Tm, Tc, seq, reinterpret_cast<CholCtrl *>(ws));
+  (*launches) += 2;
+}
+void dense_cholesky_solve_dist(const DistPeers &p, int n, int max_n, double *x, void *ws, int *not_spd, const unsigned *d_ops, int n_ops, int seq,
+                               cudaStream_t st, long long *launches, int sm_cap) {
+  if (n <= 0) return;
+  const int Tm = dense_num_blocks(max_n), Tc = dense_num_blocks(n);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  CholCtrl *ctrl = reinterpret_cast<CholCtrl *>(ws);
+  int *ver = reinterpret_cast<int *>(reinterpret_cast<char *>(ws) + 256);
+  unsigned long long *xll = reinterpret_cast<unsigned long long *>(ver + (((size_t)(Tm + 1) * Tm + 1) & ~(size_t)1));
+  const long long cap = sm_cap > 0 ? sm_cap : sm_count(dev);
+  const int grid = (int)(1 + ((long long)n_ops < cap - 1 ? (long long)n_ops : cap - 1));
+  CholDistArgs d;
+  d.a.S = p.S[p.rank], d.a.Tm = Tm, d.a.n = n, d.a.Tc = Tc, d.a.Winv = p.Winv[p.rank], d.a.ver = ver, d.a.ctrl = ctrl, d.a.not_spd = not_spd;
+  d.p = p, d.ops = d_ops, d.n_ops = n_ops, d.base = (seq & 0x3fffff) * 256;
+  k_chol_dist<<<grid, CH_THREADS, sizeof(ChSmem), st>>>(d);
+  if (g_mid_event) cudaEventRecord(g_mid_event, st);
+  k_backsolve_chain<true><<<Tc, 256, sizeof(BsSmem), st>>>(p.S[p.rank], Tm, n, Tc, p.Winv[p.rank], x, xll, ctrl, ver, d.base, not_spd);
   (*launches) += 2;
 }
 
