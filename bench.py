@@ -263,6 +263,13 @@ def strong_scaling_config4(ppo, torch, dist, rank, world, local_rank, comm):
     vals = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     ms = float(vals[0])
+    # per-phase CUDA events of one more call (rank 0's view; the phases end at collectives, so the ranks agree to within a trial)
+    eng.reset()
+    eng.set_profiling(True)
+    pr = eng.local_ba()
+    eng.set_profiling(False)
+    phases = {k: getattr(pr.round1, k) + getattr(pr.round2, k) for k in ("ms_linearize", "ms_schur", "ms_solve", "ms_update", "ms_total")}
+    dist_solve = os.environ.get("PPO_DIST_SOLVE", "1") != "0" and world <= 8
     eng.close()
     out = None
     err = torch.zeros(1, dtype=torch.float64, device="cuda")
@@ -302,8 +309,13 @@ def strong_scaling_config4(ppo, torch, dist, rank, world, local_rank, comm):
                "lm_it_per_s": rate, "ms_per_call": ms, "lm_iterations": iters, "n1_lm_it_per_s": single[0], "n1_ms_per_call": single[1],
                "speedup_vs_n1": rate / single[0], "efficiency": rate / single[0] / world, "shard_parity_max_err": float(err[0]),
                "same_iterations_as_n1": iters == single[3], "collectives_per_call": colls, "damped_trials": trials,
-               "allreduce_bytes_per_trial": s_bytes, "n_pose_dim": n_p,
-               "collective": "ncclAllReduce(sum, f64) of the packed lower triangle of Hschur + reduced gradient per damped trial; every rank factorises the identical system"}
+               "n_pose_dim": n_p, "phases_ms_per_call": phases,
+               "reduced_system_bytes": s_bytes,
+               "collective": ("distributed dense solve over NVLink peer memory (cudaIpc): tile column j of Hschur belongs to rank j mod N; per damped trial every owner "
+                              "pulls and sums the other ranks' partial columns (k_dist_reduce, %.0f MB read per rank), the dataflow Cholesky pushes each finished panel tile "
+                              "to all ranks with TMA bulk stores + system-scope version counters (k_chol_dist, %.0f MB written per rank), back-substitution replicated; "
+                              "NCCL only for the Hpp blocks and three scalars per trial" % (s_bytes * (world - 1) / world / 1e6, s_bytes * (world - 1) / world / 1e6))
+                             if dist_solve else "ncclAllReduce(sum, f64) of the packed lower triangle of Hschur + reduced gradient per damped trial; every rank factorises the identical system"}
     return out
 
 

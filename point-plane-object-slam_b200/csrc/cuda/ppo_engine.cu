@@ -45,6 +45,7 @@ typedef enum { ncclInt32_ = 2, ncclFloat64_ = 8 } ncclDataType_t_;
 struct ncclUniqueId_ { char internal[128]; };
 struct NcclApi {
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GetUniqueId)(ncclUniqueId_ *) = nullptr;
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
@@ -56,6 +57,7 @@ struct NcclApi {
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) return;
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
@@ -134,6 +136,25 @@ struct ppo_ba_handle {
   int rank = 0, world = 1;
   double *d_red = nullptr;  // 4 doubles for scalar allreduce
   long long collectives = 0;
+  // distributed dense solve of a sharded window (ppo_dense.h): S | Winv | workspace live in ONE cudaMalloc'd arena that every
+  // rank of the node maps through cudaIpc; the factorisation is spread over the ranks by tile column
+  bool dist_solve = false;
+  void *dist_arena = nullptr;
+  size_t dist_arena_bytes = 0;
+  void *dist_peer_base[DIST_MAX] = {};  // (other ranks: cudaIpcOpenMemHandle)
+  DistPeers dist_peers;
+  int dist_seq = 0;                     // solves so far (identical on every rank)
+  unsigned *d_dist_ops = nullptr;       // this rank's worker queue for dist_ops_tc tile columns
+  int dist_n_ops = 0, dist_ops_tc = -1;
+  void dist_release() {
+    for (int q = 0; q < DIST_MAX; q++) {
+      if (dist_peer_base[q] && q != rank) cudaIpcCloseMemHandle(dist_peer_base[q]);
+      dist_peer_base[q] = nullptr;
+    }
+    if (dist_arena) cudaFree(dist_arena);
+    if (d_dist_ops) cudaFree(d_dist_ops);
+    dist_arena = nullptr, d_dist_ops = nullptr, dist_arena_bytes = 0, dist_ops_tc = -1;
+  }
 
   template <typename T>
   int dalloc(T **p, size_t n) {
@@ -301,6 +322,7 @@ void ppo_ba_destroy(ppo_ba_handle *h) {
   cudaStreamSynchronize(h->st);
   h->free_graph();
   cudaStreamSynchronize(h->st);
+  h->dist_release();
   if (h->hstage) cudaFreeHost(h->hstage);
   cudaFreeHost(h->h_scal);
   cudaFreeHost(h->h_dims);
@@ -389,6 +411,65 @@ static double cpe_chi_const(const ppo_ba_handle *h) {
     s += c;
   }
   return s;
+}
+
+// ---- peer-mapped arena of the distributed dense solve (collective: every rank of the sharded window calls set_graph) ----------
+static int dist_setup(ppo_ba_handle *h) {
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t sS = al(dense_matrix_doubles(h->max_np) * 8), sW = al((size_t)dense_num_blocks(h->max_np) * DENSE_TILE * 8), sWs = al(dense_workspace_bytes(h->max_np));
+  const size_t bytes = sS + sW + sWs;
+  if (!g_nccl.AllGather) {
+    h->err = "ncclAllGather not found in libnccl";
+    return PPO_E_NCCL;
+  }
+  if (bytes != h->dist_arena_bytes) {  // (same decision on every rank: key-frames and cuboids are replicated, so max_np agrees)
+    CK(cudaStreamSynchronize(h->st));
+    h->dist_release();
+    CK(cudaMalloc(&h->dist_arena, bytes));
+    h->dist_arena_bytes = bytes;
+    // exchange {cudaIpc handle, arena size} over the window's NCCL communicator
+    struct Slot {
+      cudaIpcMemHandle_t hd;
+      unsigned long long bytes;
+      unsigned long long pad;
+    };
+    static_assert(sizeof(Slot) == 80, "slot layout");
+    std::vector<Slot> slots((size_t)h->world);
+    std::memset(slots.data(), 0, sizeof(Slot) * slots.size());
+    CK(cudaIpcGetMemHandle(&slots[h->rank].hd, h->dist_arena));
+    slots[h->rank].bytes = bytes;
+    Slot *d_slots = nullptr;
+    CK(cudaMalloc((void **)&d_slots, sizeof(Slot) * slots.size()));
+    CK(cudaMemcpyAsync(d_slots, slots.data(), sizeof(Slot) * slots.size(), cudaMemcpyHostToDevice, h->st));
+    const int r = g_nccl.AllGather(d_slots + h->rank, d_slots, sizeof(Slot), /*ncclInt8*/ 0, h->comm, h->st);
+    if (r != 0) {
+      h->err = std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+      cudaFree(d_slots);
+      return PPO_E_NCCL;
+    }
+    h->collectives++;
+    CK(cudaMemcpyAsync(slots.data(), d_slots, sizeof(Slot) * slots.size(), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    cudaFree(d_slots);
+    h->dist_peers.rank = h->rank, h->dist_peers.world = h->world;
+    for (int q = 0; q < h->world; q++) {
+      if (slots[q].bytes != bytes) {
+        h->err = "sharded window: the ranks disagree on the size of the reduced system";
+        return PPO_E_INVALID;
+      }
+      void *base = h->dist_arena;
+      if (q != h->rank) CK(cudaIpcOpenMemHandle(&base, slots[q].hd, cudaIpcMemLazyEnablePeerAccess));
+      h->dist_peer_base[q] = base;
+      char *b = reinterpret_cast<char *>(base);
+      dense_dist_set_peer(&h->dist_peers, q, reinterpret_cast<double *>(b), reinterpret_cast<double *>(b + sS), b + sS + sW);
+    }
+    dense_workspace_init(reinterpret_cast<char *>(h->dist_arena) + sS + sW, h->max_np, h->st);
+  }
+  char *b = reinterpret_cast<char *>(h->dist_arena);
+  h->g.S = reinterpret_cast<double *>(b);
+  h->d_Winv = reinterpret_cast<double *>(b + sS);
+  h->d_dense_ws = b + sS + sW;
+  return PPO_OK;
 }
 
 int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
@@ -719,7 +800,13 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   h->ld = dense_num_blocks(h->max_np);  // Tm: tile columns of the (tiled, packed lower) reduced system, see ppo_dense.h
   DA(g.Hpp_kf, 36 * (size_t)g.n_kf); DA(g.Hpp_cu, 81 * (size_t)g.n_cu); DA(g.Hpc, 54 * (size_t)g.n_cbe); DA(g.bp, (size_t)h->max_np);
   DA(g.Hll, 6 * (size_t)g.n_lm); DA(g.bl, 3 * (size_t)g.n_lm); DA(g.Hpl, 18 * (size_t)g.n_ent); DA(g.BD, 18 * (size_t)g.n_ent); DA(g.Zent, 3 * (size_t)g.n_ent); DA(g.Dinv, 6 * (size_t)g.n_lm);
-  DA(g.xl, 3 * (size_t)g.n_lm); DA(g.S, dense_matrix_doubles(h->max_np)); DA(g.xp, dense_x_doubles(h->max_np));
+  DA(g.xl, 3 * (size_t)g.n_lm); DA(g.xp, dense_x_doubles(h->max_np));
+  h->dist_solve = h->world > 1 && h->world <= DIST_MAX && !(std::getenv("PPO_DIST_SOLVE") && std::atoi(std::getenv("PPO_DIST_SOLVE")) == 0);
+  if (h->dist_solve) {  // S | Winv | workspace in the peer-mapped arena
+    if ((rc = dist_setup(h))) return rc;
+  } else {
+    DA(g.S, dense_matrix_doubles(h->max_np));
+  }
   {  // linearisation: a grid-stride loop over the work units, sized to fill the device once
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -730,8 +817,8 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   h->nb_bs = cdiv(g.n_pl, BS_WARPS) + g.n_units;  // partial sums of k_backsub (planes) + k_backsub_points
   DA(h->d_chi_pt, (size_t)std::max(h->nb_lin, h->nb_res)); DA(h->d_chi_pl, (size_t)h->nb_pl); DA(h->d_chi_cb, (size_t)h->nb_cb); DA(h->d_chi_pc, (size_t)h->nb_pc);
   DA(h->d_scale_part, (size_t)h->nb_bs);
-  DA(h->d_Winv, (size_t)dense_num_blocks(h->max_np) * DENSE_TILE);
-  {
+  if (!h->dist_solve) {
+    DA(h->d_Winv, (size_t)dense_num_blocks(h->max_np) * DENSE_TILE);
     char *ws = nullptr;
     DA(ws, dense_workspace_bytes(h->max_np));
     h->d_dense_ws = ws;
@@ -989,12 +1076,40 @@ static int schur_system(ppo_ba_handle *h) {
   const int n_comp = g.n_kf * 36 + g.n_cu * 81 + g.n_cbe * 54 + n_p;
   if (n_comp && own) { k_compose<<<cdiv(n_comp, 256), 256, 0, st>>>(g, h->d_lm, n_p, ld, grow); h->launches++; }
   // single large window sharded over ranks: sum the partial reduced systems (Hschur | bschur) over NVLink
-  if (h->world > 1) return allreduce(h, g.S, s_used, ncclFloat64_, ncclSum_);  // packed lower triangle + gradient row only
+  if (h->world > 1) {
+    if (h->dist_solve) {  // every column is summed by its owner straight from the other ranks' memory (ppo_dense.cu: k_dist_reduce)
+      dense_dist_reduce(h->dist_peers, n_p, h->max_np, h->d_dense_ws, ++h->dist_seq, st, &h->launches);
+      return PPO_OK;
+    }
+    return allreduce(h, g.S, s_used, ncclFloat64_, ncclSum_);  // packed lower triangle + gradient row only
+  }
+  return PPO_OK;
+}
+// factorisation + both substitutions of the reduced system in g.S (single GPU, or spread over the ranks of a sharded window)
+static int enqueue_dense_solve(ppo_ba_handle *h) {
+  DevGraph &g = h->g;
+  if (h->dist_solve) {
+    const int Tc = dense_num_blocks(h->n_p);
+    if (Tc != h->dist_ops_tc) {  // this rank's operation queue for the current number of tile columns
+      std::vector<unsigned> ops;
+      dense_dist_build_ops(Tc, h->rank, h->world, &ops);
+      CK(cudaStreamSynchronize(h->st));
+      if (h->d_dist_ops) cudaFree(h->d_dist_ops);
+      h->d_dist_ops = nullptr;
+      CK(cudaMalloc((void **)&h->d_dist_ops, std::max<size_t>(4, ops.size() * sizeof(unsigned))));
+      if (!ops.empty()) CK(cudaMemcpy(h->d_dist_ops, ops.data(), ops.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+      h->dist_n_ops = (int)ops.size(), h->dist_ops_tc = Tc;
+    }
+    dense_cholesky_solve_dist(h->dist_peers, h->n_p, h->max_np, g.xp, h->d_dense_ws, h->d_not_spd, h->d_dist_ops, h->dist_n_ops, h->dist_seq, h->st, &h->launches);
+  } else {
+    dense_cholesky_solve(g.S, h->n_p, h->max_np, g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches);
+  }
   return PPO_OK;
 }
 static int solve_and_backsub(ppo_ba_handle *h) {
   DevGraph &g = h->g;
-  dense_cholesky_solve(g.S, h->n_p, h->max_np, g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches);
+  int rc_solve = enqueue_dense_solve(h);
+  if (rc_solve) return rc_solve;
   // planes: one warp per landmark; points: one lane per 6x3 block (work units of the linearisation); partial sums of the
   // LM scale go to disjoint ranges of d_scale_part
   const int nbp = cdiv(g.n_pl, BS_WARPS);
@@ -1032,9 +1147,9 @@ static int enqueue_trial(ppo_ba_handle *h) {
                               (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, h->d_lm, own ? 1 : 0, h->d_scale_part,
                               g.n_lm ? h->nb_bs : 0, own ? h->n_p : 0, h->d_not_spd, h->d_red);
   h->launches++;
-  if (h->world > 1) {
-    if ((rc = allreduce(h, h->d_red, 2, ncclFloat64_, ncclSum_))) return rc;
-    k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 0);
+  if (h->world > 1) {  // {chi2, scale, "some rank met a non-positive pivot"}
+    if ((rc = allreduce(h, h->d_red, 3, ncclFloat64_, ncclSum_))) return rc;
+    k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 2);
   }
   if (h->profiling) cudaEventRecord(h->evp[5], st);
   return PPO_OK;
@@ -1460,7 +1575,7 @@ int ppo_ba_time_solve(ppo_ba_handle *h, int reps, double *ms_mean, double *flops
   for (int i = 0; i < reps + 2; i++) {
     if ((rc = schur_system(h))) return rc;
     CK(cudaEventRecord(h->ev0, h->st));
-    dense_cholesky_solve(h->g.S, h->n_p, h->max_np, h->g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches);
+    if ((rc = enqueue_dense_solve(h))) return rc;
     CK(cudaEventRecord(h->ev1, h->st));
     CK(cudaEventSynchronize(h->ev1));
     float ms;

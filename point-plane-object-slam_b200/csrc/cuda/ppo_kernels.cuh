@@ -1422,6 +1422,7 @@ __global__ void __launch_bounds__(SCAL_THREADS) k_scalars(DevGraph g, Scalars *o
     if (red) {
       red[0] = out->chi2;
       red[1] = out->scale;
+      red[2] = (double)out->not_spd;
     }
   }
 }
@@ -1450,9 +1451,10 @@ __global__ void __launch_bounds__(256) k_max_diag(DevGraph g, Scalars *out) {
 // after the cross-rank reductions: copy the reduced scalars back into the Scalars block
 __global__ void k_scalars_from_red(Scalars *out, const double *red, int which) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    if (which == 0) {
+    if (which == 0 || which == 2) {
       out->chi2 = red[0];
       out->scale = red[1];
+      if (which == 2) out->not_spd = red[2] != 0.0;  // distributed factorisation: the pivots live on their owners
     } else {
       out->max_diag = red[2];
     }
