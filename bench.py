@@ -226,11 +226,13 @@ def _protect_stdout():
     return os.fdopen(saved, "w")
 
 
-def state_max_err(a, b, sl=None):
+def state_max_err(a, b, sl=None, pl=None):
     import numpy as np
     m = 0.0
     for name in ("kf_pose", "pl_coef", "cu_state"):
         x, y = getattr(a, name), getattr(b, name)
+        if name == "pl_coef" and pl is not None:
+            y = y[pl[0]:pl[1]]
         if x.size:
             m = max(m, float(np.max(np.abs(x - y) / np.maximum(np.abs(y), 1.0))))
     x, y = a.pt_xyz, (b.pt_xyz if sl is None else b.pt_xyz[sl[0]:sl[1]])
@@ -287,7 +289,7 @@ def strong_scaling_config4(ppo, torch, dist, rank, world, local_rank, comm):
         e1.close()
         it1 = r1.round1.iterations + r1.round2.iterations
         single = (it1 / (ms1 * 1e-3), ms1, s1, it1)
-        err[0] = state_max_err(st, s1, (p0, p1))
+        err[0] = state_max_err(st, s1, (p0, p1), ppo.sharding.plane_range(g_full, rank, world))
     # parity of the other ranks' point slices: rank 0 broadcasts its single-GPU points
     import numpy as np
     n_pt = g_full.c.n_pt
@@ -305,7 +307,7 @@ def strong_scaling_config4(ppo, torch, dist, rank, world, local_rank, comm):
         tiles = (n_p + 63) // 64
         s_bytes = 8 * (tiles * (tiles + 3) // 2) * 64 * 68
         rate = iters / (ms * 1e-3)
-        out = {"workload": workload_name(4), "partition": "points sharded contiguously over the ranks (balanced edge counts); key-frames, cuboids, planes replicated",
+        out = {"workload": workload_name(4), "partition": "landmarks partitioned over the ranks: points by edge count, planes by Schur pair count (with their edges); key-frames, cuboids and their edges replicated, owned by rank 0",
                "lm_it_per_s": rate, "ms_per_call": ms, "lm_iterations": iters, "n1_lm_it_per_s": single[0], "n1_ms_per_call": single[1],
                "speedup_vs_n1": rate / single[0], "efficiency": rate / single[0] / world, "shard_parity_max_err": float(err[0]),
                "same_iterations_as_n1": iters == single[3], "collectives_per_call": colls, "damped_trials": trials,

@@ -225,7 +225,9 @@ struct ppo_ba_handle {
     allocs.clear();
     have_graph = false;
   }
-  bool owner() const { return rank == 0; }  // accumulates the non-point ("shared") edges in sharded mode
+  // sharded window: landmarks (points, planes, their edges and the cuboid-plane edges of those planes) are rank-local; key-frames and
+  // cuboids are replicated and the edges among them (camera-cuboid, point-cuboid) are accumulated by rank 0
+  bool owner() const { return rank == 0; }
 };
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -904,11 +906,9 @@ static int init_mapping(ppo_ba_handle *h) {
     k_mark_active_cpe<<<cdiv(g.n_cpe, 256), 256, 0, st>>>(g, h->d_cpe_cuboid, h->d_cpe_plane, h->d_cpe_flags);
     h->launches++;
   }
-  if (h->world > 1) {  // a key-frame / cuboid / plane is active if ANY rank holds an active edge on it
+  if (h->world > 1) {  // a key-frame / cuboid is active if ANY rank holds an active edge on it (landmarks -- points, planes -- are rank-local)
     int rc;
-    if ((rc = allreduce(h, g.kf_act, g.n_kf, ncclInt32_, ncclMax_)) || (rc = allreduce(h, g.cu_act, g.n_cu, ncclInt32_, ncclMax_)) ||
-        (rc = allreduce(h, g.pl_act, g.n_pl, ncclInt32_, ncclMax_)))
-      return rc;
+    if ((rc = allreduce(h, g.kf_act, g.n_kf, ncclInt32_, ncclMax_)) || (rc = allreduce(h, g.cu_act, g.n_cu, ncclInt32_, ncclMax_))) return rc;
   }
   k_build_index<<<1, 32, 0, st>>>(g);
   h->launches++;
@@ -960,13 +960,6 @@ static int linearize(ppo_ba_handle *h, bool only_points_kernel = false) {
     k_pose_accumulate<<<g.n_chunks, POSE_THREADS, 0, st>>>(g, s, h->d_chunk_part);
     h->launches++;
   }
-  if (h->world > 1 && g.n_chunks) {  // pose side of the point edges of all shards (every rank has the same chunk layout? no: chunks are per shard, so the
-    // partials are first reduced per key-frame into a compact array, summed across ranks and fed back as a single chunk per key-frame)
-    int rc;
-    k_chunk_reduce<<<cdiv(g.n_kf * 27, 128), 128, 0, st>>>(g.n_kf, h->d_kf_chunk_ptr, h->d_chunk_part, h->d_kf_part);
-    h->launches++;
-    if ((rc = allreduce(h, h->d_kf_part, 27 * (size_t)g.n_kf, ncclFloat64_, ncclSum_))) return rc;
-  }
   if (g.n_ple) {
     k_plane_jac<<<cdiv(g.n_ple * 9, 128), 128, 0, s_pl>>>(g, s);
     k_plane_edges<true><<<h->nb_pl, SMALL_THREADS, 0, s_pl>>>(g, s, h->d_chi_pl);
@@ -990,14 +983,23 @@ static int linearize(ppo_ba_handle *h, bool only_points_kernel = false) {
     }
   {  // fixed-order assembly of the key-frame / cuboid / plane blocks from the per-edge records
     const int n = g.n_kf * 27 + g.n_cu * 54 + g.n_pl * 9 + g.n_slots * 18;
-    if (h->world > 1) k_combine<<<cdiv(n, 128), 128, 0, st>>>(g, h->d_kf_iota_ptr, h->d_kf_part);
-    else k_combine<<<cdiv(n, 128), 128, 0, st>>>(g, h->d_kf_chunk_ptr, h->d_chunk_part);
+    if (h->world > 1) {
+      // sharded window: the pose side of this rank's landmark edges (points: chunk partials, planes: edge records) is first summed per
+      // key-frame into a compact array, added up across the ranks and fed back as ONE chunk per key-frame
+      int rc;
+      k_chunk_reduce<<<cdiv(g.n_kf * 27, 128), 128, 0, st>>>(g, h->d_kf_chunk_ptr, h->d_chunk_part, h->d_kf_part);
+      h->launches++;
+      if ((rc = allreduce(h, h->d_kf_part, 27 * (size_t)g.n_kf, ncclFloat64_, ncclSum_))) return rc;
+      k_combine<<<cdiv(n, 128), 128, 0, st>>>(g, h->d_kf_iota_ptr, h->d_kf_part, 0);
+    } else {
+      k_combine<<<cdiv(n, 128), 128, 0, st>>>(g, h->d_kf_chunk_ptr, h->d_chunk_part, 1);
+    }
     h->launches++;
   }
   if (h->profiling) cudaEventRecord(h->evp[1], st);
   const bool own = h->owner();  // replicated (non-point) edges count once: on rank 0
-  k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
-                              (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, h->d_lm, own ? 1 : 0, nullptr, 0, 0, nullptr,
+  k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_units ? h->nb_lin : 0, h->d_chi_pl, g.n_ple ? h->nb_pl : 0, h->d_chi_cb,
+                              (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, h->d_lm, 1, nullptr, 0, 0, nullptr,
                               h->d_red);
   h->launches++;
   CK(cudaMemsetAsync(&h->d_scal->max_diag, 0, sizeof(double), st));
@@ -1064,7 +1066,7 @@ static int schur_system(ppo_ba_handle *h) {
   CK(cudaMemsetAsync(g.S, 0, 8 * s_used, st));
   CK(cudaMemsetAsync(h->d_not_spd, 0, sizeof(int), st));
   const int own = h->owner() ? 1 : 0;
-  if (g.n_pl) { k_schur_bd<<<cdiv(g.n_pl, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, h->d_lm, n_p, ld, own, g.n_pl); h->launches++; }
+  if (g.n_pl) { k_schur_bd<<<cdiv(g.n_pl, BD_WARPS), BD_WARPS * 32, 0, st>>>(g, h->d_lm, n_p, ld, 1, g.n_pl); h->launches++; }
   if (g.n_units) { k_schur_bd_points<<<g.n_units, 32, 0, st>>>(g, h->d_lm); h->launches++; }
   if (h->n_pairs) {
     const int n_warps = cdiv(h->n_pairs, PAIR_CHUNK);
@@ -1119,7 +1121,7 @@ static int solve_and_backsub(ppo_ba_handle *h) {
     CK(cudaEventRecord(h->ev_fork, h->st));
     CK(cudaStreamWaitEvent(s_pl, h->ev_fork, 0));
   }
-  if (g.n_pl) { k_backsub<<<nbp, BS_WARPS * 32, 0, s_pl>>>(g, h->d_lm, h->d_scale_part, h->owner() ? 1 : 0, g.n_pl); h->launches++; }
+  if (g.n_pl) { k_backsub<<<nbp, BS_WARPS * 32, 0, s_pl>>>(g, h->d_lm, h->d_scale_part, 1, g.n_pl); h->launches++; }
   if (g.n_units) { k_backsub_points<<<g.n_units, 32, 0, h->st>>>(g, h->d_lm, h->d_scale_part + nbp); h->launches++; }
   if (fork) {
     CK(cudaEventRecord(h->ev_join[0], s_pl));
@@ -1143,8 +1145,8 @@ static int enqueue_trial(ppo_ba_handle *h) {
   h->launches++;
   residual_kernels(h, h->sb);
   const bool own = h->owner();
-  k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_pe ? h->nb_res : 0, h->d_chi_pl, (own && g.n_ple) ? h->nb_pl : 0, h->d_chi_cb,
-                              (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, h->d_lm, own ? 1 : 0, h->d_scale_part,
+  k_scalars<<<1, SCAL_THREADS, 0, st>>>(g, h->d_scal, h->d_chi_pt, g.n_pe ? h->nb_res : 0, h->d_chi_pl, g.n_ple ? h->nb_pl : 0, h->d_chi_cb,
+                              (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, h->d_lm, 1, h->d_scale_part,
                               g.n_lm ? h->nb_bs : 0, own ? h->n_p : 0, h->d_not_spd, h->d_red);
   h->launches++;
   if (h->world > 1) {  // {chi2, scale, "some rank met a non-positive pivot"}

@@ -464,12 +464,17 @@ __global__ void __launch_bounds__(POSE_THREADS) k_pose_accumulate(DevGraph g, De
   }
 }
 // per-key-frame sums of the chunk partials (sharded windows: summed across ranks before k_combine)
-__global__ void k_chunk_reduce(int n_kf, const int *kf_chunk_ptr, const double *chunk_part, double *kf_part) {
+// plus the records of this rank's plane edges: pose side of ALL landmark edges of the rank
+__global__ void k_chunk_reduce(DevGraph g, const int *kf_chunk_ptr, const double *chunk_part, double *kf_part) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_kf * 27) return;
+  if (t >= g.n_kf * 27) return;
   const int kf = t / 27, i = t % 27;
   double sum = 0;
   for (int c = kf_chunk_ptr[kf]; c < kf_chunk_ptr[kf + 1]; c++) sum += chunk_part[27 * (size_t)c + i];
+  for (int q = g.kf_ple_ptr[kf]; q < g.kf_ple_ptr[kf + 1]; q++) {
+    const int e = g.kf_ple_idx[q];
+    if (!(g.ple_flags[e] & PPO_EF_LEVEL1_)) sum += g.ple_part[54 * (size_t)e + i];
+  }
   kf_part[t] = sum;
 }
 // Fixed-order assembly of everything that is not a point landmark: one thread per scalar of
@@ -478,7 +483,8 @@ __global__ void k_chunk_reduce(int n_kf, const int *kf_chunk_ptr, const double *
 //   a plane landmark    ( 9: Hll + bl)               = its plane edges
 //   a (plane, KF) slot  (18: Hpl block)              = its plane edges
 // summed in list order and written with plain stores: no atomics, bit-reproducible, and no clearing of the targets beforehand.
-__global__ void k_combine(DevGraph g, const int *kf_chunk_ptr, const double *chunk_part) {
+// with_ple = 0 (sharded window): the plane-edge records of the key-frame blocks are already inside the chunk partials (k_chunk_reduce).
+__global__ void k_combine(DevGraph g, const int *kf_chunk_ptr, const double *chunk_part, int with_ple) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < g.n_kf * 27) {
     const int kf = t / 27, i = t % 27;
@@ -486,7 +492,7 @@ __global__ void k_combine(DevGraph g, const int *kf_chunk_ptr, const double *chu
     if (idx < 0) return;
     double sum = 0;
     for (int c = kf_chunk_ptr[kf]; c < kf_chunk_ptr[kf + 1]; c++) sum += chunk_part[27 * (size_t)c + i];
-    for (int q = g.kf_ple_ptr[kf]; q < g.kf_ple_ptr[kf + 1]; q++) {
+    for (int q = g.kf_ple_ptr[kf]; with_ple && q < g.kf_ple_ptr[kf + 1]; q++) {
       const int e = g.kf_ple_idx[q];
       if (!(g.ple_flags[e] & PPO_EF_LEVEL1_)) sum += g.ple_part[54 * (size_t)e + i];
     }

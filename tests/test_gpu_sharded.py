@@ -1,5 +1,5 @@
-"""Single large window with its points sharded over 2 GPUs (NCCL all-reduce of the reduced system)
-must reproduce the single-GPU solve.  Needs >= 2 GPUs (skipped otherwise)."""
+"""Single large window with its landmarks (points and planes) partitioned over 2 GPUs and its reduced system factorised by both
+(ppo_dense.cu: distributed solve over peer memory) must reproduce the single-GPU solve.  Needs >= 2 GPUs (skipped otherwise)."""
 import os
 import sys
 
@@ -22,7 +22,8 @@ def _worker(rank, world, uid, q, cfg_kw):
     eng.set_graph(gs)
     res = eng.local_ba()
     st = eng.get_state()
-    out = dict(rank=rank, p0=p0, p1=p1, kf=st.kf_pose, pt=st.pt_xyz, pl=st.pl_coef, cu=st.cu_state, chi=res.round2.chi2_final,
+    q0, q1 = ppo.sharding.plane_range(g, rank, world)
+    out = dict(rank=rank, p0=p0, p1=p1, q0=q0, q1=q1, kf=st.kf_pose, pt=st.pt_xyz, pl=st.pl_coef, cu=st.cu_state, chi=res.round2.chi2_final,
                it=(res.round1.iterations, res.round2.iterations), coll=eng.collective_count(), n_out=res.n_outlier_point_edges)
     if rank == 0:
         ref = ppo.LocalBA(device=0)
@@ -61,5 +62,5 @@ def test_sharded_window_matches_single_gpu():
     for o in outs:
         assert np.isclose(o["chi"], ref["chi"], rtol=1e-6)
         assert np.abs(o["kf"] - ref["kf"]).max() < 1e-6 and np.abs(o["cu"] - ref["cu"]).max() < 1e-5
-        assert np.abs(o["pl"] - ref["pl"]).max() < 1e-6
+        assert np.abs(o["pl"] - ref["pl"][o["q0"]:o["q1"]]).max() < 1e-6
         assert np.abs(o["pt"] - ref["pt"][o["p0"]:o["p1"]]).max() < 1e-5

@@ -1,6 +1,6 @@
 """world_size-2 gloo tests (CPU) of the host-side multi-GPU logic:
  * window -> rank dealing for independent windows,
- * landmark sharding of one window: the reduced system is additive over point shards, i.e.
+ * landmark sharding of one window: the reduced system is additive over landmark (point and plane) shards, i.e.
    all_reduce(sum) of the per-rank [Hschur | bschur | chi2] (replicated edges counted on rank 0 only)
    equals the unsharded system — the identity the NCCL path of the engine relies on.
 The per-rank linear algebra is done by the CPU oracle (tests-only); the collective is torch.distributed/gloo."""
@@ -32,13 +32,13 @@ def _worker(rank, world, port, out):
     full = o.debug_linearize()
     lam = 1e-5 * max(np.abs(np.diag(full["Hpp"])).max(), np.abs(full["Hll"][:, [0, 4, 8]]).max())
     full_s = o.debug_solve(lam, full["n_p"], full["n_l"])
-    # this rank's shard: its points + replicas of everything else; replicated edges are owned by rank 0
+    # this rank's shard: its points and planes (with their edges) + replicas of the key-frames, cuboids and their edges, which rank 0 owns
     gs, (p0, p1), _ = ppo.sharding.shard_graph(g, rank, world)
     if rank != 0:
         # keep the replicated edges (so every vertex stays active, as the engine's activity all-reduce guarantees)
         # but with zero information: their contribution is owned by rank 0
         a = {k: v.copy() for k, v in gs.a.items()}
-        for k in ("ple_info", "cbe_info", "cpe_info"):
+        for k in ("cbe_info",):
             a[k][...] = 0.0
         for k in ("pce_cuboid", "pce_rowptr", "pce_pts"):
             a.pop(k, None)
