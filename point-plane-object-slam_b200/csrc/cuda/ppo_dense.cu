@@ -949,27 +949,30 @@ struct CholDistArgs {
   int base;             // version-counter tag of this solve (the same on every rank)
 };
 
-// communication thread: the tile staged at `src` goes to offset `off` of every rank's copy (rank `first` is served first and
-// sees its counter before the others are waited for), then counter `flag` of every rank is released with `value`
-__device__ __forceinline__ void dist_push_publish(const DistPeers &p, double *const *bases, size_t off, const void *src, int flag, int value, int first) {
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_sys(int *p, int v) { asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// communication thread: the tile staged at `src` goes to offset `off` of the copies of ranks q with (mask >> q) & 1 (rank `first`, if any,
+// is served first and sees its counter before the other copies are waited for), then counter `flag` of those ranks is released with
+// `value`: completion of the bulk stores (wait_group) -> proxy fence -> ONE system-scope release fence -> relaxed counter stores.
+__device__ __forceinline__ void dist_push_publish(const DistPeers &p, double *const *bases, size_t off, const void *src, int flag, int value, int first, unsigned mask) {
   if (first >= 0) {
     bulk_s2g(bases[first] + off, src, TILE_BYTES);
     bulk_commit();
   }
   for (int q = 0; q < p.world; q++)
-    if (q != first) bulk_s2g(bases[q] + off, src, TILE_BYTES);
+    if (q != first && ((mask >> q) & 1)) bulk_s2g(bases[q] + off, src, TILE_BYTES);
   bulk_commit();
   if (first >= 0) {
     bulk_wait<1>();
     fence_proxy_async();
-    __threadfence_system();
-    st_release_sys(p.ver[first] + flag, value);
+    fence_acq_rel_sys();
+    st_relaxed_sys(p.ver[first] + flag, value);
   }
   bulk_wait<0>();
   fence_proxy_async();
-  __threadfence_system();
+  fence_acq_rel_sys();
   for (int q = 0; q < p.world; q++)
-    if (q != first) st_release_sys(p.ver[q] + flag, value);
+    if (q != first && ((mask >> q) & 1)) st_relaxed_sys(p.ver[q] + flag, value);
 }
 
 __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
@@ -981,6 +984,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
   double *S = a.S;
   const int Tm = a.Tm, Tc = a.Tc, vs = a.Tm, base = d.base;
   const int R = d.p.rank, Wd = d.p.world;
+  const unsigned all_ranks = (1u << Wd) - 1;
   CholCtrl *ctrl = a.ctrl;
   if (tid == 0) {
     s_role = atomicAdd(&ctrl->ticket, 1);
@@ -1029,12 +1033,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
             mbar_expect_tx(&sm.full[1], TILE_BYTES);
             bulk_g2s(A, tile(k + 1, k), TILE_BYTES, &sm.full[1]);
           }
+          // W_k: to my own copy at once (my workers' panel operations wait for it); the other ranks only need it for the backward
+          // substitution, so their copies go out after the panel tile P_{k+1,k}, which the next owner's critical path waits for
           ok = ok && mbar_wait_bounded(&sm.done[0], pd0, ctrl);
           pd0 ^= 1;
-          if (ok) dist_push_publish(d.p, d.p.Winv, (size_t)k * TILE, W, k * vs + k, base + k + 1, -1);
+          if (ok) dist_push_publish(d.p, d.p.Winv, (size_t)k * TILE, W, k * vs + k, base + k + 1, -1, 1u << R);
           ok = ok && mbar_wait_bounded(&sm.done[1], pd1, ctrl);
           pd1 ^= 1;
-          if (ok) dist_push_publish(d.p, d.p.S, tile_off(k + 1, k), A, (k + 1) * vs + k, base + k + 1, (k + 1) % Wd);
+          if (ok) {
+            dist_push_publish(d.p, d.p.S, tile_off(k + 1, k), A, (k + 1) * vs + k, base + k + 1, (k + 1) % Wd, all_ranks);
+            dist_push_publish(d.p, d.p.Winv, (size_t)k * TILE, W, k * vs + k, base + k + 1, -1, all_ranks & ~(1u << R));
+          }
           if (!ok) {  // timed out (here or elsewhere): release the compute warps from whichever wait they sit in
             atomicExch(&ctrl->err, 1);
             sm.abort = 1;
@@ -1138,7 +1147,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
         if (inflight > 0 && mbar_test(&sm.done[tail], pd[tail])) {
           pd[tail] ^= 1;
           if (rel_t[tail] == 0) {  // a panel tile: staged in the first buffer of the set -> every rank
-            dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail], -1);
+            dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail], -1, all_ranks);
           } else {                 // a trailing update of one of my tiles: stays here
             __threadfence();
             st_release(&a.ver[rel_i[tail] * vs + rel_j[tail]], rel_v[tail]);
