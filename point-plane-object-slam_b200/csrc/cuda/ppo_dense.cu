@@ -955,19 +955,22 @@ __device__ __forceinline__ void st_relaxed_sys(int *p, int v) { asm volatile("st
 // is served first and sees its counter before the other copies are waited for), then counter `flag` of those ranks is released with
 // `value`: completion of the bulk stores (wait_group) -> proxy fence -> ONE system-scope release fence -> relaxed counter stores.
 __device__ __forceinline__ void dist_push_publish(const DistPeers &p, double *const *bases, size_t off, const void *src, int flag, int value, int first, unsigned mask) {
-  if (first >= 0) {
+  if (first >= 0) {  // alone on the wire until its counter is out: a system-scope fence drains every store this thread has in flight
     bulk_s2g(bases[first] + off, src, TILE_BYTES);
     bulk_commit();
-  }
-  for (int q = 0; q < p.world; q++)
-    if (q != first && ((mask >> q) & 1)) bulk_s2g(bases[q] + off, src, TILE_BYTES);
-  bulk_commit();
-  if (first >= 0) {
-    bulk_wait<1>();
+    bulk_wait<0>();
     fence_proxy_async();
     fence_acq_rel_sys();
     st_relaxed_sys(p.ver[first] + flag, value);
   }
+  const int q0 = first >= 0 ? first + 1 : 0;  // the other copies in the order in which their ranks own the next columns
+  bool any = false;
+  for (int t = 0; t < p.world; t++) {
+    const int q = (q0 + t) % p.world;
+    if (q != first && ((mask >> q) & 1)) bulk_s2g(bases[q] + off, src, TILE_BYTES), any = true;
+  }
+  if (!any) return;
+  bulk_commit();
   bulk_wait<0>();
   fence_proxy_async();
   fence_acq_rel_sys();
@@ -1147,7 +1150,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
         if (inflight > 0 && mbar_test(&sm.done[tail], pd[tail])) {
           pd[tail] ^= 1;
           if (rel_t[tail] == 0) {  // a panel tile: staged in the first buffer of the set -> every rank
-            dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail], -1, all_ranks);
+            // (all panel tiles of column k become ready together, right after W_k: the owner of column k+1, whose critical path needs
+            // the first of them next, gets its copies ahead of the rest of the burst)
+            dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail],
+                              (rel_v[tail] - base) % Wd, all_ranks);
           } else {                 // a trailing update of one of my tiles: stays here
             __threadfence();
             st_release(&a.ver[rel_i[tail] * vs + rel_j[tail]], rel_v[tail]);

@@ -968,7 +968,7 @@ static int linearize(ppo_ba_handle *h, bool only_points_kernel = false) {
   if (g.n_cbe) {
     k_cuboid_jac<<<cdiv(g.n_cbe * 15, 128), 128, 0, s_cb>>>(g, s);
     k_cuboid_edges<true><<<h->nb_cb, SMALL_THREADS, 0, s_cb>>>(g, s, h->d_chi_cb);
-    k_cuboid_assemble<<<cdiv(g.n_cbe * 15, 128), 128, 0, s_cb>>>(g);
+    k_cuboid_assemble<<<cdiv(g.n_cbe, CBA_EDGES), CBA_EDGES * 15, 0, s_cb>>>(g);
     h->launches += 3;
   }
   if (g.n_pce) {

@@ -754,26 +754,38 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_cuboid_edges(DevGraph g, DevS
 // entries + 6 gradient) and the cuboid block (45 + 9) go to the edge's own record (summed per vertex by k_combine), the 6 x 9
 // off-diagonal block to Hpc
 __device__ __forceinline__ int upper_index(int n, int a, int b) { return a * n - a * (a - 1) / 2 + (b - a); }  // b >= a
-__global__ void k_cuboid_assemble(DevGraph g) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = t / 15, a = t % 15;
-  if (e >= g.n_cbe || (g.cbe_flags[e] & PPO_EF_LEVEL1_)) return;
+constexpr int CBA_EDGES = 8;  // edges per CTA of k_cuboid_assemble (15 threads each)
+__global__ void __launch_bounds__(CBA_EDGES * 15) k_cuboid_assemble(DevGraph g) {
+  // the Jacobians (15 columns x 16 rows) and error vectors of the CTA's edges are contiguous in global memory: staged in shared memory
+  // with coalesced loads, row stride 17 so that the 15 threads of an edge (one column each) hit different banks
+  __shared__ double sJ[CBA_EDGES][15][17];
+  __shared__ double sE[CBA_EDGES][16];
+  const int e0 = blockIdx.x * CBA_EDGES;
+  const int ne = min(CBA_EDGES, g.n_cbe - e0);
+  for (int i = threadIdx.x; i < ne * 240; i += CBA_EDGES * 15) {
+    const int le = i / 240, r = i % 240;
+    sJ[le][r >> 4][r & 15] = g.cbe_J[240 * (size_t)e0 + i];
+  }
+  for (int i = threadIdx.x; i < ne * 16; i += CBA_EDGES * 15) sE[i >> 4][i & 15] = g.cbe_err[16 * (size_t)e0 + i];
+  __syncthreads();
+  const int le = threadIdx.x / 15, a = threadIdx.x % 15;
+  const int e = e0 + le;
+  if (le >= ne || (g.cbe_flags[e] & PPO_EF_LEVEL1_)) return;
   const double wi = g.cbe_w[e];
-  const double *J = g.cbe_J + 240 * (size_t)e;  // [col][row16], rows >= D are zero
   double *out = g.cbe_part + 81 * (size_t)e;
   double ja[16];
 #pragma unroll
-  for (int r = 0; r < 16; r++) ja[r] = J[16 * a + r];
+  for (int r = 0; r < 16; r++) ja[r] = sJ[le][a][r];
   double ga = 0;
 #pragma unroll
-  for (int r = 0; r < 16; r++) ga += ja[r] * g.cbe_err[16 * (size_t)e + r];
+  for (int r = 0; r < 16; r++) ga += ja[r] * sE[le][r];
   ga *= -wi;
   if (a < 6) out[21 + a] = ga;
   else out[27 + 45 + (a - 6)] = ga;
   for (int b = a; b < 15; b++) {
     double hv = 0;
 #pragma unroll
-    for (int r = 0; r < 16; r++) hv += ja[r] * J[16 * b + r];
+    for (int r = 0; r < 16; r++) hv += ja[r] * sJ[le][b][r];
     hv *= wi;
     if (a < 6 && b < 6) out[upper_index(6, a, b)] = hv;
     else if (a < 6) g.Hpc[54 * (size_t)e + 9 * a + (b - 6)] = hv;
