@@ -23,6 +23,7 @@
 // CTAs leave, and the solve counts as failed.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -1328,7 +1329,7 @@ void dense_setup_device(int dev) {  // per-device function attributes (> 48 KB o
 static cudaEvent_t g_mid_event = nullptr;  // test hook: recorded between the factorisation and the back-substitution
 void dense_debug_set_mid_event(cudaEvent_t e) { g_mid_event = e; }
 
-void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, void *ws, int *not_spd, cudaStream_t st, long long *launches) {
+void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, void *ws, int *not_spd, cudaStream_t st, long long *launches, int sm_cap) {
   if (n <= 0) return;
   const int Tm = dense_num_blocks(max_n), Tc = dense_num_blocks(n);
   int dev = 0;
@@ -1341,7 +1342,9 @@ void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, 
     const long long m = Tc - 1 - k;
     ops += m + (m >= 1 ? (m + 1) * (m + 2) / 2 - 2 : 0);
   }
-  const long long cap = sm_count(dev);  // one persistent CTA per SM (208 KB of staging buffers each)
+  // one persistent CTA per SM (208 KB of staging buffers each); sm_cap > 0: this window's share of the device when several windows are
+  // solved side by side (their dependency chains overlap instead of queueing for all SMs one after the other)
+  const long long cap = sm_cap > 0 ? std::min(sm_cap, sm_count(dev)) : sm_count(dev);
   const int grid = (int)(1 + (ops < cap - 1 ? ops : cap - 1));
   CholArgs a;
   a.S = S, a.Tm = Tm, a.n = n, a.Tc = Tc, a.Winv = Winv, a.ver = ver, a.ctrl = ctrl, a.not_spd = not_spd;

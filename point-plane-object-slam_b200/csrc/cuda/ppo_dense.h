@@ -20,7 +20,8 @@ __host__ __device__ inline size_t dense_elem_index(int Tm, int r, int c) {
   return dense_tile_index(Tm, r >> 6, c >> 6) * (size_t)DENSE_TILE + (size_t)(c & 63) * DENSE_CLD + (size_t)(r & 63);
 }
 // Winv: dense_num_blocks(max_n) * DENSE_TILE doubles; ws: dense_workspace_bytes(max_n), initialised once by dense_workspace_init.
-void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, void *ws, int *not_spd, cudaStream_t st, long long *launches);
+// sm_cap > 0 limits the persistent factorisation to that many CTAs (windows solved side by side share the SMs).
+void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, void *ws, int *not_spd, cudaStream_t st, long long *launches, int sm_cap = 0);
 int dense_num_blocks(int n);
 size_t dense_matrix_doubles(int max_n);
 size_t dense_x_doubles(int max_n);

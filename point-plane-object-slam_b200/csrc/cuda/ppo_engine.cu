@@ -123,13 +123,14 @@ struct ppo_ba_handle {
   int *d_stop = nullptr;   // device view of h_stop
   // captured LM loops (one per (n_p, n_l) of a window): nested conditional WHILE nodes over the iteration / trial bodies
   struct LmGraph {
-    int n_p, n_l;
+    int n_p, n_l, sm_cap;
     cudaGraphExec_t exec;
     cudaGraph_t graph;
     int nodes_iter, nodes_trial;
   };
   std::vector<LmGraph> lm_graphs;
   bool use_graph = true;
+  int solve_sm_cap = 0;  // > 0: CTAs of the persistent factorisation (batch entry points: the windows of a batch share the SMs)
   long long host_syncs = 0;
   // sharding (multi-GPU, single window)
   ncclComm_t comm = nullptr;
@@ -1104,7 +1105,7 @@ static int enqueue_dense_solve(ppo_ba_handle *h) {
     }
     dense_cholesky_solve_dist(h->dist_peers, h->n_p, h->max_np, g.xp, h->d_dense_ws, h->d_not_spd, h->d_dist_ops, h->dist_n_ops, h->dist_seq, h->st, &h->launches);
   } else {
-    dense_cholesky_solve(g.S, h->n_p, h->max_np, g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches);
+    dense_cholesky_solve(g.S, h->n_p, h->max_np, g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches, h->solve_sm_cap);
   }
   return PPO_OK;
 }
@@ -1251,10 +1252,10 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
   if (graph) {
     ppo_ba_handle::LmGraph *G = nullptr;
     for (auto &q : h->lm_graphs)
-      if (q.n_p == h->n_p && q.n_l == h->n_l) G = &q;
+      if (q.n_p == h->n_p && q.n_l == h->n_l && q.sm_cap == h->solve_sm_cap) G = &q;
     if (!G) {
       ppo_ba_handle::LmGraph q;
-      q.n_p = h->n_p, q.n_l = h->n_l;
+      q.n_p = h->n_p, q.n_l = h->n_l, q.sm_cap = h->solve_sm_cap;
       if ((rc = build_lm_graph(h, &q))) return rc;
       h->lm_graphs.push_back(q);
       G = &h->lm_graphs.back();
@@ -1328,13 +1329,37 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
 }
 
 // ---- batch variants (run_batch above): one host thread per window drives that window's LM loop on its own stream --------
+// The dense solve of one window is a dependency chain that cannot fill the device; a batch gives every window an equal share of the
+// SMs for its persistent factorisation, so that the chains of the windows on one device run side by side.
+static void batch_share_sms(ppo_ba_handle **h, int n) {
+  int per_dev[64] = {};
+  for (int i = 0; i < n; i++)
+    if (h[i] && h[i]->device >= 0 && h[i]->device < 64) per_dev[h[i]->device]++;
+  for (int i = 0; i < n; i++) {
+    if (!h[i]) continue;
+    const int k = (h[i]->device >= 0 && h[i]->device < 64) ? per_dev[h[i]->device] : 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h[i]->device);
+    // (not every window is in its solve at the same moment: PPO_BATCH_SM_OVERSUB lets the shares add up to more than the device)
+    static const double oversub = std::getenv("PPO_BATCH_SM_OVERSUB") ? std::atof(std::getenv("PPO_BATCH_SM_OVERSUB")) : 1.0;
+    h[i]->solve_sm_cap = k > 1 ? std::max(4, std::min(sms, (int)(oversub * sms / k))) : 0;
+  }
+}
 int ppo_ba_optimize_batch(ppo_ba_handle **h, int n, int iters, const volatile unsigned char *stop, ppo_ba_stats *stats) {
   if (!h || (n > 0 && !stats)) return PPO_E_INVALID;
-  return run_batch(n, [=](int i) { return ppo_ba_optimize(h[i], iters, stop, &stats[i]); });
+  batch_share_sms(h, n);
+  const int rc = run_batch(n, [=](int i) { return ppo_ba_optimize(h[i], iters, stop, &stats[i]); });
+  for (int i = 0; i < n; i++)
+    if (h[i]) h[i]->solve_sm_cap = 0;
+  return rc;
 }
 int ppo_ba_local_ba_batch(ppo_ba_handle **h, int n, const volatile unsigned char *stop, ppo_ba_result *res) {
   if (!h || (n > 0 && !res)) return PPO_E_INVALID;
-  return run_batch(n, [=](int i) { return ppo_ba_local_ba(h[i], stop, &res[i]); });
+  batch_share_sms(h, n);
+  const int rc = run_batch(n, [=](int i) { return ppo_ba_local_ba(h[i], stop, &res[i]); });
+  for (int i = 0; i < n; i++)
+    if (h[i]) h[i]->solve_sm_cap = 0;
+  return rc;
 }
 
 int ppo_ba_recompute_edge_errors(ppo_ba_handle *h, int kind) {
