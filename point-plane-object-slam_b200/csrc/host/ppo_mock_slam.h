@@ -61,9 +61,15 @@ class MapPoint {
   cv::Mat GetWorldPos() { return mWorldPos.clone(); }
   std::map<KeyFrame *, size_t> GetObservations() { return mObservations; }
   int Observations() { return nObs; }
-  void EraseObservation(KeyFrame *pKF) { erased.push_back(pKF); mObservations.erase(pKF); }
+  void AddObservation(KeyFrame *pKF, size_t idx) { mObservations[pKF] = idx; mnObsVersion++; }
+  void EraseObservation(KeyFrame *pKF) { erased.push_back(pKF); mObservations.erase(pKF); mnObsVersion++; }
   bool isBad() { return mbBad; }
   void UpdateNormalAndDepth() { n_updates++; }
+  // Observation version (INTEGRATION.md "observation mirror"): the ONE member the shim asks the reference to add -- incremented wherever
+  // MapPoint.cc changes mObservations (AddObservation :95-107, EraseObservation :109-139, SetBadFlag :151-167, Replace :176-213).  With it the
+  // shim keeps the flattened observation row of a map point across local-BA calls instead of copying its std::map every time.
+  long unsigned int mnObsVersion = 1;
+#define PPO_HAVE_OBS_VERSION 1
   std::map<MapCuboid *, int> MapObjObservations;
   long unsigned int mnId = 0;
   long unsigned int mnBALocalForKF = 0;

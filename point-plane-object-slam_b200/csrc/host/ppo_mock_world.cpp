@@ -32,13 +32,91 @@ static double g_last_call_ms = 0;
 extern "C" double ppo_mock_last_call_ms() { return g_last_call_ms; }
 extern "C" void ppo_mock_set_options(int bad_point_every, int bad_kf) { g_bad_point_every = bad_point_every, g_bad_kf = bad_kf; }
 
-extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int fixPoint, unsigned char *stop, ppo_ba_state *out,
-                            int32_t counts[4] /* erased point obs, erased plane obs, SetPose calls, UpdateNormalAndDepth calls */) {
+extern "C" void ppo_shim_mirror_clear();
+// A mock map that outlives one Optimizer:: call (ppo_mock_world_*): consecutive local-BA calls on the same map, as LocalMapping makes them.
+struct MockWorld {
   std::vector<std::unique_ptr<KeyFrame>> kfs;
   std::vector<std::unique_ptr<MapPoint>> pts, extra_pts;
   std::vector<std::unique_ptr<MapPlane>> pls;
   std::vector<std::unique_ptr<MapCuboid>> cus, local_cus;
   Map map;
+  int pkf = 0;
+  bool flags[5] = {false, false, false, false, false};
+  const ppo_ba_graph *g = nullptr;  // (counts only, after build)
+  int n_kf = 0, n_pt = 0, n_pl = 0, n_cu = 0;
+};
+static void world_build(MockWorld &W, const ppo_ba_graph *g);
+static int world_run(MockWorld &W, int mixed, int fixCamera, int fixPoint, unsigned char *stop);
+static void world_read(MockWorld &W, ppo_ba_state *out, int32_t counts[4]);
+
+extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int fixPoint, unsigned char *stop, ppo_ba_state *out,
+                            int32_t counts[4] /* erased point obs, erased plane obs, SetPose calls, UpdateNormalAndDepth calls */) {
+  MockWorld W;
+  world_build(W, g);
+  world_run(W, mixed, fixCamera, fixPoint, stop);
+  world_read(W, out, counts);
+  ppo_shim_mirror_clear();  // the map objects die with W
+  return 0;
+}
+extern "C" MockWorld *ppo_mock_world_create(const ppo_ba_graph *g) {
+  MockWorld *W = new MockWorld();
+  world_build(*W, g);
+  return W;
+}
+extern "C" int ppo_mock_world_run(MockWorld *W, int mixed, int fixCamera, int fixPoint, unsigned char *stop, ppo_ba_state *out, int32_t counts[4]) {
+  world_run(*W, mixed, fixCamera, fixPoint, stop);
+  if (out) world_read(*W, out, counts);
+  return 0;
+}
+// what Tracking / LocalMapping do to the map between two local-BA calls, reduced to the two operations the mirror must notice
+extern "C" int ppo_mock_world_erase_observation(MockWorld *W, int point, int kf) {
+  if (point < 0 || point >= W->n_pt || kf < 0 || kf >= W->n_kf) return -1;
+  MapPoint *mp = W->pts[point].get();
+  if (!mp->mObservations.count(W->kfs[kf].get())) return 0;
+  mp->EraseObservation(W->kfs[kf].get());
+  mp->erased.pop_back();  // (not an erasure made by the BA)
+  mp->nObs -= 1;
+  return 1;
+}
+extern "C" void ppo_mock_world_perturb_point(MockWorld *W, int point, float dx) {
+  if (point >= 0 && point < W->n_pt) W->pts[point]->mWorldPos.at<float>(0, 0) += dx;
+}
+// puts the estimates of the flat graph back into the map (poses, points, planes, cuboids); observations stay as they are
+extern "C" void ppo_mock_world_restore_estimates(MockWorld *W, const ppo_ba_graph *g) {
+  for (int i = 0; i < g->n_kf && i < W->n_kf; i++) {
+    float T[16];
+    ppo::pose7_to_tcw_float(&g->kf_pose[7 * i], T);
+    cv::Mat m(4, 4, CV_32F);
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) m.at<float>(r, c) = T[4 * r + c];
+    W->kfs[i]->Tcw = m;
+  }
+  for (int p = 0; p < g->n_pt && p < W->n_pt; p++)
+    for (int k = 0; k < 3; k++) W->pts[p]->mWorldPos.at<float>(k, 0) = (float)g->pt_xyz[3 * p + k];
+  for (int p = 0; p < g->n_pl && p < W->n_pl; p++)
+    for (int k = 0; k < 4; k++) W->pls[p]->mWorldPos.at<float>(k, 0) = (float)g->pl_coef[4 * p + k];
+  for (int c = 0; c < g->n_cu && c < W->n_cu; c++) {
+    const double *s = &g->cu_state[10 * c];
+    const double p7[7] = {s[3], s[4], s[5], s[6], s[0], s[1], s[2]};
+    std::memcpy(W->cus[c]->cuboid_global_data.pose7, p7, sizeof p7);
+    for (int k = 0; k < 3; k++) W->cus[c]->cuboid_global_data.scale[k] = s[7 + k];
+    W->cus[c]->obj_been_optimized = false;
+  }
+}
+extern "C" void ppo_mock_world_destroy(MockWorld *W) {
+  delete W;
+  ppo_shim_mirror_clear();
+}
+
+static void world_build(MockWorld &W, const ppo_ba_graph *g) {
+  ppo_shim_mirror_clear();  // a new map: nothing cached may refer to the objects of an earlier one
+  auto &kfs = W.kfs;
+  auto &pts = W.pts;
+  auto &extra_pts = W.extra_pts;
+  auto &pls = W.pls;
+  auto &cus = W.cus;
+  auto &local_cus = W.local_cus;
+  W.n_kf = g->n_kf, W.n_pt = g->n_pt, W.n_pl = g->n_pl, W.n_cu = g->n_cu;
   float inv_sigma2[8];
   {
     float sf = 1.0f;
@@ -167,20 +245,39 @@ extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int
     pl->asso_cuboid_id = g->cpe_cuboid[e];
     for (int k = 0; k < 3; k++) pl->asso_cuboid_meas(k) = g->cpe_meas[3 * e + k];
   }
-  optimize_with_plane_3d = g->n_ple > 0;
-  optimize_with_cuboid_2d = any_bbox;
-  optimize_with_corners_2d = any_corner;
-  optimize_with_pt_obj_3d = g->n_pce > 0;
-  optimize_with_cuboid_plane = g->n_cpe > 0;
+  W.pkf = pkf;
+  W.flags[0] = g->n_ple > 0, W.flags[1] = any_bbox, W.flags[2] = any_corner, W.flags[3] = g->n_pce > 0, W.flags[4] = g->n_cpe > 0;
+}
 
-  // ---- the call LocalMapping::Run makes ------------------------------------------------------------------------------------------
+// ---- the call LocalMapping::Run makes ------------------------------------------------------------------------------------------
+static int world_run(MockWorld &W, int mixed, int fixCamera, int fixPoint, unsigned char *stop) {
+  optimize_with_plane_3d = W.flags[0];
+  optimize_with_cuboid_2d = W.flags[1];
+  optimize_with_corners_2d = W.flags[2];
+  optimize_with_pt_obj_3d = W.flags[3];
+  optimize_with_cuboid_plane = W.flags[4];
+  // every real call has a new pKF->mnId, which invalidates the mnBALocalForKF / mnBAFixedForKF marks of the call before; the mock calls
+  // with the same key-frame again, so the marks are invalidated by hand
+  const unsigned long none = ~0ul;
+  for (auto &k : W.kfs) k->mnBALocalForKF = k->mnBAFixedForKF = none;
+  for (auto &q : W.pts) q->mnBALocalForKF = none;
+  for (auto &q : W.pls) q->mnBALocalForKF = none;
+  for (auto &q : W.cus) q->mnBALocalForKF = none;
   bool stop_flag = stop ? (*stop != 0) : false;
   const auto t_call = std::chrono::steady_clock::now();
-  if (mixed) Optimizer::LocalBACameraPlaneCuboids(kfs[pkf].get(), &stop_flag, &map, fixCamera != 0, fixPoint != 0);
-  else Optimizer::LocalBundleAdjustment(kfs[pkf].get(), &stop_flag, &map);
+  if (mixed) Optimizer::LocalBACameraPlaneCuboids(W.kfs[W.pkf].get(), &stop_flag, &W.map, fixCamera != 0, fixPoint != 0);
+  else Optimizer::LocalBundleAdjustment(W.kfs[W.pkf].get(), &stop_flag, &W.map);
   g_last_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+  return 0;
+}
 
-  // ---- read the map back ------------------------------------------------------------------------------------------------------------
+// ---- read the map back ------------------------------------------------------------------------------------------------------------
+static void world_read(MockWorld &W, ppo_ba_state *out, int32_t counts[4]) {
+  auto &kfs = W.kfs;
+  auto &pts = W.pts;
+  auto &pls = W.pls;
+  auto &cus = W.cus;
+  struct { int n_kf, n_pt, n_pl, n_cu; } gs{W.n_kf, W.n_pt, W.n_pl, W.n_cu}, *g = &gs;
   counts[0] = counts[1] = counts[2] = counts[3] = 0;
   for (int i = 0; i < g->n_kf; i++) {
     float T[16];
@@ -204,7 +301,6 @@ extern "C" int ppo_mock_run(const ppo_ba_graph *g, int mixed, int fixCamera, int
     s[3] = q.pose7[0]; s[4] = q.pose7[1]; s[5] = q.pose7[2]; s[6] = q.pose7[3];
     s[7] = q.scale[0]; s[8] = q.scale[1]; s[9] = q.scale[2];
   }
-  return 0;
 }
 
 // Global BA (Optimizer::GlobalBundleAdjustemnt, src/Optimizer.cc:46-241) on a mock map made of the key-frames and points

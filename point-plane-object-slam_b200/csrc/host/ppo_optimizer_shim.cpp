@@ -164,13 +164,81 @@ static ppo_ba_handle *engine(Slot &S, const ppo_ba_params &P) {
 
 using namespace ORB_SLAM2;
 
+// ---- observation mirror (second half) ------------------------------------------------------------------------------
+// The flattened observation row of a map point -- (key-frame, feature index, undistorted key-point, right coordinate, 1 / sigma^2 of its
+// octave), sorted by key-frame id -- only changes when MapPoint::mObservations changes; the key-point data of a key-frame never changes.
+// The mirror keeps the rows of all map points seen so far, keyed by mnId and validated by MapPoint::mnObsVersion (the counter the
+// reference increments next to every change of mObservations).  A local-BA call then reads the unchanged rows back
+// (one version compare + a contiguous copy per point) instead of copying 10^5 std::maps under their mutexes and chasing
+// mvKeysUn / mvuRight / mvInvLevelSigma2 per observation: consecutive windows share almost all of their points.
+struct ObsRec {
+  KeyFrame *kf;
+  uint32_t idx;
+  float u, v, ur, inv_sigma2;
+};
+struct Mirror {
+  struct Row {
+    MapPoint *mp = nullptr;
+    unsigned long version = 0;
+    uint32_t off = 0, n = 0;
+  };
+  std::vector<Row> rows;     // by MapPoint::mnId
+  std::vector<ObsRec> pool;  // rows are appended; stale rows are dropped when the pool is compacted
+  size_t live = 0;           // records referenced by current rows
+  long long hits = 0, misses = 0;
+  void clear() {
+    rows.clear();
+    pool.clear();
+    live = 0;
+  }
+  void compact() {  // (only between calls: a window holds offsets into the pool) stale rows exceed the live ones: copy the live rows into a fresh pool
+    if (pool.size() <= 2 * live + (1u << 20)) return;
+    std::vector<ObsRec> np;
+    np.reserve(live + live / 4);
+    for (Row &r : rows)
+      if (r.mp) {
+        const uint32_t off = (uint32_t)np.size();
+        np.insert(np.end(), pool.begin() + r.off, pool.begin() + r.off + r.n);
+        r.off = off;
+      }
+    pool.swap(np);
+  }
+  // current row of pMP (rebuilt from GetObservations() when the map point changed or is new)
+  const Row &row(MapPoint *pMP) {
+#ifdef PPO_HAVE_OBS_VERSION
+    const unsigned long ver = pMP->mnObsVersion;
+#else
+    const unsigned long ver = 0;  // no counter in this build of the reference: every call rebuilds every row
+#endif
+    const size_t id = pMP->mnId;
+    if (id >= rows.size()) rows.resize(std::max(id + 1, rows.size() * 2));
+    Row &r = rows[id];
+    if (ver != 0 && r.mp == pMP && r.version == ver) {
+      hits++;
+      return r;
+    }
+    misses++;
+    if (r.mp) live -= r.n;
+    const std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
+    r.mp = pMP, r.version = ver, r.off = (uint32_t)pool.size(), r.n = (uint32_t)observations.size();
+    for (auto &mit : observations) {
+      KeyFrame *pKFi = mit.first;
+      const size_t idx = mit.second;
+      const cv::KeyPoint &kpUn = pKFi->mvKeysUn[idx];
+      pool.push_back({pKFi, (uint32_t)idx, kpUn.pt.x, kpUn.pt.y, pKFi->mvuRight[idx] < 0 ? -1.0f : pKFi->mvuRight[idx], pKFi->mvInvLevelSigma2[kpUn.octave]});
+    }
+    // key-frame slots of a window are ordered by mnId, so rows sorted by mnId come out in edge order
+    std::sort(pool.begin() + r.off, pool.end(), [](const ObsRec &a, const ObsRec &b) { return a.kf->mnId < b.kf->mnId; });
+    live += r.n;
+    return r;
+  }
+};
+static Mirror g_mirror;  // guarded by the mutex of the local-BA slot (run() is its only user)
+
 struct Window {
   std::vector<KeyFrame *> lLocalKeyFrames, lFixedCameras;
   std::vector<MapPoint *> lLocalMapPoints;
-  // one GetObservations() snapshot per local map point (the getter copies a std::map under a mutex: 80 k copies are a
-  // third of the host time of a 200-key-frame window), shared by the fixed-camera search and the edge flattening
-  std::vector<int> obs_ptr;                              // CSR over lLocalMapPoints
-  std::vector<std::pair<KeyFrame *, size_t>> obs;        // (key-frame, feature index) in std::map (pointer) order
+  std::vector<std::pair<uint32_t, uint32_t>> obs_row;  // per local map point: (offset, count) of its row in the mirror's pool
   std::vector<MapCuboid *> lLocalMapCuboids;
   std::vector<MapPlane *> lLocalMapPlanes;
 };
@@ -212,17 +280,15 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w) {
       if (!pKFi->isBad()) w.lFixedCameras.push_back(pKFi);
     }
   };
-  w.obs_ptr.reserve(w.lLocalMapPoints.size() + 1);
-  w.obs.reserve(8 * w.lLocalMapPoints.size());
-  w.obs_ptr.push_back(0);
+  g_mirror.compact();
+  w.obs_row.reserve(w.lLocalMapPoints.size());
   for (MapPoint *pMP : w.lLocalMapPoints) {
-    const std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
-    for (auto &mit : observations) {
-      add_fixed(mit.first);
-      w.obs.push_back({mit.first, mit.second});
-    }
-    w.obs_ptr.push_back((int)w.obs.size());
+    const Mirror::Row &r = g_mirror.row(pMP);
+    w.obs_row.push_back({r.off, r.n});
   }
+  // (after the loop: a row rebuilt later may have moved the pool)
+  for (auto &r : w.obs_row)
+    for (uint32_t q = r.first; q < r.first + r.second; q++) add_fixed(g_mirror.pool[q].kf);
   if (mixed)
     for (MapCuboid *pMC : w.lLocalMapCuboids) {
       std::unordered_map<KeyFrame *, size_t> observations = pMC->GetObservations();
@@ -335,15 +401,19 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   } else {
     P.solver = PPO_SOLVER_6_3;
   }
+  tick("  B: vertices + plane edges");
   // ---- points and reprojection edges :2332-2424 (mixed) / :560-650 (points only) ----------------------------
   std::vector<MapPoint *> graph_points;  // points that got a vertex (mixed: Observations() != 1, q1)
   std::vector<std::pair<KeyFrame *, MapPoint *>> point_edge_owner;
-  point_edge_owner.reserve(w.obs.size());
-  F.pe_kf.reserve(w.obs.size()); F.pe_obs.reserve(3 * w.obs.size()); F.pe_invsigma2.reserve(w.obs.size());
+  size_t n_obs = 0;
+  for (auto &r : w.obs_row) n_obs += r.second;
+  // edge arrays sized for every observation of the window and filled by index (trimmed below): no capacity checks in the 10^5..10^6-edge loop
+  point_edge_owner.resize(n_obs);
+  F.pe_kf.resize(n_obs); F.pe_obs.resize(3 * n_obs); F.pe_invsigma2.resize(n_obs);
+  size_t ne = 0;
   F.pt_xyz.reserve(3 * w.lLocalMapPoints.size()); F.pt_fixed.reserve(w.lLocalMapPoints.size()); F.pt_rowptr.reserve(w.lLocalMapPoints.size() + 1);
   graph_points.reserve(w.lLocalMapPoints.size());
   F.pt_rowptr.push_back(0);
-  std::vector<std::pair<int, std::pair<KeyFrame *, size_t>>> obs;
   for (size_t ip = 0; ip < w.lLocalMapPoints.size(); ip++) {
     MapPoint *pMP = w.lLocalMapPoints[ip];
     if (mixed && pMP->Observations() == 1) continue;  // :2336
@@ -351,28 +421,25 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     cv::Mat X = pMP->GetWorldPos();
     for (int i = 0; i < 3; i++) F.pt_xyz.push_back((double)X.at<float>(i, 0));  // Converter::toVector3d
     F.pt_fixed.push_back(mixed && fixPoint);
-    obs.clear();
-    for (int q = w.obs_ptr[ip]; q < w.obs_ptr[ip + 1]; q++) {  // the snapshot taken in stage A
-      KeyFrame *pKFi = w.obs[q].first;
+    const ObsRec *row = g_mirror.pool.data() + w.obs_row[ip].first;  // the row read in stage A, already in key-frame (= slot) order
+    for (uint32_t q = 0; q < w.obs_row[ip].second; q++) {
+      const ObsRec &o = row[q];
+      KeyFrame *pKFi = o.kf;
       if (pKFi->isBad() || pKFi->mnId >= slot_of_id.size()) continue;
       const int sl = slot_of_id[pKFi->mnId];
-      if (sl >= 0 && slots[sl].kf == pKFi) obs.push_back({sl, {pKFi, w.obs[q].second}});
+      if (sl < 0 || slots[sl].kf != pKFi) continue;
+      F.pe_kf[ne] = sl;
+      F.pe_obs[3 * ne] = o.u, F.pe_obs[3 * ne + 1] = o.v, F.pe_obs[3 * ne + 2] = o.ur;
+      F.pe_invsigma2[ne] = o.inv_sigma2;
+      point_edge_owner[ne] = {pKFi, pMP};
+      ne++;
     }
-    std::sort(obs.begin(), obs.end(), [](auto &a, auto &b) { return a.first < b.first; });
-    for (auto &o : obs) {
-      KeyFrame *pKFi = o.second.first;
-      const size_t idx = o.second.second;
-      const cv::KeyPoint &kpUn = pKFi->mvKeysUn[idx];
-      F.pe_kf.push_back(o.first);
-      F.pe_obs.push_back(kpUn.pt.x);
-      F.pe_obs.push_back(kpUn.pt.y);
-      F.pe_obs.push_back(pKFi->mvuRight[idx] < 0 ? -1.0f : pKFi->mvuRight[idx]);
-      F.pe_invsigma2.push_back(pKFi->mvInvLevelSigma2[kpUn.octave]);
-      point_edge_owner.push_back({pKFi, pMP});
-    }
-    F.pt_rowptr.push_back((int32_t)F.pe_kf.size());
+    F.pt_rowptr.push_back((int32_t)ne);
   }
+  point_edge_owner.resize(ne);
+  F.pe_kf.resize(ne); F.pe_obs.resize(3 * ne); F.pe_invsigma2.resize(ne);
   if (mixed) {
+    tick("  B: points + point edges");
     // ---- camera-cuboid edges :2433-2551 ------------------------------------------------------------------
     for (int pass = 0; pass < 2; pass++) {
       if (pass == 0 ? !optimize_with_cuboid_2d : !optimize_with_corners_2d) continue;
@@ -403,6 +470,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
         }
       }
     }
+    tick("  B: camera-cuboid edges");
     // ---- point-cuboid edges :2556-2655 ----------------------------------------------------------------------
     F.pce_rowptr.push_back(0);
     if (optimize_with_pt_obj_3d) {
@@ -791,6 +859,14 @@ void Optimizer::LocalBACameraPlaneCuboids(KeyFrame *pKF, bool *pbStopFlag, Map *
 
 // introspection for tests and logging
 extern "C" {
+// observation mirror: drop everything (a new map) / counters {rows reused, rows rebuilt, records in the pool}
+void ppo_shim_mirror_clear() {
+  std::lock_guard<std::mutex> lk(ppo_shim::g_slots[ppo_shim::SLOT_LOCAL].m);
+  ppo_shim::g_mirror.clear();
+}
+void ppo_shim_mirror_stats(long long out[3]) {
+  out[0] = ppo_shim::g_mirror.hits, out[1] = ppo_shim::g_mirror.misses, out[2] = (long long)ppo_shim::g_mirror.pool.size();
+}
 const ppo_ba_graph *ppo_shim_last_graph() { return &ppo_shim::g_last_slot.load()->last.g; }
 const ppo_ba_result *ppo_shim_last_result() { return &ppo_shim::g_last_slot.load()->res; }
 int ppo_shim_last_rc() { return ppo_shim::g_last_slot.load()->rc; }

@@ -22,6 +22,17 @@ def _declare(L):
     L.ppo_mock_run_global.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_ulong, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
     L.ppo_shim_last_result.restype = C.POINTER(A.Result)
     L.ppo_mock_run_pose.argtypes = [C.POINTER(A.Graph), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32 * 3)]
+    L.ppo_mock_world_create.argtypes = [C.POINTER(A.Graph)]
+    L.ppo_mock_world_create.restype = C.c_void_p
+    L.ppo_mock_world_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(A.State), C.POINTER(C.c_int32 * 4)]
+    L.ppo_mock_world_erase_observation.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ppo_mock_world_perturb_point.argtypes = [C.c_void_p, C.c_int, C.c_float]
+    L.ppo_mock_world_destroy.argtypes = [C.c_void_p]
+    L.ppo_mock_world_destroy.restype = None
+    L.ppo_shim_mirror_clear.restype = None
+    L.ppo_shim_mirror_stats.argtypes = [C.POINTER(C.c_longlong * 3)]
+    L.ppo_shim_mirror_stats.restype = None
+    L.ppo_mock_last_call_ms.restype = C.c_double
 
 
 def oracle_backed_lib():
@@ -100,3 +111,43 @@ def run_pose(g, kf, backend=None):
     assert rc == 0
     flat = A.GraphArrays.from_c(L.ppo_shim_last_graph().contents)
     return pose, out[:n], list(counts), flat, L.ppo_shim_last_rc()
+
+
+class World:
+    """A mock map that outlives one call: consecutive Optimizer::LocalBACameraPlaneCuboids calls on the same map (ppo_mock_world_*)."""
+
+    def __init__(self, g, backend=None):
+        self.L = backend or lib()
+        self.g = g
+        self.h = self.L.ppo_mock_world_create(C.byref(g.c))
+
+    def run(self, mixed=True, fix_camera=False, fix_point=False, stop=False):
+        st = A.StateArrays(self.g.c)
+        counts = (C.c_int32 * 4)()
+        flag = np.array([1 if stop else 0], np.uint8)
+        rc = self.L.ppo_mock_world_run(self.h, int(mixed), int(fix_camera), int(fix_point), flag.ctypes.data, C.byref(st.c), C.byref(counts))
+        assert rc == 0
+        flat = A.GraphArrays.from_c(self.L.ppo_shim_last_graph().contents)
+        return st, list(counts), flat
+
+    def erase_observation(self, point, kf):
+        return self.L.ppo_mock_world_erase_observation(self.h, int(point), int(kf))
+
+    def perturb_point(self, point, dx):
+        self.L.ppo_mock_world_perturb_point(self.h, int(point), float(dx))
+
+    def mirror_stats(self):
+        out = (C.c_longlong * 3)()
+        self.L.ppo_shim_mirror_stats(C.byref(out))
+        return {"reused": out[0], "rebuilt": out[1], "pool": out[2]}
+
+    def mirror_clear(self):
+        self.L.ppo_shim_mirror_clear()
+
+    def last_call_ms(self):
+        return float(self.L.ppo_mock_last_call_ms())
+
+    def close(self):
+        if self.h:
+            self.L.ppo_mock_world_destroy(self.h)
+            self.h = None

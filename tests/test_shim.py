@@ -293,3 +293,42 @@ def test_random_windows_through_the_oracle_backed_shim(ppo, oracle_mod, seed):
     assert np.isclose(res.round2.chi2_final, ro.round2.chi2_final, rtol=1e-9)
     assert np.abs(st.kf_pose - o.get_state().kf_pose).max() < 5e-6
     assert counts[3] == flat.c.n_pt
+
+
+def test_observation_mirror_across_calls_cpu(ppo, oracle_mod):
+    """SURVEY 8f rank 1, second half: consecutive local-BA calls on ONE map.  A later call must take the observation rows of the
+    unchanged map points from the mirror (no std::map copies), rebuild exactly the rows whose MapPoint::mnObsVersion moved, and
+    flatten the same graph a cold shim flattens from the same map state."""
+    import shim_lib
+    L = shim_lib.oracle_backed_lib()
+    g = _graph(ppo)
+    w = shim_lib.World(g, backend=L)
+    try:
+        s0 = w.mirror_stats()  # (counters run over the life of the process)
+        _, c1, flat1 = w.run()
+        s1 = w.mirror_stats()
+        n_local = s1["rebuilt"] - s0["rebuilt"]  # cold: every local map point read from the map once
+        assert s1["reused"] == s0["reused"] and n_local >= flat1.c.n_pt > 0
+        # between the calls: the BA's own erasures (c1[0]) changed some rows; the tracker drops two more observations and moves a point
+        rp = g["pt_rowptr"]
+        touched = sum(w.erase_observation(p, int(g["pe_kf"][rp[p]])) for p in (5, 17))
+        w.perturb_point(40, 0.01)  # positions are not part of a row
+        # stop flag raised on entry: the shim collects and flattens, then returns without touching the map (Optimizer.cc:2723-2725)
+        _, c2, flat2 = w.run(stop=True)
+        s2 = w.mirror_stats()
+        reused, rebuilt = s2["reused"] - s1["reused"], s2["rebuilt"] - s1["rebuilt"]
+        assert c2 == c1 and reused + rebuilt == n_local  # (the counters are cumulative over the life of the map: nothing written, nothing erased)
+        assert touched == 2 and 2 <= rebuilt <= 2 + c1[0]  # only the rows whose observations changed
+        w.mirror_clear()
+        _, _, flat3 = w.run(stop=True)  # the same map state through a cold mirror
+        s3 = w.mirror_stats()
+        assert s3["rebuilt"] - s2["rebuilt"] == n_local
+        # and a normal call on the warm mirror still works
+        _, c4, _ = w.run()
+        assert c4[2] > c1[2]
+    finally:
+        w.close()
+    assert flat2.c.n_pe == flat1.c.n_pe - c1[0] - touched  # the erased observations are gone from the graph
+    assert set(flat2.a) == set(flat3.a)
+    for k in flat2.a:
+        assert np.array_equal(flat2[k], flat3[k]), k

@@ -37,7 +37,9 @@ def ncu_raw(path):
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "smsp__inst_executed.sum",
             "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_op_dmma.sum",
-            "sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+            "sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "smsp__average_warp_latency_issue_stalled_barrier.pct", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum"]
     res = collections.OrderedDict()
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
@@ -52,20 +54,31 @@ def ncu_raw(path):
     return res
 
 
-def main():
-    tag, lpath, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+def write_launches(tag, lpath, ci, suffix=""):
     agg = launches(lpath)
     tot = sum(v[1] for v in agg.values())
-    with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as f:
-        f.write(f"# {tag}: ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`), one local BA call on config 2\n\n")
-        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv python tools/profile_one.py 2`.\n")
+    with open(os.path.join(ROOT, "profiles", f"{tag}_launches{suffix}.md"), "w") as f:
+        f.write(f"# {tag}: ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`), one local BA call on config {ci}\n\n")
+        f.write(f"Command: `PPO_BA_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv python tools/profile_one.py {ci}`\n")
+        f.write("(host-driven LM loop: the same kernels as the captured graph, one launch per node).\n")
         f.write("Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
         f.write(f"total kernel time {tot / 1e3:.2f} ms over {sum(v[0] for v in agg.values())} launches\n\n| kernel | launches | total us | avg us | max us | share |\n|---|---|---|---|---|---|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {k} | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.2f} | {v[2]:.2f} | {100 * v[1] / tot:.1f}% |\n")
-    traffic = {}
+
+
+def main():
+    """python tools/summarize_profiles.py <tag> <launches.csv> [<launches_config4.csv>] [<report.ncu-rep> ...]
+    A report whose name contains `config4` feeds the config4 entry of <tag>_traffic.json, every other one the config2 entry."""
+    tag, lpath, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    write_launches(tag, lpath, 2)
+    if reps and reps[0].endswith(".csv"):
+        write_launches(tag, reps[0], 4, "_config4")
+        reps = reps[1:]
+    traffic_all = {}
     for rp in reps:
+        traffic = traffic_all.setdefault("config4" if "config4" in os.path.basename(rp) else "config2", {})
         res = ncu_raw(rp)
         base = os.path.splitext(os.path.basename(rp))[0]
         if base.startswith(tag + "_"):
@@ -76,7 +89,7 @@ def main():
                 for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     v, u = d[m].split()
                     tot_b += float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-                traffic[k.replace("ppo::", "")] = tot_b
+                traffic[re.sub(r"<.*", "", k.replace("ppo::", ""))] = tot_b
             except Exception:
                 pass
         with open(os.path.join(ROOT, "profiles", f"{tag}_{base}.md"), "w") as f:
@@ -87,8 +100,8 @@ def main():
                     f.write(f"- `{m}` = {v}\n")
                 f.write("\n")
         json.dump(res, open(os.path.join(ROOT, "profiles", f"{tag}_{base}.json"), "w"), indent=1)
-    if traffic:
-        json.dump(traffic, open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
+    if traffic_all:
+        json.dump(traffic_all, open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
