@@ -49,6 +49,10 @@ enum ppo_edge_kind {
 /* cbe_kind values */
 #define PPO_CUBOID_BBOX 0   /* EdgeSE3CuboidProj       4-D  */
 #define PPO_CUBOID_CORNER 1 /* EdgeSE3CuboidCornerProj 16-D */
+#define PPO_CUBOID_SE3 2    /* EdgeSE3Cuboid 9-D: min_log_error of the measured cuboid moved to the world frame, over the four yaw
+                             * rotations of the ambiguous front face (g2o_cuboid.h:72-109,322-340); only added by
+                             * LocalBACameraPointCuboids2D (Optimizer.cc:1764-1804).  cbe_meas = the measured cuboid in the CAMERA
+                             * frame, laid out like cu_state: [tx ty tz qx qy qz qw sx sy sz] (+ 6 unused) */
 /* cu_flags bits (VertexCuboid, g2o_cuboid.h:281-285) */
 #define PPO_CU_FIXROLLPITCH 1u
 #define PPO_CU_FIXHEIGHT 2u
@@ -92,6 +96,9 @@ typedef struct ppo_ba_params {
   /* point-cuboid edge constants (Optimizer.cc:2647, g2o_cuboid.cc:147) */
   double ptcu_max_outside_margin_ratio; /* 1.0 */
   double ptcu_prior_weight;             /* 0.2 */
+  /* EdgeSE3Cuboid (PPO_CUBOID_SE3, Optimizer.cc:1792-1794,1875-1882; Parameters.cc:65) */
+  double huber_se3;                     /* thHuberSE3 = 900 (set as the delta itself, no square root) */
+  double norm_se3;                      /* thHuberSE3: compared with ||error|| in the outlier pass      */
 } ppo_ba_params;
 
 /* Flat SoA factor graph. Index spaces are typed (KF slot, point, plane, cuboid) instead of

@@ -26,6 +26,7 @@ typedef struct ppo_synth_cfg {
   double outlier_frac; /* gross outliers among point observations (0.03)         */
   double stereo_frac;  /* fraction of stereo observations (0.7)                   */
   int32_t sort_points; /* 1: order points by their first observing KF (banded CSR) */
+  int32_t cuboid_3d;   /* optimize_with_cuboid_3d: EdgeSE3Cuboid edges (PPO_CUBOID_SE3), LocalBACameraPointCuboids2D only */
 } ppo_synth_cfg;
 
 typedef struct ppo_synth ppo_synth;

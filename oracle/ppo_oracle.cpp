@@ -125,7 +125,15 @@ inline void K_from_intr(const float intr[5], double K[9]) {
   K[6] = 0; K[7] = 0; K[8] = 1;
 }
 // EdgeSE3CuboidProj::computeError src/g2o_cuboid.cc:70-80 ; EdgeSE3CuboidCornerProj :103-120
+inline int cbe_dim(int kind) { return kind == PPO_CUBOID_BBOX ? 4 : (kind == PPO_CUBOID_SE3 ? 9 : 16); }
 inline int cuboid_cam_error(int kind, const SE3 &T, const Cuboid &c, const double K[9], const double *meas, double err[16]) {
+  if (kind == PPO_CUBOID_SE3) {  // EdgeSE3Cuboid::computeError include/g2o_cuboid.h:330-340; measurement laid out like a cuboid state
+    Cuboid m;
+    m.pose = se3_from_qt(Quat{meas[3], meas[4], meas[5], meas[6]}, v3(meas[0], meas[1], meas[2]));
+    m.scale = v3(meas[7], meas[8], meas[9]);
+    cuboid_se3_error(T, c, m, err);
+    return 9;
+  }
   if (kind == PPO_CUBOID_BBOX) {
     double b[4];
     cuboid_project_bbox(c, T, K, b);
@@ -315,7 +323,7 @@ struct ppo_oracle_handle {
     switch (kind) {
       case PPO_EDGE_POINT: return pe_obs[3 * e + 2] < 0 ? P.huber_mono : P.huber_stereo;
       case PPO_EDGE_PLANE: return ple_kind[e] == PPO_PLANE_OBS ? P.huber_plane : P.huber_vp_plane;
-      case PPO_EDGE_CUBOID_CAM: return cbe_kind[e] == PPO_CUBOID_BBOX ? P.huber_bbox : P.huber_corner;
+      case PPO_EDGE_CUBOID_CAM: return cbe_kind[e] == PPO_CUBOID_BBOX ? P.huber_bbox : (cbe_kind[e] == PPO_CUBOID_SE3 ? P.huber_se3 : P.huber_corner);
       case PPO_EDGE_CUBOID_PLANE: return P.huber_cuboid_plane;
     }
     return 0;
@@ -340,7 +348,7 @@ struct ppo_oracle_handle {
       }
       case PPO_EDGE_CUBOID_CAM: {
         const double *r = &cbe_err[16 * e];
-        int d = cbe_kind[e] == PPO_CUBOID_BBOX ? 4 : 16;
+        int d = cbe_dim(cbe_kind[e]);
         double c = 0;
         for (int i = 0; i < d; i++) c += r[i] * (cbe_info[e] * r[i]);
         return c;
@@ -600,7 +608,7 @@ struct ppo_oracle_handle {
     for (int e = 0; e < n_cbe; e++) {
       if (!lvl0(PPO_EDGE_CUBOID_CAM, e)) continue;
       int k = cbe_kf[e], c = cbe_cuboid[e];
-      int D = cbe_kind[e] == PPO_CUBOID_BBOX ? 4 : 16;
+      int D = cbe_dim(cbe_kind[e]);
       double Jkf[16 * 6] = {0}, Jcu[16 * 9] = {0}, ep[16], em[16];
       if (!kf_fixed[k]) {
         for (int d = 0; d < 6; d++) {
@@ -949,10 +957,10 @@ struct ppo_oracle_handle {
       ef[PPO_EDGE_POINT][e] &= ~PPO_EF_ROBUST;
     }
     for (int e = 0; e < n_cbe; e++) {
-      int D = cbe_kind[e] == PPO_CUBOID_BBOX ? 4 : 16;
+      int D = cbe_dim(cbe_kind[e]);
       double s = 0;
       for (int i = 0; i < D; i++) s += cbe_err[16 * e + i] * cbe_err[16 * e + i];
-      if (std::sqrt(s) > (cbe_kind[e] == PPO_CUBOID_BBOX ? P.norm_bbox : P.norm_corner)) {
+      if (std::sqrt(s) > (cbe_kind[e] == PPO_CUBOID_BBOX ? P.norm_bbox : (cbe_kind[e] == PPO_CUBOID_SE3 ? P.norm_se3 : P.norm_corner))) {  // SE3: Optimizer.cc:1875-1882
         if (lvl0(PPO_EDGE_CUBOID_CAM, e)) n_out[2]++;
         ef[PPO_EDGE_CUBOID_CAM][e] |= PPO_EF_LEVEL1;
       }
@@ -987,6 +995,8 @@ void ppo_oracle_default_params(ppo_ba_params *p) {
   p->chi2_vp_plane = 200.0;
   p->norm_bbox = 80.0;
   p->norm_corner = 10.0;
+  p->huber_se3 = 900.0;  // rk->setDelta(thHuberSE3), Optimizer.cc:1794; Parameters.cc:65
+  p->norm_se3 = 900.0;
   p->lm_tau = 1e-5;
   p->lm_good_upper = 2. / 3.;
   p->lm_good_lower = 1. / 3.;
@@ -1116,7 +1126,7 @@ int ppo_oracle_edge_chi2(ppo_oracle_handle *h, int kind, double *chi2, unsigned 
       switch (kind) {
         case PPO_EDGE_POINT: r = &h->pe_err[3 * e]; D = h->pe_obs[3 * e + 2] < 0 ? 2 : 3; break;
         case PPO_EDGE_PLANE: r = &h->ple_err[3 * e]; D = h->ple_kind[e] == PPO_PLANE_OBS ? 3 : 2; break;
-        case PPO_EDGE_CUBOID_CAM: r = &h->cbe_err[16 * e]; D = h->cbe_kind[e] == PPO_CUBOID_BBOX ? 4 : 16; break;
+        case PPO_EDGE_CUBOID_CAM: r = &h->cbe_err[16 * e]; D = cbe_dim(h->cbe_kind[e]); break;
         case PPO_EDGE_POINT_CUBOID: r = &h->pce_err[3 * e]; D = 3; break;
         default: r = &h->cpe_err[3 * e]; D = 3; break;
       }

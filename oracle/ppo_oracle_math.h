@@ -424,6 +424,63 @@ inline V3 cuboid_point_boundary_error(const Cuboid &c, const V3 &pt, double max_
   return e;
 }
 // toMinimalVector: g2o_cuboid.h:145-163
+// SE3Quat::log  Thirdparty/g2o/g2o/types/se3quat.h:229-264 (deltaR: se3_ops.hpp:40-47)
+inline void se3_log(const SE3 &T, double out[6]) {
+  const M3 R = quat_to_matrix(T.r);
+  const double d = 0.5 * (R.m[0][0] + R.m[1][1] + R.m[2][2] - 1);
+  const V3 dR = v3(R.m[2][1] - R.m[1][2], R.m[0][2] - R.m[2][0], R.m[1][0] - R.m[0][1]);
+  V3 omega;
+  M3 V_inv;
+  if (d > 0.99999) {
+    omega = 0.5 * dR;
+    const M3 Om = skew(omega);
+    V_inv = add_scaled(add_scaled(m3_identity(), -0.5, Om), 1. / 12., Om * Om);
+  } else {
+    const double theta = std::acos(d);
+    omega = (theta / (2 * std::sqrt(1 - d * d))) * dR;
+    const M3 Om = skew(omega);
+    V_inv = add_scaled(add_scaled(m3_identity(), -0.5, Om), (1 - theta / (2 * std::tan(theta / 2))) / (theta * theta), Om * Om);
+  }
+  const V3 ups = V_inv * T.t;
+  for (int i = 0; i < 3; i++) out[i] = omega[i], out[3 + i] = ups[i];
+}
+// cuboid::rotate_cuboid  include/g2o_cuboid.h:112-122
+inline Cuboid cuboid_rotate(const Cuboid &c, double yaw_angle) {
+  Cuboid res;
+  SE3 rot = se3_from_qt(Quat{0, 0, std::sin(yaw_angle * 0.5), std::cos(yaw_angle * 0.5)}, v3(0, 0, 0));
+  res.pose = se3_mul(c.pose, rot);
+  res.scale = c.scale;
+  if ((yaw_angle == M_PI / 2.0) || (yaw_angle == -M_PI / 2.0) || (yaw_angle == 3 * M_PI / 2.0)) std::swap(res.scale[0], res.scale[1]);
+  return res;
+}
+// cuboid::cube_log_error :72-79
+inline void cuboid_log_error(const Cuboid &self, const Cuboid &newone, double res[9]) {
+  const SE3 pose_diff = se3_mul(se3_inverse(newone.pose), self.pose);
+  se3_log(pose_diff, res);
+  for (int i = 0; i < 3; i++) res[6 + i] = self.scale[i] - newone.scale[i];
+}
+// cuboid::min_log_error :82-109 (whether_rotate_cubes = true): the error of the yaw rotation (-90, 0, 90, 180 degrees) of smallest norm
+inline void cuboid_min_log_error(const Cuboid &self, const Cuboid &newone, double res[9]) {
+  const double angles[4] = {-1, 0, 1, 2};
+  double best = 0;
+  for (int i = 0; i < 4; i++) {
+    double e[9], n2 = 0;
+    cuboid_log_error(self, cuboid_rotate(newone, angles[i] * M_PI / 2.0), e);
+    for (int k = 0; k < 9; k++) n2 += e[k] * e[k];
+    const double n = std::sqrt(n2);
+    if (i == 0 || n < best) {  // Eigen minCoeff: the first of equal minima
+      best = n;
+      for (int k = 0; k < 9; k++) res[k] = e[k];
+    }
+  }
+}
+// EdgeSE3Cuboid::computeError :330-340: the measured cuboid (camera frame) moved to the world frame with Twc = Tcw^-1 (cuboid::transform_from :125-131)
+inline void cuboid_se3_error(const SE3 &Tcw, const Cuboid &global_cube, const Cuboid &meas, double err[9]) {
+  Cuboid esti;
+  esti.pose = se3_mul(se3_inverse(Tcw), meas.pose);
+  esti.scale = meas.scale;
+  cuboid_min_log_error(global_cube, esti, err);
+}
 inline void cuboid_to_minimal(const Cuboid &c, double v[9]) {
   const Quat &q = c.pose.r;
   v[0] = c.pose.t[0];

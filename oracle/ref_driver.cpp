@@ -224,6 +224,21 @@ void Handle::build() {
       ed->setId(e);
       opt->addEdge(ed);
       e_cb.push_back(ed);
+    } else if (cbe_kind[e] == PPO_CUBOID_SE3) {  // Optimizer.cc:1781-1798 (LocalBACameraPointCuboids2D)
+      g2o::EdgeSE3Cuboid *ed = new g2o::EdgeSE3Cuboid();
+      ed->setVertex(0, v_kf[kf]), ed->setVertex(1, v_cu[cbe_cuboid[e]]);
+      Vector10d mv;
+      for (int k = 0; k < 10; k++) mv(k) = cbe_meas[16 * (size_t)e + k];
+      g2o::cuboid mc;
+      mc.fromVector(mv);  // [t q scale], like the cuboid states
+      ed->setMeasurement(mc);
+      Eigen::Matrix<double, 9, 9> info = Eigen::Matrix<double, 9, 9>::Identity() * cbe_info[e];
+      ed->setInformation(info);
+      ed->setRobustKernel(rk);
+      rk->setDelta(P.huber_se3);
+      ed->setId(e);
+      opt->addEdge(ed);
+      e_cb.push_back(ed);
     } else {
       g2o::EdgeSE3CuboidCornerProj *ed = new g2o::EdgeSE3CuboidCornerProj();
       ed->setVertex(0, v_kf[kf]), ed->setVertex(1, v_cu[cbe_cuboid[e]]);
@@ -301,6 +316,7 @@ void ppo_ref_default_params(ppo_ba_params *p) {
   p->lm_tau = 1e-5, p->lm_good_upper = 2. / 3., p->lm_good_lower = 1. / 3., p->lm_max_trials = 10;
   p->solver = PPO_SOLVER_DENSE_X, p->iters_round1 = 5, p->iters_round2 = 10;
   p->ptcu_max_outside_margin_ratio = 1.0, p->ptcu_prior_weight = 0.2;
+  p->huber_se3 = 900.0, p->norm_se3 = 900.0;  // thHuberSE3 (Parameters.cc:65; Optimizer.cc:1794,1878)
 }
 
 int ppo_ref_create(const ppo_ba_params *params, void **out) {
@@ -442,7 +458,7 @@ int ppo_ref_outlier_pass(void *hv, int32_t n_out[3]) {
   }
   for (size_t i = 0; i < h->e_cb.size(); i++) {
     g2o::OptimizableGraph::Edge *e = h->e_cb[i];
-    if (err_norm(e) > (h->cbe_kind[i] == PPO_CUBOID_BBOX ? h->P.norm_bbox : h->P.norm_corner)) {
+    if (err_norm(e) > (h->cbe_kind[i] == PPO_CUBOID_BBOX ? h->P.norm_bbox : (h->cbe_kind[i] == PPO_CUBOID_SE3 ? h->P.norm_se3 : h->P.norm_corner))) {
       ncb += e->level() != 1;
       e->setLevel(1);
     }
@@ -723,6 +739,15 @@ int ppo_ref_cuboid_cam_edge(int kind, const double pose[7], const double c[10], 
     for (int i = 0; i < 4; i++) err[i] = e.error()(i);
     e.setVertex(0, nullptr), e.setVertex(1, nullptr);
     return 4;
+  }
+  if (kind == PPO_CUBOID_SE3) {
+    g2o::EdgeSE3Cuboid e;
+    e.setVertex(0, &vk), e.setVertex(1, &vc);
+    e.setMeasurement(cu_in(meas));
+    e.computeError();
+    for (int i = 0; i < 9; i++) err[i] = e.error()(i);
+    e.setVertex(0, nullptr), e.setVertex(1, nullptr);
+    return 9;
   }
   g2o::EdgeSE3CuboidCornerProj e;
   e.setVertex(0, &vk), e.setVertex(1, &vc);

@@ -11,7 +11,7 @@ PPO_OK, PPO_E_INVALID, PPO_E_CUDA, PPO_E_NCCL, PPO_E_NOGPU, PPO_E_EMPTY = 0, -1,
 EDGE_POINT, EDGE_PLANE, EDGE_CUBOID_CAM, EDGE_POINT_CUBOID, EDGE_CUBOID_PLANE = range(5)
 EDGE_KINDS = 5
 PLANE_OBS, PLANE_VER, PLANE_PAR = 0, 1, 2
-CUBOID_BBOX, CUBOID_CORNER = 0, 1
+CUBOID_BBOX, CUBOID_CORNER, CUBOID_SE3 = 0, 1, 2
 CU_FIXROLLPITCH, CU_FIXHEIGHT = 1, 2
 EF_LEVEL1, EF_ROBUST = 1, 2
 SOLVER_DENSE_X, SOLVER_6_3 = 0, 1
@@ -30,7 +30,7 @@ class Params(C.Structure):
         "norm_corner", "lm_tau", "lm_good_upper", "lm_good_lower")] + [
         ("lm_max_trials", C.c_int32), ("solver", C.c_int32), ("iters_round1", C.c_int32),
         ("iters_round2", C.c_int32), ("ptcu_max_outside_margin_ratio", C.c_double),
-        ("ptcu_prior_weight", C.c_double)]
+        ("ptcu_prior_weight", C.c_double), ("huber_se3", C.c_double), ("norm_se3", C.c_double)]
 
 
 class Graph(C.Structure):
@@ -81,7 +81,8 @@ class SynthCfg(C.Structure):
     _fields_ = [("n_kf", C.c_int32), ("n_fixed", C.c_int32), ("n_pt", C.c_int32), ("n_pl", C.c_int32),
                 ("n_cu", C.c_int32), ("seed", C.c_uint64), ("cuboid_2d", C.c_int32), ("corners_2d", C.c_int32),
                 ("pt_obj_3d", C.c_int32), ("cuboid_plane", C.c_int32), ("plane_3d", C.c_int32),
-                ("outlier_frac", C.c_double), ("stereo_frac", C.c_double), ("sort_points", C.c_int32)]
+                ("outlier_frac", C.c_double), ("stereo_frac", C.c_double), ("sort_points", C.c_int32),
+                ("cuboid_3d", C.c_int32)]
 
 
 _GRAPH_ARRAYS = {

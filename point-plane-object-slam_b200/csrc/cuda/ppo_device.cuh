@@ -98,7 +98,7 @@ struct DevGraph {
   double *S;       // (n_p + 1) x ld, row-major upper = column-major lower; last column = reduced rhs
   double *xp;      // n_p
   // huber deltas / constants
-  double huber_mono, huber_stereo, huber_plane, huber_vp, huber_bbox, huber_corner;
+  double huber_mono, huber_stereo, huber_plane, huber_vp, huber_bbox, huber_corner, huber_se3;
   double ptcu_ratio, ptcu_prior;
 };
 

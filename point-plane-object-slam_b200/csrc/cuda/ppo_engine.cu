@@ -266,6 +266,8 @@ void ppo_ba_default_params(ppo_ba_params *p) {
   p->chi2_vp_plane = 200.0;
   p->norm_bbox = 80.0;
   p->norm_corner = 10.0;
+  p->huber_se3 = 900.0;  // rk->setDelta(thHuberSE3), Optimizer.cc:1794; Parameters.cc:65
+  p->norm_se3 = 900.0;
   p->lm_tau = 1e-5;
   p->lm_good_upper = 2. / 3.;
   p->lm_good_lower = 1. / 3.;
@@ -355,7 +357,7 @@ int ppo_ba_set_params(ppo_ba_handle *h, const ppo_ba_params *params) {
   if (h->have_graph) {  // constants the resident window carries (ppo_ba_set_graph copies them)
     DevGraph &g = h->g;
     g.huber_mono = h->P.huber_mono; g.huber_stereo = h->P.huber_stereo; g.huber_plane = h->P.huber_plane; g.huber_vp = h->P.huber_vp_plane;
-    g.huber_bbox = h->P.huber_bbox; g.huber_corner = h->P.huber_corner;
+    g.huber_bbox = h->P.huber_bbox; g.huber_corner = h->P.huber_corner; g.huber_se3 = h->P.huber_se3;
     g.ptcu_ratio = h->P.ptcu_max_outside_margin_ratio; g.ptcu_prior = h->P.ptcu_prior_weight;
     h->drop_lm_graphs();  // the captured kernels hold the old constants by value
   }
@@ -501,7 +503,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   for (int e = 0; e < g.n_ple; e++)
     if (gi->ple_kf[e] < 0 || gi->ple_kf[e] >= g.n_kf || gi->ple_plane[e] < 0 || gi->ple_plane[e] >= g.n_pl || gi->ple_kind[e] > 2) { h->err = "plane edge out of range"; return PPO_E_INVALID; }
   for (int e = 0; e < g.n_cbe; e++)
-    if (gi->cbe_kf[e] < 0 || gi->cbe_kf[e] >= g.n_kf || gi->cbe_cuboid[e] < 0 || gi->cbe_cuboid[e] >= g.n_cu || gi->cbe_kind[e] > 1) { h->err = "cuboid edge out of range"; return PPO_E_INVALID; }
+    if (gi->cbe_kf[e] < 0 || gi->cbe_kf[e] >= g.n_kf || gi->cbe_cuboid[e] < 0 || gi->cbe_cuboid[e] >= g.n_cu || gi->cbe_kind[e] > PPO_CUBOID_SE3) { h->err = "cuboid edge out of range"; return PPO_E_INVALID; }
   for (int e = 0; e < g.n_pce; e++)
     if (gi->pce_cuboid[e] < 0 || gi->pce_cuboid[e] >= g.n_cu || gi->pce_rowptr[e + 1] < gi->pce_rowptr[e]) { h->err = "point-cuboid edge out of range"; return PPO_E_INVALID; }
   for (int e = 0; e < g.n_cpe; e++)
@@ -843,7 +845,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   CK(cudaMemsetAsync(g.cbe_flags, PPO_EF_ROBUST, (size_t)g.n_cbe, h->st));
   CK(cudaMemsetAsync(g.pce_flags, 0, (size_t)g.n_pce, h->st));
   g.huber_mono = h->P.huber_mono; g.huber_stereo = h->P.huber_stereo; g.huber_plane = h->P.huber_plane; g.huber_vp = h->P.huber_vp_plane;
-  g.huber_bbox = h->P.huber_bbox; g.huber_corner = h->P.huber_corner;
+  g.huber_bbox = h->P.huber_bbox; g.huber_corner = h->P.huber_corner; g.huber_se3 = h->P.huber_se3;
   g.ptcu_ratio = h->P.ptcu_max_outside_margin_ratio; g.ptcu_prior = h->P.ptcu_prior_weight;
   tick("scratch alloc + memsets");
   CK(cudaStreamSynchronize(h->st));  // host vectors go out of scope
@@ -1455,7 +1457,7 @@ int ppo_ba_outlier_pass(ppo_ba_handle *h, int32_t n_out[3]) {
   const int nmax = std::max(g.n_pe, std::max(g.n_ple, g.n_cbe));
   if (nmax) {
     k_outlier_pass<<<cdiv(nmax, 256), 256, 0, h->st>>>(g, h->sa, P.chi2_mono, P.chi2_stereo, P.chi2_plane, P.chi2_vp_plane, P.norm_bbox,
-                                                     P.norm_corner, h->d_nout);
+                                                     P.norm_corner, P.norm_se3, h->d_nout);
     h->launches++;
   }
   int out[4];

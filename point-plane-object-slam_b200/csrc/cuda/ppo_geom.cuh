@@ -294,6 +294,79 @@ PPO_D int cuboid_cam_error(int kind, const double Rt[12], const double c[10], co
   }
   return 16;
 }
+// ---- EdgeSE3Cuboid (include/g2o_cuboid.h:322-340): 9-D error between the cuboid vertex and the measured cuboid moved to the world ----
+// SE3Quat product / inverse with normalizeRotation (se3quat.h:110-134); poses as (q[4] = x y z w, t[3])
+PPO_D void se3q_mul(const double qa[4], const double ta[3], const double qb[4], const double tb[3], double q[4], double t[3]) {
+  double r[3];
+  quat_rot(qa, tb, r);
+  t[0] = ta[0] + r[0], t[1] = ta[1] + r[1], t[2] = ta[2] + r[2];
+  quat_mul(qa, qb, q);
+  quat_normalize_pos(q);
+}
+PPO_D void se3q_inv(const double q[4], const double t[3], double qi[4], double ti[3]) {
+  qi[0] = -q[0], qi[1] = -q[1], qi[2] = -q[2], qi[3] = q[3];
+  const double nt[3] = {-t[0], -t[1], -t[2]};
+  quat_rot(qi, nt, ti);
+}
+// SE3Quat::log (se3quat.h:229-264)
+PPO_D void se3q_log(const double q[4], const double t[3], double out[6]) {
+  double R[9];
+  quat_to_R(q, R);
+  const double d = 0.5 * (R[0] + R[4] + R[8] - 1);
+  const double dR[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  double w[3], k2;  // V_inv = I - 0.5 Omega + k2 Omega^2
+  if (d > 0.99999) {
+    w[0] = 0.5 * dR[0], w[1] = 0.5 * dR[1], w[2] = 0.5 * dR[2];
+    k2 = 1. / 12.;
+  } else {
+    const double theta = acos(d), f = theta / (2 * sqrt(1 - d * d));
+    w[0] = f * dR[0], w[1] = f * dR[1], w[2] = f * dR[2];
+    k2 = (1 - theta / (2 * tan(theta / 2))) / (theta * theta);
+  }
+  // Omega = skew(w); Omega^2 as a matrix product, entry by entry like Eigen's 3 x 3 product
+  const double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double V[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double o2 = O[3 * i] * O[j] + O[3 * i + 1] * O[3 + j] + O[3 * i + 2] * O[6 + j];
+      V[3 * i + j] = ((i == j ? 1.0 : 0.0) + -0.5 * O[3 * i + j]) + k2 * o2;
+    }
+  out[0] = w[0], out[1] = w[1], out[2] = w[2];
+  mat3_vec(V, t, out + 3);
+}
+// cam = Tcw as [qx qy qz qw tx ty tz]; c, meas = cuboids as [t(3) q(4) scale(3)] (meas in the camera frame)
+PPO_D void cuboid_se3_error(const double cam[7], const double c[10], const double *meas, double err[9]) {
+  double qwc[4], twc[3], qe[4], te[3];
+  se3q_inv(cam, cam + 4, qwc, twc);                 // Twc
+  se3q_mul(qwc, twc, meas + 3, meas, qe, te);       // transform_from: Twc * meas.pose
+  double best = 0;
+#pragma unroll 1
+  for (int i = 0; i < 4; i++) {                     // min_log_error: yaw -90, 0, 90, 180 degrees of the measured cuboid
+    const double yaw = (double)(i - 1) * 3.14159265358979323846 / 2.0;
+    double qz[4] = {0, 0, sin(yaw * 0.5), cos(yaw * 0.5)};
+    quat_normalize_pos(qz);
+    const double tz[3] = {0, 0, 0};
+    double qr[4], tr[3], qi[4], ti[3], qd[4], td[3], e[9];
+    se3q_mul(qe, te, qz, tz, qr, tr);               // rotate_cuboid
+    const bool swap = (i == 0 || i == 2);
+    const double s0 = swap ? meas[8] : meas[7], s1 = swap ? meas[7] : meas[8];
+    se3q_inv(qr, tr, qi, ti);
+    se3q_mul(qi, ti, c + 3, c, qd, td);             // cube_log_error: newone.pose^-1 * this.pose
+    se3q_log(qd, td, e);
+    e[6] = c[7] - s0, e[7] = c[8] - s1, e[8] = c[9] - meas[9];
+    double n2 = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) n2 += e[k] * e[k];
+    const double n = sqrt(n2);
+    if (i == 0 || n < best) {
+      best = n;
+#pragma unroll
+      for (int k = 0; k < 9; k++) err[k] = e[k];
+    }
+  }
+}
 // EdgePointCuboidOnlyObject::computeError (g2o_cuboid.cc:132-160) with point_boundary_error
 // (g2o_cuboid.h:237-255); prior_object_half_size is never set by the BA.
 PPO_D void point_cuboid_error(const double c[10], const double *pts, int n, double ratio, double prior_w, double err[3]) {

@@ -686,7 +686,8 @@ __global__ void k_cuboid_jac(DevGraph g, DevState s) {
 #pragma unroll
   for (int i = 0; i < 10; i++) c[i] = s.cu[10 * cu + i];
   double *J = g.cbe_J + 240 * (size_t)e + 16 * col;
-  const int D = kind == 0 ? 4 : 16;
+  const int D = kind == 0 ? 4 : (kind == 2 ? 9 : 16);
+  // kind 2 (EdgeSE3Cuboid) works on the pose itself, the projection edges on its [R|t] form
   if (col < 6) {
     if (g.kf_fixed[kf]) {
       for (int r = 0; r < 16; r++) J[r] = 0;
@@ -697,23 +698,35 @@ __global__ void k_cuboid_jac(DevGraph g, DevState s) {
     for (int i = 0; i < 7; i++) pose[i] = s.kf_pose[7 * kf + i];
     add[col] = NUM_DELTA;
     se3_oplus(pose, add, po);
-    pose_to_Rt(po, Rt);
-    cuboid_cam_error(kind, Rt, c, intr, meas, ep);
+    if (kind == 2) {
+      cuboid_se3_error(po, c, meas, ep);
+    } else {
+      pose_to_Rt(po, Rt);
+      cuboid_cam_error(kind, Rt, c, intr, meas, ep);
+    }
     add[col] = -NUM_DELTA;
     se3_oplus(pose, add, po);
-    pose_to_Rt(po, Rt);
-    cuboid_cam_error(kind, Rt, c, intr, meas, em);
+    if (kind == 2) {
+      cuboid_se3_error(po, c, meas, em);
+    } else {
+      pose_to_Rt(po, Rt);
+      cuboid_cam_error(kind, Rt, c, intr, meas, em);
+    }
   } else {
-    double Rt[12], add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, co[10];
+    double Rt[12], pose[7], add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, co[10];
 #pragma unroll
     for (int i = 0; i < 12; i++) Rt[i] = s.kf_Rt[12 * kf + i];
+#pragma unroll
+    for (int i = 0; i < 7; i++) pose[i] = s.kf_pose[7 * kf + i];
     const unsigned cf = g.cu_flags[cu];
     add[col - 6] = NUM_DELTA;
     cuboid_oplus(c, cf, add, co);
-    cuboid_cam_error(kind, Rt, co, intr, meas, ep);
+    if (kind == 2) cuboid_se3_error(pose, co, meas, ep);
+    else cuboid_cam_error(kind, Rt, co, intr, meas, ep);
     add[col - 6] = -NUM_DELTA;
     cuboid_oplus(c, cf, add, co);
-    cuboid_cam_error(kind, Rt, co, intr, meas, em);
+    if (kind == 2) cuboid_se3_error(pose, co, meas, em);
+    else cuboid_cam_error(kind, Rt, co, intr, meas, em);
   }
   for (int r = 0; r < 16; r++) J[r] = r < D ? NUM_SCALAR * (ep[r] - em[r]) : 0.0;
 }
@@ -733,7 +746,15 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_cuboid_edges(DevGraph g, DevS
     for (int i = 0; i < 10; i++) c[i] = s.cu[10 * cu + i];
 #pragma unroll
     for (int i = 0; i < 12; i++) Rt[i] = s.kf_Rt[12 * kf + i];
-    const int D = cuboid_cam_error(kind, Rt, c, intr, g.cbe_meas + 16 * (size_t)e, err);
+    int D = 9;
+    if (kind == 2) {
+      double pose[7];
+#pragma unroll
+      for (int i = 0; i < 7; i++) pose[i] = s.kf_pose[7 * kf + i];
+      cuboid_se3_error(pose, c, g.cbe_meas + 16 * (size_t)e, err);
+    } else {
+      D = cuboid_cam_error(kind, Rt, c, intr, g.cbe_meas + 16 * (size_t)e, err);
+    }
     const double info = g.cbe_info[e];
     double chi2 = 0, nrm = 0;
     for (int r = 0; r < D; r++) chi2 += err[r] * (info * err[r]), nrm += err[r] * err[r];
@@ -741,7 +762,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_cuboid_edges(DevGraph g, DevS
     g.cbe_norm[e] = sqrt(nrm);
     rho0 = chi2;
     double w = 1.0;
-    if (g.cbe_flags[e] & PPO_EF_ROBUST_) w = huber_w(chi2, kind == 0 ? g.huber_bbox : g.huber_corner, &rho0);
+    if (g.cbe_flags[e] & PPO_EF_ROBUST_) w = huber_w(chi2, kind == 0 ? g.huber_bbox : (kind == 2 ? g.huber_se3 : g.huber_corner), &rho0);
     if (STORE) {
       for (int r = 0; r < 16; r++) g.cbe_err[16 * (size_t)e + r] = r < D ? err[r] : 0.0;
       g.cbe_w[e] = w * info;
@@ -1589,7 +1610,7 @@ __global__ void k_accept(DevGraph g, DevState cur, DevState tr, const LmDev *lm)
 // outlier pass (Optimizer.cc:2736-2833) and depth test
 // ---------------------------------------------------------------------------------------------
 __global__ void k_outlier_pass(DevGraph g, DevState s, double chi2_mono, double chi2_stereo, double chi2_plane, double chi2_vp,
-                               double norm_bbox, double norm_corner, int *n_out) {
+                               double norm_bbox, double norm_corner, double norm_se3, int *n_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < g.n_pe) {
     const PointEdgeRec rec = g.pe_rec[i];
@@ -1606,7 +1627,7 @@ __global__ void k_outlier_pass(DevGraph g, DevState s, double chi2_mono, double 
   }
   if (i < g.n_cbe) {
     unsigned fl = g.cbe_flags[i];
-    if (g.cbe_norm[i] > (g.cbe_kind[i] == 0 ? norm_bbox : norm_corner)) {
+    if (g.cbe_norm[i] > (g.cbe_kind[i] == 0 ? norm_bbox : (g.cbe_kind[i] == 2 ? norm_se3 : norm_corner))) {  // SE3: Optimizer.cc:1875-1882
       if (!(fl & PPO_EF_LEVEL1_)) atomicAdd(&n_out[2], 1);
       fl |= PPO_EF_LEVEL1_;
     }

@@ -399,8 +399,9 @@ ppo_synth *ppo_synth_create(const ppo_synth_cfg *cfgp) {
   static const double sgn[3][8] = {{1, 1, -1, -1, 1, 1, -1, -1}, {1, -1, -1, 1, 1, -1, -1, 1}, {-1, -1, -1, -1, 1, 1, 1, 1}};
   struct CamObs {
     int kf, cu;
-    double bbox[4], corners[16];
+    double bbox[4], corners[16], local[10];  // local: the cuboid in the camera frame [t q scale] (EdgeSE3Cuboid measurement)
   };
+  Rng rng3(c.seed * 7919u + 17u);  // own stream: the content of the other edge kinds does not depend on cuboid_3d
   std::vector<CamObs> cobs;
   S->pce_rowptr.push_back(0);
   // MapPlane holds ONE asso_cuboid_id (MapPlane.h:67): distinct planes for distinct cuboids while planes last
@@ -456,6 +457,31 @@ ppo_synth *ppo_synth_create(const ppo_synth_cfg *cfgp) {
       int rx = (int)std::floor(o.bbox[0] - o.bbox[2] / 2), ry = (int)std::floor(o.bbox[1] - o.bbox[3] / 2);
       int rw = (int)std::ceil(o.bbox[2]), rh = (int)std::ceil(o.bbox[3]);
       if (!(rx > 5 && ry > 5 && rx + rw < IMG_W - 5 && ry + rh < IMG_H - 5)) continue;
+      if (c.cuboid_3d) {  // the detector's 3-D cuboid in the camera frame: noisy, and with an arbitrary choice of the front face
+        const int quarter = rng3.below(4);  // measured yaw off by a multiple of 90 degrees, x / y half sizes swapped accordingly
+        const double yw = yaw + 2 * deg * rng3.normal() + quarter * (M_PI / 2.0);
+        const double cyw = std::cos(yw), syw = std::sin(yw);
+        const Pose &T = Ttrue[kf];
+        float Tco[16] = {0};
+        const double Rwo[3][3] = {{cyw, -syw, 0}, {syw, cyw, 0}, {0, 0, 1}};
+        for (int r = 0; r < 3; r++) {
+          for (int q = 0; q < 3; q++) {
+            double a = 0;
+            for (int m = 0; m < 3; m++) a += T.R.m[r][m] * Rwo[m][q];
+            Tco[4 * r + q] = (float)a;
+          }
+          Tco[4 * r + 3] = (float)(T.R.m[r][0] * ctr[0] + T.R.m[r][1] * ctr[1] + T.R.m[r][2] * ctr[2] + T.t[r] + 0.02 * rng3.normal());
+        }
+        Tco[15] = 1;
+        double p7[7];
+        ppo::tcw_float_to_pose7(Tco, p7);
+        o.local[0] = p7[4], o.local[1] = p7[5], o.local[2] = p7[6];
+        o.local[3] = p7[0], o.local[4] = p7[1], o.local[5] = p7[2], o.local[6] = p7[3];
+        const bool sw = quarter & 1;
+        o.local[7] = (sw ? sc[1] : sc[0]) * (1 + 0.03 * rng3.normal());
+        o.local[8] = (sw ? sc[0] : sc[1]) * (1 + 0.03 * rng3.normal());
+        o.local[9] = sc[2] * (1 + 0.03 * rng3.normal());
+      }
       cobs.push_back(o);
     }
     if (c.pt_obj_3d) {
@@ -484,18 +510,21 @@ ppo_synth *ppo_synth_create(const ppo_synth_cfg *cfgp) {
     }
   }
   const double cam_info = (1.0 * 0.7) * (1.0 * 0.7);  // (ba_weight * meas_quality)^2, Optimizer.cc:2462-2465
-  for (int pass = 0; pass < 2; pass++) {
+  const double se3_info = (1.0 * 0.75) * (1.0 * 0.75);  // (ba_weight_SE3 * meas_quality)^2, Optimizer.cc:1786-1790
+  for (int pass = 0; pass < 3; pass++) {
     if (pass == 0 && !c.cuboid_2d) continue;
     if (pass == 1 && !c.corners_2d) continue;
+    if (pass == 2 && !c.cuboid_3d) continue;
     for (const CamObs &o : cobs) {
       S->cbe_kf.push_back(o.kf);
       S->cbe_cuboid.push_back(o.cu);
-      S->cbe_kind.push_back(pass == 0 ? PPO_CUBOID_BBOX : PPO_CUBOID_CORNER);
+      S->cbe_kind.push_back(pass == 0 ? PPO_CUBOID_BBOX : (pass == 1 ? PPO_CUBOID_CORNER : PPO_CUBOID_SE3));
       double m[16] = {0};
       if (pass == 0) std::memcpy(m, o.bbox, sizeof o.bbox);
-      else std::memcpy(m, o.corners, sizeof o.corners);
+      else if (pass == 1) std::memcpy(m, o.corners, sizeof o.corners);
+      else std::memcpy(m, o.local, sizeof o.local);
       S->cbe_meas.insert(S->cbe_meas.end(), m, m + 16);
-      S->cbe_info.push_back(cam_info);
+      S->cbe_info.push_back(pass == 2 ? se3_info : cam_info);
     }
   }
 

@@ -12,6 +12,8 @@ WINDOWS = {
     "points_only": (dict(index=0, n_kf=6, n_fixed=2, n_pt=160), True),
     "mixed_bbox": (dict(index=1, n_kf=8, n_fixed=2, n_pt=220, n_pl=4, n_cu=3), False),
     "mixed_corners": (dict(index=1, n_kf=8, n_fixed=2, n_pt=220, n_pl=4, n_cu=3, corners_2d=1, cuboid_2d=0), False),
+    # the graph of LocalBACameraPointCuboids2D (Optimizer.cc:1252-1992): no planes, bbox edges + the 9-D EdgeSE3Cuboid
+    "cuboids_se3": (dict(index=1, n_kf=8, n_fixed=2, n_pt=220, n_pl=0, n_cu=3, cuboid_2d=1, cuboid_3d=1, plane_3d=0, cuboid_plane=0), False),
 }
 INTR = np.array([517.306408, 516.469215, 318.643040, 255.313989, 40.0], np.float32)
 
@@ -45,7 +47,8 @@ def function_vectors(lib, prefix, n=24, seed=20261017):
     out = {k: [] for k in ("se3_exp", "se3_oplus", "se3_map", "se3_matrix", "se3_from_Rt", "plane_normalize", "plane_oplus", "plane_ominus", "plane_ominus_ver",
                            "plane_ominus_par", "plane_transform", "cuboid_oplus", "cuboid_corners", "cuboid_project_corners", "cuboid_project_bbox",
                            "cuboid_point_error", "cuboid_to_minimal", "huber", "point_edge_mono", "point_edge_stereo", "plane_edge", "cuboid_cam_bbox",
-                           "cuboid_cam_corner")}
+                           "cuboid_cam_corner", "cuboid_cam_se3")}
+    rng3 = np.random.default_rng(seed + 3)  # own stream for the vectors added later: the earlier ones keep their inputs
     for it in range(n):
         # SE3: exponential (incl. the small-angle branch at |w| < 1e-5), oplus, map, matrix, construction from a float32 rotation
         u = rng.normal(size=6) * (1e-6 if it % 6 == 0 else (3.0 if it % 6 == 1 else 0.4))
@@ -128,6 +131,30 @@ def function_vectors(lib, prefix, n=24, seed=20261017):
         err = _d(16)
         f("cuboid_cam_edge")(1, _a(cam), _a(cu), _a(INTR, C.c_float), _a(np.array(co) + rng.normal(size=16) * 2), err)
         out["cuboid_cam_corner"].append(np.array(err))
+        # EdgeSE3Cuboid: the measured cuboid in the camera frame = the true one seen from `campose3`, with a random choice of the front
+        # face (yaw off by k * 90 degrees, x / y half sizes swapped for odd k) and noise; it % 4 == 3: a gross yaw error near the 45-degree tie
+        campose3 = _pose(f, rng3, 0.3)
+        cu3 = _cuboid(rng3)
+        k4 = int(rng3.integers(0, 4))
+        yaw_off = k4 * np.pi / 2 + rng3.normal() * 0.05 + (np.pi / 4 - 0.01 if it % 4 == 3 else 0.0)
+        qz = np.array([0.0, 0.0, np.sin(yaw_off / 2), np.cos(yaw_off / 2)])
+        qa = cu3[3:7]
+        qm = np.array([qa[3] * qz[0] + qa[0] * qz[3] + qa[1] * qz[2] - qa[2] * qz[1], qa[3] * qz[1] + qa[1] * qz[3] + qa[2] * qz[0] - qa[0] * qz[2],
+                       qa[3] * qz[2] + qa[2] * qz[3] + qa[0] * qz[1] - qa[1] * qz[0], qa[3] * qz[3] - qa[0] * qz[0] - qa[1] * qz[1] - qa[2] * qz[2]])
+        sc = cu3[7:10] * (1 + rng3.normal(size=3) * 0.05)
+        if k4 % 2:
+            sc = sc[[1, 0, 2]]
+        world_meas = np.r_[cu3[:3] + rng3.normal(size=3) * 0.05, qm, sc]
+        # into the camera frame: Tcw * pose  (rotation by the pose quaternion through se3_map of the centre; orientation q_c * q)
+        ctr = _d(3)
+        f("se3_map")(_a(campose3), _a(world_meas[:3]), ctr)
+        qc = campose3[:4]
+        ql = np.array([qc[3] * qm[0] + qc[0] * qm[3] + qc[1] * qm[2] - qc[2] * qm[1], qc[3] * qm[1] + qc[1] * qm[3] + qc[2] * qm[0] - qc[0] * qm[2],
+                       qc[3] * qm[2] + qc[2] * qm[3] + qc[0] * qm[1] - qc[1] * qm[0], qc[3] * qm[3] - qc[0] * qm[0] - qc[1] * qm[1] - qc[2] * qm[2]])
+        meas3 = np.r_[np.array(ctr), ql / np.linalg.norm(ql), sc, np.zeros(6)]
+        err = _d(16)
+        D = f("cuboid_cam_edge")(2, _a(campose3), _a(cu3), _a(INTR, C.c_float), _a(meas3), err)
+        out["cuboid_cam_se3"].append(np.r_[D, np.array(err)[:9]])
         _ = ident
     return {k: np.array(v) for k, v in out.items()}
 

@@ -141,6 +141,16 @@ def test_small_mixed_window(ppo, oracle_mod, flags):
     full_parity(ppo, oracle_mod, g)
 
 
+@pytest.mark.parametrize("flags", [dict(cuboid_3d=1, cuboid_2d=1), dict(cuboid_3d=1, cuboid_2d=0, corners_2d=1)])
+def test_point_cuboid_window_with_se3_edges(ppo, oracle_mod, flags):
+    """The graph of LocalBACameraPointCuboids2D (Optimizer.cc:1252-1992): no planes, 2-D camera-cuboid edges plus the
+    9-D EdgeSE3Cuboid with its four-way yaw ambiguity (g2o_cuboid.h:82-109,322-340); the oracle is pinned to the reference's own
+    EdgeSE3Cuboid by tests/test_ref_pin.py."""
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=16, n_pt=2500, n_pl=0, n_cu=5, plane_3d=0, cuboid_plane=0, **flags))
+    assert int((g["cbe_kind"] == ppo.abi.CUBOID_SE3).sum()) > 0 and g.c.n_ple == 0
+    full_parity(ppo, oracle_mod, g)
+
+
 def test_config1_mixed_window(ppo, oracle_mod):
     """BASELINE.json configs[1]: 50 KF / 20k points / 50 planes / 10 cuboids."""
     g = ppo.synth.make_graph(ppo.synth.config(1))

@@ -20,7 +20,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = {"se3_exp": 1e-13, "se3_oplus": 1e-13, "se3_map": 1e-13, "se3_matrix": 1e-14, "se3_from_Rt": 1e-13, "plane_normalize": 1e-15, "plane_oplus": 1e-13,
        "plane_ominus": 1e-13, "plane_ominus_ver": 1e-12, "plane_ominus_par": 1e-13, "plane_transform": 1e-13, "cuboid_oplus": 1e-13, "cuboid_corners": 1e-13,
        "cuboid_project_corners": 1e-9, "cuboid_project_bbox": 1e-9, "cuboid_point_error": 1e-13, "cuboid_to_minimal": 1e-13, "huber": 1e-14,
-       "point_edge_mono": 1e-9, "point_edge_stereo": 1e-9, "plane_edge": 1e-12, "cuboid_cam_bbox": 1e-9, "cuboid_cam_corner": 1e-9}
+       "point_edge_mono": 1e-9, "point_edge_stereo": 1e-9, "plane_edge": 1e-12, "cuboid_cam_bbox": 1e-9, "cuboid_cam_corner": 1e-9, "cuboid_cam_se3": 1e-12}
 
 
 @pytest.fixture(scope="module")
