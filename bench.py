@@ -188,18 +188,22 @@ def shim_e2e(ppo, g, reps=3):
             ms = float(L.ppo_mock_last_call_ms())
             r = L.ppo_shim_last_result().contents
             it = r.round1.iterations + r.round2.iterations
+            dev = r.round1.ms_total + r.round2.ms_total  # device time of the two optimize() calls
             if rep == 0:
-                cold, cold_iters = ms, it
+                cold, cold_iters, cold_host = ms, it, ms - dev
             elif best is None or ms < best:
-                best, iters = ms, it
+                best, iters, best_host = ms, it, ms - dev
                 reused, rebuilt = stats1[0] - stats0[0], stats1[1] - stats0[1]
     finally:
         L.ppo_mock_world_destroy(W)
-    return {"value": iters / (best * 1e-3), "unit": UNIT, "ms_per_call": best, "lm_iterations": iters,
-            "first_call": {"value": cold_iters / (cold * 1e-3), "ms_per_call": cold, "lm_iterations": cold_iters, "note": "observation mirror cold"},
+    return {"value": iters / (best * 1e-3), "unit": UNIT, "ms_per_call": best, "lm_iterations": iters, "host_ms_per_call": best_host,
+            "first_call": {"value": cold_iters / (cold * 1e-3), "ms_per_call": cold, "lm_iterations": cold_iters, "host_ms_per_call": cold_host,
+                           "note": "observation mirror cold: every map point's observation map is copied, as the reference does on every call"},
             "mirror": {"rows_reused": int(reused), "rows_rebuilt": int(rebuilt)},
             "note": "Optimizer::LocalBACameraPlaneCuboids on a mock map of the same window, map kept across calls: collection + flattening (observation "
-                    "rows of unchanged map points from the shim's mirror) + H2D + solve + D2H + write-back, wall clock"}
+                    "rows of unchanged map points from the shim's mirror) + H2D + solve + D2H + write-back, wall clock; host_ms = wall clock minus the "
+                    "device time of the two optimize() calls; the later calls solve the window without the observations the first call erased and may "
+                    "stop after fewer LM iterations"}
 
 
 def run_reference(args, rank, world, out_stream):

@@ -109,6 +109,8 @@ class MapCuboid {
   bool isBad() { return mbBad; }
   std::vector<MapPoint *> GetUniqueMapPoints() { return mappoints_unique_own; }
   long int mnId = 0;
+  int object_graph_id = 0;                 // MapCuboid.h:97
+  g2o::cuboid cuboid_local_meas{};         // MapCuboid.h:100: local measurement in the camera frame
   g2o::cuboid cuboid_global_data{};
   double meas_quality = 0.7;
   Eigen::Vector4d bbox_vec{};
@@ -184,8 +186,8 @@ class Map {
 };
 
 // include/Parameters.h:45-76 (only what the local BA reads)
-extern bool optimize_with_cuboid_plane, optimize_with_plane_3d, optimize_with_cuboid_2d, optimize_with_corners_2d, optimize_with_pt_obj_3d;
-extern double ba_weight_bbox, ba_weight_corner, thHuberBbox2d, thHuberConer2d;
+extern bool optimize_with_cuboid_plane, optimize_with_plane_3d, optimize_with_cuboid_2d, optimize_with_corners_2d, optimize_with_pt_obj_3d, optimize_with_cuboid_3d;
+extern double ba_weight_bbox, ba_weight_corner, thHuberBbox2d, thHuberConer2d, ba_weight_SE3, thHuberSE3;
 extern double plane_angle_info, plane_dist_info, plane_chi, cuboid_plane_angle_info, cuboid_plane_dist_info, cuboid_plane_chi;
 
 // include/Optimizer.h:40-45,62 — the entry points the shim re-implements, signatures unchanged
@@ -197,5 +199,6 @@ class Optimizer {
   int static PoseOptimization(Frame *pFrame);
   void static LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap);
   void static LocalBACameraPlaneCuboids(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool fixCamera = false, bool fixPoint = false);
+  void static LocalBACameraPointCuboids2D(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool fixCamera = false, bool fixPoint = false);  // Optimizer.h:60
 };
 }  // namespace ORB_SLAM2

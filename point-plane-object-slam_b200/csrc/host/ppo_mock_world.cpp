@@ -2,6 +2,7 @@
 // the inverse of the flattening the shim performs — calls ORB_SLAM2::Optimizer::LocalBACameraPlaneCuboids /
 // LocalBundleAdjustment exactly like LocalMapping::Run does (src/LocalMapping.cc:100,107) and reads the written-back
 // map state out again.  Input generation / bookkeeping only.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -16,8 +17,8 @@
 namespace ORB_SLAM2 {
 // src/Parameters.cc:43-74 defaults relevant to the BA (flags are set per test from the graph content)
 bool optimize_with_cuboid_plane = false, optimize_with_plane_3d = false, optimize_with_cuboid_2d = false, optimize_with_corners_2d = false,
-     optimize_with_pt_obj_3d = false;
-double ba_weight_bbox = 1.0, ba_weight_corner = 1.0, thHuberBbox2d = 80.0, thHuberConer2d = 10.0;
+     optimize_with_pt_obj_3d = false, optimize_with_cuboid_3d = false;
+double ba_weight_bbox = 1.0, ba_weight_corner = 1.0, thHuberBbox2d = 80.0, thHuberConer2d = 10.0, ba_weight_SE3 = 1.0, thHuberSE3 = 900.0;
 double plane_angle_info = 1.0, plane_dist_info = 100.0, plane_chi = 500.0, cuboid_plane_angle_info = 2.0, cuboid_plane_dist_info = 100.0,
        cuboid_plane_chi = 500.0;
 }  // namespace ORB_SLAM2
@@ -41,7 +42,7 @@ struct MockWorld {
   std::vector<std::unique_ptr<MapCuboid>> cus, local_cus;
   Map map;
   int pkf = 0;
-  bool flags[5] = {false, false, false, false, false};
+  bool flags[6] = {false, false, false, false, false, false};
   const ppo_ba_graph *g = nullptr;  // (counts only, after build)
   int n_kf = 0, n_pt = 0, n_pl = 0, n_cu = 0;
 };
@@ -197,12 +198,14 @@ static void world_build(MockWorld &W, const ppo_ba_graph *g) {
     cus.emplace_back(new MapCuboid());
     MapCuboid *cu = cus.back().get();
     cu->mnId = c;
+    cu->object_graph_id = c;
     const double *s = &g->cu_state[10 * c];
     const double p7[7] = {s[3], s[4], s[5], s[6], s[0], s[1], s[2]};
     std::memcpy(cu->cuboid_global_data.pose7, p7, sizeof p7);
     for (int k = 0; k < 3; k++) cu->cuboid_global_data.scale[k] = s[7 + k];
   }
-  bool any_bbox = false, any_corner = false;
+  bool any_bbox = false, any_corner = false, any_se3 = false;
+  std::vector<char> any_se3_of((size_t)std::max(g->n_cu, 1), 0);
   for (int e = 0; e < g->n_cbe; e++) {
     KeyFrame *kf = kfs[g->cbe_kf[e]].get();
     MapCuboid *cu = cus[g->cbe_cuboid[e]].get();
@@ -212,14 +215,27 @@ static void world_build(MockWorld &W, const ppo_ba_graph *g) {
       local_cus.emplace_back(new MapCuboid());
       lo = local_cus.back().get();
       lo->bbox_2d = cv::Rect{50, 50, 100, 100};  // inside the 5 px margin (the flat graph only holds edges that passed the test)
-      lo->meas_quality = std::sqrt(g->cbe_info[e]);
+      if (g->cbe_kind[e] != PPO_CUBOID_SE3) lo->meas_quality = std::sqrt(g->cbe_info[e]);
       cu->mObservations[kf] = kf->local_cuboids.size();
       kf->local_cuboids.push_back(lo);
-      if (is_local(g->cbe_kf[e])) kf->mvpMapCuboid.push_back(cu);
+      // mvpMapCuboid runs parallel to the key-frame's detections (Tracking associates detection i with landmark mvpMapCuboid[i]); stage A
+      // only walks the lists of the LOCAL key-frames, and skips landmarks already marked
+      kf->mvpMapCuboid.push_back(cu);
     } else {
       lo = kf->local_cuboids[it->second];
     }
-    if (g->cbe_kind[e] == PPO_CUBOID_BBOX) {
+    if (g->cbe_kind[e] == PPO_CUBOID_SE3) {
+      // the reference takes the 3-D measurement from the LANDMARK (mvpMapCuboid[idx]->cuboid_local_meas, Optimizer.cc:1779,1785): one
+      // measurement per landmark, whichever key-frame observes it -- the first such edge of the flat graph provides it
+      if (!any_se3_of[g->cbe_cuboid[e]]) {
+        const double *m = &g->cbe_meas[16 * e];
+        const double p7[7] = {m[3], m[4], m[5], m[6], m[0], m[1], m[2]};
+        std::memcpy(cu->cuboid_local_meas.pose7, p7, sizeof p7);
+        for (int k = 0; k < 3; k++) cu->cuboid_local_meas.scale[k] = m[7 + k];
+        any_se3_of[g->cbe_cuboid[e]] = 1;
+      }
+      any_se3 = true;
+    } else if (g->cbe_kind[e] == PPO_CUBOID_BBOX) {
       any_bbox = true;
       for (int k = 0; k < 4; k++) lo->bbox_vec(k) = g->cbe_meas[16 * e + k];
     } else {
@@ -246,7 +262,7 @@ static void world_build(MockWorld &W, const ppo_ba_graph *g) {
     for (int k = 0; k < 3; k++) pl->asso_cuboid_meas(k) = g->cpe_meas[3 * e + k];
   }
   W.pkf = pkf;
-  W.flags[0] = g->n_ple > 0, W.flags[1] = any_bbox, W.flags[2] = any_corner, W.flags[3] = g->n_pce > 0, W.flags[4] = g->n_cpe > 0;
+  W.flags[0] = g->n_ple > 0, W.flags[1] = any_bbox, W.flags[2] = any_corner, W.flags[3] = g->n_pce > 0, W.flags[4] = g->n_cpe > 0, W.flags[5] = any_se3;
 }
 
 // ---- the call LocalMapping::Run makes ------------------------------------------------------------------------------------------
@@ -256,6 +272,7 @@ static int world_run(MockWorld &W, int mixed, int fixCamera, int fixPoint, unsig
   optimize_with_corners_2d = W.flags[2];
   optimize_with_pt_obj_3d = W.flags[3];
   optimize_with_cuboid_plane = W.flags[4];
+  optimize_with_cuboid_3d = W.flags[5];
   // every real call has a new pKF->mnId, which invalidates the mnBALocalForKF / mnBAFixedForKF marks of the call before; the mock calls
   // with the same key-frame again, so the marks are invalidated by hand
   const unsigned long none = ~0ul;
@@ -265,7 +282,8 @@ static int world_run(MockWorld &W, int mixed, int fixCamera, int fixPoint, unsig
   for (auto &q : W.cus) q->mnBALocalForKF = none;
   bool stop_flag = stop ? (*stop != 0) : false;
   const auto t_call = std::chrono::steady_clock::now();
-  if (mixed) Optimizer::LocalBACameraPlaneCuboids(W.kfs[W.pkf].get(), &stop_flag, &W.map, fixCamera != 0, fixPoint != 0);
+  if (mixed == 2) Optimizer::LocalBACameraPointCuboids2D(W.kfs[W.pkf].get(), &stop_flag, &W.map, fixCamera != 0, fixPoint != 0);
+  else if (mixed) Optimizer::LocalBACameraPlaneCuboids(W.kfs[W.pkf].get(), &stop_flag, &W.map, fixCamera != 0, fixPoint != 0);
   else Optimizer::LocalBundleAdjustment(W.kfs[W.pkf].get(), &stop_flag, &W.map);
   g_last_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
   return 0;

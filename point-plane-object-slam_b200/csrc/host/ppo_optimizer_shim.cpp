@@ -1,6 +1,7 @@
 // Drop-in replacement for the two local-BA entry points of src/Optimizer.cc:
 //   void Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*)                         (:461-786)
 //   void Optimizer::LocalBACameraPlaneCuboids(KeyFrame*, bool*, Map*, bool, bool)         (:1994-2967)
+//   void Optimizer::LocalBACameraPointCuboids2D(KeyFrame*, bool*, Map*, bool, bool)       (:1252-1992)
 // Stage A (window collection), stage B (graph flattening instead of g2o vertex/edge construction), stage F
 // (erase lists) and stage G (write-back) stay on the host and follow the reference statement by statement;
 // stages C-E (optimize(5), outlier pass, optimize(10)) run on the GPU through the C-ABI (include/ppo_ba.h).
@@ -244,7 +245,7 @@ struct Window {
 };
 
 // stage A: Optimizer.cc:1997-2100 (mixed) / :463-514 (points only)
-static void collect(KeyFrame *pKF, bool mixed, Window &w) {
+static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = true) {
   w.lLocalKeyFrames.push_back(pKF);
   pKF->mnBALocalForKF = pKF->mnId;
   const std::vector<KeyFrame *> vNeighKFs = pKF->GetVectorCovisibleKeyFrames();
@@ -268,6 +269,7 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w) {
           pMC->mnBALocalForKF = pKF->mnId;
         }
     for (KeyFrame *kf : w.lLocalKeyFrames)
+      if (with_planes)
       for (MapPlane *pMP : kf->mvpMapPlanes)
         if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) {
           w.lLocalMapPlanes.push_back(pMP);
@@ -296,7 +298,9 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w) {
     }
 }
 
-static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fixCamera, bool fixPoint) {
+// cuboids2d: Optimizer::LocalBACameraPointCuboids2D (Optimizer.cc:1252-1992) -- the mixed window without planes (no plane vertices, plane
+// edges or cuboid-plane edges) plus, with optimize_with_cuboid_3d, one EdgeSE3Cuboid per cuboid observation (:1764-1804)
+static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fixCamera, bool fixPoint, bool cuboids2d = false) {
   Slot &S = g_slots[0];
   g_last_slot = &S;
   std::lock_guard<std::mutex> lk(S.m);
@@ -310,7 +314,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     t_prev = now;
   };
   Window w;
-  collect(pKF, mixed, w);
+  collect(pKF, mixed, w, !cuboids2d);
   tick("collect window (stage A)");
 
   // ---- stage B: flatten (vertices) ------------------------------------------------------------------
@@ -372,7 +376,9 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     P.huber_corner = ppo::huber_delta(thHuberConer2d);
     P.norm_corner = thHuberConer2d;
     P.huber_cuboid_plane = ppo::huber_delta(cuboid_plane_chi);
-    if (optimize_with_plane_3d)
+    P.huber_se3 = thHuberSE3;  // rk->setDelta(thHuberSE3): the threshold itself (:1794)
+    P.norm_se3 = thHuberSE3;   // :1878
+    if (optimize_with_plane_3d && !cuboids2d)
       for (MapPlane *pMP : w.lLocalMapPlanes) {
         auto add = [&](const std::map<KeyFrame *, int> &obs, int kind) {
           for (auto &mit : obs) {
@@ -470,6 +476,33 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
         }
       }
     }
+    // ---- EdgeSE3Cuboid :1764-1804 (LocalBACameraPointCuboids2D only) --------------------------------------------------
+    if (cuboids2d && optimize_with_cuboid_3d)
+      for (MapCuboid *pMCuboid : w.lLocalMapCuboids) {
+        const std::unordered_map<KeyFrame *, size_t> observations = pMCuboid->GetObservations();
+        for (auto &mit : observations) {
+          KeyFrame *pKFi = mit.first;
+          if (pKFi->isBad()) continue;
+          auto it = kf_slot.find(pKFi);
+          if (it == kf_slot.end()) continue;
+          // the reference reads the measurement from the LANDMARK list of the key-frame, mvpMapCuboid[idx] (:1779), not from its local
+          // detections, and addresses the vertex by object_graph_id (:1783); a vertex that is not in the window would be a NULL vertex there
+          if (mit.second >= pKFi->mvpMapCuboid.size() || !pKFi->mvpMapCuboid[mit.second]) continue;
+          const MapCuboid *local_object = pKFi->mvpMapCuboid[mit.second];
+          int cu = -1;
+          for (MapCuboid *pMC : w.lLocalMapCuboids)
+            if (pMC->mnId == (long int)pMCuboid->object_graph_id) cu = cu_index[pMC];
+          if (cu < 0) continue;
+          double m[16] = {0};
+          cuboid_to10(local_object->cuboid_local_meas, m);
+          const double s = ba_weight_SE3 * 0.75;  // meas_quality = 0.75 (:1788)
+          F.cbe_kf.push_back(it->second);
+          F.cbe_cuboid.push_back(cu);
+          F.cbe_kind.push_back(PPO_CUBOID_SE3);
+          F.cbe_meas.insert(F.cbe_meas.end(), m, m + 16);
+          F.cbe_info.push_back(s * s);
+        }
+      }
     tick("  B: camera-cuboid edges");
     // ---- point-cuboid edges :2556-2655 ----------------------------------------------------------------------
     F.pce_rowptr.push_back(0);
@@ -514,7 +547,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
       }
     }
     // ---- cuboid-plane edges :2662-2714 -------------------------------------------------------------------------
-    if (optimize_with_cuboid_plane) {
+    if (optimize_with_cuboid_plane && !cuboids2d) {
       const double a = 3282.8 / (cuboid_plane_angle_info * cuboid_plane_angle_info), d = cuboid_plane_dist_info * cuboid_plane_dist_info;
       for (MapPlane *pMP : w.lLocalMapPlanes) {
         if (pMP->asso_cuboid_id == 999) continue;
@@ -854,6 +887,9 @@ void Optimizer::GlobalBundleAdjustemnt(Map *pMap, int nIterations, bool *pbStopF
 void Optimizer::LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap) { ppo_shim::run(pKF, pbStopFlag, pMap, false, false, false); }
 void Optimizer::LocalBACameraPlaneCuboids(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool fixCamera, bool fixPoint) {
   ppo_shim::run(pKF, pbStopFlag, pMap, true, fixCamera, fixPoint);
+}
+void Optimizer::LocalBACameraPointCuboids2D(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool fixCamera, bool fixPoint) {
+  ppo_shim::run(pKF, pbStopFlag, pMap, true, fixCamera, fixPoint, true);
 }
 }  // namespace ORB_SLAM2
 

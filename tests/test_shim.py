@@ -332,3 +332,39 @@ def test_observation_mirror_across_calls_cpu(ppo, oracle_mod):
     assert set(flat2.a) == set(flat3.a)
     for k in flat2.a:
         assert np.array_equal(flat2[k], flat3[k]), k
+
+
+# ---- Optimizer::LocalBACameraPointCuboids2D ------------------------------------------------------------------
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_point_cuboids_2d_entry_point(ppo, oracle_mod, backend):
+    """The sibling BA of the plane BA (Optimizer.cc:1252-1992): no plane vertices or edges even if the map has planes, bbox edges and one
+    9-D EdgeSE3Cuboid per cuboid observation whose measurement is the LANDMARK's cuboid_local_meas (the reference reads
+    pKFi->mvpMapCuboid[idx], :1779-1785); result = the oracle on the graph the shim flattened."""
+    import shim_lib
+    L = _backend(backend)
+    A = ppo.abi
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=14, n_fixed=3, n_pt=900, n_pl=6, n_cu=3, cuboid_3d=1))
+    assert g.c.n_pl == 6 and g.c.n_ple > 0  # the map has planes; this entry point ignores them
+    st, counts, flat = shim_lib.run(g, mixed=2, backend=L)
+    assert L.ppo_shim_last_rc() == 0
+    assert flat.c.n_pl == 0 and flat.c.n_ple == 0 and flat.c.n_cpe == 0 and flat.c.n_cu == g.c.n_cu
+    kinds = flat["cbe_kind"]
+    n_se3, n_bbox = int((kinds == A.CUBOID_SE3).sum()), int((kinds == A.CUBOID_BBOX).sum())
+    assert n_se3 > 0 and n_se3 >= n_bbox  # every cuboid observation gets an SE3 edge; the bbox edges also pass the image-margin test
+    # one measurement per landmark, information (ba_weight_SE3 * 0.75)^2
+    se3 = kinds == A.CUBOID_SE3
+    assert np.allclose(flat["cbe_info"][se3], 0.75 ** 2)
+    for c in range(flat.c.n_cu):
+        m = flat["cbe_meas"][se3 & (flat["cbe_cuboid"] == c)]
+        assert len(m) == 0 or np.abs(m - m[0]).max() == 0.0
+    o = oracle_mod.Oracle()
+    o.set_graph(flat)
+    ro = o.local_ba()
+    so = o.get_state()
+    res = L.ppo_shim_last_result().contents
+    assert (res.round1.iterations, res.round2.iterations) == (ro.round1.iterations, ro.round2.iterations)
+    assert np.isclose(res.round2.chi2_final, ro.round2.chi2_final, rtol=1e-6)
+    assert np.abs(st.kf_pose - so.kf_pose).max() < 5e-6
+    pc = [int(np.abs(g["cu_state"] - r).sum(axis=1).argmin()) for r in flat["cu_state"]]
+    assert sorted(pc) == list(range(g.c.n_cu)) and np.abs(st.cu_state[pc] - so.cu_state).max() < 1e-5
+    assert np.abs(st.pl_coef - g["pl_coef"]).max() < 1e-6  # planes untouched (float32 round trip of the map)
