@@ -220,8 +220,10 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
                     ppo_ba_stats *stats);
 
 /* Batch variants: n independent windows (one handle each, possibly on different devices) optimised concurrently;
- * every handle runs its own host-driven LM loop on its own stream, so the latency-bound phases of one window
- * overlap the others (BASELINE configs[3]: many independent key-frame windows).  stats / res are arrays of n.
+ * every handle replays its own LM graph on its own stream, so the latency-bound phases of one window
+ * overlap the others (BASELINE configs[3]: many independent key-frame windows).  The windows of one device
+ * share its SMs for the persistent factorisation of the reduced system (SMs / windows CTAs each), so that
+ * their dependency chains run side by side.  stats / res are arrays of n.
  * Returns the first non-zero error code of any window (all windows are always run to completion). */
 int ppo_ba_optimize_batch(ppo_ba_handle **h, int n, int iters, const volatile unsigned char *stop_flag, ppo_ba_stats *stats);
 int ppo_ba_local_ba_batch(ppo_ba_handle **h, int n, const volatile unsigned char *stop_flag, ppo_ba_result *res);
@@ -295,11 +297,20 @@ int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, do
                        double *x, int32_t *ok);
 
 /* -- multi-GPU: one window, landmarks sharded over ranks ------------------------ */
-/* Each rank builds a handle with the SAME poses/cuboids/plane/cuboid edges and ITS OWN
- * contiguous slice of points.  The reduced system [Hschur | bschur | chi2 | scale] is summed
- * over ranks with ncclAllReduce (f64) on the handle's stream; every rank then factorises the
- * identical system.  nccl_comm is an ncclComm_t passed as void*; rank 0 alone accumulates the
- * non-point edges. */
+/* Call before ppo_ba_set_graph, on every rank (one process per GPU of ONE node; world <= 8 for the
+ * distributed solve).  Each rank then sets a graph with the SAME key-frames, cuboids, camera-cuboid and
+ * point-cuboid edges and ITS OWN landmarks: a slice of the points with their edges and a slice of the
+ * planes with their plane edges and the cuboid-plane edges that name them (sharding.py: shard_graph).
+ * Rank 0 alone accumulates the replicated edges.  Per linearisation the per-key-frame pose blocks of the
+ * landmark edges are all-reduced (NCCL, n_kf x 27 doubles); per damped trial every rank accumulates the
+ * Schur complement of ITS landmarks into its copy of the reduced system, which lives in peer-mapped
+ * (cudaIpc) memory: tile column j is summed by its owner, rank j mod world, straight from the other ranks'
+ * copies, the Cholesky factorisation is spread over the ranks by tile column with the finished panel
+ * tiles pushed to every rank over NVLink, and every rank back-substitutes and updates its own landmarks
+ * (csrc/cuda/ppo_dense.cu, "distributed factorisation").  {chi2, scale, failed-pivot flag} are all-reduced
+ * per trial, so all ranks take the same LM decisions.  ppo_ba_set_graph / ppo_ba_optimize / ppo_ba_local_ba
+ * are COLLECTIVE in this mode.  PPO_DIST_SOLVE=0 in the environment falls back to an ncclAllReduce of the
+ * whole reduced system with a replicated factorisation.  nccl_comm is an ncclComm_t passed as void*. */
 int ppo_ba_set_shard(ppo_ba_handle *h, void *nccl_comm, int rank, int world);
 /* NCCL plumbing without a link-time dependency (libnccl.so.2 is dlopen'ed; the torch wheel already maps it):
  * rank 0 creates the 128-byte unique id, the host program broadcasts it (e.g. torch.distributed), every rank
