@@ -1073,8 +1073,11 @@ static int schur_system(ppo_ba_handle *h) {
   if (g.n_units) { k_schur_bd_points<<<g.n_units, 32, 0, st>>>(g, h->d_lm); h->launches++; }
   if (h->n_pairs) {
     const int n_warps = cdiv(h->n_pairs, PAIR_CHUNK);
-    k_schur_pairs<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld, grow, h->d_pair_bnd, h->d_pair_bnd_key,
-                                                                            h->d_pair_bnd_flag);
+    // <U = 2 records in flight per warp, 1 accumulator chain, 8 CTAs per SM (32 registers)>: the kernel gathers 0.6 GB (config 2) out of an
+    // L2-resident array and wants warps, not per-warp parallelism -- measured 150 us against 222 (<8,1,1>: 96 registers), 155 (<8,2,4>) and
+    // 154 (<4,1,6>); config 4: 1.90 ms against 3.05 / 2.04 / 2.02
+    k_schur_pairs<2, 1, 8><<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, h->d_pair_keys, h->d_pair_vals, h->n_pairs, ld, grow, h->d_pair_bnd,
+                                                                                     h->d_pair_bnd_key, h->d_pair_bnd_flag);
     k_schur_pairs_fix<<<cdiv(n_warps, PAIR_WARPS), PAIR_WARPS * 32, 0, st>>>(g, n_warps, ld, grow, h->d_pair_bnd, h->d_pair_bnd_key, h->d_pair_bnd_flag);
     h->launches += 2;
   }

@@ -1087,8 +1087,9 @@ PPO_D void schur_store(const DevGraph &g, unsigned key, int lane, double acc0, d
 // (slot 0: the chunk's first pair continues from the previous chunk, slot 1: its last pair continues into the next one) and
 // k_schur_pairs_fix adds the partials of such a pair in chunk order: no atomics, the result does not depend on scheduling.
 // bnd_flag[chunk]: bit 0 slot 0 valid, bit 1 slot 1 valid, bit 2 the whole chunk is one pair that continues on both sides.
-__global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, const unsigned *__restrict__ keys, const unsigned long long *__restrict__ vals,
-                                                                 int n_pairs, int ld, int grow, double *bnd, unsigned *bnd_key, int *bnd_flag) {
+template <int U, int CHAINS, int MINB>
+__global__ void __launch_bounds__(PAIR_WARPS * 32, MINB) k_schur_pairs(DevGraph g, const unsigned *__restrict__ keys, const unsigned long long *__restrict__ vals,
+                                                                       int n_pairs, int ld, int grow, double *bnd, unsigned *bnd_key, int *bnd_flag) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
   const long long c0 = w * PAIR_CHUNK;
@@ -1105,7 +1106,17 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
   int flags = 0;
   unsigned cur = PAD;
   double acc0 = 0.0, acc1 = 0.0;
+  // CHAINS > 1: the records of a group go round-robin to CHAINS accumulator fragments (independent DMMA chains); they are added
+  // in a fixed order when the key-frame pair ends
+  double ex0[CHAINS > 1 ? CHAINS - 1 : 1], ex1[CHAINS > 1 ? CHAINS - 1 : 1];
+#pragma unroll
+  for (int q = 0; q < CHAINS - 1; q++) ex0[q] = ex1[q] = 0.0;
   auto flush = [&]() {
+#pragma unroll
+    for (int q = 0; q < CHAINS - 1; q++) {
+      acc0 += ex0[q], acc1 += ex1[q];
+      ex0[q] = ex1[q] = 0.0;
+    }
     if (cur != PAD) {
       const bool from_prev = cont_prev && cur == first_key, to_next = cont_next && cur == last_key;
       if (!from_prev && !to_next) {
@@ -1120,11 +1131,20 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
     }
     acc0 = acc1 = 0.0;
   };
-  constexpr int U = 8;  // contributions whose operand loads are in flight together
+  // Per-lane operand addressing, fixed for the whole chunk: the lanes of the 6 x 3 block read Y (18 doubles per entry) for both operands,
+  // the three lanes of row 6 read z (3 doubles per entry) as their B operand -- one load per operand and record, no per-record selects.
+  // Column 6 of C (the reduced-gradient term) is only ever stored for the self pairs kf_a == kf_b, which are exactly the records with
+  // e1 == e2 (a landmark has at most one block per key-frame: set_graph rejects duplicates), so the z lanes need no e1 == e2 test.
+  const double *pa = g.BD + idx;
+  const double *pb = in_blk ? g.BD + idx : g.Zent + kk;
+  const unsigned sb = in_blk ? 18u : 3u;
+  const bool lb = in_blk || z_lane;
+  // U contributions have their operand loads in flight together
   for (int base = 0; base < cnt; base += 32) {
     const int c = base + lane;
     const unsigned kl = c < cnt ? keys[c0 + c] : PAD;  // (the list ends with 0xffffffff padding)
     const unsigned long long vl = c < cnt ? vals[c0 + c] : 0ull;
+    const unsigned v1 = (unsigned)(vl >> 32), v2 = (unsigned)(vl & 0xffffffffu);
     for (int cb = 0; cb < 32; cb += U) {
       if (base + cb >= cnt) break;  // warp-uniform
       unsigned key[U];
@@ -1132,11 +1152,18 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_schur_pairs(DevGraph g, con
 #pragma unroll
       for (int u = 0; u < U; u++) {
         key[u] = __shfl_sync(FULL, kl, cb + u);
-        const unsigned long long v = __shfl_sync(FULL, vl, cb + u);
-        const unsigned e1 = (unsigned)(v >> 32), e2 = (unsigned)(v & 0xffffffffu);
+        const unsigned e1 = __shfl_sync(FULL, v1, cb + u), e2 = __shfl_sync(FULL, v2, cb + u);
         const bool ok = key[u] != PAD;
-        av[u] = (ok && in_blk) ? g.BD[18 * (size_t)e1 + idx] : 0.0;
-        bv[u] = (ok && in_blk) ? g.BD[18 * (size_t)e2 + idx] : ((ok && z_lane && e1 == e2) ? g.Zent[3 * (size_t)e1 + kk] : 0.0);
+        av[u] = (ok && in_blk) ? pa[18 * (size_t)e1] : 0.0;
+        bv[u] = (ok && lb) ? pb[(size_t)sb * e2] : 0.0;
+      }
+      if (key[0] == cur && key[U - 1] == cur) {  // the list is sorted: the whole group continues the current key-frame pair (~90 records per pair)
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (CHAINS == 1 || u % CHAINS == 0) dmma884(acc0, acc1, av[u], bv[u]);
+          else dmma884(ex0[u % CHAINS - 1], ex1[u % CHAINS - 1], av[u], bv[u]);
+        }
+        continue;
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
