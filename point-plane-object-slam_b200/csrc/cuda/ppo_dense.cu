@@ -1011,42 +1011,67 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
   };
+  const int Bc = d.p.blk;  // columns per ownership block: column j belongs to rank (j / Bc) mod world
+  auto own = [&](int j) { return (j / Bc) % Wd; };
   if (role == 0) {
-    // =============================== critical path of my columns k = R, R + world, .. ================================
-    TilePtr D = sm.T[0], W = sm.T[1], A = sm.T[2], C = sm.T[3], Pp = sm.T[4];
+    // =============================== critical path of my columns ================================================================
+    // Inside a block of Bc consecutive columns the critical path stays on this GPU (the panel tile just computed is still in shared
+    // memory, like in k_chol_dataflow); it crosses NVLink once per block.
+    TilePtr D = sm.T[0], A = sm.T[2], C = sm.T[3], Pp = sm.T[4];
     if (comm) {
       if (lane == 0) {
-        unsigned pd0 = 0, pd1 = 0;
-        bool ok = true;
-        for (int k = R; k < Tc; k += Wd) {
-          // operands of U_{k-1}(k,k): P_{k,k-1} (pushed by the owner of column k-1) and my tile (k,k) after the updates U_0 .. U_{k-2}
-          if (k > 0) {
-            ok = flag_wait_sys(&a.ver[k * vs + k - 1], base + k, ctrl);
+        unsigned pd0 = 0, pd1 = 0, pd2 = 0;
+        bool ok = true, early = false;
+        int it = 0;
+        for (int k = 0; k < Tc; k++) {
+          if (own(k) != R) continue;
+          TilePtr W = (it++ & 1) ? sm.T[5] : sm.T[1];
+          const bool local_prev = k > 0 && own(k - 1) == R;
+          // operands of U_{k-1}(k,k): P_{k,k-1} (still in A if column k-1 is mine, else pushed by its owner) and my tile (k,k) after U_0 .. U_{k-2}
+          if (!early) {
+            if (!local_prev && k > 0) ok = flag_wait_sys(&a.ver[k * vs + k - 1], base + k, ctrl);
             if (ok && k >= 2) ok = flag_wait_sys(&a.ver[k * vs + k], base + k - 1, ctrl);
+            if (ok) {
+              const bool need_p = !local_prev && k > 0;
+              fence_proxy_async();
+              mbar_expect_tx(&sm.full[0], (need_p ? 2 : 1) * TILE_BYTES);
+              if (need_p) bulk_g2s(Pp, tile(k, k - 1), TILE_BYTES, &sm.full[0]);
+              bulk_g2s(C, tile(k, k), TILE_BYTES, &sm.full[0]);
+            }
           }
-          if (ok) {
-            fence_proxy_async();
-            mbar_expect_tx(&sm.full[0], (k > 0 ? 2 : 1) * TILE_BYTES);
-            if (k > 0) bulk_g2s(Pp, tile(k, k - 1), TILE_BYTES, &sm.full[0]);
-            bulk_g2s(C, tile(k, k), TILE_BYTES, &sm.full[0]);
-            // operand of T_k(k+1): my tile (k+1,k) after U_0 .. U_{k-1}
-            if (k > 0) ok = flag_wait_sys(&a.ver[(k + 1) * vs + k], base + k, ctrl);
-          }
+          early = false;
+          // operand of T_k(k+1): my tile (k+1,k) after U_0 .. U_{k-1}; buffer A is free once the diagonal update has read it
+          ok = ok && mbar_wait_bounded(&sm.done[2], pd2, ctrl);
+          pd2 ^= 1;
+          if (ok && k > 0) ok = flag_wait_sys(&a.ver[(k + 1) * vs + k], base + k, ctrl);
           if (ok) {
             fence_proxy_async();
             mbar_expect_tx(&sm.full[1], TILE_BYTES);
             bulk_g2s(A, tile(k + 1, k), TILE_BYTES, &sm.full[1]);
           }
           // W_k: to my own copy at once (my workers' panel operations wait for it); the other ranks only need it for the backward
-          // substitution, so their copies go out after the panel tile P_{k+1,k}, which the next owner's critical path waits for
+          // substitution, so their copies go out last
           ok = ok && mbar_wait_bounded(&sm.done[0], pd0, ctrl);
           pd0 ^= 1;
           if (ok) dist_push_publish(d.p, d.p.Winv, (size_t)k * TILE, W, k * vs + k, base + k + 1, -1, 1u << R);
           ok = ok && mbar_wait_bounded(&sm.done[1], pd1, ctrl);
           pd1 ^= 1;
           if (ok) {
-            dist_push_publish(d.p, d.p.S, tile_off(k + 1, k), A, (k + 1) * vs + k, base + k + 1, (k + 1) % Wd, all_ranks);
-            dist_push_publish(d.p, d.p.Winv, (size_t)k * TILE, W, k * vs + k, base + k + 1, -1, all_ranks & ~(1u << R));
+            const bool next_local = k + 1 < Tc && own(k + 1) == R;
+            if (next_local) {  // the critical path continues here: get the next diagonal tile on its way before anything is pushed
+              if (k + 1 >= 2) ok = flag_wait_sys(&a.ver[(k + 1) * vs + k + 1], base + k, ctrl);
+              if (ok) {
+                fence_proxy_async();
+                mbar_expect_tx(&sm.full[0], TILE_BYTES);
+                bulk_g2s(C, tile(k + 1, k + 1), TILE_BYTES, &sm.full[0]);
+                early = true;
+              }
+            }
+            if (ok) {
+              // the panel tile P_{k+1,k}: the next owner's critical path waits for it (served first), everybody needs it later
+              dist_push_publish(d.p, d.p.S, tile_off(k + 1, k), A, (k + 1) * vs + k, base + k + 1, (next_local || k + 1 >= Tc) ? -1 : own(k + 1), all_ranks);
+              dist_push_publish(d.p, d.p.Winv, (size_t)k * TILE, W, k * vs + k, base + k + 1, -1, all_ranks & ~(1u << R));
+            }
           }
           if (!ok) {  // timed out (here or elsewhere): release the compute warps from whichever wait they sit in
             atomicExch(&ctrl->err, 1);
@@ -1059,7 +1084,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
       }
     } else {
       unsigned pf0 = 0, pf1 = 0;
-      for (int k = R; k < Tc; k += Wd) {
+      int it = 0;
+      for (int k = 0; k < Tc; k++) {
+        if (own(k) != R) continue;
+        TilePtr W = (it++ & 1) ? sm.T[5] : sm.T[1];
+        const bool local_prev = k > 0 && own(k - 1) == R;
+        TilePtr P = local_prev ? A : Pp;
         mbar_wait(&sm.full[0], pf0);
         pf0 ^= 1;
         if (*(volatile int *)&sm.abort) break;
@@ -1069,7 +1099,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
           double acc[8][2];
 #pragma unroll
           for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
-          if (k > 0) tile_mma64<1>(Pp, Pp, acc);
+          if (k > 0) tile_mma64<1>(P, P, acc);
 #pragma unroll
           for (int q = 0; q < 8; q++)
 #pragma unroll
@@ -1082,6 +1112,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
               }
             }
         }
+        warp_arrive(&sm.done[2]);  // A / Pp / C are read: A may be refilled
         cbar();
         diag_factor(D, W, sm.fs, a.not_spd);  // ends with a barrier of the compute warps
         fence_proxy_async_smem();             // W is read by the TMA stores of the communication thread
@@ -1154,7 +1185,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
             // (all panel tiles of column k become ready together, right after W_k: the owner of column k+1, whose critical path needs
             // the first of them next, gets its copies ahead of the rest of the burst)
             dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail],
-                              (rel_v[tail] - base) % Wd, all_ranks);
+                              own(rel_v[tail] - base), all_ranks);
           } else {                 // a trailing update of one of my tiles: stays here
             __threadfence();
             st_release(&a.ver[rel_i[tail] * vs + rel_j[tail]], rel_v[tail]);
@@ -1267,15 +1298,19 @@ __global__ void __launch_bounds__(256) k_dist_reduce(DistPeers p, int Tm, int Tc
   __syncthreads();
   if (!s_ok) return;
   // flatten my columns into one index space of double2 elements, block-cyclic over the CTAs
+  auto mine = [&](int j) { return (j / p.blk) % p.world == p.rank; };
   size_t total = 0;
-  for (int j = p.rank; j < Tc; j += p.world) total += (size_t)(Tc - j + 1) * (TILE / 2);
+  for (int j = 0; j < Tc; j++)
+    if (mine(j)) total += (size_t)(Tc - j + 1) * (TILE / 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  int j = p.rank;
+  int j = 0;
+  while (j < Tc && !mine(j)) j++;
   size_t col_start = 0, col_len = j < Tc ? (size_t)(Tc - j + 1) * (TILE / 2) : 0;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     while (e >= col_start + col_len) {
       col_start += col_len;
-      j += p.world;
+      j++;
+      while (!mine(j)) j++;
       col_len = (size_t)(Tc - j + 1) * (TILE / 2);
     }
     const size_t off = dense_tile_index(Tm, j, j) * (size_t)(TILE / 2) + (e - col_start);
@@ -1357,14 +1392,15 @@ void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, 
 // ---- distributed variant ------------------------------------------------------------------------------------------------------
 // worker queue of one rank, level by level: T_k(i) for i = k+2 .. Tc when the rank owns column k, then U_k(i, j) for its columns
 // j > k (the diagonal update U_k(k+1,k+1) and T_k(k+1) belong to the critical-path CTA of the owner)
-void dense_dist_build_ops(int Tc, int rank, int world, std::vector<unsigned> *ops) {
+void dense_dist_build_ops(int Tc, int rank, int world, std::vector<unsigned> *ops, int blk) {
   ops->clear();
   auto pack = [](int type, int k, int i, int j) { return (unsigned)type << 24 | (unsigned)k << 16 | (unsigned)i << 8 | (unsigned)j; };
+  auto own = [&](int j) { return (j / blk) % world; };
   for (int k = 0; k < Tc; k++) {
-    if (k % world == rank)
+    if (own(k) == rank)
       for (int i = k + 2; i <= Tc; i++) ops->push_back(pack(0, k, i, k));
     for (int j = k + 1; j < Tc; j++) {
-      if (j % world != rank) continue;
+      if (own(j) != rank) continue;
       for (int i = (j == k + 1 ? j + 1 : j); i <= Tc; i++) ops->push_back(pack(1, k, i, j));
     }
   }

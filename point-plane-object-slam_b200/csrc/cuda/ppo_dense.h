@@ -28,12 +28,14 @@ size_t dense_x_doubles(int max_n);
 size_t dense_workspace_bytes(int max_n);
 void dense_workspace_init(void *ws, int max_n, cudaStream_t st);
 void dense_setup_device(int dev);
-// One window on several GPUs (ppo_dense.cu, "distributed factorisation"): tile column j belongs to rank j mod world.  All pointers
+// One window on several GPUs (ppo_dense.cu, "distributed factorisation"): tile column j belongs to rank (j / blk) mod world.  All pointers
 // are valid on the calling device: S / Winv / ver / sig of rank q are its peer-mapped (cudaIpc) buffers; ver = ws + 256 bytes and
 // sig = ws + 64 bytes of rank q's workspace.  `seq` numbers the solves of the window and must agree on all ranks.
 constexpr int DIST_MAX = 8;
+constexpr int DIST_BLOCK_DEFAULT = 1;
 struct DistPeers {
   int rank, world;
+  int blk;  // ownership block: tile column j belongs to rank (j / blk) mod world (the critical path crosses NVLink once per block)
   double *S[DIST_MAX];
   double *Winv[DIST_MAX];
   int *ver[DIST_MAX];
@@ -44,7 +46,7 @@ inline void dense_dist_set_peer(DistPeers *p, int q, double *S, double *Winv, vo
   p->ver[q] = reinterpret_cast<int *>(reinterpret_cast<char *>(ws) + 256);
   p->sig[q] = reinterpret_cast<int *>(reinterpret_cast<char *>(ws) + 64);
 }
-void dense_dist_build_ops(int Tc, int rank, int world, std::vector<unsigned> *ops);
+void dense_dist_build_ops(int Tc, int rank, int world, std::vector<unsigned> *ops, int blk = 1);
 // every rank has accumulated ITS partial reduced system into its own S: owner-side sum of all ranks' copies (pulled over NVLink)
 void dense_dist_reduce(const DistPeers &p, int n, int max_n, void *ws, int seq, cudaStream_t st, long long *launches, int sm_cap = 0);
 // factorisation + backward substitution; d_ops = dense_dist_build_ops(...) on the device; x is computed on every rank

@@ -25,6 +25,7 @@ using namespace ppo;
     }                                                                             \
   } while (0)
 
+static int g_blk = 1;
 static int run(int n, int world, bool virt, int reps) {
   const int max_n = n;
   const int Tm = dense_num_blocks(max_n), Tc = dense_num_blocks(n), grow = 64 * Tc;
@@ -86,7 +87,7 @@ static int run(int n, int world, bool virt, int reps) {
     CKE(cudaStreamCreate(&st[q]));
     dense_workspace_init(ws[q], max_n, st[q]);
     std::vector<unsigned> ops;
-    dense_dist_build_ops(Tc, q, world, &ops);
+    dense_dist_build_ops(Tc, q, world, &ops, g_blk);
     nops[q] = (int)ops.size();
     CKE(cudaMalloc(&dops[q], std::max<size_t>(4, ops.size() * 4)));
     CKE(cudaMemcpy(dops[q], ops.data(), ops.size() * 4, cudaMemcpyHostToDevice));
@@ -96,7 +97,7 @@ static int run(int n, int world, bool virt, int reps) {
   }
   std::vector<DistPeers> peers(world);
   for (int q = 0; q < world; q++) {
-    peers[q].rank = q, peers[q].world = world;
+    peers[q].rank = q, peers[q].world = world, peers[q].blk = g_blk;
     for (int r = 0; r < world; r++) dense_dist_set_peer(&peers[q], r, dS[r], dW[r], ws[r]);
   }
   long long launches = 0;
@@ -136,7 +137,7 @@ static int run(int n, int world, bool virt, int reps) {
         CKE(cudaMemcpy(Sq.data(), dS[q], nS * 8, cudaMemcpyDeviceToHost));
         double worst = 0;
         for (int j = 0; j < n; j++) {
-          if ((j / 64) % world != q) continue;
+          if (((j / 64) / g_blk) % world != q) continue;
           for (int i = j; i <= n; i++) {
             const size_t e = i < n ? dense_elem_index(Tm, i, j) : dense_elem_index(Tm, grow, j);
             const double want = (i < n ? A[(size_t)i * n + j] : b[j]);
@@ -216,6 +217,8 @@ int main(int argc, char **argv) {
   const int world = argc > 1 ? atoi(argv[1]) : 2;
   const bool virt = argc > 2 ? atoi(argv[2]) != 0 : true;
   dense_setup_device(0);
+  if (getenv("PPO_DIST_BLOCK")) g_blk = std::max(1, atoi(getenv("PPO_DIST_BLOCK")));
+  printf("ownership block: %d column(s)\n", g_blk);
   std::vector<int> ns;
   for (int i = 3; i < argc; i++) ns.push_back(atoi(argv[i]));
   if (ns.empty()) ns = {9, 64, 100, 384, 1000, 1644, 4000, 7794};
