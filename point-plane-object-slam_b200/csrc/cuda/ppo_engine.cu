@@ -1156,9 +1156,11 @@ static int enqueue_trial(ppo_ba_handle *h) {
                               (own && g.n_cbe) ? h->nb_cb : 0, h->d_chi_pc, (own && g.n_pce) ? h->nb_pc : 0, h->d_lm, 1, h->d_scale_part,
                               g.n_lm ? h->nb_bs : 0, own ? h->n_p : 0, h->d_not_spd, h->d_red);
   h->launches++;
-  if (h->world > 1) {  // {chi2, scale, "some rank met a non-positive pivot"}
-    if ((rc = allreduce(h, h->d_red, 3, ncclFloat64_, ncclSum_))) return rc;
+  if (h->world > 1) {  // {chi2, scale, "some rank met a non-positive pivot", "some rank saw the stop flag"}
+    k_stop_to_red<<<1, 32, 0, st>>>(h->d_stop, h->d_red);
+    if ((rc = allreduce(h, h->d_red, 4, ncclFloat64_, ncclSum_))) return rc;
     k_scalars_from_red<<<1, 32, 0, st>>>(h->d_scal, h->d_red, 2);
+    k_stop_from_red<<<1, 32, 0, st>>>(h->d_stop, h->d_red);
   }
   if (h->profiling) cudaEventRecord(h->evp[5], st);
   return PPO_OK;
@@ -1235,24 +1237,28 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
   int rc = init_mapping(h);  // (host sync 1: the sizes of the reduced system decide the launch shapes)
   if (rc) return rc;
   h->host_syncs++;
+  bool stop_at_entry = stop && *stop;
   {  // all ranks of a sharded window must take the same branch: emptiness of the UNION of the shards
     int n_l_all = h->n_l;
-    if (h->world > 1) {
-      int *d = reinterpret_cast<int *>(h->d_red + 3);
-      CK(cudaMemcpyAsync(d, &n_l_all, sizeof(int), cudaMemcpyHostToDevice, st));
-      if ((rc = allreduce(h, d, 1, ncclInt32_, ncclSum_))) return rc;
-      CK(cudaMemcpyAsync(&n_l_all, d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (h->world > 1) {  // ... and the stop flag at entry: all ranks run the same number of iterations
+      int both[2] = {n_l_all, (stop && *stop) ? 1 : 0};
+      int *d = reinterpret_cast<int *>(h->d_red + 2);
+      CK(cudaMemcpyAsync(d, both, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+      if ((rc = allreduce(h, d, 2, ncclInt32_, ncclSum_))) return rc;
+      CK(cudaMemcpyAsync(both, d, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
+      n_l_all = both[0];
+      stop_at_entry = both[1] > 0;
     }
     if (h->n_p + n_l_all == 0) return PPO_E_EMPTY;
   }
   const ppo_ba_params &P = h->P;
   LmIn &in = *h->h_lm_in;
-  in.iters = (stop && *stop) ? 0 : iters;  // SparseOptimizer::optimize tests terminate() at the loop head
+  in.iters = stop_at_entry ? 0 : iters;  // SparseOptimizer::optimize tests terminate() at the loop head
   in.max_trials = P.lm_max_trials, in.tau = P.lm_tau, in.good_upper = P.lm_good_upper, in.good_lower = P.lm_good_lower;
   in.chi_const = cpe_chi_const(h);
   CK(cudaMemcpyAsync(h->d_lm_in, h->h_lm_in, sizeof(LmIn), cudaMemcpyHostToDevice, st));
-  *h->h_stop = (stop && *stop) ? 1 : 0;
+  *h->h_stop = stop_at_entry ? 1 : 0;
   const bool graph = h->use_graph && h->world == 1 && !h->profiling;
   float ms;
   if (graph) {

@@ -1514,6 +1514,14 @@ __global__ void __launch_bounds__(256) k_max_diag(DevGraph g, Scalars *out) {
   }
   if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long *>(&out->max_diag), (unsigned long long)__double_as_longlong(sm[0]));
 }
+// sharded window: the caller's stop flag joins the per-trial all-reduce, so that every rank leaves the LM loop at the same trial
+// (red[3]: this rank's view before the reduction, the number of ranks that saw the flag after it)
+__global__ void k_stop_to_red(const volatile int *stop, double *red) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) red[3] = (stop && *stop) ? 1.0 : 0.0;
+}
+__global__ void k_stop_from_red(volatile int *stop, const double *red) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && red[3] > 0.0) *stop = 1;
+}
 // after the cross-rank reductions: copy the reduced scalars back into the Scalars block
 __global__ void k_scalars_from_red(Scalars *out, const double *red, int which) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {

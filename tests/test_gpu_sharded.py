@@ -20,6 +20,11 @@ def _worker(rank, world, uid, q, cfg_kw):
     eng = ppo.LocalBA(device=rank)
     eng.set_shard(comm, rank, world)
     eng.set_graph(gs)
+    # a stop flag that only ONE rank sees raised must stop all ranks together (it joins the entry all-reduce): no iteration anywhere, no hang
+    flag = np.array([1 if rank == world - 1 else 0], np.uint8)
+    st0 = eng.optimize(5, flag)
+    assert st0.iterations == 0, st0.iterations
+    eng.reset()
     res = eng.local_ba()
     st = eng.get_state()
     q0, q1 = ppo.sharding.plane_range(g, rank, world)
