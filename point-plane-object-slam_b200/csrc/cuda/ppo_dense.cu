@@ -279,6 +279,9 @@ __device__ __forceinline__ void blk_mma16(FA aop, FB bop, double &c0, double &c1
 }
 // barrier of the 8 compute warps (the 9th warp of the CTA only talks to the rest of the device)
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// FIRST_DONE: warp 0 has already factorised sub-block 0 (overlapped with the last trailing update of the tile, see k_chol_dataflow) and a
+// barrier of the compute warps has passed since
+template <bool FIRST_DONE = false>
 __device__ __forceinline__ void diag_factor(TilePtr D, TilePtr X, FacSmem &fs, int *not_spd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rr = lane >> 2, cc = 2 * (lane & 3);
@@ -295,11 +298,13 @@ __device__ __forceinline__ void diag_factor(TilePtr D, TilePtr X, FacSmem &fs, i
       D[r0 + rr][c0 + cc + 1] = v1;
     }
   };
-  CH_STAMP(ta0);
-  if (warp == 0) sub_factor16(D, X, 0, fs, not_spd);
-  CH_STAMP(ta1);
-  CH_ACC(4, ta0, ta1);
-  cbar();
+  if (!FIRST_DONE) {
+    CH_STAMP(ta0);
+    if (warp == 0) sub_factor16(D, X, 0, fs, not_spd);
+    CH_STAMP(ta1);
+    CH_ACC(4, ta0, ta1);
+    cbar();
+  }
   for (int s = 0; s < NB / SB; s++) {
     const int o = SB * s, R0 = o + SB;
     CH_STAMP(tb0);
@@ -527,7 +532,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dataflow(CholArgs a) {
       }
       for (int k = 0; k < Tc; k++) {
         CH_STAMP(t0);
-        diag_factor(D, W, sm.fs, a.not_spd);  // ends with a barrier of the compute warps
+        if (k == 0) diag_factor<false>(D, W, sm.fs, a.not_spd);  // ends with a barrier of the compute warps
+        else diag_factor<true>(D, W, sm.fs, a.not_spd);         // (sub-block 0 was factorised next to the update that produced the tile)
         CH_STAMP(t1);
         {  // W_k to global memory (tile layout, so that workers fetch it with one bulk copy)
           double *Wg = a.Winv + (size_t)k * TILE;
@@ -568,21 +574,39 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dataflow(CholArgs a) {
         cbar();  // P is complete in shared memory
         // U_k(k+1,k+1) on the next diagonal tile, which then stays in shared memory for F_{k+1}
         {
+          // Look-ahead: warp 0 updates the first 16 x 16 sub-block alone (3 of the 36 lower 8 x 8 blocks) and goes straight on to
+          // factorise it -- the serial part of F_{k+1} -- while warps 1..7 update the other 33 blocks.
           const int nb2 = min(NB, a.n - NB * (k + 1));
+          const int rr = lane >> 2, kk = lane & 3;
+          auto upd_block = [&](int rb, int cb) {  // D(rb, cb) = C - sum_m A[m][rb..] A[m][cb..]  (+ mirror), identity beyond the valid size
+            double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-          for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
-          tile_mma64<1>(A, A, acc);
-#pragma unroll
-          for (int q = 0; q < 8; q++)
+            for (int m0 = 0; m0 < NB; m0 += 4) dmma(c0, c1, A[m0 + kk][8 * rb + rr], A[m0 + kk][8 * cb + rr]);
+            const int r = 8 * rb + rr;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-              const int jl = q * 8 + jc + h;
-              if (il >= jl) {
-                const double v = (il < nb2 && jl < nb2) ? C[jl][il] - acc[q][h] : (il == jl ? 1.0 : 0.0);
-                D[jl][il] = v;
-                D[il][jl] = v;
+              const int c = 8 * cb + jc + h;
+              if (r >= c) {
+                const double v = (r < nb2 && c < nb2) ? C[c][r] - (h ? c1 : c0) : (r == c ? 1.0 : 0.0);
+                D[c][r] = v;
+                D[r][c] = v;
               }
             }
+          };
+          if (warp == 0) {
+            upd_block(0, 0);
+            upd_block(1, 0);
+            upd_block(1, 1);
+            __syncwarp();
+            sub_factor16(D, W, 0, sm.fs, a.not_spd);
+          } else {
+            for (int u = warp - 1; u < 33; u += 7) {  // row blocks 2 .. 7, column blocks 0 .. rb
+              int rb = 2, rem = u;
+              while (rem > rb) rem -= ++rb;
+              upd_block(rb, rem);
+            }
+          }
+          (void)acc;
         }
         warp_arrive(&sm.done[2]);  // A and C may be refilled
         cbar();
@@ -1094,27 +1118,45 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
         pf0 ^= 1;
         if (*(volatile int *)&sm.abort) break;
         for (int e = tid; e < TILE; e += 256) (&W[0][0])[e] = 0.0;
-        {  // D = C - P P^T (last update of the diagonal tile), symmetric, identity beyond the valid size
+        {  // D = C - P P^T (last update of the diagonal tile), symmetric, identity beyond the valid size; as in k_chol_dataflow warp 0
+           // updates the first 16 x 16 sub-block alone and factorises it while the other warps update the rest
           const int nb = min(NB, a.n - NB * k);
-          double acc[8][2];
+          const int rr = lane >> 2, kk = lane & 3;
+          auto upd_block = [&](int rb, int cb) {
+            double c0 = 0.0, c1 = 0.0;
+            if (k > 0) {
 #pragma unroll
-          for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
-          if (k > 0) tile_mma64<1>(P, P, acc);
-#pragma unroll
-          for (int q = 0; q < 8; q++)
+              for (int m0 = 0; m0 < NB; m0 += 4) dmma(c0, c1, P[m0 + kk][8 * rb + rr], P[m0 + kk][8 * cb + rr]);
+            }
+            const int r = 8 * rb + rr;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-              const int jl = q * 8 + jc + h;
-              if (il >= jl) {
-                const double v = (il < nb && jl < nb) ? C[jl][il] - acc[q][h] : (il == jl ? 1.0 : 0.0);
-                D[jl][il] = v;
-                D[il][jl] = v;
+              const int c = 8 * cb + jc + h;
+              if (r >= c) {
+                const double v = (r < nb && c < nb) ? C[c][r] - (h ? c1 : c0) : (r == c ? 1.0 : 0.0);
+                D[c][r] = v;
+                D[r][c] = v;
               }
             }
+          };
+          cbar();  // W is zero everywhere before warp 0 writes into it
+          if (warp == 0) {
+            upd_block(0, 0);
+            upd_block(1, 0);
+            upd_block(1, 1);
+            __syncwarp();
+            sub_factor16(D, W, 0, sm.fs, a.not_spd);
+          } else {
+            for (int u = warp - 1; u < 33; u += 7) {
+              int rb = 2, rem = u;
+              while (rem > rb) rem -= ++rb;
+              upd_block(rb, rem);
+            }
+          }
         }
         warp_arrive(&sm.done[2]);  // A / Pp / C are read: A may be refilled
         cbar();
-        diag_factor(D, W, sm.fs, a.not_spd);  // ends with a barrier of the compute warps
+        diag_factor<true>(D, W, sm.fs, a.not_spd);  // ends with a barrier of the compute warps
         fence_proxy_async_smem();             // W is read by the TMA stores of the communication thread
         warp_arrive(&sm.done[0]);
         mbar_wait(&sm.full[1], pf1);
