@@ -111,6 +111,13 @@ struct Flat {
   std::vector<float> kf_intr, pe_obs, pe_invsigma2;
   std::vector<int32_t> pt_rowptr, pe_kf, ple_plane, ple_kf, cbe_kf, cbe_cuboid, pce_cuboid, pce_rowptr, cpe_cuboid, cpe_plane;
   ppo_ba_graph g;
+  // empties the arrays but keeps their memory: a steady-state call then touches no fresh pages (30 MB for a 200-key-frame window)
+  void clear() {
+    for (auto *v : {&kf_pose, &pt_xyz, &pl_coef, &cu_state, &ple_meas, &ple_info, &cbe_meas, &cbe_info, &pce_pts, &cpe_meas, &cpe_info}) v->clear();
+    for (auto *v : {&kf_fixed, &pt_fixed, &cu_flags, &ple_kind, &cbe_kind}) v->clear();
+    for (auto *v : {&kf_intr, &pe_obs, &pe_invsigma2}) v->clear();
+    for (auto *v : {&pt_rowptr, &pe_kf, &ple_plane, &ple_kf, &cbe_kf, &cbe_cuboid, &pce_cuboid, &pce_rowptr, &cpe_cuboid, &cpe_plane}) v->clear();
+  }
   void publish() {
     std::memset(&g, 0, sizeof g);
     g.n_kf = (int32_t)kf_fixed.size(); g.kf_pose = kf_pose.data(); g.kf_fixed = kf_fixed.data(); g.kf_intr = kf_intr.data();
@@ -174,7 +181,7 @@ using namespace ORB_SLAM2;
 // mvKeysUn / mvuRight / mvInvLevelSigma2 per observation: consecutive windows share almost all of their points.
 struct ObsRec {
   KeyFrame *kf;
-  uint32_t idx;
+  uint32_t idx, kf_id;  // feature index in the key-frame; KeyFrame::mnId (so that flattening needs no pointer chase per observation)
   float u, v, ur, inv_sigma2;
 };
 struct Mirror {
@@ -226,10 +233,11 @@ struct Mirror {
       KeyFrame *pKFi = mit.first;
       const size_t idx = mit.second;
       const cv::KeyPoint &kpUn = pKFi->mvKeysUn[idx];
-      pool.push_back({pKFi, (uint32_t)idx, kpUn.pt.x, kpUn.pt.y, pKFi->mvuRight[idx] < 0 ? -1.0f : pKFi->mvuRight[idx], pKFi->mvInvLevelSigma2[kpUn.octave]});
+      pool.push_back({pKFi, (uint32_t)idx, (uint32_t)pKFi->mnId, kpUn.pt.x, kpUn.pt.y, pKFi->mvuRight[idx] < 0 ? -1.0f : pKFi->mvuRight[idx],
+                      pKFi->mvInvLevelSigma2[kpUn.octave]});
     }
     // key-frame slots of a window are ordered by mnId, so rows sorted by mnId come out in edge order
-    std::sort(pool.begin() + r.off, pool.end(), [](const ObsRec &a, const ObsRec &b) { return a.kf->mnId < b.kf->mnId; });
+    std::sort(pool.begin() + r.off, pool.end(), [](const ObsRec &a, const ObsRec &b) { return a.kf_id < b.kf_id; });
     live += r.n;
     return r;
   }
@@ -319,7 +327,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
 
   // ---- stage B: flatten (vertices) ------------------------------------------------------------------
   Flat &F = S.last;
-  F = Flat();
+  F.clear();
   // key-frame slots ordered by mnId = g2o's Hessian order (core/sparse_optimizer.cpp:166-190,482-487)
   struct Slot { KeyFrame *kf; bool fixed; };
   std::vector<Slot> slots;
@@ -330,9 +338,11 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   long unsigned int max_id = 0;
   for (const Slot &sl : slots) max_id = std::max(max_id, sl.kf->mnId);
   std::vector<int> slot_of_id(slots.empty() ? 0 : max_id + 1, -1);  // O(1) key-frame -> slot for the 10^5..10^6 point edges
+  std::vector<char> slot_bad(slots.size(), 0);
   for (size_t i = 0; i < slots.size(); i++) {
     kf_slot[slots[i].kf] = (int)i;
     slot_of_id[slots[i].kf->mnId] = (int)i;
+    slot_bad[i] = slots[i].kf->isBad();
     float T[16];
     double p7[7];
     mat_to_float16(slots[i].kf->GetPose(), T);
@@ -420,6 +430,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   F.pt_xyz.reserve(3 * w.lLocalMapPoints.size()); F.pt_fixed.reserve(w.lLocalMapPoints.size()); F.pt_rowptr.reserve(w.lLocalMapPoints.size() + 1);
   graph_points.reserve(w.lLocalMapPoints.size());
   F.pt_rowptr.push_back(0);
+  tick("  B: point arrays sized");
   for (size_t ip = 0; ip < w.lLocalMapPoints.size(); ip++) {
     MapPoint *pMP = w.lLocalMapPoints[ip];
     if (mixed && pMP->Observations() == 1) continue;  // :2336
@@ -431,9 +442,9 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     for (uint32_t q = 0; q < w.obs_row[ip].second; q++) {
       const ObsRec &o = row[q];
       KeyFrame *pKFi = o.kf;
-      if (pKFi->isBad() || pKFi->mnId >= slot_of_id.size()) continue;
-      const int sl = slot_of_id[pKFi->mnId];
-      if (sl < 0 || slots[sl].kf != pKFi) continue;
+      if (o.kf_id >= slot_of_id.size()) continue;
+      const int sl = slot_of_id[o.kf_id];
+      if (sl < 0 || slots[sl].kf != pKFi || slot_bad[sl]) continue;  // (!pKFi->isBad(), :2352, read once per key-frame)
       F.pe_kf[ne] = sl;
       F.pe_obs[3 * ne] = o.u, F.pe_obs[3 * ne + 1] = o.v, F.pe_obs[3 * ne + 2] = o.ur;
       F.pe_invsigma2[ne] = o.inv_sigma2;
@@ -664,7 +675,7 @@ static void run_global(const std::vector<KeyFrame *> &vpKFs, const std::vector<M
   g_last_slot = &S;
   std::lock_guard<std::mutex> lk(S.m);
   Flat &F = S.last;
-  F = Flat();
+  F.clear();
   // key-frame vertices :73-86, slots ordered by mnId = g2o's Hessian order
   std::vector<KeyFrame *> kfs;
   for (KeyFrame *pKF : vpKFs)
@@ -786,7 +797,7 @@ static int run_pose(Frame *pFrame) {
   g_last_slot = &S;
   std::lock_guard<std::mutex> lk(S.m);
   Flat &F = S.last;
-  F = Flat();
+  F.clear();
   {
     float T[16];
     double p7[7];
