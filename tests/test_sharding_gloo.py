@@ -105,3 +105,34 @@ def test_point_slices_balance_edges():
         assert max(edges) - min(edges) <= 12  # one point's edges at most
         parts = [ppo.sharding.shard_graph(g, r, world)[0] for r in range(world)]
         assert sum(p.c.n_pe for p in parts) == g.c.n_pe and sum(p.c.n_pt for p in parts) == 999
+
+
+def test_landmark_partition_is_exact():
+    """shard_graph partitions the landmarks: every point edge, plane, plane edge and cuboid-plane edge goes to exactly one rank (planes balanced
+    by their Schur pair count), key-frames / cuboids / camera-cuboid / point-cuboid edges are replicated."""
+    sys.path.insert(0, ROOT)
+    from ppo_pkg import ppo
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=20, n_fixed=3, n_pt=1500, n_pl=13, n_cu=4))
+    for world in (1, 2, 3, 8):
+        parts = [ppo.sharding.shard_graph(g, r, world)[0] for r in range(world)]
+        ranges = [ppo.sharding.plane_range(g, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == g.c.n_pl and all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:]))
+        assert sum(p.c.n_pl for p in parts) == g.c.n_pl and sum(p.c.n_ple for p in parts) == g.c.n_ple
+        assert sum(p.c.n_cpe for p in parts) == g.c.n_cpe and sum(p.c.n_pe for p in parts) == g.c.n_pe
+        for r, p in enumerate(parts):
+            q0, q1 = ranges[r]
+            assert p.c.n_pl == q1 - q0 and np.array_equal(p["pl_coef"], g["pl_coef"][q0:q1])
+            if p.c.n_ple:
+                assert p["ple_plane"].min() >= 0 and p["ple_plane"].max() < p.c.n_pl
+                m = (g["ple_plane"] >= q0) & (g["ple_plane"] < q1)
+                assert np.array_equal(p["ple_meas"], g["ple_meas"][m]) and np.array_equal(p["ple_kf"], g["ple_kf"][m])
+            if p.c.n_cpe:
+                assert p["cpe_plane"].min() >= 0 and p["cpe_plane"].max() < p.c.n_pl
+            # replicated parts
+            assert p.c.n_kf == g.c.n_kf and p.c.n_cu == g.c.n_cu and p.c.n_cbe == g.c.n_cbe and p.c.n_pce == g.c.n_pce
+        if world > 1:  # balance by pair count: no rank carries more than its share plus one plane's pairs
+            u = np.unique(np.stack([g["ple_plane"], g["ple_kf"]], 1), axis=0)
+            k = np.bincount(u[:, 0], minlength=g.c.n_pl).astype(np.int64)
+            cost = k * (k + 1) // 2
+            loads = [int(cost[a:b].sum()) for a, b in ranges]
+            assert max(loads) <= cost.sum() / world + cost.max()
