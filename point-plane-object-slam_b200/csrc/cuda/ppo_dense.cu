@@ -20,7 +20,19 @@
 // that were claimed before it, by CTAs that are therefore running -- the kernel cannot deadlock whatever number of CTAs
 // is resident, and it needs no cooperative launch.  Workers prefetch the operands of their next operation while the
 // current one runs on the tensor cores (DMMA).  Every wait is bounded: on a time-out the kernel raises ctrl->err, all
-// CTAs leave, and the solve counts as failed.
+// CTAs leave, and the solve counts as failed (the back-substitution kernel clears the flag for the next solve).
+//
+// What was measured on the way (tools/ubench/chol_test[_t]; n = 1644 is latency-bound by the 26-panel chain, n = 7794 throughput-bound):
+//   * a 9th warp per CTA that does all the talking (claims, counter polls, TMA issue, publication)      0.454 -> 0.445 ms, 11.9 -> 10.1 ms
+//   * warp 0 updates + factorises the first 16 x 16 sub-block of the next diagonal tile while warps 1..7
+//     finish the tile's last trailing update                                                             0.445 -> 0.415 ms
+//   * workers at n = 7794 spend 2700 of 8500 cycles per operation waiting for operands and 5750 computing + storing (4096 = the DMMA
+//     time of a 64^3 product).  Tried and dropped: claiming runs of entries that share their column operand (a third less operand
+//     traffic: 10.0 -> 9.9 ms, 1.70 -> 1.93 at n = 4000), a communication thread that runs ahead of the buffer ring (9.7 ms without the
+//     device-scope fence before the release, which racecheck does not accept; 10.4 with it), three buffer sets with the target tile read
+//     straight into registers (waiting 1900, computing 7500: 11.0 ms).
+//
+// The second half of the file spreads the same factorisation over the GPUs of a node (k_chol_dist and friends).
 #include <cuda_runtime.h>
 
 #include <algorithm>
