@@ -1415,12 +1415,12 @@ int ppo_ba_edge_chi2(ppo_ba_handle *h, int kind, double *chi2, unsigned char *de
   if (depth_positive) {
     if (kind == PPO_EDGE_POINT || kind == PPO_EDGE_PLANE) {
       unsigned char *d = nullptr;
-      CK(cudaMalloc((void **)&d, n));
+      CK(cudaMallocAsync((void **)&d, n, h->st));  // stream-ordered pool: no OS call in the steady state
       k_depth_flags<<<cdiv(n, 256), 256, 0, h->st>>>(g, h->sa, kind, d);
       h->launches++;
       cudaError_t e = cudaMemcpyAsync(depth_positive, d, n, cudaMemcpyDeviceToHost, h->st);
+      cudaFreeAsync(d, h->st);
       cudaStreamSynchronize(h->st);
-      cudaFree(d);
       CK(e);
     } else {
       std::memset(depth_positive, 1, n);

@@ -81,19 +81,36 @@ __global__ void k_mark_active_cpe(DevGraph g, const int *cpe_cuboid, const int *
     g.pl_act[cpe_plane[i]] = 1;
   }
 }
+// compacts the free active key-frames and the active cuboids into the pose block [key-frames by slot | cuboids]: one warp, ballot + popc
+// prefix sums over 32 vertices per step (launched <<<1, 32>>>)
 __global__ void k_build_index(DevGraph g) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    int nb = 0;
-    for (int i = 0; i < g.n_kf; i++) g.kf_idx[i] = (g.kf_act[i] && !g.kf_fixed[i]) ? nb++ : -1;
-    int off = 6 * nb;
-    for (int i = 0; i < g.n_cu; i++) {
-      g.cu_off[i] = g.cu_act[i] ? off : -1;
-      if (g.cu_act[i]) off += 9;
-    }
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  const unsigned below = (1u << lane) - 1u;
+  int nb = 0;
+  for (int i0 = 0; i0 < g.n_kf; i0 += 32) {
+    const int i = i0 + lane;
+    const bool on = i < g.n_kf && g.kf_act[i] && !g.kf_fixed[i];
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (i < g.n_kf) g.kf_idx[i] = on ? nb + __popc(m & below) : -1;
+    nb += __popc(m);
+  }
+  int off = 6 * nb;
+  for (int i0 = 0; i0 < g.n_cu; i0 += 32) {
+    const int i = i0 + lane;
+    const bool on = i < g.n_cu && g.cu_act[i];
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (i < g.n_cu) g.cu_off[i] = on ? off + 9 * __popc(m & below) : -1;
+    off += 9 * __popc(m);
+  }
+  int nl = 0;
+  for (int i0 = 0; i0 < g.n_pl; i0 += 32) {
+    const int i = i0 + lane;
+    nl += __popc(__ballot_sync(0xffffffffu, i < g.n_pl && g.pl_act[i] != 0));
+  }
+  if (lane == 0) {
     g.dims[0] = nb;
     g.dims[1] = off;
-    int nl = 0;
-    for (int i = 0; i < g.n_pl; i++) nl += g.pl_act[i] != 0;
     g.dims[2] = nl;  // active planes; active points are counted by k_entry_pidx
     g.dims[3] = 0;
     g.dims[4] = 0;
