@@ -60,8 +60,12 @@ enum ppo_edge_kind {
 #define PPO_EF_LEVEL1 1u /* edge->setLevel(1): inactive in optimize() of level 0      */
 #define PPO_EF_ROBUST 2u /* a RobustKernelHuber is attached                            */
 
-/* Solver flavour: which g2o stack the call mirrors. Both run the same dense Cholesky of the
- * Schur-reduced pose system on the GPU; the value is recorded in the stats for reporting. */
+/* Solver flavour: which g2o stack the call mirrors.  Both factorise the Schur-reduced pose system with the same
+ * dense tile Cholesky on the GPU.  They differ where the reference's linear solvers differ: LinearSolverDense
+ * (Eigen::LDLT + isPositive(), solvers/linear_solver_dense.h:65-113) reports a failed solve on a system that is not
+ * positive definite; LinearSolverEigen (Eigen::SimplicialLDLT, solvers/linear_solver_eigen.h:94-124) is an LDL^T
+ * without pivoting that fails only on a zero pivot -- for PPO_SOLVER_6_3 a failed Cholesky is followed by such an
+ * LDL^T on a copy of the system. */
 #define PPO_SOLVER_DENSE_X 0 /* BlockSolverX + LinearSolverDense   (Optimizer.cc:2108-2113) */
 #define PPO_SOLVER_6_3 1     /* BlockSolver_6_3 + LinearSolverEigen (Optimizer.cc:516-522)   */
 
@@ -295,6 +299,11 @@ int ppo_ba_debug_linearize(ppo_ba_handle *h, int32_t dims[2], double *Hpp, doubl
 /* After debug_linearize: damped Schur system and its solution for a given lambda. */
 int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, double *bschur,
                        double *x, int32_t *ok);
+/* The linear solver of the handle's stack alone, on a caller-supplied dense symmetric system (A: n x n row-major, upper
+ * triangle used): LinearSolver::solve(A, x, b).  PPO_SOLVER_DENSE_X = LinearSolverDense (solvers/linear_solver_dense.h:65-113:
+ * *ok = 0 unless A is positive definite); PPO_SOLVER_6_3 = LinearSolverEigen (solvers/linear_solver_eigen.h:94-124: LDL^T
+ * without pivoting, *ok = 0 only on a zero pivot, so an indefinite A is solved).  Does not need or touch a resident window. */
+int ppo_ba_debug_dense_solve(ppo_ba_handle *h, int32_t n, const double *A_upper, const double *b, double *x, int32_t *ok);
 
 /* -- multi-GPU: one window, landmarks sharded over ranks ------------------------ */
 /* Call before ppo_ba_set_graph, on every rank (one process per GPU of ONE node; world <= 8 for the

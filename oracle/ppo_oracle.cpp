@@ -682,7 +682,11 @@ struct ppo_oracle_handle {
   // ---- dense LDLT (solvers/linear_solver_dense.h:65-113: Eigen::LDLT, fail if !isPositive) -------
   // Unpivoted LDL^T on the mirrored upper triangle; for SPD input it is the same decomposition
   // up to rounding as Eigen's pivoted one.  Returns false if a pivot is <= 0.
+  // PPO_SOLVER_6_3 = LinearSolverEigen (solvers/linear_solver_eigen.h:94-124): Eigen::SimplicialLDLT, an LDL^T without pivoting
+  // whose numeric factorisation only fails on a pivot that is exactly zero -- an indefinite system is solved, not rejected.  (Its
+  // fill-reducing ordering changes the rounding of the result, not the result.)
   bool dense_solve(std::vector<double> &A, const double *rhs, double *sol) {
+    const bool eigen_flavour = P.solver == PPO_SOLVER_6_3;
     const int n = n_p;
     // work on lower triangle, row-major: L(i,j) j<i stored in A[i*n+j]
     for (int i = 0; i < n; i++)
@@ -695,7 +699,7 @@ struct ppo_oracle_handle {
         tmp[k] = Aj[k] * d[k];
         dj -= Aj[k] * tmp[k];
       }
-      if (!(dj > 0.0)) return false;
+      if (eigen_flavour ? dj == 0.0 : !(dj > 0.0)) return false;
       d[j] = dj;
       double inv = 1.0 / dj;
 #pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1 && n - j > 64)
@@ -1372,11 +1376,14 @@ int ppo_oracle_cuboid_cam_edge(int kind, const double pose[7], const double c[10
   return cuboid_cam_error(kind, se3_in(pose), cu_in(c), K, meas, err);
 }
 // dense LDLT KAT: A is n x n row-major symmetric (upper used)
-int ppo_oracle_dense_solve(int n, const double *A, const double *rhs, double *sol) {
+// the same with the linear solver of the given stack: PPO_SOLVER_DENSE_X = LinearSolverDense, PPO_SOLVER_6_3 = LinearSolverEigen
+int ppo_oracle_dense_solve_flavour(int solver, int n, const double *A, const double *rhs, double *sol) {
   ppo_oracle_handle h;
+  h.P.solver = solver;
   h.n_p = n;
   std::vector<double> M(A, A + (size_t)n * n);
   return h.dense_solve(M, rhs, sol) ? 1 : 0;
 }
+int ppo_oracle_dense_solve(int n, const double *A, const double *rhs, double *sol) { return ppo_oracle_dense_solve_flavour(PPO_SOLVER_DENSE_X, n, A, rhs, sol); }
 
 }  // extern "C"

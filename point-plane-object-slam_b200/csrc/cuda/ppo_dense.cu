@@ -1443,6 +1443,53 @@ void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, 
   (*launches) += 2;
 }
 
+// ---- LinearSolverEigen flavour: the solve of an INDEFINITE reduced system ---------------------------------------------------------
+// LinearSolverEigen::solve (Thirdparty/g2o/g2o/solvers/linear_solver_eigen.h:94-124) factorises with Eigen::SimplicialLDLT, an LDL^T
+// WITHOUT pivoting that reports failure only on a pivot that is exactly zero: on an indefinite system it still returns the solution,
+// where LinearSolverDense (Eigen::LDLT + isPositive()) and the tile Cholesky above report a failed solve.  Windows of the
+// BlockSolver_6_3 / LinearSolverEigen stack (PPO_SOLVER_6_3) therefore keep a copy of the reduced system and, when the Cholesky has
+// raised not_spd (or timed out), this kernel redoes the solve on the copy as a right-looking LDL^T in natural order (the fill-reducing
+// ordering of the reference changes the rounding, not the solution).  The damped systems LM produces are positive definite, so this is
+// the exceptional path: one CTA, one block barrier per column, no attempt at speed; it leaves at once when not_spd is clear.
+// The gradient row rides along as row n, exactly as in the Cholesky: after column j it holds y = L^-1 b.
+__global__ void __launch_bounds__(1024) k_ldlt_fallback(double *M, int Tm, int n, int Tc, double *x, int *not_spd) {
+  if (*(volatile int *)not_spd == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grow = NB * Tc;
+  for (int j = 0; j < n; j++) {
+    const double d = M[dense_elem_index(Tm, j, j)];
+    if (d == 0.0) return;  // SimplicialLDLT: "failure, D(k,k) is zero" -- not_spd stays set, the step is rejected
+    const double inv = 1.0 / d;
+    const double gj = M[dense_elem_index(Tm, grow, j)];
+    for (int k = j + 1 + warp; k < n; k += 32) {
+      const double lk = M[dense_elem_index(Tm, k, j)] * inv;
+      for (int i = k + lane; i < n; i += 32) M[dense_elem_index(Tm, i, k)] -= M[dense_elem_index(Tm, i, j)] * lk;
+      if (lane == 0) M[dense_elem_index(Tm, grow, k)] -= gj * lk;
+    }
+    __syncthreads();
+  }
+  // x <- D^-1 y, columns of L scaled, then the backward substitution L^T x = D^-1 y column by column
+  for (int j = warp; j < n; j += 32) {
+    const double inv = 1.0 / M[dense_elem_index(Tm, j, j)];
+    for (int i = j + 1 + lane; i < n; i += 32) M[dense_elem_index(Tm, i, j)] *= inv;
+    if (lane == 0) x[j] = M[dense_elem_index(Tm, grow, j)] * inv;
+  }
+  for (int i = n + tid; i < NB * Tc; i += 1024) x[i] = 0.0;
+  __syncthreads();
+  for (int k = n - 1; k > 0; k--) {
+    const double xk = x[k];
+    for (int i = tid; i < k; i += 1024) x[i] -= M[dense_elem_index(Tm, k, i)] * xk;
+    __syncthreads();
+  }
+  if (tid == 0) *not_spd = 0;
+}
+size_t dense_used_doubles(int n, int max_n) { return dense_tile_index(dense_num_blocks(max_n), dense_num_blocks(n), dense_num_blocks(n)) * (size_t)TILE; }
+void dense_ldlt_fallback(double *S_copy, int n, int max_n, double *x, int *not_spd, cudaStream_t st, long long *launches) {
+  if (n <= 0) return;
+  k_ldlt_fallback<<<1, 1024, 0, st>>>(S_copy, dense_num_blocks(max_n), n, dense_num_blocks(n), x, not_spd);
+  (*launches)++;
+}
+
 // ---- distributed variant ------------------------------------------------------------------------------------------------------
 // worker queue of one rank, level by level: T_k(i) for i = k+2 .. Tc when the rank owns column k, then U_k(i, j) for its columns
 // j > k (the diagonal update U_k(k+1,k+1) and T_k(k+1) belong to the critical-path CTA of the owner)

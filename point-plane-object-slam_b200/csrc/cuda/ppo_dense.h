@@ -22,6 +22,11 @@ __host__ __device__ inline size_t dense_elem_index(int Tm, int r, int c) {
 // Winv: dense_num_blocks(max_n) * DENSE_TILE doubles; ws: dense_workspace_bytes(max_n), initialised once by dense_workspace_init.
 // sm_cap > 0 limits the persistent factorisation to that many CTAs (windows solved side by side share the SMs).
 void dense_cholesky_solve(double *S, int n, int max_n, double *x, double *Winv, void *ws, int *not_spd, cudaStream_t st, long long *launches, int sm_cap = 0);
+// LinearSolverEigen flavour (solvers/linear_solver_eigen.h:94-124): S_copy = the first dense_used_doubles(n, max_n) doubles of S as they
+// were BEFORE dense_cholesky_solve; if that solve raised *not_spd the system is solved again by an unpivoted LDL^T (fails only on a zero
+// pivot, like Eigen::SimplicialLDLT), x is overwritten and *not_spd cleared.  No-op (one empty launch) otherwise.
+void dense_ldlt_fallback(double *S_copy, int n, int max_n, double *x, int *not_spd, cudaStream_t st, long long *launches);
+size_t dense_used_doubles(int n, int max_n);
 int dense_num_blocks(int n);
 size_t dense_matrix_doubles(int max_n);
 size_t dense_x_doubles(int max_n);

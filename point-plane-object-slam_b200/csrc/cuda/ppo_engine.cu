@@ -110,6 +110,7 @@ struct ppo_ba_handle {
   Scalars *d_scal = nullptr, *h_scal = nullptr;
   int *d_not_spd = nullptr, *d_nout = nullptr;
   double *d_Winv = nullptr;
+  double *d_S_bak = nullptr;   // PPO_SOLVER_6_3 (LinearSolverEigen semantics): the reduced system as it was before the Cholesky, for dense_ldlt_fallback
   void *d_dense_ws = nullptr;  // control block + tile version counters of the persistent factorisation
   int *h_dims = nullptr;
   // current mapping
@@ -360,6 +361,10 @@ int ppo_ba_set_params(ppo_ba_handle *h, const ppo_ba_params *params) {
     g.huber_bbox = h->P.huber_bbox; g.huber_corner = h->P.huber_corner; g.huber_se3 = h->P.huber_se3;
     g.ptcu_ratio = h->P.ptcu_max_outside_margin_ratio; g.ptcu_prior = h->P.ptcu_prior_weight;
     h->drop_lm_graphs();  // the captured kernels hold the old constants by value
+    if (h->P.solver == PPO_SOLVER_6_3 && !h->d_S_bak && !h->dist_solve) {
+      int rc = h->dalloc(&h->d_S_bak, dense_matrix_doubles(h->max_np));
+      if (rc) return rc;
+    }
   }
   return PPO_OK;
 }
@@ -823,6 +828,8 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   h->nb_bs = cdiv(g.n_pl, BS_WARPS) + g.n_units;  // partial sums of k_backsub (planes) + k_backsub_points
   DA(h->d_chi_pt, (size_t)std::max(h->nb_lin, h->nb_res)); DA(h->d_chi_pl, (size_t)h->nb_pl); DA(h->d_chi_cb, (size_t)h->nb_cb); DA(h->d_chi_pc, (size_t)h->nb_pc);
   DA(h->d_scale_part, (size_t)h->nb_bs);
+  h->d_S_bak = nullptr;
+  if (!h->dist_solve && h->P.solver == PPO_SOLVER_6_3) DA(h->d_S_bak, dense_matrix_doubles(h->max_np));
   if (!h->dist_solve) {
     DA(h->d_Winv, (size_t)dense_num_blocks(h->max_np) * DENSE_TILE);
     char *ws = nullptr;
@@ -1111,7 +1118,11 @@ static int enqueue_dense_solve(ppo_ba_handle *h) {
     }
     dense_cholesky_solve_dist(h->dist_peers, h->n_p, h->max_np, g.xp, h->d_dense_ws, h->d_not_spd, h->d_dist_ops, h->dist_n_ops, h->dist_seq, h->st, &h->launches);
   } else {
+    // LinearSolverEigen (solvers/linear_solver_eigen.h:94-124) also solves indefinite systems: keep the system, redo it by LDL^T if the Cholesky fails
+    const bool eigen_flavour = h->P.solver == PPO_SOLVER_6_3 && h->d_S_bak != nullptr;
+    if (eigen_flavour) CK(cudaMemcpyAsync(h->d_S_bak, g.S, 8 * dense_used_doubles(h->n_p, h->max_np), cudaMemcpyDeviceToDevice, h->st));
     dense_cholesky_solve(g.S, h->n_p, h->max_np, g.xp, h->d_Winv, h->d_dense_ws, h->d_not_spd, h->st, &h->launches, h->solve_sm_cap);
+    if (eigen_flavour) dense_ldlt_fallback(h->d_S_bak, h->n_p, h->max_np, g.xp, h->d_not_spd, h->st, &h->launches);
   }
   return PPO_OK;
 }
@@ -1223,7 +1234,10 @@ static int build_lm_graph(ppo_ba_handle *h, ppo_ba_handle::LmGraph *out) {
   h->launches = l0;  // nothing ran yet: launches are counted per replay
   out->graph = G;
   out->nodes_iter = (int)(l1 - l0), out->nodes_trial = (int)(l2 - l1);
+  static const bool timing = std::getenv("PPO_BA_TIMING") != nullptr;
+  const auto ti0 = std::chrono::steady_clock::now();
   CK(cudaGraphInstantiate(&out->exec, G, 0));
+  if (timing) std::fprintf(stderr, "[build_lm_graph] instantiate %8.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ti0).count());
   return PPO_OK;
 }
 
@@ -1268,7 +1282,10 @@ int ppo_ba_optimize(ppo_ba_handle *h, int iters, const volatile unsigned char *s
     if (!G) {
       ppo_ba_handle::LmGraph q;
       q.n_p = h->n_p, q.n_l = h->n_l, q.sm_cap = h->solve_sm_cap;
+      static const bool timing = std::getenv("PPO_BA_TIMING") != nullptr;
+      const auto tb0 = std::chrono::steady_clock::now();
       if ((rc = build_lm_graph(h, &q))) return rc;
+      if (timing) std::fprintf(stderr, "[ppo_ba_optimize] build_lm_graph %8.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count());
       h->lm_graphs.push_back(q);
       G = &h->lm_graphs.back();
     }
@@ -1728,6 +1745,48 @@ int ppo_ba_debug_solve(ppo_ba_handle *h, double lambda, double *Hschur_upper, do
     }
   }
 #undef DL
+  return PPO_OK;
+}
+
+int ppo_ba_debug_dense_solve(ppo_ba_handle *h, int32_t n, const double *A_upper, const double *b, double *x, int32_t *ok) {
+  if (!h || n <= 0 || !A_upper || !b || !x) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int Tm = dense_num_blocks(n), grow = 64 * Tm;
+  const size_t nS = dense_matrix_doubles(n);
+  std::vector<double> S(nS, 0.0);
+  for (int j = 0; j < n; j++) {  // lower (i, j) of the tiled storage = upper (j, i) of the caller's matrix
+    for (int i = j; i < n; i++) S[dense_elem_index(Tm, i, j)] = A_upper[(size_t)j * n + i];
+    S[dense_elem_index(Tm, grow, j)] = b[j];
+  }
+  double *dS = nullptr, *dBak = nullptr, *dx = nullptr, *dW = nullptr;
+  void *ws = nullptr;
+  int *dns = nullptr;
+  auto release = [&] { cudaFree(dS), cudaFree(dBak), cudaFree(dx), cudaFree(dW), cudaFree(ws), cudaFree(dns); };
+  const bool eigen_flavour = h->P.solver == PPO_SOLVER_6_3;
+  cudaError_t e = cudaMalloc((void **)&dS, nS * 8);
+  if (e == cudaSuccess && eigen_flavour) e = cudaMalloc((void **)&dBak, nS * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dx, dense_x_doubles(n) * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dW, (size_t)Tm * DENSE_TILE * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&ws, dense_workspace_bytes(n));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dns, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(dns, 0, sizeof(int), h->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dS, S.data(), nS * 8, cudaMemcpyHostToDevice, h->st);
+  if (e == cudaSuccess && eigen_flavour) e = cudaMemcpyAsync(dBak, dS, 8 * dense_used_doubles(n, n), cudaMemcpyDeviceToDevice, h->st);
+  if (e != cudaSuccess) {
+    release();
+    CK(e);
+  }
+  dense_workspace_init(ws, n, h->st);
+  dense_cholesky_solve(dS, n, n, dx, dW, ws, dns, h->st, &h->launches, h->solve_sm_cap);
+  if (eigen_flavour) dense_ldlt_fallback(dBak, n, n, dx, dns, h->st, &h->launches);
+  int ns = 0;
+  e = cudaMemcpyAsync(&ns, dns, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(x, dx, 8 * (size_t)n, cudaMemcpyDeviceToHost, h->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  release();
+  CK(e);
+  if (ok) *ok = !ns;
   return PPO_OK;
 }
 

@@ -730,7 +730,7 @@ static void run_global(const std::vector<KeyFrame *> &vpKFs, const std::vector<M
 
   ppo_ba_params P;
   ppo_ba_default_params(&P);
-  P.solver = PPO_SOLVER_6_3;                // :62-66 (BlockSolver_6_3; the linear solver is the engine's dense Cholesky)
+  P.solver = PPO_SOLVER_6_3;                // :62-66 (BlockSolver_6_3 + LinearSolverEigen: tile Cholesky, LDL^T fall-back on a failed factorisation)
   P.huber_mono = ppo::huber_delta(5.99);    // :88  "sqrt(5.99)", not the 5.991 of the local BA
   P.huber_stereo = ppo::huber_delta(7.815);  // :89
   ppo_ba_handle *h = engine(S, P);

@@ -73,6 +73,7 @@ def load_library():
         lib.ppo_ba_collective_count.restype = C.c_longlong
         lib.ppo_ba_debug_linearize.argtypes = [C.c_void_p, C.POINTER(C.c_int32 * 2), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ppo_ba_debug_solve.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        lib.ppo_ba_debug_dense_solve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         _LIB = lib
     return _LIB
 
@@ -176,6 +177,15 @@ class Handle:
         ok = C.c_int32()
         self._check(self._f("debug_solve")(self.h, C.c_double(lam), S.ctypes.data, bs.ctypes.data, x.ctypes.data if solve else None, C.byref(ok)), "debug_solve")
         return dict(Hschur=S, bschur=bs, x=x, ok=ok.value)
+
+    def debug_dense_solve(self, A, b):
+        """The handle's linear solver alone on a dense symmetric system (upper triangle of A used): (x, ok)."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(len(b))
+        ok = C.c_int32()
+        self._check(self._f("debug_dense_solve")(self.h, len(b), A.ctypes.data, b.ctypes.data, x.ctypes.data, C.byref(ok)), "debug_dense_solve")
+        return x, ok.value
 
     def close(self):
         if self.h:

@@ -1,6 +1,8 @@
 """Parity of the CUDA engine (through the C-ABI, include/ppo_ba.h) against the CPU oracle on the
 same seeded synthetic windows.  Tolerance: BASELINE.json north_star — pose / landmark outputs
 within 1e-4 relative of the reference solve.  Everything here needs a GPU (-m gpu)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -121,6 +123,41 @@ def test_linearize_blocks_match_oracle(ppo, oracle_mod):
     assert close(np.triu(se["Hschur"]), np.triu(so["Hschur"]), 1e-6)
     assert close(se["bschur"], so["bschur"], 1e-6)
     assert close(se["x"], so["x"], 1e-4)
+
+
+@pytest.mark.parametrize("n", [9, 64, 150, 700])
+def test_linear_solver_flavours_on_definite_and_indefinite_systems(ppo, oracle_mod, n):
+    """a21 / a21b: LinearSolverDense (solvers/linear_solver_dense.h:65-113, Eigen::LDLT + isPositive()) rejects a system that is not
+    positive definite; LinearSolverEigen (solvers/linear_solver_eigen.h:94-124, Eigen::SimplicialLDLT) factorises without pivoting,
+    fails only on a zero pivot and so returns the solution of an indefinite system.  With lambda > 0 the reduced system of a window is
+    positive definite, so the second case is only reachable with the solver alone: engine (tile Cholesky, then the LDL^T fall-back of the
+    PPO_SOLVER_6_3 stack) against the oracle's solver of the same flavour and LAPACK."""
+    rng = np.random.default_rng(100 + n)
+    M = rng.normal(size=(n, n))
+    spd = M @ M.T + n * np.eye(n)
+    ind = spd - 1.7 * n * np.eye(n)
+    zero = spd.copy()
+    zero[0, :] = zero[:, 0] = 0.0
+    rhs = rng.normal(size=n)
+    L = oracle_mod.lib()
+    arr = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+    for solver in (ppo.abi.SOLVER_DENSE_X, ppo.abi.SOLVER_6_3):
+        p = ppo.default_params()
+        p.solver = solver
+        e = ppo.LocalBA(p)
+        for name, A_ in (("spd", spd), ("indefinite", ind), ("zero pivot", zero), ("spd again", spd)):
+            ev = np.linalg.eigvalsh(A_)
+            xo = np.zeros(n)
+            ok_o = L.ppo_oracle_dense_solve_flavour(int(solver), n, arr(np.triu(A_)).ctypes.data_as(C.c_void_p), arr(rhs).ctypes.data_as(C.c_void_p),
+                                                    xo.ctypes.data_as(C.c_void_p))
+            x, ok = e.debug_dense_solve(np.triu(A_), rhs)
+            want = 1 if (ev > 0).all() else (1 if (solver == ppo.abi.SOLVER_6_3 and name == "indefinite") else 0)
+            assert ok == want and ok_o == want, (name, solver, ok, ok_o)
+            if ok:
+                xr = np.linalg.solve(A_, rhs)
+                assert np.abs(x - xr).max() <= 1e-8 * np.abs(xr).max(), name
+                assert np.abs(x - xo).max() <= 1e-8 * np.abs(xo).max(), name
+        e.close()
 
 
 def test_config0_points_only_local_bundle_adjustment(ppo, oracle_mod):

@@ -243,6 +243,27 @@ def test_dense_ldlt(L):
     assert L.ppo_oracle_dense_solve(n, _arr(np.triu(Aind)), _arr(rhs), sol) == 0
 
 
+def test_linear_solver_eigen_flavour_solves_indefinite_systems(L):
+    """LinearSolverEigen (solvers/linear_solver_eigen.h:94-124) = Eigen::SimplicialLDLT: LDL^T without pivoting that fails only on
+    an exactly zero pivot; LinearSolverDense rejects the same system (isPositive() false).  Flavours: 0 = PPO_SOLVER_DENSE_X, 1 = PPO_SOLVER_6_3."""
+    rng = np.random.default_rng(11)
+    n = 83
+    M = rng.normal(size=(n, n))
+    Aspd = M @ M.T + n * np.eye(n)
+    Aind = Aspd - 1.7 * n * np.eye(n)
+    assert (np.linalg.eigvalsh(Aind) < 0).any() and (np.linalg.eigvalsh(Aind) > 0).any()
+    rhs = rng.normal(size=n)
+    sol = _d(n)
+    for A_, want in ((Aspd, 1), (Aind, 1)):
+        assert L.ppo_oracle_dense_solve_flavour(1, n, _arr(np.triu(A_)), _arr(rhs), sol) == want
+        x = np.array(sol)
+        assert np.abs(A_ @ x - rhs).max() <= 1e-9 * (np.abs(A_).max() * np.abs(x).max())
+    assert L.ppo_oracle_dense_solve_flavour(0, n, _arr(np.triu(Aind)), _arr(rhs), sol) == 0
+    Azero = Aspd.copy()
+    Azero[0, :] = Azero[:, 0] = 0.0  # first pivot exactly zero: "failure, D(k,k) is zero"
+    assert L.ppo_oracle_dense_solve_flavour(1, n, _arr(np.triu(Azero)), _arr(rhs), sol) == 0
+
+
 # ----- whole-system algebra re-derived densely in numpy -------------------------------------------
 def _np_system(g, P, A, flags=None, rec=None):
     """Builds the full (un-reduced) Gauss-Newton system of a tiny graph with np_ref residuals and
