@@ -31,6 +31,15 @@
 //     traffic: 10.0 -> 9.9 ms, 1.70 -> 1.93 at n = 4000), a communication thread that runs ahead of the buffer ring (9.7 ms without the
 //     device-scope fence before the release, which racecheck does not accept; 10.4 with it), three buffer sets with the target tile read
 //     straight into registers (waiting 1900, computing 7500: 11.0 ms).
+//   * per panel at n = 1644 (instrumented build, cycles): F 17.9 k (four 16 x 16 factorisations of 2.7 k each, i.e. ~300 per 2 x 2 pivot step,
+//     plus the strips / updates between them), T 4.3 k, U 6.3 k (with the look-ahead factorisation inside), publish + operands 1.1 k.
+//     Tried and dropped: (1) warp 0 carrying the whole serial chain of F alone (its own strips of L, bar.arrive hand-over, no block
+//     barrier between (b) and (c)): 0.416 -> 0.418 ms, (b) was already one parallel round.  (2) T and U re-arranged around the chain:
+//     all warps form rows 0..15 of P first, then warp 0 updates + factorises the first sub-block of the next tile while the other warps
+//     form the remaining 48 rows and update the other 33 blocks (W double-buffered): T + U 10.5 k -> 8.2 k, but the look-ahead
+//     factorisation next to 7 warps of DMMA + fragment loads takes 4.5 k instead of 2.7 k (shared-memory round trips of the pivot steps
+//     queue behind the fragment traffic; keeping the warp on the same scheduler idle does not help): 0.423 / 0.427 ms.  The tensor work of
+//     T + U on one SM is 1152 DMMAs = 4.6 k cycles at 16 cycles per DMMA and sub-partition, so the chain cannot hide behind it.
 //
 // The second half of the file spreads the same factorisation over the GPUs of a node (k_chol_dist and friends).
 #include <cuda_runtime.h>
