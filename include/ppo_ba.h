@@ -239,6 +239,12 @@ int ppo_ba_local_ba_batch(ppo_ba_handle **h, int n, const volatile unsigned char
 int ppo_ba_edge_chi2(ppo_ba_handle *h, int kind, double *chi2, unsigned char *depth_positive,
                      double *err_norm);
 
+/* The point edges LocalBundleAdjustment / LocalBACameraPlaneCuboids erase after the optimisation (Optimizer.cc:2840-2852, :719-741):
+ * ascending indices of the point edges with e->chi2() > chi2_mono (monocular) / chi2_stereo (stereo) or !e->isDepthPositive() --
+ * the test of ppo_ba_edge_chi2's outputs done on the device, so that a few KB come back instead of 9 bytes per edge.
+ * *idx points into the handle and stays valid until the next call of this function or ppo_ba_set_graph. */
+int ppo_ba_point_edge_outliers(ppo_ba_handle *h, double chi2_mono, double chi2_stereo, const int32_t **idx, int32_t *n);
+
 /* e->computeError() at the current estimates for every LEVEL-1 edge of a kind (the optimiser skips those, so their
  * stored error is stale); afterwards ppo_ba_edge_chi2 reports a fresh chi2 for them.  This is what
  * Optimizer::PoseOptimization does before re-classifying its outliers (Optimizer.cc:400-403,431-434).

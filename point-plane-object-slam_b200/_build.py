@@ -106,7 +106,7 @@ def build_shim(force=False):
     deps = srcs + [os.path.join(host, "ppo_mock_slam.h"), os.path.join(host, "ppo_convert.h"), os.path.join(ROOT, "include", "ppo_ba.h"),
                    os.path.join(LIB, "libppo_ba.so")]
     if force or _newer(out, deps):
-        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out] + srcs + ["-L", LIB, "-lppo_ba", "-Wl,-rpath,$ORIGIN"])
+        _run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", out] + srcs + ["-L", LIB, "-lppo_ba", "-Wl,-rpath,$ORIGIN"])
     return out
 
 

@@ -102,6 +102,7 @@ struct ppo_ba_handle {
   std::vector<int> cpe_cuboid, cpe_plane;
   std::vector<double> cpe_chi2, cpe_norm;
   std::vector<uint8_t> cpe_flags;
+  std::vector<int32_t> outlier_idx;  // result of ppo_ba_point_edge_outliers (valid until its next call)
   int *d_cpe_cuboid = nullptr, *d_cpe_plane = nullptr;
   uint8_t *d_cpe_flags = nullptr;
   // partial-sum buffers
@@ -1443,6 +1444,35 @@ int ppo_ba_edge_chi2(ppo_ba_handle *h, int kind, double *chi2, unsigned char *de
       std::memset(depth_positive, 1, n);
     }
   }
+  return PPO_OK;
+}
+
+int ppo_ba_point_edge_outliers(ppo_ba_handle *h, double chi2_mono, double chi2_stereo, const int32_t **idx, int32_t *n) {
+  if (!h || !h->have_graph || !idx || !n) return PPO_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevGraph &g = h->g;
+  *idx = nullptr, *n = 0;
+  h->outlier_idx.clear();
+  if (g.n_pe == 0) return PPO_OK;
+  int *d_idx = nullptr, *d_cnt = nullptr;
+  CK(cudaMallocAsync((void **)&d_idx, sizeof(int) * ((size_t)g.n_pe + 1), h->st));  // stream-ordered pool: no OS call in the steady state
+  d_cnt = d_idx + g.n_pe;
+  cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(int), h->st);
+  k_point_edge_outliers<<<cdiv(g.n_pe, 256), 256, 0, h->st>>>(g, h->sa, chi2_mono, chi2_stereo, d_idx, d_cnt);
+  h->launches++;
+  int cnt = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+  if (e == cudaSuccess && cnt > 0) {
+    h->outlier_idx.resize((size_t)cnt);
+    e = cudaMemcpyAsync(h->outlier_idx.data(), d_idx, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+  }
+  cudaFreeAsync(d_idx, h->st);
+  CK(e);
+  CK(cudaGetLastError());
+  std::sort(h->outlier_idx.begin(), h->outlier_idx.end());
+  *idx = h->outlier_idx.data(), *n = (int32_t)h->outlier_idx.size();
   return PPO_OK;
 }
 

@@ -1695,6 +1695,29 @@ __global__ void k_outlier_pass(DevGraph g, DevState s, double chi2_mono, double 
     g.ple_flags[i] = (uint8_t)fl;
   }
 }
+// Point edges the caller erases after the BA (Optimizer.cc:2840-2852): e->chi2() above the threshold of its kind or !e->isDepthPositive();
+// compacted edge ids in arbitrary order (the host sorts the few it gets)
+__global__ void k_point_edge_outliers(DevGraph g, DevState s, double th_mono, double th_stereo, int *idx, int *count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool out = false;
+  if (i < g.n_pe) {
+    const PointEdgeRec rec = g.pe_rec[i];
+    const int pt = g.pe_pt[i];
+    double p[3], X[3] = {s.pt[3 * pt], s.pt[3 * pt + 1], s.pt[3 * pt + 2]};
+    double q[4] = {s.kf_pose[7 * rec.kf], s.kf_pose[7 * rec.kf + 1], s.kf_pose[7 * rec.kf + 2], s.kf_pose[7 * rec.kf + 3]};
+    quat_rot(q, X, p);
+    const bool depth_positive = (p[2] + s.kf_pose[7 * rec.kf + 6]) > 0.0;
+    out = g.pe_chi2[i] > (rec.ur < 0 ? th_mono : th_stereo) || !depth_positive;
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, out);
+  if (mask) {
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (out) idx[base + __popc(mask & ((1u << lane) - 1))] = i;
+  }
+}
 __global__ void k_depth_flags(DevGraph g, DevState s, int kind, unsigned char *out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (kind == 0 && i < g.n_pe) {

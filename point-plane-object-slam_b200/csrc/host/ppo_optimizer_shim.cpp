@@ -29,6 +29,9 @@
 #include <cstdio>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <functional>
+#include <condition_variable>
 #include <vector>
 
 #include "../../../include/ppo_ba.h"
@@ -171,6 +174,25 @@ static ppo_ba_handle *engine(Slot &S, const ppo_ba_params &P) {
 }
 
 using namespace ORB_SLAM2;
+// indices (ascending) of the point edges the local BA erases: chi2 above the threshold of the edge's kind, or a non-positive depth
+#ifdef PPO_SHIM_ON_ORACLE
+static int point_edge_outliers(ppo_ba_handle *h, const Flat &F, double th_mono, double th_stereo, const int32_t **idx, int32_t *n) {
+  static std::vector<int32_t> out;  // (test build: the oracle has no such call; same test on its per-edge outputs)
+  std::vector<double> chi2(F.g.n_pe);
+  std::vector<unsigned char> dpos(F.g.n_pe);
+  const int rc = ppo_ba_edge_chi2(h, PPO_EDGE_POINT, chi2.data(), dpos.data(), nullptr);
+  out.clear();
+  for (int e = 0; e < F.g.n_pe; e++)
+    if (chi2[e] > (F.pe_obs[3 * (size_t)e + 2] < 0 ? th_mono : th_stereo) || !dpos[e]) out.push_back(e);
+  *idx = out.data(), *n = (int32_t)out.size();
+  return rc;
+}
+#else
+static int point_edge_outliers(ppo_ba_handle *h, const Flat &, double th_mono, double th_stereo, const int32_t **idx, int32_t *n) {
+  return ppo_ba_point_edge_outliers(h, th_mono, th_stereo, idx, n);
+}
+#endif
+
 
 // ---- observation mirror (second half) ------------------------------------------------------------------------------
 // The flattened observation row of a map point -- (key-frame, feature index, undistorted key-point, right coordinate, 1 / sigma^2 of its
@@ -252,6 +274,87 @@ struct Window {
   std::vector<MapPlane *> lLocalMapPlanes;
 };
 
+// Host threads of the flattening loops: a small pool of workers that SLEEP between jobs (condition variable, no spinning -- the
+// caller is the LocalMapping thread of a process whose other threads track and close loops).  PPO_SHIM_THREADS overrides the
+// size (default: min(8, hardware threads)); 1 = the serial loops.  A job is split into equal contiguous index ranges.
+class HostPool {
+ public:
+  HostPool() {
+    int n = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char *e = std::getenv("PPO_SHIM_THREADS")) n = std::max(1, std::min(64, std::atoi(e)));
+    n_ = n;
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  int threads() const { return n_; }
+  void resize(int n) {  // (not while a job runs: callers hold the mutex of the local-BA slot)
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+    th_.clear();
+    quit_ = false;
+    n_ = std::max(1, std::min(64, n));
+  }
+  // f(begin, end) on disjoint ranges covering [0, n); returns when all ranges are done
+  void for_ranges(long n, const std::function<void(long, long)> &f) {
+    const int parts = (int)std::min<long>(n_, std::max<long>(1, n / 2048));
+    if (parts <= 1) {
+      f(0, n);
+      return;
+    }
+    if (th_.empty())
+      for (int i = 1; i < n_; i++) th_.emplace_back([this, i, g = gen_] { worker(i, g); });  // (a new worker must not mistake an old generation for a job)
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &f, job_n_ = n, parts_ = parts, pending_ = parts - 1, gen_++;
+    }
+    cv_.notify_all();
+    f(0, n / parts);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void worker(int id, int seen) {
+    for (;;) {
+      const std::function<void(long, long)> *f;
+      long n;
+      int parts;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
+        if (quit_) return;
+        seen = gen_, f = job_, n = job_n_, parts = parts_;
+      }
+      if (id >= parts) continue;
+      (*f)(n * id / parts, n * (id + 1) / parts);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        pending_--;
+      }
+      done_.notify_one();
+    }
+  }
+  int n_ = 1;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(long, long)> *job_ = nullptr;
+  long job_n_ = 0;
+  int parts_ = 0, pending_ = 0, gen_ = 0;
+  bool quit_ = false;
+};
+static HostPool g_pool;  // (used under the mutex of the local-BA slot)
+
 // stage A: Optimizer.cc:1997-2100 (mixed) / :463-514 (points only)
 static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = true) {
   w.lLocalKeyFrames.push_back(pKF);
@@ -297,8 +400,18 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = tru
     w.obs_row.push_back({r.off, r.n});
   }
   // (after the loop: a row rebuilt later may have moved the pool)
-  for (auto &r : w.obs_row)
-    for (uint32_t q = r.first; q < r.first + r.second; q++) add_fixed(g_mirror.pool[q].kf);
+  {
+    std::vector<uint8_t> seen;  // by KeyFrame::mnId: one look at the key-frame itself per key-frame, not per observation
+    const ObsRec *pool = g_mirror.pool.data();
+    for (auto &r : w.obs_row)
+      for (uint32_t q = r.first; q < r.first + r.second; q++) {
+        const ObsRec &o = pool[q];
+        if (o.kf_id < seen.size() && seen[o.kf_id]) continue;
+        if (o.kf_id >= seen.size()) seen.resize((size_t)o.kf_id + 1 + seen.size(), 0);
+        seen[o.kf_id] = 1;
+        add_fixed(o.kf);
+      }
+  }
   if (mixed)
     for (MapCuboid *pMC : w.lLocalMapCuboids) {
       std::unordered_map<KeyFrame *, size_t> observations = pMC->GetObservations();
@@ -421,40 +534,59 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   // ---- points and reprojection edges :2332-2424 (mixed) / :560-650 (points only) ----------------------------
   std::vector<MapPoint *> graph_points;  // points that got a vertex (mixed: Observations() != 1, q1)
   std::vector<std::pair<KeyFrame *, MapPoint *>> point_edge_owner;
-  size_t n_obs = 0;
-  for (auto &r : w.obs_row) n_obs += r.second;
-  // edge arrays sized for every observation of the window and filled by index (trimmed below): no capacity checks in the 10^5..10^6-edge loop
-  point_edge_owner.resize(n_obs);
-  F.pe_kf.resize(n_obs); F.pe_obs.resize(3 * n_obs); F.pe_invsigma2.resize(n_obs);
-  size_t ne = 0;
-  F.pt_xyz.reserve(3 * w.lLocalMapPoints.size()); F.pt_fixed.reserve(w.lLocalMapPoints.size()); F.pt_rowptr.reserve(w.lLocalMapPoints.size() + 1);
-  graph_points.reserve(w.lLocalMapPoints.size());
-  F.pt_rowptr.push_back(0);
-  tick("  B: point arrays sized");
-  for (size_t ip = 0; ip < w.lLocalMapPoints.size(); ip++) {
+  // Two passes over the local map points, both spread over the host threads (every point only reads its own map point and its own row of
+  // the mirror and writes its own range of the arrays): (1) does the point get a vertex, and how many of its observations become edges;
+  // prefix sums give every point its vertex index and its edge range; (2) fill.  The result is the one the serial loop produces.
+  const size_t NP = w.lLocalMapPoints.size();
+  std::vector<uint32_t> pt_first(NP + 1, 0), e_first(NP + 1, 0);  // (counts, then exclusive prefix sums)
+  auto edge_ok = [&](const ObsRec &o) {
+    if (o.kf_id >= slot_of_id.size()) return -1;
+    const int sl = slot_of_id[o.kf_id];
+    return (sl < 0 || slots[sl].kf != o.kf || slot_bad[sl]) ? -1 : sl;  // (!pKFi->isBad(), :2352, read once per key-frame)
+  };
+  const ObsRec *pool = g_mirror.pool.data();
+  g_pool.for_ranges((long)NP, [&](long ip0, long ip1) {
+  for (long ip = ip0; ip < ip1; ip++) {
     MapPoint *pMP = w.lLocalMapPoints[ip];
     if (mixed && pMP->Observations() == 1) continue;  // :2336
-    graph_points.push_back(pMP);
+    pt_first[ip + 1] = 1;
+    const ObsRec *row = pool + w.obs_row[ip].first;  // the row read in stage A, already in key-frame (= slot) order
+    uint32_t c = 0;
+    for (uint32_t q = 0; q < w.obs_row[ip].second; q++) c += edge_ok(row[q]) >= 0;
+    e_first[ip + 1] = c;
+  }
+  });
+  for (size_t ip = 0; ip < NP; ip++) pt_first[ip + 1] += pt_first[ip], e_first[ip + 1] += e_first[ip];
+  const size_t npt = pt_first[NP], ne = e_first[NP];
+  graph_points.resize(npt);
+  point_edge_owner.resize(ne);
+  F.pt_xyz.resize(3 * npt); F.pt_fixed.assign(npt, mixed && fixPoint); F.pt_rowptr.resize(npt + 1);
+  F.pe_kf.resize(ne); F.pe_obs.resize(3 * ne); F.pe_invsigma2.resize(ne);
+  F.pt_rowptr[0] = 0;
+  tick("  B: point arrays sized");
+  g_pool.for_ranges((long)NP, [&](long ip0, long ip1) {
+  for (long ip = ip0; ip < ip1; ip++) {
+    if (pt_first[ip + 1] == pt_first[ip]) continue;
+    MapPoint *pMP = w.lLocalMapPoints[ip];
+    const size_t pi = pt_first[ip];
+    graph_points[pi] = pMP;
     cv::Mat X = pMP->GetWorldPos();
-    for (int i = 0; i < 3; i++) F.pt_xyz.push_back((double)X.at<float>(i, 0));  // Converter::toVector3d
-    F.pt_fixed.push_back(mixed && fixPoint);
-    const ObsRec *row = g_mirror.pool.data() + w.obs_row[ip].first;  // the row read in stage A, already in key-frame (= slot) order
+    for (int i = 0; i < 3; i++) F.pt_xyz[3 * pi + i] = (double)X.at<float>(i, 0);  // Converter::toVector3d
+    const ObsRec *row = pool + w.obs_row[ip].first;
+    size_t e = e_first[ip];
     for (uint32_t q = 0; q < w.obs_row[ip].second; q++) {
       const ObsRec &o = row[q];
-      KeyFrame *pKFi = o.kf;
-      if (o.kf_id >= slot_of_id.size()) continue;
-      const int sl = slot_of_id[o.kf_id];
-      if (sl < 0 || slots[sl].kf != pKFi || slot_bad[sl]) continue;  // (!pKFi->isBad(), :2352, read once per key-frame)
-      F.pe_kf[ne] = sl;
-      F.pe_obs[3 * ne] = o.u, F.pe_obs[3 * ne + 1] = o.v, F.pe_obs[3 * ne + 2] = o.ur;
-      F.pe_invsigma2[ne] = o.inv_sigma2;
-      point_edge_owner[ne] = {pKFi, pMP};
-      ne++;
+      const int sl = edge_ok(o);
+      if (sl < 0) continue;
+      F.pe_kf[e] = sl;
+      F.pe_obs[3 * e] = o.u, F.pe_obs[3 * e + 1] = o.v, F.pe_obs[3 * e + 2] = o.ur;
+      F.pe_invsigma2[e] = o.inv_sigma2;
+      point_edge_owner[e] = {o.kf, pMP};
+      e++;
     }
-    F.pt_rowptr.push_back((int32_t)ne);
+    F.pt_rowptr[pi + 1] = (int32_t)e_first[ip + 1];
   }
-  point_edge_owner.resize(ne);
-  F.pe_kf.resize(ne); F.pe_obs.resize(3 * ne); F.pe_invsigma2.resize(ne);
+  });
   if (mixed) {
     tick("  B: points + point edges");
     // ---- camera-cuboid edges :2433-2551 ------------------------------------------------------------------
@@ -597,14 +729,15 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   std::vector<std::pair<KeyFrame *, MapPoint *>> vToErase;
   std::vector<std::pair<KeyFrame *, MapPlane *>> vToErasePlane;
   {
-    std::vector<double> chi2(F.g.n_pe);
-    std::vector<unsigned char> dpos(F.g.n_pe);
-    if (F.g.n_pe) ppo_ba_edge_chi2(h, PPO_EDGE_POINT, chi2.data(), dpos.data(), nullptr);
-    for (int e = 0; e < F.g.n_pe; e++) {
-      MapPoint *pMP = point_edge_owner[e].second;
+    // the chi2 / depth test of every point edge runs on the device; only the indices of the edges that fail it come back (ascending,
+    // i.e. in the order of the reference's loop over vpEdgesMono / vpEdgesStereo as the shim laid the edges out)
+    const int32_t *bad = nullptr;
+    int32_t n_bad = 0;
+    if (F.g.n_pe && (S.rc = point_edge_outliers(h, F, 5.991, 7.815, &bad, &n_bad)) != PPO_OK) return;
+    for (int32_t q = 0; q < n_bad; q++) {
+      MapPoint *pMP = point_edge_owner[bad[q]].second;
       if (pMP->isBad()) continue;
-      const bool mono = F.pe_obs[3 * (size_t)e + 2] < 0;
-      if (chi2[e] > (mono ? 5.991 : 7.815) || !dpos[e]) vToErase.push_back(point_edge_owner[e]);
+      vToErase.push_back(point_edge_owner[bad[q]]);
     }
     if (F.g.n_ple) {
       std::vector<double> pchi(F.g.n_ple);
@@ -918,6 +1051,12 @@ const ppo_ba_graph *ppo_shim_last_graph() { return &ppo_shim::g_last_slot.load()
 const ppo_ba_result *ppo_shim_last_result() { return &ppo_shim::g_last_slot.load()->res; }
 int ppo_shim_last_rc() { return ppo_shim::g_last_slot.load()->rc; }
 void ppo_shim_set_device(int device) { ppo_shim::g_device = device; }
+// host threads of the flattening loops of the local-BA entry points (default min(8, hardware threads), PPO_SHIM_THREADS); 1 = serial
+void ppo_shim_set_threads(int n) {
+  std::lock_guard<std::mutex> lk(ppo_shim::g_slots[ppo_shim::SLOT_LOCAL].m);
+  ppo_shim::g_pool.resize(n);
+}
+int ppo_shim_get_threads() { return ppo_shim::g_pool.threads(); }
 void ppo_shim_shutdown() {
   for (auto &S : ppo_shim::g_slots)
     if (S.h) ppo_ba_destroy(S.h), S.h = nullptr;

@@ -73,6 +73,7 @@ def load_library():
         lib.ppo_ba_collective_count.restype = C.c_longlong
         lib.ppo_ba_debug_linearize.argtypes = [C.c_void_p, C.POINTER(C.c_int32 * 2), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ppo_ba_debug_solve.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        lib.ppo_ba_point_edge_outliers.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
         lib.ppo_ba_debug_dense_solve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         _LIB = lib
     return _LIB
@@ -177,6 +178,13 @@ class Handle:
         ok = C.c_int32()
         self._check(self._f("debug_solve")(self.h, C.c_double(lam), S.ctypes.data, bs.ctypes.data, x.ctypes.data if solve else None, C.byref(ok)), "debug_solve")
         return dict(Hschur=S, bschur=bs, x=x, ok=ok.value)
+
+    def point_edge_outliers(self, chi2_mono, chi2_stereo):
+        """Ascending indices of the point edges with chi2 above the threshold of their kind or a non-positive depth."""
+        p = C.POINTER(C.c_int32)()
+        n = C.c_int32()
+        self._check(self._f("point_edge_outliers")(self.h, C.c_double(chi2_mono), C.c_double(chi2_stereo), C.byref(p), C.byref(n)), "point_edge_outliers")
+        return np.array(p[:n.value], dtype=np.int32)
 
     def debug_dense_solve(self, A, b):
         """The handle's linear solver alone on a dense symmetric system (upper triangle of A used): (x, ok)."""

@@ -33,6 +33,8 @@ def _declare(L):
     L.ppo_shim_mirror_stats.argtypes = [C.POINTER(C.c_longlong * 3)]
     L.ppo_shim_mirror_stats.restype = None
     L.ppo_mock_last_call_ms.restype = C.c_double
+    L.ppo_shim_set_threads.argtypes = [C.c_int]
+    L.ppo_shim_set_threads.restype = None
 
 
 def oracle_backed_lib():
@@ -49,7 +51,7 @@ def oracle_backed_lib():
         srcs = [os.path.join(host, "ppo_optimizer_shim.cpp"), os.path.join(host, "ppo_mock_world.cpp")]
         deps = srcs + [os.path.join(host, f) for f in ("ppo_mock_slam.h", "ppo_convert.h")] + [os.path.join(bdir, "libppo_oracle.so")]
         if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DPPO_SHIM_ON_ORACLE", "-o", out] + srcs +
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-DPPO_SHIM_ON_ORACLE", "-o", out] + srcs +
                                   ["-L", bdir, "-lppo_oracle", "-Wl,-rpath,$ORIGIN"])
         L = C.CDLL(out)
         _declare(L)

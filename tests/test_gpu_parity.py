@@ -188,6 +188,31 @@ def test_point_cuboid_window_with_se3_edges(ppo, oracle_mod, flags):
     full_parity(ppo, oracle_mod, g)
 
 
+def test_point_edge_outliers_on_the_device_equal_the_host_test(ppo, oracle_mod):
+    """ppo_ba_point_edge_outliers: the erase test of Optimizer.cc:2840-2852 (chi2 above the threshold of the edge's kind, or a
+    non-positive depth) evaluated on the device must list exactly the edges the same test on ppo_ba_edge_chi2's outputs lists,
+    in ascending order -- and the oracle's per-edge outputs must give the same list."""
+    A = ppo.abi
+    for cfg in (dict(n_kf=8, n_fixed=2, n_pt=300, n_pl=4, n_cu=3), dict(n_kf=24, n_fixed=5, n_pt=12000, n_pl=6, n_cu=3)):
+        g = ppo.synth.make_graph(ppo.synth.config(1, **cfg))
+        o, e = run_both(ppo, oracle_mod, g)
+        o.local_ba(), e.local_ba()
+        mono = g["pe_obs"].reshape(-1, 3)[:, 2] < 0
+        for th in ((5.991, 7.815), (0.5, 0.7)):
+            lists = []
+            for h in (e, o):
+                chi2, dpos, _ = h.edge_chi2(A.EDGE_POINT)
+                lists.append(np.nonzero((chi2 > np.where(mono, th[0], th[1])) | (dpos == 0))[0])
+            got = e.point_edge_outliers(*th)
+            assert np.array_equal(got, lists[0])
+            # (the oracle's chi2 differs from the engine's in the last digits: edges within 1e-6 relative of a threshold may flip)
+            sym = np.setxor1d(lists[0], lists[1])
+            chi2e = e.edge_chi2(A.EDGE_POINT)[0]
+            assert all(abs(chi2e[i] / (th[0] if mono[i] else th[1]) - 1) < 1e-4 for i in sym), sym
+        assert len(e.point_edge_outliers(0.5, 0.7)) > 0
+        e.close()
+
+
 def test_config1_mixed_window(ppo, oracle_mod):
     """BASELINE.json configs[1]: 50 KF / 20k points / 50 planes / 10 cuboids."""
     g = ppo.synth.make_graph(ppo.synth.config(1))

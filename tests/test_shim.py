@@ -44,6 +44,30 @@ def test_flattening_reproduces_the_flat_graph_cpu(ppo):
     assert np.allclose(np.sort(flat["cpe_info"].ravel()), np.sort(g["cpe_info"].ravel()))
 
 
+@pytest.mark.parametrize("mixed", [True, False])
+def test_threaded_flattening_equals_the_serial_loops_cpu(ppo, oracle_mod, mixed):
+    """Stage B spreads the point / point-edge loops over host threads once a window has more than 4096 local map points: the
+    flattened graph must be bit-identical to the one the serial loops produce (stop flag set: collection + flattening only)."""
+    import shim_lib
+    L = shim_lib.oracle_backed_lib()
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=24, n_fixed=5, n_pt=12000, n_pl=6, n_cu=3))
+    flats = []
+    try:
+        for n in (1, 5, 8, 3, 8):
+            L.ppo_shim_set_threads(n)
+            assert L.ppo_shim_get_threads() == n
+            flats.append(shim_lib.run(g, mixed=mixed, stop=True, backend=L)[2])
+    finally:
+        L.ppo_shim_set_threads(1)
+    ref = flats[0]
+    assert ref.c.n_pt > 4096 and ref.c.n_pe > 4 * ref.c.n_pt
+    for f in flats[1:]:
+        assert (f.c.n_kf, f.c.n_pt, f.c.n_pe, f.c.n_ple, f.c.n_cbe, f.c.n_pce, f.c.n_cpe) == (
+            ref.c.n_kf, ref.c.n_pt, ref.c.n_pe, ref.c.n_ple, ref.c.n_cbe, ref.c.n_pce, ref.c.n_cpe)
+        for k in ("pt_xyz", "pt_fixed", "pt_rowptr", "pe_kf", "pe_obs", "pe_invsigma2", "kf_pose", "kf_fixed"):
+            assert np.array_equal(f[k], ref[k]), k
+
+
 def test_points_only_entry_point_flattening_cpu(ppo):
     import shim_lib
     g = ppo.synth.make_graph(ppo.synth.config(0))
