@@ -169,6 +169,7 @@ def shim_e2e(ppo, g, reps=3):
     L.ppo_shim_last_result.restype = C.POINTER(A.Result)
     L.ppo_shim_mirror_stats.argtypes = [C.POINTER(C.c_longlong * 3)]
     L.ppo_shim_mirror_stats.restype = None
+    L.ppo_shim_get_threads.restype = C.c_int
     import numpy as np
     st = A.StateArrays(g.c)
     counts = (C.c_int32 * 4)()
@@ -205,6 +206,7 @@ def shim_e2e(ppo, g, reps=3):
             "first_call": {"value": cold_iters / (cold * 1e-3), "ms_per_call": cold, "lm_iterations": cold_iters, "host_ms_per_call": cold_host,
                            "note": "observation mirror cold: every map point's observation map is copied, as the reference does on every call"},
             "mirror": {"rows_reused": int(reused), "rows_rebuilt": int(rebuilt)},
+            "host_threads": int(L.ppo_shim_get_threads()),
             "note": "Optimizer::LocalBACameraPlaneCuboids on a mock map of the same window, map kept across calls: collection + flattening (observation "
                     "rows of unchanged map points from the shim's mirror) + H2D + solve + D2H + write-back, wall clock; host_ms = wall clock minus the "
                     "device time of the two optimize() calls; the later calls solve the window without the observations the first call erased and may "

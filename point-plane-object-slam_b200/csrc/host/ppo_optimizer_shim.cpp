@@ -115,11 +115,17 @@ struct Flat {
   std::vector<int32_t> pt_rowptr, pe_kf, ple_plane, ple_kf, cbe_kf, cbe_cuboid, pce_cuboid, pce_rowptr, cpe_cuboid, cpe_plane;
   ppo_ba_graph g;
   // empties the arrays but keeps their memory: a steady-state call then touches no fresh pages (30 MB for a 200-key-frame window)
-  void clear() {
-    for (auto *v : {&kf_pose, &pt_xyz, &pl_coef, &cu_state, &ple_meas, &ple_info, &cbe_meas, &cbe_info, &pce_pts, &cpe_meas, &cpe_info}) v->clear();
-    for (auto *v : {&kf_fixed, &pt_fixed, &cu_flags, &ple_kind, &cbe_kind}) v->clear();
-    for (auto *v : {&kf_intr, &pe_obs, &pe_invsigma2}) v->clear();
-    for (auto *v : {&pt_rowptr, &pe_kf, &ple_plane, &ple_kf, &cbe_kf, &cbe_cuboid, &pce_cuboid, &pce_rowptr, &cpe_cuboid, &cpe_plane}) v->clear();
+  // keep_point_arrays: the point / point-edge arrays are then RESIZED and overwritten by the caller (run()), so they keep their size too --
+  // a resize to nearly the same length value-initialises nothing, where clear() + resize() would zero 10 MB per call
+  void clear(bool keep_point_arrays = false) {
+    for (auto *v : {&kf_pose, &pl_coef, &cu_state, &ple_meas, &ple_info, &cbe_meas, &cbe_info, &pce_pts, &cpe_meas, &cpe_info}) v->clear();
+    for (auto *v : {&kf_fixed, &cu_flags, &ple_kind, &cbe_kind}) v->clear();
+    kf_intr.clear();
+    for (auto *v : {&ple_plane, &ple_kf, &cbe_kf, &cbe_cuboid, &pce_cuboid, &pce_rowptr, &cpe_cuboid, &cpe_plane}) v->clear();
+    if (!keep_point_arrays) {
+      pt_xyz.clear(), pt_fixed.clear(), pt_rowptr.clear();
+      pe_kf.clear(), pe_obs.clear(), pe_invsigma2.clear();
+    }
   }
   void publish() {
     std::memset(&g, 0, sizeof g);
@@ -151,6 +157,10 @@ struct Slot {
   ppo_ba_params P;
   int device = -1;
   Flat last;  // last flattened window (introspection for tests / logging)
+  // per-call work arrays of run() that are as long as the window's points / point edges: kept across calls like the flat arrays
+  std::vector<std::pair<ORB_SLAM2::KeyFrame *, ORB_SLAM2::MapPoint *>> point_edge_owner;
+  std::vector<ORB_SLAM2::MapPoint *> graph_points;
+  std::vector<uint32_t> pt_first, e_first;
   ppo_ba_result res;
   int rc = 0;
 };
@@ -440,7 +450,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
 
   // ---- stage B: flatten (vertices) ------------------------------------------------------------------
   Flat &F = S.last;
-  F.clear();
+  F.clear(true);
   // key-frame slots ordered by mnId = g2o's Hessian order (core/sparse_optimizer.cpp:166-190,482-487)
   struct Slot { KeyFrame *kf; bool fixed; };
   std::vector<Slot> slots;
@@ -532,13 +542,14 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   }
   tick("  B: vertices + plane edges");
   // ---- points and reprojection edges :2332-2424 (mixed) / :560-650 (points only) ----------------------------
-  std::vector<MapPoint *> graph_points;  // points that got a vertex (mixed: Observations() != 1, q1)
-  std::vector<std::pair<KeyFrame *, MapPoint *>> point_edge_owner;
+  std::vector<MapPoint *> &graph_points = S.graph_points;  // points that got a vertex (mixed: Observations() != 1, q1)
+  std::vector<std::pair<KeyFrame *, MapPoint *>> &point_edge_owner = S.point_edge_owner;
   // Two passes over the local map points, both spread over the host threads (every point only reads its own map point and its own row of
   // the mirror and writes its own range of the arrays): (1) does the point get a vertex, and how many of its observations become edges;
   // prefix sums give every point its vertex index and its edge range; (2) fill.  The result is the one the serial loop produces.
   const size_t NP = w.lLocalMapPoints.size();
-  std::vector<uint32_t> pt_first(NP + 1, 0), e_first(NP + 1, 0);  // (counts, then exclusive prefix sums)
+  std::vector<uint32_t> &pt_first = S.pt_first, &e_first = S.e_first;  // (counts, then exclusive prefix sums)
+  pt_first.assign(NP + 1, 0), e_first.assign(NP + 1, 0);
   auto edge_ok = [&](const ObsRec &o) {
     if (o.kf_id >= slot_of_id.size()) return -1;
     const int sl = slot_of_id[o.kf_id];
