@@ -40,6 +40,10 @@
 //     factorisation next to 7 warps of DMMA + fragment loads takes 4.5 k instead of 2.7 k (shared-memory round trips of the pivot steps
 //     queue behind the fragment traffic; keeping the warp on the same scheduler idle does not help): 0.423 / 0.427 ms.  The tensor work of
 //     T + U on one SM is 1152 DMMAs = 4.6 k cycles at 16 cycles per DMMA and sub-partition, so the chain cannot hide behind it.
+//     (3) inside the 16 x 16 factorisation: the pivot block by shuffle from its owners instead of through shared memory (kept: 2744 -> 2572
+//     cycles per sub-block, 0.416 -> 0.414 ms).  Every lane forming the NEXT pivot block itself, so that only one FMA, the determinant
+//     and the reciprocal are on the chain (dropped: 3400 cycles per sub-block, 0.457 ms -- the warp issues in order at 2 cycles per
+//     FP64 instruction, and the extra off-chain arithmetic delays the chain more than the shorter dependency path gains).
 //
 // The second half of the file spreads the same factorisation over the GPUs of a node (k_chol_dist and friends).
 #include <cuda_runtime.h>
@@ -249,13 +253,20 @@ __device__ __forceinline__ void sub_factor16(TilePtr D, TilePtr X, int s, FacSme
 #pragma unroll
   for (int j = 0; j <= SB; j += 2) {  // (the last round only flushes the lagging identity half)
     const int bi = (j >> 1) & 1;
+    // The 2 x 2 pivot block comes straight out of the registers of its owners (lanes j, j+1) by shuffle, and a lane's own entries of the
+    // two pivot columns are its own r[j], r[j+1] (symmetry): the serial chain does not wait for the shared-memory round trip below, which
+    // only feeds the rank-2 update at the end of the step.
+    double b00 = 1.0, b10 = 0.0, b11 = 1.0;
+    if (j < SB) {
+      b00 = __shfl_sync(0xffffffffu, r[j], j);
+      b10 = __shfl_sync(0xffffffffu, r[j], j + 1);
+      b11 = __shfl_sync(0xffffffffu, r[j + 1], j + 1);
+    }
     if (j < SB && lo) fs.buf[0][bi][0][li] = r[j], fs.buf[0][bi][1][li] = r[j + 1];  // columns j, j+1 of the current A (= rows, by symmetry)
     __syncwarp();
     double s0 = 0.0, s1 = 0.0;
     if (j < SB) {
-      const double *v0 = fs.buf[0][bi][0], *v1 = fs.buf[0][bi][1];
-      double b00 = v0[j], b10 = v0[j + 1], b11 = v1[j + 1];
-      const double c0 = v0[li], c1 = v1[li];
+      const double c0 = r[j], c1 = r[j + 1];
       double det = fma(b00, b11, -b10 * b10);
       const bool bad = !(b00 > 0.0) || !(det > 0.0);
       if (bad && lane == 0) *not_spd = 1;  // everything computed from here on is garbage and will be discarded
@@ -274,13 +285,16 @@ __device__ __forceinline__ void sub_factor16(TilePtr D, TilePtr X, int s, FacSme
     }
     if (!lo && j >= 2) s0 = r[j >= 2 ? j - 2 : 0], s1 = r[j >= 2 ? j - 1 : 1];  // X(j-2, c), X(j-1, c) of my column c, before this step touches them
     const double *vec0 = mine + bi * 2 * SB, *vec1 = vec0 + SB;
-#pragma unroll
-    for (int c = (j >= 2 ? j - 2 : 2); c < SB; c += 2) {
+    auto upd = [&](int c) {
       const double2 p = *reinterpret_cast<const double2 *>(&vec0[c]);
       const double2 q = *reinterpret_cast<const double2 *>(&vec1[c]);
       r[c] = fma(q.x, s1, fma(p.x, s0, r[c]));
       r[c + 1] = fma(q.y, s1, fma(p.y, s0, r[c + 1]));
-    }
+    };
+    if (j + 2 < SB) upd(j + 2);  // the next pivot pair first: the next step starts from it
+#pragma unroll
+    for (int c = (j >= 2 ? j - 2 : 2); c < SB; c += 2)
+      if (c != j + 2) upd(c);
   }
   // V(i, c) = X(i, c) / sqrt(d_i): column lanes hold X(:, c)
   if (lo) fs.rs[li] = pf_rsqrt(my_d);
