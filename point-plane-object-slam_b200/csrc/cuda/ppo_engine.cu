@@ -215,12 +215,22 @@ struct ppo_ba_handle {
     hstage_off += bytes;
     return PPO_OK;
   }
-  void drop_lm_graphs() {
+  // A captured loop holds the window's device pointers and constants by value, so a new window (or new parameters) needs a new graph --
+  // but not a new EXECUTABLE: cudaGraphExecUpdate accepts a re-captured graph of the same topology (new kernel arguments, launch
+  // shapes and conditional handles; tools/ubench/cgraph_update_test.cu) in ~10 us where cudaGraphInstantiate takes ~0.6 ms.  The
+  // executables of dropped loops are therefore kept (a few) and offered to build_lm_graph.
+  std::vector<cudaGraphExec_t> spare_execs;
+  void drop_lm_graphs(bool keep_execs = true) {
     for (auto &q : lm_graphs) {
-      cudaGraphExecDestroy(q.exec);
+      if (keep_execs && spare_execs.size() < 4) spare_execs.push_back(q.exec);
+      else cudaGraphExecDestroy(q.exec);
       cudaGraphDestroy(q.graph);
     }
     lm_graphs.clear();
+    if (!keep_execs) {
+      for (auto &x : spare_execs) cudaGraphExecDestroy(x);
+      spare_execs.clear();
+    }
   }
   void free_graph() {
     drop_lm_graphs();  // they hold the device pointers of the window
@@ -328,6 +338,7 @@ void ppo_ba_destroy(ppo_ba_handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
   h->free_graph();
+  h->drop_lm_graphs(false);  // ... and the spare executables
   cudaStreamSynchronize(h->st);
   h->dist_release();
   if (h->hstage) cudaFreeHost(h->hstage);
@@ -1237,8 +1248,22 @@ static int build_lm_graph(ppo_ba_handle *h, ppo_ba_handle::LmGraph *out) {
   out->nodes_iter = (int)(l1 - l0), out->nodes_trial = (int)(l2 - l1);
   static const bool timing = std::getenv("PPO_BA_TIMING") != nullptr;
   const auto ti0 = std::chrono::steady_clock::now();
-  CK(cudaGraphInstantiate(&out->exec, G, 0));
-  if (timing) std::fprintf(stderr, "[build_lm_graph] instantiate %8.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ti0).count());
+  out->exec = nullptr;
+  while (!out->exec && !h->spare_execs.empty()) {  // same topology as an earlier loop of this handle: update its executable in place
+    cudaGraphExec_t x = h->spare_execs.back();
+    h->spare_execs.pop_back();
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(x, G, &info) == cudaSuccess) {
+      out->exec = x;
+    } else {  // (other edge kinds present, say: the topology differs)
+      cudaGetLastError();
+      cudaGraphExecDestroy(x);
+    }
+  }
+  const bool updated = out->exec != nullptr;
+  if (!out->exec) CK(cudaGraphInstantiate(&out->exec, G, 0));
+  if (timing)
+    std::fprintf(stderr, "[build_lm_graph] %s %8.3f ms\n", updated ? "exec update" : "instantiate", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ti0).count());
   return PPO_OK;
 }
 
