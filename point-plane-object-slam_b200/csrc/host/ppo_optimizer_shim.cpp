@@ -779,14 +779,19 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     ppo::pose7_to_tcw_float(&o_kf[7 * (size_t)kf_slot[kf]], T);  // Converter::toCvMat(SE3Quat)
     kf->SetPose(float16_to_mat(T));
   }
-  for (size_t i = 0; i < graph_points.size(); i++) {  // points without a vertex are skipped (the reference dereferences NULL there, q1)
-    MapPoint *pMP = graph_points[i];
-    if (mixed) pMP->mnBALocalForKF = 0;
-    cv::Mat X(3, 1, CV_32F);
-    for (int k = 0; k < 3; k++) X.at<float>(k, 0) = (float)o_pt[3 * i + k];
-    pMP->SetWorldPos(X);
-    pMP->UpdateNormalAndDepth();
-  }
+  // points without a vertex are skipped (the reference dereferences NULL there, q1).  Every map point is written through its own
+  // mutexes (SetWorldPos, UpdateNormalAndDepth) and appears once in graph_points, so the loop is spread over the host threads; the
+  // caller still holds mMutexMapUpdate for the whole write-back, as the reference does.
+  g_pool.for_ranges((long)graph_points.size(), [&](long i0, long i1) {
+    for (long i = i0; i < i1; i++) {
+      MapPoint *pMP = graph_points[i];
+      if (mixed) pMP->mnBALocalForKF = 0;
+      cv::Mat X(3, 1, CV_32F);
+      for (int k = 0; k < 3; k++) X.at<float>(k, 0) = (float)o_pt[3 * i + k];
+      pMP->SetWorldPos(X);
+      pMP->UpdateNormalAndDepth();
+    }
+  });
   if (mixed) {
     for (KeyFrame *kf : w.lFixedCameras) {
       kf->mnBAFixedForKF = 0;

@@ -68,6 +68,27 @@ def test_threaded_flattening_equals_the_serial_loops_cpu(ppo, oracle_mod, mixed)
             assert np.array_equal(f[k], ref[k]), k
 
 
+def test_threaded_write_back_equals_the_serial_one_cpu(ppo, oracle_mod):
+    """The full call (flattening, oracle-backed solve, erase lists, write-back) on a window large enough for the host thread pool:
+    the map after the call must be the same whether the point loops ran on one thread or on several."""
+    import shim_lib
+    L = shim_lib.oracle_backed_lib()
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=10, n_fixed=2, n_pt=5000, n_pl=4, n_cu=2))
+    outs = []
+    try:
+        for n in (1, 4):
+            L.ppo_shim_set_threads(n)
+            st, counts, flat = shim_lib.run(g, backend=L)
+            outs.append((st, counts, flat))
+    finally:
+        L.ppo_shim_set_threads(1)
+    (sa, ca, fa), (sb, cb, fb) = outs
+    assert fa.c.n_pt > 4096
+    assert ca == cb and ca[0] > 0  # same erase lists (and some observations were erased)
+    for k in ("kf_pose", "pt_xyz", "pl_coef", "cu_state"):
+        assert np.array_equal(getattr(sa, k), getattr(sb, k)), k
+
+
 def test_points_only_entry_point_flattening_cpu(ppo):
     import shim_lib
     g = ppo.synth.make_graph(ppo.synth.config(0))
