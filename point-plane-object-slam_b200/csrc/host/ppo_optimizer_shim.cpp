@@ -243,6 +243,19 @@ struct Mirror {
       }
     pool.swap(np);
   }
+  // the row of pMP if it is current, else null (read-only: safe from several threads at once)
+  const Row *find(MapPoint *pMP) const {
+#ifdef PPO_HAVE_OBS_VERSION
+    const unsigned long ver = pMP->mnObsVersion;
+    const size_t id = pMP->mnId;
+    if (ver == 0 || id >= rows.size()) return nullptr;
+    const Row &r = rows[id];
+    return (r.mp == pMP && r.version == ver) ? &r : nullptr;
+#else
+    (void)pMP;
+    return nullptr;
+#endif
+  }
   // current row of pMP (rebuilt from GetObservations() when the map point changed or is new)
   const Row &row(MapPoint *pMP) {
 #ifdef PPO_HAVE_OBS_VERSION
@@ -314,9 +327,16 @@ class HostPool {
     quit_ = false;
     n_ = std::max(1, std::min(64, n));
   }
+  // number of ranges for_ranges / for_parts split n indices into
+  int parts_for(long n, long min_per_part = 2048) const { return (int)std::min<long>(n_, std::max<long>(1, n / min_per_part)); }
+  // f(part, begin, end): like for_ranges, for loops that leave one result per range (part = 0 .. parts_for(n) - 1, in index order)
+  void for_parts(long n, const std::function<void(int, long, long)> &f, long min_per_part = 2048) {
+    const int parts = parts_for(n, min_per_part);
+    for_ranges(n, [&](long b, long e) { f(parts <= 1 ? 0 : (int)((b * parts + n - 1) / n), b, e); }, min_per_part);
+  }
   // f(begin, end) on disjoint ranges covering [0, n); returns when all ranges are done
-  void for_ranges(long n, const std::function<void(long, long)> &f) {
-    const int parts = (int)std::min<long>(n_, std::max<long>(1, n / 2048));
+  void for_ranges(long n, const std::function<void(long, long)> &f, long min_per_part = 2048) {
+    const int parts = parts_for(n, min_per_part);
     if (parts <= 1) {
       f(0, n);
       return;
@@ -367,6 +387,14 @@ static HostPool g_pool;  // (used under the mutex of the local-BA slot)
 
 // stage A: Optimizer.cc:1997-2100 (mixed) / :463-514 (points only)
 static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = true) {
+  static const bool timing = std::getenv("PPO_BA_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto tick = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ppo shim]   A: %-25s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   w.lLocalKeyFrames.push_back(pKF);
   pKF->mnBALocalForKF = pKF->mnId;
   const std::vector<KeyFrame *> vNeighKFs = pKF->GetVectorCovisibleKeyFrames();
@@ -374,13 +402,41 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = tru
     pKFi->mnBALocalForKF = pKF->mnId;
     if (!pKFi->isBad()) w.lLocalKeyFrames.push_back(pKFi);
   }
-  for (KeyFrame *kf : w.lLocalKeyFrames) {
-    std::vector<MapPoint *> vpMPs = kf->GetMapPointMatches();
-    for (MapPoint *pMP : vpMPs)
-      if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) {
-        w.lLocalMapPoints.push_back(pMP);
-        pMP->mnBALocalForKF = pKF->mnId;
+  {
+    // Two phases with the result of the reference's loop: (1) every local key-frame's matches are copied (under the key-frame's mutex, as
+    // the reference does) and the live, not yet marked map points among them kept with their ids -- the part that walks 10^5..10^6 pointers
+    // into the map, spread over the host threads by key-frame; (2) the first-seen order, serially in key-frame order, on a byte map
+    // indexed by MapPoint::mnId instead of a second look at every map point.  The mnBALocalForKF marks are set in the pass that reads
+    // the mirror rows below (one look at each local map point).
+    struct Cand {
+      MapPoint *p;
+      size_t id;
+    };
+    static std::vector<std::vector<Cand>> cand;  // (guarded by the mutex of the local-BA slot; keep their memory across calls)
+    static std::vector<uint8_t> seen;
+    const size_t nkf = w.lLocalKeyFrames.size();
+    if (cand.size() < nkf) cand.resize(nkf);
+    g_pool.for_ranges((long)nkf, [&](long i0, long i1) {
+      for (long i = i0; i < i1; i++) {
+        const std::vector<MapPoint *> vpMPs = w.lLocalKeyFrames[i]->GetMapPointMatches();
+        std::vector<Cand> &c = cand[i];
+        c.clear();
+        for (MapPoint *pMP : vpMPs)
+          if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) c.push_back({pMP, (size_t)pMP->mnId});
       }
+    }, 8);
+    tick("live matches per key-frame");
+    size_t max_id = 0;
+    for (size_t i = 0; i < nkf; i++)
+      for (const Cand &c : cand[i]) max_id = std::max(max_id, c.id);
+    seen.assign(max_id + 1, 0);
+    for (size_t i = 0; i < nkf; i++)
+      for (const Cand &c : cand[i])
+        if (!seen[c.id]) {
+          seen[c.id] = 1;
+          w.lLocalMapPoints.push_back(c.p);
+        }
+    tick("first-seen order");
   }
   if (mixed) {
     for (KeyFrame *kf : w.lLocalKeyFrames)
@@ -403,25 +459,69 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = tru
       if (!pKFi->isBad()) w.lFixedCameras.push_back(pKFi);
     }
   };
+  tick("cuboids, planes");
   g_mirror.compact();
-  w.obs_row.reserve(w.lLocalMapPoints.size());
-  for (MapPoint *pMP : w.lLocalMapPoints) {
-    const Mirror::Row &r = g_mirror.row(pMP);
-    w.obs_row.push_back({r.off, r.n});
-  }
-  // (after the loop: a row rebuilt later may have moved the pool)
   {
-    std::vector<uint8_t> seen;  // by KeyFrame::mnId: one look at the key-frame itself per key-frame, not per observation
-    const ObsRec *pool = g_mirror.pool.data();
-    for (auto &r : w.obs_row)
-      for (uint32_t q = r.first; q < r.first + r.second; q++) {
-        const ObsRec &o = pool[q];
-        if (o.kf_id < seen.size() && seen[o.kf_id]) continue;
-        if (o.kf_id >= seen.size()) seen.resize((size_t)o.kf_id + 1 + seen.size(), 0);
-        seen[o.kf_id] = 1;
-        add_fixed(o.kf);
+    // mirror rows: the unchanged ones (one version compare per map point) are looked up by all host threads, the others are rebuilt
+    // serially afterwards (a rebuild appends to the pool); the pass also leaves the mnBALocalForKF mark of the reference's loop
+    const size_t NP = w.lLocalMapPoints.size();
+    const uint32_t MISS = 0xffffffffu;
+    w.obs_row.assign(NP, {MISS, 0});
+    std::atomic<long long> hits{0};
+    g_pool.for_ranges((long)NP, [&](long i0, long i1) {
+      long long h = 0;
+      for (long ip = i0; ip < i1; ip++) {
+        MapPoint *pMP = w.lLocalMapPoints[ip];
+        pMP->mnBALocalForKF = pKF->mnId;
+        if (const Mirror::Row *r = g_mirror.find(pMP)) {
+          w.obs_row[ip] = {r->off, r->n};
+          h++;
+        }
+      }
+      hits += h;
+    });
+    g_mirror.hits += hits.load();
+    for (size_t ip = 0; ip < NP; ip++)
+      if (w.obs_row[ip].first == MISS) {
+        const Mirror::Row &r = g_mirror.row(w.lLocalMapPoints[ip]);
+        w.obs_row[ip] = {r.off, r.n};
       }
   }
+  tick("mirror rows");
+  {
+    // fixed cameras in the order of their first appearance among the observations: every range of map points lists the key-frames it
+    // meets (first appearance inside the range); the lists are merged in range order, which is the order of the serial scan
+    struct Seen {
+      uint32_t id;
+      KeyFrame *kf;
+    };
+    const long NP = (long)w.obs_row.size();
+    std::vector<std::vector<Seen>> found((size_t)g_pool.parts_for(NP));
+    const ObsRec *pool = g_mirror.pool.data();
+    g_pool.for_parts(NP, [&](int part, long i0, long i1) {
+      std::vector<uint8_t> seen;  // by KeyFrame::mnId: one entry per key-frame, not per observation
+      std::vector<Seen> &out = found[(size_t)part];
+      for (long ip = i0; ip < i1; ip++) {
+        const auto &r = w.obs_row[ip];
+        for (uint32_t q = r.first; q < r.first + r.second; q++) {
+          const ObsRec &o = pool[q];
+          if (o.kf_id < seen.size() && seen[o.kf_id]) continue;
+          if (o.kf_id >= seen.size()) seen.resize((size_t)o.kf_id + 1 + seen.size(), 0);
+          seen[o.kf_id] = 1;
+          out.push_back({o.kf_id, o.kf});
+        }
+      }
+    });
+    std::vector<uint8_t> seen;
+    for (auto &list : found)
+      for (const Seen &f : list) {
+        if (f.id < seen.size() && seen[f.id]) continue;
+        if (f.id >= seen.size()) seen.resize((size_t)f.id + 1 + seen.size(), 0);
+        seen[f.id] = 1;
+        add_fixed(f.kf);
+      }
+  }
+  tick("fixed cameras");
   if (mixed)
     for (MapCuboid *pMC : w.lLocalMapCuboids) {
       std::unordered_map<KeyFrame *, size_t> observations = pMC->GetObservations();
@@ -475,6 +575,12 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     const float in[5] = {slots[i].kf->fx, slots[i].kf->fy, slots[i].kf->cx, slots[i].kf->cy, slots[i].kf->mbf};
     F.kf_intr.insert(F.kf_intr.end(), in, in + 5);
   }
+  auto slot_of = [&](KeyFrame *k) -> int {  // slot of a key-frame of the window, -1 otherwise (O(1): the edge loops below look up 10^4 observations)
+    const size_t id = k->mnId;
+    if (id >= slot_of_id.size()) return -1;
+    const int sl = slot_of_id[id];
+    return (sl >= 0 && slots[sl].kf == k) ? sl : -1;
+  };
   std::map<MapCuboid *, int> cu_index;
   for (MapCuboid *pMC : w.lLocalMapCuboids) {  // :2158-2178: estimate = cuboid_global_data, roll/pitch and height locked
     cu_index[pMC] = (int)cu_index.size();
@@ -517,14 +623,14 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
           for (auto &mit : obs) {
             KeyFrame *pKFi = mit.first;
             if (pKFi->isBad()) continue;
-            auto it = kf_slot.find(pKFi);
-            if (it == kf_slot.end()) continue;  // optimizer.vertex(pKFi->mnId) == NULL -> continue (:2235-2236, q8)
+            const int sl_kf = slot_of(pKFi);
+            if (sl_kf < 0) continue;  // optimizer.vertex(pKFi->mnId) == NULL -> continue (:2235-2236, q8)
             cv::Mat m = pKFi->mvPlaneCoefficients[mit.second];
             const float c4[4] = {m.at<float>(0, 0), m.at<float>(1, 0), m.at<float>(2, 0), m.at<float>(3, 0)};
             double c[4];
             ppo::plane_float_to_coef(c4, c);
             F.ple_plane.push_back(pl_index[pMP]);
-            F.ple_kf.push_back(it->second);
+            F.ple_kf.push_back(sl_kf);
             F.ple_kind.push_back((uint8_t)kind);
             F.ple_meas.insert(F.ple_meas.end(), c, c + 4);
             const double info[3] = {kind == PPO_PLANE_OBS ? angleInfo : pvInfo, kind == PPO_PLANE_OBS ? angleInfo : pvInfo, kind == PPO_PLANE_OBS ? disInfo : 0.0};
@@ -608,8 +714,8 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
         for (auto &mit : observations) {
           KeyFrame *pKFi = mit.first;
           if (pKFi->isBad()) continue;
-          auto it = kf_slot.find(pKFi);
-          if (it == kf_slot.end()) continue;
+          const int sl_kf = slot_of(pKFi);
+          if (sl_kf < 0) continue;
           const MapCuboid *local_object = pKFi->local_cuboids[mit.second];
           const int object_boundary_margin = 5;
           const cv::Rect bbox_2d = local_object->bbox_2d;
@@ -622,7 +728,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
           else
             for (int i = 0; i < 8; i++) m[2 * i] = local_object->box_corners_2d(0, i), m[2 * i + 1] = local_object->box_corners_2d(1, i);
           const double s = (pass == 0 ? ba_weight_bbox : ba_weight_corner) * local_object->meas_quality;
-          F.cbe_kf.push_back(it->second);
+          F.cbe_kf.push_back(sl_kf);
           F.cbe_cuboid.push_back(cu_index[pMCuboid]);
           F.cbe_kind.push_back(pass == 0 ? PPO_CUBOID_BBOX : PPO_CUBOID_CORNER);
           F.cbe_meas.insert(F.cbe_meas.end(), m, m + 16);
@@ -637,8 +743,8 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
         for (auto &mit : observations) {
           KeyFrame *pKFi = mit.first;
           if (pKFi->isBad()) continue;
-          auto it = kf_slot.find(pKFi);
-          if (it == kf_slot.end()) continue;
+          const int sl_kf = slot_of(pKFi);
+          if (sl_kf < 0) continue;
           // the reference reads the measurement from the LANDMARK list of the key-frame, mvpMapCuboid[idx] (:1779), not from its local
           // detections, and addresses the vertex by object_graph_id (:1783); a vertex that is not in the window would be a NULL vertex there
           if (mit.second >= pKFi->mvpMapCuboid.size() || !pKFi->mvpMapCuboid[mit.second]) continue;
@@ -650,7 +756,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
           double m[16] = {0};
           cuboid_to10(local_object->cuboid_local_meas, m);
           const double s = ba_weight_SE3 * 0.75;  // meas_quality = 0.75 (:1788)
-          F.cbe_kf.push_back(it->second);
+          F.cbe_kf.push_back(sl_kf);
           F.cbe_cuboid.push_back(cu);
           F.cbe_kind.push_back(PPO_CUBOID_SE3);
           F.cbe_meas.insert(F.cbe_meas.end(), m, m + 16);
