@@ -412,26 +412,37 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = tru
       MapPoint *p;
       size_t id;
     };
-    static std::vector<std::vector<Cand>> cand;  // (guarded by the mutex of the local-BA slot; keep their memory across calls)
-    static std::vector<uint8_t> seen;
+    // (1) per RANGE of key-frames: candidates in key-frame order, already without the repeats inside the range
+    static std::vector<std::vector<Cand>> cand;        // (guarded by the mutex of the local-BA slot; keep their memory across calls)
+    static std::vector<std::vector<uint8_t>> seen_of;  // per range: byte map by MapPoint::mnId
     const size_t nkf = w.lLocalKeyFrames.size();
-    if (cand.size() < nkf) cand.resize(nkf);
-    g_pool.for_ranges((long)nkf, [&](long i0, long i1) {
+    const int parts = g_pool.parts_for((long)nkf, 8);
+    if ((int)cand.size() < parts) cand.resize(parts), seen_of.resize(parts);
+    g_pool.for_parts((long)nkf, [&](int part, long i0, long i1) {
+      std::vector<Cand> &c = cand[part];
+      std::vector<uint8_t> &seen = seen_of[part];
+      c.clear();
+      std::fill(seen.begin(), seen.end(), 0);
       for (long i = i0; i < i1; i++) {
         const std::vector<MapPoint *> vpMPs = w.lLocalKeyFrames[i]->GetMapPointMatches();
-        std::vector<Cand> &c = cand[i];
-        c.clear();
         for (MapPoint *pMP : vpMPs)
-          if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) c.push_back({pMP, (size_t)pMP->mnId});
+          if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) {
+            const size_t id = pMP->mnId;
+            if (id >= seen.size()) seen.resize(id + 1 + seen.size() / 2, 0);
+            if (seen[id]) continue;
+            seen[id] = 1;
+            c.push_back({pMP, id});
+          }
       }
     }, 8);
     tick("live matches per key-frame");
+    // (2) merge in range order
+    static std::vector<uint8_t> seen;
     size_t max_id = 0;
-    for (size_t i = 0; i < nkf; i++)
-      for (const Cand &c : cand[i]) max_id = std::max(max_id, c.id);
+    for (int q = 0; q < parts; q++) max_id = std::max(max_id, seen_of[q].size());
     seen.assign(max_id + 1, 0);
-    for (size_t i = 0; i < nkf; i++)
-      for (const Cand &c : cand[i])
+    for (int q = 0; q < parts; q++)
+      for (const Cand &c : cand[q])
         if (!seen[c.id]) {
           seen[c.id] = 1;
           w.lLocalMapPoints.push_back(c.p);
