@@ -492,11 +492,67 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = tru
       hits += h;
     });
     g_mirror.hits += hits.load();
+    std::vector<size_t> miss;
     for (size_t ip = 0; ip < NP; ip++)
-      if (w.obs_row[ip].first == MISS) {
+      if (w.obs_row[ip].first == MISS) miss.push_back(ip);
+    if (miss.size() < 4096) {
+      for (size_t ip : miss) {
         const Mirror::Row &r = g_mirror.row(w.lLocalMapPoints[ip]);
         w.obs_row[ip] = {r.off, r.n};
       }
+    } else {
+      // many rows to (re)build -- a new map, or a build of the reference without the version counter: the observation maps are copied and
+      // flattened by all host threads into per-range buffers (what Mirror::row does for one point), then appended to the pool in order
+      struct Built {
+        size_t id;
+        unsigned long version;
+        uint32_t n;
+      };
+      const long NM = (long)miss.size();
+      std::vector<Built> built(miss.size());
+      std::vector<std::vector<ObsRec>> recs((size_t)g_pool.parts_for(NM));
+      g_pool.for_parts(NM, [&](int part, long k0, long k1) {
+        std::vector<ObsRec> &out = recs[(size_t)part];
+        for (long k = k0; k < k1; k++) {
+          MapPoint *pMP = w.lLocalMapPoints[miss[k]];
+#ifdef PPO_HAVE_OBS_VERSION
+          const unsigned long ver = pMP->mnObsVersion;
+#else
+          const unsigned long ver = 0;
+#endif
+          const std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
+          const size_t first = out.size();
+          for (auto &mit : observations) {
+            KeyFrame *pKFi = mit.first;
+            const size_t idx = mit.second;
+            const cv::KeyPoint &kpUn = pKFi->mvKeysUn[idx];
+            out.push_back({pKFi, (uint32_t)idx, (uint32_t)pKFi->mnId, kpUn.pt.x, kpUn.pt.y, pKFi->mvuRight[idx] < 0 ? -1.0f : pKFi->mvuRight[idx],
+                           pKFi->mvInvLevelSigma2[kpUn.octave]});
+          }
+          std::sort(out.begin() + first, out.end(), [](const ObsRec &a, const ObsRec &b) { return a.kf_id < b.kf_id; });
+          built[k] = {(size_t)pMP->mnId, ver, (uint32_t)observations.size()};
+        }
+      });
+      size_t max_id = 0, total = 0;
+      for (const Built &bt : built) max_id = std::max(max_id, bt.id), total += bt.n;
+      if (max_id >= g_mirror.rows.size()) g_mirror.rows.resize(std::max(max_id + 1, g_mirror.rows.size() * 2));
+      g_mirror.pool.reserve(g_mirror.pool.size() + total);
+      long k = 0;
+      for (size_t part = 0; part < recs.size(); part++) {
+        const long k1 = recs.size() <= 1 ? NM : (long)(NM * (long)(part + 1) / (long)recs.size());
+        uint32_t off = (uint32_t)g_mirror.pool.size();
+        for (; k < k1; k++) {
+          Mirror::Row &r = g_mirror.rows[built[k].id];
+          if (r.mp) g_mirror.live -= r.n;
+          r.mp = w.lLocalMapPoints[miss[k]], r.version = built[k].version, r.off = off, r.n = built[k].n;
+          g_mirror.live += r.n;
+          w.obs_row[miss[k]] = {r.off, r.n};
+          off += r.n;
+        }
+        g_mirror.pool.insert(g_mirror.pool.end(), recs[part].begin(), recs[part].end());
+      }
+      g_mirror.misses += NM;
+    }
   }
   tick("mirror rows");
   {

@@ -8,12 +8,8 @@ def _graph(ppo, **kw):
     return ppo.synth.make_graph(ppo.synth.config(1, n_kf=14, n_fixed=3, n_pt=900, n_pl=6, n_cu=3, **kw))
 
 
-def test_flattening_reproduces_the_flat_graph_cpu(ppo):
-    """With the stop flag set on entry the shim collects + flattens the window and returns before touching the GPU
-    (Optimizer.cc:2723-2725): the flattened graph must equal the flat graph the mock map was built from."""
-    import shim_lib
-    g = _graph(ppo, corners_2d=1)
-    st, counts, flat = shim_lib.run(g, stop=True)
+def _assert_flat_matches_source(g, st, counts, flat, landmarks_all_local=True):
+    """The flattened graph of a stop-at-entry call must equal the flat graph the mock map was built from."""
     assert counts == [0, 0, 0, 0]  # nothing written back, nothing erased
     assert np.allclose(st.kf_pose, g["kf_pose"], atol=2e-7)  # untouched (float32 round trip of the pose)
     # points seen by no local key-frame are not part of the reference's local window: compare the others
@@ -32,6 +28,8 @@ def test_flattening_reproduces_the_flat_graph_cpu(ppo):
         assert np.array_equal(flat["pe_kf"][frp[q]:frp[q + 1]], g["pe_kf"][rp[p]:rp[p + 1]])
         assert np.array_equal(flat["pe_obs"][frp[q]:frp[q + 1]], g["pe_obs"][rp[p]:rp[p + 1]])
         assert np.allclose(flat["pe_invsigma2"][frp[q]:frp[q + 1]], g["pe_invsigma2"][rp[p]:rp[p + 1]], rtol=1e-6)
+    if not landmarks_all_local:  # (a plane / cuboid seen by fixed key-frames only is not part of the window: the generic graph may have some)
+        return
     # planes / cuboids and their edges (order of edges may differ: compare as multisets)
     assert flat.c.n_pl == g.c.n_pl and flat.c.n_cu == g.c.n_cu
     assert np.allclose(np.sort(flat["pl_coef"], axis=0), np.sort(g["pl_coef"], axis=0), atol=1e-6)
@@ -42,6 +40,15 @@ def test_flattening_reproduces_the_flat_graph_cpu(ppo):
     assert np.allclose(np.sort(flat["cbe_meas"].ravel()), np.sort(g["cbe_meas"].ravel()))
     assert np.allclose(np.sort(flat["cbe_info"]), np.sort(g["cbe_info"]))
     assert np.allclose(np.sort(flat["cpe_info"].ravel()), np.sort(g["cpe_info"].ravel()))
+
+
+def test_flattening_reproduces_the_flat_graph_cpu(ppo):
+    """With the stop flag set on entry the shim collects + flattens the window and returns before touching the GPU
+    (Optimizer.cc:2723-2725): the flattened graph must equal the flat graph the mock map was built from."""
+    import shim_lib
+    g = _graph(ppo, corners_2d=1)
+    st, counts, flat = shim_lib.run(g, stop=True)
+    _assert_flat_matches_source(g, st, counts, flat)
 
 
 @pytest.mark.parametrize("mixed", [True, False])
@@ -56,7 +63,10 @@ def test_threaded_flattening_equals_the_serial_loops_cpu(ppo, oracle_mod, mixed)
         for n in (1, 5, 8, 3, 8):
             L.ppo_shim_set_threads(n)
             assert L.ppo_shim_get_threads() == n
-            flats.append(shim_lib.run(g, mixed=mixed, stop=True, backend=L)[2])
+            st, counts, flat = shim_lib.run(g, mixed=mixed, stop=True, backend=L)
+            if mixed:  # (also against the source: a window of this size takes the batched mirror rebuild and the threaded collection)
+                _assert_flat_matches_source(g, st, counts, flat, landmarks_all_local=False)
+            flats.append(flat)
     finally:
         L.ppo_shim_set_threads(1)
     ref = flats[0]
