@@ -495,7 +495,7 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = tru
     std::vector<size_t> miss;
     for (size_t ip = 0; ip < NP; ip++)
       if (w.obs_row[ip].first == MISS) miss.push_back(ip);
-    if (miss.size() < 4096) {
+    if (miss.size() < 4096 || g_pool.threads() == 1) {
       for (size_t ip : miss) {
         const Mirror::Row &r = g_mirror.row(w.lLocalMapPoints[ip]);
         w.obs_row[ip] = {r.off, r.n};
