@@ -222,8 +222,15 @@ struct ppo_ba_handle {
   std::vector<cudaGraphExec_t> spare_execs;
   void drop_lm_graphs(bool keep_execs = true) {
     for (auto &q : lm_graphs) {
-      if (keep_execs && spare_execs.size() < 4) spare_execs.push_back(q.exec);
-      else cudaGraphExecDestroy(q.exec);
+      if (keep_execs) {
+        if (spare_execs.size() >= 6) {  // (oldest out)
+          cudaGraphExecDestroy(spare_execs.front());
+          spare_execs.erase(spare_execs.begin());
+        }
+        spare_execs.push_back(q.exec);
+      } else {
+        cudaGraphExecDestroy(q.exec);
+      }
       cudaGraphDestroy(q.graph);
     }
     lm_graphs.clear();
@@ -1249,15 +1256,16 @@ static int build_lm_graph(ppo_ba_handle *h, ppo_ba_handle::LmGraph *out) {
   static const bool timing = std::getenv("PPO_BA_TIMING") != nullptr;
   const auto ti0 = std::chrono::steady_clock::now();
   out->exec = nullptr;
-  while (!out->exec && !h->spare_execs.empty()) {  // same topology as an earlier loop of this handle: update its executable in place
-    cudaGraphExec_t x = h->spare_execs.back();
-    h->spare_execs.pop_back();
+  // same topology as an earlier loop of this handle: update its executable in place.  An executable of another topology (a window
+  // with other edge kinds) stays in the list for a later window of its kind: it is only ever launched after a successful update,
+  // which rewrites every node.
+  for (size_t q = h->spare_execs.size(); q-- > 0 && !out->exec;) {
     cudaGraphExecUpdateResultInfo info;
-    if (cudaGraphExecUpdate(x, G, &info) == cudaSuccess) {
-      out->exec = x;
-    } else {  // (other edge kinds present, say: the topology differs)
+    if (cudaGraphExecUpdate(h->spare_execs[q], G, &info) == cudaSuccess) {
+      out->exec = h->spare_execs[q];
+      h->spare_execs.erase(h->spare_execs.begin() + (long)q);
+    } else {
       cudaGetLastError();
-      cudaGraphExecDestroy(x);
     }
   }
   const bool updated = out->exec != nullptr;

@@ -213,6 +213,31 @@ def test_point_edge_outliers_on_the_device_equal_the_host_test(ppo, oracle_mod):
         e.close()
 
 
+def test_one_handle_across_different_windows_equals_fresh_handles(ppo):
+    """A handle keeps the graph executables of its earlier windows and updates them in place for the next one (cudaGraphExecUpdate), or
+    instantiates a new one when the topology differs (other edge kinds present): windows of different sizes and kinds solved one after
+    the other on ONE handle must give exactly what a fresh handle gives for each of them."""
+    cfgs = [dict(c=1, n_kf=8, n_fixed=2, n_pt=300, n_pl=4, n_cu=3), dict(c=0, n_kf=6, n_fixed=2, n_pt=500),
+            dict(c=1, n_kf=12, n_fixed=3, n_pt=900, n_pl=6, n_cu=2), dict(c=1, n_kf=8, n_fixed=2, n_pt=300, n_pl=4, n_cu=3),
+            dict(c=1, n_kf=9, n_fixed=2, n_pt=350, n_pl=0, n_cu=2)]
+    one = ppo.LocalBA()
+    for cfg in cfgs:
+        cfg = dict(cfg)
+        g = ppo.synth.make_graph(ppo.synth.config(cfg.pop("c"), **cfg))
+        outs = []
+        for h in (one, ppo.LocalBA()):
+            h.set_graph(g)
+            r = h.local_ba()
+            outs.append((r, h.get_state()))
+        (ra, sa), (rb, sb) = outs
+        assert (ra.round1.iterations, ra.round2.iterations, ra.round1.total_trials, ra.round2.total_trials) == (
+            rb.round1.iterations, rb.round2.iterations, rb.round1.total_trials, rb.round2.total_trials)
+        assert ra.round2.chi2_final == rb.round2.chi2_final
+        for k in ("kf_pose", "pt_xyz", "pl_coef", "cu_state"):
+            assert np.array_equal(getattr(sa, k), getattr(sb, k)), (cfg, k)
+    one.close()
+
+
 def test_config1_mixed_window(ppo, oracle_mod):
     """BASELINE.json configs[1]: 50 KF / 20k points / 50 planes / 10 cuboids."""
     g = ppo.synth.make_graph(ppo.synth.config(1))
