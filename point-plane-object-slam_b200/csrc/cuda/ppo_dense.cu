@@ -1232,6 +1232,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
       auto deps_ready = [&](int slot) -> bool {
         const int type = sm.op[slot][0], k = sm.op[slot][1], i = sm.op[slot][2], j = sm.op[slot][3];
         if (type == 0) return ready(k, k, base + k + 1) && (k == 0 || ready(i, k, base + k));
+        if (type == 2) return ready(i, k, base + k + 1);  // the panel tile I forward has arrived from its producer
         return ready(i, k, base + k + 1) && (j == i || ready(j, k, base + k + 1)) && (k == 0 || ready(i, j, base + k));
       };
       auto issue = [&](int slot) {
@@ -1241,6 +1242,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
           mbar_expect_tx(&sm.full[slot], 2 * TILE_BYTES);
           bulk_g2s(sm.T[3 * slot], tile(i, k), TILE_BYTES, &sm.full[slot]);
           bulk_g2s(sm.T[3 * slot + 1], a.Winv + (size_t)k * TILE, TILE_BYTES, &sm.full[slot]);
+        } else if (type == 2) {
+          mbar_expect_tx(&sm.full[slot], TILE_BYTES);
+          bulk_g2s(sm.T[3 * slot], tile(i, k), TILE_BYTES, &sm.full[slot]);
         } else {
           const bool diag = i == j;
           mbar_expect_tx(&sm.full[slot], (diag ? 2 : 3) * TILE_BYTES);
@@ -1261,8 +1265,20 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
           if (rel_t[tail] == 0) {  // a panel tile: staged in the first buffer of the set -> every rank
             // (all panel tiles of column k become ready together, right after W_k: the owner of column k+1, whose critical path needs
             // the first of them next, gets its copies ahead of the rest of the burst)
-            dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail],
-                              own(rel_v[tail] - base), all_ranks);
+            // With forwarding (d.p.fwd, PPO_DIST_FORWARD=1; off by default) a panel tile of tile row i leaves its producer ONCE, for the
+            // owner of column i -- the rank that needs it first (its updates of column i all read it) --, which passes it on to the other
+            // ranks (operation type 2 of its queue): every rank's links carry a share of the panel instead of the producer's links carrying
+            // world - 1 copies of it.  Measured on 8 GPUs at n = 7794: 4.00 ms without, 4.61 ms with -- the broadcast is not what bounds the
+            // solve, the second hop costs more than the spread egress gains.
+            const int f = own(rel_i[tail]);
+            if (d.p.fwd && f != R)
+              dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail], f, (1u << R) | (1u << f));
+            else
+              dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail],
+                                own(rel_v[tail] - base), all_ranks);
+          } else if (rel_t[tail] == 2) {  // a panel tile of another rank's column that I pass on: to everybody but its producer and me
+            dist_push_publish(d.p, d.p.S, tile_off(rel_i[tail], rel_j[tail]), sm.T[3 * tail], rel_i[tail] * vs + rel_j[tail], rel_v[tail], -1,
+                              all_ranks & ~(1u << R) & ~(1u << own(rel_j[tail])));
           } else {                 // a trailing update of one of my tiles: stays here
             __threadfence();
             st_release(&a.ver[rel_i[tail] * vs + rel_j[tail]], rel_v[tail]);
@@ -1313,7 +1329,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_dist(CholDistArgs d) {
       if (type < 0 || *(volatile int *)&sm.abort) break;
       TilePtr A = sm.T[3 * cur], B = sm.T[3 * cur + 1], C = sm.T[3 * cur + 2];
       const bool one_row = (i == Tc);
-      if (!one_row || warp == 0) {
+      if (type != 2 && (!one_row || warp == 0)) {  // (type 2: the tile only passes through this CTA's shared memory)
         double acc[8][2];
 #pragma unroll
         for (int q = 0; q < 8; q++) acc[q][0] = acc[q][1] = 0.0;
@@ -1516,13 +1532,16 @@ void dense_ldlt_fallback(double *S_copy, int n, int max_n, double *x, int *not_s
 // ---- distributed variant ------------------------------------------------------------------------------------------------------
 // worker queue of one rank, level by level: T_k(i) for i = k+2 .. Tc when the rank owns column k, then U_k(i, j) for its columns
 // j > k (the diagonal update U_k(k+1,k+1) and T_k(k+1) belong to the critical-path CTA of the owner)
-void dense_dist_build_ops(int Tc, int rank, int world, std::vector<unsigned> *ops, int blk) {
+void dense_dist_build_ops(int Tc, int rank, int world, std::vector<unsigned> *ops, int blk, int fwd) {
   ops->clear();
   auto pack = [](int type, int k, int i, int j) { return (unsigned)type << 24 | (unsigned)k << 16 | (unsigned)i << 8 | (unsigned)j; };
   auto own = [&](int j) { return (j / blk) % world; };
   for (int k = 0; k < Tc; k++) {
     if (own(k) == rank)
       for (int i = k + 2; i <= Tc; i++) ops->push_back(pack(0, k, i, k));
+    else if (fwd && world > 2)  // panel tiles of my tile rows produced elsewhere: I pass them on (type 2), before my updates of the level
+      for (int i = k + 2; i <= Tc; i++)
+        if (own(i) == rank) ops->push_back(pack(2, k, i, k));
     for (int j = k + 1; j < Tc; j++) {
       if (own(j) != rank) continue;
       for (int i = (j == k + 1 ? j + 1 : j); i <= Tc; i++) ops->push_back(pack(1, k, i, j));

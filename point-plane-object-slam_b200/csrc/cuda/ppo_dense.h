@@ -38,9 +38,11 @@ void dense_setup_device(int dev);
 // sig = ws + 64 bytes of rank q's workspace.  `seq` numbers the solves of the window and must agree on all ranks.
 constexpr int DIST_MAX = 8;
 constexpr int DIST_BLOCK_DEFAULT = 1;
+constexpr int DIST_FORWARD_DEFAULT = 0;
 struct DistPeers {
   int rank, world;
   int blk;  // ownership block: tile column j belongs to rank (j / blk) mod world (the critical path crosses NVLink once per block)
+  int fwd;  // 1: a panel tile of tile row i goes from its producer to the owner of column i only, which forwards it (world > 2)
   double *S[DIST_MAX];
   double *Winv[DIST_MAX];
   int *ver[DIST_MAX];
@@ -51,7 +53,7 @@ inline void dense_dist_set_peer(DistPeers *p, int q, double *S, double *Winv, vo
   p->ver[q] = reinterpret_cast<int *>(reinterpret_cast<char *>(ws) + 256);
   p->sig[q] = reinterpret_cast<int *>(reinterpret_cast<char *>(ws) + 64);
 }
-void dense_dist_build_ops(int Tc, int rank, int world, std::vector<unsigned> *ops, int blk = 1);
+void dense_dist_build_ops(int Tc, int rank, int world, std::vector<unsigned> *ops, int blk = 1, int fwd = 0);
 // every rank has accumulated ITS partial reduced system into its own S: owner-side sum of all ranks' copies (pulled over NVLink)
 void dense_dist_reduce(const DistPeers &p, int n, int max_n, void *ws, int seq, cudaStream_t st, long long *launches, int sm_cap = 0);
 // factorisation + backward substitution; d_ops = dense_dist_build_ops(...) on the device; x is computed on every rank

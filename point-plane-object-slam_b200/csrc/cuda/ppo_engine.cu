@@ -482,6 +482,7 @@ static int dist_setup(ppo_ba_handle *h) {
     cudaFree(d_slots);
     h->dist_peers.rank = h->rank, h->dist_peers.world = h->world;
     h->dist_peers.blk = std::getenv("PPO_DIST_BLOCK") ? std::max(1, std::atoi(std::getenv("PPO_DIST_BLOCK"))) : DIST_BLOCK_DEFAULT;
+    h->dist_peers.fwd = std::getenv("PPO_DIST_FORWARD") ? (std::atoi(std::getenv("PPO_DIST_FORWARD")) != 0) : DIST_FORWARD_DEFAULT;
     for (int q = 0; q < h->world; q++) {
       if (slots[q].bytes != bytes) {
         h->err = "sharded window: the ranks disagree on the size of the reduced system";
@@ -1127,7 +1128,7 @@ static int enqueue_dense_solve(ppo_ba_handle *h) {
     const int Tc = dense_num_blocks(h->n_p);
     if (Tc != h->dist_ops_tc) {  // this rank's operation queue for the current number of tile columns
       std::vector<unsigned> ops;
-      dense_dist_build_ops(Tc, h->rank, h->world, &ops, h->dist_peers.blk);
+      dense_dist_build_ops(Tc, h->rank, h->world, &ops, h->dist_peers.blk, h->dist_peers.fwd);
       CK(cudaStreamSynchronize(h->st));
       if (h->d_dist_ops) cudaFree(h->d_dist_ops);
       h->d_dist_ops = nullptr;

@@ -26,6 +26,7 @@ using namespace ppo;
   } while (0)
 
 static int g_blk = 1;
+static int g_fwd = 0;  // PPO_DIST_FORWARD=1: panel tiles go to the owner of their tile row's column, which forwards them
 static int run(int n, int world, bool virt, int reps) {
   const int max_n = n;
   const int Tm = dense_num_blocks(max_n), Tc = dense_num_blocks(n), grow = 64 * Tc;
@@ -87,7 +88,7 @@ static int run(int n, int world, bool virt, int reps) {
     CKE(cudaStreamCreate(&st[q]));
     dense_workspace_init(ws[q], max_n, st[q]);
     std::vector<unsigned> ops;
-    dense_dist_build_ops(Tc, q, world, &ops, g_blk);
+    dense_dist_build_ops(Tc, q, world, &ops, g_blk, g_fwd);
     nops[q] = (int)ops.size();
     CKE(cudaMalloc(&dops[q], std::max<size_t>(4, ops.size() * 4)));
     CKE(cudaMemcpy(dops[q], ops.data(), ops.size() * 4, cudaMemcpyHostToDevice));
@@ -97,7 +98,7 @@ static int run(int n, int world, bool virt, int reps) {
   }
   std::vector<DistPeers> peers(world);
   for (int q = 0; q < world; q++) {
-    peers[q].rank = q, peers[q].world = world, peers[q].blk = g_blk;
+    peers[q].rank = q, peers[q].world = world, peers[q].blk = g_blk, peers[q].fwd = g_fwd;
     for (int r = 0; r < world; r++) dense_dist_set_peer(&peers[q], r, dS[r], dW[r], ws[r]);
   }
   long long launches = 0;
@@ -218,7 +219,8 @@ int main(int argc, char **argv) {
   const bool virt = argc > 2 ? atoi(argv[2]) != 0 : true;
   dense_setup_device(0);
   if (getenv("PPO_DIST_BLOCK")) g_blk = std::max(1, atoi(getenv("PPO_DIST_BLOCK")));
-  printf("ownership block: %d column(s)\n", g_blk);
+  if (getenv("PPO_DIST_FORWARD")) g_fwd = atoi(getenv("PPO_DIST_FORWARD")) != 0;
+  printf("ownership block: %d column(s), panel forwarding %s\n", g_blk, g_fwd ? "on" : "off");
   std::vector<int> ns;
   for (int i = 3; i < argc; i++) ns.push_back(atoi(argv[i]));
   if (ns.empty()) ns = {9, 64, 100, 384, 1000, 1644, 4000, 7794};
