@@ -472,7 +472,12 @@ def main():
     launches = eng.launch_count() - l0
     host_syncs = eng.host_sync_count() - s0
     sampler.stop_flag = True
-    # end-to-end through the C-ABI with host buffers
+    # end-to-end through the C-ABI with host buffers: the step's inputs lie in page-locked host memory (the numpy arrays of the window,
+    # registered once), and ppo_ba_set_graph copies page-locked arrays to the device from where they lie
+    pinned_inputs = 0
+    for v in g.a.values():
+        if v.nbytes >= 65536 and eng.lib.ppo_ba_host_register(v.ctypes.data, v.nbytes) == 0:
+            pinned_inputs += v.nbytes
     for _ in range(1):
         step_e2e()
     barrier()
@@ -553,7 +558,7 @@ def main():
                        "lm_control": "on the device: one CUDA graph with conditional WHILE nodes per optimize()"},
             "kf_windows_per_sec": (1 if shard else world) * args.steps / (ms * 1e-3),
             "e2e": {"value": e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": g.nbytes(), "d2h_bytes_per_step": state_bytes,
-                    "ms_per_step": 1e3 * e2e_s / n_e2e},
+                    "ms_per_step": 1e3 * e2e_s / n_e2e, "host_inputs": "page-locked (cudaHostRegister), %d of %d bytes; copied to the device from where they lie" % (pinned_inputs, g.nbytes())},
             "e2e_shim": e2e_shim,
             "gpu_launches": launches,
             "host_syncs_per_step": host_syncs / max(1, args.steps),

@@ -18,6 +18,7 @@
 #ifndef PPO_BA_H
 #define PPO_BA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -213,8 +214,14 @@ int ppo_ba_set_params(ppo_ba_handle *h, const ppo_ba_params *params);
 
 /* Replaces every optimizer.addVertex / addEdge of Optimizer.cc:2120-2714 (and :526-650).
  * Copies the graph to the device; all edges start at level 0 with their Huber kernel on
- * (point, plane, cuboid-cam, cuboid-plane) or off (point-cuboid), as the reference builds them. */
+ * (point, plane, cuboid-cam, cuboid-plane) or off (point-cuboid), as the reference builds them.
+ * The caller's arrays are only read during the call.  Pageable arrays go through the handle's pinned staging arena (one host copy);
+ * an array that is page-locked already (cudaMallocHost, cudaHostRegister, ppo_ba_host_register) is copied from where it lies. */
 int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *g);
+/* Page-locks / releases a host range (cudaHostRegister / cudaHostUnregister) for callers that do not link the CUDA runtime themselves:
+ * a host that keeps its flat arrays across calls registers them once and saves the staging copy of every ppo_ba_set_graph. */
+int ppo_ba_host_register(void *ptr, size_t bytes);
+int ppo_ba_host_unregister(void *ptr);
 
 /* One SparseOptimizer::initializeOptimization(0) + optimize(iters)
  * (core/sparse_optimizer.cpp:199-267,354-420): rebuilds the index mapping from the current

@@ -183,17 +183,31 @@ struct ppo_ba_handle {
     }
     return PPO_OK;
   }
-  // caller's array -> pinned staging -> device: one host pass, no intermediate std::vector
+  // Is the caller's array page-locked already (cudaMallocHost / cudaHostRegister)?  Then it is copied from where it lies: the caller's
+  // arrays only have to stay valid until ppo_ba_set_graph returns, and set_graph drains the stream before it does.
+  static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+  }
+  // caller's array -> (pinned staging unless it is pinned itself) -> device: one host pass at most, no intermediate std::vector
   template <typename T>
   int upload_raw(T **p, const T *src, size_t n) {
     ppo_ba_handle *h = this;
     int rc = dalloc(p, n);
     if (rc) return rc;
     if (n) {
-      void *stage = nullptr;
-      if ((rc = pinned(&stage, n * sizeof(T)))) return rc;
-      std::memcpy(stage, src, n * sizeof(T));
-      CK(cudaMemcpyAsync(*p, stage, n * sizeof(T), cudaMemcpyHostToDevice, st));
+      const void *from = src;
+      if (n * sizeof(T) < 65536 || !is_pinned(src)) {
+        void *stage = nullptr;
+        if ((rc = pinned(&stage, n * sizeof(T)))) return rc;
+        std::memcpy(stage, src, n * sizeof(T));
+        from = stage;
+      }
+      CK(cudaMemcpyAsync(*p, from, n * sizeof(T), cudaMemcpyHostToDevice, st));
     }
     return PPO_OK;
   }
@@ -503,7 +517,7 @@ static int dist_setup(ppo_ba_handle *h) {
   return PPO_OK;
 }
 
-int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
+static int set_graph_impl(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   if (!h || !gi) return PPO_E_INVALID;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->st));
@@ -572,11 +586,15 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   if ((rc = alloc_state(h, &h->sa)) || (rc = alloc_state(h, &h->sb)) || (rc = alloc_state(h, &h->s0))) return rc;
   auto stage_up = [&](double *dst, const double *src, size_t n) -> int {
     if (n == 0) return PPO_OK;
-    void *stage = nullptr;
-    int r = h->pinned(&stage, n * 8);
-    if (r) return r;
-    std::memcpy(stage, src, n * 8);
-    CK(cudaMemcpyAsync(dst, stage, n * 8, cudaMemcpyHostToDevice, h->st));
+    const void *from = src;
+    if (n * 8 < 65536 || !ppo_ba_handle::is_pinned(src)) {  // (the local vectors above are small and pageable; pt_xyz may be the caller's pinned array)
+      void *stage = nullptr;
+      int r = h->pinned(&stage, n * 8);
+      if (r) return r;
+      std::memcpy(stage, src, n * 8);
+      from = stage;
+    }
+    CK(cudaMemcpyAsync(dst, from, n * 8, cudaMemcpyHostToDevice, h->st));
     return PPO_OK;
   };
   if ((rc = stage_up(h->s0.kf_pose, kf_pose.data(), kf_pose.size())) || (rc = stage_up(h->s0.pt, gi->pt_xyz, 3 * (size_t)g.n_pt)) ||
@@ -891,6 +909,31 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
   return PPO_OK;
 #undef UP
 #undef DA
+}
+
+int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
+  const int rc = set_graph_impl(h, gi);
+  // arrays of the caller that are page-locked are read by the copy engine where they lie: no copy may be in flight when the call returns,
+  // whatever the outcome (the successful path has drained the stream already)
+  if (rc != PPO_OK && h && h->st) cudaStreamSynchronize(h->st);
+  return rc;
+}
+
+int ppo_ba_host_register(void *ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return PPO_E_INVALID;
+  if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return PPO_E_CUDA;
+  }
+  return PPO_OK;
+}
+int ppo_ba_host_unregister(void *ptr) {
+  if (!ptr) return PPO_E_INVALID;
+  if (cudaHostUnregister(ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return PPO_E_CUDA;
+  }
+  return PPO_OK;
 }
 
 int ppo_ba_reset(ppo_ba_handle *h) {

@@ -68,6 +68,8 @@ int ppo_oracle_set_params(ppo_oracle_handle *, const ppo_ba_params *);
 #define ppo_ba_set_edge_flags ppo_oracle_set_edge_flags
 #define ppo_ba_local_ba ppo_oracle_local_ba
 #define ppo_ba_get_state ppo_oracle_get_state
+#define ppo_ba_host_register(p, n) (-1)  /* (no device in the test build: nothing to page-lock) */
+#define ppo_ba_host_unregister(p) (0)
 #define ppo_ba_last_error(h) "oracle backend"
 #endif
 
@@ -114,6 +116,27 @@ struct Flat {
   std::vector<float> kf_intr, pe_obs, pe_invsigma2;
   std::vector<int32_t> pt_rowptr, pe_kf, ple_plane, ple_kf, cbe_kf, cbe_cuboid, pce_cuboid, pce_rowptr, cpe_cuboid, cpe_plane;
   ppo_ba_graph g;
+  // The arrays as long as the window's points / point edges are kept page-locked (ppo_ba_host_register), so that ppo_ba_set_graph copies
+  // them to the device from where they lie instead of staging them.  A vector is released BEFORE it may reallocate and registered again
+  // at its new place; in the steady state (capacity reached) neither happens.
+  struct Pin {
+    void *p = nullptr;
+    size_t bytes = 0;
+  };
+  Pin pins[5];
+  template <class V>
+  void resize_pinned(V &v, size_t n, Pin &pin) {
+    if (n > v.capacity()) {
+      if (pin.p) ppo_ba_host_unregister(pin.p), pin = Pin();
+      v.reserve(n + n / 4);
+    }
+    v.resize(n);
+    const size_t bytes = v.capacity() * sizeof(typename V::value_type);
+    if ((void *)v.data() != pin.p || bytes != pin.bytes) {
+      if (pin.p) ppo_ba_host_unregister(pin.p), pin = Pin();
+      if (bytes >= 65536 && ppo_ba_host_register((void *)v.data(), bytes) == PPO_OK) pin.p = (void *)v.data(), pin.bytes = bytes;
+    }
+  }
   // empties the arrays but keeps their memory: a steady-state call then touches no fresh pages (30 MB for a 200-key-frame window)
   // keep_point_arrays: the point / point-edge arrays are then RESIZED and overwritten by the caller (run()), so they keep their size too --
   // a resize to nearly the same length value-initialises nothing, where clear() + resize() would zero 10 MB per call
@@ -744,8 +767,8 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
   const size_t npt = pt_first[NP], ne = e_first[NP];
   graph_points.resize(npt);
   point_edge_owner.resize(ne);
-  F.pt_xyz.resize(3 * npt); F.pt_fixed.assign(npt, mixed && fixPoint); F.pt_rowptr.resize(npt + 1);
-  F.pe_kf.resize(ne); F.pe_obs.resize(3 * ne); F.pe_invsigma2.resize(ne);
+  F.resize_pinned(F.pt_xyz, 3 * npt, F.pins[0]); F.pt_fixed.assign(npt, mixed && fixPoint); F.resize_pinned(F.pt_rowptr, npt + 1, F.pins[1]);
+  F.resize_pinned(F.pe_kf, ne, F.pins[2]); F.resize_pinned(F.pe_obs, 3 * ne, F.pins[3]); F.resize_pinned(F.pe_invsigma2, ne, F.pins[4]);
   F.pt_rowptr[0] = 0;
   tick("  B: point arrays sized");
   g_pool.for_ranges((long)NP, [&](long ip0, long ip1) {

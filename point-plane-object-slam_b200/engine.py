@@ -73,6 +73,8 @@ def load_library():
         lib.ppo_ba_collective_count.restype = C.c_longlong
         lib.ppo_ba_debug_linearize.argtypes = [C.c_void_p, C.POINTER(C.c_int32 * 2), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ppo_ba_debug_solve.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        lib.ppo_ba_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        lib.ppo_ba_host_unregister.argtypes = [C.c_void_p]
         lib.ppo_ba_point_edge_outliers.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
         lib.ppo_ba_debug_dense_solve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         _LIB = lib
