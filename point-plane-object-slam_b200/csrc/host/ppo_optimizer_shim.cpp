@@ -436,40 +436,46 @@ static void collect(KeyFrame *pKF, bool mixed, Window &w, bool with_planes = tru
       size_t id;
     };
     // (1) per RANGE of key-frames: candidates in key-frame order, already without the repeats inside the range
-    static std::vector<std::vector<Cand>> cand;        // (guarded by the mutex of the local-BA slot; keep their memory across calls)
-    static std::vector<std::vector<uint8_t>> seen_of;  // per range: byte map by MapPoint::mnId
+    // "seen" maps are indexed by MapPoint::mnId, which only grows over a session: they hold the number of the CALL that last saw the id
+    // instead of a flag, so that nothing has to be cleared per call
+    static std::vector<std::vector<Cand>> cand;         // (guarded by the mutex of the local-BA slot; keep their memory across calls)
+    static std::vector<std::vector<uint32_t>> seen_of;  // per range
+    static std::vector<uint32_t> seen;
+    static uint32_t call = 0;
+    if (++call == 0) {  // (wrapped: forget everything once)
+      for (auto &v : seen_of) std::fill(v.begin(), v.end(), 0u);
+      std::fill(seen.begin(), seen.end(), 0u);
+      call = 1;
+    }
     const size_t nkf = w.lLocalKeyFrames.size();
     const int parts = g_pool.parts_for((long)nkf, 8);
     if ((int)cand.size() < parts) cand.resize(parts), seen_of.resize(parts);
     g_pool.for_parts((long)nkf, [&](int part, long i0, long i1) {
       std::vector<Cand> &c = cand[part];
-      std::vector<uint8_t> &seen = seen_of[part];
+      std::vector<uint32_t> &mine = seen_of[part];
       c.clear();
-      std::fill(seen.begin(), seen.end(), 0);
       for (long i = i0; i < i1; i++) {
         const std::vector<MapPoint *> vpMPs = w.lLocalKeyFrames[i]->GetMapPointMatches();
         for (MapPoint *pMP : vpMPs)
           if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) {
             const size_t id = pMP->mnId;
-            if (id >= seen.size()) seen.resize(id + 1 + seen.size() / 2, 0);
-            if (seen[id]) continue;
-            seen[id] = 1;
+            if (id >= mine.size()) mine.resize(id + 1 + mine.size() / 2, 0u);
+            if (mine[id] == call) continue;
+            mine[id] = call;
             c.push_back({pMP, id});
           }
       }
     }, 8);
     tick("live matches per key-frame");
     // (2) merge in range order
-    static std::vector<uint8_t> seen;
-    size_t max_id = 0;
-    for (int q = 0; q < parts; q++) max_id = std::max(max_id, seen_of[q].size());
-    seen.assign(max_id + 1, 0);
     for (int q = 0; q < parts; q++)
-      for (const Cand &c : cand[q])
-        if (!seen[c.id]) {
-          seen[c.id] = 1;
+      for (const Cand &c : cand[q]) {
+        if (c.id >= seen.size()) seen.resize(c.id + 1 + seen.size() / 2, 0u);
+        if (seen[c.id] != call) {
+          seen[c.id] = call;
           w.lLocalMapPoints.push_back(c.p);
         }
+      }
     tick("first-seen order");
   }
   if (mixed) {
