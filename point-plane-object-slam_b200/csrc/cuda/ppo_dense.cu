@@ -44,6 +44,8 @@
 //     cycles per sub-block, 0.416 -> 0.414 ms).  Every lane forming the NEXT pivot block itself, so that only one FMA, the determinant
 //     and the reciprocal are on the chain (dropped: 3400 cycles per sub-block, 0.457 ms -- the warp issues in order at 2 cycles per
 //     FP64 instruction, and the extra off-chain arithmetic delays the chain more than the shorter dependency path gains).
+//     (4) the three look-ahead blocks of warp 0 in U as three interleaved DMMA chains instead of one after the other: no change
+//     (0.416 ms), U is not bound by that warp's tensor work.
 //
 // The second half of the file spreads the same factorisation over the GPUs of a node (k_chol_dist and friends).
 #include <cuda_runtime.h>
