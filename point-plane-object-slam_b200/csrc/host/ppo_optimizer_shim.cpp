@@ -715,6 +715,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     P.norm_se3 = thHuberSE3;   // :1878
     if (optimize_with_plane_3d && !cuboids2d)
       for (MapPlane *pMP : w.lLocalMapPlanes) {
+        const int ipl = pl_index[pMP];  // (once per plane, not per observation)
         auto add = [&](const std::map<KeyFrame *, int> &obs, int kind) {
           for (auto &mit : obs) {
             KeyFrame *pKFi = mit.first;
@@ -725,7 +726,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
             const float c4[4] = {m.at<float>(0, 0), m.at<float>(1, 0), m.at<float>(2, 0), m.at<float>(3, 0)};
             double c[4];
             ppo::plane_float_to_coef(c4, c);
-            F.ple_plane.push_back(pl_index[pMP]);
+            F.ple_plane.push_back(ipl);
             F.ple_kf.push_back(sl_kf);
             F.ple_kind.push_back((uint8_t)kind);
             F.ple_meas.insert(F.ple_meas.end(), c, c + 4);
