@@ -2,13 +2,13 @@
   B=oracle/_build; H=point-plane-object-slam_b200/csrc/host
   g++ -O1 -g -std=c++17 -pthread -fsanitize=thread -shared -fPIC -DPPO_SHIM_ON_ORACLE -I include -o /tmp/libppo_shim_tsan.so \
       $H/ppo_optimizer_shim.cpp $H/ppo_mock_world.cpp -L $B -lppo_oracle -Wl,-rpath,$PWD/$B
-  TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0" LD_PRELOAD=$(gcc -print-file-name=libtsan.so) python tools/tsan_shim.py
+  TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0" LD_PRELOAD=$(gcc -print-file-name=libtsan.so) python tests/tsan_shim.py
 Expected: no "WARNING: ThreadSanitizer" line (round 2: none over threaded flattening with 4 and 8 threads, a full call with
 write-back, and two warm calls on a persistent map)."""
 import os, sys, ctypes as C
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)  # (test infrastructure: links the oracle-backed test build of the shim)
 import shim_lib
 from ppo_pkg import ppo
 A = ppo.abi
