@@ -921,7 +921,7 @@ int ppo_ba_set_graph(ppo_ba_handle *h, const ppo_ba_graph *gi) {
 
 int ppo_ba_host_register(void *ptr, size_t bytes) {
   if (!ptr || bytes == 0) return PPO_E_INVALID;
-  if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+  if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {  // (page-locked for every device of the process)
     cudaGetLastError();
     return PPO_E_CUDA;
   }
