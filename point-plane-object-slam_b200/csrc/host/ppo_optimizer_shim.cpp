@@ -694,6 +694,7 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     ppo::plane_float_to_coef(c4, c);  // Converter::toPlane3D
     F.pl_coef.insert(F.pl_coef.end(), c, c + 4);
   }
+  tick("  B: vertices");
   // ---- plane edges :2222-2309 ---------------------------------------------------------------------------
   ppo_ba_params P;
   ppo_ba_default_params(&P);
@@ -713,37 +714,63 @@ static void run(KeyFrame *pKF, bool *pbStopFlag, Map *pMap, bool mixed, bool fix
     P.huber_cuboid_plane = ppo::huber_delta(cuboid_plane_chi);
     P.huber_se3 = thHuberSE3;  // rk->setDelta(thHuberSE3): the threshold itself (:1794)
     P.norm_se3 = thHuberSE3;   // :1878
-    if (optimize_with_plane_3d && !cuboids2d)
-      for (MapPlane *pMP : w.lLocalMapPlanes) {
-        const int ipl = pl_index[pMP];  // (once per plane, not per observation)
-        auto add = [&](const std::map<KeyFrame *, int> &obs, int kind) {
-          for (auto &mit : obs) {
-            KeyFrame *pKFi = mit.first;
-            if (pKFi->isBad()) continue;
-            const int sl_kf = slot_of(pKFi);
-            if (sl_kf < 0) continue;  // optimizer.vertex(pKFi->mnId) == NULL -> continue (:2235-2236, q8)
-            cv::Mat m = pKFi->mvPlaneCoefficients[mit.second];
-            const float c4[4] = {m.at<float>(0, 0), m.at<float>(1, 0), m.at<float>(2, 0), m.at<float>(3, 0)};
-            double c[4];
-            ppo::plane_float_to_coef(c4, c);
-            F.ple_plane.push_back(ipl);
-            F.ple_kf.push_back(sl_kf);
-            F.ple_kind.push_back((uint8_t)kind);
-            F.ple_meas.insert(F.ple_meas.end(), c, c + 4);
-            const double info[3] = {kind == PPO_PLANE_OBS ? angleInfo : pvInfo, kind == PPO_PLANE_OBS ? angleInfo : pvInfo, kind == PPO_PLANE_OBS ? disInfo : 0.0};
-            F.ple_info.insert(F.ple_info.end(), info, info + 3);
-            plane_edge_owner.push_back({pKFi, pMP});
-            plane_edge_is_obs.push_back(kind == PPO_PLANE_OBS);
-          }
-        };
-        add(pMP->GetObservations(), PPO_PLANE_OBS);
-        add(pMP->GetVerObservations(), PPO_PLANE_VER);
-        add(pMP->GetParObservations(), PPO_PLANE_PAR);
+    if (optimize_with_plane_3d && !cuboids2d) {
+      // Per plane the reference copies three observation maps (GetObservations / GetVerObservations / GetParObservations return by
+      // value, under the plane's mutex): ranges of planes are flattened by the host threads into their own arrays, which are then
+      // appended in plane order -- the edge order of the serial loop.
+      struct Part {
+        std::vector<int32_t> plane, kf;
+        std::vector<uint8_t> kind;
+        std::vector<double> meas, info;
+        std::vector<std::pair<KeyFrame *, MapPlane *>> owner;
+        std::vector<int> is_obs;
+      };
+      const long npl = (long)w.lLocalMapPlanes.size();
+      std::vector<Part> parts((size_t)g_pool.parts_for(npl, 16));
+      g_pool.for_parts(npl, [&](int part, long i0, long i1) {
+        Part &o = parts[(size_t)part];
+        for (long ip = i0; ip < i1; ip++) {
+          MapPlane *pMP = w.lLocalMapPlanes[ip];
+          const int ipl = (int)ip;  // (= pl_index[pMP]: the planes were numbered in this order)
+          auto add = [&](const std::map<KeyFrame *, int> &obs, int kind) {
+            for (auto &mit : obs) {
+              KeyFrame *pKFi = mit.first;
+              if (pKFi->isBad()) continue;
+              const int sl_kf = slot_of(pKFi);
+              if (sl_kf < 0) continue;  // optimizer.vertex(pKFi->mnId) == NULL -> continue (:2235-2236, q8)
+              cv::Mat m = pKFi->mvPlaneCoefficients[mit.second];
+              const float c4[4] = {m.at<float>(0, 0), m.at<float>(1, 0), m.at<float>(2, 0), m.at<float>(3, 0)};
+              double c[4];
+              ppo::plane_float_to_coef(c4, c);
+              o.plane.push_back(ipl);
+              o.kf.push_back(sl_kf);
+              o.kind.push_back((uint8_t)kind);
+              o.meas.insert(o.meas.end(), c, c + 4);
+              const double info[3] = {kind == PPO_PLANE_OBS ? angleInfo : pvInfo, kind == PPO_PLANE_OBS ? angleInfo : pvInfo, kind == PPO_PLANE_OBS ? disInfo : 0.0};
+              o.info.insert(o.info.end(), info, info + 3);
+              o.owner.push_back({pKFi, pMP});
+              o.is_obs.push_back(kind == PPO_PLANE_OBS);
+            }
+          };
+          add(pMP->GetObservations(), PPO_PLANE_OBS);
+          add(pMP->GetVerObservations(), PPO_PLANE_VER);
+          add(pMP->GetParObservations(), PPO_PLANE_PAR);
+        }
+      }, 16);
+      for (const Part &o : parts) {
+        F.ple_plane.insert(F.ple_plane.end(), o.plane.begin(), o.plane.end());
+        F.ple_kf.insert(F.ple_kf.end(), o.kf.begin(), o.kf.end());
+        F.ple_kind.insert(F.ple_kind.end(), o.kind.begin(), o.kind.end());
+        F.ple_meas.insert(F.ple_meas.end(), o.meas.begin(), o.meas.end());
+        F.ple_info.insert(F.ple_info.end(), o.info.begin(), o.info.end());
+        plane_edge_owner.insert(plane_edge_owner.end(), o.owner.begin(), o.owner.end());
+        plane_edge_is_obs.insert(plane_edge_is_obs.end(), o.is_obs.begin(), o.is_obs.end());
       }
+    }
   } else {
     P.solver = PPO_SOLVER_6_3;
   }
-  tick("  B: vertices + plane edges");
+  tick("  B: plane edges");
   // ---- points and reprojection edges :2332-2424 (mixed) / :560-650 (points only) ----------------------------
   std::vector<MapPoint *> &graph_points = S.graph_points;  // points that got a vertex (mixed: Observations() != 1, q1)
   std::vector<std::pair<KeyFrame *, MapPoint *>> &point_edge_owner = S.point_edge_owner;

@@ -57,7 +57,7 @@ def test_threaded_flattening_equals_the_serial_loops_cpu(ppo, oracle_mod, mixed)
     flattened graph must be bit-identical to the one the serial loops produce (stop flag set: collection + flattening only)."""
     import shim_lib
     L = shim_lib.oracle_backed_lib()
-    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=24, n_fixed=5, n_pt=12000, n_pl=6, n_cu=3))
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=24, n_fixed=5, n_pt=12000, n_pl=70, n_cu=3))
     flats = []
     try:
         for n in (1, 5, 8, 3, 8):
@@ -75,6 +75,37 @@ def test_threaded_flattening_equals_the_serial_loops_cpu(ppo, oracle_mod, mixed)
         assert (f.c.n_kf, f.c.n_pt, f.c.n_pe, f.c.n_ple, f.c.n_cbe, f.c.n_pce, f.c.n_cpe) == (
             ref.c.n_kf, ref.c.n_pt, ref.c.n_pe, ref.c.n_ple, ref.c.n_cbe, ref.c.n_pce, ref.c.n_cpe)
         for k in ("pt_xyz", "pt_fixed", "pt_rowptr", "pe_kf", "pe_obs", "pe_invsigma2", "kf_pose", "kf_fixed"):
+            assert np.array_equal(f[k], ref[k]), k
+        if mixed:
+            # plane edges are flattened by ranges of planes and appended in plane order; inside a plane the order is that of a std::map keyed
+            # by KeyFrame pointers (as in the reference), i.e. of the heap addresses of this run's mock map: compare plane by plane as sets
+            def rows(x):
+                m = np.column_stack([x["ple_plane"], x["ple_kf"], x["ple_kind"], x["ple_meas"].reshape(-1, 4), x["ple_info"].reshape(-1, 3)])
+                return m[np.lexsort(m.T[::-1])]
+            assert np.array_equal(f["ple_plane"], ref["ple_plane"])  # (plane order itself is fixed)
+            assert np.array_equal(rows(f), rows(ref))
+
+
+def test_threaded_flattening_on_one_map_is_bit_identical_cpu(ppo, oracle_mod):
+    """Same mock map (same heap addresses, hence the same std::map orders), flattened with 1, 3 and 8 host threads: every array of the
+    flat graph, plane / cuboid edges included, must come out identical."""
+    import shim_lib
+    L = shim_lib.oracle_backed_lib()
+    g = ppo.synth.make_graph(ppo.synth.config(1, n_kf=24, n_fixed=5, n_pt=12000, n_pl=70, n_cu=3))
+    W = shim_lib.World(g, backend=L)
+    flats = []
+    try:
+        for n in (1, 3, 8, 1):
+            L.ppo_shim_set_threads(n)
+            flats.append(W.run(stop=True)[2])
+    finally:
+        L.ppo_shim_set_threads(1)
+        W.close()
+    ref = flats[0]
+    assert ref.c.n_ple >= 300 and ref.c.n_pt > 4096
+    for f in flats[1:]:
+        assert set(f.a) == set(ref.a)
+        for k in ref.a:
             assert np.array_equal(f[k], ref[k]), k
 
 
