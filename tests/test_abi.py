@@ -86,3 +86,14 @@ def test_product_libraries_never_reference_the_oracle(built):
         needed = subprocess.check_output(["readelf", "-d", path], text=True)
         assert "libppo_oracle" not in needed, path
     assert not any("oracle" in f for f in os.listdir(os.path.dirname(built["cuda"])))
+
+
+def test_public_headers_compile_as_c_and_cxx():
+    """The drop-in boundary is a C-ABI: include/*.h must be valid C99 (plain pointers and sizes, no C++ types) and valid C++."""
+    import glob
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for h in sorted(glob.glob(os.path.join(root, "include", "*.h"))):
+        for cmd in (["gcc", "-std=c99", "-Wall", "-fsyntax-only", "-x", "c", h], ["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++", h]):
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            assert r.returncode == 0, (cmd, r.stderr)
