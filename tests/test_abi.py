@@ -97,3 +97,14 @@ def test_public_headers_compile_as_c_and_cxx():
         for cmd in (["gcc", "-std=c99", "-Wall", "-fsyntax-only", "-x", "c", h], ["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++", h]):
             r = subprocess.run(cmd, capture_output=True, text=True)
             assert r.returncode == 0, (cmd, r.stderr)
+
+
+def test_engine_links_no_vendor_solver_library(built):
+    """Every kernel on the path is the repo's own: the engine library links the CUDA runtime only -- no cuBLAS / cuSOLVER / cuSPARSE /
+    cuDNN (NCCL is looked up at run time for sharded windows only)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "point-plane-object-slam_b200", "lib", "libppo_ba.so")
+    out = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout.lower()
+    for name in ("cublas", "cusolver", "cusparse", "cudnn", "cutlass", "nccl"):
+        assert name not in out, name
+    assert "libcudart" in out
